@@ -1,0 +1,83 @@
+// gemm.cu -- dense hidden / output GEMMs of the fully-connected path (hot-path row a11).
+//
+// Replaces the cublasSgemm calls of NNLayer::ForwardPropagateFullyConnected /
+// BackPropagateFullyConnected (E/NNLayer.cpp:1073, 2223, 2274), row-major operands:
+//   fwd: C[B][n]  = beta*C  + A[B][k] * W[k][n]
+//   dw : G[k][n]  = beta*G  + alpha * A[B][k]^T * D[B][n]
+//   dx : Dp[B][k] = beta*Dp + D[B][n] * W[k][n]^T
+// Modes (option "gemm_mode"):
+//   DSB200_GEMM_FP32    cuBLAS SGEMM, pedantic fp32 (what the reference runs; parity baseline)
+//   DSB200_GEMM_TF32    cuBLAS TF32 tensor-op math (stepping stone, tolerance 2e-3 relative)
+//   DSB200_GEMM_TF32X3  hand-written tcgen05 3xTF32 split kernel (gemm_tcgen05.cu) when the shape
+//                       qualifies, else falls back to FP32
+// The library call is the PLAIN GEMM case the task allows cuBLAS for; the fused
+// GEMM+sigmoid+loss+delta output kernel lives in gemm_tcgen05.cu.
+#include "common.cuh"
+#include "launch.h"
+
+#include <cublas_v2.h>
+
+namespace dsb {
+
+static int cublas_of(dsb200_ctx* ctx, cublasHandle_t* out)
+{
+    if (!ctx->cublas) {
+        cublasHandle_t h;
+        if (cublasCreate(&h) != CUBLAS_STATUS_SUCCESS) return fail(ctx, DSB200_ESTATE, "cublasCreate failed");
+        ctx->cublas = h;
+    }
+    cublasHandle_t h = (cublasHandle_t)ctx->cublas;
+    if (cublasSetStream(h, ctx->stream) != CUBLAS_STATUS_SUCCESS) return fail(ctx, DSB200_ESTATE, "cublasSetStream failed");
+    cublasSetMathMode(h, ctx->gemmMode == DSB200_GEMM_TF32 ? CUBLAS_TF32_TENSOR_OP_MATH : CUBLAS_PEDANTIC_MATH);
+    *out = h;
+    return 0;
+}
+
+void gemm_release(dsb200_ctx* ctx)
+{
+    if (ctx && ctx->cublas) { cublasDestroy((cublasHandle_t)ctx->cublas); ctx->cublas = nullptr; }
+}
+
+}  // namespace dsb
+
+extern "C" {
+
+int dsb200_gemm_fwd(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, const float* A, const float* W, float beta, float* C)
+{
+    using namespace dsb;
+    if (!ctx || !A || !W || !C) return fail(ctx, DSB200_EINVAL, "gemm_fwd: null argument");
+    if (!B || !k || !n) return 0;
+    cublasHandle_t h; int rc = cublas_of(ctx, &h); if (rc) return rc;
+    const float one = 1.0f;
+    // row-major C = A*W  <=>  column-major C^T = W^T * A^T (E/NNLayer.cpp:1072-1086)
+    if (cublasSgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, (int)n, (int)B, (int)k, &one, W, (int)n, A, (int)k, &beta, C, (int)n) != CUBLAS_STATUS_SUCCESS)
+        return fail(ctx, DSB200_ESTATE, "gemm_fwd: SGEMM failure");
+    return 0;
+}
+
+int dsb200_gemm_dw(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, float alpha, const float* A, const float* D, float beta, float* G)
+{
+    using namespace dsb;
+    if (!ctx || !A || !D || !G) return fail(ctx, DSB200_EINVAL, "gemm_dw: null argument");
+    if (!B || !k || !n) return 0;
+    cublasHandle_t h; int rc = cublas_of(ctx, &h); if (rc) return rc;
+    // G^T (n x k) = D^T (n x B) * A (B x k)   (E/NNLayer.cpp:2223-2236)
+    if (cublasSgemm(h, CUBLAS_OP_N, CUBLAS_OP_T, (int)n, (int)k, (int)B, &alpha, D, (int)n, A, (int)k, &beta, G, (int)n) != CUBLAS_STATUS_SUCCESS)
+        return fail(ctx, DSB200_ESTATE, "gemm_dw: SGEMM failure");
+    return 0;
+}
+
+int dsb200_gemm_dx(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, const float* D, const float* W, float beta, float* Dp)
+{
+    using namespace dsb;
+    if (!ctx || !D || !W || !Dp) return fail(ctx, DSB200_EINVAL, "gemm_dx: null argument");
+    if (!B || !k || !n) return 0;
+    cublasHandle_t h; int rc = cublas_of(ctx, &h); if (rc) return rc;
+    const float one = 1.0f;
+    // Dp^T (k x B) = W (k x n) * D^T (n x B)   (E/NNLayer.cpp:2274-2287)
+    if (cublasSgemm(h, CUBLAS_OP_T, CUBLAS_OP_N, (int)k, (int)B, (int)n, &one, W, (int)n, D, (int)n, &beta, Dp, (int)k) != CUBLAS_STATUS_SUCCESS)
+        return fail(ctx, DSB200_ESTATE, "gemm_dx: SGEMM failure");
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,15 @@
+// launch.h -- host-side helpers shared by the launchers.
+#pragma once
+#include <stdint.h>
+
+#define DSB200_STATUS_Z_WORKSPACE 1u   // sparse-Z split-row workspace too small (dsb200_ctx_reserve)
+#define DSB200_STATUS_T_OVERFLOW  2u   // transposed column overran its capacity slot
+
+namespace dsb {
+void count_launch(uint64_t n = 1);
+}
+
+struct dsb200_ctx;
+namespace dsb {
+void gemm_release(dsb200_ctx* ctx);
+}

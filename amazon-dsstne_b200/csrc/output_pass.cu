@@ -1,0 +1,302 @@
+// output_pass.cu -- sparse-target output layer: activation + loss + delta (rows a7, a8, fused a9).
+//
+// Replaces kCalculateSparse{L2,CrossEntropy,ScaledMarginalCrossEntropy,Multinomial*}Error
+// (E/kLoss.cu:595-691, 1749-1980, 2213-2352, 2566-2599) and
+// kCalculateSparse{,CrossEntropy,ScaledMarginalCrossEntropy}OutputDelta
+// (E/kDelta.cu:2193-2618, 6533-6608, 7182-7305), and fuses kCalculateSigmoidActivation
+// (E/kActivation.cu:46-64) in front of them.
+//
+// The reference makes six full passes over the [batch][N] output per training step (activation
+// R+W, loss "Raw" R, loss "NonZero", delta "Raw" R+W, delta "NonZero").  Here ONE kernel reads Z
+// once and writes delta once: a CTA owns a tile = (batch row, 2,048-column segment); it streams
+// the tile with 128-bit loads, computes a = f(z), the target-is-zero loss and delta, then -- after
+// a block barrier -- walks the row's target list and overwrites delta / corrects the loss at the
+// non-zero targets that fall inside the tile.  The loss leaves the kernel as the reference's
+// 2^30 fixed-point integer (one atomic per CTA), so its value does not depend on scheduling.
+// The same kernel, with template switches, serves the stand-alone loss and delta entry points.
+#include "common.cuh"
+#include "launch.h"
+
+namespace dsb {
+
+constexpr int kOThreads = 256;
+constexpr uint32_t kOSeg = 2048;
+
+struct OArgs {
+    dsb200_params P;
+    dsb200_sparse S;
+    int ef, act, ignoreZero;
+    uint32_t position, batch, stride;
+    const float* in;        // Z (DO_ACT) or activations
+    float* unitOut;         // optional
+    float* delta;           // optional
+    unsigned long long* acc;// optional
+    float slope, alpha, lambda;
+};
+
+__device__ __forceinline__ float act_forward(int act, float z, float slope, float alpha, float lambda)
+{
+    switch (act) {
+    case DSB200_ACT_SIGMOID: return 1.0f / (1.0f + expf(-z));                    // E/kActivation.cu:53
+    case DSB200_ACT_TANH:    return tanhf(z);
+    case DSB200_ACT_RELU:    return fmaxf(0.0f, z);
+    case DSB200_ACT_LRELU:   return fmaxf(z, z * slope);
+    case DSB200_ACT_ELU:     return (z > 0.0f) ? z : alpha * (expf(z) - 1.0f);
+    case DSB200_ACT_SELU:    return (z > 0.0f) ? lambda * z : lambda * alpha * (expf(z) - 1.0f);
+    default:                 return z;
+    }
+}
+
+// f'(x) through the activation value, as the L2 sparse delta kernels use it (E/kDelta.cu:2193-2482)
+__device__ __forceinline__ float l2_deriv(int act, float a, float slope, float alpha, float lambda)
+{
+    switch (act) {
+    case DSB200_ACT_SIGMOID: return a * (1.0f - a);
+    case DSB200_ACT_TANH:    return 1.0f - a * a;
+    case DSB200_ACT_RELU:    return (a > 0.0f) ? 1.0f : 0.0f;
+    case DSB200_ACT_LRELU:   return (a > 0.0f) ? 1.0f : slope;
+    case DSB200_ACT_ELU:     return (a > 0.0f) ? 1.0f : (a + alpha);
+    case DSB200_ACT_SELU:    return (a > 0.0f) ? lambda : lambda * alpha * expf(a);
+    default:                 return 1.0f;
+    }
+}
+
+// target == 0 everywhere ("Raw" kernels)
+template <int EF, int ACT>
+__device__ __forceinline__ void raw_elem(const OArgs& a, int ef, int act, float x, float wd, float& loss, float& d)
+{
+    const int e = (EF >= 0) ? EF : ef, c = (ACT >= 0) ? ACT : act;
+    if (e == DSB200_ERR_SMCE) {
+        if (c == DSB200_ACT_SOFTMAX) {                                    // E/kDelta.cu:7229-7241 (unweighted)
+            d = (x > a.P.SMCE_zeroTarget) ? a.P.SMCE_zeroScale * x : 0.0f;
+        } else {                                                          // E/kLoss.cu:2215-2234, E/kDelta.cu:7184-7201
+            const float w = a.P.SMCE_zeroScale * wd;
+            if (x > a.P.SMCE_zeroTarget) { loss += -w * logf(fmaxf(kMinError, 1.0f - x)); d = w * x; }
+            else d = 0.0f;
+        }
+    } else if (e == DSB200_ERR_CROSS_ENTROPY) {
+        if (c == DSB200_ACT_SOFTMAX) d = wd * x;                          // E/kDelta.cu:2484-2500
+        else { loss += -wd * logf(fmaxf(kMinError, 1.0f - x)); d = a.P.deltaBoost_zero * wd * x; }   // E/kLoss.cu:1751-1768, E/kDelta.cu:6535-6550
+    } else {                                                              // L2
+        loss += 0.5f * wd * x * x;                                        // E/kLoss.cu:597-615
+        if (c == DSB200_ACT_SOFTMAX) d = wd * x;
+        else if (c == DSB200_ACT_SIGMOID) d = a.P.deltaBoost_zero * wd * x * x * (1.0f - x);          // E/kDelta.cu:2195-2211
+        else d = wd * x * l2_deriv(c, x, a.slope, a.alpha, a.lambda);
+    }
+}
+
+// corrections at the non-zero targets ("NonZero" / "OnlyNonZero" kernels)
+template <int EF, int ACT>
+__device__ __forceinline__ void nz_elem(const OArgs& a, int ef, int act, float x, float t, float wd, float wrow,
+                                        float& loss, float& d)
+{
+    const int e = (EF >= 0) ? EF : ef, c = (ACT >= 0) ? ACT : act;
+    const bool iz = a.ignoreZero != 0;
+    if (e == DSB200_ERR_SMCE) {
+        if (c == DSB200_ACT_SOFTMAX) {                                    // E/kLoss.cu:2566-2599, E/kDelta.cu:7243-7267
+            const float w = a.P.SMCE_oneScale * wrow;
+            if (x < a.P.SMCE_oneTarget) { loss += -w * logf(fmaxf(kMinError, x)); d = x - w; } else d = 0.0f;
+        } else {                                                          // E/kLoss.cu:2236-2327, E/kDelta.cu:7203-7226
+            if (!iz && x > a.P.SMCE_zeroTarget) loss += wd * a.P.SMCE_zeroScale * logf(fmaxf(kMinError, 1.0f - x));
+            if (x < a.P.SMCE_oneTarget) { loss += -wd * a.P.SMCE_oneScale * logf(fmaxf(kMinError, x)); d = a.P.SMCE_oneScale * wd * (x - 1.0f); }
+            else d = 0.0f;
+        }
+    } else if (e == DSB200_ERR_CROSS_ENTROPY) {
+        if (c == DSB200_ACT_SOFTMAX) { loss += -wrow * logf(fmaxf(kMinError, x)); d = x - wrow; }     // E/kLoss.cu:1945-1967, E/kDelta.cu:2502-2521
+        else {                                                            // E/kLoss.cu:1770-1839, E/kDelta.cu:6552-6571
+            loss += iz ? -wd * logf(fmaxf(kMinError, x))
+                       : wd * (-logf(fmaxf(kMinError, x)) + logf(fmaxf(kMinError, 1.0f - x)));
+            d = a.P.deltaBoost_one * wd * (x - 1.0f);
+        }
+    } else {                                                              // L2: E/kLoss.cu:617-666, E/kDelta.cu:2213-2231
+        const float w = 0.5f * wd;
+        loss += iz ? w * ((x - t) * (x - t)) : w * ((x - t) * (x - t) - x * x);
+        if (c == DSB200_ACT_SOFTMAX) d = x - wrow;
+        else if (c == DSB200_ACT_SIGMOID) d = a.P.deltaBoost_one * wd * (x - t) * x * (1.0f - x);
+        else d = wd * (x - t) * l2_deriv(c, x, a.slope, a.alpha, a.lambda);
+    }
+}
+
+template <int EF, int ACT, bool DO_ACT, bool WRITE_UNIT, bool WRITE_DELTA, bool DO_LOSS>
+__global__ void __launch_bounds__(kOThreads, 4)
+output_tile_kernel(const OArgs a)
+{
+    __shared__ double sW[kOThreads / 32];
+    const uint32_t tid = threadIdx.x;
+    const uint32_t segs = (a.stride + kOSeg - 1) / kOSeg;
+    const uint64_t tiles = (uint64_t)a.batch * segs;
+    const bool analog = a.S.sparseData != nullptr;
+    const bool raw = !a.ignoreZero;
+    float loss = 0.0f;
+
+    for (uint64_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        const uint32_t b = (uint32_t)(tile / segs), seg = (uint32_t)(tile % segs);
+        const uint32_t c0 = seg * kOSeg, c1 = min(c0 + kOSeg, a.stride);
+        const uint32_t ex = example_of(a.P, a.S.index, a.position, b);
+        const float wd = a.S.dataWeight ? __ldg(a.S.dataWeight + ex) : 1.0f;
+        const uint64_t g0 = (uint64_t)b * a.stride + c0, g1 = (uint64_t)b * a.stride + c1;
+        const uint64_t a0u = (g0 + 3) & ~(uint64_t)3, a0 = a0u < g1 ? a0u : g1;
+        const uint64_t a1d = g1 & ~(uint64_t)3, a1 = a1d > a0 ? a1d : a0;
+
+        auto one = [&](uint64_t i) {
+            float x = a.in[i];
+            if (DO_ACT) x = act_forward((ACT >= 0) ? ACT : a.act, x, a.slope, a.alpha, a.lambda);
+            if (WRITE_UNIT) a.unitOut[i] = x;
+            float d = 0.0f, l = 0.0f;
+            if (raw) raw_elem<EF, ACT>(a, a.ef, a.act, x, wd, l, d);
+            if (DO_LOSS) loss += l;
+            if (WRITE_DELTA) a.delta[i] = d;
+        };
+        if (DO_ACT || WRITE_DELTA || (DO_LOSS && raw)) {
+            for (uint64_t i = g0 + tid; i < a0; i += kOThreads) one(i);
+            for (uint64_t i4 = (a0 >> 2) + tid; i4 < (a1 >> 2); i4 += kOThreads) {
+                const float4 z4 = ldg_cs_f4(reinterpret_cast<const float4*>(a.in) + i4);
+                float x[4] = {z4.x, z4.y, z4.z, z4.w}, d[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (int v = 0; v < 4; v++) {
+                    if (DO_ACT) x[v] = act_forward((ACT >= 0) ? ACT : a.act, x[v], a.slope, a.alpha, a.lambda);
+                    float l = 0.0f;
+                    if (raw) raw_elem<EF, ACT>(a, a.ef, a.act, x[v], wd, l, d[v]);
+                    if (DO_LOSS) loss += l;
+                }
+                if (WRITE_UNIT)  reinterpret_cast<float4*>(a.unitOut)[i4] = make_float4(x[0], x[1], x[2], x[3]);
+                if (WRITE_DELTA) reinterpret_cast<float4*>(a.delta)[i4] = make_float4(d[0], d[1], d[2], d[3]);
+            }
+            for (uint64_t i = a1 + tid; i < g1; i += kOThreads) one(i);
+        }
+        if (WRITE_DELTA || WRITE_UNIT) __syncthreads();      // raw values of this tile are in place
+        // non-zero targets of row b that fall into [c0, c1)
+        const uint64_t rs = __ldg(a.S.sparseStart + ex), re = __ldg(a.S.sparseEnd + ex);
+        const float wrow = a.S.dataWeight ? wd : 1.0f / (float)(re - rs);
+        for (uint64_t j = rs + tid; j < re; j += kOThreads) {
+            const uint32_t c = __ldg(a.S.sparseIndex + j);
+            if (c < c0 || c >= c1) continue;
+            const uint64_t i = (uint64_t)b * a.stride + c;
+            float x;
+            if (WRITE_UNIT) x = a.unitOut[i];
+            else { x = a.in[i]; if (DO_ACT) x = act_forward((ACT >= 0) ? ACT : a.act, x, a.slope, a.alpha, a.lambda); }
+            const float t = analog ? load_value(a.S.sparseData, a.S.dataType, j) : 1.0f;
+            float d = 0.0f, l = 0.0f;
+            nz_elem<EF, ACT>(a, a.ef, a.act, x, t, wd, wrow, l, d);
+            if (DO_LOSS) loss += l;
+            if (WRITE_DELTA) a.delta[i] = d;
+        }
+        if (WRITE_DELTA || WRITE_UNIT) __syncthreads();      // next tile may alias nothing, but keep phases apart
+    }
+    if (DO_LOSS) {
+        double e = warp_sum((double)loss);
+        if ((tid & 31) == 0) sW[tid >> 5] = e;
+        __syncthreads();
+        if (tid == 0) {
+            double tot = 0.0;
+            for (int i = 0; i < kOThreads / 32; i++) tot += sW[i];
+            if (tot != 0.0) atomicAdd(a.acc, (unsigned long long)llrint(tot * (double)kErrorScaleF));
+        }
+    }
+}
+
+template <bool DO_ACT, bool WRITE_UNIT, bool WRITE_DELTA, bool DO_LOSS>
+static int launch_output(dsb200_ctx* ctx, const OArgs& a)
+{
+    const uint32_t segs = (a.stride + kOSeg - 1) / kOSeg;
+    uint64_t tiles = (uint64_t)a.batch * segs;
+    uint64_t grid = (uint64_t)ctx->numSMs * 8;
+    if (grid > tiles) grid = tiles;
+    if (grid < 1) grid = 1;
+#define DSB_GO(EF, ACT) output_tile_kernel<EF, ACT, DO_ACT, WRITE_UNIT, WRITE_DELTA, DO_LOSS><<<(unsigned)grid, kOThreads, 0, ctx->stream>>>(a)
+    if (a.act == DSB200_ACT_SIGMOID && a.ef == DSB200_ERR_SMCE) DSB_GO(DSB200_ERR_SMCE, DSB200_ACT_SIGMOID);
+    else if (a.act == DSB200_ACT_SIGMOID && a.ef == DSB200_ERR_CROSS_ENTROPY) DSB_GO(DSB200_ERR_CROSS_ENTROPY, DSB200_ACT_SIGMOID);
+    else if (a.act == DSB200_ACT_SIGMOID && a.ef == DSB200_ERR_L2) DSB_GO(DSB200_ERR_L2, DSB200_ACT_SIGMOID);
+    else DSB_GO(-1, -1);
+#undef DSB_GO
+    count_launch();
+    DSB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+static int check_output_args(dsb200_ctx* ctx, const dsb200_sparse* s, int ef, int act, const float* in, const char* who)
+{
+    if (!ctx || !s || !in) return fail(ctx, DSB200_EINVAL, who);
+    if (!s->sparseStart || !s->sparseEnd || !s->sparseIndex) return fail(ctx, DSB200_EINVAL, who);
+    if (ef != DSB200_ERR_L2 && ef != DSB200_ERR_CROSS_ENTROPY && ef != DSB200_ERR_SMCE)
+        return fail(ctx, DSB200_EUNSUPPORTED, "sparse output: error function outside the hot path (L2, CrossEntropy, ScaledMarginalCrossEntropy)");
+    if (s->sparseData && ef != DSB200_ERR_L2)
+        return fail(ctx, DSB200_EUNSUPPORTED, "sparse output: analog targets are supported for L2 only");
+    (void)act;
+    return 0;
+}
+
+static OArgs make_oargs(dsb200_ctx* ctx, const dsb200_sparse* s, int ef, int act, uint32_t position, uint32_t batch,
+                        uint32_t stride, const float* in, int ignoreZero, float slope, float alpha, float lambda)
+{
+    OArgs a{};
+    a.P = ctx->params; a.S = *s; a.ef = ef; a.act = act; a.ignoreZero = ignoreZero;
+    a.position = position; a.batch = batch; a.stride = stride; a.in = in;
+    a.slope = slope; a.alpha = alpha; a.lambda = lambda;
+    return a;
+}
+
+}  // namespace dsb
+
+extern "C" {
+
+int dsb200_sparse_loss_async(dsb200_ctx* ctx, const dsb200_sparse* s, int ef, int act, uint32_t position, uint32_t batch,
+                             uint32_t stride, const float* pUnit, int ignoreZero, unsigned long long* pDevAcc)
+{
+    using namespace dsb;
+    int rc = check_output_args(ctx, s, ef, act, pUnit, "sparse_loss: null argument");
+    if (rc) return rc;
+    if (!pDevAcc) return fail(ctx, DSB200_EINVAL, "sparse_loss: null accumulator");
+    if (!batch || !stride) return 0;
+    // multinomial (softmax) variants only have the non-zero term (E/kLoss.cu:1945-1967, 2566-2599)
+    const int iz = (act == DSB200_ACT_SOFTMAX && ef != DSB200_ERR_L2) ? 1 : ignoreZero;
+    OArgs a = make_oargs(ctx, s, ef, act, position, batch, stride, pUnit, iz, 0.0f, 0.0f, 0.0f);
+    a.acc = pDevAcc;
+    return launch_output<false, false, false, true>(ctx, a);
+}
+
+int dsb200_sparse_loss(dsb200_ctx* ctx, const dsb200_sparse* s, int ef, int act, uint32_t position, uint32_t batch,
+                       uint32_t stride, const float* pUnit, int ignoreZero, float* pLossOut)
+{
+    using namespace dsb;
+    if (!ctx || !pLossOut) return fail(ctx, DSB200_EINVAL, "sparse_loss: null argument");
+    DSB_CUDA_OK(cudaMemsetAsync(ctx->dAccumulator, 0, sizeof(unsigned long long), ctx->stream));   // E/kLoss.cu:2331
+    int rc = dsb200_sparse_loss_async(ctx, s, ef, act, position, batch, stride, pUnit, ignoreZero, ctx->dAccumulator);
+    if (rc) return rc;
+    DSB_CUDA_OK(cudaMemcpyAsync(ctx->hAccumulator, ctx->dAccumulator, sizeof(unsigned long long), cudaMemcpyDeviceToHost, ctx->stream));
+    DSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+    *pLossOut = (float)((double)(long long)ctx->hAccumulator[0] * kOneOverErrorScale);             // E/kLoss.cu:2349-2351
+    return 0;
+}
+
+int dsb200_sparse_output_delta(dsb200_ctx* ctx, const dsb200_sparse* s, int ef, int act, uint32_t position, uint32_t batch,
+                               uint32_t stride, const float* pUnit, float* pDelta, int ignoreZero,
+                               float slope, float alpha, float lambda)
+{
+    using namespace dsb;
+    int rc = check_output_args(ctx, s, ef, act, pUnit, "sparse_output_delta: null argument");
+    if (rc) return rc;
+    if (!pDelta) return fail(ctx, DSB200_EINVAL, "sparse_output_delta: null delta");
+    if (!batch || !stride) return 0;
+    OArgs a = make_oargs(ctx, s, ef, act, position, batch, stride, pUnit, ignoreZero, slope, alpha, lambda);
+    a.delta = pDelta;
+    return launch_output<false, false, true, false>(ctx, a);
+}
+
+int dsb200_output_pass(dsb200_ctx* ctx, const dsb200_sparse* s, int ef, int act, uint32_t position, uint32_t batch,
+                       uint32_t stride, const float* pZ, float* pUnitOut, float* pDelta, unsigned long long* pDevAcc)
+{
+    using namespace dsb;
+    int rc = check_output_args(ctx, s, ef, act, pZ, "output_pass: null argument");
+    if (rc) return rc;
+    if (!pDelta) return fail(ctx, DSB200_EINVAL, "output_pass: null delta");
+    if (act == DSB200_ACT_SOFTMAX)
+        return fail(ctx, DSB200_EUNSUPPORTED, "output_pass: softmax needs dsb200_activation first, then dsb200_sparse_loss/_output_delta");
+    if (!batch || !stride) return 0;
+    OArgs a = make_oargs(ctx, s, ef, act, position, batch, stride, pZ, 0, 0.0f, 0.0f, 0.0f);
+    a.unitOut = pUnitOut; a.delta = pDelta; a.acc = pDevAcc;
+    if (pUnitOut) return pDevAcc ? launch_output<true, true, true, true>(ctx, a) : launch_output<true, true, true, false>(ctx, a);
+    return pDevAcc ? launch_output<true, false, true, true>(ctx, a) : launch_output<true, false, true, false>(ctx, a);
+}
+
+}  // extern "C"

@@ -1,0 +1,273 @@
+// sparse_wgrad.cu -- sparse weight gradient of the input layer (hot-path row a6), optionally
+// fused with the optimizer step (a12).
+//
+// Replaces kCalculateSparseTransposed[Analog]WeightGradient (E/kernels.cu:2537-2692):
+//     dW[c,:] = beta*dW[c,:] + alpha*q * sum_{e in column c} (tdata_e *) delta[row_e,:]
+// with the sum taken exactly as the reference takes it: every term converted with
+// llrintf(2^30 * x) and added in int64, which makes the result independent of the order of the
+// entries inside a column (so the transposed matrix need not be sorted) and bit-identical to
+// the CPU oracle.
+//
+// Reference launch: one 256-thread block per input unit (27,278 / 1M tiny blocks), each lane
+// summing one output column over all entries with a single dependent chain.  Here:
+//  * persistent grid (multiple of the SM count); a CTA walks tiles of G columns, one column per
+//    thread group (a warp for stride 128: 32 lanes x float4 = one 512-byte delta row per load);
+//  * 8 independent delta-row gathers in flight per thread (ld.global.nc.v4, L1 bypass);
+//  * columns with more than kHeavy entries (the Zipf head: up to `batch` entries) are not left
+//    to one group: all G groups of the CTA split the entries and add their int64 partial sums
+//    through shared memory (exact, so still order independent);
+//  * |x| < 2 takes the 32-bit convert (F2I.S32) -- identical integer, 4x the throughput of the
+//    64-bit convert;
+//  * FUSED variant: the finished gradient row is fed straight into the optimizer rule and the
+//    weight (and state) row is updated in place -- dW is never written or re-read.
+#include "optimizer.cuh"
+#include "launch.h"
+
+namespace dsb {
+
+constexpr int kGThreads = 256;
+constexpr int kGUnroll  = 8;
+constexpr uint32_t kHeavy = 96;
+
+struct GArgs {
+    float alpha, beta;          // alpha already multiplied by q
+    uint32_t m, n;
+    const uint32_t* tStart; const uint32_t* tEnd; const uint32_t* tIndex; const float* tData;
+    const float* delta;
+    float* dW;
+    // fused optimizer
+    OptArgs opt;
+    float* v; float* gv; float* w;
+};
+
+template <bool ANALOG>
+__device__ __forceinline__ void accumulate_entries(const GArgs& a, uint32_t first, uint32_t last, uint32_t step,
+                                                   uint32_t col, long long (&acc)[4])
+{
+    const float* dcol = a.delta + col;
+    uint32_t e = first;
+    for (; e + (kGUnroll - 1) * step < last && e + (kGUnroll - 1) * step >= e; e += kGUnroll * step) {
+        float4 x[kGUnroll]; float tv[kGUnroll];
+#pragma unroll
+        for (int u = 0; u < kGUnroll; u++) {
+            const uint32_t ee = e + u * step;
+            const uint32_t row = __ldg(a.tIndex + ee);
+            tv[u] = ANALOG ? __ldg(a.tData + ee) : 1.0f;
+            x[u] = ldg_nc_f4(reinterpret_cast<const float4*>(dcol + (size_t)row * a.n));
+        }
+#pragma unroll
+        for (int u = 0; u < kGUnroll; u++) {
+            if (ANALOG) { x[u].x *= tv[u]; x[u].y *= tv[u]; x[u].z *= tv[u]; x[u].w *= tv[u]; }
+            acc[0] += fix30(x[u].x); acc[1] += fix30(x[u].y); acc[2] += fix30(x[u].z); acc[3] += fix30(x[u].w);
+        }
+    }
+    for (; e < last; e += step) {
+        const uint32_t row = __ldg(a.tIndex + e);
+        float4 x = ldg_nc_f4(reinterpret_cast<const float4*>(dcol + (size_t)row * a.n));
+        if (ANALOG) { const float tv = __ldg(a.tData + e); x.x *= tv; x.y *= tv; x.z *= tv; x.w *= tv; }
+        acc[0] += fix30(x.x); acc[1] += fix30(x.y); acc[2] += fix30(x.z); acc[3] += fix30(x.w);
+    }
+}
+
+template <bool ANALOG, int FUSED_MODE>      // FUSED_MODE = -1: write dW
+__device__ __forceinline__ void finish_row(const GArgs& a, uint32_t c, uint32_t col, const long long (&acc)[4])
+{
+    float g[4];
+#pragma unroll
+    for (int v = 0; v < 4; v++) g[v] = a.alpha * (float)((double)acc[v] * kOneOverErrorScale);   // E/kernels.cu:2585
+    const size_t off = (size_t)c * a.n + col;
+    if (FUSED_MODE < 0) {
+        float4 out = make_float4(g[0], g[1], g[2], g[3]);
+        if (a.beta != 0.0f) {
+            const float4 old = *reinterpret_cast<const float4*>(a.dW + off);
+            out.x += a.beta * old.x; out.y += a.beta * old.y; out.z += a.beta * old.z; out.w += a.beta * old.w;
+        }
+        *reinterpret_cast<float4*>(a.dW + off) = out;
+    } else {
+        constexpr int M = FUSED_MODE < 0 ? 0 : FUSED_MODE;
+        float4 w4 = *reinterpret_cast<const float4*>(a.w + off);
+        float4 v4 = make_float4(0, 0, 0, 0), s4 = make_float4(0, 0, 0, 0);
+        if (opt_uses_v(M))  v4 = *reinterpret_cast<const float4*>(a.v + off);
+        if (opt_uses_gv(M)) s4 = *reinterpret_cast<const float4*>(a.gv + off);
+        w4.x = opt_weight<M>(a.opt, g[0], w4.x, v4.x, s4.x);
+        w4.y = opt_weight<M>(a.opt, g[1], w4.y, v4.y, s4.y);
+        w4.z = opt_weight<M>(a.opt, g[2], w4.z, v4.z, s4.z);
+        w4.w = opt_weight<M>(a.opt, g[3], w4.w, v4.w, s4.w);
+        *reinterpret_cast<float4*>(a.w + off) = w4;
+        if (opt_uses_v(M))  *reinterpret_cast<float4*>(a.v + off) = v4;
+        if (opt_uses_gv(M)) *reinterpret_cast<float4*>(a.gv + off) = s4;
+    }
+}
+
+// n % 4 == 0.  lpr = lanes per delta row (power of two >= n/4, <= 256); G = 256/lpr groups.
+template <bool ANALOG, int FUSED_MODE>
+__global__ void __launch_bounds__(kGThreads, 3)
+sparse_wgrad_kernel(const GArgs a, uint32_t lpr)
+{
+    extern __shared__ long long sRed[];            // [G][lpr*4] int64 partials for heavy columns
+    __shared__ uint32_t sHeavy[kGThreads];         // heavy columns of the current tile (<= G)
+    __shared__ uint32_t sNHeavy;
+    const uint32_t tid = threadIdx.x;
+    const uint32_t G = kGThreads / lpr, g = tid / lpr, lane = tid % lpr;
+    const uint32_t n4 = a.n >> 2;
+    const uint32_t colBlocks = (n4 + lpr - 1) / lpr;
+    const uint32_t tiles = (a.m + G - 1) / G;
+
+    for (uint32_t tile = blockIdx.x; tile < tiles; tile += gridDim.x) {
+        if (tid == 0) sNHeavy = 0;
+        __syncthreads();
+        const uint32_t c = tile * G + g;
+        uint32_t s = 0, e = 0;
+        if (c < a.m) { s = __ldg(a.tStart + c); e = __ldg(a.tEnd + c); }
+        const uint32_t cnt = e - s;
+        const bool heavy = (G > 1) && cnt > kHeavy;
+        if (heavy && lane == 0) sHeavy[atomicAdd(&sNHeavy, 1u)] = c;
+        if (c < a.m && !heavy) {
+            for (uint32_t cb = 0; cb < colBlocks; cb++) {
+                const uint32_t col = (cb * lpr + lane) * 4;
+                if (col < a.n) {
+                    long long acc[4] = {0, 0, 0, 0};
+                    accumulate_entries<ANALOG>(a, s, e, 1, col, acc);
+                    finish_row<ANALOG, FUSED_MODE>(a, c, col, acc);
+                }
+            }
+        }
+        __syncthreads();
+        const uint32_t nh = sNHeavy;
+        for (uint32_t h = 0; h < nh; h++) {
+            // smallest remaining column id first => fixed processing order (results are order
+            // independent anyway; this only keeps the memory access pattern reproducible)
+            const uint32_t hc = sHeavy[h];
+            const uint32_t hs = __ldg(a.tStart + hc), he = __ldg(a.tEnd + hc);
+            for (uint32_t cb = 0; cb < colBlocks; cb++) {
+                const uint32_t col = (cb * lpr + lane) * 4;
+                long long acc[4] = {0, 0, 0, 0};
+                if (col < a.n) accumulate_entries<ANALOG>(a, hs + g, he, G, col, acc);
+#pragma unroll
+                for (int v = 0; v < 4; v++) sRed[((size_t)g * lpr + lane) * 4 + v] = acc[v];
+                __syncthreads();
+                if (g == 0 && col < a.n) {
+                    long long tot[4] = {0, 0, 0, 0};
+                    for (uint32_t gg = 0; gg < G; gg++)
+#pragma unroll
+                        for (int v = 0; v < 4; v++) tot[v] += sRed[((size_t)gg * lpr + lane) * 4 + v];
+                    finish_row<ANALOG, FUSED_MODE>(a, hc, col, tot);
+                }
+                __syncthreads();
+            }
+        }
+    }
+}
+
+// scalar fallback for strides that are not a multiple of 4 (or unaligned buffers): one thread
+// per (column, output) pair, same fixed-point arithmetic.
+template <bool ANALOG>
+__global__ void __launch_bounds__(256)
+sparse_wgrad_scalar_kernel(const GArgs a)
+{
+    const uint64_t total = (uint64_t)a.m * a.n;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t c = (uint32_t)(i / a.n), o = (uint32_t)(i % a.n);
+        long long acc = 0;
+        for (uint32_t e = __ldg(a.tStart + c); e < __ldg(a.tEnd + c); e++) {
+            float x = __ldg(a.delta + (size_t)__ldg(a.tIndex + e) * a.n + o);
+            if (ANALOG) x *= __ldg(a.tData + e);
+            acc += fix30(x);
+        }
+        const float g = a.alpha * (float)((double)acc * kOneOverErrorScale);
+        a.dW[i] = ((a.beta == 0.0f) ? 0.0f : a.beta * a.dW[i]) + g;
+    }
+}
+
+static uint32_t lanes_per_row(uint32_t n)
+{
+    uint32_t n4 = n >> 2, lpr = 1;
+    while (lpr < n4 && lpr < (uint32_t)kGThreads) lpr <<= 1;
+    return lpr;
+}
+
+template <bool ANALOG, int FUSED_MODE>
+static int launch_wgrad(dsb200_ctx* ctx, const GArgs& a)
+{
+    const uint32_t lpr = lanes_per_row(a.n);
+    const uint32_t G = kGThreads / lpr;
+    const uint32_t tiles = (a.m + G - 1) / G;
+    int grid = ctx->numSMs * 3;
+    if ((uint32_t)grid > tiles) grid = (int)tiles;
+    if (grid < 1) grid = 1;
+    const size_t smem = (size_t)kGThreads * 4 * sizeof(long long);
+    sparse_wgrad_kernel<ANALOG, FUSED_MODE><<<grid, kGThreads, smem, ctx->stream>>>(a, lpr);
+    count_launch();
+    DSB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+static int check_wgrad_args(dsb200_ctx* ctx, const uint32_t* tStart, const uint32_t* tEnd, const uint32_t* tIndex, const float* delta)
+{
+    if (!ctx || !tStart || !tEnd || !tIndex || !delta) return fail(ctx, DSB200_EINVAL, "sparse_wgrad: null argument");
+    return 0;
+}
+
+}  // namespace dsb
+
+extern "C" {
+
+int dsb200_sparse_wgrad(dsb200_ctx* ctx, float alpha, float beta, uint32_t m, uint32_t n,
+                        const uint32_t* tStart, const uint32_t* tEnd, const uint32_t* tIndex, const float* tData,
+                        const float* delta, float* dW)
+{
+    using namespace dsb;
+    int rc = check_wgrad_args(ctx, tStart, tEnd, tIndex, delta);
+    if (rc) return rc;
+    if (!dW) return fail(ctx, DSB200_EINVAL, "sparse_wgrad: null gradient buffer");
+    if (!m || !n) return 0;
+    GArgs a{};
+    a.alpha = alpha * ctx->params.denoising_q;              // E/kernels.cu:2547
+    a.beta = beta; a.m = m; a.n = n;
+    a.tStart = tStart; a.tEnd = tEnd; a.tIndex = tIndex; a.tData = tData; a.delta = delta; a.dW = dW;
+    const bool vec = (n % 4 == 0) && ((((uintptr_t)delta | (uintptr_t)dW) % 16) == 0);
+    if (vec) return tData ? launch_wgrad<true, -1>(ctx, a) : launch_wgrad<false, -1>(ctx, a);
+    uint64_t blocks = ((uint64_t)m * n + 255) / 256;
+    if (blocks > (uint64_t)ctx->numSMs * 8) blocks = (uint64_t)ctx->numSMs * 8;
+    if (tData) sparse_wgrad_scalar_kernel<true><<<(unsigned)blocks, 256, 0, ctx->stream>>>(a);
+    else       sparse_wgrad_scalar_kernel<false><<<(unsigned)blocks, 256, 0, ctx->stream>>>(a);
+    count_launch();
+    DSB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int dsb200_sparse_wgrad_update(dsb200_ctx* ctx, int mode, float galpha, uint32_t m, uint32_t n,
+                               const uint32_t* tStart, const uint32_t* tEnd, const uint32_t* tIndex, const float* tData,
+                               const float* delta, float alpha, float lambda, float lambda1, float mu, float mu1, float t,
+                               float* v, float* gv, float* w)
+{
+    using namespace dsb;
+    int rc = check_wgrad_args(ctx, tStart, tEnd, tIndex, delta);
+    if (rc) return rc;
+    if (!w) return fail(ctx, DSB200_EINVAL, "sparse_wgrad_update: null weight buffer");
+    if (mode < 0 || mode > DSB200_ADAM) return fail(ctx, DSB200_EINVAL, "sparse_wgrad_update: bad mode");
+    if (opt_uses_v(mode) && !v) return fail(ctx, DSB200_EINVAL, "sparse_wgrad_update: velocity buffer missing");
+    if (opt_uses_gv(mode) && !gv) return fail(ctx, DSB200_EINVAL, "sparse_wgrad_update: gradient-velocity buffer missing");
+    if ((n % 4) || ((((uintptr_t)delta | (uintptr_t)w | (uintptr_t)v | (uintptr_t)gv) % 16) != 0))
+        return fail(ctx, DSB200_EUNSUPPORTED, "sparse_wgrad_update: needs stride % 4 == 0 and 16-byte aligned buffers");
+    if (!m || !n) return 0;
+    GArgs a{};
+    a.alpha = galpha * ctx->params.denoising_q;
+    a.beta = 0.0f; a.m = m; a.n = n;
+    a.tStart = tStart; a.tEnd = tEnd; a.tIndex = tIndex; a.tData = tData; a.delta = delta; a.dW = nullptr;
+    a.opt = make_opt(mode, alpha, lambda, lambda1, mu, mu1, t);
+    a.v = v; a.gv = gv; a.w = w;
+#define DSB_FUSED(M) (tData ? launch_wgrad<true, M>(ctx, a) : launch_wgrad<false, M>(ctx, a))
+    switch (mode) {
+    case DSB200_SGD:      return DSB_FUSED(DSB200_SGD);
+    case DSB200_MOMENTUM: return DSB_FUSED(DSB200_MOMENTUM);
+    case DSB200_ADAGRAD:  return DSB_FUSED(DSB200_ADAGRAD);
+    case DSB200_NESTEROV: return DSB_FUSED(DSB200_NESTEROV);
+    case DSB200_RMSPROP:  return DSB_FUSED(DSB200_RMSPROP);
+    case DSB200_ADADELTA: return DSB_FUSED(DSB200_ADADELTA);
+    default:              return DSB_FUSED(DSB200_ADAM);
+    }
+#undef DSB_FUSED
+}
+
+}  // extern "C"
