@@ -161,6 +161,7 @@ extern "C" {
 
 int dsb200_activation(dsb200_ctx* ctx, int act, float* pData, uint32_t batch, uint32_t stride, float slope, float alpha, float lambda)
 {
+    DSB_PROFILE(ctx, "activation");
     using namespace dsb;
     if (!ctx || !pData) return fail(ctx, DSB200_EINVAL, "activation: null argument");
     const uint64_t size = (uint64_t)batch * stride;
@@ -182,6 +183,7 @@ int dsb200_activation(dsb200_ctx* ctx, int act, float* pData, uint32_t batch, ui
 int dsb200_hadamard(dsb200_ctx* ctx, int act, uint64_t size, float scale, const float* pUnit, float* pDelta,
                     float slope, float alpha, float lambda)
 {
+    DSB_PROFILE(ctx, "hadamard");
     using namespace dsb;
     if (!ctx || !pUnit || !pDelta) return fail(ctx, DSB200_EINVAL, "hadamard: null argument");
     if (!size || act == DSB200_ACT_LINEAR) return 0;
@@ -194,6 +196,7 @@ int dsb200_hadamard(dsb200_ctx* ctx, int act, uint64_t size, float scale, const 
 
 int dsb200_sparseness_penalty(dsb200_ctx* ctx, uint32_t batch, uint32_t stride, const float* pUnit, float* pDelta, float p, float beta)
 {
+    DSB_PROFILE(ctx, "sparseness_penalty");
     using namespace dsb;
     if (!ctx || !pUnit || !pDelta) return fail(ctx, DSB200_EINVAL, "sparseness_penalty: null argument");
     if (!batch || !stride) return 0;
@@ -204,3 +207,23 @@ int dsb200_sparseness_penalty(dsb200_ctx* ctx, uint32_t batch, uint32_t stride, 
 }
 
 }  // extern "C"
+
+// kAddBuffers (E/kernels.cu:39-57): pDst += pSrc -- used after a reduce-scatter that lands in scratch
+namespace dsb {
+__global__ void __launch_bounds__(256) add_buffers_kernel(float* __restrict__ dst, const float* __restrict__ src, uint64_t size)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < size; i += (uint64_t)gridDim.x * blockDim.x) dst[i] += src[i];
+}
+}  // namespace dsb
+
+extern "C" int dsb200_add_buffers(dsb200_ctx* ctx, float* pDst, const float* pSrc, uint64_t size)
+{
+    DSB_PROFILE(ctx, "add_buffers");
+    using namespace dsb;
+    if (!ctx || !pDst || !pSrc) return fail(ctx, DSB200_EINVAL, "add_buffers: null argument");
+    if (!size) return 0;
+    add_buffers_kernel<<<grid_for(ctx, size), 256, 0, ctx->stream>>>(pDst, pSrc, size);
+    count_launch();
+    DSB_CUDA_OK(cudaGetLastError());
+    return 0;
+}

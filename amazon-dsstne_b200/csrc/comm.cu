@@ -149,6 +149,7 @@ int dsb200_comm_destroy(dsb200_ctx* ctx)
 
 int dsb200_reduce_scatter(dsb200_ctx* ctx, uint32_t batch, uint32_t stride, const float* pIn, float* pOut)
 {
+    DSB_PROFILE(ctx, "reduce_scatter");
     using namespace dsb;
     if (!ctx || !pIn || !pOut) return fail(ctx, DSB200_EINVAL, "reduce_scatter: null argument");
     const uint32_t P = (uint32_t)ctx->nranks;
@@ -178,6 +179,7 @@ int dsb200_reduce_scatter(dsb200_ctx* ctx, uint32_t batch, uint32_t stride, cons
 
 int dsb200_all_gather(dsb200_ctx* ctx, uint32_t batch, uint32_t stride, const float* pLocal, float* pFull)
 {
+    DSB_PROFILE(ctx, "all_gather");
     using namespace dsb;
     if (!ctx || !pLocal || !pFull) return fail(ctx, DSB200_EINVAL, "all_gather: null argument");
     const uint32_t P = (uint32_t)ctx->nranks;
@@ -223,6 +225,7 @@ int dsb200_all_gather(dsb200_ctx* ctx, uint32_t batch, uint32_t stride, const fl
 
 int dsb200_all_reduce(dsb200_ctx* ctx, float* pBuffer, uint64_t size)
 {
+    DSB_PROFILE(ctx, "all_reduce");
     using namespace dsb;
     if (!ctx || !pBuffer) return fail(ctx, DSB200_EINVAL, "all_reduce: null argument");
     if (ctx->nranks == 1 || !size) return 0;
@@ -233,6 +236,7 @@ int dsb200_all_reduce(dsb200_ctx* ctx, float* pBuffer, uint64_t size)
 
 int dsb200_all_reduce_u64(dsb200_ctx* ctx, unsigned long long* pBuffer, uint64_t size)
 {
+    DSB_PROFILE(ctx, "all_reduce_u64");
     using namespace dsb;
     if (!ctx || !pBuffer) return fail(ctx, DSB200_EINVAL, "all_reduce_u64: null argument");
     if (ctx->nranks == 1 || !size) return 0;

@@ -44,6 +44,7 @@ extern "C" {
 
 int dsb200_gemm_fwd(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, const float* A, const float* W, float beta, float* C)
 {
+    DSB_PROFILE(ctx, "gemm_fwd");
     using namespace dsb;
     if (!ctx || !A || !W || !C) return fail(ctx, DSB200_EINVAL, "gemm_fwd: null argument");
     if (!B || !k || !n) return 0;
@@ -57,6 +58,7 @@ int dsb200_gemm_fwd(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, const f
 
 int dsb200_gemm_dw(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, float alpha, const float* A, const float* D, float beta, float* G)
 {
+    DSB_PROFILE(ctx, "gemm_dw");
     using namespace dsb;
     if (!ctx || !A || !D || !G) return fail(ctx, DSB200_EINVAL, "gemm_dw: null argument");
     if (!B || !k || !n) return 0;
@@ -69,6 +71,7 @@ int dsb200_gemm_dw(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, float al
 
 int dsb200_gemm_dx(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, const float* D, const float* W, float beta, float* Dp)
 {
+    DSB_PROFILE(ctx, "gemm_dx");
     using namespace dsb;
     if (!ctx || !D || !W || !Dp) return fail(ctx, DSB200_EINVAL, "gemm_dx: null argument");
     if (!B || !k || !n) return 0;

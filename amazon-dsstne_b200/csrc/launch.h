@@ -13,3 +13,16 @@ struct dsb200_ctx;
 namespace dsb {
 void gemm_release(dsb200_ctx* ctx);
 }
+
+// ---- optional per-family device timing (option "profile"): CUDA events on the launching stream
+// around every C-ABI kernel entry; bench.py reads the totals with dsb200_profile_report ----
+#include <cuda_runtime.h>
+namespace dsb {
+struct ProfileScope {
+    dsb200_ctx* ctx;
+    int slot;
+    ProfileScope(dsb200_ctx* c, const char* name);
+    ~ProfileScope();
+};
+}
+#define DSB_PROFILE(ctx, name) dsb::ProfileScope _dsb_prof_scope((ctx), (name))

@@ -177,6 +177,7 @@ extern "C" {
 int dsb200_update_weights(dsb200_ctx* ctx, int mode, float alpha, float lambda, float lambda1, float mu, float mu1, float t,
                           uint64_t size, float* v, const float* g, float* gv, float* w)
 {
+    DSB_PROFILE(ctx, "update_weights");
     using namespace dsb;
     if (!ctx || !g || !w) return fail(ctx, DSB200_EINVAL, "update_weights: null argument");
     if (mode < 0 || mode > DSB200_ADAM) return fail(ctx, DSB200_EINVAL, "update_weights: bad mode");
@@ -198,6 +199,7 @@ int dsb200_update_weights(dsb200_ctx* ctx, int mode, float alpha, float lambda, 
 int dsb200_update_biases(dsb200_ctx* ctx, int mode, float alpha, float mu, float mu1, float t, uint32_t batch, uint32_t width,
                          const float* delta, float* v, float* gv, float* bias)
 {
+    DSB_PROFILE(ctx, "update_biases");
     using namespace dsb;
     if (!ctx || !delta || !bias) return fail(ctx, DSB200_EINVAL, "update_biases: null argument");
     if (mode < 0 || mode > DSB200_ADAM) return fail(ctx, DSB200_EINVAL, "update_biases: bad mode");
@@ -218,6 +220,7 @@ int dsb200_update_biases(dsb200_ctx* ctx, int mode, float alpha, float mu, float
 
 int dsb200_regularization_error(dsb200_ctx* ctx, float lambda, float lambda1, const float* w, uint64_t size, float* out)
 {
+    DSB_PROFILE(ctx, "regularization_error");
     using namespace dsb;
     if (!ctx || !w || !out) return fail(ctx, DSB200_EINVAL, "regularization_error: null argument");
     DSB_CUDA_OK(cudaMemsetAsync(ctx->dAccumulator, 0, sizeof(unsigned long long), ctx->stream));

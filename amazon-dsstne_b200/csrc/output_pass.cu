@@ -243,6 +243,7 @@ extern "C" {
 int dsb200_sparse_loss_async(dsb200_ctx* ctx, const dsb200_sparse* s, int ef, int act, uint32_t position, uint32_t batch,
                              uint32_t stride, const float* pUnit, int ignoreZero, unsigned long long* pDevAcc)
 {
+    DSB_PROFILE(ctx, "sparse_loss_async");
     using namespace dsb;
     int rc = check_output_args(ctx, s, ef, act, pUnit, "sparse_loss: null argument");
     if (rc) return rc;
@@ -273,6 +274,7 @@ int dsb200_sparse_output_delta(dsb200_ctx* ctx, const dsb200_sparse* s, int ef, 
                                uint32_t stride, const float* pUnit, float* pDelta, int ignoreZero,
                                float slope, float alpha, float lambda)
 {
+    DSB_PROFILE(ctx, "sparse_output_delta");
     using namespace dsb;
     int rc = check_output_args(ctx, s, ef, act, pUnit, "sparse_output_delta: null argument");
     if (rc) return rc;
@@ -286,6 +288,7 @@ int dsb200_sparse_output_delta(dsb200_ctx* ctx, const dsb200_sparse* s, int ef, 
 int dsb200_output_pass(dsb200_ctx* ctx, const dsb200_sparse* s, int ef, int act, uint32_t position, uint32_t batch,
                        uint32_t stride, const float* pZ, float* pUnitOut, float* pDelta, unsigned long long* pDevAcc)
 {
+    DSB_PROFILE(ctx, "output_pass");
     using namespace dsb;
     int rc = check_output_args(ctx, s, ef, act, pZ, "output_pass: null argument");
     if (rc) return rc;

@@ -205,6 +205,7 @@ static int launch_scatter(dsb200_ctx* ctx, const TArgs& a)
 extern "C" int dsb200_sparse_transpose(dsb200_ctx* ctx, const dsb200_sparse* s, uint32_t position, uint32_t batch, int denoised,
                                        uint32_t N, const uint32_t* tStart, uint32_t* tEnd, uint32_t* tIndex, float* tData)
 {
+    DSB_PROFILE(ctx, "sparse_transpose");
     using namespace dsb;
     if (!ctx || !s || !tEnd || !tIndex) return fail(ctx, DSB200_EINVAL, "sparse_transpose: null argument");
     if (!s->sparseStart || !s->sparseEnd || !s->sparseIndex) return fail(ctx, DSB200_EINVAL, "sparse_transpose: CSR arrays missing");

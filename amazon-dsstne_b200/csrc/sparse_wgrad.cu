@@ -216,6 +216,7 @@ int dsb200_sparse_wgrad(dsb200_ctx* ctx, float alpha, float beta, uint32_t m, ui
                         const uint32_t* tStart, const uint32_t* tEnd, const uint32_t* tIndex, const float* tData,
                         const float* delta, float* dW)
 {
+    DSB_PROFILE(ctx, "sparse_wgrad");
     using namespace dsb;
     int rc = check_wgrad_args(ctx, tStart, tEnd, tIndex, delta);
     if (rc) return rc;
@@ -241,6 +242,7 @@ int dsb200_sparse_wgrad_update(dsb200_ctx* ctx, int mode, float galpha, uint32_t
                                const float* delta, float alpha, float lambda, float lambda1, float mu, float mu1, float t,
                                float* v, float* gv, float* w)
 {
+    DSB_PROFILE(ctx, "sparse_wgrad_update");
     using namespace dsb;
     int rc = check_wgrad_args(ctx, tStart, tEnd, tIndex, delta);
     if (rc) return rc;

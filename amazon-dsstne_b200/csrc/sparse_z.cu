@@ -428,12 +428,14 @@ extern "C" {
 int dsb200_sparse_z(dsb200_ctx* ctx, const dsb200_sparse* s, uint32_t position, uint32_t batch, uint32_t stride,
                     const float* pWeight, float* pUnit, float beta, int denoised)
 {
+    DSB_PROFILE(ctx, "sparse_z");
     return dsb::sparse_z_impl(ctx, s, position, batch, stride, pWeight, nullptr, -1, pUnit, beta, denoised, 0);
 }
 
 int dsb200_sparse_z_bias_act(dsb200_ctx* ctx, const dsb200_sparse* s, uint32_t position, uint32_t batch, uint32_t stride,
                              const float* pWeight, const float* pBias, int activation, float* pUnit, int denoised)
 {
+    DSB_PROFILE(ctx, "sparse_z_bias_act");
     if (!pBias) return dsb::fail(ctx, DSB200_EINVAL, "sparse_z_bias_act: bias missing");
     if (activation != DSB200_ACT_SIGMOID && activation != DSB200_ACT_TANH && activation != DSB200_ACT_RELU &&
         activation != DSB200_ACT_LINEAR)
@@ -443,6 +445,7 @@ int dsb200_sparse_z_bias_act(dsb200_ctx* ctx, const dsb200_sparse* s, uint32_t p
 
 int dsb200_clear_unit(dsb200_ctx* ctx, float* pUnit, const float* pBias, uint32_t stride, uint32_t batch)
 {
+    DSB_PROFILE(ctx, "clear_unit");
     if (!ctx || !pUnit || !pBias) return dsb::fail(ctx, DSB200_EINVAL, "clear_unit: null argument");
     uint64_t size = (uint64_t)stride * batch;
     if (!size) return 0;
@@ -455,6 +458,7 @@ int dsb200_clear_unit(dsb200_ctx* ctx, float* pUnit, const float* pBias, uint32_
 
 int dsb200_add_bias(dsb200_ctx* ctx, float* pUnit, const float* pBias, uint32_t stride, uint32_t batch)
 {
+    DSB_PROFILE(ctx, "add_bias");
     if (!ctx || !pUnit || !pBias) return dsb::fail(ctx, DSB200_EINVAL, "add_bias: null argument");
     uint64_t size = (uint64_t)stride * batch;
     if (!size) return 0;

@@ -235,12 +235,14 @@ extern "C" {
 int dsb200_topk(dsb200_ctx* ctx, const float* pScores, uint32_t batch, uint32_t width, uint32_t k,
                 const uint64_t* fs, const uint64_t* fe, const uint32_t* fi, float* pOutKey, uint32_t* pOutValue)
 {
+    DSB_PROFILE(ctx, "topk");
     return dsb::topk_impl(ctx, pScores, nullptr, batch, width, k, fs, fe, fi, pOutKey, pOutValue);
 }
 
 int dsb200_topk_kv(dsb200_ctx* ctx, const float* pKey, const uint32_t* pValue, uint32_t batch, uint32_t width, uint32_t k,
                    float* pOutKey, uint32_t* pOutValue)
 {
+    DSB_PROFILE(ctx, "topk_kv");
     if (!pValue) return dsb::fail(ctx, DSB200_EINVAL, "topk_kv: null value array");
     return dsb::topk_impl(ctx, pKey, pValue, batch, width, k, nullptr, nullptr, nullptr, pOutKey, pOutValue);
 }

@@ -1,0 +1,81 @@
+// GpuTypes.cpp -- see GpuTypes.h.  Replaces E/GpuTypes.cpp (MPI rank -> GPU selection, P2P
+// probing, cuBLAS/cuRAND/cuDNN handles) with: rank from the launcher, one dsb200_ctx, NCCL.
+#include "GpuTypes.h"
+
+static GpuContext g_gpu;
+GpuContext& getGpu() { return g_gpu; }
+
+GpuContext::GpuContext()
+    : _ctx(nullptr), _numprocs(1), _id(0), _device(0), _warpSize(32), _pNetwork(nullptr), _seed(0), _bStarted(false),
+      _totalGPUMemory(0), _totalCPUMemory(0), _stream(nullptr)
+{
+    dsb200_params_default(&_data);
+}
+
+GpuContext::~GpuContext() {}
+
+void GpuContext::Check(int rc, const char* what)
+{
+    if (rc) throw DsbEngineError(std::string(what) + ": " + (_ctx ? dsb200_last_error(_ctx) : "no context") + " (" + std::to_string(rc) + ")");
+}
+
+static int env_int(const char* name, int dflt)
+{
+    const char* v = getenv(name);
+    return (v && *v) ? atoi(v) : dflt;
+}
+
+// torchrun-style environment instead of MPI_Init (E/GpuTypes.cpp:62-140): RANK / WORLD_SIZE /
+// LOCAL_RANK.  The NCCL unique id has to be handed in by the launcher for nranks > 1.
+void GpuContext::Startup(int argc, char** argv)
+{
+    (void)argc; (void)argv;
+    Startup(env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0), nullptr);
+}
+
+void GpuContext::Startup(int rank, int nranks, int device, const void* ncclUniqueId128)
+{
+    if (_bStarted) Shutdown();
+    _id = rank; _numprocs = nranks; _device = device;
+    int rc = dsb200_ctx_create(&_ctx, device);
+    if (rc) throw DsbEngineError("GpuContext::Startup: no sm_100 GPU " + std::to_string(device) + " (there is no CPU fallback)");
+    RTERROR(cudaSetDevice(device), "GpuContext::Startup cudaSetDevice");
+    dsb200_ctx_set_stream(_ctx, _stream);
+    if (nranks > 1) {
+        if (!ncclUniqueId128) throw DsbEngineError("GpuContext::Startup: nranks > 1 needs the NCCL unique id from the launcher");
+        Check(dsb200_comm_init(_ctx, ncclUniqueId128, rank, nranks), "dsb200_comm_init");
+    }
+    _bStarted = true;
+    CopyConstants();
+}
+
+void GpuContext::Shutdown()
+{
+    if (_ctx) { dsb200_ctx_destroy(_ctx); _ctx = nullptr; }
+    _bStarted = false;
+    _pNetwork = nullptr;
+}
+
+void GpuContext::SetStream(cudaStream_t stream)
+{
+    _stream = stream;
+    if (_ctx) dsb200_ctx_set_stream(_ctx, stream);
+}
+
+void GpuContext::SetRandomSeed(unsigned long seed) { _seed = seed; }
+
+void GpuContext::CopyConstants()
+{
+    if (_ctx) Check(dsb200_ctx_set_params(_ctx, &_data), "dsb200_ctx_set_params");
+}
+
+void GpuContext::GetMemoryUsage(int* gpuMemory, int* cpuMemory)
+{
+    *gpuMemory = (int)(_totalGPUMemory / 1024ll);
+    *cpuMemory = (int)(_totalCPUMemory / 1024ll);
+}
+
+void GpuContext::Synchronize()
+{
+    Check(dsb200_ctx_sync(_ctx), "dsb200_ctx_sync");
+}

@@ -1,0 +1,586 @@
+// NNNetwork.cpp -- graph, training and prediction loops for fully-connected networks.
+//
+// Follows E/NNNetwork.cpp: constructor (:404-700), LoadDataSets (:1001-1170), RefreshState (:909-1000),
+// PredictBatch / PredictTrainingBatch (:1376-1470), Train (:1536-1694), CalculateError (:1708-1744),
+// BackPropagate (:1747-1768), UpdateWeights (:1770-1790), CalculateTopK (:1792-1822).
+// B200-first differences:
+//  * the per-minibatch loss is a fixed-point device accumulator copied to pinned memory behind an
+//    event; the host launches BackPropagate BEFORE it waits for the value, so the GPU never idles on
+//    the read-back (the reference blocks in a synchronous Download every batch, E/kLoss.cu:2349);
+//    skipping BackPropagate while the divergence brake skips the update (E/NNNetwork.cpp:1641-1650) has
+//    no observable effect, so it always runs and only the update is conditional;
+//  * model parallelism: per-layer exchange through NCCL (NNLayer::Reduce / Gather), the two loss
+//    scalars through an int64 all-reduce of the fixed-point words instead of MPI_Allreduce on doubles;
+//  * shuffle indices come from a host Fisher-Yates driven by the counter-based generator (identical
+//    on every rank, so no broadcast).
+#include "NNNetwork.h"
+
+#include <algorithm>
+#include <chrono>
+#include <cfloat>
+#include <iostream>
+#include <sstream>
+
+using namespace std;
+
+NNNetworkDescriptor::NNNetworkDescriptor()
+    : _kind(NNNetwork::Kind::FeedForward), _errorFunction(ErrorFunction::CrossEntropy), _bShuffleIndices(true), _decay(0.0f),
+      _RELUSlope(1.0f), _ELUAlpha(1.0f), _SELULambda(1.050701f), _bSparsenessPenalty(false), _sparsenessPenalty_p(0.0f),
+      _sparsenessPenalty_beta(0.0f), _bDenoising(false), _denoising_p(0.0f), _deltaBoost_one(1.0f), _deltaBoost_zero(1.0f),
+      _SMCE_oneTarget(0.9f), _SMCE_zeroTarget(0.1f), _SMCE_oneScale(1.0f), _SMCE_zeroScale(1.0f), _checkpoint_name("checkpoint"),
+      _checkpoint_interval(0), _checkpoint_epochs(0)
+{
+}
+
+NNNetwork* CreateNeuralNetwork(NNNetworkDescriptor& nd, uint32_t batch) { return new NNNetwork(nd, batch); }
+
+NNNetwork::NNNetwork(NNNetworkDescriptor& d, uint32_t batch)
+    : _name(d._name), _batch(batch), _position(0), _bExamplesFound(false), _bAllDataLoaded(true), _examples(0), _kind(d._kind),
+      _errorFunction(d._errorFunction), _trainingMode(SGD), _mode(Prediction), _epochs(0), _batches(0), _decay(d._decay),
+      _RELUSlope(d._RELUSlope), _ELUAlpha(d._ELUAlpha), _SELULambda(d._SELULambda), _bSparsenessPenalty(d._bSparsenessPenalty),
+      _sparsenessPenalty_p(d._sparsenessPenalty_p), _sparsenessPenalty_beta(d._sparsenessPenalty_beta), _bDenoising(d._bDenoising),
+      _denoising_p(d._denoising_p), _deltaBoost_one(d._deltaBoost_one), _deltaBoost_zero(d._deltaBoost_zero),
+      _SMCE_oneTarget(d._SMCE_oneTarget), _SMCE_zeroTarget(d._SMCE_zeroTarget), _SMCE_oneScale(d._SMCE_oneScale),
+      _SMCE_zeroScale(d._SMCE_zeroScale), _bShuffleIndices(d._bShuffleIndices), _shuffleIndices(0), _shuffleEpoch(0),
+      _checkpoint_name(d._checkpoint_name), _checkpoint_interval(d._checkpoint_interval), _checkpoint_epochs(0), _bDirty(true),
+      _bClearVelocity(true), _scratchBufferSize(0), _maxStride(0), _errorEvent(NULL), _verbose(false), _bFusion(true),
+      _movingAverage(0.0f), _brakeSteps(0), _initSteps(100)
+{
+    if (!getGpu()._ctx) throw DsbEngineError("NNNetwork: getGpu().Startup() has not been called (no GPU context; there is no CPU fallback)");
+    for (auto l : d._vLayerDescriptor) {
+        if (std::isnan(l._RELUSlope)) l._RELUSlope = _RELUSlope;            // layer inherits the network defaults (E/NNNetwork.cpp:3683-3690)
+        if (std::isnan(l._ELUAlpha)) l._ELUAlpha = _ELUAlpha;
+        if (std::isnan(l._SELULambda)) l._SELULambda = _SELULambda;
+        if (_mLayer.count(l._name)) throw DsbEngineError("NNNetwork: duplicate layer name " + l._name);
+        _vLayer.push_back(new NNLayer(l, batch));
+        _mLayer[_vLayer.back()->_name] = _vLayer.back();
+        if (_vLayer.back()->_kind == NNLayer::Kind::Input) _vInputLayer.push_back(_vLayer.back());
+        else if (_vLayer.back()->_kind == NNLayer::Kind::Output) _vOutputLayer.push_back(_vLayer.back());
+    }
+    for (auto& wd : d._vWeightDescriptor) {                                  // E/NNNetwork.cpp:540-600
+        if (!_mLayer.count(wd._inputLayer) || !_mLayer.count(wd._outputLayer))
+            throw DsbEngineError("NNNetwork: weight between unknown layers " + wd._inputLayer + " -> " + wd._outputLayer);
+        NNWeight* pWeight = new NNWeight(*_mLayer[wd._inputLayer], *_mLayer[wd._outputLayer], wd._bShared, wd._bTransposed, wd._bLocked, wd._norm);
+        _vWeight.push_back(pWeight);
+        if (wd._vWeight.empty() || wd._vBias.empty()) pWeight->Randomize();
+        if (!wd._vWeight.empty()) pWeight->SetWeights(wd._vWeight);
+        if (!wd._vBias.empty()) pWeight->SetBiases(wd._vBias);
+    }
+    CalculatePropagationOrder();
+    _pbErrorAccumulator.reset(new GpuBuffer<unsigned long long>(4, true));
+    RTERROR(cudaEventCreateWithFlags(&_errorEvent, cudaEventDisableTiming), "NNNetwork: cudaEventCreate");
+}
+
+NNNetwork::~NNNetwork()
+{
+    if (getGpu()._pNetwork == this) getGpu()._pNetwork = NULL;
+    for (auto w : _vWeight) delete w;
+    for (auto l : _vLayer) delete l;
+    if (_errorEvent) cudaEventDestroy(_errorEvent);
+}
+
+// Kahn's algorithm over the layer graph, ties broken by declaration order (the reference assigns
+// priorities by longest path, E/NNNetwork.cpp:2345-2457; for feed-forward graphs the orders agree)
+void NNNetwork::CalculatePropagationOrder()
+{
+    _vFPOrder.clear(); _vBPOrder.clear();
+    map<NNLayer*, size_t> pending;
+    for (auto l : _vLayer) pending[l] = l->_vIncomingLayer.size();
+    vector<NNLayer*> done;
+    while (done.size() < _vLayer.size()) {
+        bool progressed = false;
+        for (auto l : _vLayer) {
+            if (l->_priority >= 0 || pending[l] != 0) continue;
+            l->_priority = (int32_t)done.size();
+            done.push_back(l);
+            for (auto o : l->_vOutgoingLayer) pending[o]--;
+            progressed = true;
+        }
+        if (!progressed) throw DsbEngineError("NNNetwork: the layer graph has a cycle");
+    }
+    _vFPOrder = done;
+    _vBPOrder.assign(done.rbegin(), done.rend());
+}
+
+void GpuContext::SetNeuralNetwork(NNNetwork* pNetwork)
+{
+    // E/GpuTypes.cpp:475-498: publish the network's hyper-parameters to the kernels
+    _pNetwork = pNetwork;
+    _data.bShuffleIndices = pNetwork->_bShuffleIndices && (pNetwork->_mode == Training);
+    _data.pShuffleIndex = pNetwork->_pbShuffleIndex ? pNetwork->_pbShuffleIndex->_pDevData : NULL;
+    _data.denoising_p = pNetwork->_denoising_p;
+    _data.denoising_q = 1.0f / (1.0f - pNetwork->_denoising_p);
+    _data.deltaBoost_one = pNetwork->_deltaBoost_one;
+    _data.deltaBoost_zero = pNetwork->_deltaBoost_zero;
+    _data.SMCE_oneTarget = pNetwork->_SMCE_oneTarget;
+    _data.SMCE_zeroTarget = pNetwork->_SMCE_zeroTarget;
+    _data.SMCE_oneScale = pNetwork->_SMCE_oneScale;
+    _data.SMCE_zeroScale = pNetwork->_SMCE_zeroScale;
+    CopyConstants();
+}
+
+void NNNetwork::ClearDataSets()
+{
+    _examples = 0; _bExamplesFound = false;
+    for (auto l : _vInputLayer) l->_pDataSet = NULL;
+    for (auto l : _vOutputLayer) l->_pDataSet = NULL;
+    _bDirty = true;
+}
+
+void NNNetwork::LoadDataSets(vector<NNDataSetBase*>& vData)
+{
+    _bAllDataLoaded = false;
+    auto attach = [&](NNLayer* l, bool isInput) {
+        for (auto d : vData) {
+            if (l->_dataSet.compare(d->_name) != 0) continue;
+            if (l->_Nx < d->_width || l->_Ny < d->_height || l->_Nz < d->_length) {
+                stringstream msg;
+                msg << "NNNetwork::LoadDataSets: Data element mismatch (" << l->_Nx << ", " << l->_Ny << ", " << l->_Nz << ") layer " << l->_name
+                    << " versus (" << d->_width << ", " << d->_height << ", " << d->_length << ") data set " << d->_name;
+                throw DsbEngineError(msg.str());
+            }
+            if (!_bExamplesFound) { _examples = d->_examples; _bExamplesFound = true; }
+            if (d->_examples != _examples) throw DsbEngineError("NNNetwork::LoadDataSets: Mismatched examples count in dataset " + d->_name);
+            l->_pDataSet = d;
+            if (isInput) l->_bSparse = d->_attributes & NNDataSetEnums::Sparse;      // input layer takes the sparseness of its data
+            l->_bDirty = true;
+            break;
+        }
+    };
+    for (auto l : _vInputLayer) attach(l, true);
+    for (auto l : _vOutputLayer) attach(l, false);
+    _vData = vData;
+    _bDirty = true;
+    _bAllDataLoaded = true;
+    for (auto l : _vInputLayer) if (!l->_pDataSet) _bAllDataLoaded = false;
+    for (auto l : _vOutputLayer) if (!l->_pDataSet) _bAllDataLoaded = false;
+}
+
+void NNNetwork::Randomize()
+{
+    for (auto w : _vWeight) w->Randomize();
+}
+
+void NNNetwork::SetBatch(uint32_t batch)
+{
+    if (batch != _batch) {
+        _batch = batch;
+        for (auto l : _vLayer) l->SetBatch(batch);
+        _bDirty = true;
+    }
+}
+
+void NNNetwork::SetPosition(uint32_t position)
+{
+    if (_bExamplesFound && position >= _examples) throw DsbEngineError("NNNetwork::SetPosition: Invalid position setting");
+    _position = position;
+}
+
+bool NNNetwork::SetDecay(NNFloat decay) { if (decay < 0.0f) return false; _decay = decay; return true; }
+
+void NNNetwork::SetTrainingMode(TrainingMode mode)
+{
+    if (_trainingMode != mode) { _trainingMode = mode; _bDirty = true; }
+}
+
+void NNNetwork::SetShuffleIndices(bool bShuffleIndices)
+{
+    if (_bShuffleIndices != bShuffleIndices) { _bShuffleIndices = bShuffleIndices; _bDirty = true; }
+}
+
+bool NNNetwork::SetSparsenessPenalty(NNFloat p, NNFloat beta)
+{
+    if (p < 0.0f || p > 1.0f) return false;
+    _sparsenessPenalty_p = p; _sparsenessPenalty_beta = beta; _bSparsenessPenalty = (beta > 0.0f); _bDirty = true;
+    return true;
+}
+
+bool NNNetwork::SetDenoising(NNFloat p)
+{
+    if (p < 0.0f || p >= 1.0f) return false;
+    if (_denoising_p != p) { _denoising_p = p; _bDenoising = (p > 0.0f); _bDirty = true; }
+    return true;
+}
+
+bool NNNetwork::SetDeltaBoost(NNFloat one, NNFloat zero)
+{
+    if (one < 0.0f || zero < 0.0f) return false;
+    _deltaBoost_one = one; _deltaBoost_zero = zero; _bDirty = true;
+    return true;
+}
+
+bool NNNetwork::SetSMCE(NNFloat oneTarget, NNFloat zeroTarget, NNFloat oneScale, NNFloat zeroScale)
+{
+    if (oneTarget < 0.0f || oneTarget > 1.0f || zeroTarget < 0.0f || zeroTarget > 1.0f || oneScale < 0.0f || zeroScale < 0.0f) return false;
+    _SMCE_oneTarget = oneTarget; _SMCE_zeroTarget = zeroTarget; _SMCE_oneScale = oneScale; _SMCE_zeroScale = zeroScale; _bDirty = true;
+    return true;
+}
+
+bool NNNetwork::SetCheckpoint(string name, int32_t interval)
+{
+    _checkpoint_name = name; _checkpoint_interval = interval;
+    return true;
+}
+
+NNLayer* NNNetwork::GetLayer(const string& layer) const
+{
+    auto it = _mLayer.find(layer);
+    return it == _mLayer.end() ? NULL : it->second;
+}
+
+vector<string> NNNetwork::GetLayers() const
+{
+    vector<string> v;
+    for (auto l : _vLayer) v.push_back(l->_name);
+    return v;
+}
+
+NNWeight* NNNetwork::GetWeight(const string& inputLayer, const string& outputLayer) const
+{
+    for (auto w : _vWeight)
+        if (w->_inputLayer._name == inputLayer && w->_outputLayer._name == outputLayer) return w;
+    return NULL;
+}
+
+uint64_t NNNetwork::GetBufferSize(const string& layer) const { NNLayer* l = GetLayer(layer); return l ? l->GetBufferSize() : 0; }
+NNFloat* NNNetwork::GetUnitBuffer(const string& layer) { NNLayer* l = GetLayer(layer); return l ? l->GetUnitBuffer() : NULL; }
+NNFloat* NNNetwork::GetDeltaBuffer(const string& layer) { NNLayer* l = GetLayer(layer); return l ? l->GetDeltaBuffer() : NULL; }
+NNFloat* NNNetwork::GetWeightBuffer(const string& inputLayer, const string& outputLayer)
+{
+    NNWeight* w = GetWeight(inputLayer, outputLayer);
+    return w ? w->GetWeightBuffer() : NULL;
+}
+
+bool NNNetwork::LockWeights(const string& inputLayer, const string& outputLayer)
+{
+    NNWeight* w = GetWeight(inputLayer, outputLayer);
+    if (!w) return false;
+    w->Lock();
+    return true;
+}
+
+bool NNNetwork::UnlockWeights(const string& inputLayer, const string& outputLayer)
+{
+    NNWeight* w = GetWeight(inputLayer, outputLayer);
+    if (!w) return false;
+    w->Unlock();
+    return true;
+}
+
+NNFloat* NNNetwork::GetScratchBuffer(size_t size)
+{
+    if (size > _scratchBufferSize) {
+        _pbScratchBuffer.reset(new GpuBuffer<NNFloat>(size));
+        _scratchBufferSize = size;
+    }
+    return _pbScratchBuffer ? _pbScratchBuffer->_pDevData : NULL;
+}
+
+NNFloat* NNNetwork::GetP2PSendBuffer() { return _pbP2PBuffer ? _pbP2PBuffer->_pDevData : NULL; }
+
+bool NNNetwork::P2P_Allreduce(NNFloat* pBuffer, size_t size)
+{
+    getGpu().Check(dsb200_all_reduce(getGpu()._ctx, pBuffer, size), "dsb200_all_reduce");
+    return true;
+}
+
+void NNNetwork::AddBuffers(NNFloat* pDst, NNFloat* pSrc, uint64_t size)
+{
+    getGpu().Check(dsb200_add_buffers(getGpu()._ctx, pDst, pSrc, size), "dsb200_add_buffers");
+}
+
+// E/NNNetwork.cpp:2666-2714: one full-width exchange buffer instead of two IPC-exported peer buffers
+void NNNetwork::AllocatePeerBuffers()
+{
+    if (getGpu()._numprocs <= 1) return;
+    _maxStride = 0;
+    for (auto w : _vWeight) {
+        const uint32_t stride = w->_bOutgoingLarger ? w->_inputLayer._stride : w->_outputLayer._stride;
+        _maxStride = max(_maxStride, stride);
+    }
+    const uint64_t need = (uint64_t)_maxStride * _batch;
+    if (!_pbP2PBuffer || _pbP2PBuffer->_length < need) _pbP2PBuffer.reset(new GpuBuffer<NNFloat>(need));
+}
+
+void NNNetwork::RefreshState()
+{
+    if (!_bAllDataLoaded) {
+        _bAllDataLoaded = true;
+        if (_mode != Prediction) for (auto l : _vOutputLayer) if (!l->_pDataSet) _bAllDataLoaded = false;
+        for (auto l : _vInputLayer) if (!l->_pDataSet) _bAllDataLoaded = false;
+    }
+    if (!_bAllDataLoaded) throw DsbEngineError("NNNetwork::RefreshState: Attempt to use neural network " + _name + " without providing data sets for all input and output layers");
+    // denoising_p > 0 turns the Denoising attribute on for sparse input layers at load time (E/NNNetwork.cpp:3705-3720)
+    for (auto l : _vLayer) if (l->_bDirty) l->RefreshState(this, _trainingMode, _mode == Validation);
+    for (auto w : _vWeight) w->RefreshState(this, _trainingMode);
+    if (_bShuffleIndices && _mode == Training) RefreshShuffleBuffers();
+    AllocatePeerBuffers();
+    // split-row workspace of the sparse-Z kernel: worst case one partial row per 64 nnz plus one per example
+    for (auto l : _vInputLayer) {
+        if (!l->_pDataSet || l->_vOutgoingLayer.empty()) continue;
+        l->_pDataSet->GenerateSparseTransposedMatrix(_batch, l);
+        uint32_t stride = 0;
+        for (auto o : l->_vOutgoingLayer) stride = max(stride, o->_stride);
+        const size_t items = (size_t)l->_pDataSet->_maxBatchNnz / 64 + _batch + 1;
+        getGpu().Check(dsb200_ctx_reserve(getGpu()._ctx, _batch, items * stride), "dsb200_ctx_reserve");
+    }
+    getGpu().SetNeuralNetwork(this);
+    _bDirty = false;
+}
+
+void NNNetwork::RefreshShuffleBuffers()
+{
+    if (_shuffleIndices != _examples || !_pbShuffleIndex) {
+        _shuffleIndices = _examples;
+        _vShuffleIndex.resize(_examples);
+        for (uint32_t i = 0; i < _examples; i++) _vShuffleIndex[i] = i;
+        _pbShuffleIndex.reset(new GpuBuffer<uint32_t>(_examples));
+        _pbShuffleIndex->Upload(_vShuffleIndex.data());
+    }
+}
+
+static inline uint64_t mix64(uint64_t z)
+{
+    z = (z ^ (z >> 30)) * 0xbf58476d1ce4e5b9ull;
+    z = (z ^ (z >> 27)) * 0x94d049bb133111ebull;
+    return z ^ (z >> 31);
+}
+
+// E/NNNetwork.cpp:826-907 shuffles with cuRAND keys + CUB sort on rank 0 and broadcasts the result; the
+// permutation is "parity unpinned" (SURVEY 8c).  Here: Fisher-Yates on the host from the counter-based
+// generator, identical on every rank; examples beyond the last full batch stay in place as in the reference.
+void NNNetwork::ShuffleIndices()
+{
+    RefreshShuffleBuffers();
+    const uint64_t key = mix64((uint64_t)getGpu()._seed ^ mix64(0x5f3759dfull + _shuffleEpoch++));
+    for (uint32_t i = _examples; i > 1; i--) {
+        const uint32_t j = (uint32_t)(mix64(key + (uint64_t)i * 0x9e3779b97f4a7c15ull) % i);
+        swap(_vShuffleIndex[i - 1], _vShuffleIndex[j]);
+    }
+    _pbShuffleIndex->Upload(_vShuffleIndex.data());
+}
+
+void NNNetwork::ClearUpdates()
+{
+    for (auto w : _vWeight) { w->_updateCount = 0; w->_bDeferredSparseGradient = false; }
+    for (auto l : _vLayer) l->ClearUpdates();
+}
+
+void NNNetwork::LoadBatch()
+{
+    uint32_t batch = _batch;
+    if (_position + batch > _examples) batch = _examples - _position;
+    for (auto l : _vInputLayer) {
+        switch (_mode) {
+        case Prediction: l->LoadPredictionBatch(_position, batch); break;
+        case Training:   l->LoadTrainingBatch(_position, batch); break;
+        case Validation: l->LoadValidationBatch(_position, batch); break;
+        default: throw DsbEngineError("NNNetwork::LoadBatch: unsupported mode");
+        }
+    }
+}
+
+void NNNetwork::PredictBatch(uint32_t layers)
+{
+    if (layers > _vLayer.size()) return;
+    if (_mode != Prediction) { _mode = Prediction; _bDirty = true; }
+    if (_bDirty) RefreshState();
+    uint32_t batch = _batch;
+    if (_position + batch > _examples) batch = _examples - _position;
+    ClearUpdates();
+    LoadBatch();
+    for (auto l : _vFPOrder) l->ForwardPropagate(_position, batch, false);
+}
+
+void NNNetwork::PredictTrainingBatch(uint32_t layers)
+{
+    if (layers > _vLayer.size()) return;
+    if (_bDirty) RefreshState();
+    uint32_t batch = _batch;
+    if (_position + batch > _examples) batch = _examples - _position;
+    LoadBatch();
+    for (auto l : _vFPOrder) l->ForwardPropagate(_position, batch, true);
+}
+
+NNFloat NNNetwork::ReadErrorAccumulator()
+{
+    RTERROR(cudaMemcpyAsync(_pbErrorAccumulator->_pSysData, _pbErrorAccumulator->_pDevData, sizeof(unsigned long long),
+                            cudaMemcpyDeviceToHost, getGpu().GetStream()), "ReadErrorAccumulator copy");
+    RTERROR(cudaStreamSynchronize(getGpu().GetStream()), "ReadErrorAccumulator sync");
+    return (NNFloat)((double)(long long)_pbErrorAccumulator->_pSysData[0] * (1.0 / 1073741824.0));
+}
+
+// asynchronous half of CalculateError: loss kernels (fused with activation + delta where possible) into the
+// device accumulator, cross-rank sum of the fixed-point words, copy to pinned memory, record the event
+void NNNetwork::LaunchError()
+{
+    uint32_t batch = _batch;
+    if (_position + batch > _examples) batch = _examples - _position;
+    cudaStream_t s = getGpu().GetStream();
+    RTERROR(cudaMemsetAsync(_pbErrorAccumulator->_pDevData, 0, sizeof(unsigned long long), s), "LaunchError memset");
+    for (auto l : _vOutputLayer) l->CalculateErrorAsync(_position, batch, _errorFunction, _pbErrorAccumulator->_pDevData);
+    if (getGpu()._numprocs > 1)
+        getGpu().Check(dsb200_all_reduce_u64(getGpu()._ctx, _pbErrorAccumulator->_pDevData, 1), "dsb200_all_reduce_u64");
+    RTERROR(cudaMemcpyAsync(_pbErrorAccumulator->_pSysData, _pbErrorAccumulator->_pDevData, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s),
+            "LaunchError copy");
+    RTERROR(cudaEventRecord(_errorEvent, s), "LaunchError event");
+}
+
+tuple<NNFloat, NNFloat> NNNetwork::CalculateError(NNFloat lambda, NNFloat lambda1)
+{
+    LaunchError();
+    RTERROR(cudaEventSynchronize(_errorEvent), "CalculateError event sync");
+    NNFloat error_training = (NNFloat)((double)(long long)_pbErrorAccumulator->_pSysData[0] * (1.0 / 1073741824.0));
+    NNFloat error_regularization = (NNFloat)0.0;
+    if (lambda != (NNFloat)0.0 || lambda1 != (NNFloat)0.0) {                 // E/NNNetwork.cpp:1724-1730
+        for (auto w : _vWeight) error_regularization += w->CalculateRegularizationError(lambda, lambda1);
+        if (getGpu()._numprocs > 1) {
+            NNFloat* tmp = GetScratchBuffer(1);
+            RTERROR(cudaMemcpyAsync(tmp, &error_regularization, sizeof(NNFloat), cudaMemcpyHostToDevice, getGpu().GetStream()), "reg upload");
+            P2P_Allreduce(tmp, 1);
+            RTERROR(cudaMemcpyAsync(&error_regularization, tmp, sizeof(NNFloat), cudaMemcpyDeviceToHost, getGpu().GetStream()), "reg download");
+            RTERROR(cudaStreamSynchronize(getGpu().GetStream()), "reg sync");
+        }
+    }
+    return make_tuple(error_training, error_regularization);
+}
+
+void NNNetwork::BackPropagate()
+{
+    uint32_t batch = _batch;
+    if (_position + batch > _examples) batch = _examples - _position;
+    for (auto l : _vBPOrder) {
+        switch (l->_kind) {
+        case NNLayer::Kind::Output:
+            l->CalculateOutputDelta(_position, batch, _errorFunction);
+            l->BackPropagate(_position, batch);
+            break;
+        case NNLayer::Kind::Hidden:
+            l->BackPropagate(_position, batch);
+            break;
+        default: break;
+        }
+    }
+}
+
+void NNNetwork::UpdateWeights(NNFloat alpha, NNFloat lambda, NNFloat lambda1, NNFloat mu, NNFloat mu1)
+{
+    uint32_t batch = _batch;
+    if (_position + batch > _examples) batch = _examples - _position;
+    for (int64_t i = (int64_t)_vWeight.size() - 1; i >= 0; i--)
+        _vWeight[i]->UpdateWeights(_trainingMode, batch, alpha, lambda, lambda1, mu, mu1, (NNFloat)_batches);
+}
+
+// Body of the minibatch loop of NNNetwork::Train (E/NNNetwork.cpp:1601-1650) for the batch at `position`.
+float NNNetwork::TrainStep(uint32_t position, NNFloat alpha, NNFloat lambda, NNFloat lambda1, NNFloat mu, NNFloat mu1, NNFloat* pRegularization)
+{
+    if (_mode != Training) { _mode = Training; _bDirty = true; }
+    if (_bDirty) RefreshState();
+    SetPosition(position);
+    ClearUpdates();
+    PredictTrainingBatch();
+    LaunchError();                                   // loss (+ output delta) kernels and the async read-back
+    BackPropagate();                                 // queued behind them; does not depend on the host seeing the loss
+    RTERROR(cudaEventSynchronize(_errorEvent), "TrainStep event sync");
+    NNFloat error_training = (NNFloat)((double)(long long)_pbErrorAccumulator->_pSysData[0] * (1.0 / 1073741824.0));
+    NNFloat error_regularization = (NNFloat)0.0;
+    if (lambda != (NNFloat)0.0 || lambda1 != (NNFloat)0.0)
+        for (auto w : _vWeight) error_regularization += w->CalculateRegularizationError(lambda, lambda1);
+    if (pRegularization) *pRegularization = error_regularization;
+
+    // divergence brake, E/NNNetwork.cpp:1617-1639
+    NNFloat step_alpha = (_decay <= 0.0) ? alpha : alpha * ((NNFloat)1.0 / ((NNFloat)1.0 + _decay * ((NNFloat)_batches)));
+    _movingAverage = 0.9 * _movingAverage + 0.1 * error_training;
+    if (_initSteps == 0) {
+        if (error_training > 2.0 * _movingAverage) {
+            _brakeSteps = 25;
+            if (getGpu()._id == 0) printf("NNNetwork::Train: Detected network divergence, attempting recovery.\n");
+        }
+    } else _initSteps--;
+    if (_brakeSteps > 0) { step_alpha *= (NNFloat)0.1; _brakeSteps--; }
+    if (_brakeSteps < 24) {
+        _batches++;                                  // before the update: Adam reads it (E/NNNetwork.cpp:1646-1649)
+        UpdateWeights(step_alpha, lambda, lambda1, mu, mu1);
+    }
+    return error_training;
+}
+
+float NNNetwork::Train(uint32_t epochs, NNFloat alpha, NNFloat lambda, NNFloat lambda1, NNFloat mu, NNFloat mu1)
+{
+    if (_mode != Training) { _mode = Training; _bDirty = true; }
+    if (_bDirty) RefreshState();
+    if (_trainingMode != SGD && _bClearVelocity) {
+        for (auto w : _vWeight) w->ClearVelocity();
+        _batches = 0;
+    }
+    NNFloat total_error_training = 0, total_error_regularization = 0;
+    NNFloat average_error_training = (NNFloat)FLT_MAX, average_error_regularization = 0;
+    _movingAverage = 0; _brakeSteps = 0; _initSteps = 100;
+
+    for (uint32_t epoch = 0; epoch < epochs; epoch++) {
+        auto const start = std::chrono::steady_clock::now();
+        total_error_training = 0; total_error_regularization = 0;
+        if (_bDenoising) for (auto l : _vInputLayer) if (l->_bDenoising) l->GenerateDenoisingData();
+        if (_bShuffleIndices) ShuffleIndices();
+        for (uint32_t pos = 0; pos < GetExamples(); pos += GetBatch()) {
+            NNFloat reg = 0;
+            const NNFloat error_training = TrainStep(pos, alpha, lambda, lambda1, mu, mu1, &reg);
+            uint32_t minibatch = GetBatch();
+            if (_examples - pos < minibatch) minibatch = _examples - pos;
+            total_error_training += error_training;
+            total_error_regularization += reg * minibatch;
+            if (_verbose && getGpu()._id == 0)
+                printf("NNNetwork::Train: Minibatch@%u, average error %f, (%f training, %f regularization), alpha %f\n", pos,
+                       error_training / minibatch + reg, error_training / minibatch, reg, alpha);
+        }
+        getGpu().Synchronize();
+        auto const end = std::chrono::steady_clock::now();
+        average_error_training = total_error_training / GetExamples();
+        average_error_regularization = total_error_regularization / GetExamples();
+        if (getGpu()._id == 0)
+            printf("NNNetwork::Train: Epoch %d, average error %f, average training error %f, average regularization error %f, elapsed time %fs\n",
+                   ++_epochs, average_error_training + average_error_regularization, average_error_training, average_error_regularization,
+                   std::chrono::duration<double>(end - start).count());
+        if (_checkpoint_interval > 0) {
+            _checkpoint_epochs++;
+            if (_checkpoint_epochs >= _checkpoint_interval) {
+                string filename = _checkpoint_name + to_string(_epochs) + ".nc";
+                if (getGpu()._id == 0) printf("NNNetwork::Train: saving checkpoint %s\n", filename.c_str());
+                SaveNetCDF(filename);
+                _checkpoint_epochs = 0;
+            }
+        }
+    }
+    return average_error_training + average_error_regularization;
+}
+
+bool NNNetwork::Validate()
+{
+    throw DsbEngineError("NNNetwork::Validate: the finite-difference gradient check is re-hosted on the CPU oracle "
+                         "(tests/test_oracle_gradcheck.py) -- it forces the dense input path, which is outside the hot path");
+}
+
+// E/NNNetwork.cpp:1792-1822.  The reference caps k at 128 here; the kernel behind this takes k <= 1024.
+void NNNetwork::CalculateTopK(const string& layer, uint32_t k, GpuBuffer<NNFloat>* pbKey, GpuBuffer<uint32_t>* pbValue)
+{
+    CalculateTopKFiltered(layer, k, NULL, pbKey, pbValue);
+}
+
+void NNNetwork::CalculateTopKFiltered(const string& layer, uint32_t k, NNDataSetBase* pFilter, GpuBuffer<NNFloat>* pbKey, GpuBuffer<uint32_t>* pbValue)
+{
+    NNLayer* pLayer = GetLayer(layer);
+    if (!pLayer) { if (getGpu()._id == 0) printf("NNNetwork::CalculateTopK: Unknown layer %s.\n", layer.c_str()); return; }
+    uint32_t batch = _batch;
+    if (_position + batch > _examples) batch = _examples - _position;
+    if (!pbKey || !pbValue || pbKey->_length < (size_t)batch * k || pbValue->_length < (size_t)batch * k)
+        throw DsbEngineError("NNNetwork::CalculateTopK: output buffers are too small");
+    const uint64_t* fs = NULL; const uint64_t* fe = NULL; const uint32_t* fi = NULL;
+    if (pFilter) {
+        // the filter dataset is addressed by absolute example: offset the start / end tables to the batch
+        fs = pFilter->_pbSparseStart->_pDevData + _position;
+        fe = pFilter->_pbSparseEnd->_pDevData + _position;
+        fi = pFilter->_pbSparseIndex->_pDevData;
+    }
+    getGpu().Check(dsb200_topk(getGpu()._ctx, pLayer->GetUnitBuffer(), batch, pLayer->_localStride, k, fs, fe, fi, pbKey->_pDevData, pbValue->_pDevData),
+                   "dsb200_topk");
+}

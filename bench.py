@@ -1,0 +1,354 @@
+#!/usr/bin/env python
+"""bench.py -- headline benchmark of the dsstne_b200 hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--workload c2|c4]
+
+A "step" is one minibatch of NNNetwork::Train (transposed build, sparse-Z forward, dense layers,
+fused sigmoid + SMCE loss + delta, backward GEMMs, sparse gradient fused with the optimizer, bias
+updates) on BASELINE.json config 2: the MovieLens-20M-shape sparse autoencoder
+27,278 -> 128 -> 128 -> 128 -> 27,278, batch 1,024, synthetic CSR at ML-20M density, SGD.
+N > 1 (torchrun, one rank per GPU) runs the SAME model model-parallel (config 3): layers split by
+unit, NCCL reduce-scatter / all-gather per layer boundary -> strong scaling.
+
+Prints ONE JSON line (rank 0).  `value` = samples/s with the dataset resident in HBM; `e2e` = the
+same through the host-buffer API (each step uploads its CSR batch from pinned host memory with
+NNDataSet::LoadSparseData and reads the loss back); `roofline` = achieved algorithmic GB/s of the
+dominant hand-written kernel (CUDA events inside the timed steps) against MEASURED_PEAKS.json;
+`cpu_baseline` = the OpenMP CPU oracle on a bounded sample of the same workload.
+`--impl reference` times the CPU oracle only (the reference has no CPU path and its full build needs
+MPI/NetCDF/jsoncpp) with all host threads.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "sparse-AE train samples/s"
+UNIT = "samples/s"
+HYPER = dict(alpha=0.025, lam=1e-4, lam1=0.0, mu=0.5, mu1=0.0)     # CLI defaults of U/Train.cpp:62-66
+SMCE = (1.0, 0.0, 1.0, 1.0)                                        # samples/movielens/config.json
+
+
+def workload(name):
+    if name == "c2":
+        return dict(name="c2", items=27278, hidden=[128, 128, 128], batch=1024, mean_nnz=144.4,
+                    desc="BASELINE config 2: ML-20M-shape AE 27278-128-128-128-27278, batch 1024, sigmoid/SMCE(1,0,1,1), SGD, "
+                         "synthetic CSR (log-normal rows mean 144.4, Zipf-Mandelbrot columns)")
+    if name == "c4":
+        return dict(name="c4", items=1000000, hidden=[1024, 1024, 1024], batch=1024, mean_nnz=144.4,
+                    desc="BASELINE config 4: 1M-item AE 1M-1024-1024-1024-1M, batch 1024, model parallel")
+    raise SystemExit(f"unknown workload {name}")
+
+
+def make_data(wl, batches, seed=12134):
+    from dsstne_b200 import datagen
+    return datagen.make_csr(wl["batch"] * batches, wl["items"], wl["mean_nnz"], dist="lognormal", col="zipf", seed=seed)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks + throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, device):
+        super().__init__(daemon=True)
+        self.device, self.rows, self.stop_flag = device, [], False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.device), f"--query-gpu={self.Q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            for i, n in enumerate(names):
+                if len(r) > 4 + i and r[4 + i].lower().startswith("active"):
+                    reasons.add(n)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+def algorithmic_bytes(wl, nnz_batch, P=1):
+    """SURVEY.md section 8d per-launch ALGORITHMIC bytes of each hand-written kernel family (fp32)."""
+    B, N, S = wl["batch"], wl["items"] // P, wl["hidden"][0]
+    return {
+        # gathered weight rows + Z write (bias read) + indices + start/end
+        "sparse_z_bias_act": 4 * S * nnz_batch + 4 * B * S + 4 * nnz_batch + 16 * B,
+        "sparse_z": 4 * S * nnz_batch + 2 * 4 * B * S + 4 * nnz_batch + 16 * B,
+        # CSR read + TIndex write + End init/final
+        "sparse_transpose": 4 * nnz_batch + 16 * B + 4 * nnz_batch + 8 * N,
+        # gathered delta rows + W read/write (fused SGD: no dW) + TIndex + start/end
+        "sparse_wgrad_update": 4 * S * nnz_batch + 2 * 4 * S * N + 4 * nnz_batch + 8 * N,
+        "sparse_wgrad": 4 * S * nnz_batch + 4 * S * N + 4 * nnz_batch + 8 * N,
+        # read Z, write unit (in place), write delta + target CSR
+        "output_pass": 3 * 4 * B * N + 4 * nnz_batch + 16 * B,
+        # read g, read w, write w
+        "update_weights": 3 * 4 * wl["hidden"][-1] * N,
+        # delta read (dominated by the output layer) + bias r/w
+        "update_biases": 4 * B * N + 8 * N,
+    }
+
+
+def run_ours(args, wl, rank, world, local_rank):
+    import torch
+    import dsstne_b200
+    from dsstne_b200 import engine
+    dsstne_b200.lib()                                  # fails loudly when the CUDA extension is missing
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the dsstne_b200 path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    nccl_id = None
+    if world > 1:
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        buf = torch.zeros(128, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            buf = torch.tensor(list(engine.unique_id()), dtype=torch.uint8, device="cuda")
+        dist.broadcast(buf, 0)
+        nccl_id = bytes(buf.cpu().tolist())
+    engine.startup(rank, world, local_rank, nccl_id, seed=12134)
+    stream = torch.cuda.Stream(local_rank)
+    torch.cuda.set_stream(stream)
+    engine.set_stream(stream.cuda_stream)
+
+    n_batches = 16 if wl["name"] == "c2" else 4
+    data = make_data(wl, n_batches)
+    B = wl["batch"]
+    ds_in = engine.Dataset.from_host_csr("gl_input", data)
+    ds_out = engine.Dataset.from_host_csr("gl_output", data)
+    net = engine.Network(engine.autoencoder_json(wl["hidden"], smce=SMCE, init=("Gaussian", 0.01, 0.0)), B, [ds_in, ds_out])
+    net.set_training_mode(dsstne_b200.SGD)
+    net.set_gemm_mode(args.gemm_mode)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def step(i):
+        return net.train_step((i % n_batches) * B, HYPER["alpha"], HYPER["lam"], HYPER["lam1"], HYPER["mu"], HYPER["mu1"])
+
+    for i in range(args.warmup):
+        step(i)
+    barrier()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+    launches0 = dsstne_b200.lib().dsb200_launch_count()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    loss = 0.0
+    for i in range(args.steps):
+        loss = step(args.warmup + i)
+    ev1.record(stream)
+    barrier()
+    ms = ev0.elapsed_time(ev1)
+    launches = dsstne_b200.lib().dsb200_launch_count() - launches0
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms], device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    sampler.stop_flag = True
+
+    # ---- per-kernel device time inside the same steps (second pass with event pairs on) ----
+    engine.set_option("profile", 1)
+    pk0, pk1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    prof_steps = min(args.steps, 20)
+    barrier()
+    pk0.record(stream)
+    for i in range(prof_steps):
+        step(i)
+    pk1.record(stream)
+    barrier()
+    prof = engine.profile_report()
+    engine.set_option("profile", 0)
+    prof_ms = pk0.elapsed_time(pk1)
+
+    # ---- e2e: host buffers in, loss out, through the reference-facing API every step ----
+    e2e = None
+    if world == 1:
+        e2e = run_e2e(args, wl, data, engine, dsstne_b200, stream)
+
+    result = None
+    if rank == 0:
+        nnz_batch = data.nnz / n_batches
+        alg = algorithmic_bytes(wl, nnz_batch, world)
+        peak, peak_src = peaks()
+        kern = {}
+        for name, (calls, tot) in prof.items():
+            per = tot / max(calls, 1)
+            kern[name] = {"calls_per_step": calls / prof_steps, "ms_per_call": round(per, 5), "share": round(tot / prof_ms, 4)}
+            if name in alg:
+                kern[name]["algorithmic_GBs"] = round(alg[name] / (per * 1e-3) / 1e9, 1)
+        ours = {k: v for k, v in kern.items() if k in alg}
+        dom = max(ours, key=lambda k: ours[k]["share"]) if ours else None
+        roof = None
+        if dom:
+            a = ours[dom]["algorithmic_GBs"]
+            roof = {"kernel": dom, "bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": round(a / peak, 4),
+                    "traffic": None, "peak_source": peak_src, "share_of_step": ours[dom]["share"],
+                    "algorithmic_bytes_per_launch": int(alg[dom])}
+        value = args.steps * B / (ms * 1e-3)
+        result = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+                  "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+                  "dtype": "f32", "data": "synthetic",
+                  "config": {"workload": wl["desc"], "parallelism": "single GPU" if world == 1 else f"model-parallel mp{world} (NCCL)",
+                             "gemm": ["cuBLAS fp32 (pedantic)", "cuBLAS tf32", "tcgen05 3xTF32"][args.gemm_mode],
+                             "l2": "no explicit flush: every step streams >= 3 x 112 MB of output-layer Z/delta through the 126 MB L2 "
+                                   "and a different CSR batch; weights stay L2-resident exactly as in real training",
+                             "last_loss": round(float(loss), 3)},
+                  "clocks": sampler.summary(), "gpu_launches": int(launches), "roofline": roof, "kernels": kern}
+        if e2e:
+            result["e2e"] = e2e
+        result["cpu_baseline"] = cpu_baseline(wl, data, sample_steps=args.cpu_steps)
+    net.close()
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+        dist.destroy_process_group()
+    engine.shutdown()
+    return result
+
+
+def run_e2e(args, wl, data, engine, dsstne_b200, stream):
+    """Host-buffer path: per step, the CSR batch goes pinned host -> device through NNDataSet::LoadSparseData
+    (the call the reference's JNI binding makes per request) and the loss comes back to the host."""
+    import torch
+    from dsstne_b200 import datagen
+    B = wl["batch"]
+    n_batches = data.examples // B
+    # carve per-batch CSRs (zero-based starts) out of the synthetic dataset, pinned
+    batches = []
+    for b in range(n_batches):
+        s0 = int(data.start[b * B])
+        st = (data.start[b * B:(b + 1) * B] - np.uint64(s0)).astype(np.uint64)
+        en = (data.end[b * B:(b + 1) * B] - np.uint64(s0)).astype(np.uint64)
+        ix = data.index[s0:int(data.end[(b + 1) * B - 1])]
+        batches.append((st, en, np.ascontiguousarray(ix)))
+    big = max(batches, key=lambda b: len(b[2]))       # capacity of an NNDataSet is fixed at construction: size it for the largest batch
+    first = datagen.HostCsr(big[0], big[1], big[2], wl["items"])
+    ds_in = engine.Dataset("gl_input", first.start, first.end, first.index, wl["items"])
+    ds_out = engine.Dataset("gl_output", first.start, first.end, first.index, wl["items"])
+    net = engine.Network(engine.autoencoder_json(wl["hidden"], smce=SMCE, init=("Gaussian", 0.01, 0.0)), B, [ds_in, ds_out])
+    net.set_training_mode(dsstne_b200.SGD)
+    net.set_gemm_mode(args.gemm_mode)
+    h2d = d2h = 0
+
+    def step(i):
+        nonlocal h2d, d2h
+        st, en, ix = batches[i % n_batches]
+        ds_in.load_sparse(st, en, ix)
+        ds_out.load_sparse(st, en, ix)
+        h2d = 2 * (st.nbytes + en.nbytes + ix.nbytes)
+        d2h = 8
+        return net.train_step(0, HYPER["alpha"], HYPER["lam"], HYPER["lam1"], HYPER["mu"], HYPER["mu1"])
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        step(i)
+    torch.cuda.synchronize()
+    dt = time.perf_counter() - t0
+    net.close()
+    return {"value": round(args.steps * B / dt, 1), "unit": UNIT, "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": int(d2h),
+            "ms_per_step": round(dt / args.steps * 1e3, 4),
+            "path": "NNDataSet::LoadSparseData (pinned host CSR batch -> device) + NNNetwork train step + loss read-back, every step"}
+
+
+def cpu_baseline(wl, data, sample_steps=3):
+    """OpenMP CPU oracle (oracle/liboracle.so, a restatement -- the reference has no CPU path) on a bounded
+    sample of the same workload: `sample_steps` minibatches of the same network and data."""
+    from oracle import oracle as orc
+    from dsstne_b200 import datagen
+    B = wl["batch"]
+    sizes = [wl["items"]] + wl["hidden"] + [wl["items"]]
+    net = orc.Network(sizes, error=orc.ERR_SMCE, mode=orc.SGD, max_batch=B)
+    Ws, bs = datagen.make_weights(sizes, scale=0.01)
+    for i in range(len(sizes) - 1):
+        net.W(i)[:] = Ws[i]
+        net.b(i)[:] = bs[i]
+    net.s.params = orc.make_params(smce=SMCE)
+    sub = datagen.HostCsr(data.start[:B * 2], data.end[:B * 2], data.index[:int(data.end[B * 2 - 1])], wl["items"])
+    oc = orc.Csr(sub.start, sub.end, sub.index)
+    net.set_input(oc, B)
+    net.train_step(oc, oc, 0, B, HYPER["alpha"], HYPER["lam"])          # warm-up (page faults, thread pool)
+    t0 = time.perf_counter()
+    for i in range(sample_steps):
+        net.train_step(oc, oc, (i % 2) * B, B, HYPER["alpha"], HYPER["lam"])
+    dt = time.perf_counter() - t0
+    net.close()
+    return {"value": round(sample_steps * B / dt, 1), "unit": UNIT, "cores": orc.num_threads(), "kind": "port",
+            "sample": f"{sample_steps} minibatches of {B} examples of the same workload (after 1 warm-up), OpenMP C oracle, fp32",
+            "ms_per_step": round(dt / sample_steps * 1e3, 1)}
+
+
+def run_reference(args, wl, rank):
+    """--impl reference: the CPU arm.  The reference has no CPU implementation of this path and its full build needs
+    MPI / NetCDF-C++4 / jsoncpp (absent), so this arm times the CPU oracle port with all host threads."""
+    if rank != 0:
+        return None
+    data = make_data(wl, 2)
+    steps = max(1, min(args.steps, 5))
+    cb = cpu_baseline(wl, data, sample_steps=steps)
+    return {"impl": "reference", "metric": METRIC, "value": cb["value"], "unit": UNIT, "n_gpus": args.gpus, "steps": steps,
+            "warmup": 1, "ms_per_step": cb["ms_per_step"], "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": {"workload": wl["desc"]},
+            "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=100)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="c2", choices=["c2", "c4"])
+    ap.add_argument("--gemm-mode", type=int, default=0, help="0 cuBLAS fp32, 1 cuBLAS tf32, 2 tcgen05 3xTF32")
+    ap.add_argument("--cpu-steps", type=int, default=3)
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    wl = workload(args.workload)
+    if args.impl == "reference":
+        res = run_reference(args, wl, rank)
+    else:
+        if world != args.gpus and world == 1 and args.gpus > 1:
+            raise SystemExit("bench.py: --gpus N > 1 must be launched with torch.distributed.run (one rank per GPU)")
+        res = run_ours(args, wl, rank, world, local_rank)
+    if rank == 0 and res is not None:
+        print(json.dumps(res), flush=True)
+
+
+if __name__ == "__main__":
+    main()

@@ -103,11 +103,16 @@ int  dsb200_ctx_set_option(dsb200_ctx* ctx, const char* name, int value);  /* "n
 int  dsb200_ctx_sync(dsb200_ctx* ctx);
 const char* dsb200_last_error(dsb200_ctx* ctx);
 uint64_t dsb200_launch_count(void);      /* kernels of this library launched so far */
+/* with option "profile" = 1 every kernel entry is bracketed by CUDA events on the stream; this call
+ * synchronises and writes one line per family, "name calls total_ms\n", then clears the records */
+int  dsb200_profile_report(dsb200_ctx* ctx, char* buf, size_t cap);
 
 /* ------------------------------------------------------------------ a14
  * kClearUnit / kAddBias, E/kernels.h:30,26 (E/kernels.cu:60-80, 564-584)          */
 int dsb200_clear_unit(dsb200_ctx*, float* pUnit, const float* pBias, uint32_t stride, uint32_t batch);
 int dsb200_add_bias(dsb200_ctx*, float* pUnit, const float* pBias, uint32_t stride, uint32_t batch);
+/* kAddBuffers, E/kernels.h:45 (E/kernels.cu:39-57): pDst[i] += pSrc[i] */
+int dsb200_add_buffers(dsb200_ctx*, float* pDst, const float* pSrc, uint64_t size);
 
 /* ------------------------------------------------------------------ a1-a3
  * kCalculate[Indexed]Sparse[Analog][Denoised]Z, E/kernels.h:67-74 (E/kernels.cu:662-1977).
@@ -215,6 +220,12 @@ int dsb200_topk(dsb200_ctx*, const float* pScores, uint32_t batch, uint32_t widt
                 float* pOutKey, uint32_t* pOutValue);
 int dsb200_topk_kv(dsb200_ctx*, const float* pKey, const uint32_t* pValue, uint32_t batch, uint32_t width, uint32_t k,
                    float* pOutKey, uint32_t* pOutValue);
+
+/* ------------------------------------------------------------------ denoising randoms ("next" row 4)
+ * replaces the whole-dataset curandGenerateUniform fill of NNDataSet::GenerateDenoisingData
+ * (E/NNTypes.cpp:1617-1629): counter-based generator, pOut[i] = U(0,1] as a pure function of
+ * (seed, stream, i) -- reproducible for any launch geometry.                                    */
+int dsb200_fill_uniform(dsb200_ctx*, float* pOut, uint64_t n, uint64_t seed, uint64_t stream);
 
 /* ------------------------------------------------------------------ a15
  * NNLayer::Reduce / Gather and NNNetwork::P2P_Allreduce (E/NNLayer.cpp:2702-2826,

@@ -1,0 +1,182 @@
+"""GPU parity of the C++ host engine (NNNetwork / NNLayer / NNWeight / NNDataSet mirror, driven through
+include/dsstne_b200_engine.h) against the whole-network CPU oracle (orc_net_*), on BASELINE.json
+config 1 (2,048 -> 128 -> 2,048 sparse autoencoder, batch 256) and small multi-layer variants.
+Tolerance: 1e-5 relative (helpers.rel_err) for losses, activations, deltas and updated weights.
+"""
+import numpy as np
+import pytest
+
+from helpers import rel_err, tiny, to_oracle
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+MODES = ["SGD", "Momentum", "AdaGrad", "Nesterov", "RMSProp", "AdaDelta", "Adam"]
+
+
+@pytest.fixture(scope="module")
+def eng(dsb):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.skip("no GPU")
+    from dsstne_b200 import engine
+    engine.startup(0, 1, 0, None, seed=12134)
+    engine.use_torch_stream(0)
+    yield engine
+    engine.shutdown()
+
+
+def mix64(z):
+    z = np.asarray(z, dtype=np.uint64)
+    with np.errstate(over="ignore"):
+        z = (z ^ (z >> np.uint64(30))) * np.uint64(0xbf58476d1ce4e5b9)
+        z = (z ^ (z >> np.uint64(27))) * np.uint64(0x94d049bb133111eb)
+        return z ^ (z >> np.uint64(31))
+
+
+def fill_uniform_host(n, seed, stream):
+    """numpy restatement of dsb200_fill_uniform (csrc/random.cu): U(0,1] from (seed, stream, i)."""
+    with np.errstate(over="ignore"):
+        key = mix64(np.uint64(seed) ^ mix64(np.uint64(stream) + np.uint64(0x9e3779b97f4a7c15)))
+        r = mix64(key + np.arange(n, dtype=np.uint64) * np.uint64(0x9e3779b97f4a7c15))
+    return ((r >> np.uint64(40)).astype(np.float32) + np.float32(1.0)) * np.float32(1.0 / 16777216.0)
+
+
+def build_pair(eng, orc, sizes, h, batch, mode, error="ScaledMarginalCrossEntropy", smce=(1.0, 0.0, 1.0, 1.0), denoising_p=0.0,
+               sparseness=None, fusion=True):
+    from dsstne_b200 import datagen
+    hidden = sizes[1:-1]
+    ds_in = eng.Dataset.from_host_csr("gl_input", h)
+    ds_out = eng.Dataset.from_host_csr("gl_output", h)
+    net = eng.Network(eng.autoencoder_json(hidden, error=error, smce=smce, denoising_p=denoising_p, sparseness=sparseness),
+                      batch, [ds_in, ds_out])
+    net.set_training_mode(mode)
+    net.set_fusion(fusion)
+    Ws, bs = datagen.make_weights(sizes, scale=0.05)
+    names = ["Input"] + [f"Hidden{i + 1}" for i in range(len(hidden))] + ["Output"]
+    for i in range(len(sizes) - 1):
+        bs[i][:] = np.random.default_rng(i).standard_normal(bs[i].shape).astype(np.float32) * 0.1
+        net.set_weights(names[i], names[i + 1], Ws[i], bs[i])
+    ef = {"ScaledMarginalCrossEntropy": orc.ERR_SMCE, "CrossEntropy": orc.ERR_CE, "L2": orc.ERR_L2}[error]
+    onet = orc.Network(sizes, error=ef, mode=mode, max_batch=batch)
+    for i in range(len(sizes) - 1):
+        onet.W(i)[:] = Ws[i]
+        onet.b(i)[:] = bs[i]
+    onet.s.params = orc.make_params(denoising_p=denoising_p, smce=(smce[0], smce[1], smce[2], smce[3]))
+    if sparseness is not None:
+        onet.s.sparsenessPenalty_p, onet.s.sparsenessPenalty_beta = sparseness
+        for l in range(1, len(sizes) - 1):
+            onet.s.sparsePenalty[l] = 1
+    onet.s.denoising = 1 if denoising_p > 0 else 0
+    return net, onet, names, (ds_in, ds_out)
+
+
+@pytest.mark.parametrize("mode", range(7), ids=MODES)
+def test_config1_train_steps_match_oracle(eng, orc, mode):
+    sizes, batch = [2048, 128, 2048], 256
+    h = tiny(examples=512, width=2048)
+    net, onet, names, _ = build_pair(eng, orc, sizes, h, batch, mode)
+    oc = to_oracle(orc, h)
+    onet.set_input(oc, batch)
+    hp = dict(alpha=0.025, lam=1e-4, lam1=0.0, mu=0.5, mu1=0.999)
+    for step, pos in enumerate([0, 256, 0]):
+        got = net.train_step(pos, hp["alpha"], hp["lam"], hp["lam1"], hp["mu"], hp["mu1"])
+        want, _ = onet.train_step(oc, oc, pos, batch, hp["alpha"], hp["lam"], hp["lam1"], hp["mu"], hp["mu1"])
+        assert abs(got - want) <= TOL * abs(want), f"loss at step {step}"
+    # AdaGrad / RMSProp / Adam divide by sqrt(v) clamped at 1e-9 (1e-8 for Adam): a weight whose gradient is at
+    # rounding-noise level gets that noise multiplied by up to alpha * 3e4 (alpha * 1e8 for Adam), so two exact fp32
+    # implementations that sum the dense GEMMs in a different order (cuBLAS vs the oracle's loops) legitimately differ
+    # by more than 1e-5 after a few steps.  With identical gradients the kernels agree to 1e-5 for every mode
+    # (test_gpu_kernels.py::test_update_weights_and_biases, ::test_sparse_wgrad_update_fused_equals_unfused).
+    tol = {orc.ADAGRAD: 2e-4, orc.RMSPROP: 2e-4, orc.ADAM: 2e-3}.get(mode, TOL)
+    for i in range(2):
+        W, b = net.get_weights(names[i], names[i + 1])
+        assert rel_err(W.reshape(onet.W(i).shape), onet.W(i)) < tol
+        assert rel_err(b, onet.b(i)) < max(tol, 5e-5)          # column means are summed in tree order on the GPU
+    net.close()
+
+
+@pytest.mark.parametrize("error", ["ScaledMarginalCrossEntropy", "CrossEntropy", "L2"])
+def test_three_hidden_layers_with_penalty(eng, orc, error):
+    sizes, batch = [2048, 128, 64, 128, 2048], 128
+    h = tiny(examples=256, width=2048)
+    net, onet, names, _ = build_pair(eng, orc, sizes, h, batch, orc.SGD, error=error, sparseness=(0.5, 2.0))
+    oc = to_oracle(orc, h)
+    onet.set_input(oc, batch)
+    for pos in (0, 128):
+        got = net.train_step(pos, 0.05)
+        want, _ = onet.train_step(oc, oc, pos, batch, 0.05)
+        assert abs(got - want) <= TOL * abs(want)
+    for i in range(len(sizes) - 1):
+        W, b = net.get_weights(names[i], names[i + 1])
+        assert rel_err(W.reshape(onet.W(i).shape), onet.W(i)) < TOL
+    # hidden activations and deltas of the last step
+    for l in range(1, len(sizes) - 1):
+        u = net.get_units(names[l]).reshape(batch, sizes[l])
+        assert rel_err(u, onet.unit(l, batch)) < TOL
+    net.close()
+
+
+def test_fused_and_unfused_engine_agree(eng, orc):
+    sizes, batch = [2048, 128, 2048], 256
+    h = tiny(examples=256, width=2048)
+    res = []
+    for fusion in (True, False):
+        net, _, names, _ = build_pair(eng, orc, sizes, h, batch, orc.MOMENTUM, fusion=fusion)
+        losses = [net.train_step(0, 0.025, 1e-4, 0.0, 0.5, 0.0) for _ in range(3)]
+        res.append((losses, [net.get_weights(names[i], names[i + 1]) for i in range(2)]))
+        net.close()
+    for a, b in zip(res[0][0], res[1][0]):
+        assert abs(a - b) <= 1e-6 * abs(b)
+    for (Wa, ba), (Wb, bb) in zip(res[0][1], res[1][1]):
+        assert rel_err(Wa, Wb) < 1e-6
+        assert rel_err(ba, bb) < 1e-6
+
+
+def test_denoising_uses_the_counter_based_generator(eng, orc):
+    """Train(1 epoch) with Denoising p=0.2: the engine draws its randoms from dsb200_fill_uniform; the oracle is
+    fed the numpy restatement of that generator, so the epoch must agree end to end."""
+    sizes, batch = [2048, 128, 2048], 256
+    h = tiny(examples=512, width=2048)
+    net, onet, names, _ = build_pair(eng, orc, sizes, h, batch, orc.SGD, denoising_p=0.2)
+    rnd = fill_uniform_host(h.nnz, 12134, 0)
+    oc = to_oracle(orc, h, random=rnd)
+    onet.set_input(oc, batch)
+    got = net.train(1, 0.025)
+    tot = 0.0
+    for pos in (0, 256):
+        e, _ = onet.train_step(oc, to_oracle(orc, h), pos, batch, 0.025)
+        tot += e
+    want = tot / 512
+    assert abs(got - want) <= TOL * abs(want)
+    W, _ = net.get_weights(names[0], names[1])
+    assert rel_err(W.reshape(onet.W(0).shape), onet.W(0)) < TOL
+    net.close()
+
+
+def test_predict_and_topk_with_filter(eng, orc):
+    sizes, batch = [2048, 128, 2048], 256
+    h = tiny(examples=256, width=2048)
+    net, onet, names, (ds_in, _) = build_pair(eng, orc, sizes, h, batch, orc.SGD)
+    oc = to_oracle(orc, h)
+    net.set_position(0)
+    net.predict_batch()
+    onet.forward(oc, 0, batch)
+    scores = net.get_units("Output").reshape(batch, 2048)
+    assert rel_err(scores, onet.unit(2, batch)) < TOL
+    key, val = net.topk("Output", 100, batch, filt=ds_in)
+    want_k, want_v = orc.topk(scores, 100, filt=(h.start, h.end, h.index))     # same scores: selection must be exact
+    np.testing.assert_array_equal(key, want_k)
+    np.testing.assert_array_equal(val, want_v)
+    net.close()
+
+
+def test_engine_rejects_features_outside_the_hot_path(eng):
+    from dsstne_b200 import DsbError
+    h = tiny(examples=64, width=256)
+    ds = eng.Dataset.from_host_csr("gl_input", h)
+    bad = '{"Version":0.8,"Layers":[{"Kind":"Input","N":"auto","DataSet":"gl_input","Sparse":true},' \
+          '{"Kind":"Hidden","Type":"Convolutional","N":16},{"Kind":"Output","N":"auto","DataSet":"gl_input","Sparse":true}]}'
+    with pytest.raises(DsbError):
+        eng.Network(bad, 32, [ds])
+    with pytest.raises(DsbError):
+        eng.Network('{"Version":0.8,"Bogus":1,"Layers":[]}', 32, [ds])        # unknown key is fatal, as in the reference
