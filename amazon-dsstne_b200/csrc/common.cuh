@@ -48,6 +48,7 @@ struct dsb200_ctx {
     int            rank = 0, nranks = 1;
     void*          cublas      = nullptr;         // cublasHandle_t (fp32 GEMM fallback / reference arm)
     int            gemmMode    = 0;
+    int            fastMath    = 1;               // option "fast_math": MUFU exp/log/rcp in the output pass (default on)
     int            profile     = 0;               // option "profile": event pairs around every kernel entry
     char           lastError[256];
 };

@@ -218,6 +218,21 @@ int dsb200_update_biases(dsb200_ctx* ctx, int mode, float alpha, float mu, float
     }
 }
 
+int dsb200_regularization_error_async(dsb200_ctx* ctx, float lambda, float lambda1, const float* w, uint64_t size, unsigned long long* pDevAcc)
+{
+    DSB_PROFILE(ctx, "regularization_error");
+    using namespace dsb;
+    if (!ctx || !w || !pDevAcc) return fail(ctx, DSB200_EINVAL, "regularization_error_async: null argument");
+    if (!size) return 0;
+    uint64_t blocks = (size + 255) / 256;
+    const uint64_t cap = (uint64_t)ctx->numSMs * 8;
+    if (blocks > cap) blocks = cap;
+    regularization_kernel<<<(unsigned)blocks, 256, 0, ctx->stream>>>(0.5f * lambda, lambda1, w, size, pDevAcc);
+    count_launch();
+    DSB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 int dsb200_regularization_error(dsb200_ctx* ctx, float lambda, float lambda1, const float* w, uint64_t size, float* out)
 {
     DSB_PROFILE(ctx, "regularization_error");

@@ -32,12 +32,19 @@ struct OArgs {
     float* delta;           // optional
     unsigned long long* acc;// optional
     float slope, alpha, lambda;
+    int fast;               // option "fast_math": ex2/lg2/rcp approximations (what the reference's -use_fast_math build runs)
 };
 
-__device__ __forceinline__ float act_forward(int act, float z, float slope, float alpha, float lambda)
+// exp / log / reciprocal: accurate libdevice versions, or the MUFU approximations (relative error ~1e-6 on this
+// path's value ranges, well inside the 1e-5 parity bound) which take the pass from instruction-bound to HBM-bound
+__device__ __forceinline__ float dexp(float x, int fast) { return fast ? __expf(x) : expf(x); }
+__device__ __forceinline__ float dlog(float x, int fast) { return fast ? __logf(x) : logf(x); }
+__device__ __forceinline__ float drcp(float x, int fast) { return fast ? __frcp_rn(x) : 1.0f / x; }
+
+__device__ __forceinline__ float act_forward(int act, float z, float slope, float alpha, float lambda, int fast)
 {
     switch (act) {
-    case DSB200_ACT_SIGMOID: return 1.0f / (1.0f + expf(-z));                    // E/kActivation.cu:53
+    case DSB200_ACT_SIGMOID: return drcp(1.0f + dexp(-z, fast), fast);            // E/kActivation.cu:53
     case DSB200_ACT_TANH:    return tanhf(z);
     case DSB200_ACT_RELU:    return fmaxf(0.0f, z);
     case DSB200_ACT_LRELU:   return fmaxf(z, z * slope);
@@ -71,12 +78,12 @@ __device__ __forceinline__ void raw_elem(const OArgs& a, int ef, int act, float 
             d = (x > a.P.SMCE_zeroTarget) ? a.P.SMCE_zeroScale * x : 0.0f;
         } else {                                                          // E/kLoss.cu:2215-2234, E/kDelta.cu:7184-7201
             const float w = a.P.SMCE_zeroScale * wd;
-            if (x > a.P.SMCE_zeroTarget) { loss += -w * logf(fmaxf(kMinError, 1.0f - x)); d = w * x; }
+            if (x > a.P.SMCE_zeroTarget) { loss += -w * dlog(fmaxf(kMinError, 1.0f - x), a.fast); d = w * x; }
             else d = 0.0f;
         }
     } else if (e == DSB200_ERR_CROSS_ENTROPY) {
         if (c == DSB200_ACT_SOFTMAX) d = wd * x;                          // E/kDelta.cu:2484-2500
-        else { loss += -wd * logf(fmaxf(kMinError, 1.0f - x)); d = a.P.deltaBoost_zero * wd * x; }   // E/kLoss.cu:1751-1768, E/kDelta.cu:6535-6550
+        else { loss += -wd * dlog(fmaxf(kMinError, 1.0f - x), a.fast); d = a.P.deltaBoost_zero * wd * x; }   // E/kLoss.cu:1751-1768, E/kDelta.cu:6535-6550
     } else {                                                              // L2
         loss += 0.5f * wd * x * x;                                        // E/kLoss.cu:597-615
         if (c == DSB200_ACT_SOFTMAX) d = wd * x;
@@ -95,17 +102,17 @@ __device__ __forceinline__ void nz_elem(const OArgs& a, int ef, int act, float x
     if (e == DSB200_ERR_SMCE) {
         if (c == DSB200_ACT_SOFTMAX) {                                    // E/kLoss.cu:2566-2599, E/kDelta.cu:7243-7267
             const float w = a.P.SMCE_oneScale * wrow;
-            if (x < a.P.SMCE_oneTarget) { loss += -w * logf(fmaxf(kMinError, x)); d = x - w; } else d = 0.0f;
+            if (x < a.P.SMCE_oneTarget) { loss += -w * dlog(fmaxf(kMinError, x), a.fast); d = x - w; } else d = 0.0f;
         } else {                                                          // E/kLoss.cu:2236-2327, E/kDelta.cu:7203-7226
-            if (!iz && x > a.P.SMCE_zeroTarget) loss += wd * a.P.SMCE_zeroScale * logf(fmaxf(kMinError, 1.0f - x));
-            if (x < a.P.SMCE_oneTarget) { loss += -wd * a.P.SMCE_oneScale * logf(fmaxf(kMinError, x)); d = a.P.SMCE_oneScale * wd * (x - 1.0f); }
+            if (!iz && x > a.P.SMCE_zeroTarget) loss += wd * a.P.SMCE_zeroScale * dlog(fmaxf(kMinError, 1.0f - x), a.fast);
+            if (x < a.P.SMCE_oneTarget) { loss += -wd * a.P.SMCE_oneScale * dlog(fmaxf(kMinError, x), a.fast); d = a.P.SMCE_oneScale * wd * (x - 1.0f); }
             else d = 0.0f;
         }
     } else if (e == DSB200_ERR_CROSS_ENTROPY) {
-        if (c == DSB200_ACT_SOFTMAX) { loss += -wrow * logf(fmaxf(kMinError, x)); d = x - wrow; }     // E/kLoss.cu:1945-1967, E/kDelta.cu:2502-2521
+        if (c == DSB200_ACT_SOFTMAX) { loss += -wrow * dlog(fmaxf(kMinError, x), a.fast); d = x - wrow; }     // E/kLoss.cu:1945-1967, E/kDelta.cu:2502-2521
         else {                                                            // E/kLoss.cu:1770-1839, E/kDelta.cu:6552-6571
-            loss += iz ? -wd * logf(fmaxf(kMinError, x))
-                       : wd * (-logf(fmaxf(kMinError, x)) + logf(fmaxf(kMinError, 1.0f - x)));
+            loss += iz ? -wd * dlog(fmaxf(kMinError, x), a.fast)
+                       : wd * (-dlog(fmaxf(kMinError, x), a.fast) + dlog(fmaxf(kMinError, 1.0f - x), a.fast));
             d = a.P.deltaBoost_one * wd * (x - 1.0f);
         }
     } else {                                                              // L2: E/kLoss.cu:617-666, E/kDelta.cu:2213-2231
@@ -140,7 +147,7 @@ output_tile_kernel(const OArgs a)
 
         auto one = [&](uint64_t i) {
             float x = a.in[i];
-            if (DO_ACT) x = act_forward((ACT >= 0) ? ACT : a.act, x, a.slope, a.alpha, a.lambda);
+            if (DO_ACT) x = act_forward((ACT >= 0) ? ACT : a.act, x, a.slope, a.alpha, a.lambda, a.fast);
             if (WRITE_UNIT) a.unitOut[i] = x;
             float d = 0.0f, l = 0.0f;
             if (raw) raw_elem<EF, ACT>(a, a.ef, a.act, x, wd, l, d);
@@ -154,7 +161,7 @@ output_tile_kernel(const OArgs a)
                 float x[4] = {z4.x, z4.y, z4.z, z4.w}, d[4] = {0, 0, 0, 0};
 #pragma unroll
                 for (int v = 0; v < 4; v++) {
-                    if (DO_ACT) x[v] = act_forward((ACT >= 0) ? ACT : a.act, x[v], a.slope, a.alpha, a.lambda);
+                    if (DO_ACT) x[v] = act_forward((ACT >= 0) ? ACT : a.act, x[v], a.slope, a.alpha, a.lambda, a.fast);
                     float l = 0.0f;
                     if (raw) raw_elem<EF, ACT>(a, a.ef, a.act, x[v], wd, l, d[v]);
                     if (DO_LOSS) loss += l;
@@ -174,7 +181,7 @@ output_tile_kernel(const OArgs a)
             const uint64_t i = (uint64_t)b * a.stride + c;
             float x;
             if (WRITE_UNIT) x = a.unitOut[i];
-            else { x = a.in[i]; if (DO_ACT) x = act_forward((ACT >= 0) ? ACT : a.act, x, a.slope, a.alpha, a.lambda); }
+            else { x = a.in[i]; if (DO_ACT) x = act_forward((ACT >= 0) ? ACT : a.act, x, a.slope, a.alpha, a.lambda, a.fast); }
             const float t = analog ? load_value(a.S.sparseData, a.S.dataType, j) : 1.0f;
             float d = 0.0f, l = 0.0f;
             nz_elem<EF, ACT>(a, a.ef, a.act, x, t, wd, wrow, l, d);
@@ -233,6 +240,7 @@ static OArgs make_oargs(dsb200_ctx* ctx, const dsb200_sparse* s, int ef, int act
     a.P = ctx->params; a.S = *s; a.ef = ef; a.act = act; a.ignoreZero = ignoreZero;
     a.position = position; a.batch = batch; a.stride = stride; a.in = in;
     a.slope = slope; a.alpha = alpha; a.lambda = lambda;
+    a.fast = ctx->fastMath;
     return a;
 }
 

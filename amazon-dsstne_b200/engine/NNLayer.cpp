@@ -320,7 +320,7 @@ void NNLayer::BackPropagateFullyConnected(uint32_t position, uint32_t batch)
                 const NNFloat sgemm_alpha = -(NNFloat)1.0 / (w->_sharingCount * (NNFloat)batch);
                 const NNFloat sgemm_beta = (w->_updateCount == 0) ? (NNFloat)0.0 : (NNFloat)1.0;
                 if (in->_kind == Input && in->_bFastSparse) {
-                    if (net->FusionEnabled() && net->_mode == Training && sgemm_beta == (NNFloat)0.0 && w->_sharingCount == 1) {
+                    if (net->FusionEnabled() && net->_mode == Training && sgemm_beta == (NNFloat)0.0 && w->_sharingCount == 1 && (_stride % 4 == 0)) {
                         // produced inside NNWeight::UpdateWeights, fused with the optimizer: dW is never written
                         w->_bDeferredSparseGradient = true;
                         w->_pDeferredDelta = GetDeltaBuffer();
@@ -378,7 +378,7 @@ void NNLayer::BackPropagateFullyConnected(uint32_t position, uint32_t batch)
             const NNFloat sgemm_alpha = -(NNFloat)1.0 / (w->_sharingCount * (NNFloat)batch);
             const NNFloat sgemm_beta = (w->_updateCount == 0) ? (NNFloat)0.0 : (NNFloat)1.0;
             if (in->_kind == Input && in->_bFastSparse) {
-                if (net->FusionEnabled() && net->_mode == Training && sgemm_beta == (NNFloat)0.0 && w->_sharingCount == 1) {
+                if (net->FusionEnabled() && net->_mode == Training && sgemm_beta == (NNFloat)0.0 && w->_sharingCount == 1 && (_stride % 4 == 0)) {
                     // the gathered delta stays in the send buffer until UpdateWeights: this is the last Gather of the step
                     // for the input weight (the input layer is the end of the back-propagation order)
                     w->_bDeferredSparseGradient = true;

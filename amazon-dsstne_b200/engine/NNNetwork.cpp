@@ -324,6 +324,9 @@ void NNNetwork::RefreshState()
         const size_t items = (size_t)l->_pDataSet->_maxBatchNnz / 64 + _batch + 1;
         getGpu().Check(dsb200_ctx_reserve(getGpu()._ctx, _batch, items * stride), "dsb200_ctx_reserve");
     }
+    // the gradient kernel sums in fixed point, so the order inside a transposed column does not matter: skip the
+    // canonical-order pass in the training loop (kernel-level callers keep it on by default)
+    getGpu().Check(dsb200_ctx_set_option(getGpu()._ctx, "transpose_sort", 0), "dsb200_ctx_set_option");
     getGpu().SetNeuralNetwork(this);
     _bDirty = false;
 }
@@ -412,36 +415,33 @@ NNFloat NNNetwork::ReadErrorAccumulator()
 
 // asynchronous half of CalculateError: loss kernels (fused with activation + delta where possible) into the
 // device accumulator, cross-rank sum of the fixed-point words, copy to pinned memory, record the event
-void NNNetwork::LaunchError()
+void NNNetwork::LaunchError(NNFloat lambda, NNFloat lambda1)
 {
     uint32_t batch = _batch;
     if (_position + batch > _examples) batch = _examples - _position;
     cudaStream_t s = getGpu().GetStream();
-    RTERROR(cudaMemsetAsync(_pbErrorAccumulator->_pDevData, 0, sizeof(unsigned long long), s), "LaunchError memset");
-    for (auto l : _vOutputLayer) l->CalculateErrorAsync(_position, batch, _errorFunction, _pbErrorAccumulator->_pDevData);
+    unsigned long long* acc = _pbErrorAccumulator->_pDevData;        // [0] training error, [1] regularisation error
+    RTERROR(cudaMemsetAsync(acc, 0, 2 * sizeof(unsigned long long), s), "LaunchError memset");
+    for (auto l : _vOutputLayer) l->CalculateErrorAsync(_position, batch, _errorFunction, acc);
+    // regularisation error of every weight shard (E/NNNetwork.cpp:1724-1730), into the second fixed-point word instead
+    // of one blocking Download per weight matrix (kCalculateRegularizationError, E/kernels.cu:2736-2744)
+    if (lambda != (NNFloat)0.0 || lambda1 != (NNFloat)0.0)
+        for (auto w : _vWeight)
+            if (!w->_bShared)
+                getGpu().Check(dsb200_regularization_error_async(getGpu()._ctx, lambda, lambda1, w->_pbWeight->_pDevData, w->_localSize, acc + 1),
+                               "dsb200_regularization_error_async");
     if (getGpu()._numprocs > 1)
-        getGpu().Check(dsb200_all_reduce_u64(getGpu()._ctx, _pbErrorAccumulator->_pDevData, 1), "dsb200_all_reduce_u64");
-    RTERROR(cudaMemcpyAsync(_pbErrorAccumulator->_pSysData, _pbErrorAccumulator->_pDevData, sizeof(unsigned long long), cudaMemcpyDeviceToHost, s),
-            "LaunchError copy");
+        getGpu().Check(dsb200_all_reduce_u64(getGpu()._ctx, acc, 2), "dsb200_all_reduce_u64");
+    RTERROR(cudaMemcpyAsync(_pbErrorAccumulator->_pSysData, acc, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s), "LaunchError copy");
     RTERROR(cudaEventRecord(_errorEvent, s), "LaunchError event");
 }
 
 tuple<NNFloat, NNFloat> NNNetwork::CalculateError(NNFloat lambda, NNFloat lambda1)
 {
-    LaunchError();
+    LaunchError(lambda, lambda1);
     RTERROR(cudaEventSynchronize(_errorEvent), "CalculateError event sync");
-    NNFloat error_training = (NNFloat)((double)(long long)_pbErrorAccumulator->_pSysData[0] * (1.0 / 1073741824.0));
-    NNFloat error_regularization = (NNFloat)0.0;
-    if (lambda != (NNFloat)0.0 || lambda1 != (NNFloat)0.0) {                 // E/NNNetwork.cpp:1724-1730
-        for (auto w : _vWeight) error_regularization += w->CalculateRegularizationError(lambda, lambda1);
-        if (getGpu()._numprocs > 1) {
-            NNFloat* tmp = GetScratchBuffer(1);
-            RTERROR(cudaMemcpyAsync(tmp, &error_regularization, sizeof(NNFloat), cudaMemcpyHostToDevice, getGpu().GetStream()), "reg upload");
-            P2P_Allreduce(tmp, 1);
-            RTERROR(cudaMemcpyAsync(&error_regularization, tmp, sizeof(NNFloat), cudaMemcpyDeviceToHost, getGpu().GetStream()), "reg download");
-            RTERROR(cudaStreamSynchronize(getGpu().GetStream()), "reg sync");
-        }
-    }
+    const NNFloat error_training = (NNFloat)((double)(long long)_pbErrorAccumulator->_pSysData[0] * (1.0 / 1073741824.0));
+    const NNFloat error_regularization = (NNFloat)((double)(long long)_pbErrorAccumulator->_pSysData[1] * (1.0 / 1073741824.0));
     return make_tuple(error_training, error_regularization);
 }
 
@@ -479,13 +479,11 @@ float NNNetwork::TrainStep(uint32_t position, NNFloat alpha, NNFloat lambda, NNF
     SetPosition(position);
     ClearUpdates();
     PredictTrainingBatch();
-    LaunchError();                                   // loss (+ output delta) kernels and the async read-back
+    LaunchError(lambda, lambda1);                    // loss (+ output delta) + regularisation kernels and the async read-back
     BackPropagate();                                 // queued behind them; does not depend on the host seeing the loss
     RTERROR(cudaEventSynchronize(_errorEvent), "TrainStep event sync");
-    NNFloat error_training = (NNFloat)((double)(long long)_pbErrorAccumulator->_pSysData[0] * (1.0 / 1073741824.0));
-    NNFloat error_regularization = (NNFloat)0.0;
-    if (lambda != (NNFloat)0.0 || lambda1 != (NNFloat)0.0)
-        for (auto w : _vWeight) error_regularization += w->CalculateRegularizationError(lambda, lambda1);
+    const NNFloat error_training = (NNFloat)((double)(long long)_pbErrorAccumulator->_pSysData[0] * (1.0 / 1073741824.0));
+    const NNFloat error_regularization = (NNFloat)((double)(long long)_pbErrorAccumulator->_pSysData[1] * (1.0 / 1073741824.0));
     if (pRegularization) *pRegularization = error_regularization;
 
     // divergence brake, E/NNNetwork.cpp:1617-1639

@@ -138,7 +138,7 @@ private:
     void RefreshShuffleBuffers();
     void ShuffleIndices();
     tuple<NNFloat, NNFloat> CalculateError(NNFloat lambda, NNFloat lambda1);
-    void LaunchError();                                    // asynchronous part of CalculateError
+    void LaunchError(NNFloat lambda, NNFloat lambda1);     // asynchronous part of CalculateError
     void ClearUpdates();
     void BackPropagate();
     void UpdateWeights(NNFloat alpha, NNFloat lambda, NNFloat lambda1, NNFloat mu, NNFloat mu1);

@@ -209,6 +209,9 @@ int dsb200_update_biases(dsb200_ctx*, int mode, float alpha, float mu, float mu1
                          const float* pDelta, float* pBiasVelocity, float* pBiasGradientVelocity, float* pBias);
 int dsb200_regularization_error(dsb200_ctx*, float lambda, float lambda1, const float* pWeight, uint64_t size,
                                 float* pErrorOut);            /* synchronous, by value     */
+/* asynchronous variant: adds the fixed-point (2^30) value into *pDevAccumulator (device u64) */
+int dsb200_regularization_error_async(dsb200_ctx*, float lambda, float lambda1, const float* pWeight, uint64_t size,
+                                      unsigned long long* pDevAccumulator);
 
 /* ------------------------------------------------------------------ a13
  * kCalculateTopK 3-arg (E/kernels.h:41) and 4-arg (E/kernels.h:42-43), E/kernels.cu:3201-4385.
