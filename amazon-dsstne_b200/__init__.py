@@ -58,7 +58,7 @@ def lib():
     if _lib is None:
         if not os.path.exists(LIB_PATH):
             raise DsbError(f"{LIB_PATH} is missing: run __graft_entry__.build() (there is no CPU fallback)")
-        _lib = C.CDLL(LIB_PATH, mode=C.RTLD_GLOBAL)
+        _lib = C.CDLL(LIB_PATH)        # RTLD_LOCAL: the engine exports C++ names (getGpu, GpuContext) the reference also uses
         _lib.dsb200_last_error.restype = C.c_char_p
         _lib.dsb200_launch_count.restype = C.c_uint64
     return _lib
