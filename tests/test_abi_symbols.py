@@ -62,3 +62,31 @@ def test_product_never_touches_the_oracle():
                     if re.search(r"liboracle|from oracle|import oracle|oracle/_ref|dsstne_oracle\.h", text):
                         bad.append(os.path.join(dirpath, f))
     assert not bad, bad
+
+
+def test_cpp_shim_with_reference_kernel_names_compiles(tmp_path):
+    """include/dsstne_b200_kernels.hpp re-declares the E/kernels.h launcher names over the C ABI; it must compile as
+    C++14 (the reference's dialect, Makefile.inc:64) and cover the launchers of the hot path."""
+    import subprocess
+    src = tmp_path / "shim.cpp"
+    src.write_text('#include "dsstne_b200_kernels.hpp"\n'
+                   "void use(float* f, uint64_t* u64, uint32_t* u32) {\n"
+                   "  kCalculateSparseZ(0, 1, 4, f, u64, u64, u32, f, f, 1.0f);\n"
+                   "  kCalculateSparseAnalogZ<unsigned char>(0, 1, 4, f, u64, u64, u32, f, (unsigned char*)0, f, 1.0f);\n"
+                   "  kCalculateSparseTransposedWeightGradient(1.0f, 0.0f, 4, 4, u32, u32, u32, f, f);\n"
+                   "  (void)kCalculateSparseScaledMarginalCrossEntropyError(0, 1, 4, f, u64, u64, u32, f, false);\n"
+                   "  kCalculateSparseCrossEntropyOutputDelta(0, 0, 1, 4, f, f, u64, u64, u32, f, false);\n"
+                   "  kAdamUpdateWeights(.1f, 0, 0, .9f, .999f, 1.f, 16, f, f, f, f);\n"
+                   "  kCalculateTopK(f, f, u32, 1, 4, 2);\n"
+                   "}\nint main() { return 0; }\n")
+    r = subprocess.run(["/usr/bin/g++", "-std=c++14", "-fsyntax-only", "-Wall", "-I", os.path.join(ROOT, "include"), str(src)],
+                       capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
+    text = open(os.path.join(ROOT, "include", "dsstne_b200_kernels.hpp")).read()
+    for name in ["kCalculateSparseZ", "kCalculateIndexedSparseZ", "kCalculateSparseAnalogZ", "kCalculateSparseDenoisedZ",
+                 "kCalculateSparseTransposedMatrix", "kCalculateSparseTransposedWeightGradient", "kCalculateSparseL2Error",
+                 "kCalculateSparseCrossEntropyError", "kCalculateSparseScaledMarginalCrossEntropyError", "kCalculateSparseOutputDelta",
+                 "kCalculateSparseCrossEntropyOutputDelta", "kCalculateSparseScaledMarginalCrossEntropyOutputDelta", "kSGDUpdateWeights",
+                 "kMomentumUpdateWeights", "kAdaGradUpdateWeights", "kNesterovUpdateWeights", "kRMSPropUpdateWeights", "kAdaDeltaUpdateWeights",
+                 "kAdamUpdateWeights", "kCalculateTopK", "kClearUnit", "kCalculateRegularizationError"]:
+        assert re.search(r"\b" + name + r"\b", text), name
