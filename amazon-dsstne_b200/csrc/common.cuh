@@ -48,6 +48,11 @@ struct dsb200_ctx {
     int            rank = 0, nranks = 1;
     void*          cublas      = nullptr;         // cublasHandle_t (fp32 GEMM fallback / reference arm)
     int            gemmMode    = 0;
+    int            gemmDebug   = 0;               // bring-up switches of gemm_tc.cu (option "gemm_debug")
+    int            gemmDepth   = 0;               // option "gemm_depth": 0 = automatic copy look-ahead
+    int            gemmStages  = 0;               // option "gemm_stages": 0 = automatic ring depth
+    float*         dGemmWs     = nullptr;         // split-K partial tiles of the tcgen05 GEMM
+    size_t         gemmWsCap   = 0;               // in floats
     int            fastMath    = 1;               // option "fast_math": MUFU exp/log/rcp in the output pass (default on)
     int            profile     = 0;               // option "profile": event pairs around every kernel entry
     char           lastError[256];

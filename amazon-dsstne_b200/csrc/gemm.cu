@@ -7,11 +7,9 @@
 //   dx : Dp[B][k] = beta*Dp + D[B][n] * W[k][n]^T
 // Modes (option "gemm_mode"):
 //   DSB200_GEMM_FP32    cuBLAS SGEMM, pedantic fp32 (what the reference runs; parity baseline)
-//   DSB200_GEMM_TF32    cuBLAS TF32 tensor-op math (stepping stone, tolerance 2e-3 relative)
-//   DSB200_GEMM_TF32X3  hand-written tcgen05 3xTF32 split kernel (gemm_tcgen05.cu) when the shape
-//                       qualifies, else falls back to FP32
-// The library call is the PLAIN GEMM case the task allows cuBLAS for; the fused
-// GEMM+sigmoid+loss+delta output kernel lives in gemm_tcgen05.cu.
+//   DSB200_GEMM_TF32    hand-written tcgen05 kernel (gemm_tc.cu), one tf32 MMA per k-step (~1e-3 relative)
+//   DSB200_GEMM_TF32X3  the same kernel with the 3xTF32 split (fp32-grade, bound in tests/test_gpu_gemm.py)
+// The library call is the PLAIN GEMM case the task allows cuBLAS for.
 #include "common.cuh"
 #include "launch.h"
 
@@ -28,10 +26,16 @@ static int cublas_of(dsb200_ctx* ctx, cublasHandle_t* out)
     }
     cublasHandle_t h = (cublasHandle_t)ctx->cublas;
     if (cublasSetStream(h, ctx->stream) != CUBLAS_STATUS_SUCCESS) return fail(ctx, DSB200_ESTATE, "cublasSetStream failed");
-    cublasSetMathMode(h, ctx->gemmMode == DSB200_GEMM_TF32 ? CUBLAS_TF32_TENSOR_OP_MATH : CUBLAS_PEDANTIC_MATH);
+    cublasSetMathMode(h, CUBLAS_PEDANTIC_MATH);
     *out = h;
     return 0;
 }
+
+int gemm_tc_launch(dsb200_ctx* ctx, const float* A, int aMN, uint32_t lda, const float* B, int bMN, uint32_t ldb, float* C, uint32_t ldc,
+                   uint32_t M, uint32_t N, uint32_t K, float alpha, float beta, const float* bias, int act, float slope, float ealpha,
+                   float lambda);
+
+static inline bool use_tc(const dsb200_ctx* ctx) { return ctx->gemmMode == DSB200_GEMM_TF32 || ctx->gemmMode == DSB200_GEMM_TF32X3; }
 
 void gemm_release(dsb200_ctx* ctx)
 {
@@ -48,6 +52,7 @@ int dsb200_gemm_fwd(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, const f
     using namespace dsb;
     if (!ctx || !A || !W || !C) return fail(ctx, DSB200_EINVAL, "gemm_fwd: null argument");
     if (!B || !k || !n) return 0;
+    if (use_tc(ctx)) return gemm_tc_launch(ctx, A, 0, k, W, 1, n, C, n, B, n, k, 1.0f, beta, nullptr, DSB200_ACT_LINEAR, 0.f, 0.f, 0.f);
     cublasHandle_t h; int rc = cublas_of(ctx, &h); if (rc) return rc;
     const float one = 1.0f;
     // row-major C = A*W  <=>  column-major C^T = W^T * A^T (E/NNLayer.cpp:1072-1086)
@@ -62,6 +67,7 @@ int dsb200_gemm_dw(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, float al
     using namespace dsb;
     if (!ctx || !A || !D || !G) return fail(ctx, DSB200_EINVAL, "gemm_dw: null argument");
     if (!B || !k || !n) return 0;
+    if (use_tc(ctx)) return gemm_tc_launch(ctx, A, 1, k, D, 1, n, G, n, k, n, B, alpha, beta, nullptr, DSB200_ACT_LINEAR, 0.f, 0.f, 0.f);
     cublasHandle_t h; int rc = cublas_of(ctx, &h); if (rc) return rc;
     // G^T (n x k) = D^T (n x B) * A (B x k)   (E/NNLayer.cpp:2223-2236)
     if (cublasSgemm(h, CUBLAS_OP_N, CUBLAS_OP_T, (int)n, (int)k, (int)B, &alpha, D, (int)n, A, (int)k, &beta, G, (int)n) != CUBLAS_STATUS_SUCCESS)
@@ -75,12 +81,31 @@ int dsb200_gemm_dx(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, const fl
     using namespace dsb;
     if (!ctx || !D || !W || !Dp) return fail(ctx, DSB200_EINVAL, "gemm_dx: null argument");
     if (!B || !k || !n) return 0;
+    if (use_tc(ctx)) return gemm_tc_launch(ctx, D, 0, n, W, 0, n, Dp, k, B, k, n, 1.0f, beta, nullptr, DSB200_ACT_LINEAR, 0.f, 0.f, 0.f);
     cublasHandle_t h; int rc = cublas_of(ctx, &h); if (rc) return rc;
     const float one = 1.0f;
     // Dp^T (k x B) = W (k x n) * D^T (n x B)   (E/NNLayer.cpp:2274-2287)
     if (cublasSgemm(h, CUBLAS_OP_T, CUBLAS_OP_N, (int)k, (int)B, (int)n, &one, W, (int)n, D, (int)n, &beta, Dp, (int)k) != CUBLAS_STATUS_SUCCESS)
         return fail(ctx, DSB200_ESTATE, "gemm_dx: SGEMM failure");
     return 0;
+}
+
+/* fused forward of a dense layer: C = act(A * W + bias), i.e. kClearUnit + cublasSgemm(beta = 1) + kCalculate*Activation
+ * (E/NNLayer.cpp:1009, 1073, 1157) in one kernel in the tensor-core modes; three calls in DSB200_GEMM_FP32. */
+int dsb200_gemm_fwd_bias_act(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, const float* A, const float* W, const float* pBias,
+                             int activation, float* C, float slope, float alpha, float lambda)
+{
+    using namespace dsb;
+    if (!ctx || !A || !W || !C || !pBias) return fail(ctx, DSB200_EINVAL, "gemm_fwd_bias_act: null argument");
+    if (!B || !k || !n) return 0;
+    if (use_tc(ctx) && activation != DSB200_ACT_SOFTMAX) {
+        DSB_PROFILE(ctx, "gemm_fwd_bias_act");
+        return gemm_tc_launch(ctx, A, 0, k, W, 1, n, C, n, B, n, k, 1.0f, 0.0f, pBias, activation, slope, alpha, lambda);
+    }
+    int rc = dsb200_clear_unit(ctx, C, pBias, n, B);
+    if (!rc) rc = dsb200_gemm_fwd(ctx, B, k, n, A, W, 1.0f, C);
+    if (!rc && activation != DSB200_ACT_LINEAR) rc = dsb200_activation(ctx, activation, C, B, n, slope, alpha, lambda);
+    return rc;
 }
 
 }  // extern "C"

@@ -197,6 +197,9 @@ int dsb200_hadamard(dsb200_ctx*, int activation, uint64_t size, float scale, con
 int dsb200_gemm_fwd(dsb200_ctx*, uint32_t B, uint32_t k, uint32_t n, const float* A, const float* W, float beta, float* C);
 int dsb200_gemm_dw(dsb200_ctx*, uint32_t B, uint32_t k, uint32_t n, float alpha, const float* A, const float* D, float beta, float* G);
 int dsb200_gemm_dx(dsb200_ctx*, uint32_t B, uint32_t k, uint32_t n, const float* D, const float* W, float beta, float* Dp);
+/* fused dense forward C = act(A*W + bias): kClearUnit + cublasSgemm(beta=1) + activation (E/NNLayer.cpp:1009,1073,1157) */
+int dsb200_gemm_fwd_bias_act(dsb200_ctx*, uint32_t B, uint32_t k, uint32_t n, const float* A, const float* W, const float* pBias,
+                             int activation, float* C, float slope, float alpha, float lambda);
 
 /* ------------------------------------------------------------------ a12
  * k{SGD,Momentum,AdaGrad,Nesterov,RMSProp,AdaDelta,Adam}Update{Weights,Biases} and

@@ -1,0 +1,91 @@
+"""Dense GEMMs (hot-path row a11) through the C ABI, all three arithmetic modes, against a float64 product.
+
+Stated bounds (helpers.rel_err = max |a-b| / (|b| + rms(b))):
+  DSB200_GEMM_FP32    cuBLAS SGEMM                                   1e-5
+  DSB200_GEMM_TF32X3  tcgen05, 3xTF32 split, fp32 accumulation in TMEM  3e-5   (products are fp32-grade, ~2e-6 for K <= 128;
+                      the tensor core's fp32 accumulator truncates, so the bound grows with the length of one
+                      accumulation chain: 1.8e-5 measured at K = 1,024, 1e-5 at K = 27,278 split 37 ways)
+  DSB200_GEMM_TF32    tcgen05, one tf32 MMA per k-step                  3e-3
+Shapes: BASELINE.json config 2's output layer (1,024 x 128 x 27,278), its hidden layers, and ragged / odd sizes that
+exercise zero fill, 8- and 4-byte copy paths and partial tiles."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import rel_err
+
+pytestmark = pytest.mark.gpu
+BOUND = {0: 1e-5, 2: 3e-5, 1: 3e-3}
+SHAPES = [(1024, 128, 27278), (1024, 128, 128), (256, 128, 256), (300, 70, 1000), (130, 33, 259), (64, 1024, 2000), (1, 5, 7)]
+
+
+def ref64(a):
+    return a.double().cpu().numpy()
+
+
+@pytest.mark.parametrize("mode", [0, 2, 1], ids=["fp32", "tf32x3", "tf32"])
+@pytest.mark.parametrize("B,k,n", SHAPES)
+def test_gemm_fwd_dw_dx(ctx, mode, B, k, n):
+    g = torch.Generator(device="cuda").manual_seed(B * 7 + k * 3 + n)
+    A = torch.randn(B, k, device="cuda", generator=g)
+    W = torch.randn(k, n, device="cuda", generator=g) * 0.1
+    D = torch.randn(B, n, device="cuda", generator=g) * 0.1
+    C0 = torch.randn(B, n, device="cuda", generator=g)
+    ctx.set_option("gemm_mode", mode)
+    try:
+        C = C0.clone()
+        ctx.gemm_fwd(A, W, C, beta=1.0)
+        G = torch.zeros(k, n, device="cuda")
+        ctx.gemm_dw(A, D, G, -1.0 / B)
+        G2 = G.clone()
+        ctx.gemm_dw(A, D, G2, -1.0 / B, beta=1.0)
+        Dp = torch.zeros(B, k, device="cuda")
+        ctx.gemm_dx(D, W, Dp)
+        ctx.sync()
+    finally:
+        ctx.set_option("gemm_mode", 0)
+    a, w, d = ref64(A), ref64(W), ref64(D)
+    tol = BOUND[mode]
+    assert rel_err(C.cpu().numpy(), ref64(C0) + a @ w) < tol
+    assert rel_err(G.cpu().numpy(), (-1.0 / B) * (a.T @ d)) < tol
+    assert rel_err(G2.cpu().numpy(), 2 * (-1.0 / B) * (a.T @ d)) < tol
+    assert rel_err(Dp.cpu().numpy(), d @ w.T) < tol
+
+
+@pytest.mark.parametrize("mode", [0, 2], ids=["fp32", "tf32x3"])
+@pytest.mark.parametrize("act", [0, 1, 2, 3], ids=["sigmoid", "tanh", "relu", "linear"])
+def test_fused_bias_activation_forward(ctx, orc, mode, act):
+    B, k, n = 512, 128, 1000
+    g = torch.Generator(device="cuda").manual_seed(act)
+    A = torch.randn(B, k, device="cuda", generator=g)
+    W = torch.randn(k, n, device="cuda", generator=g) * 0.1
+    bias = torch.randn(n, device="cuda", generator=g)
+    C = torch.empty(B, n, device="cuda")
+    ctx.set_option("gemm_mode", mode)
+    try:
+        ctx.gemm_fwd_bias_act(A, W, bias, act, C)
+        ctx.sync()
+    finally:
+        ctx.set_option("gemm_mode", 0)
+    z = (ref64(A) @ ref64(W) + ref64(bias)[None, :]).astype(np.float32)
+    want = orc.activation(act, np.ascontiguousarray(z))              # E/kActivation.cu semantics via the oracle
+    assert rel_err(C.cpu().numpy(), want) < BOUND[mode]
+
+
+def test_tensor_core_gemm_is_deterministic(ctx):
+    B, k, n = 1024, 128, 27278
+    g = torch.Generator(device="cuda").manual_seed(5)
+    D = torch.randn(B, n, device="cuda", generator=g) * 0.1
+    W = torch.randn(k, n, device="cuda", generator=g) * 0.1
+    ctx.set_option("gemm_mode", 2)
+    try:
+        outs = []
+        for _ in range(3):
+            Dp = torch.zeros(B, k, device="cuda")
+            ctx.gemm_dx(D, W, Dp)                                   # split-K: partial tiles summed in a fixed order
+            ctx.sync()
+            outs.append(Dp.cpu().numpy())
+    finally:
+        ctx.set_option("gemm_mode", 0)
+    np.testing.assert_array_equal(outs[0], outs[1])
+    np.testing.assert_array_equal(outs[0], outs[2])
