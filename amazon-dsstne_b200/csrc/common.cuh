@@ -49,8 +49,7 @@ struct dsb200_ctx {
     void*          cublas      = nullptr;         // cublasHandle_t (fp32 GEMM fallback / reference arm)
     int            gemmMode    = 0;
     int            gemmDebug   = 0;               // bring-up switches of gemm_tc.cu (option "gemm_debug")
-    int            gemmDepth   = 0;               // option "gemm_depth": 0 = automatic copy look-ahead
-    int            gemmStages  = 0;               // option "gemm_stages": 0 = automatic ring depth
+    int            gemmSplits  = 0;               // option "gemm_splits": 0 = automatic split-K factor
     float*         dGemmWs     = nullptr;         // split-K partial tiles of the tcgen05 GEMM
     size_t         gemmWsCap   = 0;               // in floats
     int            fastMath    = 1;               // option "fast_math": MUFU exp/log/rcp in the output pass (default on)

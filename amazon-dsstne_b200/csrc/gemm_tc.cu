@@ -5,22 +5,29 @@
 // tensor core reads, lo = the exact fp32 remainder, and lo*hi + hi*lo + hi*hi accumulate in fp32 in TMEM) or
 // DSB200_GEMM_TF32 (hi*hi only).
 //
-// One 128x128 output tile per CTA, two CTAs per SM so that one CTA's epilogue overlaps the other's main loop.
-//   warps 0-7  loaders, then epilogue.  Operand rows are not 16-byte aligned in general (N = 27,278 floats), so TMA
-//              tensor maps are not usable; each thread copies its 16-byte chunks global -> shared with cp.async
-//              (16 / 8 / 4-byte pieces by alignment, zero fill at the matrix edge) straight into the UMMA layouts,
-//              ring depth - 1 panels ahead, then derives the "lo" panel of the 3xTF32 split from its own chunks.
-//   warp 8     TMEM allocation; lane 0 issues every tcgen05.mma and signals stage reuse / accumulator completion
-//              with tcgen05.commit on mbarriers.
+// Persistent kernel, one CTA per SM, 128 x 128 output tiles, 17 warps with separate roles so that no warp's serial
+// chain (wait -> work -> fence -> signal) sits on the critical path of every k-iteration:
+//   warps 0-3    copy:     operand rows are not 16-byte aligned in general (N = 27,278 floats), so TMA tensor maps are
+//                          not usable; each thread copies its 16-byte chunks global -> shared with cp.async (16 / 8 /
+//                          4-byte pieces by alignment, zero fill at the edges) straight into the UMMA layouts of a
+//                          7-deep ring of raw panels and lets the copies signal an mbarrier when they land
+//                          (cp.async.mbarrier.arrive.noinc) -- the copy warps never wait for data.
+//   warps 4-11   split:    two groups taking alternate k-iterations: wait for the panel, derive the "lo" panel of the
+//                          3xTF32 split (elementwise, a - trunc_tf32(a)) into a 3-deep ring, make both visible to the
+//                          tensor core (fence.proxy.async) and hand the iteration to the MMA warp.
+//   warp 12      MMA:      TMEM allocation; lane 0 issues every tcgen05.mma (3 per K = 8 step) into one of two 128-column
+//                          accumulators and releases ring slots / publishes accumulators with tcgen05.commit.
+//   warps 13-16  epilogue: TMEM -> registers -> padded shared-memory tile -> row-contiguous global stores with the
+//                          alpha / beta / bias / activation epilogue, overlapped with the next tile's main loop.
 // Shared-memory layouts of one 128 x 16 operand panel (16-byte chunks = 4 floats along the contiguous dimension):
 //   K-major operand (k contiguous in memory): no swizzle, core matrix = 8 mn-rows x 16 bytes,
 //       chunk(mn, kc) at (mn/8)*128 + (mn%8)*16 + kc*2048                                   LBO=2048 SBO=128
-//       lanes of a load: 8 rows x 4 chunks -- a quarter-warp writes one whole core matrix (conflict free).
+//       lanes of a copy: 8 rows x 4 chunks -- a quarter-warp writes one whole core matrix (conflict free).
 //   MN-major operand (mn contiguous in memory): the 32-bit "128B, 32B-base" swizzle, the only layout the tensor core
 //       accepts for transposed tf32 operands (every other layout type returns zeros -- measured, tools/umma_probe.cu):
 //       atom = 4 k-rows x 128 bytes (32 mn), 32-byte granules XOR-ed with k%4,
 //       chunk(k, mc) at (mc/8)*2048 + (k/4)*512 + (k%4)*128 + ((((mc%8)/2) ^ (k%4))*32) + (mc%2)*16   LBO=2048 SBO=512
-//       lanes of a load: 4 k-rows x 8 chunks (128 contiguous bytes per row) -- conflict free as well.
+//       lanes of a copy: 4 k-rows x 8 chunks (128 contiguous bytes per row) -- conflict free as well.
 // Split-K (K = 27,278 for the input-delta GEMM of the output layer) writes raw partial tiles to a workspace that
 // gemm_reduce_kernel sums in a fixed order -- deterministic, no float atomics.
 #include "common.cuh"
@@ -29,26 +36,29 @@
 namespace dsb {
 namespace tc {
 
-constexpr int BM = 128, BN = 128, BK = 16, MAX_STAGES = 6;
-constexpr int PANEL = 128 * BK * 4;            // one operand panel (raw or lo): 8 KB
-constexpr int STAGE_BYTES = 4 * PANEL;         // A raw | A lo | B raw | B lo
-constexpr int LOADERS = 256, THREADS = 288, MMA_WARP = 8;   // warps 0-7 load + run the epilogue, warp 8 issues the MMAs
-constexpr int smem_bytes(int stages) { return stages * STAGE_BYTES + 1024; }
+constexpr int BM = 128, BN = 128, BK = 16;
+constexpr int PANEL = 128 * BK * 4;            // one operand panel: 8 KB
+constexpr int STAGE = 2 * PANEL;               // A panel | B panel (raw ring and lo ring alike)
+constexpr int RAW_SLOTS = 7, LO_SLOTS = 3;
+constexpr int COPY_WARPS = 4, SPLIT_GROUPS = 2, SPLIT_WARPS = 8, MMA_WARP = 12, EPI_WARP0 = 13, EPI_WARPS = 4;
+constexpr int THREADS = (EPI_WARP0 + EPI_WARPS) * 32;
+constexpr int EPI_COLS = BN / 2;               // the epilogue drains the accumulator in two 64-column halves
+constexpr int EPI_LD = EPI_COLS + 4;           // padded row of the per-warp staging tile (floats)
+constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_LD * 4;
+constexpr int SMEM_BYTES = (RAW_SLOTS + LO_SLOTS) * STAGE + EPI_BYTES + 1024;
 
 struct Args {
     const float* A; const float* B; float* C;
     uint32_t M, N, K;                          // C[M][N] (+)= A(M x K) * B(K x N)
     uint32_t lda, ldb, ldc;
-    int aMN, bMN;                              // operand is MN-contiguous in memory (else K-contiguous)
     int vecA, vecB, vecC;                      // widest aligned access in floats (4, 2, 1)
     float alpha, beta;
     const float* bias; int act; float slope, ealpha, lambda;
-    uint32_t kPerSplit;                        // multiple of BK; == K rounded up when not split
+    uint32_t tilesM, tilesN, splits;
+    uint32_t kPerSplit;                        // multiple of BK
     float* partial;                            // split-K workspace [splits][M][N] or NULL
     int passes;                                // 3 = 3xTF32, 1 = TF32
-    int debug;                                 // bring-up switches: 1 no global loads, 2 no MMA, 4 no epilogue stores, 8 no lo pass
-    uint32_t depth;                            // panels of copies in flight ahead of the consumer
-    uint32_t stages;                           // shared-memory ring depth: 3 (two CTAs per SM) or 6 (one CTA per SM)
+    int debug;                                 // bring-up: 1 no proxy fence, 2 no copies, 4 no MMA, 8 no lo pass, 16 no stores
 };
 
 __device__ __forceinline__ float act_apply(int act, float z, float slope, float alpha, float lambda)
@@ -121,57 +131,25 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v)
 
 // ---- operand staging: global -> shared with cp.async (LDGSTS), zero fill outside the matrix ----
 // The raw fp32 panel doubles as the "hi" operand: the tf32 tensor core reads the upper 19 bits of each word and
-// ignores the rest, so hi = trunc_tf32(a) needs no pass of its own; the "lo" panel (a - hi, exact in fp32) is
-// produced by the thread that issued the copy, from its own chunks, once its copy group has landed.
-__device__ __forceinline__ void cp_async_chunk(uint32_t dst, const float* __restrict__ base, uint32_t ld, uint32_t row, uint32_t col,
-                                               uint32_t rowLimit, uint32_t colLimit, int vec)
+// ignores the rest (measured: feeding raw words gives bit-identical results to feeding masked words).
+__device__ __forceinline__ void cp_async_landed(uint64_t* bar)
 {
-    const bool in = row < rowLimit && col < colLimit;
-    const uint32_t valid = in ? min(4u, colLimit - col) : 0u;                   // floats of this chunk inside the matrix
-    const float* p = in ? base + (size_t)row * ld + col : base;
-    if (vec == 4) {
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(p), "r"(valid * 4) : "memory");
-    } else if (vec == 2) {
-        const uint32_t b0 = min(valid, 2u) * 4, b1 = (valid > 2 ? valid - 2 : 0u) * 4;
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(dst), "l"(p), "r"(b0) : "memory");
-        asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(dst + 8), "l"(b1 ? p + 2 : p), "r"(b1) : "memory");
-    } else {
-#pragma unroll
-        for (uint32_t e = 0; e < 4; e++)
-            asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(dst + 4 * e), "l"(e < valid ? p + e : p), "r"(e < valid ? 4u : 0u) : "memory");
-    }
-}
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait(int pending)
-{
-    switch (pending) {
-    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
-    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
-    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
-    case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
-    case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
-    default: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
-    }
+    asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
 
-// Per-thread plan of one operand: CHUNKS 16-byte chunks of every 128 x BK panel, everything that does not depend on
-// the k-iteration hoisted out of the main loop (the loaders are issue-bound: ~10 cycles per dependent instruction
-// with one warp per scheduler, so instructions per byte is what matters).
-constexpr int EPI_COLS = BN / 2;               // a warp's share of the tile in the epilogue: 32 rows x 64 columns
-constexpr int EPI_LD = EPI_COLS + 4;           // padded row of the per-warp staging tile (floats)
-constexpr int CHUNKS = 2;                      // 16 warp-level chunk groups per panel / 8 loader warps
+// Per-thread plan of one operand of one tile: CHUNKS 16-byte chunks of every 128 x BK panel, everything that does not
+// depend on the k-iteration hoisted out of the main loop.
+constexpr int CHUNKS = 4;                      // 16 warp-level chunk groups per panel / 4 copy warps
 template <bool MN>
 struct OperandPlan {
     const float* ptr[CHUNKS];                  // global address of the chunk in the next k-iteration to issue
     uint32_t     soff[CHUNKS];                 // byte offset inside the panel
     uint32_t     valid[CHUNKS];                // floats inside the matrix along the contiguous dimension (full iterations)
-    uint32_t     b0[CHUNKS], b1[CHUNKS];       // source bytes of the first / second copy of a full iteration
     uint32_t     kOff[CHUNKS];                 // first k of the chunk inside the panel
-    size_t       step;                         // pointer advance per k-iteration (0 for chunks outside the matrix)
+    size_t       step;                         // pointer advance per k-iteration
     const float* base;
 
-    __device__ __forceinline__ void init(const float* b, uint32_t ld, uint32_t mn0, uint32_t kBegin, uint32_t mnLimit, int vec, uint32_t warp,
-                                         uint32_t lane)
+    __device__ __forceinline__ void init(const float* b, uint32_t ld, uint32_t mn0, uint32_t kBegin, uint32_t mnLimit, uint32_t warp, uint32_t lane)
     {
         base = b;
         step = MN ? (size_t)BK * ld : (size_t)BK;
@@ -191,8 +169,6 @@ struct OperandPlan {
                 ptr[i] = valid[i] ? b + (size_t)mn * ld + kBegin + k : b;
             }
             kOff[i] = k;
-            b0[i] = (vec == 4) ? valid[i] * 4 : min(valid[i], 2u) * 4;
-            b1[i] = (valid[i] > 2 ? valid[i] - 2 : 0u) * 4;
         }
     }
     // a full panel (k0 + BK <= kEnd): nothing but the copies and the pointer advance
@@ -200,23 +176,22 @@ struct OperandPlan {
     {
 #pragma unroll
         for (int i = 0; i < CHUNKS; i++) {
-            const uint32_t dst = panelAddr + soff[i];
+            const uint32_t dst = panelAddr + soff[i], v = valid[i];
             if (vec == 4) {
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(ptr[i]), "r"(b0[i]) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(ptr[i]), "r"(v * 4) : "memory");
             } else if (vec == 2) {
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(dst), "l"(ptr[i]), "r"(b0[i]) : "memory");
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(dst + 8), "l"(ptr[i] + (b1[i] ? 2 : 0)), "r"(b1[i]) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(dst), "l"(ptr[i]), "r"(min(v, 2u) * 4) : "memory");
+                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(dst + 8), "l"(ptr[i] + (v > 2 ? 2 : 0)), "r"((v > 2 ? v - 2 : 0u) * 4) : "memory");
             } else {
 #pragma unroll
                 for (uint32_t e = 0; e < 4; e++)
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(dst + 4 * e), "l"(e < valid[i] ? ptr[i] + e : base),
-                                 "r"(e < valid[i] ? 4u : 0u) : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(dst + 4 * e), "l"(e < v ? ptr[i] + e : base), "r"(e < v ? 4u : 0u) : "memory");
             }
-            ptr[i] += valid[i] ? step : 0;
+            ptr[i] += v ? step : 0;
         }
     }
     // the last, partial panel of the K range: element-wise bounds
-    __device__ __noinline__ void issue_tail(uint32_t panelAddr, uint32_t k0, uint32_t kEnd)
+    __device__ __forceinline__ void issue_tail(uint32_t panelAddr, uint32_t k0, uint32_t kEnd)
     {
 #pragma unroll
         for (int i = 0; i < CHUNKS; i++) {
@@ -228,27 +203,6 @@ struct OperandPlan {
 #pragma unroll
             for (uint32_t e = 0; e < 4; e++)
                 asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(dst + 4 * e), "l"(e < v ? ptr[i] + e : base), "r"(e < v ? 4u : 0u) : "memory");
-        }
-    }
-    __device__ __forceinline__ void issue(uint32_t panelAddr, uint32_t k0, uint32_t kEnd, int vec)
-    {
-        if (k0 + BK <= kEnd) issue_full(panelAddr, vec);
-        else issue_tail(panelAddr, k0, kEnd);
-    }
-    // lo = a - trunc_tf32(a) for this thread's own chunks
-    __device__ __forceinline__ void make_lo(uint8_t* raw, uint8_t* lo) const
-    {
-        float4 r[CHUNKS];
-#pragma unroll
-        for (int i = 0; i < CHUNKS; i++) r[i] = *reinterpret_cast<const float4*>(raw + soff[i]);
-#pragma unroll
-        for (int i = 0; i < CHUNKS; i++) {
-            float4 l;
-            l.x = r[i].x - __uint_as_float(__float_as_uint(r[i].x) & 0xFFFFE000u);
-            l.y = r[i].y - __uint_as_float(__float_as_uint(r[i].y) & 0xFFFFE000u);
-            l.z = r[i].z - __uint_as_float(__float_as_uint(r[i].z) & 0xFFFFE000u);
-            l.w = r[i].w - __uint_as_float(__float_as_uint(r[i].w) & 0xFFFFE000u);
-            *reinterpret_cast<float4*>(lo + soff[i]) = l;
         }
     }
 };
@@ -272,150 +226,200 @@ __device__ __forceinline__ void store_rows(const float* __restrict__ sp, float* 
     }
 }
 
+struct Tile { uint32_t m0, n0, split, kBegin, kEnd, numK; };
+__device__ __forceinline__ Tile tile_of(const Args& a, uint32_t t)
+{
+    // m fastest: CTAs running at the same time share the B (weight / delta column) tile through L2
+    Tile x;
+    const uint32_t mn = a.tilesM * a.tilesN;
+    x.split = t / mn;
+    const uint32_t r = t - x.split * mn;
+    x.n0 = (r / a.tilesM) * BN;
+    x.m0 = (r % a.tilesM) * BM;
+    x.kBegin = x.split * a.kPerSplit;
+    x.kEnd = min(a.K, x.kBegin + a.kPerSplit);
+    x.numK = (x.kEnd - x.kBegin + BK - 1) / BK;               // >= 1: the host never creates an empty split
+    return x;
+}
+
 template <bool AMN, bool BMN>
-__global__ void __launch_bounds__(THREADS, 2)
+__global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const Args a)
 {
     extern __shared__ uint8_t smemRaw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smemRaw + 1023) & ~(uintptr_t)1023);
-    __shared__ uint64_t fullBar[MAX_STAGES], emptyBar[MAX_STAGES], accumBar;
+    uint8_t* rawRing = smem;
+    uint8_t* loRing = smem + RAW_SLOTS * STAGE;
+    float* epiStage = reinterpret_cast<float*>(smem + (RAW_SLOTS + LO_SLOTS) * STAGE);
+    __shared__ uint64_t landedBar[RAW_SLOTS], emptyRawBar[RAW_SLOTS], fullBar[LO_SLOTS], emptyLoBar[LO_SLOTS], accFullBar[2], accEmptyBar[2];
     __shared__ uint32_t tmemBase;
 
     const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-    const uint32_t m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-    const uint32_t kBegin = blockIdx.z * a.kPerSplit;
-    const uint32_t kEnd = min(a.K, kBegin + a.kPerSplit);
-    const uint32_t numK = (kEnd > kBegin) ? (kEnd - kBegin + BK - 1) / BK : 0;
-    // copies run `depth` panels ahead of the panel being handed to the MMA warp; depth <= stages - 2 leaves slack on both
-    // handshakes (a refilled slot was released two iterations ago, a full slot is waiting before the MMA warp asks)
-    const uint32_t stages = a.stages, depth = a.depth;
+    const uint32_t numTiles = a.tilesM * a.tilesN * a.splits;
 
     if (threadIdx.x == 0) {
-        for (uint32_t s = 0; s < stages; s++) { mbar_init(&fullBar[s], LOADERS / 32); mbar_init(&emptyBar[s], 1); }
-        mbar_init(&accumBar, 1);
+        for (int s = 0; s < RAW_SLOTS; s++) { mbar_init(&landedBar[s], COPY_WARPS * 32); mbar_init(&emptyRawBar[s], 1); }
+        for (int s = 0; s < LO_SLOTS; s++) { mbar_init(&fullBar[s], SPLIT_WARPS / SPLIT_GROUPS); mbar_init(&emptyLoBar[s], 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(&accFullBar[s], 1); mbar_init(&accEmptyBar[s], EPI_WARPS); }
         mbar_fence_init();
     }
-    if (warp == MMA_WARP) tmem_alloc(&tmemBase, BN);
+    if (warp == MMA_WARP) tmem_alloc(&tmemBase, 2 * BN);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = tmemBase;
 
-    if (warp < MMA_WARP) {
-        // ---------------------------------------------------------------- loaders
-        const uint32_t smemAddr = smem_u32(smem);
-        OperandPlan<AMN> pa;
-        OperandPlan<BMN> pb;
-        pa.init(a.A, a.lda, m0, kBegin, a.M, a.vecA, warp, lane);
-        pb.init(a.B, a.ldb, n0, kBegin, a.N, a.vecB, warp, lane);
-        uint32_t issued = 0;                                                     // k-iterations whose copies have been issued
-        for (; issued < depth; issued++) {
-            if (issued < numK && !(a.debug & 1)) {
-                const uint32_t st = smemAddr + issued * STAGE_BYTES, k0 = kBegin + issued * BK;
-                pa.issue(st, k0, kEnd, a.vecA);
-                pb.issue(st + 2 * PANEL, k0, kEnd, a.vecB);
+    if (warp < COPY_WARPS) {
+        // ---------------------------------------------------------------- copy warps
+        const uint32_t rawAddr = smem_u32(rawRing);
+        uint32_t slot = 0, parity = 1;                                            // ring position / emptyRaw wait parity
+        for (uint32_t t = blockIdx.x; t < numTiles; t += gridDim.x) {
+            const Tile tl = tile_of(a, t);
+            OperandPlan<AMN> pa;
+            OperandPlan<BMN> pb;
+            pa.init(a.A, a.lda, tl.m0, tl.kBegin, a.M, warp, lane);
+            pb.init(a.B, a.ldb, tl.n0, tl.kBegin, a.N, warp, lane);
+            for (uint32_t kt = 0; kt < tl.numK; kt++) {
+                mbar_wait(&emptyRawBar[slot], parity);                            // the MMAs that read this slot have retired
+                const uint32_t st = rawAddr + slot * STAGE, k0 = tl.kBegin + kt * BK;
+                if (a.debug & 2) {}
+                else if (k0 + BK <= tl.kEnd) { pa.issue_full(st, a.vecA); pb.issue_full(st + PANEL, a.vecB); }
+                else { pa.issue_tail(st, k0, tl.kEnd); pb.issue_tail(st + PANEL, k0, tl.kEnd); }
+                cp_async_landed(&landedBar[slot]);                                // arrives when this thread's copies have landed
+                if (++slot == RAW_SLOTS) { slot = 0; parity ^= 1; }
             }
-            cp_async_commit();
         }
-        uint32_t s = 0, sNext = depth % stages, phNext = 1;                      // slot of kt; slot / wait parity of kt + depth
-        for (uint32_t kt = 0; kt < numK; kt++) {
-            cp_async_wait((int)depth - 1);                                       // this thread's copies of stage kt have landed
-            uint8_t* st = smem + s * STAGE_BYTES;
-            if (a.passes == 3 && !(a.debug & 8)) {
-                pa.make_lo(st, st + PANEL);
-                pb.make_lo(st + 2 * PANEL, st + 3 * PANEL);
-            }
-            fence_async_smem();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&fullBar[s]);                             // one arrival per loader warp
-            if (++s == stages) s = 0;
-            // refill the slot the MMAs of iteration kt - 1 read (they were issued one iteration ago: normally retired)
-            if (issued < numK) {
-                mbar_wait(&emptyBar[sNext], phNext);
-                const uint32_t sn = smemAddr + sNext * STAGE_BYTES, k0 = kBegin + issued * BK;
-                if (!(a.debug & 1)) {
-                    pa.issue(sn, k0, kEnd, a.vecA);
-                    pb.issue(sn + 2 * PANEL, k0, kEnd, a.vecB);
+        asm volatile("cp.async.wait_all;" ::: "memory");
+    } else if (warp < MMA_WARP) {
+        // ---------------------------------------------------------------- split warps (two groups, alternate iterations)
+        const uint32_t group = (warp - COPY_WARPS) >> 2, tid = threadIdx.x - (COPY_WARPS + group * 4) * 32;   // 0..127 inside the group
+        uint32_t it = 0, rs = 0, rph = 0, ls = 0, lph = 1;
+        for (uint32_t t = blockIdx.x; t < numTiles; t += gridDim.x) {
+            const Tile tl = tile_of(a, t);
+            for (uint32_t kt = 0; kt < tl.numK; kt++, it++) {
+                if ((it & 1) == group) {
+                    mbar_wait(&landedBar[rs], rph);                               // every copy thread's pieces of the panel are in
+                    mbar_wait(&emptyLoBar[ls], lph);
+                    if (a.passes == 3 && !(a.debug & 8)) {
+                        const uint8_t* src = rawRing + rs * STAGE + tid * 16;
+                        uint8_t* dst = loRing + ls * STAGE + tid * 16;
+                        float4 r[8];
+#pragma unroll
+                        for (int j = 0; j < 8; j++) r[j] = *reinterpret_cast<const float4*>(src + j * 2048);
+#pragma unroll
+                        for (int j = 0; j < 8; j++) {
+                            float4 l;
+                            l.x = r[j].x - __uint_as_float(__float_as_uint(r[j].x) & 0xFFFFE000u);
+                            l.y = r[j].y - __uint_as_float(__float_as_uint(r[j].y) & 0xFFFFE000u);
+                            l.z = r[j].z - __uint_as_float(__float_as_uint(r[j].z) & 0xFFFFE000u);
+                            l.w = r[j].w - __uint_as_float(__float_as_uint(r[j].w) & 0xFFFFE000u);
+                            *reinterpret_cast<float4*>(dst + j * 2048) = l;
+                        }
+                    }
+                    if (!(a.debug & 1)) fence_async_smem();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&fullBar[ls]);
                 }
+                if (++rs == RAW_SLOTS) { rs = 0; rph ^= 1; }
+                if (++ls == LO_SLOTS) { ls = 0; lph ^= 1; }
             }
-            issued++;
-            if (++sNext == stages) { sNext = 0; phNext ^= 1; }
-            cp_async_commit();
         }
-        // ---------------------------------------------------------------- epilogue
-        // TMEM -> registers (thread = row) -> per-warp padded staging tile in the now idle pipeline memory ->
-        // row-contiguous global stores (one warp instruction writes 256 contiguous bytes of an output row).
-        // warp w: accumulator rows 32*(w%4) .. +31 (the TMEM lanes a warp may read), columns 64*(w/4) .. +63
-        if (numK) { mbar_wait(&accumBar, 0); tc_fence_after(); }
-        const uint32_t rowBase = (warp & 3) * 32, colBase = (warp >> 2) * EPI_COLS;
-        float* stage = reinterpret_cast<float*>(smem) + warp * (32 * EPI_LD);
-#pragma unroll 1
-        for (int cb = 0; cb < EPI_COLS / 32; cb++) {
-            float v[32];
-            if (numK) tmem_ld32(tmem + (rowBase << 16) + colBase + cb * 32, v);
-            else {
-#pragma unroll
-                for (int j = 0; j < 32; j++) v[j] = 0.f;
-            }
-#pragma unroll
-            for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(stage + lane * EPI_LD + cb * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-        }
-        __syncwarp();
-        const uint32_t mBase = m0 + rowBase;
-        const uint32_t rows = (mBase < a.M) ? min(32u, a.M - mBase) : 0u;
-        const uint32_t c0 = colBase + lane * 2, nc = n0 + c0;                     // this lane's 2 columns
-        const uint32_t ncol = (nc < a.N) ? min(2u, a.N - nc) : 0u;
-        float bias2[2] = {0.f, 0.f};
-        if (a.bias && !a.partial) {
-            if (ncol > 0) bias2[0] = __ldg(a.bias + nc);
-            if (ncol > 1) bias2[1] = __ldg(a.bias + nc + 1);
-        }
-        const uint32_t ldo = a.partial ? a.N : a.ldc;
-        float* outBase = a.partial ? a.partial + (size_t)blockIdx.z * a.M * a.N : a.C;
-        const bool vec2 = ncol == 2 && (a.partial ? ((a.N & 1) == 0) : (a.vecC >= 2));
-        if (ncol && !(a.debug & 4)) {
-            float* o = outBase + (size_t)mBase * ldo + nc;
-            const float* sp = stage + lane * 2;
-            if (a.partial)                           store_rows<-1>(sp, o, rows, ldo, ncol, vec2, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f);
-            else if (a.act == DSB200_ACT_LINEAR)     store_rows<DSB200_ACT_LINEAR>(sp, o, rows, ldo, ncol, vec2, a.alpha, a.beta, bias2[0], bias2[1], 0.f, 0.f, 0.f);
-            else if (a.act == DSB200_ACT_SIGMOID)    store_rows<DSB200_ACT_SIGMOID>(sp, o, rows, ldo, ncol, vec2, a.alpha, a.beta, bias2[0], bias2[1], 0.f, 0.f, 0.f);
-            else if (a.act == DSB200_ACT_TANH)       store_rows<DSB200_ACT_TANH>(sp, o, rows, ldo, ncol, vec2, a.alpha, a.beta, bias2[0], bias2[1], 0.f, 0.f, 0.f);
-            else if (a.act == DSB200_ACT_RELU)       store_rows<DSB200_ACT_RELU>(sp, o, rows, ldo, ncol, vec2, a.alpha, a.beta, bias2[0], bias2[1], 0.f, 0.f, 0.f);
-            else if (a.act == DSB200_ACT_LRELU)      store_rows<DSB200_ACT_LRELU>(sp, o, rows, ldo, ncol, vec2, a.alpha, a.beta, bias2[0], bias2[1], a.slope, 0.f, 0.f);
-            else if (a.act == DSB200_ACT_ELU)        store_rows<DSB200_ACT_ELU>(sp, o, rows, ldo, ncol, vec2, a.alpha, a.beta, bias2[0], bias2[1], 0.f, a.ealpha, 0.f);
-            else                                     store_rows<DSB200_ACT_SELU>(sp, o, rows, ldo, ncol, vec2, a.alpha, a.beta, bias2[0], bias2[1], 0.f, a.ealpha, a.lambda);
-        }
-    } else if (lane == 0) {
+    } else if (warp == MMA_WARP) {
         // ---------------------------------------------------------------- MMA issuer
-        // instruction descriptor: D = F32, A = B = TF32, M = 128, N = 128, majors from the template
-        const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((AMN ? 1u : 0u) << 15) | ((BMN ? 1u : 0u) << 16) |
-                               ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
-        for (uint32_t kt = 0; kt < numK; kt++) {
-            const uint32_t s = kt % stages, ph = (kt / stages) & 1;
-            mbar_wait(&fullBar[s], ph);
-            tc_fence_after();
-            const uint32_t sa = smem_u32(smem + s * STAGE_BYTES);
+        if (lane == 0) {
+            // instruction descriptor: D = F32, A = B = TF32, M = 128, N = 128, majors from the template
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((AMN ? 1u : 0u) << 15) | ((BMN ? 1u : 0u) << 16) |
+                                   ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            const uint32_t rawAddr = smem_u32(rawRing), loAddr = smem_u32(loRing);
+            uint32_t rs = 0, ls = 0, lph = 0, seq = 0;
+            for (uint32_t t = blockIdx.x; t < numTiles; t += gridDim.x, seq++) {
+                const Tile tl = tile_of(a, t);
+                const uint32_t acc = seq & 1, d = tmem + acc * BN;
+                mbar_wait(&accEmptyBar[acc], ((seq >> 1) & 1) ^ 1);               // the epilogue has drained this accumulator
+                tc_fence_after();
+                for (uint32_t kt = 0; kt < tl.numK; kt++) {
+                    mbar_wait(&fullBar[ls], lph);
+                    tc_fence_after();
+                    const uint32_t ra = rawAddr + rs * STAGE, la = loAddr + ls * STAGE;
 #pragma unroll
-            for (int j = 0; j < BK / 8; j++) {
-                const uint64_t aHi = panel_desc<AMN>(sa, j), aLo = panel_desc<AMN>(sa + PANEL, j);
-                const uint64_t bHi = panel_desc<BMN>(sa + 2 * PANEL, j), bLo = panel_desc<BMN>(sa + 3 * PANEL, j);
-                const uint32_t first = (kt == 0 && j == 0) ? 0u : 1u;
-                if (a.debug & 2) {
-                } else if (a.passes == 3) {
-                    tc_mma_tf32(tmem, aLo, bHi, idesc, first);      // small terms first
-                    tc_mma_tf32(tmem, aHi, bLo, idesc, 1u);
-                    tc_mma_tf32(tmem, aHi, bHi, idesc, 1u);
-                } else {
-                    tc_mma_tf32(tmem, aHi, bHi, idesc, first);
+                    for (int j = 0; j < BK / 8; j++) {
+                        const uint64_t aHi = panel_desc<AMN>(ra, j), bHi = panel_desc<BMN>(ra + PANEL, j);
+                        const uint32_t first = (kt == 0 && j == 0) ? 0u : 1u;
+                        if (a.debug & 4) {
+                        } else if (a.passes == 3) {
+                            const uint64_t aLo = panel_desc<AMN>(la, j), bLo = panel_desc<BMN>(la + PANEL, j);
+                            tc_mma_tf32(d, aLo, bHi, idesc, first);               // small terms first
+                            tc_mma_tf32(d, aHi, bLo, idesc, 1u);
+                            tc_mma_tf32(d, aHi, bHi, idesc, 1u);
+                        } else {
+                            tc_mma_tf32(d, aHi, bHi, idesc, first);
+                        }
+                    }
+                    tc_commit(&emptyRawBar[rs]);                                  // slots reusable once these MMAs have read them
+                    tc_commit(&emptyLoBar[ls]);
+                    if (++rs == RAW_SLOTS) rs = 0;
+                    if (++ls == LO_SLOTS) { ls = 0; lph ^= 1; }
                 }
+                tc_commit(&accFullBar[acc]);
             }
-            tc_commit(&emptyBar[s]);                                 // stage reusable once these MMAs have read it
         }
-        if (numK) tc_commit(&accumBar);
+    } else {
+        // ---------------------------------------------------------------- epilogue warps
+        // warp w may read TMEM lanes 32*(w%4) .. +31 = accumulator rows; thread = row
+        const uint32_t rowBase = (warp & 3) * 32;
+        float* stage = epiStage + (warp - EPI_WARP0) * (32 * EPI_LD);
+        uint32_t seq = 0;
+        for (uint32_t t = blockIdx.x; t < numTiles; t += gridDim.x, seq++) {
+            const Tile tl = tile_of(a, t);
+            const uint32_t acc = seq & 1;
+            mbar_wait(&accFullBar[acc], (seq >> 1) & 1);
+            tc_fence_after();
+            const uint32_t mBase = tl.m0 + rowBase;
+            const uint32_t rows = (mBase < a.M) ? min(32u, a.M - mBase) : 0u;
+            const uint32_t ldo = a.partial ? a.N : a.ldc;
+            float* outBase = a.partial ? a.partial + (size_t)tl.split * a.M * a.N : a.C;
+#pragma unroll 1
+            for (int half = 0; half < 2; half++) {
+#pragma unroll 1
+                for (int cb = 0; cb < EPI_COLS / 32; cb++) {
+                    float v[32];
+                    tmem_ld32(tmem + (rowBase << 16) + acc * BN + half * EPI_COLS + cb * 32, v);
+#pragma unroll
+                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(stage + lane * EPI_LD + cb * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                }
+                if (half == 1) {                                                  // accumulator fully read: the MMA warp may reuse it
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&accEmptyBar[acc]);
+                }
+                __syncwarp();
+                const uint32_t c0 = half * EPI_COLS + lane * 2, nc = tl.n0 + c0;    // this lane's 2 columns
+                const uint32_t ncol = (nc < a.N) ? min(2u, a.N - nc) : 0u;
+                if (ncol && !(a.debug & 16)) {
+                    float bias0 = 0.f, bias1 = 0.f;
+                    if (a.bias && !a.partial) {
+                        bias0 = __ldg(a.bias + nc);
+                        if (ncol > 1) bias1 = __ldg(a.bias + nc + 1);
+                    }
+                    const bool vec2 = ncol == 2 && (a.partial ? ((a.N & 1) == 0) : (a.vecC >= 2));
+                    float* o = outBase + (size_t)mBase * ldo + nc;
+                    const float* sp = stage + lane * 2;
+                    if (a.partial)                        store_rows<-1>(sp, o, rows, ldo, ncol, vec2, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f);
+                    else if (a.act == DSB200_ACT_LINEAR)  store_rows<DSB200_ACT_LINEAR>(sp, o, rows, ldo, ncol, vec2, a.alpha, a.beta, bias0, bias1, 0.f, 0.f, 0.f);
+                    else if (a.act == DSB200_ACT_SIGMOID) store_rows<DSB200_ACT_SIGMOID>(sp, o, rows, ldo, ncol, vec2, a.alpha, a.beta, bias0, bias1, 0.f, 0.f, 0.f);
+                    else if (a.act == DSB200_ACT_TANH)    store_rows<DSB200_ACT_TANH>(sp, o, rows, ldo, ncol, vec2, a.alpha, a.beta, bias0, bias1, 0.f, 0.f, 0.f);
+                    else if (a.act == DSB200_ACT_RELU)    store_rows<DSB200_ACT_RELU>(sp, o, rows, ldo, ncol, vec2, a.alpha, a.beta, bias0, bias1, 0.f, 0.f, 0.f);
+                    else if (a.act == DSB200_ACT_LRELU)   store_rows<DSB200_ACT_LRELU>(sp, o, rows, ldo, ncol, vec2, a.alpha, a.beta, bias0, bias1, a.slope, 0.f, 0.f);
+                    else if (a.act == DSB200_ACT_ELU)     store_rows<DSB200_ACT_ELU>(sp, o, rows, ldo, ncol, vec2, a.alpha, a.beta, bias0, bias1, 0.f, a.ealpha, 0.f);
+                    else                                  store_rows<DSB200_ACT_SELU>(sp, o, rows, ldo, ncol, vec2, a.alpha, a.beta, bias0, bias1, 0.f, a.ealpha, a.lambda);
+                }
+                __syncwarp();                                                     // staging tile free for the next half
+            }
+        }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == MMA_WARP) tmem_dealloc(tmem, BN);
+    if (warp == MMA_WARP) tmem_dealloc(tmem, 2 * BN);
 }
 
 // out = alpha * sum_z partial[z] (+ beta * out) (+ bias) -> activation; fixed summation order
@@ -446,7 +450,7 @@ static int vec_of(const void* p, uint32_t ld)
 
 }  // namespace tc
 
-// C[M][N] = act(alpha * op(A) * op(B) + beta * C + bias); see Args for the operand conventions.
+// C[M][N] = act(alpha * op(A) * op(B) + beta * C + bias); aMN / bMN: the operand is MN-contiguous in memory
 int gemm_tc_launch(dsb200_ctx* ctx, const float* A, int aMN, uint32_t lda, const float* B, int bMN, uint32_t ldb, float* C, uint32_t ldc,
                    uint32_t M, uint32_t N, uint32_t K, float alpha, float beta, const float* bias, int act, float slope, float ealpha,
                    float lambda)
@@ -454,28 +458,35 @@ int gemm_tc_launch(dsb200_ctx* ctx, const float* A, int aMN, uint32_t lda, const
     using namespace tc;
     static bool attrSet = false;
     if (!attrSet) {
-        DSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(MAX_STAGES)));
-        DSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(MAX_STAGES)));
-        DSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(MAX_STAGES)));
-        DSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes(MAX_STAGES)));
+        DSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        DSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        DSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        DSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         attrSet = true;
     }
     Args a;
-    a.A = A; a.B = B; a.C = C; a.M = M; a.N = N; a.K = K; a.lda = lda; a.ldb = ldb; a.ldc = ldc; a.aMN = aMN; a.bMN = bMN;
+    a.A = A; a.B = B; a.C = C; a.M = M; a.N = N; a.K = K; a.lda = lda; a.ldb = ldb; a.ldc = ldc;
     a.vecA = vec_of(A, lda); a.vecB = vec_of(B, ldb); a.vecC = vec_of(C, ldc);
     a.alpha = alpha; a.beta = beta; a.bias = bias; a.act = act; a.slope = slope; a.ealpha = ealpha; a.lambda = lambda;
     a.passes = (ctx->gemmMode == DSB200_GEMM_TF32) ? 1 : 3;
     a.debug = ctx->gemmDebug;
-    const uint32_t tilesM = (M + BM - 1) / BM, tilesN = (N + BN - 1) / BN, kTiles = (K + BK - 1) / BK;
-    // split K when the tile grid cannot fill the machine (two CTAs per SM)
+    a.tilesM = (M + BM - 1) / BM; a.tilesN = (N + BN - 1) / BN;
+    const uint32_t tilesMN = a.tilesM * a.tilesN, kTiles = (K + BK - 1) / BK, sms = (uint32_t)ctx->numSMs;
+    // split K so that the persistent grid has whole rounds of work: minimise rounds * (k-iterations + fixed tile cost)
     uint32_t splits = 1;
-    const uint32_t target = (uint32_t)ctx->numSMs * 2;
-    if (tilesM * tilesN < target / 2 && kTiles >= 16) {
-        splits = min(min((target + tilesM * tilesN - 1) / (tilesM * tilesN), kTiles / 8), 64u);
-        if (splits < 1) splits = 1;
+    if (ctx->gemmSplits > 0) splits = min((uint32_t)ctx->gemmSplits, kTiles);
+    else {
+        uint64_t best = ~0ull;
+        for (uint32_t s = 1; s <= 64 && s * 8 <= max(kTiles, 8u); s++) {
+            const uint32_t per = (kTiles + s - 1) / s, real = (kTiles + per - 1) / per;
+            const uint64_t rounds = ((uint64_t)tilesMN * real + sms - 1) / sms;
+            const uint64_t cost = rounds * (per + 12) + (real > 1 ? (uint64_t)real * tilesMN / sms + 4 : 0);   // + partial write / reduce traffic
+            if (cost < best) { best = cost; splits = real; }
+        }
     }
     uint32_t kTilesPerSplit = (kTiles + splits - 1) / splits;
     splits = (kTiles + kTilesPerSplit - 1) / kTilesPerSplit;
+    a.splits = splits;
     a.kPerSplit = kTilesPerSplit * BK;
     a.partial = nullptr;
     if (splits > 1) {
@@ -487,12 +498,7 @@ int gemm_tc_launch(dsb200_ctx* ctx, const float* A, int aMN, uint32_t lda, const
         }
         a.partial = ctx->dGemmWs;
     }
-    // short K (the forward GEMMs): shallow ring, two CTAs per SM so one CTA's epilogue overlaps the other's loads;
-    // long K (gradient GEMMs): one CTA per SM with a deep ring, more bytes in flight
-    a.stages = (ctx->gemmStages >= 3 && ctx->gemmStages <= MAX_STAGES) ? (uint32_t)ctx->gemmStages : ((kTilesPerSplit <= 16) ? 3u : 6u);
-    a.depth = (ctx->gemmDepth >= 1 && ctx->gemmDepth < (int)a.stages) ? (uint32_t)ctx->gemmDepth : (a.stages > 3 ? a.stages - 2 : a.stages - 1);
-    const int SMEM_BYTES = smem_bytes((int)a.stages);
-    dim3 grid(tilesN, tilesM, splits);
+    const uint32_t grid = min(sms, tilesMN * splits);
     if (aMN) {
         if (bMN) gemm_tc_kernel<true, true><<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(a);
         else     gemm_tc_kernel<true, false><<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(a);

@@ -166,6 +166,16 @@ void NNLayer::ForwardPropagateFullyConnected(uint32_t position, uint32_t batch, 
                                                           _vIncomingWeight[0]->_pbBias->_pDevData, _activation, GetIncomingUnitBuffer(),
                                                           bTraining && in->_bDenoising);
             activated = true;
+        } else if (_vIncomingLayer.size() == 1 && !_vIncomingLayer[0]->_bFastSparse && net && net->FusionEnabled() &&
+                   (_activation == Sigmoid || _activation == Tanh || _activation == RectifiedLinear || _activation == Linear ||
+                    _activation == LeakyRectifiedLinear || _activation == ExponentialLinear || _activation == ScaledExponentialLinear)) {
+            // dense layer with a single source: bias + GEMM (+ activation unless the fused loss pass applies it) in one
+            // call -- one tcgen05 kernel in the tensor-core GEMM modes (E/NNLayer.cpp:1009 + 1073 + 1157)
+            NNLayer* in = _vIncomingLayer[0];
+            getGpu().Check(dsb200_gemm_fwd_bias_act(ctx, batch, in->_stride, _localStride, in->GetUnitBuffer(), _vIncomingWeight[0]->_pbWeight->_pDevData,
+                                                    _vIncomingWeight[0]->_pbBias->_pDevData, deferActivation ? (int)Linear : (int)_activation,
+                                                    GetIncomingUnitBuffer(), _RELUSlope, _ELUAlpha, _SELULambda), "dsb200_gemm_fwd_bias_act");
+            activated = !deferActivation;
         } else {
             // E/NNLayer.cpp:1002-1044: units start as the (sum of the) incoming biases
             getGpu().Check(dsb200_clear_unit(ctx, GetIncomingUnitBuffer(), _vIncomingWeight[0]->_pbBias->_pDevData, _stride, batch), "dsb200_clear_unit");

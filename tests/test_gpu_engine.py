@@ -95,25 +95,31 @@ def test_config1_train_steps_match_oracle(eng, orc, mode):
     net.close()
 
 
+@pytest.mark.parametrize("gemm_mode,tol", [(0, TOL), (2, 3e-5)], ids=["fp32", "tf32x3"])
 @pytest.mark.parametrize("error", ["ScaledMarginalCrossEntropy", "CrossEntropy", "L2"])
-def test_three_hidden_layers_with_penalty(eng, orc, error):
+def test_three_hidden_layers_with_penalty(eng, orc, error, gemm_mode, tol):
+    """gemm_mode 2 = the tcgen05 3xTF32 kernels (bound stated in tests/test_gpu_gemm.py); 0 = cuBLAS fp32."""
     sizes, batch = [2048, 128, 64, 128, 2048], 128
     h = tiny(examples=256, width=2048)
     net, onet, names, _ = build_pair(eng, orc, sizes, h, batch, orc.SGD, error=error, sparseness=(0.5, 2.0))
+    net.set_gemm_mode(gemm_mode)
     oc = to_oracle(orc, h)
     onet.set_input(oc, batch)
-    for pos in (0, 128):
-        got = net.train_step(pos, 0.05)
-        want, _ = onet.train_step(oc, oc, pos, batch, 0.05)
-        assert abs(got - want) <= TOL * abs(want)
-    for i in range(len(sizes) - 1):
-        W, b = net.get_weights(names[i], names[i + 1])
-        assert rel_err(W.reshape(onet.W(i).shape), onet.W(i)) < TOL
-    # hidden activations and deltas of the last step
-    for l in range(1, len(sizes) - 1):
-        u = net.get_units(names[l]).reshape(batch, sizes[l])
-        assert rel_err(u, onet.unit(l, batch)) < TOL
-    net.close()
+    try:
+        for pos in (0, 128):
+            got = net.train_step(pos, 0.05)
+            want, _ = onet.train_step(oc, oc, pos, batch, 0.05)
+            assert abs(got - want) <= tol * abs(want)
+        for i in range(len(sizes) - 1):
+            W, b = net.get_weights(names[i], names[i + 1])
+            assert rel_err(W.reshape(onet.W(i).shape), onet.W(i)) < tol
+        # hidden activations and deltas of the last step
+        for l in range(1, len(sizes) - 1):
+            u = net.get_units(names[l]).reshape(batch, sizes[l])
+            assert rel_err(u, onet.unit(l, batch)) < tol
+    finally:
+        net.set_gemm_mode(0)
+        net.close()
 
 
 def test_fused_and_unfused_engine_agree(eng, orc):

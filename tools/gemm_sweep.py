@@ -19,9 +19,8 @@ def t(fn):
     return e0.elapsed_time(e1) / 10 * 1e3
 for mode in (2, 1):
     ctx.set_option("gemm_mode", mode)
-    for stages, depth in ((3, 2), (3, 1), (6, 5), (6, 4), (6, 3), (6, 2), (5, 3), (4, 2)):
-        ctx.set_option("gemm_stages", stages)
-        ctx.set_option("gemm_depth", depth)
-        for dbg in (0, 15):
+    for splits in (0, 1):
+        ctx.set_option("gemm_splits", splits)
+        for dbg in (0, 1, 2, 4, 8, 16, 3, 6, 7, 15, 31):
             ctx.set_option("gemm_debug", dbg)
-            print(f"mode={mode} stages={stages} depth={depth} debug={dbg}: " + " ".join(f"{name} {t(fn):7.1f}" for name, fn in ops), flush=True)
+            print(f"mode={mode} splits={splits} debug={dbg}: " + " ".join(f"{name} {t(fn):7.1f}" for name, fn in ops), flush=True)
