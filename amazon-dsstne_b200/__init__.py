@@ -197,6 +197,12 @@ class Context:
         self.check(lib().dsb200_hadamard(self.h, C.c_int(act), C.c_uint64(unit.numel()), C.c_float(scale), _ptr(unit),
                                          _ptr(delta), C.c_float(slope), C.c_float(alpha), C.c_float(lam)))
 
+    def dropout(self, act, unit, p, seed, stream, full_stride=None, col_offset=0, elu_alpha=1.0, selu_lambda=1.050701):
+        b, s = unit.shape
+        self.check(lib().dsb200_dropout(self.h, C.c_int(act), _ptr(unit), C.c_uint32(b), C.c_uint32(s), C.c_uint32(full_stride or s),
+                                        C.c_uint32(col_offset), C.c_float(p), C.c_float(elu_alpha), C.c_float(selu_lambda),
+                                        C.c_uint64(seed), C.c_uint64(stream)))
+
     def gemm_fwd(self, A, W, Cm, beta=1.0):
         B, k = A.shape
         self.check(lib().dsb200_gemm_fwd(self.h, C.c_uint32(B), C.c_uint32(k), C.c_uint32(W.shape[1]), _ptr(A), _ptr(W),

@@ -98,6 +98,16 @@ class Dataset:
     def from_host_csr(cls, name, h, **kw):
         return cls(name, h.start, h.end, h.index, h.width, data=h.data, weight=h.weight, ex_index=h.ex_index, **kw)
 
+    @classmethod
+    def _from_handle(cls, h):
+        self = cls.__new__(cls)
+        self.h = C.c_void_p(h)
+        name = C.create_string_buffer(256)
+        attrs, examples, width, nnz = C.c_uint32(), C.c_uint32(), C.c_uint32(), C.c_uint64()
+        _check(lib().dsb200_dataset_info(self.h, name, C.c_int(256), C.byref(attrs), C.byref(examples), C.byref(width), C.byref(nnz)))
+        self.name, self.attributes, self.examples, self.width, self.nnz = name.value.decode(), attrs.value, examples.value, width.value, nnz.value
+        return self
+
     def load_sparse(self, start, end, index, data=None):
         """NNDataSet::LoadSparseData: replace the contents (host arrays are copied and uploaded)."""
         _check(lib().dsb200_dataset_load_sparse(self.h, _p(start), _p(end), _p(index), _p(data)))
@@ -106,6 +116,19 @@ class Dataset:
         if self.h:
             lib().dsb200_dataset_destroy(self.h)
             self.h = C.c_void_p()
+
+
+def load_netcdf(fname):
+    """LoadNetCDF (E/NNTypes.cpp:2456): every dataset of a NetCDF classic file."""
+    arr = (C.c_void_p * 16)()
+    n = C.c_int()
+    _check(lib().dsb200_datasets_load_netcdf(fname.encode(), arr, C.c_int(16), C.byref(n)))
+    return [Dataset._from_handle(arr[i]) for i in range(n.value)]
+
+
+def save_netcdf(fname, datasets):
+    """SaveNetCDF: the datasets into one NetCDF (CDF-5) file."""
+    _check(lib().dsb200_datasets_save_netcdf(fname.encode(), _handles(datasets), C.c_int(len(datasets))))
 
 
 def _handles(datasets):
@@ -125,6 +148,20 @@ class Network:
                                               C.c_int(len(datasets))))
         _check(lib().dsb200_network_load_datasets(self.h, _handles(datasets), C.c_int(len(datasets))))
         self.batch = batch
+
+    @classmethod
+    def from_netcdf(cls, fname, batch, datasets):
+        """LoadNeuralNetworkNetCDF + LoadDataSets."""
+        self = cls.__new__(cls)
+        self.h = C.c_void_p()
+        self.datasets = list(datasets)
+        _check(lib().dsb200_network_load_netcdf(C.byref(self.h), fname.encode(), C.c_uint32(batch)))
+        _check(lib().dsb200_network_load_datasets(self.h, _handles(datasets), C.c_int(len(datasets))))
+        self.batch = batch
+        return self
+
+    def save_netcdf(self, fname):
+        _check(lib().dsb200_network_save_netcdf(self.h, fname.encode()))
 
     def close(self):
         if self.h:
@@ -210,7 +247,7 @@ class Network:
 
 def autoencoder_json(hidden, error="ScaledMarginalCrossEntropy", smce=(1.0, 0.0, 1.0, 1.0), denoising_p=0.0,
                      sparseness=None, shuffle=False, in_name="gl_input", out_name="gl_output", activation="Sigmoid",
-                     out_activation="Sigmoid", init=("Gaussian", 0.01, 0.0)):
+                     out_activation="Sigmoid", init=("Gaussian", 0.01, 0.0), p_dropout=0.0):
     """JSON in the reference's layer-description language for a sparse-in / sparse-out autoencoder
     (shape of samples/movielens/config.json and benchmarks/dsstne/config.json)."""
     import json
@@ -219,6 +256,8 @@ def autoencoder_json(hidden, error="ScaledMarginalCrossEntropy", smce=(1.0, 0.0,
     for i, n in enumerate(hidden):
         layers.append({"Name": f"Hidden{i + 1}", "Kind": "Hidden", "Type": "FullyConnected", "N": int(n), "Activation": activation,
                        "Sparse": bool(sparseness is not None), "WeightInit": wi})
+        if p_dropout > 0:
+            layers[-1]["pDropout"] = float(p_dropout)
     layers.append({"Name": "Output", "Kind": "Output", "Type": "FullyConnected", "DataSet": out_name, "N": "auto",
                    "Activation": out_activation, "Sparse": True, "WeightInit": wi})
     cfg = {"Version": 0.8, "Name": "AE", "Kind": "FeedForward", "ShuffleIndices": bool(shuffle),

@@ -37,12 +37,12 @@ NNLayer::NNLayer(NNLayerDescriptor& d, uint32_t batch)
       _bSparse(d._attributes & NNLayer::Attributes::Sparse), _bFastSparse(false), _sparsenessPenalty_p(d._sparsenessPenalty_p),
       _sparsenessPenalty_beta(d._sparsenessPenalty_beta), _bDenoising(d._attributes & NNLayer::Attributes::Denoising),
       _weightNorm(d._weightNorm), _deltaNorm(d._deltaNorm), _parallelization(Serial), _bDirty(true), _bActivationPending(false),
-      _bDeltaReady(false), _priority(-1)
+      _bDeltaReady(false), _priority(-1), _dropoutCalls(0)
 {
     if (_type != FullyConnected) throw DsbEngineError("NNLayer: layer " + _name + ": only FullyConnected layers are on the dsstne_b200 hot path");
     if (_attributes & BatchNormalization) throw DsbEngineError("NNLayer: layer " + _name + ": batch normalisation is outside the hot path");
     if (!d._vSkip.empty()) throw DsbEngineError("NNLayer: layer " + _name + ": skip connections are outside the hot path");
-    if (_pDropout > (NNFloat)0.0) throw DsbEngineError("NNLayer: layer " + _name + ": dropout is a 'next' row (SURVEY 8f) and not built yet");
+    if (_pDropout >= (NNFloat)1.0) throw DsbEngineError("NNLayer: layer " + _name + ": pDropout must be below 1");
     _stride = _Nx * _Ny * _Nz * _Nw;
     _parallelization = Model;
     // E/NNLayer.cpp:108-112
@@ -136,7 +136,7 @@ bool NNLayer::FusedOutputEligible(ErrorFunction ef) const
     if (_kind != Output || !_pDataSet || !(_pDataSet->_attributes & NNDataSetEnums::Sparse)) return false;
     if (_pDataSet->_attributes & NNDataSetEnums::SparseIgnoreZero) return false;
     if (!getGpu()._pNetwork || !getGpu()._pNetwork->FusionEnabled()) return false;
-    if (_activation == SoftMax) return false;
+    if (_activation == SoftMax || _pDropout > (NNFloat)0.0) return false;
     if (ef == CrossEntropy || ef == ScaledMarginalCrossEntropy) return _activation == Sigmoid;
     return ef == L2 && (_activation == Sigmoid || _activation == Linear || _activation == Tanh || _activation == RectifiedLinear);
 }
@@ -147,7 +147,14 @@ void NNLayer::CalculateActivation(uint32_t batch)
                    "dsb200_activation");
 }
 
-void NNLayer::CalculateDropout(uint32_t batch) { (void)batch; }
+// NNLayer::CalculateDropout (E/NNLayer.cpp:1685-1708): the mask of call number c of this layer is drawn from the
+// counter-based generator with stream (layer order << 40 | c); see dsb200_dropout.
+void NNLayer::CalculateDropout(uint32_t batch)
+{
+    const uint64_t stream = 0x4000000000000000ull | ((uint64_t)(uint32_t)_priority << 40) | (_dropoutCalls++ & 0xffffffffffull);
+    getGpu().Check(dsb200_dropout(getGpu()._ctx, (int)_activation, GetUnitBuffer(), batch, _localStride, _stride, _minX * _Ny * _Nz * _Nw, _pDropout,
+                                  _ELUAlpha, _SELULambda, (uint64_t)getGpu()._seed, stream), "dsb200_dropout");
+}
 
 void NNLayer::ForwardPropagateFullyConnected(uint32_t position, uint32_t batch, bool bTraining)
 {
@@ -197,6 +204,7 @@ void NNLayer::ForwardPropagateFullyConnected(uint32_t position, uint32_t batch, 
             if (deferActivation) _bActivationPending = true;        // applied by the fused loss/delta pass
             else CalculateActivation(batch);                        // E/NNLayer.cpp:1157
         }
+        if (bTraining && _pDropout > (NNFloat)0.0 && !_bActivationPending) CalculateDropout(batch);   // E/NNLayer.cpp:1160-1161
         return;
     }
 
@@ -230,6 +238,7 @@ void NNLayer::ForwardPropagateFullyConnected(uint32_t position, uint32_t batch, 
             getGpu().Check(dsb200_add_bias(ctx, GetIncomingUnitBuffer(), _vIncomingWeight[i]->_pbBias->_pDevData, _localStride, batch), "dsb200_add_bias");
         if (deferActivation) _bActivationPending = true;
         else CalculateActivation(batch);
+        if (bTraining && _pDropout > (NNFloat)0.0 && !_bActivationPending) CalculateDropout(batch);   // E/NNLayer.cpp:1340-1341
     }
     // circulate activations to the outgoing larger layers (E/NNLayer.cpp:1340-1421)
     if (!_vOutgoingLargerLayer.empty()) {

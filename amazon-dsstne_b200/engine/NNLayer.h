@@ -65,6 +65,7 @@ private:
     unique_ptr<GpuBuffer<NNFloat>> _pbDelta;
     unique_ptr<GpuBuffer<NNFloat>> _pbDropout;
     int32_t                 _priority;
+    uint64_t                _dropoutCalls;        // masks drawn so far (stream id of the counter-based generator)
 
     NNLayer(NNLayerDescriptor& l, uint32_t batch);
     ~NNLayer();

@@ -6,6 +6,7 @@
 
 #include "../../include/dsstne_b200_engine.h"
 #include "NNNetwork.h"
+#include "NetCDF.h"
 
 using namespace std;
 
@@ -134,6 +135,88 @@ int dsb200_datasets_save_netcdf(const char* fname, dsb200_dataset** sets, int n)
     vector<NNDataSetBase*> v;
     for (int i = 0; i < n; i++) v.push_back(DS(sets[i]));
     if (!SaveNetCDF(fname, v)) throw DsbEngineError(string("SaveNetCDF failed for ") + fname);
+    DSB_ENGINE_CATCH
+}
+
+int dsb200_netcdf_describe(const char* fname, char* buf, size_t cap)
+{
+    DSB_ENGINE_TRY
+    if (!fname || !buf || !cap) throw DsbEngineError("dsb200_netcdf_describe: null argument");
+    const string text = nc::File(fname).describe();
+    strncpy(buf, text.c_str(), cap - 1);
+    buf[cap - 1] = 0;
+    DSB_ENGINE_CATCH
+}
+
+int dsb200_netcdf_read_var(const char* fname, const char* var, double* out, uint64_t cap, uint64_t* n)
+{
+    DSB_ENGINE_TRY
+    if (!fname || !var) throw DsbEngineError("dsb200_netcdf_read_var: null argument");
+    nc::File f(fname);
+    const nc::Var* v = f.var(var);
+    if (!v) throw DsbEngineError(string("dsb200_netcdf_read_var: no variable ") + var + " in " + fname);
+    if (n) *n = v->nelems;
+    if (out) {
+        if (cap < v->nelems) throw DsbEngineError("dsb200_netcdf_read_var: output buffer too small");
+        vector<double> tmp;
+        f.read(*v, tmp);
+        memcpy(out, tmp.data(), tmp.size() * sizeof(double));
+    }
+    DSB_ENGINE_CATCH
+}
+
+int dsb200_netcdf_write_sparse(const char* fname, int version, const char* name, uint32_t attributes, int dataType, uint32_t width, uint32_t examples,
+                               uint32_t uniqueExamples, const uint64_t* s, const uint64_t* e, const uint32_t* idx, const void* data, const float* weight,
+                               const uint32_t* index)
+{
+    DSB_ENGINE_TRY
+    if (!fname || !name || !s || !e || !idx || !uniqueExamples) throw DsbEngineError("dsb200_netcdf_write_sparse: null argument");
+    const uint64_t nnz = e[uniqueExamples - 1];
+    attributes |= NNDataSetEnums::Sparse;
+    if (!data) attributes |= NNDataSetEnums::Boolean;
+    if (weight) attributes |= NNDataSetEnums::Weighted;
+    if (index) attributes |= NNDataSetEnums::Indexed;
+    nc::Writer w(version);
+    const bool classic = version != 5;
+    const nc::Type U = classic ? nc::NC_INT : nc::NC_UINT;
+    w.put_att("datasets", nc::NC_UINT, 1);
+    w.put_att("name0", string(name));
+    w.put_att("attributes0", nc::NC_UINT, attributes);
+    w.put_att("kind0", nc::NC_UINT, NNDataSetEnums::Numeric);
+    w.put_att("dataType0", nc::NC_UINT, dataType);
+    w.put_att("dimensions0", nc::NC_UINT, 1);
+    w.put_att("width0", nc::NC_UINT, width);
+    const bool uniq = index != NULL || uniqueExamples != examples;
+    if (uniq) w.add_dim("uniqueExamplesDim0", uniqueExamples);
+    w.add_dim("examplesDim0", examples);
+    w.add_dim("sparseDataDim0", nnz);
+    const string rowDim = uniq ? "uniqueExamplesDim0" : "examplesDim0";
+    if (nnz > 0x7fffffffull && classic) throw DsbEngineError("dsb200_netcdf_write_sparse: more than 2^31 data points need CDF-5");
+    vector<uint32_t> s32(s, s + uniqueExamples), e32(e, e + uniqueExamples);
+    if (nnz <= 0xffffffffull) {
+        w.add_var("sparseStart0", U, rowDim, s32.data());
+        w.add_var("sparseEnd0", U, rowDim, e32.data());
+    } else {
+        w.add_var("sparseStart0", nc::NC_UINT64, rowDim, s);
+        w.add_var("sparseEnd0", nc::NC_UINT64, rowDim, e);
+    }
+    w.add_var("sparseIndex0", U, "sparseDataDim0", idx);
+    if (data) {
+        nc::Type t;
+        switch (dataType) {
+        case NNDataSetEnums::UInt: t = U; break;
+        case NNDataSetEnums::Int: t = nc::NC_INT; break;
+        case NNDataSetEnums::Float: t = nc::NC_FLOAT; break;
+        case NNDataSetEnums::Double: t = nc::NC_DOUBLE; break;
+        case NNDataSetEnums::UChar: t = classic ? nc::NC_BYTE : nc::NC_UBYTE; break;
+        case NNDataSetEnums::Char: t = nc::NC_BYTE; break;
+        default: throw DsbEngineError("dsb200_netcdf_write_sparse: unsupported data type");
+        }
+        w.add_var("sparseData0", t, "sparseDataDim0", data);
+    }
+    if (weight) w.add_var("dataWeight0", nc::NC_FLOAT, rowDim, weight);
+    if (index) w.add_var("index0", U, "examplesDim0", index);
+    w.write(fname);
     DSB_ENGINE_CATCH
 }
 

@@ -232,6 +232,13 @@ int dsb200_topk_kv(dsb200_ctx*, const float* pKey, const uint32_t* pValue, uint3
  * (E/NNTypes.cpp:1617-1629): counter-based generator, pOut[i] = U(0,1] as a pure function of
  * (seed, stream, i) -- reproducible for any launch geometry.                                    */
 int dsb200_fill_uniform(dsb200_ctx*, float* pOut, uint64_t n, uint64_t seed, uint64_t stream);
+/* NNLayer::CalculateDropout (E/NNLayer.cpp:1685-1708; kCalculateDropout / kCalculateScaledBiasedDropout, E/kernels.h:48-49,
+ * E/kernels.cu:4497-4537), random draw fused in: pUnit[b][c] = (r < p) ? target : a * pUnit[b][c] + b' with r the uniform
+ * dsb200_fill_uniform would give element b * fullStride + colOffset + c (fullStride / colOffset: the un-sharded layer width and
+ * this rank's first unit, so the mask is independent of the sharding).  Sigmoid drops to 0.5 unscaled, ELU / SELU use the
+ * self-normalising affine form, every other activation drops to 0 and rescales by 1 / (1 - p).                              */
+int dsb200_dropout(dsb200_ctx*, int activation, float* pUnit, uint32_t batch, uint32_t stride, uint32_t fullStride, uint32_t colOffset,
+                   float p, float eluAlpha, float seluLambda, uint64_t seed, uint64_t stream);
 
 /* ------------------------------------------------------------------ a15
  * NNLayer::Reduce / Gather and NNNetwork::P2P_Allreduce (E/NNLayer.cpp:2702-2826,

@@ -53,6 +53,17 @@ int dsb200_dataset_destroy(dsb200_dataset* d);
 int dsb200_datasets_load_netcdf(const char* fname, dsb200_dataset** out, int maxOut, int* nOut);
 int dsb200_datasets_save_netcdf(const char* fname, dsb200_dataset** sets, int n);
 int dsb200_dataset_info(dsb200_dataset* d, char* name, int nameCap, uint32_t* attributes, uint32_t* examples, uint32_t* width, uint64_t* nnz);
+/* Host-only NetCDF helpers (no GPU, no engine start-up): the classic-format (CDF-1/2/5) reader / writer the engine uses.
+ *   describe     `ncdump -h`-like text of any classic file into buf
+ *   read_var     a whole variable converted to double (cap elements available in out; *n = elements in the file)
+ *   write_sparse one sparse dataset in the schema generateNetCDF emits (U/NetCDFhelper.cpp:332-416); version 5 = CDF-5
+ *                (uint / uint64 variables, what the engine itself writes), 2 = CDF-2 with int variables for tools that
+ *                only know the classic types; data / weight / exIndex may be NULL                                       */
+int dsb200_netcdf_describe(const char* fname, char* buf, size_t cap);
+int dsb200_netcdf_read_var(const char* fname, const char* var, double* out, uint64_t cap, uint64_t* n);
+int dsb200_netcdf_write_sparse(const char* fname, int version, const char* name, uint32_t attributes, int dataType, uint32_t width,
+                               uint32_t examples, uint32_t uniqueExamples, const uint64_t* sparseStart, const uint64_t* sparseEnd,
+                               const uint32_t* sparseIndex, const void* sparseData, const float* dataWeight, const uint32_t* index);
 
 /* LoadNeuralNetworkJSON / LoadNeuralNetworkNetCDF / SaveNetCDF / delete (E/NNNetwork.h:287-291) */
 int dsb200_network_load_json(dsb200_network** out, const char* jsonText, uint32_t batch, dsb200_dataset** sets, int nSets);

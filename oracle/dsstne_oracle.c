@@ -724,3 +724,22 @@ int orc_weight_outgoing_larger(uint32_t inputStride, uint32_t outputStride)
 {   /* E/NNWeight.cpp:435-457 */
     return (uint64_t)outputStride * 3 > (uint64_t)inputStride * 2;
 }
+
+/* E/NNLayer.cpp:1685-1708, E/kernels.cu:4497-4537 */
+void orc_dropout(int activation, float* unit, const float* random, uint32_t batch, uint32_t stride, float p, float eluAlpha, float seluLambda)
+{
+    const size_t size = (size_t)batch * stride;
+    if (activation == ORC_ACT_ELU || activation == ORC_ACT_SELU) {
+        const float lambda = (activation == ORC_ACT_SELU) ? seluLambda : 1.0f;
+        const float alpha = -lambda * eluAlpha;
+        const float q = 1.0f - p;
+        const float a = 1.0f / sqrtf(q + alpha * alpha * p * q);
+        const float b = -a * p * alpha;
+        const float target = a * alpha + b;
+        for (size_t i = 0; i < size; i++) unit[i] = (random[i] < p) ? target : a * unit[i] + b;
+    } else {
+        const float target = (activation == ORC_ACT_SIGMOID) ? 0.5f : 0.0f;
+        const float scale = (target == 0.0f) ? 1.0f / (1.0f - p) : 1.0f;
+        for (size_t i = 0; i < size; i++) unit[i] = (random[i] < p) ? target : scale * unit[i];
+    }
+}

@@ -203,7 +203,15 @@ typedef struct orc_network {
     float*     delta[ORC_MAX_WEIGHTS + 1];
     /* transposed input matrix */
     uint32_t*  tStart; uint32_t* tEnd; uint32_t* tIndex; float* tData; uint32_t tCapacity;
+    /* dropout of hidden layer l (training only): probability and the caller-supplied uniform randoms [maxBatch][size[l]] */
+    float      pDropout[ORC_MAX_WEIGHTS + 1];
+    const float* dropoutRandom[ORC_MAX_WEIGHTS + 1];
 } orc_network;
+
+/* NNLayer::CalculateDropout (E/NNLayer.cpp:1685-1708) with kCalculateDropout / kCalculateScaledBiasedDropout
+ * (E/kernels.cu:4497-4537): unit = (r < p) ? target : scale * unit; Sigmoid drops to 0.5 unscaled, ELU / SELU use the
+ * self-normalising affine form, everything else drops to 0 and rescales by 1 / (1 - p).                            */
+void orc_dropout(int activation, float* unit, const float* random, uint32_t batch, uint32_t stride, float p, float eluAlpha, float seluLambda);
 
 orc_network* orc_net_create(int nWeights, const uint32_t* sizes, const int* activations,
                             int errorFunction, int trainingMode, uint32_t maxBatch);

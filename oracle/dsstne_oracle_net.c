@@ -82,6 +82,8 @@ void orc_net_forward(orc_network* net, const orc_csr* in, uint32_t position, uin
         else                                                                          /* E/NNLayer.cpp:1057-1086 */
             orc_gemm_fwd(batch, net->size[l - 1], S, net->unit[l - 1], net->W[l - 1], 1.0f, net->unit[l]);
         orc_activation(net->activation[l], net->unit[l], batch, S, 0.0f, 0.0f, 0.0f);  /* E/NNLayer.cpp:1157 */
+        if (training && l < net->nWeights && net->pDropout[l] > 0.0f && net->dropoutRandom[l])    /* E/NNLayer.cpp:1160 */
+            orc_dropout(net->activation[l], net->unit[l], net->dropoutRandom[l], batch, S, net->pDropout[l], 1.0f, 1.050701f);
     }
 }
 
@@ -112,7 +114,8 @@ static void orc_net_backprop(orc_network* net, const orc_csr* out, uint32_t posi
             if (net->sparsePenalty[l] && net->sparsenessPenalty_beta > 0.0f)
                 orc_sparseness_penalty(batch, S, net->unit[l], net->delta[l],
                                        net->sparsenessPenalty_p, net->sparsenessPenalty_beta);
-            orc_hadamard(net->activation[l], (uint64_t)batch * S, 1.0f, net->unit[l], net->delta[l], 0.0f, 0.0f, 0.0f);
+            orc_hadamard(net->activation[l], (uint64_t)batch * S, 1.0f / (1.0f - net->pDropout[l]), net->unit[l], net->delta[l],
+                         0.0f, 0.0f, 0.0f);                          /* scale: E/NNLayer.cpp:2137 */
         }
         float galpha = -1.0f / (float)batch;                             /* E/NNLayer.cpp:2213 (sharingCount 1) */
         if (l == 1)                                                      /* E/NNLayer.cpp:2217-2220 */

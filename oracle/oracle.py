@@ -200,6 +200,13 @@ def hadamard(act, unit, delta, scale=1.0, slope=0.0, alpha=0.0, lam=0.0):
     return delta
 
 
+def dropout(act, unit, random, p, elu_alpha=1.0, selu_lambda=1.050701):
+    batch, stride = unit.shape
+    lib().orc_dropout(C.c_int(act), _f32(unit), _f32(random), C.c_uint32(batch), C.c_uint32(stride), C.c_float(p),
+                      C.c_float(elu_alpha), C.c_float(selu_lambda))
+    return unit
+
+
 def gemm_fwd(A, W, C_, beta=1.0):
     B, k = A.shape
     n = W.shape[1]
@@ -271,7 +278,8 @@ class _NetStruct(C.Structure):
                 ("vb", C.POINTER(C.c_float) * 8), ("gvb", C.POINTER(C.c_float) * 8),
                 ("unit", C.POINTER(C.c_float) * 9), ("delta", C.POINTER(C.c_float) * 9),
                 ("tStart", C.POINTER(C.c_uint32)), ("tEnd", C.POINTER(C.c_uint32)),
-                ("tIndex", C.POINTER(C.c_uint32)), ("tData", C.POINTER(C.c_float)), ("tCapacity", C.c_uint32)]
+                ("tIndex", C.POINTER(C.c_uint32)), ("tData", C.POINTER(C.c_float)), ("tCapacity", C.c_uint32),
+                ("pDropout", C.c_float * 9), ("dropoutRandom", C.POINTER(C.c_float) * 9)]
 
 
 class Network:
@@ -318,6 +326,13 @@ class Network:
 
     def delta(self, l, batch):
         return self._arr(self.s.delta[l], (self.max_batch, self.sizes[l]))[:batch]
+
+    def set_dropout(self, l, p, random):
+        """hidden layer l drops with probability p using the uniform randoms `random` [max_batch][size[l]] (kept alive here)."""
+        self._drop = getattr(self, "_drop", {})
+        self._drop[l] = np.ascontiguousarray(random, dtype=np.float32)
+        self.s.pDropout[l] = p
+        self.s.dropoutRandom[l] = self._drop[l].ctypes.data_as(C.POINTER(C.c_float))
 
     def set_input(self, csr, batch):
         self._in_view = csr.view()

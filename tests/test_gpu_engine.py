@@ -42,12 +42,12 @@ def fill_uniform_host(n, seed, stream):
 
 
 def build_pair(eng, orc, sizes, h, batch, mode, error="ScaledMarginalCrossEntropy", smce=(1.0, 0.0, 1.0, 1.0), denoising_p=0.0,
-               sparseness=None, fusion=True):
+               sparseness=None, fusion=True, p_dropout=0.0):
     from dsstne_b200 import datagen
     hidden = sizes[1:-1]
     ds_in = eng.Dataset.from_host_csr("gl_input", h)
     ds_out = eng.Dataset.from_host_csr("gl_output", h)
-    net = eng.Network(eng.autoencoder_json(hidden, error=error, smce=smce, denoising_p=denoising_p, sparseness=sparseness),
+    net = eng.Network(eng.autoencoder_json(hidden, error=error, smce=smce, denoising_p=denoising_p, sparseness=sparseness, p_dropout=p_dropout),
                       batch, [ds_in, ds_out])
     net.set_training_mode(mode)
     net.set_fusion(fusion)
@@ -159,6 +159,32 @@ def test_denoising_uses_the_counter_based_generator(eng, orc):
     net.close()
 
 
+def test_dropout_training_matches_oracle(eng, orc):
+    """pDropout 0.5 on every hidden layer (the reference's benchmark config, benchmarks/dsstne/config.json): the engine draws
+    each mask inside dsb200_dropout from (seed, stream = 1<<62 | layer order << 40 | call number); the oracle network is fed
+    the numpy restatement of the same uniforms.  Prediction must not drop anything."""
+    sizes, batch = [2048, 128, 64, 2048], 128
+    h = tiny(examples=256, width=2048)
+    net, onet, names, _ = build_pair(eng, orc, sizes, h, batch, orc.SGD, p_dropout=0.5)
+    oc = to_oracle(orc, h)
+    onet.set_input(oc, batch)
+    for step, pos in enumerate((0, 128, 0)):
+        for l in (1, 2):
+            stream = (1 << 62) | (l << 40) | step
+            onet.set_dropout(l, 0.5, fill_uniform_host(batch * sizes[l], 12134, stream).reshape(batch, sizes[l]))
+        got = net.train_step(pos, 0.05)
+        want, _ = onet.train_step(oc, oc, pos, batch, 0.05)
+        assert abs(got - want) <= TOL * abs(want), f"step {step}"
+    for i in range(3):
+        W, b = net.get_weights(names[i], names[i + 1])
+        assert rel_err(W.reshape(onet.W(i).shape), onet.W(i)) < TOL
+    net.set_position(0)
+    net.predict_batch()
+    onet.forward(oc, 0, batch)                                      # training=False: no dropout
+    assert rel_err(net.get_units("Output").reshape(batch, 2048), onet.unit(3, batch)) < TOL
+    net.close()
+
+
 def test_predict_and_topk_with_filter(eng, orc):
     sizes, batch = [2048, 128, 2048], 256
     h = tiny(examples=256, width=2048)
@@ -174,6 +200,38 @@ def test_predict_and_topk_with_filter(eng, orc):
     np.testing.assert_array_equal(key, want_k)
     np.testing.assert_array_equal(val, want_v)
     net.close()
+
+
+def test_netcdf_datasets_and_network_checkpoint_round_trip(eng, orc, tmp_path):
+    """SaveNetCDF -> LoadNetCDF of the datasets and NNNetwork::SaveNetCDF -> LoadNeuralNetworkNetCDF of the trained
+    network reproduce the same training step and the same predictions (checkpoint / resume, E/NNNetwork.cpp:1678-1691)."""
+    sizes, batch = [2048, 128, 2048], 256
+    h = tiny(examples=512, width=2048)
+    net, onet, names, (ds_in, ds_out) = build_pair(eng, orc, sizes, h, batch, orc.MOMENTUM)
+    for pos in (0, 256):
+        net.train_step(pos, 0.025, 1e-4, 0.0, 0.5, 0.0)
+    data_nc, net_nc = str(tmp_path / "data.nc"), str(tmp_path / "net.nc")
+    eng.save_netcdf(data_nc, [ds_in, ds_out])
+    net.save_netcdf(net_nc)
+    loaded = eng.load_netcdf(data_nc)
+    assert [d.name for d in loaded] == ["gl_input", "gl_output"] and loaded[0].examples == 512 and loaded[0].width == 2048
+    assert loaded[0].nnz == h.nnz and loaded[0].attributes & 3 == 3                     # Sparse | Boolean
+    net2 = eng.Network.from_netcdf(net_nc, batch, loaded)
+    net2.set_training_mode(orc.MOMENTUM)
+    for i in range(2):
+        Wa, ba = net.get_weights(names[i], names[i + 1])
+        Wb, bb = net2.get_weights(names[i], names[i + 1])
+        np.testing.assert_array_equal(Wa, Wb)
+        np.testing.assert_array_equal(ba, bb)
+    net.set_position(0); net.predict_batch()
+    net2.set_position(0); net2.predict_batch()
+    np.testing.assert_array_equal(net.get_units("Output"), net2.get_units("Output"))
+    # the optimizer state is not part of a DSSTNE checkpoint (weights + biases only): compare a velocity-free step
+    net.set_training_mode(orc.SGD); net2.set_training_mode(orc.SGD)
+    a = net.train_step(256, 0.025, 1e-4)
+    b = net2.train_step(256, 0.025, 1e-4)
+    assert a == b
+    net.close(); net2.close()
 
 
 def test_engine_rejects_features_outside_the_hot_path(eng):

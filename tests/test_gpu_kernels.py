@@ -455,3 +455,30 @@ def test_topk_kv_merge_variant(ctx, orc, dsb):
     ctx.sync()
     np.testing.assert_array_equal(host(ok), ref_k)
     np.testing.assert_array_equal(u32(ov), ref_v)
+
+
+@pytest.mark.parametrize("act", [0, 1, 2, 10, 12], ids=["sigmoid", "tanh", "relu", "elu", "selu"])
+def test_dropout_matches_oracle_with_the_same_uniforms(ctx, orc, act):
+    """dsb200_dropout draws its uniforms from the counter-based generator of dsb200_fill_uniform (restated in numpy in
+    test_gpu_engine.fill_uniform_host); fed the same uniforms the oracle's NNLayer::CalculateDropout must agree exactly,
+    also when the layer is split over column shards (mask independent of the sharding)."""
+    import torch
+    from test_gpu_engine import fill_uniform_host
+    B, S, p, seed, stream = 64, 200, 0.35, 12134, 77
+    rng = np.random.default_rng(act)
+    u = rng.standard_normal((B, S)).astype(np.float32)
+    rnd = fill_uniform_host(B * S, seed, stream).reshape(B, S)
+    want = orc.dropout(act, u.copy(), rnd, p)
+    d = torch.from_numpy(u.copy()).cuda()
+    ctx.dropout(act, d, p, seed, stream)
+    ctx.sync()
+    got = d.cpu().numpy()
+    assert rel_err(got, want) < 1e-6
+    if act not in (10, 12):                                     # a * x + b of ELU / SELU may contract to an FMA on the device
+        np.testing.assert_array_equal(got, want)
+    assert 0.25 < float((rnd < p).mean()) < 0.45
+    lo, hi = 50, 130                                            # a column shard [50, 130) of the same layer
+    d2 = torch.from_numpy(np.ascontiguousarray(u[:, lo:hi])).cuda()
+    ctx.dropout(act, d2, p, seed, stream, full_stride=S, col_offset=lo)
+    ctx.sync()
+    np.testing.assert_array_equal(d2.cpu().numpy(), got[:, lo:hi])

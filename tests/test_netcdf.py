@@ -1,0 +1,127 @@
+"""NetCDF classic-format reader / writer of the engine (amazon-dsstne_b200/engine/NetCDF.cpp), on the CPU.
+
+Independent cross-checks with scipy.io.netcdf_file (a separate implementation of CDF-1 / CDF-2):
+  * a dataset file in the schema generateNetCDF emits (U/NetCDFhelper.cpp:332-416) written by OUR writer in CDF-2 is read
+    back by scipy with identical contents;
+  * a file written by scipy (CDF-1 and CDF-2, classic int types) is parsed by OUR reader;
+  * CDF-5 (uint / uint64 variables, what the engine writes) round-trips through our own reader, header fields included;
+  * netCDF-4 / HDF5 containers are rejected with the conversion hint, not mis-parsed."""
+import ctypes as C
+import os
+
+import numpy as np
+import pytest
+from scipy.io import netcdf_file
+
+from helpers import tiny
+
+
+def describe(lib, path):
+    buf = C.create_string_buffer(1 << 16)
+    rc = lib.dsb200_netcdf_describe(path.encode(), buf, C.c_size_t(len(buf)))
+    return rc, buf.value.decode()
+
+
+def read_var(lib, path, name):
+    n = C.c_uint64()
+    assert lib.dsb200_netcdf_read_var(path.encode(), name.encode(), None, C.c_uint64(0), C.byref(n)) == 0
+    out = np.zeros(n.value, dtype=np.float64)
+    assert lib.dsb200_netcdf_read_var(path.encode(), name.encode(), out.ctypes.data_as(C.c_void_p), C.c_uint64(out.size), C.byref(n)) == 0
+    return out
+
+
+def write_sparse(lib, path, version, name, h, data=None, weight=None, index=None, dtype=0, examples=None):
+    uniq = len(h.start)
+    lib.dsb200_netcdf_write_sparse.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, C.c_uint32,
+                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    p = lambda a: None if a is None else a.ctypes.data_as(C.c_void_p)
+    return lib.dsb200_netcdf_write_sparse(path.encode(), version, name.encode(), 0, dtype, h.width, examples or uniq, uniq, p(h.start), p(h.end),
+                                          p(h.index), p(data), p(weight), p(index))
+
+
+def test_our_cdf2_writer_is_read_by_scipy(dsb, tmp_path):
+    lib = dsb.lib()
+    h = tiny(examples=300, width=2048)
+    vals = np.random.default_rng(1).uniform(0.5, 5.0, h.nnz).astype(np.float32)
+    path = str(tmp_path / "gl_input.nc")
+    assert write_sparse(lib, path, 2, "gl_input", h, data=vals, dtype=4) == 0
+    with netcdf_file(path, "r", mmap=False) as f:
+        assert f.version_byte == 2
+        assert f.datasets == 1 and f.name0 == b"gl_input" and f.width0 == 2048 and f.dataType0 == 4 and f.dimensions0 == 1
+        assert f.attributes0 == 1                                             # Sparse
+        assert f.dimensions["examplesDim0"] == 300 and f.dimensions["sparseDataDim0"] == h.nnz
+        np.testing.assert_array_equal(f.variables["sparseStart0"][:], h.start.astype(np.int64))
+        np.testing.assert_array_equal(f.variables["sparseEnd0"][:], h.end.astype(np.int64))
+        np.testing.assert_array_equal(f.variables["sparseIndex0"][:], h.index.astype(np.int64))
+        np.testing.assert_array_equal(f.variables["sparseData0"][:], vals)
+
+
+@pytest.mark.parametrize("version", [1, 2])
+def test_scipy_written_file_is_parsed_by_our_reader(dsb, tmp_path, version):
+    lib = dsb.lib()
+    h = tiny(examples=64, width=512)
+    path = str(tmp_path / f"scipy_v{version}.nc")
+    with netcdf_file(path, "w", version=version) as f:
+        f.datasets = np.int32(1)
+        f.name0 = "gl_output"
+        f.attributes0 = np.int32(3)                                           # Sparse + Boolean
+        f.kind0 = np.int32(0)
+        f.dataType0 = np.int32(0)
+        f.dimensions0 = np.int32(1)
+        f.width0 = np.int32(512)
+        f.createDimension("examplesDim0", 64)
+        f.createDimension("sparseDataDim0", h.nnz)
+        for name, arr, dim in (("sparseStart0", h.start, "examplesDim0"), ("sparseEnd0", h.end, "examplesDim0"), ("sparseIndex0", h.index, "sparseDataDim0")):
+            v = f.createVariable(name, "i4", (dim,))
+            v[:] = arr.astype(np.int32)
+        w = f.createVariable("dataWeight0", "f4", ("examplesDim0",))
+        w[:] = np.linspace(0.5, 1.5, 64, dtype=np.float32)
+    rc, text = describe(lib, path)
+    assert rc == 0, text
+    assert f"(CDF-{version})" in text and "examplesDim0 = 64" in text and 'name0 = "gl_output"' in text and "int sparseIndex0(sparseDataDim0)" in text
+    np.testing.assert_array_equal(read_var(lib, path, "sparseStart0"), h.start.astype(np.float64))
+    np.testing.assert_array_equal(read_var(lib, path, "sparseEnd0"), h.end.astype(np.float64))
+    np.testing.assert_array_equal(read_var(lib, path, "sparseIndex0"), h.index.astype(np.float64))
+    np.testing.assert_array_equal(read_var(lib, path, "dataWeight0"), np.linspace(0.5, 1.5, 64, dtype=np.float32).astype(np.float64))
+
+
+def test_cdf5_round_trip_with_unsigned_types_weights_and_index(dsb, tmp_path):
+    lib = dsb.lib()
+    h = tiny(examples=100, width=1024)
+    rng = np.random.default_rng(2)
+    weight = rng.uniform(0.5, 1.5, 100).astype(np.float32)
+    index = rng.integers(0, 100, 250).astype(np.uint32)
+    vals = rng.integers(0, 255, h.nnz).astype(np.uint8)
+    path = str(tmp_path / "indexed.nc")
+    assert write_sparse(lib, path, 5, "indexed", h, data=vals, weight=weight, index=index, dtype=8, examples=250) == 0
+    rc, text = describe(lib, path)
+    assert rc == 0, text
+    assert "(CDF-5)" in text and "uniqueExamplesDim0 = 100" in text and "examplesDim0 = 250" in text
+    assert "uint sparseStart0(uniqueExamplesDim0)" in text and "ubyte sparseData0(sparseDataDim0)" in text and "uint index0(examplesDim0)" in text
+    assert "attributes0 = 193" in text                                        # Sparse | Indexed | Weighted
+    np.testing.assert_array_equal(read_var(lib, path, "sparseEnd0"), h.end.astype(np.float64))
+    np.testing.assert_array_equal(read_var(lib, path, "sparseData0"), vals.astype(np.float64))
+    np.testing.assert_array_equal(read_var(lib, path, "index0"), index.astype(np.float64))
+    np.testing.assert_array_equal(read_var(lib, path, "dataWeight0"), weight.astype(np.float64))
+    # every variable starts on a 4-byte boundary and the file ends with the last one (classic-format layout rule)
+    begins = [int(l.split("begin=")[1].split()[0]) for l in text.splitlines() if "begin=" in l]
+    sizes = [int(l.split("vsize=")[1].split()[0]) for l in text.splitlines() if "vsize=" in l]
+    assert all(b % 4 == 0 for b in begins) and begins == sorted(begins)
+    assert os.path.getsize(path) == begins[-1] + sizes[-1]
+
+
+def test_hdf5_and_garbage_are_rejected_loudly(dsb, tmp_path):
+    lib = dsb.lib()
+    lib.dsb200_engine_last_error.restype = C.c_char_p
+    p1 = tmp_path / "nc4.nc"
+    p1.write_bytes(b"\x89HDF\r\n\x1a\n" + bytes(64))
+    rc, _ = describe(lib, str(p1))
+    assert rc != 0 and b"nccopy -k cdf5" in lib.dsb200_engine_last_error()
+    p2 = tmp_path / "junk.nc"
+    p2.write_bytes(b"hello world, not a netcdf file")
+    rc, _ = describe(lib, str(p2))
+    assert rc != 0 and b"bad magic" in lib.dsb200_engine_last_error()
+    p3 = tmp_path / "short.nc"
+    p3.write_bytes(b"CDF\x05\x00\x00")
+    rc, _ = describe(lib, str(p3))
+    assert rc != 0 and b"truncated" in lib.dsb200_engine_last_error()
