@@ -2,6 +2,10 @@
 // probing, cuBLAS/cuRAND/cuDNN handles) with: rank from the launcher, one dsb200_ctx, NCCL.
 #include "GpuTypes.h"
 
+#include <sys/stat.h>
+#include <time.h>
+#include <unistd.h>
+
 static GpuContext g_gpu;
 GpuContext& getGpu() { return g_gpu; }
 
@@ -27,10 +31,44 @@ static int env_int(const char* name, int dflt)
 
 // torchrun-style environment instead of MPI_Init (E/GpuTypes.cpp:62-140): RANK / WORLD_SIZE /
 // LOCAL_RANK.  The NCCL unique id has to be handed in by the launcher for nranks > 1.
+// For the command line tools (train / predict started by torchrun or any launcher that sets those variables) the id
+// is exchanged through a small file: rank 0 writes it, the others wait for it.  DSB200_RENDEZVOUS_FILE names the file;
+// the default is /tmp/dsb200_nccl_<MASTER_PORT>_<run id>.
 void GpuContext::Startup(int argc, char** argv)
 {
     (void)argc; (void)argv;
-    Startup(env_int("RANK", 0), env_int("WORLD_SIZE", 1), env_int("LOCAL_RANK", 0), nullptr);
+    const int rank = env_int("RANK", 0), nranks = env_int("WORLD_SIZE", 1), local = env_int("LOCAL_RANK", 0);
+    if (nranks <= 1) { Startup(rank, nranks, local, nullptr); return; }
+    std::string path;
+    if (const char* f = getenv("DSB200_RENDEZVOUS_FILE")) path = f;
+    else {
+        const char* port = getenv("MASTER_PORT");
+        const char* run = getenv("TORCHELASTIC_RUN_ID");
+        path = std::string("/tmp/dsb200_nccl_") + (port ? port : "0") + "_" + (run ? run : "default");
+    }
+    unsigned char id[128];
+    if (rank == 0) {
+        if (dsb200_comm_unique_id(id)) throw DsbEngineError("GpuContext::Startup: cannot create the NCCL unique id");
+        const std::string tmp = path + ".tmp";
+        FILE* f = fopen(tmp.c_str(), "wb");
+        if (!f || fwrite(id, 1, sizeof(id), f) != sizeof(id)) throw DsbEngineError("GpuContext::Startup: cannot write " + tmp);
+        fclose(f);
+        if (rename(tmp.c_str(), path.c_str()) != 0) throw DsbEngineError("GpuContext::Startup: cannot publish " + path);
+    } else {
+        const time_t started = time(nullptr);
+        bool ok = false;
+        for (int tries = 0; tries < 1200 && !ok; tries++) {                      // up to two minutes
+            struct stat st;
+            if (stat(path.c_str(), &st) == 0 && st.st_size == (off_t)sizeof(id) && st.st_mtime + 30 >= started) {   // ignore leftovers of older runs
+                FILE* f = fopen(path.c_str(), "rb");
+                if (f) { ok = fread(id, 1, sizeof(id), f) == sizeof(id); fclose(f); }
+            }
+            if (!ok) usleep(100000);
+        }
+        if (!ok) throw DsbEngineError("GpuContext::Startup: rank " + std::to_string(rank) + " never saw the NCCL id file " + path);
+    }
+    Startup(rank, nranks, local, id);
+    if (rank == 0) { usleep(2000000); remove(path.c_str()); }                    // everyone has joined the communicator by now
 }
 
 void GpuContext::Startup(int rank, int nranks, int device, const void* ncclUniqueId128)

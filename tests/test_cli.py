@@ -1,0 +1,95 @@
+"""Command line tools (amazon-dsstne_b200/bin: generateNetCDF, train, predict -- the reference's U/NetCDFGenerator.cpp,
+U/Train.cpp, U/Predict.cpp) end to end on a small synthetic "ratings" file, the shape of samples/movielens/
+run_movielens_sample.sh.  generateNetCDF is host-only and runs in the CPU suite; train / predict need the GPU."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+BIN = os.path.join(ROOT, "amazon-dsstne_b200", "bin")
+CONFIG = """{
+    "Version" : 0.8, "Name" : "AE", "Kind" : "FeedForward",
+    "SparsenessPenalty" : { "p" : 0.5, "beta" : 2.0 },
+    "ShuffleIndices" : false,
+    "Denoising" : { "p" : 0.2 },
+    "ScaledMarginalCrossEntropy" : { "oneTarget" : 1.0, "zeroTarget" : 0.0, "oneScale" : 1.0, "zeroScale" : 1.0 },
+    "Layers" : [
+        { "Name" : "Input", "Kind" : "Input", "N" : "auto", "DataSet" : "gl_input", "Sparse" : true },
+        { "Name" : "Hidden", "Kind" : "Hidden", "Type" : "FullyConnected", "N" : 128, "Activation" : "Sigmoid", "Sparse" : true },
+        { "Name" : "Output", "Kind" : "Output", "Type" : "FullyConnected", "DataSet" : "gl_output", "N" : "auto", "Activation" : "Sigmoid", "Sparse" : true }
+    ],
+    "ErrorFunction" : "ScaledMarginalCrossEntropy"
+}"""
+
+
+def write_ratings(path, users=600, items=300, seed=3):
+    """Two taste groups: users of group g rate items of group g -- a trained autoencoder must recommend inside the group."""
+    rng = np.random.default_rng(seed)
+    rows = {}
+    with open(path, "w") as f:
+        for u in range(users):
+            g = u % 2
+            liked = rng.choice(np.arange(g * items // 2, (g + 1) * items // 2), size=12, replace=False)
+            rows[f"u{u}"] = [f"i{i}" for i in liked]
+            f.write(f"u{u}\t" + ":".join(f"i{i},{1000 + k}" for k, i in enumerate(liked)) + "\n")
+    return rows
+
+
+def run(cmd, cwd):
+    r = subprocess.run(cmd, cwd=cwd, capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stdout[-3000:] + r.stderr[-2000:]
+    return r.stdout
+
+
+def test_generate_netcdf_writes_dataset_and_indexes(dsb, tmp_path):
+    rows = write_ratings(str(tmp_path / "ratings"))
+    out = run([os.path.join(BIN, "generateNetCDF"), "-d", "gl_input", "-i", "ratings", "-o", "gl_input.nc", "-f", "features_input", "-s", "samples_input", "-c"],
+              str(tmp_path))
+    assert "Created NetCDF file gl_input.nc" in out
+    feats = dict(l.rstrip("\n").split("\t") for l in open(tmp_path / "features_input"))
+    samples = dict(l.rstrip("\n").split("\t") for l in open(tmp_path / "samples_input"))
+    assert len(samples) == 600 and sorted(int(v) for v in samples.values()) == list(range(600))
+    assert sorted(int(v) for v in feats.values()) == list(range(len(feats)))
+    from test_netcdf import describe, read_var
+    rc, text = describe(dsb.lib(), str(tmp_path / "gl_input.nc"))
+    assert rc == 0 and 'name0 = "gl_input"' in text and "attributes0 = 3" in text and "examplesDim0 = 600" in text
+    assert f"width0 = {((len(feats) + 127) // 128) * 128}" in text            # roundUpMaxIndex, U/NetCDFhelper.cpp:325-330
+    start, end, index = (read_var(dsb.lib(), str(tmp_path / "gl_input.nc"), v).astype(np.int64) for v in ("sparseStart0", "sparseEnd0", "sparseIndex0"))
+    inv = {int(v): k for k, v in feats.items()}
+    for name, row in list(samples.items())[:50]:
+        r = int(row)
+        assert sorted(inv[int(c)] for c in index[start[r]:end[r]]) == sorted(rows[name])
+    # second run re-uses both indexes (no -c): same feature ids
+    run([os.path.join(BIN, "generateNetCDF"), "-d", "gl_output", "-i", "ratings", "-o", "gl_output.nc", "-f", "features_input", "-s", "samples_input"], str(tmp_path))
+    np.testing.assert_array_equal(read_var(dsb.lib(), str(tmp_path / "gl_output.nc"), "sparseIndex0").astype(np.int64), index)
+
+
+@pytest.mark.gpu
+def test_train_then_predict_recommends_inside_the_taste_group(tmp_path):
+    rows = write_ratings(str(tmp_path / "ratings"))
+    (tmp_path / "config.json").write_text(CONFIG)
+    gen = os.path.join(BIN, "generateNetCDF")
+    run([gen, "-d", "gl_input", "-i", "ratings", "-o", "gl_input.nc", "-f", "features_input", "-s", "samples_input", "-c"], str(tmp_path))
+    run([gen, "-d", "gl_output", "-i", "ratings", "-o", "gl_output.nc", "-f", "features_output", "-s", "samples_input", "-c"], str(tmp_path))
+    out = run([os.path.join(BIN, "train"), "-c", "config.json", "-i", "gl_input.nc", "-o", "gl_output.nc", "-n", "gl.nc", "-b", "128", "-e", "30", "-alpha", "0.1",
+               "-m", "Momentum"], str(tmp_path))
+    errors = [float(l.split()[-1]) for l in out.splitlines() if l.startswith("Epoch ")]
+    assert len(errors) == 30 and errors[-1] < 0.6 * errors[0], errors
+    assert (tmp_path / "gl.nc").exists() and (tmp_path / "initial_network.nc").exists()
+    run([os.path.join(BIN, "predict"), "-b", "128", "-d", "gl", "-i", "features_input", "-o", "features_output", "-k", "10", "-n", "gl.nc", "-f", "ratings",
+         "-s", "recs", "-r", "ratings"], str(tmp_path))
+    lines = open(tmp_path / "recs").read().splitlines()
+    assert len(lines) == 600
+    inside = total = 0
+    for line in lines:
+        user, recs = line.split("\t")
+        items = [r.split(",")[0] for r in recs.split(":") if r]
+        assert len(items) == 10 and not set(items) & set(rows[user])                # exclusion filter: nothing the user already has
+        scores = [float(r.split(",")[1]) for r in recs.split(":") if r]
+        assert scores == sorted(scores, reverse=True)
+        g = int(user[1:]) % 2
+        inside += sum(1 for i in items if (int(i[1:]) >= 150) == (g == 1))
+        total += len(items)
+    assert inside / total > 0.9, inside / total
