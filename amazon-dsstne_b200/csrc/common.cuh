@@ -49,9 +49,11 @@ struct dsb200_ctx {
     void*          cublas      = nullptr;         // cublasHandle_t (fp32 GEMM fallback / reference arm)
     int            gemmMode    = 0;
     int            gemmDebug   = 0;               // bring-up switches of gemm_tc.cu (option "gemm_debug")
+    int            gemmTcMinWork = 2048;          // option "gemm_tc_min_work": tiles x k-iterations below which cuBLAS runs
     int            gemmSplits  = 0;               // option "gemm_splits": 0 = automatic split-K factor
     float*         dGemmWs     = nullptr;         // split-K partial tiles of the tcgen05 GEMM
     size_t         gemmWsCap   = 0;               // in floats
+    int            outputTileKernel = 0;          // option "output_tile_kernel": force the two-phase tile kernel in dsb200_output_pass
     int            fastMath    = 1;               // option "fast_math": MUFU exp/log/rcp in the output pass (default on)
     int            profile     = 0;               // option "profile": event pairs around every kernel entry
     char           lastError[256];

@@ -35,7 +35,15 @@ int gemm_tc_launch(dsb200_ctx* ctx, const float* A, int aMN, uint32_t lda, const
                    uint32_t M, uint32_t N, uint32_t K, float alpha, float beta, const float* bias, int act, float slope, float ealpha,
                    float lambda);
 
-static inline bool use_tc(const dsb200_ctx* ctx) { return ctx->gemmMode == DSB200_GEMM_TF32 || ctx->gemmMode == DSB200_GEMM_TF32X3; }
+// The persistent tcgen05 kernel pays ~15 us of fixed latency (launch, TMEM allocation, pipeline fill, epilogue); a GEMM
+// that covers only a handful of 128 x 128 tiles (the 128 x 128 hidden weights of BASELINE config 2: 8 tiles) is
+// latency bound and stays on the plain library SGEMM, which is also the exact-fp32 path.  Option "gemm_tc_min_tiles".
+static inline bool use_tc(const dsb200_ctx* ctx, uint64_t M, uint64_t N, uint64_t K)
+{
+    if (ctx->gemmMode != DSB200_GEMM_TF32 && ctx->gemmMode != DSB200_GEMM_TF32X3) return false;
+    const uint64_t tiles = ((M + 127) / 128) * ((N + 127) / 128);
+    return tiles * ((K + 15) / 16) >= (uint64_t)ctx->gemmTcMinWork;
+}
 
 void gemm_release(dsb200_ctx* ctx)
 {
@@ -52,7 +60,7 @@ int dsb200_gemm_fwd(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, const f
     using namespace dsb;
     if (!ctx || !A || !W || !C) return fail(ctx, DSB200_EINVAL, "gemm_fwd: null argument");
     if (!B || !k || !n) return 0;
-    if (use_tc(ctx)) return gemm_tc_launch(ctx, A, 0, k, W, 1, n, C, n, B, n, k, 1.0f, beta, nullptr, DSB200_ACT_LINEAR, 0.f, 0.f, 0.f);
+    if (use_tc(ctx, B, n, k)) return gemm_tc_launch(ctx, A, 0, k, W, 1, n, C, n, B, n, k, 1.0f, beta, nullptr, DSB200_ACT_LINEAR, 0.f, 0.f, 0.f);
     cublasHandle_t h; int rc = cublas_of(ctx, &h); if (rc) return rc;
     const float one = 1.0f;
     // row-major C = A*W  <=>  column-major C^T = W^T * A^T (E/NNLayer.cpp:1072-1086)
@@ -67,7 +75,7 @@ int dsb200_gemm_dw(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, float al
     using namespace dsb;
     if (!ctx || !A || !D || !G) return fail(ctx, DSB200_EINVAL, "gemm_dw: null argument");
     if (!B || !k || !n) return 0;
-    if (use_tc(ctx)) return gemm_tc_launch(ctx, A, 1, k, D, 1, n, G, n, k, n, B, alpha, beta, nullptr, DSB200_ACT_LINEAR, 0.f, 0.f, 0.f);
+    if (use_tc(ctx, k, n, B)) return gemm_tc_launch(ctx, A, 1, k, D, 1, n, G, n, k, n, B, alpha, beta, nullptr, DSB200_ACT_LINEAR, 0.f, 0.f, 0.f);
     cublasHandle_t h; int rc = cublas_of(ctx, &h); if (rc) return rc;
     // G^T (n x k) = D^T (n x B) * A (B x k)   (E/NNLayer.cpp:2223-2236)
     if (cublasSgemm(h, CUBLAS_OP_N, CUBLAS_OP_T, (int)n, (int)k, (int)B, &alpha, D, (int)n, A, (int)k, &beta, G, (int)n) != CUBLAS_STATUS_SUCCESS)
@@ -81,7 +89,7 @@ int dsb200_gemm_dx(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, const fl
     using namespace dsb;
     if (!ctx || !D || !W || !Dp) return fail(ctx, DSB200_EINVAL, "gemm_dx: null argument");
     if (!B || !k || !n) return 0;
-    if (use_tc(ctx)) return gemm_tc_launch(ctx, D, 0, n, W, 0, n, Dp, k, B, k, n, 1.0f, beta, nullptr, DSB200_ACT_LINEAR, 0.f, 0.f, 0.f);
+    if (use_tc(ctx, B, k, n)) return gemm_tc_launch(ctx, D, 0, n, W, 0, n, Dp, k, B, k, n, 1.0f, beta, nullptr, DSB200_ACT_LINEAR, 0.f, 0.f, 0.f);
     cublasHandle_t h; int rc = cublas_of(ctx, &h); if (rc) return rc;
     const float one = 1.0f;
     // Dp^T (k x B) = W (k x n) * D^T (n x B)   (E/NNLayer.cpp:2274-2287)
@@ -98,7 +106,7 @@ int dsb200_gemm_fwd_bias_act(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n
     using namespace dsb;
     if (!ctx || !A || !W || !C || !pBias) return fail(ctx, DSB200_EINVAL, "gemm_fwd_bias_act: null argument");
     if (!B || !k || !n) return 0;
-    if (use_tc(ctx) && activation != DSB200_ACT_SOFTMAX) {
+    if (use_tc(ctx, B, n, k) && activation != DSB200_ACT_SOFTMAX) {
         DSB_PROFILE(ctx, "gemm_fwd_bias_act");
         return gemm_tc_launch(ctx, A, 0, k, W, 1, n, C, n, B, n, k, 1.0f, 0.0f, pBias, activation, slope, alpha, lambda);
     }

@@ -103,6 +103,7 @@ def test_three_hidden_layers_with_penalty(eng, orc, error, gemm_mode, tol):
     h = tiny(examples=256, width=2048)
     net, onet, names, _ = build_pair(eng, orc, sizes, h, batch, orc.SGD, error=error, sparseness=(0.5, 2.0))
     net.set_gemm_mode(gemm_mode)
+    eng.set_option("gemm_tc_min_work", 0)                           # these shapes are small: force the tensor-core kernel anyway
     oc = to_oracle(orc, h)
     onet.set_input(oc, batch)
     try:
@@ -119,6 +120,7 @@ def test_three_hidden_layers_with_penalty(eng, orc, error, gemm_mode, tol):
             assert rel_err(u, onet.unit(l, batch)) < tol
     finally:
         net.set_gemm_mode(0)
+        eng.set_option("gemm_tc_min_work", 2048)
         net.close()
 
 

@@ -32,6 +32,7 @@ def test_gemm_fwd_dw_dx(ctx, mode, B, k, n):
     D = torch.randn(B, n, device="cuda", generator=g) * 0.1
     C0 = torch.randn(B, n, device="cuda", generator=g)
     ctx.set_option("gemm_mode", mode)
+    ctx.set_option("gemm_tc_min_work", 0)                       # force the tensor-core kernel for every shape
     try:
         C = C0.clone()
         ctx.gemm_fwd(A, W, C, beta=1.0)
@@ -44,6 +45,7 @@ def test_gemm_fwd_dw_dx(ctx, mode, B, k, n):
         ctx.sync()
     finally:
         ctx.set_option("gemm_mode", 0)
+        ctx.set_option("gemm_tc_min_work", 2048)
     a, w, d = ref64(A), ref64(W), ref64(D)
     tol = BOUND[mode]
     assert rel_err(C.cpu().numpy(), ref64(C0) + a @ w) < tol
@@ -62,11 +64,13 @@ def test_fused_bias_activation_forward(ctx, orc, mode, act):
     bias = torch.randn(n, device="cuda", generator=g)
     C = torch.empty(B, n, device="cuda")
     ctx.set_option("gemm_mode", mode)
+    ctx.set_option("gemm_tc_min_work", 0)
     try:
         ctx.gemm_fwd_bias_act(A, W, bias, act, C)
         ctx.sync()
     finally:
         ctx.set_option("gemm_mode", 0)
+        ctx.set_option("gemm_tc_min_work", 2048)
     z = (ref64(A) @ ref64(W) + ref64(bias)[None, :]).astype(np.float32)
     want = orc.activation(act, np.ascontiguousarray(z))              # E/kActivation.cu semantics via the oracle
     assert rel_err(C.cpu().numpy(), want) < BOUND[mode]

@@ -295,11 +295,14 @@ def test_sparse_loss_and_delta(ctx, orc, dsb, ef, act, weighted, iz):
 
 @pytest.mark.parametrize("ef", ["smce", "ce", "l2"])
 @pytest.mark.parametrize("want_unit", [False, True])
-def test_output_pass_fused(ctx, orc, dsb, ef, want_unit):
+@pytest.mark.parametrize("kernel,stride", [("row", 27278), ("row", 40001), ("tile", 27278)])
+def test_output_pass_fused(ctx, orc, dsb, ef, want_unit, kernel, stride):
+    """kernel = "row": the one-pass bitmap kernel (Boolean targets); "tile": the two-phase tile kernel it falls back to.
+    stride 40,001: three column segments per row, odd width (unaligned rows, scalar head / tail)."""
     import torch
     EF = {"l2": 1, "ce": 2, "smce": 3}[ef]
-    h = ml20m(examples=64, width=27278)
-    batch, stride = 64, 27278
+    h = ml20m(examples=64, width=stride)
+    batch = 64
     z = _output_inputs(h, batch, stride)
     smce = (1.0, 0.0, 1.0, 1.0)                                        # samples/movielens/config.json
     params = orc.make_params(smce=smce)
@@ -312,8 +315,12 @@ def test_output_pass_fused(ctx, orc, dsb, ef, want_unit):
     d_unit = torch.empty_like(d_z) if want_unit else None
     d_delta = torch.empty_like(d_z)
     acc = torch.zeros(1, dtype=torch.int64, device="cuda")
-    ctx.output_pass(to_device(dsb, h), EF, dsb.ACT_SIGMOID, 0, batch, d_z, d_unit, d_delta, acc)
-    ctx.sync()
+    ctx.set_option("output_tile_kernel", int(kernel == "tile"))
+    try:
+        ctx.output_pass(to_device(dsb, h), EF, dsb.ACT_SIGMOID, 0, batch, d_z, d_unit, d_delta, acc)
+        ctx.sync()
+    finally:
+        ctx.set_option("output_tile_kernel", 0)
     ctx.set_params()
     got_loss = float(acc.item()) / float(1 << 30)
     assert abs(got_loss - ref_loss) <= TOL * max(abs(ref_loss), 1.0)
