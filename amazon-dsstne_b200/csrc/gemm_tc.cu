@@ -36,13 +36,13 @@
 namespace dsb {
 namespace tc {
 
-constexpr int BM = 128, BN = 128, BK = 16;
-constexpr int PANEL = 128 * BK * 4;            // one operand panel: 8 KB
+constexpr int BM = 128, BN = 128, BK = 32;
+constexpr int PANEL = 128 * BK * 4;            // one operand panel: 16 KB
 constexpr int STAGE = 2 * PANEL;               // A panel | B panel (raw ring and lo ring alike)
-constexpr int RAW_SLOTS = 7, LO_SLOTS = 3;
-constexpr int COPY_WARPS = 4, SPLIT_GROUPS = 2, SPLIT_WARPS = 8, MMA_WARP = 12, EPI_WARP0 = 13, EPI_WARPS = 4;
+constexpr int RAW_SLOTS = 4, LO_SLOTS = 2;
+constexpr int COPY_WARPS = 8, SPLIT_GROUPS = 2, SPLIT_WARPS = 8, MMA_WARP = 16, EPI_WARP0 = 17, EPI_WARPS = 4;
 constexpr int THREADS = (EPI_WARP0 + EPI_WARPS) * 32;
-constexpr int EPI_COLS = BN / 2;               // the epilogue drains the accumulator in two 64-column halves
+constexpr int EPI_COLS = 32;                   // the epilogue drains the accumulator 32 columns at a time
 constexpr int EPI_LD = EPI_COLS + 4;           // padded row of the per-warp staging tile (floats)
 constexpr int EPI_BYTES = EPI_WARPS * 32 * EPI_LD * 4;
 constexpr int SMEM_BYTES = (RAW_SLOTS + LO_SLOTS) * STAGE + EPI_BYTES + 1024;
@@ -109,8 +109,8 @@ __device__ __forceinline__ uint64_t smem_desc(uint32_t saddr, uint32_t lboBytes,
 template <bool MN>
 __device__ __forceinline__ uint64_t panel_desc(uint32_t panelAddr, int kStep)
 {
-    // one K = 8 step: two 16-byte chunks (K-major) or two groups of 4 k-rows (MN-major)
-    return MN ? smem_desc(panelAddr + kStep * 1024, 2048, 512, 1) : smem_desc(panelAddr + kStep * 4096, 2048, 128, 0);
+    // one K = 8 step: 32 bytes along the 128-byte swizzled rows (K-major) or two groups of 4 k-rows (MN-major)
+    return MN ? smem_desc(panelAddr + kStep * 1024, 4096, 512, 1) : smem_desc(panelAddr + kStep * 32, 16, 1024, 2);
 }
 // 32 lanes x 32 consecutive fp32 columns: thread t of warp w gets row 32*(w%4)+t
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v)
@@ -137,83 +137,125 @@ __device__ __forceinline__ void cp_async_landed(uint64_t* bar)
     asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
 }
 
-// Per-thread plan of one operand of one tile: CHUNKS 16-byte chunks of every 128 x BK panel, everything that does not
-// depend on the k-iteration hoisted out of the main loop.
-constexpr int CHUNKS = 4;                      // 16 warp-level chunk groups per panel / 4 copy warps
+// Per-thread plan of one operand of one tile.  A 128 x 32 panel is 1,024 16-byte chunks; one warp-level copy moves 32
+// of them (16 in the 8-byte mode), the 8 copy warps take them round robin: piece i of warp w is group g = i * 8 + w.
+//   K-major  (rows = mn, 128 bytes each): a group is 4 whole rows (2 in the 8-byte mode) -> the copy touches 4 (2)
+//            cache lines, the fewest possible, and writes whole swizzled 128-byte rows (no bank conflicts)
+//   MN-major (rows = k, 512 bytes each):  a group is 4 k-rows x 128 bytes of one 32-column atom
+// Everything that does not depend on the k-iteration is hoisted: one base pointer and a constant stride per piece.
 template <bool MN>
 struct OperandPlan {
-    const float* ptr[CHUNKS];                  // global address of the chunk in the next k-iteration to issue
-    uint32_t     soff[CHUNKS];                 // byte offset inside the panel
-    uint32_t     valid[CHUNKS];                // floats inside the matrix along the contiguous dimension (full iterations)
-    uint32_t     kOff[CHUNKS];                 // first k of the chunk inside the panel
-    size_t       step;                         // pointer advance per k-iteration
+    const float* ptr;                          // global address of piece 0 in the next k-iteration to issue
     const float* base;
+    size_t       pieceStride;                  // floats between consecutive pieces
+    size_t       step;                         // pointer advance per k-iteration
+    uint32_t     soff, spiece;                 // byte offset of piece 0 inside the panel / between pieces
+    uint32_t     validPieces;                  // K-major: pieces whose row is inside the matrix
+    uint32_t     valid0, valid1, valid2, valid3;  // MN-major: floats inside the matrix for the 4 atoms (pieces)
+    uint32_t     kOff;                         // first k of this thread's chunk inside the panel
+    int          vec;
 
-    __device__ __forceinline__ void init(const float* b, uint32_t ld, uint32_t mn0, uint32_t kBegin, uint32_t mnLimit, uint32_t warp, uint32_t lane)
+    __device__ __forceinline__ void init(const float* b, uint32_t ld, uint32_t mn0, uint32_t kBegin, uint32_t mnLimit, int v, uint32_t warp, uint32_t lane)
     {
-        base = b;
+        base = b; vec = v;
         step = MN ? (size_t)BK * ld : (size_t)BK;
-#pragma unroll
-        for (int i = 0; i < CHUNKS; i++) {
-            const uint32_t u = warp * CHUNKS + i;
-            uint32_t mn, k;
-            if (MN) {
-                mn = mn0 + (u >> 2) * 32 + (lane >> 2) * 4; k = (u & 3) * 4 + (lane & 3);
-                soff[i] = (u >> 2) * 2048 + (u & 3) * 512 + (lane & 3) * 128 + (((lane >> 3) ^ (lane & 3)) * 32) + ((lane >> 2) & 1) * 16;
-                valid[i] = mn < mnLimit ? min(4u, mnLimit - mn) : 0u;
-                ptr[i] = valid[i] ? b + (size_t)(kBegin + k) * ld + mn : b;
-            } else {
-                mn = mn0 + u * 8 + (lane & 7); k = (lane >> 3) * 4;
-                soff[i] = u * 128 + (lane & 7) * 16 + (lane >> 3) * 2048;
-                valid[i] = mn < mnLimit ? 4u : 0u;
-                ptr[i] = valid[i] ? b + (size_t)mn * ld + kBegin + k : b;
-            }
-            kOff[i] = k;
+        if (MN) {
+            // piece i: atom i (32 columns), k-group = warp (4 rows), row in group = lane & 3, 16-byte chunk = lane >> 2
+            const uint32_t k = warp * 4 + (lane & 3), mn = mn0 + (lane >> 2) * 4;
+            kOff = k;
+            soff = warp * 512 + (lane & 3) * 128 + (((lane >> 3) ^ (lane & 3)) * 32) + ((lane >> 2) & 1) * 16;
+            spiece = 4096;
+            pieceStride = 32;
+            valid0 = mn < mnLimit ? min(4u, mnLimit - mn) : 0u;
+            valid1 = mn + 32 < mnLimit ? min(4u, mnLimit - mn - 32) : 0u;
+            valid2 = mn + 64 < mnLimit ? min(4u, mnLimit - mn - 64) : 0u;
+            valid3 = mn + 96 < mnLimit ? min(4u, mnLimit - mn - 96) : 0u;
+            validPieces = 4;
+            ptr = b + (size_t)(kBegin + k) * ld + mn;                            // may point past the matrix: only dereferenced when valid
+        } else if (v == 4) {
+            // piece i: rows (i * 8 + warp) * 4 + (lane >> 3), 16-byte chunk lane & 7
+            const uint32_t r = warp * 4 + (lane >> 3), c = lane & 7;
+            kOff = c * 4;
+            soff = (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) * 16);
+            spiece = 4096;                                                       // 32 rows further
+            pieceStride = (size_t)32 * ld;
+            const uint32_t row = mn0 + r;
+            validPieces = row < mnLimit ? min(4u, (mnLimit - row + 31) / 32) : 0u;
+            valid0 = valid1 = valid2 = valid3 = 4;
+            ptr = b + (size_t)row * ld + kBegin + c * 4;
+        } else {
+            // 8-byte (or 4-byte) copies: piece i: rows (i * 8 + warp) * 2 + (lane >> 4), 8-byte half-chunk lane & 15
+            const uint32_t r = warp * 2 + (lane >> 4), h = lane & 15, c = h >> 1;
+            kOff = h * 2;
+            soff = (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) * 16) + (h & 1) * 8;
+            spiece = 2048;                                                       // 16 rows further
+            pieceStride = (size_t)16 * ld;
+            const uint32_t row = mn0 + r;
+            validPieces = row < mnLimit ? min(8u, (mnLimit - row + 15) / 16) : 0u;
+            valid0 = valid1 = valid2 = valid3 = 2;
+            ptr = b + (size_t)row * ld + kBegin + h * 2;
         }
     }
-    // a full panel (k0 + BK <= kEnd): nothing but the copies and the pointer advance
-    __device__ __forceinline__ void issue_full(uint32_t panelAddr, int vec)
+    __device__ __forceinline__ uint32_t mn_valid(int i) const { return i == 0 ? valid0 : i == 1 ? valid1 : i == 2 ? valid2 : valid3; }
+
+    // Issues this thread's copies of the panel that starts at k0.  `full`: the whole panel lies inside [kBegin, kEnd).
+    __device__ __forceinline__ void issue(uint32_t panelAddr, uint32_t k0, uint32_t kEnd, bool full)
     {
+        if (MN) {
+            const bool rowIn = full || (k0 + kOff < kEnd);
 #pragma unroll
-        for (int i = 0; i < CHUNKS; i++) {
-            const uint32_t dst = panelAddr + soff[i], v = valid[i];
-            if (vec == 4) {
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(ptr[i]), "r"(v * 4) : "memory");
-            } else if (vec == 2) {
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(dst), "l"(ptr[i]), "r"(min(v, 2u) * 4) : "memory");
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(dst + 8), "l"(ptr[i] + (v > 2 ? 2 : 0)), "r"((v > 2 ? v - 2 : 0u) * 4) : "memory");
-            } else {
+            for (int i = 0; i < 4; i++) {
+                const uint32_t dst = panelAddr + soff + i * spiece, v = rowIn ? mn_valid(i) : 0u;
+                const float* p = v ? ptr + i * pieceStride : base;
+                if (vec == 4) asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" :: "r"(dst), "l"(p), "r"(v * 4) : "memory");
+                else if (vec == 2) {
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(dst), "l"(p), "r"(min(v, 2u) * 4) : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(dst + 8), "l"(v > 2 ? p + 2 : base), "r"((v > 2 ? v - 2 : 0u) * 4) : "memory");
+                } else {
 #pragma unroll
-                for (uint32_t e = 0; e < 4; e++)
-                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(dst + 4 * e), "l"(e < v ? ptr[i] + e : base), "r"(e < v ? 4u : 0u) : "memory");
+                    for (uint32_t e = 0; e < 4; e++)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(dst + 4 * e), "l"(e < v ? p + e : base), "r"(e < v ? 4u : 0u) : "memory");
+                }
             }
-            ptr[i] += v ? step : 0;
-        }
-    }
-    // the last, partial panel of the K range: element-wise bounds
-    __device__ __forceinline__ void issue_tail(uint32_t panelAddr, uint32_t k0, uint32_t kEnd)
-    {
+        } else if (vec == 4) {
+            const uint32_t kv = full ? 4u : (k0 + kOff < kEnd ? min(4u, kEnd - k0 - kOff) : 0u);
 #pragma unroll
-        for (int i = 0; i < CHUNKS; i++) {
-            uint32_t v = valid[i];
-            const uint32_t k = k0 + kOff[i];
-            if (MN) v = (k < kEnd) ? v : 0u;
-            else    v = (v && k < kEnd) ? min(4u, kEnd - k) : 0u;
-            const uint32_t dst = panelAddr + soff[i];
+            for (int i = 0; i < 4; i++) {
+                const uint32_t v = (uint32_t)i < validPieces ? kv : 0u;
+                const float* p = v ? ptr + i * pieceStride : base;
+                if (v == 4 || v == 0) asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;" :: "r"(panelAddr + soff + i * spiece), "l"(p), "r"(v * 4) : "memory");
+                else {                                                           // ragged end of K: rows stay 16-byte aligned, sizes are not
 #pragma unroll
-            for (uint32_t e = 0; e < 4; e++)
-                asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(dst + 4 * e), "l"(e < v ? ptr[i] + e : base), "r"(e < v ? 4u : 0u) : "memory");
+                    for (uint32_t e = 0; e < 4; e++)
+                        asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(panelAddr + soff + i * spiece + 4 * e), "l"(e < v ? p + e : base),
+                                     "r"(e < v ? 4u : 0u) : "memory");
+                }
+            }
+        } else {
+            const uint32_t kv = full ? 2u : (k0 + kOff < kEnd ? min(2u, kEnd - k0 - kOff) : 0u);
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const uint32_t v = (uint32_t)i < validPieces ? kv : 0u;
+                const float* p = v ? ptr + i * pieceStride : base;
+                const uint32_t dst = panelAddr + soff + i * spiece;
+                if (vec == 2 && v != 1) asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;" :: "r"(dst), "l"(p), "r"(v * 4) : "memory");
+                else {
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(dst), "l"(p), "r"(v ? 4u : 0u) : "memory");
+                    asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" :: "r"(dst + 4), "l"(v > 1 ? p + 1 : base), "r"(v > 1 ? 4u : 0u) : "memory");
+                }
+            }
         }
+        ptr += step;
     }
 };
 
 // row loop of the epilogue: staging tile (2 columns per lane) -> global, ACT < 0 = raw copy (split-K partials)
 template <int ACT>
-__device__ __forceinline__ void store_rows(const float* __restrict__ sp, float* __restrict__ o, uint32_t rows, uint32_t ldo, uint32_t ncol, bool vec2,
-                                           float alpha, float beta, float bias0, float bias1, float slope, float ealpha, float lambda)
+__device__ __forceinline__ void store_rows(const float* __restrict__ sp, float* __restrict__ o, uint32_t r0, uint32_t rows, uint32_t ldo, uint32_t ncol,
+                                           bool vec2, float alpha, float beta, float bias0, float bias1, float slope, float ealpha, float lambda)
 {
 #pragma unroll 4
-    for (uint32_t r = 0; r < rows; r++, o += ldo, sp += EPI_LD) {
+    for (uint32_t r = r0; r < rows; r += 2, o += 2 * (size_t)ldo, sp += 2 * EPI_LD) {
         const float2 t = *reinterpret_cast<const float2*>(sp);
         float x0 = t.x, x1 = t.y;
         if (ACT >= 0) {
@@ -277,14 +319,16 @@ gemm_tc_kernel(const Args a)
             const Tile tl = tile_of(a, t);
             OperandPlan<AMN> pa;
             OperandPlan<BMN> pb;
-            pa.init(a.A, a.lda, tl.m0, tl.kBegin, a.M, warp, lane);
-            pb.init(a.B, a.ldb, tl.n0, tl.kBegin, a.N, warp, lane);
+            pa.init(a.A, a.lda, tl.m0, tl.kBegin, a.M, a.vecA, warp, lane);
+            pb.init(a.B, a.ldb, tl.n0, tl.kBegin, a.N, a.vecB, warp, lane);
             for (uint32_t kt = 0; kt < tl.numK; kt++) {
                 mbar_wait(&emptyRawBar[slot], parity);                            // the MMAs that read this slot have retired
                 const uint32_t st = rawAddr + slot * STAGE, k0 = tl.kBegin + kt * BK;
-                if (a.debug & 2) {}
-                else if (k0 + BK <= tl.kEnd) { pa.issue_full(st, a.vecA); pb.issue_full(st + PANEL, a.vecB); }
-                else { pa.issue_tail(st, k0, tl.kEnd); pb.issue_tail(st + PANEL, k0, tl.kEnd); }
+                if (!(a.debug & 2)) {
+                    const bool full = k0 + BK <= tl.kEnd;
+                    pa.issue(st, k0, tl.kEnd, full);
+                    pb.issue(st + PANEL, k0, tl.kEnd, full);
+                }
                 cp_async_landed(&landedBar[slot]);                                // arrives when this thread's copies have landed
                 if (++slot == RAW_SLOTS) { slot = 0; parity ^= 1; }
             }
@@ -303,9 +347,11 @@ gemm_tc_kernel(const Args a)
                     if (a.passes == 3 && !(a.debug & 8)) {
                         const uint8_t* src = rawRing + rs * STAGE + tid * 16;
                         uint8_t* dst = loRing + ls * STAGE + tid * 16;
+#pragma unroll
+                        for (int half = 0; half < 2; half++) {
                         float4 r[8];
 #pragma unroll
-                        for (int j = 0; j < 8; j++) r[j] = *reinterpret_cast<const float4*>(src + j * 2048);
+                        for (int j = 0; j < 8; j++) r[j] = *reinterpret_cast<const float4*>(src + (half * 8 + j) * 2048);
 #pragma unroll
                         for (int j = 0; j < 8; j++) {
                             float4 l;
@@ -313,7 +359,8 @@ gemm_tc_kernel(const Args a)
                             l.y = r[j].y - __uint_as_float(__float_as_uint(r[j].y) & 0xFFFFE000u);
                             l.z = r[j].z - __uint_as_float(__float_as_uint(r[j].z) & 0xFFFFE000u);
                             l.w = r[j].w - __uint_as_float(__float_as_uint(r[j].w) & 0xFFFFE000u);
-                            *reinterpret_cast<float4*>(dst + j * 2048) = l;
+                            *reinterpret_cast<float4*>(dst + (half * 8 + j) * 2048) = l;
+                        }
                         }
                     }
                     if (!(a.debug & 1)) fence_async_smem();
@@ -379,22 +426,23 @@ gemm_tc_kernel(const Args a)
             const uint32_t ldo = a.partial ? a.N : a.ldc;
             float* outBase = a.partial ? a.partial + (size_t)tl.split * a.M * a.N : a.C;
 #pragma unroll 1
-            for (int half = 0; half < 2; half++) {
-#pragma unroll 1
-                for (int cb = 0; cb < EPI_COLS / 32; cb++) {
+            for (int half = 0; half < BN / EPI_COLS; half++) {
+                {
                     float v[32];
-                    tmem_ld32(tmem + (rowBase << 16) + acc * BN + half * EPI_COLS + cb * 32, v);
+                    tmem_ld32(tmem + (rowBase << 16) + acc * BN + half * EPI_COLS, v);
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(stage + lane * EPI_LD + cb * 32 + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(stage + lane * EPI_LD + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
                 }
-                if (half == 1) {                                                  // accumulator fully read: the MMA warp may reuse it
+                if (half == BN / EPI_COLS - 1) {                                  // accumulator fully read: the MMA warp may reuse it
                     tc_fence_before();
                     __syncwarp();
                     if (lane == 0) mbar_arrive(&accEmptyBar[acc]);
                 }
                 __syncwarp();
-                const uint32_t c0 = half * EPI_COLS + lane * 2, nc = tl.n0 + c0;    // this lane's 2 columns
+                // 32 columns per pass: lanes 0-15 take the even rows, lanes 16-31 the odd rows, 2 columns each
+                const uint32_t c0 = half * EPI_COLS + (lane & 15) * 2, nc = tl.n0 + c0;
                 const uint32_t ncol = (nc < a.N) ? min(2u, a.N - nc) : 0u;
+                const uint32_t rsel = lane >> 4;
                 if (ncol && !(a.debug & 16)) {
                     float bias0 = 0.f, bias1 = 0.f;
                     if (a.bias && !a.partial) {
@@ -402,16 +450,16 @@ gemm_tc_kernel(const Args a)
                         if (ncol > 1) bias1 = __ldg(a.bias + nc + 1);
                     }
                     const bool vec2 = ncol == 2 && (a.partial ? ((a.N & 1) == 0) : (a.vecC >= 2));
-                    float* o = outBase + (size_t)mBase * ldo + nc;
-                    const float* sp = stage + lane * 2;
-                    if (a.partial)                        store_rows<-1>(sp, o, rows, ldo, ncol, vec2, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f);
-                    else if (a.act == DSB200_ACT_LINEAR)  store_rows<DSB200_ACT_LINEAR>(sp, o, rows, ldo, ncol, vec2, a.alpha, a.beta, bias0, bias1, 0.f, 0.f, 0.f);
-                    else if (a.act == DSB200_ACT_SIGMOID) store_rows<DSB200_ACT_SIGMOID>(sp, o, rows, ldo, ncol, vec2, a.alpha, a.beta, bias0, bias1, 0.f, 0.f, 0.f);
-                    else if (a.act == DSB200_ACT_TANH)    store_rows<DSB200_ACT_TANH>(sp, o, rows, ldo, ncol, vec2, a.alpha, a.beta, bias0, bias1, 0.f, 0.f, 0.f);
-                    else if (a.act == DSB200_ACT_RELU)    store_rows<DSB200_ACT_RELU>(sp, o, rows, ldo, ncol, vec2, a.alpha, a.beta, bias0, bias1, 0.f, 0.f, 0.f);
-                    else if (a.act == DSB200_ACT_LRELU)   store_rows<DSB200_ACT_LRELU>(sp, o, rows, ldo, ncol, vec2, a.alpha, a.beta, bias0, bias1, a.slope, 0.f, 0.f);
-                    else if (a.act == DSB200_ACT_ELU)     store_rows<DSB200_ACT_ELU>(sp, o, rows, ldo, ncol, vec2, a.alpha, a.beta, bias0, bias1, 0.f, a.ealpha, 0.f);
-                    else                                  store_rows<DSB200_ACT_SELU>(sp, o, rows, ldo, ncol, vec2, a.alpha, a.beta, bias0, bias1, 0.f, a.ealpha, a.lambda);
+                    float* o = outBase + (size_t)(mBase + rsel) * ldo + nc;
+                    const float* sp = stage + rsel * EPI_LD + (lane & 15) * 2;
+                    if (a.partial)                        store_rows<-1>(sp, o, rsel, rows, ldo, ncol, vec2, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f);
+                    else if (a.act == DSB200_ACT_LINEAR)  store_rows<DSB200_ACT_LINEAR>(sp, o, rsel, rows, ldo, ncol, vec2, a.alpha, a.beta, bias0, bias1, 0.f, 0.f, 0.f);
+                    else if (a.act == DSB200_ACT_SIGMOID) store_rows<DSB200_ACT_SIGMOID>(sp, o, rsel, rows, ldo, ncol, vec2, a.alpha, a.beta, bias0, bias1, 0.f, 0.f, 0.f);
+                    else if (a.act == DSB200_ACT_TANH)    store_rows<DSB200_ACT_TANH>(sp, o, rsel, rows, ldo, ncol, vec2, a.alpha, a.beta, bias0, bias1, 0.f, 0.f, 0.f);
+                    else if (a.act == DSB200_ACT_RELU)    store_rows<DSB200_ACT_RELU>(sp, o, rsel, rows, ldo, ncol, vec2, a.alpha, a.beta, bias0, bias1, 0.f, 0.f, 0.f);
+                    else if (a.act == DSB200_ACT_LRELU)   store_rows<DSB200_ACT_LRELU>(sp, o, rsel, rows, ldo, ncol, vec2, a.alpha, a.beta, bias0, bias1, a.slope, 0.f, 0.f);
+                    else if (a.act == DSB200_ACT_ELU)     store_rows<DSB200_ACT_ELU>(sp, o, rsel, rows, ldo, ncol, vec2, a.alpha, a.beta, bias0, bias1, 0.f, a.ealpha, 0.f);
+                    else                                  store_rows<DSB200_ACT_SELU>(sp, o, rsel, rows, ldo, ncol, vec2, a.alpha, a.beta, bias0, bias1, 0.f, a.ealpha, a.lambda);
                 }
                 __syncwarp();                                                     // staging tile free for the next half
             }

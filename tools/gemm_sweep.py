@@ -19,8 +19,8 @@ def t(fn):
     return e0.elapsed_time(e1) / 10 * 1e3
 for mode in (2, 1):
     ctx.set_option("gemm_mode", mode)
-    for splits in (0, 1):
+    for splits in (0,):
         ctx.set_option("gemm_splits", splits)
-        for dbg in (0, 1, 2, 4, 8, 16, 3, 6, 7, 15, 31):
+        for dbg in (0, 2, 4, 8, 16, 6, 14, 30, 31):
             ctx.set_option("gemm_debug", dbg)
             print(f"mode={mode} splits={splits} debug={dbg}: " + " ".join(f"{name} {t(fn):7.1f}" for name, fn in ops), flush=True)
