@@ -53,6 +53,7 @@ struct dsb200_ctx {
     int            gemmSplits  = 0;               // option "gemm_splits": 0 = automatic split-K factor
     float*         dGemmWs     = nullptr;         // split-K partial tiles of the tcgen05 GEMM
     size_t         gemmWsCap   = 0;               // in floats
+    int            zStagedKernel = 0;             // option "z_staged_kernel": force the TMA-staged CTA kernel for sparse Z
     int            outputTileKernel = 0;          // option "output_tile_kernel": force the two-phase tile kernel in dsb200_output_pass
     int            fastMath    = 1;               // option "fast_math": MUFU exp/log/rcp in the output pass (default on)
     int            profile     = 0;               // option "profile": event pairs around every kernel entry

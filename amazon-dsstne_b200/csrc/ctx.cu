@@ -137,6 +137,7 @@ int dsb200_ctx_set_option(dsb200_ctx* ctx, const char* name, int value)
     if (!strcmp(name, "gemm_mode")) { ctx->gemmMode = value; return 0; }
     if (!strcmp(name, "profile")) { ctx->profile = value; return 0; }
     if (!strcmp(name, "fast_math")) { ctx->fastMath = value; return 0; }
+    if (!strcmp(name, "z_staged_kernel")) { ctx->zStagedKernel = value; return 0; }
     if (!strcmp(name, "output_tile_kernel")) { ctx->outputTileKernel = value; return 0; }
     if (!strcmp(name, "gemm_splits")) { ctx->gemmSplits = value; return 0; }
     if (!strcmp(name, "gemm_tc_min_work")) { ctx->gemmTcMinWork = value; return 0; }

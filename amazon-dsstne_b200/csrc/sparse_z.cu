@@ -345,6 +345,190 @@ sparse_z_kernel(const ZArgs a)
 }
 
 // bias broadcast (kClearUnit, E/kernels.cu:60-80) and bias add (kAddBias, E/kernels.cu:564-584)
+
+// ---------------------------------------------------------------- warp-autonomous kernel (stride % 4 == 0)
+// Work item = (row, chunk of <= C nnz), taken by ONE WARP: the item's indices (and values / randoms) are read straight
+// into registers with coalesced loads, broadcast lane to lane with shuffles, and every lane gathers its float4 column of
+// the weight rows, 8 independent 512-byte row reads in flight per warp-instruction slot.  No shared-memory staging, no
+// block barrier per item, up to 64 warps per SM: the whole batch (~2,800 items for BASELINE config 2) is one wave.
+// Rows spanning several items are combined exactly as before: partial sums to the context workspace, the last warp to
+// arrive (atomic counter per row) adds them in chunk order -- deterministic, no float atomics.
+constexpr int kZWThreads = 256;
+constexpr int kZWUnroll  = 8;
+
+struct ZWSmem {
+    uint32_t prefix[kZMaxRows + 1];
+    uint32_t scan[kZWThreads / 32];
+};
+
+template <bool ANALOG, bool DENOISED>
+__global__ void __launch_bounds__(kZWThreads, 3)
+sparse_z_warp_kernel(const ZArgs a)
+{
+    __shared__ ZWSmem sm;
+    const int tid = threadIdx.x;
+    const uint32_t batch = a.batch, lane = tid & 31;
+
+    // ---- plan: chunk counts per row -> exclusive prefix (identical in every CTA); larger chunks if the split-row
+    // workspace would overflow
+    uint32_t C = (uint32_t)a.chunk;
+    uint32_t T = 0;
+    for (;;) {
+        for (uint32_t r = tid; r < batch; r += kZWThreads) {
+            const uint32_t ex = example_of(a.P, a.S.index, a.position, a.rowBase + r);
+            const uint64_t len = __ldg(a.S.sparseEnd + ex) - __ldg(a.S.sparseStart + ex);
+            uint32_t c = (uint32_t)((len + C - 1) / C);
+            if (a.fused && c == 0) c = 1;
+            sm.prefix[r] = c;
+        }
+        __syncthreads();
+        const uint32_t per = (batch + kZWThreads - 1) / kZWThreads;
+        const uint32_t lo = min((uint32_t)tid * per, batch), hi = min(lo + per, batch);
+        uint32_t local = 0;
+        for (uint32_t r = lo; r < hi; r++) local += sm.prefix[r];
+        uint32_t incl = local;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (uint32_t)o) incl += n;
+        }
+        if (lane == 31) sm.scan[tid >> 5] = incl;
+        __syncthreads();
+        uint32_t warpBase = 0;
+        for (int w = 0; w < (tid >> 5); w++) warpBase += sm.scan[w];
+        uint32_t run = warpBase + incl - local;
+        __syncthreads();
+        for (uint32_t r = lo; r < hi; r++) { const uint32_t c = sm.prefix[r]; sm.prefix[r] = run; run += c; }
+        if (tid == kZWThreads - 1) sm.prefix[batch] = run;
+        __syncthreads();
+        T = sm.prefix[batch];
+        if ((unsigned long long)T * a.stride <= a.partialsCap) break;
+        if (C >= 65536u) {
+            if (blockIdx.x == 0 && tid == 0) *a.status = DSB200_STATUS_Z_WORKSPACE;
+            return;
+        }
+        C *= 2;
+        __syncthreads();
+    }
+
+    const uint32_t stride = a.stride;
+    const float dp = a.P.denoising_p;
+    const uint32_t warpsPerCta = kZWThreads / 32, gw = blockIdx.x * warpsPerCta + (tid >> 5), nw = gridDim.x * warpsPerCta;
+    for (uint32_t t = gw; t < T; t += nw) {
+        uint32_t lo = 0, hi = batch;                                      // last row r with prefix[r] <= t
+        while (hi - lo > 1) { const uint32_t mid = (lo + hi) >> 1; if (sm.prefix[mid] <= t) lo = mid; else hi = mid; }
+        const uint32_t row = lo, k = t - sm.prefix[row], nChunks = sm.prefix[row + 1] - sm.prefix[row];
+        const uint32_t ex = example_of(a.P, a.S.index, a.position, a.rowBase + row);
+        const uint64_t rs = __ldg(a.S.sparseStart + ex), re = __ldg(a.S.sparseEnd + ex);
+        const uint64_t e0 = rs + (uint64_t)k * C;
+        const uint64_t e1 = (re < e0 + C) ? re : e0 + C;
+        const float w = a.S.dataWeight ? __ldg(a.S.dataWeight + ex) : 1.0f;
+        const float scale = DENOISED ? a.P.denoising_q * w : w;
+        float* zrow = a.Z + (size_t)(a.rowBase + row) * stride;
+        float* prow = a.partials + (size_t)t * stride;
+        const bool multi = nChunks > 1;
+
+        for (uint32_t colBase = 0; colBase < stride; colBase += 128) {   // every lane runs the loop: the shuffles need the whole warp
+            const uint32_t col = colBase + lane * 4;
+            const bool active = col < stride;
+            const float* wcol = a.W + (active ? col : 0u);
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (uint64_t e = e0; e < e1; e += 32) {
+                // 32 entries of the item: one per lane
+                const uint32_t n = (uint32_t)min((uint64_t)32, e1 - e);
+                uint32_t myIdx = 0;
+                float myMul = 0.0f;
+                if (lane < n) {
+                    myIdx = __ldg(a.S.sparseIndex + e + lane);
+                    myMul = ANALOG ? load_value(a.S.sparseData, a.S.dataType, e + lane) : 1.0f;
+                    if (DENOISED && __ldg(a.S.denoisingRandom + e + lane) < dp) myMul = 0.0f;
+                }
+                uint32_t j = 0;
+                for (; j + kZWUnroll <= n; j += kZWUnroll) {
+                    float4 x[kZWUnroll];
+                    float m[kZWUnroll];
+#pragma unroll
+                    for (int u = 0; u < kZWUnroll; u++) {
+                        const uint32_t idx = __shfl_sync(0xffffffffu, myIdx, j + u);
+                        if (ANALOG || DENOISED) m[u] = __shfl_sync(0xffffffffu, myMul, j + u);
+                        x[u] = ldg_nc_f4(reinterpret_cast<const float4*>(wcol + (size_t)idx * stride));
+                    }
+#pragma unroll
+                    for (int u = 0; u < kZWUnroll; u++) {
+                        const float mm = (ANALOG || DENOISED) ? m[u] : 1.0f;
+                        acc.x = fmaf(x[u].x, mm, acc.x); acc.y = fmaf(x[u].y, mm, acc.y);
+                        acc.z = fmaf(x[u].z, mm, acc.z); acc.w = fmaf(x[u].w, mm, acc.w);
+                    }
+                }
+                for (; j < n; j++) {
+                    const uint32_t idx = __shfl_sync(0xffffffffu, myIdx, j);
+                    const float mm = (ANALOG || DENOISED) ? __shfl_sync(0xffffffffu, myMul, j) : 1.0f;
+                    const float4 x = ldg_nc_f4(reinterpret_cast<const float4*>(wcol + (size_t)idx * stride));
+                    acc.x = fmaf(x.x, mm, acc.x); acc.y = fmaf(x.y, mm, acc.y);
+                    acc.z = fmaf(x.z, mm, acc.z); acc.w = fmaf(x.w, mm, acc.w);
+                }
+            }
+            if (!active) continue;
+            if (!multi) {
+                float v[4] = {acc.x, acc.y, acc.z, acc.w};
+#pragma unroll
+                for (int q = 0; q < 4; q++) {
+                    const float zold = a.bias ? __ldg(a.bias + col + q) : ((a.beta == 0.0f) ? 0.0f : a.beta * zrow[col + q]);
+                    const float z = DENOISED && !ANALOG ? scale * (zold + v[q]) : fmaf(scale, v[q], zold);
+                    v[q] = (a.activation >= 0) ? apply_act(a.activation, z) : z;
+                }
+                *reinterpret_cast<float4*>(zrow + col) = make_float4(v[0], v[1], v[2], v[3]);
+            } else {
+                *reinterpret_cast<float4*>(prow + col) = acc;
+            }
+        }
+        if (multi) {
+            // deterministic split-row combine by the last warp to arrive
+            __threadfence();
+            __syncwarp();
+            uint32_t last = 0;
+            if (lane == 0) {
+                const uint32_t old = atomicAdd(a.rowCounters + a.rowBase + row, 1u);
+                last = (old == nChunks - 1) ? 1u : 0u;
+                if (last) a.rowCounters[a.rowBase + row] = 0;              // self-reset for the next launch
+            }
+            last = __shfl_sync(0xffffffffu, last, 0);
+            if (last) {
+                __threadfence();
+                const float* pbase = a.partials + (size_t)sm.prefix[row] * stride;
+                for (uint32_t col = lane * 4; col < stride; col += 128) {
+                    float4 sum = make_float4(0.f, 0.f, 0.f, 0.f);
+                    for (uint32_t kk = 0; kk < nChunks; kk++) {
+                        const float4 x = ldg_cg_f4(reinterpret_cast<const float4*>(pbase + (size_t)kk * stride + col));
+                        sum.x += x.x; sum.y += x.y; sum.z += x.z; sum.w += x.w;
+                    }
+                    float v[4] = {sum.x, sum.y, sum.z, sum.w};
+#pragma unroll
+                    for (int q = 0; q < 4; q++) {
+                        const float zold = a.bias ? __ldg(a.bias + col + q) : ((a.beta == 0.0f) ? 0.0f : a.beta * zrow[col + q]);
+                        const float z = DENOISED && !ANALOG ? scale * (zold + v[q]) : fmaf(scale, v[q], zold);
+                        v[q] = (a.activation >= 0) ? apply_act(a.activation, z) : z;
+                    }
+                    *reinterpret_cast<float4*>(zrow + col) = make_float4(v[0], v[1], v[2], v[3]);
+                }
+            }
+        }
+    }
+}
+
+template <bool ANALOG, bool DENOISED>
+static int launch_zw(dsb200_ctx* ctx, const ZArgs& a)
+{
+    int grid = ctx->numSMs * 3;
+    const uint32_t want = (a.batch * 3u + 7u) / 8u;                        // ~3 items per row at the ML-20M row lengths
+    if ((uint32_t)grid > want) grid = (int)want;
+    if (grid < 1) grid = 1;
+    sparse_z_warp_kernel<ANALOG, DENOISED><<<grid, kZWThreads, 0, ctx->stream>>>(a);
+    count_launch();
+    DSB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 template <bool ADD>
 __global__ void __launch_bounds__(256) bias_kernel(float* __restrict__ unit, const float* __restrict__ bias, uint32_t stride, uint64_t size)
 {
@@ -409,7 +593,11 @@ int sparse_z_impl(dsb200_ctx* ctx, const dsb200_sparse* s, uint32_t position, ui
         int grid = ctx->numSMs * 2;
         if ((uint32_t)grid > a.batch * 4u) grid = (int)(a.batch * 4u);
         if (grid < 1) grid = 1;
-        if (vec4) {
+        if (vec4 && !ctx->zStagedKernel) {                                  // warp-autonomous kernel, 64-nnz items
+            a.chunk = 64;
+            if (analog) rc = denoised ? launch_zw<true, true>(ctx, a) : launch_zw<true, false>(ctx, a);
+            else        rc = denoised ? launch_zw<false, true>(ctx, a) : launch_zw<false, false>(ctx, a);
+        } else if (vec4) {
             if (analog) rc = denoised ? launch_z<4, true, true>(ctx, a, grid) : launch_z<4, true, false>(ctx, a, grid);
             else        rc = denoised ? launch_z<4, false, true>(ctx, a, grid) : launch_z<4, false, false>(ctx, a, grid);
         } else {

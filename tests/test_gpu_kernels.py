@@ -39,6 +39,14 @@ def test_clear_unit_add_bias(ctx, orc):
 
 
 # ------------------------------------------------------------------ a1-a3
+@pytest.fixture(params=["warp", "staged"])
+def zkernel(request, ctx):
+    """both sparse-Z kernels: the warp-autonomous one (default for stride % 4 == 0) and the TMA-staged CTA kernel"""
+    ctx.set_option("z_staged_kernel", int(request.param == "staged"))
+    yield request.param
+    ctx.set_option("z_staged_kernel", 0)
+
+
 def _run_sparse_z(ctx, orc, dsb, h, stride, batch, position=0, beta=1.0, denoised=False, shuffle=None,
                   ex_index=None, p=0.0, no_tma=False):
     import torch
@@ -60,20 +68,20 @@ def _run_sparse_z(ctx, orc, dsb, h, stride, batch, position=0, beta=1.0, denoise
 
 
 @pytest.mark.parametrize("stride", [128, 1024, 64, 96, 100, 2048])
-def test_sparse_z_boolean_strides(ctx, orc, dsb, stride):
+def test_sparse_z_boolean_strides(zkernel, ctx, orc, dsb, stride):
     h = tiny(examples=256)
     got, ref = _run_sparse_z(ctx, orc, dsb, h, stride, 256)
     assert rel_err(got, ref) < TOL
 
 
 @pytest.mark.parametrize("beta", [0.0, 1.0, 0.5])
-def test_sparse_z_beta_and_empty_rows(ctx, orc, dsb, beta):
+def test_sparse_z_beta_and_empty_rows(zkernel, ctx, orc, dsb, beta):
     h = tiny(examples=300, empty_rows=17)
     got, ref = _run_sparse_z(ctx, orc, dsb, h, 128, 256, position=44, beta=beta)
     assert rel_err(got, ref) < TOL
 
 
-def test_sparse_z_ml20m_shape_long_rows(ctx, orc, dsb):
+def test_sparse_z_ml20m_shape_long_rows(zkernel, ctx, orc, dsb):
     import scipy.sparse as sp
     h = with_long_rows(ml20m(examples=1024), [9254, 4609, 4608, 513, 512, 1])
     got, ref = _run_sparse_z(ctx, orc, dsb, h, 128, 1024)
@@ -91,7 +99,7 @@ def test_sparse_z_ml20m_shape_long_rows(ctx, orc, dsb):
     np.testing.assert_array_equal(got, got2)          # split-row combine is deterministic
 
 
-def test_sparse_z_plain_load_path_matches_tma(ctx, orc, dsb):
+def test_sparse_z_plain_load_path_matches_tma(zkernel, ctx, orc, dsb):
     h = with_long_rows(ml20m(examples=512), [3000, 700])
     a, ref = _run_sparse_z(ctx, orc, dsb, h, 128, 512, no_tma=False)
     b, _ = _run_sparse_z(ctx, orc, dsb, h, 128, 512, no_tma=True)
@@ -99,20 +107,20 @@ def test_sparse_z_plain_load_path_matches_tma(ctx, orc, dsb):
     assert rel_err(a, ref) < TOL
 
 
-def test_sparse_z_analog_weighted(ctx, orc, dsb):
+def test_sparse_z_analog_weighted(zkernel, ctx, orc, dsb):
     h = tiny(examples=256, analog=True, weighted=True)
     got, ref = _run_sparse_z(ctx, orc, dsb, h, 128, 256)
     assert rel_err(got, ref) < TOL
 
 
 @pytest.mark.parametrize("analog", [False, True])
-def test_sparse_z_denoised(ctx, orc, dsb, analog):
+def test_sparse_z_denoised(zkernel, ctx, orc, dsb, analog):
     h = tiny(examples=256, analog=analog, weighted=True)
     got, ref = _run_sparse_z(ctx, orc, dsb, h, 128, 256, denoised=True, p=0.2)
     assert rel_err(got, ref) < TOL
 
 
-def test_sparse_z_shuffled_indexed(ctx, orc, dsb):
+def test_sparse_z_shuffled_indexed(zkernel, ctx, orc, dsb):
     h = tiny(examples=200)
     rng = np.random.default_rng(3)
     ex_index = rng.integers(0, 200, size=400).astype(np.uint32)      # Indexed: 400 examples over 200 rows
@@ -121,7 +129,7 @@ def test_sparse_z_shuffled_indexed(ctx, orc, dsb):
     assert rel_err(got, ref) < TOL
 
 
-def test_sparse_z_bias_act_fused(ctx, orc, dsb):
+def test_sparse_z_bias_act_fused(zkernel, ctx, orc, dsb):
     h = tiny(examples=256, empty_rows=9)
     rng = np.random.default_rng(5)
     W = (rng.standard_normal((h.width, 128)) * 0.05).astype(np.float32)
