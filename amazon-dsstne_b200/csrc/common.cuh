@@ -53,6 +53,9 @@ struct dsb200_ctx {
     int            gemmSplits  = 0;               // option "gemm_splits": 0 = automatic split-K factor
     float*         dGemmWs     = nullptr;         // split-K partial tiles of the tcgen05 GEMM
     size_t         gemmWsCap   = 0;               // in floats
+    uint32_t*      dHeavy      = nullptr;         // sparse gradient: [0] heavy-column count, [1..] heavy-column list
+    size_t         heavyCap    = 0;
+    int            wgradTileKernel = 0;           // option "wgrad_tile_kernel": force the one-kernel tile scheme
     int            zStagedKernel = 0;             // option "z_staged_kernel": force the TMA-staged CTA kernel for sparse Z
     int            outputTileKernel = 0;          // option "output_tile_kernel": force the two-phase tile kernel in dsb200_output_pass
     int            fastMath    = 1;               // option "fast_math": MUFU exp/log/rcp in the output pass (default on)

@@ -90,6 +90,7 @@ int dsb200_ctx_destroy(dsb200_ctx* ctx)
     cudaFree(ctx->dRowCounters);
     cudaFree(ctx->dPartials);
     cudaFree(ctx->dGemmWs);
+    cudaFree(ctx->dHeavy);
     delete ctx;
     return 0;
 }
@@ -137,6 +138,7 @@ int dsb200_ctx_set_option(dsb200_ctx* ctx, const char* name, int value)
     if (!strcmp(name, "gemm_mode")) { ctx->gemmMode = value; return 0; }
     if (!strcmp(name, "profile")) { ctx->profile = value; return 0; }
     if (!strcmp(name, "fast_math")) { ctx->fastMath = value; return 0; }
+    if (!strcmp(name, "wgrad_tile_kernel")) { ctx->wgradTileKernel = value; return 0; }
     if (!strcmp(name, "z_staged_kernel")) { ctx->zStagedKernel = value; return 0; }
     if (!strcmp(name, "output_tile_kernel")) { ctx->outputTileKernel = value; return 0; }
     if (!strcmp(name, "gemm_splits")) { ctx->gemmSplits = value; return 0; }

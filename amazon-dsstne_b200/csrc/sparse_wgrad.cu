@@ -28,6 +28,7 @@ namespace dsb {
 constexpr int kGThreads = 256;
 constexpr int kGUnroll  = 8;
 constexpr uint32_t kHeavy = 96;
+constexpr uint32_t kHeavy2 = 32;                // two-kernel scheme: columns above this go to the CTA-per-column kernel
 
 struct GArgs {
     float alpha, beta;          // alpha already multiplied by q
@@ -74,7 +75,8 @@ __device__ __forceinline__ void finish_row(const GArgs& a, uint32_t c, uint32_t 
 {
     float g[4];
 #pragma unroll
-    for (int v = 0; v < 4; v++) g[v] = a.alpha * (float)((double)acc[v] * kOneOverErrorScale);   // E/kernels.cu:2585
+    for (int v = 0; v < 4; v++) g[v] = a.alpha * (__ll2float_rn(acc[v]) * 9.31322574615478515625e-10f);   // acc * 2^-30, one rounding: same value as
+                                                                                                         // (float)((double)acc * 2^-30), E/kernels.cu:2585
     const size_t off = (size_t)c * a.n + col;
     if (FUSED_MODE < 0) {
         float4 out = make_float4(g[0], g[1], g[2], g[3]);
@@ -202,6 +204,230 @@ static int launch_wgrad(dsb200_ctx* ctx, const GArgs& a)
     return 0;
 }
 
+
+// ---------------------------------------------------------------- two-kernel scheme (n % 128 == 0)
+// The column population of a recommender batch is extremely skewed: ~5 entries for the typical column, up to `batch`
+// for the Zipf head.  Kernel A gives every light column (<= kHeavy entries) to ONE WARP -- indices read coalesced into
+// registers and broadcast with shuffles, each lane gathers its float4 of the delta rows, no shared memory and no block
+// barrier, ~40 warps per SM hide the three dependent latencies (start/end -> indices -> delta rows) -- and appends the
+// heavy columns to a list.  Kernel B takes one heavy column per CTA: its 8 warps split the entries and add their int64
+// fixed-point partial sums through shared memory.  Both finish a row the same way (gradient or fused optimizer).
+template <bool ANALOG, uint32_t step>
+__device__ __forceinline__ void gather_warp(const GArgs& a, uint32_t s, uint32_t e, uint32_t first, uint32_t col, uint32_t lane, long long (&acc)[4])
+{
+    // entries s + first, s + first + step, ... < e; processed in blocks of 32 (one index per lane)
+    const float* dcol = a.delta + col;
+    for (uint32_t base = s + first; base < e; base += 32 * step) {
+        const uint32_t mine = base + lane * step;
+        uint32_t myRow = 0;
+        float myVal = 1.0f;
+        if (mine < e) {
+            myRow = __ldg(a.tIndex + mine);
+            if (ANALOG) myVal = __ldg(a.tData + mine);
+        }
+        const uint32_t n = min(32u, (e - base + step - 1) / step);
+        uint32_t j = 0;
+        for (; j + kGUnroll <= n; j += kGUnroll) {
+            float4 x[kGUnroll]; float tv[kGUnroll];
+#pragma unroll
+            for (int u = 0; u < kGUnroll; u++) {
+                const uint32_t row = __shfl_sync(0xffffffffu, myRow, j + u);
+                if (ANALOG) tv[u] = __shfl_sync(0xffffffffu, myVal, j + u);
+                x[u] = ldg_nc_f4(reinterpret_cast<const float4*>(dcol + (size_t)row * a.n));
+            }
+#pragma unroll
+            for (int u = 0; u < kGUnroll; u++) {
+                if (ANALOG) { x[u].x *= tv[u]; x[u].y *= tv[u]; x[u].z *= tv[u]; x[u].w *= tv[u]; }
+                acc[0] += fix30(x[u].x); acc[1] += fix30(x[u].y); acc[2] += fix30(x[u].z); acc[3] += fix30(x[u].w);
+            }
+        }
+        for (; j < n; j++) {
+            const uint32_t row = __shfl_sync(0xffffffffu, myRow, j);
+            float4 x = ldg_nc_f4(reinterpret_cast<const float4*>(dcol + (size_t)row * a.n));
+            if (ANALOG) { const float tv = __shfl_sync(0xffffffffu, myVal, j); x.x *= tv; x.y *= tv; x.z *= tv; x.w *= tv; }
+            acc[0] += fix30(x.x); acc[1] += fix30(x.y); acc[2] += fix30(x.z); acc[3] += fix30(x.w);
+        }
+    }
+}
+
+// Light columns hold <= 32 entries: one index (and value) per lane.  The warp software-pipelines its columns so that only
+// ONE memory latency per column stays on the critical path: the column range is fetched two columns ahead, the indices
+// one column ahead, and the weight / state row of the current column is requested before its delta rows are gathered.
+template <bool ANALOG, int FUSED_MODE>
+__global__ void __launch_bounds__(kGThreads, 3)
+sparse_wgrad_light_kernel(const GArgs a, uint32_t* __restrict__ heavyList, uint32_t* __restrict__ heavyCount)
+{
+    constexpr int M = FUSED_MODE < 0 ? 0 : FUSED_MODE;
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t gw = (blockIdx.x * kGThreads + threadIdx.x) >> 5, nw = (gridDim.x * kGThreads) >> 5;
+    // pipeline registers: range of column c + 2 nw, range + indices of column c + nw
+    uint32_t s2 = 0, e2 = 0, s1 = 0, e1 = 0, row1 = 0;
+    float val1 = 1.0f;
+    auto load_range = [&](uint32_t c, uint32_t& s, uint32_t& e) { s = 0; e = 0; if (c < a.m) { s = __ldg(a.tStart + c); e = __ldg(a.tEnd + c); } };
+    auto load_entries = [&](uint32_t s, uint32_t e, uint32_t& row, float& val) {
+        row = 0; val = 1.0f;
+        if (e - s <= kHeavy2 && s + lane < e) { row = __ldg(a.tIndex + s + lane); if (ANALOG) val = __ldg(a.tData + s + lane); }
+    };
+    load_range(gw, s1, e1);
+    load_range(gw + nw, s2, e2);
+    load_entries(s1, e1, row1, val1);
+    for (uint32_t c = gw; c < a.m; c += nw) {
+        const uint32_t s = s1, e = e1, myRow = row1;
+        const float myVal = val1;
+        s1 = s2; e1 = e2;
+        load_entries(s1, e1, row1, val1);                                     // indices of the next column
+        load_range(c + 2 * nw, s2, e2);                                       // range of the one after
+        if (e - s > kHeavy2) {
+            if (lane == 0) heavyList[atomicAdd(heavyCount, 1u)] = c;
+            continue;
+        }
+        const uint32_t cnt = e - s;
+        for (uint32_t col = lane * 4; col < a.n; col += 128) {            // n % 128 == 0: every lane is active
+            const size_t off = (size_t)c * a.n + col;
+            // request the row this column updates before the gathers (its latency overlaps theirs)
+            float4 w4 = make_float4(0, 0, 0, 0), v4 = make_float4(0, 0, 0, 0), g4 = make_float4(0, 0, 0, 0);
+            if (FUSED_MODE >= 0) {
+                w4 = *reinterpret_cast<const float4*>(a.w + off);
+                if (opt_uses_v(M))  v4 = *reinterpret_cast<const float4*>(a.v + off);
+                if (opt_uses_gv(M)) g4 = *reinterpret_cast<const float4*>(a.gv + off);
+            } else if (a.beta != 0.0f) w4 = *reinterpret_cast<const float4*>(a.dW + off);
+            long long acc[4] = {0, 0, 0, 0};
+            const float* dcol = a.delta + col;
+            uint32_t j = 0;
+            for (; j + kGUnroll <= cnt; j += kGUnroll) {
+                float4 x[kGUnroll]; float tv[kGUnroll];
+#pragma unroll
+                for (int u = 0; u < kGUnroll; u++) {
+                    const uint32_t row = __shfl_sync(0xffffffffu, myRow, j + u);
+                    if (ANALOG) tv[u] = __shfl_sync(0xffffffffu, myVal, j + u);
+                    x[u] = ldg_nc_f4(reinterpret_cast<const float4*>(dcol + (size_t)row * a.n));
+                }
+#pragma unroll
+                for (int u = 0; u < kGUnroll; u++) {
+                    if (ANALOG) { x[u].x *= tv[u]; x[u].y *= tv[u]; x[u].z *= tv[u]; x[u].w *= tv[u]; }
+                    acc[0] += fix30(x[u].x); acc[1] += fix30(x[u].y); acc[2] += fix30(x[u].z); acc[3] += fix30(x[u].w);
+                }
+            }
+            if (j < cnt) {                                                     // up to 7 more: issue them together
+                float4 x[kGUnroll]; float tv[kGUnroll];
+#pragma unroll
+                for (int u = 0; u < kGUnroll - 1; u++) {
+                    const uint32_t row = __shfl_sync(0xffffffffu, myRow, min(j + u, 31u));
+                    if (ANALOG) tv[u] = __shfl_sync(0xffffffffu, myVal, min(j + u, 31u));
+                    if (j + u < cnt) x[u] = ldg_nc_f4(reinterpret_cast<const float4*>(dcol + (size_t)row * a.n));
+                }
+#pragma unroll
+                for (int u = 0; u < kGUnroll - 1; u++) {
+                    if (j + u < cnt) {
+                        if (ANALOG) { x[u].x *= tv[u]; x[u].y *= tv[u]; x[u].z *= tv[u]; x[u].w *= tv[u]; }
+                        acc[0] += fix30(x[u].x); acc[1] += fix30(x[u].y); acc[2] += fix30(x[u].z); acc[3] += fix30(x[u].w);
+                    }
+                }
+            }
+            float g[4];
+#pragma unroll
+            for (int v = 0; v < 4; v++) g[v] = a.alpha * (__ll2float_rn(acc[v]) * 9.31322574615478515625e-10f);
+            if (FUSED_MODE < 0) {
+                float4 out = make_float4(g[0], g[1], g[2], g[3]);
+                if (a.beta != 0.0f) { out.x += a.beta * w4.x; out.y += a.beta * w4.y; out.z += a.beta * w4.z; out.w += a.beta * w4.w; }
+                *reinterpret_cast<float4*>(a.dW + off) = out;
+            } else {
+                w4.x = opt_weight<M>(a.opt, g[0], w4.x, v4.x, g4.x);
+                w4.y = opt_weight<M>(a.opt, g[1], w4.y, v4.y, g4.y);
+                w4.z = opt_weight<M>(a.opt, g[2], w4.z, v4.z, g4.z);
+                w4.w = opt_weight<M>(a.opt, g[3], w4.w, v4.w, g4.w);
+                *reinterpret_cast<float4*>(a.w + off) = w4;
+                if (opt_uses_v(M))  *reinterpret_cast<float4*>(a.v + off) = v4;
+                if (opt_uses_gv(M)) *reinterpret_cast<float4*>(a.gv + off) = g4;
+            }
+        }
+    }
+}
+
+template <bool ANALOG, int FUSED_MODE>
+__global__ void __launch_bounds__(kGThreads, 2)
+sparse_wgrad_heavy_kernel(const GArgs a, const uint32_t* __restrict__ heavyList, uint32_t* __restrict__ heavyCount)
+{
+    constexpr int M = FUSED_MODE < 0 ? 0 : FUSED_MODE;
+    __shared__ long long sRed[kGThreads / 32][128];                          // one 128-column block of int64 partials per warp
+    const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    constexpr uint32_t W = kGThreads / 32;
+    const uint32_t nh = *heavyCount;
+    // column id and range of the next heavy column are fetched while the current one is reduced
+    uint32_t cN = 0, sN = 0, eN = 0;
+    if (blockIdx.x < nh) { cN = heavyList[blockIdx.x]; sN = __ldg(a.tStart + cN); eN = __ldg(a.tEnd + cN); }
+    for (uint32_t h = blockIdx.x; h < nh; h += gridDim.x) {
+        const uint32_t c = cN, s = sN, e = eN;
+        if (h + gridDim.x < nh) { cN = heavyList[h + gridDim.x]; sN = __ldg(a.tStart + cN); eN = __ldg(a.tEnd + cN); }
+        for (uint32_t col = lane * 4; col < a.n; col += 128) {
+            const size_t off = (size_t)c * a.n + col;
+            float4 w4 = make_float4(0, 0, 0, 0), v4 = make_float4(0, 0, 0, 0), g4 = make_float4(0, 0, 0, 0);
+            if (warp == 0) {                                                  // the finishing warp requests its row up front
+                if (FUSED_MODE >= 0) {
+                    w4 = *reinterpret_cast<const float4*>(a.w + off);
+                    if (opt_uses_v(M))  v4 = *reinterpret_cast<const float4*>(a.v + off);
+                    if (opt_uses_gv(M)) g4 = *reinterpret_cast<const float4*>(a.gv + off);
+                } else if (a.beta != 0.0f) w4 = *reinterpret_cast<const float4*>(a.dW + off);
+            }
+            long long acc[4] = {0, 0, 0, 0};
+            gather_warp<ANALOG, W>(a, s, e, warp, col, lane, acc);            // warp w takes entries w, w + 8, ...
+#pragma unroll
+            for (int v = 0; v < 4; v++) sRed[warp][lane * 4 + v] = acc[v];
+            __syncthreads();
+            if (warp == 0) {
+                long long tot[4] = {0, 0, 0, 0};
+#pragma unroll
+                for (uint32_t w = 0; w < W; w++)
+#pragma unroll
+                    for (int v = 0; v < 4; v++) tot[v] += sRed[w][lane * 4 + v];
+                float g[4];
+#pragma unroll
+                for (int v = 0; v < 4; v++) g[v] = a.alpha * (__ll2float_rn(tot[v]) * 9.31322574615478515625e-10f);
+                if (FUSED_MODE < 0) {
+                    float4 out = make_float4(g[0], g[1], g[2], g[3]);
+                    if (a.beta != 0.0f) { out.x += a.beta * w4.x; out.y += a.beta * w4.y; out.z += a.beta * w4.z; out.w += a.beta * w4.w; }
+                    *reinterpret_cast<float4*>(a.dW + off) = out;
+                } else {
+                    w4.x = opt_weight<M>(a.opt, g[0], w4.x, v4.x, g4.x);
+                    w4.y = opt_weight<M>(a.opt, g[1], w4.y, v4.y, g4.y);
+                    w4.z = opt_weight<M>(a.opt, g[2], w4.z, v4.z, g4.z);
+                    w4.w = opt_weight<M>(a.opt, g[3], w4.w, v4.w, g4.w);
+                    *reinterpret_cast<float4*>(a.w + off) = w4;
+                    if (opt_uses_v(M))  *reinterpret_cast<float4*>(a.v + off) = v4;
+                    if (opt_uses_gv(M)) *reinterpret_cast<float4*>(a.gv + off) = g4;
+                }
+            }
+            __syncthreads();
+        }
+    }
+}
+
+// the heavy kernel reads the count the light kernel produced; the count is cleared by a memset node ahead of the pair
+template <bool ANALOG, int FUSED_MODE>
+static int launch_wgrad2(dsb200_ctx* ctx, const GArgs& a)
+{
+    if (a.m + 1 > ctx->heavyCap) {
+        DSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->dHeavy);
+        ctx->dHeavy = nullptr; ctx->heavyCap = 0;
+        DSB_CUDA_OK(cudaMalloc(&ctx->dHeavy, ((size_t)a.m + 1) * sizeof(uint32_t)));
+        ctx->heavyCap = a.m + 1;
+    }
+    uint32_t* count = ctx->dHeavy;                                            // [0] = count, [1..] = list
+    DSB_CUDA_OK(cudaMemsetAsync(count, 0, sizeof(uint32_t), ctx->stream));
+    const uint32_t warps = kGThreads / 32;
+    int grid = ctx->numSMs * 4;
+    if ((uint32_t)grid > (a.m + warps - 1) / warps) grid = (int)((a.m + warps - 1) / warps);
+    if (grid < 1) grid = 1;
+    sparse_wgrad_light_kernel<ANALOG, FUSED_MODE><<<grid, kGThreads, 0, ctx->stream>>>(a, count + 1, count);
+    count_launch();
+    DSB_CUDA_OK(cudaGetLastError());
+    sparse_wgrad_heavy_kernel<ANALOG, FUSED_MODE><<<ctx->numSMs * 2, kGThreads, 0, ctx->stream>>>(a, count + 1, count);
+    count_launch();
+    DSB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 static int check_wgrad_args(dsb200_ctx* ctx, const uint32_t* tStart, const uint32_t* tEnd, const uint32_t* tIndex, const float* delta)
 {
     if (!ctx || !tStart || !tEnd || !tIndex || !delta) return fail(ctx, DSB200_EINVAL, "sparse_wgrad: null argument");
@@ -227,6 +453,7 @@ int dsb200_sparse_wgrad(dsb200_ctx* ctx, float alpha, float beta, uint32_t m, ui
     a.beta = beta; a.m = m; a.n = n;
     a.tStart = tStart; a.tEnd = tEnd; a.tIndex = tIndex; a.tData = tData; a.delta = delta; a.dW = dW;
     const bool vec = (n % 4 == 0) && ((((uintptr_t)delta | (uintptr_t)dW) % 16) == 0);
+    if (vec && (n % 128 == 0) && !ctx->wgradTileKernel) return tData ? launch_wgrad2<true, -1>(ctx, a) : launch_wgrad2<false, -1>(ctx, a);
     if (vec) return tData ? launch_wgrad<true, -1>(ctx, a) : launch_wgrad<false, -1>(ctx, a);
     uint64_t blocks = ((uint64_t)m * n + 255) / 256;
     if (blocks > (uint64_t)ctx->numSMs * 8) blocks = (uint64_t)ctx->numSMs * 8;
@@ -259,7 +486,9 @@ int dsb200_sparse_wgrad_update(dsb200_ctx* ctx, int mode, float galpha, uint32_t
     a.tStart = tStart; a.tEnd = tEnd; a.tIndex = tIndex; a.tData = tData; a.delta = delta; a.dW = nullptr;
     a.opt = make_opt(mode, alpha, lambda, lambda1, mu, mu1, t);
     a.v = v; a.gv = gv; a.w = w;
-#define DSB_FUSED(M) (tData ? launch_wgrad<true, M>(ctx, a) : launch_wgrad<false, M>(ctx, a))
+    const bool two = (n % 128 == 0) && !ctx->wgradTileKernel;
+#define DSB_FUSED(M) (two ? (tData ? launch_wgrad2<true, M>(ctx, a) : launch_wgrad2<false, M>(ctx, a)) \
+                          : (tData ? launch_wgrad<true, M>(ctx, a) : launch_wgrad<false, M>(ctx, a)))
     switch (mode) {
     case DSB200_SGD:      return DSB_FUSED(DSB200_SGD);
     case DSB200_MOMENTUM: return DSB_FUSED(DSB200_MOMENTUM);

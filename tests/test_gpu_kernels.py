@@ -200,8 +200,16 @@ def test_sparse_transpose_unsorted_is_same_set(ctx, orc, dsb):
         np.testing.assert_array_equal(a, b)
 
 
+@pytest.fixture(params=["two_kernel", "tile"])
+def gkernel(request, ctx):
+    """both sparse-gradient schemes: warp-per-light-column + CTA-per-heavy-column (default when n % 128 == 0) and the tile kernel"""
+    ctx.set_option("wgrad_tile_kernel", int(request.param == "tile"))
+    yield request.param
+    ctx.set_option("wgrad_tile_kernel", 0)
+
+
 @pytest.mark.parametrize("case", ["tiny128", "ml20m128", "tiny1024", "analog", "beta", "stride100"])
-def test_sparse_wgrad_bit_exact(ctx, orc, dsb, case):
+def test_sparse_wgrad_bit_exact(gkernel, ctx, orc, dsb, case):
     import torch
     n = {"tiny1024": 1024, "stride100": 100}.get(case, 128)
     if case == "ml20m128":
@@ -226,7 +234,7 @@ def test_sparse_wgrad_bit_exact(ctx, orc, dsb, case):
 
 
 @pytest.mark.parametrize("mode", range(7))
-def test_sparse_wgrad_update_fused_equals_unfused(ctx, orc, dsb, mode):
+def test_sparse_wgrad_update_fused_equals_unfused(gkernel, ctx, orc, dsb, mode):
     h, batch, n = tiny(256), 256, 128
     (tstart, r_end, r_idx, r_data), (d_start, d_end, d_idx, d_data), params = _transpose_case(ctx, orc, dsb, h, batch)
     rng = np.random.default_rng(8)
