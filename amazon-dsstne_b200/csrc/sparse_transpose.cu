@@ -200,6 +200,62 @@ static int launch_scatter(dsb200_ctx* ctx, const TArgs& a)
     return 0;
 }
 
+
+// ---------------------------------------------------------------- capacity table on the device (a4)
+// NNDataSet<T>::GenerateSparseTransposedMatrix (E/NNTypes.cpp:1631-1735) sizes every transposed column on the host from
+// per-column datapoint counts of the whole dataset.  For a dataset that is replaced every step (a serving / streaming
+// caller loading one batch at a time) that host pass is the dominant cost, so the same table is built here: count the
+// entries of every column over the first `rows` examples, then tStart = exclusive prefix of the counts rounded up to a
+// multiple of 32 (the reference's alignment).  Exact per-column counts are an upper bound for any batch window.
+__global__ void __launch_bounds__(256)
+column_count_kernel(const uint64_t* __restrict__ start, const uint64_t* __restrict__ end, const uint32_t* __restrict__ index, uint32_t rows,
+                    uint32_t N, uint32_t* __restrict__ count, volatile uint32_t* status)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t gw = (blockIdx.x * blockDim.x + threadIdx.x) >> 5, nw = (gridDim.x * blockDim.x) >> 5;
+    for (uint32_t r = gw; r < rows; r += nw) {
+        const uint64_t s = __ldg(start + r), e = __ldg(end + r);
+        for (uint64_t j = s + lane; j < e; j += 32) {
+            const uint32_t c = __ldg(index + j);
+            if (c < N) atomicAdd(count + c, 1u);
+            else *status = DSB200_STATUS_T_OVERFLOW;
+        }
+    }
+}
+
+// single CTA: exclusive scan of align32(count) -> tStart; total capacity -> *pTotal (may be NULL)
+__global__ void __launch_bounds__(1024)
+capacity_scan_kernel(const uint32_t* __restrict__ count, uint32_t N, uint32_t* __restrict__ tStart, uint32_t* __restrict__ pTotal)
+{
+    __shared__ uint32_t sWarp[32];
+    const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t per = (N + 1023) / 1024;
+    const uint32_t lo = min(tid * per, N), hi = min(lo + per, N);
+    uint32_t local = 0;
+    for (uint32_t i = lo; i < hi; i++) local += (count[i] + 31u) & ~31u;
+    uint32_t incl = local;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+        if (lane >= (uint32_t)o) incl += n;
+    }
+    if (lane == 31) sWarp[warp] = incl;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = sWarp[lane], wi = w;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t n = __shfl_up_sync(0xffffffffu, wi, o);
+            if (lane >= (uint32_t)o) wi += n;
+        }
+        sWarp[lane] = wi - w;                                             // exclusive warp offsets
+        if (lane == 31 && pTotal) *pTotal = wi;
+    }
+    __syncthreads();
+    uint32_t run = sWarp[warp] + incl - local;
+    for (uint32_t i = lo; i < hi; i++) { tStart[i] = run; run += (count[i] + 31u) & ~31u; }
+}
+
 }  // namespace dsb
 
 extern "C" int dsb200_sparse_transpose(dsb200_ctx* ctx, const dsb200_sparse* s, uint32_t position, uint32_t batch, int denoised,
@@ -235,5 +291,27 @@ extern "C" int dsb200_sparse_transpose(dsb200_ctx* ctx, const dsb200_sparse* s, 
         count_launch();
         DSB_CUDA_OK(cudaGetLastError());
     }
+    return 0;
+}
+
+extern "C" int dsb200_transposed_capacity(dsb200_ctx* ctx, const dsb200_sparse* s, uint32_t rows, uint32_t N, uint32_t* pCountScratch,
+                                          uint32_t* pTransposedStart, uint32_t* pDevTotal)
+{
+    DSB_PROFILE(ctx, "transposed_capacity");
+    using namespace dsb;
+    if (!ctx || !s || !pCountScratch || !pTransposedStart || !N) return fail(ctx, DSB200_EINVAL, "transposed_capacity: null argument");
+    if (!s->sparseStart || !s->sparseEnd || !s->sparseIndex) return fail(ctx, DSB200_EINVAL, "transposed_capacity: CSR arrays missing");
+    if (s->index) return fail(ctx, DSB200_EUNSUPPORTED, "transposed_capacity: indexed datasets size their table on the host");
+    DSB_CUDA_OK(cudaMemsetAsync(pCountScratch, 0, (size_t)N * sizeof(uint32_t), ctx->stream));
+    if (rows) {
+        int grid = (int)((rows + 7) / 8);
+        if (grid > ctx->numSMs * 8) grid = ctx->numSMs * 8;
+        column_count_kernel<<<grid, 256, 0, ctx->stream>>>(s->sparseStart, s->sparseEnd, s->sparseIndex, rows, N, pCountScratch, ctx->dStatus);
+        count_launch();
+        DSB_CUDA_OK(cudaGetLastError());
+    }
+    capacity_scan_kernel<<<1, 1024, 0, ctx->stream>>>(pCountScratch, N, pTransposedStart, pDevTotal);
+    count_launch();
+    DSB_CUDA_OK(cudaGetLastError());
     return 0;
 }

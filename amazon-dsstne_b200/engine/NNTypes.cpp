@@ -13,6 +13,7 @@
 #include <sstream>
 
 #include "NNLayer.h"
+#include "NNNetwork.h"
 
 using namespace std;
 
@@ -113,7 +114,52 @@ void NNDataSet<T>::LoadSparseData(const uint64_t* srcSparseStart, const uint64_t
                                   const uint32_t* srcSparseIndex)
 {
     CopySparseData(srcSparseStart, srcSparseEnd, srcSparseData, srcSparseIndex);
-    UploadSparse();
+    if (_sharding == NNDataSetEnums::Model && getGpu()._numprocs > 1) { UploadSparse(); return; }   // column shards are rebuilt on the host
+    UploadSparseAsync(srcSparseStart, srcSparseEnd, srcSparseData, srcSparseIndex, srcSparseEnd[_uniqueExamples - 1]);
+}
+
+// The call a serving / streaming caller makes once per batch (the reference's JNI binding, java/.../dsstne.cpp): the source
+// arrays go through pinned staging (two sets, so the caller never waits for the previous batch's copy) and only the used
+// part of the index / value arrays travels, as asynchronous copies on the engine's stream -- no stream synchronisation.
+template <typename T>
+void NNDataSet<T>::UploadSparseAsync(const uint64_t* srcStart, const uint64_t* srcEnd, const void* srcData, const uint32_t* srcIndex, uint64_t dataLength)
+{
+    Staging& st = _staging[_stagingCur];
+    _stagingCur ^= 1;
+    if (!st.start) {
+        RTERROR(cudaHostAlloc((void**)&st.start, _vSparseStart.size() * sizeof(uint64_t), cudaHostAllocDefault), "NNDataSet staging");
+        RTERROR(cudaHostAlloc((void**)&st.end, _vSparseEnd.size() * sizeof(uint64_t), cudaHostAllocDefault), "NNDataSet staging");
+        RTERROR(cudaHostAlloc((void**)&st.index, max<size_t>(_vSparseIndex.size(), 1) * sizeof(uint32_t), cudaHostAllocDefault), "NNDataSet staging");
+        RTERROR(cudaHostAlloc((void**)&st.data, max<size_t>(_vSparseData.size(), 1) * sizeof(T), cudaHostAllocDefault), "NNDataSet staging");
+        RTERROR(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming), "NNDataSet staging event");
+    }
+    if (st.pending) { RTERROR(cudaEventSynchronize(st.done), "NNDataSet staging wait"); st.pending = false; }
+    cudaStream_t stream = getGpu().GetStream();
+    memcpy(st.start, srcStart, _uniqueExamples * sizeof(uint64_t));
+    memcpy(st.end, srcEnd, _uniqueExamples * sizeof(uint64_t));
+    memcpy(st.index, srcIndex, dataLength * sizeof(uint32_t));
+    RTERROR(cudaMemcpyAsync(_pbSparseStart->_pDevData, st.start, _uniqueExamples * sizeof(uint64_t), cudaMemcpyHostToDevice, stream), "NNDataSet upload");
+    RTERROR(cudaMemcpyAsync(_pbSparseEnd->_pDevData, st.end, _uniqueExamples * sizeof(uint64_t), cudaMemcpyHostToDevice, stream), "NNDataSet upload");
+    if (dataLength) RTERROR(cudaMemcpyAsync(_pbSparseIndex->_pDevData, st.index, dataLength * sizeof(uint32_t), cudaMemcpyHostToDevice, stream), "NNDataSet upload");
+    if (srcData && dataLength) {
+        memcpy(st.data, srcData, dataLength * sizeof(T));
+        RTERROR(cudaMemcpyAsync(_pbSparseData->_pDevData, st.data, dataLength * sizeof(T), cudaMemcpyHostToDevice, stream), "NNDataSet upload");
+    }
+    RTERROR(cudaEventRecord(st.done, stream), "NNDataSet staging record");
+    st.pending = true;
+}
+
+template <typename T>
+NNDataSet<T>::~NNDataSet()
+{
+    for (Staging& st : _staging) {
+        if (st.pending) cudaEventSynchronize(st.done);
+        if (st.start) cudaFreeHost(st.start);
+        if (st.end) cudaFreeHost(st.end);
+        if (st.index) cudaFreeHost(st.index);
+        if (st.data) cudaFreeHost(st.data);
+        if (st.done) cudaEventDestroy(st.done);
+    }
 }
 
 template <typename T>
@@ -247,6 +293,32 @@ bool NNDataSet<T>::CalculateSparseDatapointCounts()
 template <typename T>
 bool NNDataSet<T>::GenerateSparseTransposedMatrix(uint32_t batch, NNLayer* pLayer)
 {
+    // A dataset no larger than one batch that is re-loaded every step (streaming / serving callers): the capacity table is
+    // built on the device from exact per-column counts (dsb200_transposed_capacity) -- no host pass over the entries,
+    // no read-back; the index buffer is sized by its upper bound nnz + 31 * N.
+    if (_bDirty && !(_attributes & NNDataSetEnums::Indexed) && _uniqueExamples <= batch && !(_sharding == NNDataSetEnums::Model && getGpu()._numprocs > 1) &&
+        getGpu()._pNetwork && getGpu()._pNetwork->FusionEnabled()) {
+        uint64_t N = (uint64_t)_width * _height * _length;
+        if (pLayer) { uint32_t Nx, Ny, Nz, Nw; tie(Nx, Ny, Nz, Nw) = pLayer->GetLocalDimensions(); N = max<uint64_t>(N, (uint64_t)Nx * Ny * Nz * Nw); }
+        if (_vSparseTransposedStart.size() != N) _vSparseTransposedStart.assign(N, 0);        // size only: the table itself lives on the device
+        if (!_pbSparseTransposedStart || _pbSparseTransposedStart->_length < N) _pbSparseTransposedStart.reset(new GpuBuffer<uint32_t>(N));
+        if (!_pbSparseTransposedEnd || _pbSparseTransposedEnd->_length < N) _pbSparseTransposedEnd.reset(new GpuBuffer<uint32_t>(N));
+        if (!_pbColumnCount || _pbColumnCount->_length < N) _pbColumnCount.reset(new GpuBuffer<uint32_t>(N));
+        const uint64_t bound = (uint64_t)_vSparseIndex.size() + 31ull * N + 32;
+        if (bound > _sparseTransposedIndices || !_pbSparseTransposedIndex) {
+            _sparseTransposedIndices = bound;
+            _pbSparseTransposedIndex.reset(new GpuBuffer<uint32_t>(_sparseTransposedIndices));
+            if (!(_attributes & NNDataSetEnums::Boolean) || (_attributes & NNDataSetEnums::Weighted))
+                _pbSparseTransposedData.reset(new GpuBuffer<NNFloat>(_sparseTransposedIndices));
+        }
+        dsb200_sparse v = View();
+        getGpu().Check(dsb200_transposed_capacity(getGpu()._ctx, &v, _uniqueExamples, (uint32_t)N, _pbColumnCount->_pDevData,
+                                                  _pbSparseTransposedStart->_pDevData, NULL), "dsb200_transposed_capacity");
+        _batch = batch;
+        _maxBatchNnz = (uint32_t)min<uint64_t>(_vSparseEnd[_uniqueExamples - 1] - _vSparseStart[0], 0xffffffffu);
+        _bDirty = false;
+        return true;
+    }
     if (_bDirty) { CalculateSparseDatapointCounts(); _bDirty = false; }
     const uint64_t NData = _vSparseDatapointCount.size();
     uint64_t NLayer = NData;

@@ -201,7 +201,6 @@ public:
     // sparse indexed dataset (E/NNTypes.cpp:703-741)
     NNDataSet(uint32_t examples, uint32_t uniqueExamples, size_t sparseDataSize, const NNDataSetDimensions& dim,
               bool isIndexed = false, bool isWeighted = false, const string& name = "");
-    ~NNDataSet() {}
 
     bool SaveNetCDF(const string& fname);
     void RefreshState(uint32_t batch) { (void)batch; }
@@ -244,6 +243,17 @@ public:
 
 private:
     void UploadSparse();
+    // streaming path of LoadSparseData: pinned double-buffered staging + asynchronous copies of the used part only
+    void UploadSparseAsync(const uint64_t* srcStart, const uint64_t* srcEnd, const void* srcData, const uint32_t* srcIndex, uint64_t dataLength);
+    struct Staging {
+        uint64_t* start = nullptr; uint64_t* end = nullptr; uint32_t* index = nullptr; T* data = nullptr;
+        cudaEvent_t done = nullptr; bool pending = false;
+    } _staging[2];
+    int _stagingCur = 0;
+    unique_ptr<GpuBuffer<uint32_t>> _pbColumnCount;        // scratch of the device-side capacity table
+public:
+    ~NNDataSet();
+private:
     float SyncError(ErrorFunction ef, Activation activation, uint32_t position, uint32_t batch, uint32_t stride, NNFloat* pUnit);
 };
 

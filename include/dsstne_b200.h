@@ -135,6 +135,13 @@ int dsb200_sparse_transpose(dsb200_ctx*, const dsb200_sparse* s, uint32_t positi
                             uint32_t N, const uint32_t* pTransposedStart, uint32_t* pTransposedEnd,
                             uint32_t* pTransposedIndex, float* pTransposedData);
 
+/* a4 on the device: the capacity table of NNDataSet<T>::GenerateSparseTransposedMatrix (E/NNTypes.cpp:1631-1735) for a
+ * non-indexed dataset that is replaced every step: per-column entry counts over the first `rows` examples (exact, hence
+ * an upper bound for any batch window), pTransposedStart = exclusive prefix of the counts rounded up to multiples of 32.
+ * pCountScratch: N uint32 of scratch; pDevTotal (device, may be NULL) receives the total capacity.                       */
+int dsb200_transposed_capacity(dsb200_ctx*, const dsb200_sparse* s, uint32_t rows, uint32_t N, uint32_t* pCountScratch,
+                               uint32_t* pTransposedStart, uint32_t* pDevTotal);
+
 /* ------------------------------------------------------------------ a6
  * kCalculateSparseTransposed[Analog]WeightGradient, E/kernels.h:81,93 (E/kernels.cu:2537-2692)
  *   dW[c,:] = beta*dW[c,:] + alpha*q * sum_{e in column c} (tdata_e *) pDelta[row_e,:]

@@ -187,6 +187,48 @@ def test_dropout_training_matches_oracle(eng, orc):
     net.close()
 
 
+def test_streamed_batches_through_load_sparse_match_oracle(eng, orc):
+    """The serving / streaming path bench.py's e2e number runs: a dataset the size of ONE batch is re-loaded every step with
+    NNDataSet::LoadSparseData (pinned staging + asynchronous copies) and its transposed capacity table is rebuilt on the
+    device (dsb200_transposed_capacity).  Same losses and weights as the oracle stepping through the resident dataset."""
+    from dsstne_b200 import datagen
+    sizes, batch = [2048, 128, 2048], 256
+    h = tiny(examples=3 * batch, width=2048)
+    parts = []
+    for b in range(3):
+        s0 = int(h.start[b * batch])
+        parts.append(((h.start[b * batch:(b + 1) * batch] - np.uint64(s0)).astype(np.uint64), (h.end[b * batch:(b + 1) * batch] - np.uint64(s0)).astype(np.uint64),
+                      np.ascontiguousarray(h.index[s0:int(h.end[(b + 1) * batch - 1])])))
+    big = max(parts, key=lambda p: len(p[2]))
+    ds_in = eng.Dataset("gl_input", big[0], big[1], big[2], 2048)
+    ds_out = eng.Dataset("gl_output", big[0], big[1], big[2], 2048)
+    net = eng.Network(eng.autoencoder_json([128]), batch, [ds_in, ds_out])
+    net.set_training_mode(orc.MOMENTUM)
+    Ws, bs = datagen.make_weights(sizes, scale=0.05)
+    names = ["Input", "Hidden1", "Output"]
+    for i in range(2):
+        net.set_weights(names[i], names[i + 1], Ws[i], bs[i])
+    onet = orc.Network(sizes, error=orc.ERR_SMCE, mode=orc.MOMENTUM, max_batch=batch)
+    for i in range(2):
+        onet.W(i)[:] = Ws[i]
+        onet.b(i)[:] = bs[i]
+    onet.s.params = orc.make_params(smce=(1.0, 0.0, 1.0, 1.0))
+    oc = to_oracle(orc, h)
+    onet.set_input(oc, batch)
+    for step, b in enumerate([0, 2, 1, 0]):
+        st, en, ix = parts[b]
+        ds_in.load_sparse(st, en, ix)
+        ds_out.load_sparse(st, en, ix)
+        got = net.train_step(0, 0.025, 1e-4, 0.0, 0.5, 0.0)
+        want, _ = onet.train_step(oc, oc, b * batch, batch, 0.025, 1e-4, 0.0, 0.5, 0.0)
+        assert abs(got - want) <= TOL * abs(want), f"step {step}"
+    for i in range(2):
+        W, bb = net.get_weights(names[i], names[i + 1])
+        assert rel_err(W.reshape(onet.W(i).shape), onet.W(i)) < TOL
+        assert rel_err(bb, onet.b(i)) < 5e-5
+    net.close()
+
+
 def test_predict_and_topk_with_filter(eng, orc):
     sizes, batch = [2048, 128, 2048], 256
     h = tiny(examples=256, width=2048)
