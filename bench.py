@@ -228,7 +228,10 @@ def run_ours(args, wl, rank, world, local_rank):
                   "clocks": sampler.summary(), "gpu_launches": int(launches), "roofline": roof, "kernels": kern}
         if e2e:
             result["e2e"] = e2e
-        result["cpu_baseline"] = cpu_baseline(wl, data, sample_steps=args.cpu_steps)
+        else:
+            result["e2e"] = {"value": None, "unit": UNIT, "h2d_bytes_per_step": None, "d2h_bytes_per_step": None,
+                             "note": "measured at N=1 only: the per-step LoadSparseData streaming path re-shards on the host when model parallel"}
+        result["cpu_baseline"] = cpu_baseline(wl, data, sample_steps=max(1, args.cpu_steps))
     net.close()
     if world > 1:
         import torch.distributed as dist
