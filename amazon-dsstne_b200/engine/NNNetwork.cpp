@@ -43,7 +43,7 @@ NNNetwork::NNNetwork(NNNetworkDescriptor& d, uint32_t batch)
       _SMCE_oneTarget(d._SMCE_oneTarget), _SMCE_zeroTarget(d._SMCE_zeroTarget), _SMCE_oneScale(d._SMCE_oneScale),
       _SMCE_zeroScale(d._SMCE_zeroScale), _bShuffleIndices(d._bShuffleIndices), _shuffleIndices(0), _shuffleEpoch(0),
       _checkpoint_name(d._checkpoint_name), _checkpoint_interval(d._checkpoint_interval), _checkpoint_epochs(0), _bDirty(true),
-      _bClearVelocity(true), _scratchBufferSize(0), _maxStride(0), _errorEvent(NULL), _verbose(false), _bFusion(true),
+      _bClearVelocity(true), _scratchBufferSize(0), _maxStride(0), _errorEvent(NULL), _sideStream(NULL), _forkEvent(NULL), _joinEvent(NULL), _verbose(false), _bRegularizationLaunched(false), _bFusion(true),
       _movingAverage(0.0f), _brakeSteps(0), _initSteps(100)
 {
     if (!getGpu()._ctx) throw DsbEngineError("NNNetwork: getGpu().Startup() has not been called (no GPU context; there is no CPU fallback)");
@@ -69,6 +69,9 @@ NNNetwork::NNNetwork(NNNetworkDescriptor& d, uint32_t batch)
     CalculatePropagationOrder();
     _pbErrorAccumulator.reset(new GpuBuffer<unsigned long long>(4, true));
     RTERROR(cudaEventCreateWithFlags(&_errorEvent, cudaEventDisableTiming), "NNNetwork: cudaEventCreate");
+    RTERROR(cudaEventCreateWithFlags(&_forkEvent, cudaEventDisableTiming), "NNNetwork: cudaEventCreate");
+    RTERROR(cudaEventCreateWithFlags(&_joinEvent, cudaEventDisableTiming), "NNNetwork: cudaEventCreate");
+    RTERROR(cudaStreamCreateWithFlags(&_sideStream, cudaStreamNonBlocking), "NNNetwork: cudaStreamCreate");
 }
 
 NNNetwork::~NNNetwork()
@@ -77,6 +80,9 @@ NNNetwork::~NNNetwork()
     for (auto w : _vWeight) delete w;
     for (auto l : _vLayer) delete l;
     if (_errorEvent) cudaEventDestroy(_errorEvent);
+    if (_forkEvent) cudaEventDestroy(_forkEvent);
+    if (_joinEvent) cudaEventDestroy(_joinEvent);
+    if (_sideStream) cudaStreamDestroy(_sideStream);
 }
 
 // Kahn's algorithm over the layer graph, ties broken by declaration order (the reference assigns
@@ -421,19 +427,44 @@ void NNNetwork::LaunchError(NNFloat lambda, NNFloat lambda1)
     if (_position + batch > _examples) batch = _examples - _position;
     cudaStream_t s = getGpu().GetStream();
     unsigned long long* acc = _pbErrorAccumulator->_pDevData;        // [0] training error, [1] regularisation error
-    RTERROR(cudaMemsetAsync(acc, 0, 2 * sizeof(unsigned long long), s), "LaunchError memset");
+    if (!_bRegularizationLaunched) {
+        RTERROR(cudaMemsetAsync(acc, 0, 2 * sizeof(unsigned long long), s), "LaunchError memset");
+        LaunchRegularization(lambda, lambda1, false);
+    }
+    _bRegularizationLaunched = false;
     for (auto l : _vOutputLayer) l->CalculateErrorAsync(_position, batch, _errorFunction, acc);
-    // regularisation error of every weight shard (E/NNNetwork.cpp:1724-1730), into the second fixed-point word instead
-    // of one blocking Download per weight matrix (kCalculateRegularizationError, E/kernels.cu:2736-2744)
-    if (lambda != (NNFloat)0.0 || lambda1 != (NNFloat)0.0)
-        for (auto w : _vWeight)
-            if (!w->_bShared)
-                getGpu().Check(dsb200_regularization_error_async(getGpu()._ctx, lambda, lambda1, w->_pbWeight->_pDevData, w->_localSize, acc + 1),
-                               "dsb200_regularization_error_async");
+    RTERROR(cudaStreamWaitEvent(s, _joinEvent, 0), "LaunchError join");
     if (getGpu()._numprocs > 1)
         getGpu().Check(dsb200_all_reduce_u64(getGpu()._ctx, acc, 2), "dsb200_all_reduce_u64");
     RTERROR(cudaMemcpyAsync(_pbErrorAccumulator->_pSysData, acc, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s), "LaunchError copy");
     RTERROR(cudaEventRecord(_errorEvent, s), "LaunchError event");
+}
+
+// Regularisation error of every weight shard (E/NNNetwork.cpp:1724-1730) into the second fixed-point word of the
+// accumulator (kCalculateRegularizationError, E/kernels.cu:2736-2744) -- no blocking Download per weight matrix.  The
+// weights do not change between the end of one update and the next, so with `fork` the kernels run on a side stream
+// BESIDE the forward pass (they read 2 x 14 MB of weights for BASELINE config 2) and join before the read-back.
+void NNNetwork::LaunchRegularization(NNFloat lambda, NNFloat lambda1, bool fork)
+{
+    cudaStream_t s = getGpu().GetStream();
+    unsigned long long* acc = _pbErrorAccumulator->_pDevData;
+    const bool any = lambda != (NNFloat)0.0 || lambda1 != (NNFloat)0.0;
+    if (fork && any) {
+        RTERROR(cudaEventRecord(_forkEvent, s), "LaunchRegularization fork");
+        RTERROR(cudaStreamWaitEvent(_sideStream, _forkEvent, 0), "LaunchRegularization fork wait");
+        getGpu().Check(dsb200_ctx_set_stream(getGpu()._ctx, _sideStream), "dsb200_ctx_set_stream");
+    }
+    if (any)
+        for (auto w : _vWeight)
+            if (!w->_bShared)
+                getGpu().Check(dsb200_regularization_error_async(getGpu()._ctx, lambda, lambda1, w->_pbWeight->_pDevData, w->_localSize, acc + 1),
+                               "dsb200_regularization_error_async");
+    if (fork && any) {
+        getGpu().Check(dsb200_ctx_set_stream(getGpu()._ctx, s), "dsb200_ctx_set_stream");
+        RTERROR(cudaEventRecord(_joinEvent, _sideStream), "LaunchRegularization join");
+    } else {
+        RTERROR(cudaEventRecord(_joinEvent, s), "LaunchRegularization join");
+    }
 }
 
 tuple<NNFloat, NNFloat> NNNetwork::CalculateError(NNFloat lambda, NNFloat lambda1)
@@ -478,8 +509,13 @@ float NNNetwork::TrainStep(uint32_t position, NNFloat alpha, NNFloat lambda, NNF
     if (_bDirty) RefreshState();
     SetPosition(position);
     ClearUpdates();
+    if (_bFusion) {                                  // regularisation error on the side stream while the forward pass runs
+        RTERROR(cudaMemsetAsync(_pbErrorAccumulator->_pDevData, 0, 2 * sizeof(unsigned long long), getGpu().GetStream()), "TrainStep memset");
+        LaunchRegularization(lambda, lambda1, true);
+        _bRegularizationLaunched = true;
+    }
     PredictTrainingBatch();
-    LaunchError(lambda, lambda1);                    // loss (+ output delta) + regularisation kernels and the async read-back
+    LaunchError(lambda, lambda1);                    // loss (+ output delta) kernels, join, and the async read-back
     BackPropagate();                                 // queued behind them; does not depend on the host seeing the loss
     RTERROR(cudaEventSynchronize(_errorEvent), "TrainStep event sync");
     const NNFloat error_training = (NNFloat)((double)(long long)_pbErrorAccumulator->_pSysData[0] * (1.0 / 1073741824.0));

@@ -66,7 +66,10 @@ private:
     unique_ptr<GpuBuffer<NNFloat>> _pbP2PBuffer;          // full-width exchange buffer ("P2P send buffer")
     unique_ptr<GpuBuffer<unsigned long long>> _pbErrorAccumulator;   // device fixed-point loss + pinned shadow
     cudaEvent_t             _errorEvent;
+    cudaStream_t            _sideStream;                  // regularisation error runs here, beside the forward pass
+    cudaEvent_t             _forkEvent, _joinEvent;
     bool                    _verbose;
+    bool                    _bRegularizationLaunched;     // LaunchError finds the regularisation kernels already in flight
     bool                    _bFusion;                     // B200 fusions on (default) / off (kernel-by-kernel, like the reference)
     // divergence-brake state that survives across Train calls made one step at a time
     NNFloat                 _movingAverage;
@@ -139,6 +142,7 @@ private:
     void ShuffleIndices();
     tuple<NNFloat, NNFloat> CalculateError(NNFloat lambda, NNFloat lambda1);
     void LaunchError(NNFloat lambda, NNFloat lambda1);     // asynchronous part of CalculateError
+    void LaunchRegularization(NNFloat lambda, NNFloat lambda1, bool fork);
     void ClearUpdates();
     void BackPropagate();
     void UpdateWeights(NNFloat alpha, NNFloat lambda, NNFloat lambda1, NNFloat mu, NNFloat mu1);
