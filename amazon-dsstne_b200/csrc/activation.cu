@@ -7,12 +7,11 @@
 // (dsb200_sparse_z_bias_act, dsb200_output_pass, the GEMM epilogues); the stand-alone entry points
 // exist because the drop-in boundary exposes them.
 //  * elementwise kernels: 128-bit accesses, grid = multiple of the SM count;
-//  * softmax: one CTA per row, row kept in registers when it fits (<= 16 values per thread),
-//    max and sum reduced through shuffles (the reference round-trips a fixed-point shared atomic);
+//  * softmax: one CTA per row, max and sum reduced through shuffles and shared memory (the reference
+//    round-trips a fixed-point shared atomic);
 //  * sparseness penalty: the reference uses one thread per hidden unit looping over the batch
 //    twice with stride `stride`; here a CTA owns 32 units x 8 batch slices, coalesced 128-byte row
-//    segments, fixed-order combine => deterministic column means, and the penalty add is fused
-//    with the Hadamard product when both are requested (dsb200_hidden_delta).
+//    segments, fixed-order combine => deterministic column means.
 #include "common.cuh"
 #include "launch.h"
 

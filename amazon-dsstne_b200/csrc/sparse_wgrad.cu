@@ -137,8 +137,8 @@ sparse_wgrad_kernel(const GArgs a, uint32_t lpr)
         __syncthreads();
         const uint32_t nh = sNHeavy;
         for (uint32_t h = 0; h < nh; h++) {
-            // smallest remaining column id first => fixed processing order (results are order
-            // independent anyway; this only keeps the memory access pattern reproducible)
+            // heavy columns of the tile in the order their warps found them (the sums are integer, so the
+            // result does not depend on it)
             const uint32_t hc = sHeavy[h];
             const uint32_t hs = __ldg(a.tStart + hc), he = __ldg(a.tEnd + hc);
             for (uint32_t cb = 0; cb < colBlocks; cb++) {

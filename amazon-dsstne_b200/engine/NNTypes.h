@@ -257,6 +257,6 @@ private:
     float SyncError(ErrorFunction ef, Activation activation, uint32_t position, uint32_t batch, uint32_t stride, NNFloat* pUnit);
 };
 
-// NetCDF dataset files (classic / 64-bit offset), E/NNTypes.cpp:2456-2584 -- see NetCDF3.h
+// NetCDF dataset files (classic CDF-1 / CDF-2 / CDF-5), E/NNTypes.cpp:2456-2584 -- see NetCDF.h, NetCDFIO.cpp
 vector<NNDataSetBase*> LoadNetCDF(const string& fname);
 bool SaveNetCDF(const string& fname, vector<NNDataSetBase*> vDataSet);
