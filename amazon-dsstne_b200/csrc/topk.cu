@@ -7,10 +7,10 @@
 // Reference: ONE warp streams a whole row (4 MB for N = 1M) with 128-byte loads and a 2k-wide
 // register bitonic network; 4,096 rows = 4,096 warps on the whole GPU, latency bound.
 // Here a row is cut into segments so that the grid holds >= 8 CTAs per SM:
-//   pass 1  CTA = (row, segment): streams the segment with 128-bit loads, zeroes the scores named
-//           by the row's exclusion list through a shared-memory bitmap, keeps candidates strictly
-//           above the running k-th key in a 4,096-entry shared buffer that is bitonic-sorted and cut
-//           back to k whenever it fills, and emits the segment's top-k (sorted);
+//   pass 1  CTA = (row, segment): streams the segment with 128-bit loads (four in flight per thread), zeroes the
+//           scores named by the row's exclusion list through a shared-memory bitmap, keeps candidates strictly
+//           above the running k-th key in a 4,096-entry shared buffer that is cut back to the k best with an
+//           O(n) radix select whenever it fills, and emits the segment's top-k (only those k are sorted);
 //   pass 2  CTA = row: the same selection over the segs*k candidates.
 // Rule (fixed, unlike the reference's arrival-order ties): descending key, ties by ascending
 // column; a candidate must be > -MAX_VALUE; unused slots hold (-MAX_VALUE, 0) (E/NNTypes.h:49).
@@ -64,6 +64,78 @@ __device__ void block_sort(float* sKey, uint32_t* sPos, uint32_t* sVal, uint32_t
     }
 }
 
+// Keeps the k best of sKey/sPos/sVal[0..n) (k < n <= kKCap) in slots [0, k), unsorted, and returns the k-th best key.
+// An O(n) radix select instead of sorting the whole buffer (the bitonic network over 4,096 entries costs ~30k
+// instructions per thread and ran ~3 times per 512 KB tile -- it, not the streaming, bounded the kernel): the order
+// "key descending, position ascending" is the descending order of the 64-bit composite (sortable key bits, ~position),
+// whose k-th largest value is found byte by byte from the top with a 256-bin shared histogram; the entries at or above
+// it that sit beyond slot k then move into the holes left below slot k.
+__device__ __forceinline__ unsigned long long composite(float key, uint32_t pos)
+{
+    uint32_t u = __float_as_uint(key);
+    u = (u & 0x80000000u) ? ~u : (u | 0x80000000u);
+    return ((unsigned long long)u << 32) | (unsigned long long)(0xFFFFFFFFu - pos);
+}
+
+__device__ float block_select(float* sKey, uint32_t* sPos, uint32_t* sVal, uint32_t n, uint32_t k, bool hasVal, uint32_t* sHist /*256 + 4*/,
+                              uint32_t* sMove /*2 * k*/)
+{
+    const uint32_t tid = threadIdx.x;
+    unsigned long long prefix = 0, maskHigh = 0;
+    uint32_t want = k;
+    for (int b = 7; b >= 0; b--) {
+        for (uint32_t i = tid; i < 256; i += kKThreads) sHist[i] = 0;
+        __syncthreads();
+        for (uint32_t i = tid; i < n; i += kKThreads) {
+            const unsigned long long c = composite(sKey[i], sPos[i]);
+            if ((c & maskHigh) == prefix) atomicAdd(&sHist[(uint32_t)(c >> (8 * b)) & 255u], 1u);
+        }
+        __syncthreads();
+        if (tid < 32) {
+            // lane l owns digits 255 - 8l .. 248 - 8l (descending); find the digit where the running count reaches `want`
+            uint32_t local[8], sum = 0;
+#pragma unroll
+            for (int q = 0; q < 8; q++) { local[q] = sHist[255 - (tid * 8 + q)]; sum += local[q]; }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t nb = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= (uint32_t)o) incl += nb; }
+            const uint32_t excl = incl - sum;
+            if (excl < want && want <= incl) {
+                uint32_t run = excl;
+#pragma unroll
+                for (int q = 0; q < 8; q++) {
+                    if (run < want && want <= run + local[q]) { sHist[256] = 255 - (tid * 8 + q); sHist[257] = want - run; }
+                    run += local[q];
+                }
+            }
+        }
+        __syncthreads();
+        prefix |= (unsigned long long)sHist[256] << (8 * b);
+        maskHigh |= 0xFFull << (8 * b);
+        want = sHist[257];
+        __syncthreads();
+    }
+    // prefix = the k-th best composite; exactly k entries are >= prefix
+    if (tid == 0) { sHist[258] = 0; sHist[259] = 0; }
+    __syncthreads();
+    for (uint32_t i = tid; i < n; i += kKThreads) {
+        const bool keep = composite(sKey[i], sPos[i]) >= prefix;
+        if (i < k && !keep) sMove[atomicAdd(&sHist[258], 1u)] = i;             // hole
+        if (i >= k && keep) sMove[k + atomicAdd(&sHist[259], 1u)] = i;         // mover
+    }
+    __syncthreads();
+    const uint32_t moves = sHist[258];                                          // == sHist[259]
+    for (uint32_t j = tid; j < moves; j += kKThreads) {
+        const uint32_t dst = sMove[j], src = sMove[k + j];
+        sKey[dst] = sKey[src]; sPos[dst] = sPos[src];
+        if (hasVal) sVal[dst] = sVal[src];
+    }
+    __syncthreads();
+    uint32_t u = (uint32_t)(prefix >> 32);
+    u = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
+    return __uint_as_float(u);
+}
+
 template <bool HAS_VALUE, bool HAS_FILTER>
 __global__ void __launch_bounds__(kKThreads)
 topk_kernel(const KArgs a)
@@ -72,7 +144,9 @@ topk_kernel(const KArgs a)
     float*    sKey = reinterpret_cast<float*>(smemRaw);
     uint32_t* sPos = reinterpret_cast<uint32_t*>(sKey + kKCap);
     uint32_t* sVal = sPos + kKCap;                                    // only when HAS_VALUE
-    uint32_t* sBits = HAS_VALUE ? sVal + kKCap : sVal;                // only when HAS_FILTER
+    uint32_t* sHist = HAS_VALUE ? sVal + kKCap : sVal;                // 260 words: radix-select histogram + scratch
+    uint32_t* sMove = sHist + 260;                                    // 2 * k words
+    uint32_t* sBits = sMove + 2 * a.k;                                // only when HAS_FILTER
     __shared__ uint32_t sCount;
     __shared__ float sThr;
 
@@ -99,53 +173,68 @@ topk_kernel(const KArgs a)
         // element i of the row is 16-byte aligned in global memory iff (rowBase + i) % 4 == 0
         const uint32_t mis = (uint32_t)((((uintptr_t)row) >> 2) & 3);
         uint32_t budget = kKCap;                                       // free slots guaranteed before next check
-        for (uint32_t base = c0; base < c1; base += kKChunk) {
-            if (budget < kKChunk) {
-                __syncthreads();
-                const uint32_t n = sCount;
-                if (n > kKCap - kKChunk) {
-                    block_sort(sKey, sPos, sVal, n, HAS_VALUE);
-                    if (tid == 0) { sCount = min(n, a.k); if (n >= a.k) sThr = sKey[a.k - 1]; }
+        constexpr int kDepth = 4;                                      // chunks whose loads are issued together
+        for (uint32_t base0 = c0; base0 < c1; base0 += kDepth * kKChunk) {
+            // issue the loads of up to four chunks first: four independent 128-bit loads in flight per thread
+            float kx[kDepth][4];
+#pragma unroll
+            for (int d = 0; d < kDepth; d++) {
+                const uint32_t p = base0 + d * kKChunk + tid * 4;
+                if (p + 3 < c1 && ((p + mis) & 3) == 0) {
+                    const float4 x = ldg_cs_f4(reinterpret_cast<const float4*>(row + p));
+                    kx[d][0] = x.x; kx[d][1] = x.y; kx[d][2] = x.z; kx[d][3] = x.w;
+                } else {
+#pragma unroll
+                    for (int v = 0; v < 4; v++) kx[d][v] = (p + v < c1) ? __ldg(row + p + v) : -INFINITY;
+                }
+            }
+#pragma unroll
+            for (int d = 0; d < kDepth; d++) {
+                const uint32_t base = base0 + d * kKChunk;
+                if (base >= c1) break;
+                if (budget < kKChunk) {
+                    __syncthreads();
+                    const uint32_t n = sCount;
+                    if (n > kKCap - kKChunk) {                        // n > k here: cut back to the k best, new threshold = k-th key
+                        const float kth = block_select(sKey, sPos, sVal, n, a.k, HAS_VALUE, sHist, sMove);
+                        if (tid == 0) { sCount = a.k; sThr = kth; }
+                        __syncthreads();
+                    }
+                    budget = kKCap - sCount;
                     __syncthreads();
                 }
-                budget = kKCap - sCount;
-                __syncthreads();
-            }
-            budget -= kKChunk;
-            const float thr = sThr;
-            const uint32_t p = base + tid * 4;
-            float kx[4];
-            if (p + 3 < c1 && ((p + mis) & 3) == 0) {
-                const float4 x = ldg_cs_f4(reinterpret_cast<const float4*>(row + p));
-                kx[0] = x.x; kx[1] = x.y; kx[2] = x.z; kx[3] = x.w;
-            } else {
+                budget -= kKChunk;
+                const float thr = sThr;
+                const uint32_t p = base + tid * 4;
+                if (HAS_FILTER && p < c1) {
+                    // c0 and p are multiples of 4: the four exclusion bits of this float4 sit in one bitmap word
+                    const uint32_t r = p - c0;
+                    const uint32_t bits = (sBits[r >> 5] >> (r & 31)) & 0xFu;
+                    if (bits) {
 #pragma unroll
-                for (int v = 0; v < 4; v++) kx[v] = (p + v < c1) ? __ldg(row + p + v) : -INFINITY;
-            }
-            uint32_t mask = 0;
-#pragma unroll
-            for (int v = 0; v < 4; v++) {
-                if (HAS_FILTER && p + v < c1) {
-                    const uint32_t r = p + v - c0;
-                    if ((sBits[r >> 5] >> (r & 31)) & 1u) kx[v] *= 0.0f;          // U/Filters.cpp:49-67: score *= 0
+                        for (int v = 0; v < 4; v++)
+                            if ((bits >> v) & 1u) kx[d][v] *= 0.0f;                       // U/Filters.cpp:49-67: score *= 0
+                    }
                 }
-                if (p + v < c1 && kx[v] > thr) mask |= 1u << v;
-            }
-            // warp-aggregated append
-            const uint32_t cnt = __popc(mask);
-            uint32_t incl = cnt;
+                uint32_t mask = 0;
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) { const uint32_t nb = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += nb; }
-            const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
-            uint32_t wbase = 0;
-            if (total) {
+                for (int v = 0; v < 4; v++)
+                    if (p + v < c1 && kx[d][v] > thr) mask |= 1u << v;
+                if (!__any_sync(0xffffffffu, mask != 0)) continue;       // common case once the threshold has settled
+                // warp-aggregated append
+                const uint32_t cnt = __popc(mask);
+                uint32_t incl = cnt;
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t nb = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += nb; }
+                const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                uint32_t wbase = 0;
                 if (lane == 31) wbase = atomicAdd(&sCount, total);
                 wbase = __shfl_sync(0xffffffffu, wbase, 31);
                 uint32_t o = wbase + incl - cnt;
 #pragma unroll
                 for (int v = 0; v < 4; v++) {
                     if (mask & (1u << v)) {
-                        sKey[o] = kx[v]; sPos[o] = p + v;
+                        sKey[o] = kx[d][v]; sPos[o] = p + v;
                         if (HAS_VALUE) sVal[o] = __ldg(vrow + p + v);
                         o++;
                     }
@@ -153,8 +242,9 @@ topk_kernel(const KArgs a)
             }
         }
         __syncthreads();
-        const uint32_t n = sCount;
-        block_sort(sKey, sPos, sVal, n, HAS_VALUE);
+        uint32_t n = sCount;
+        if (n > a.k) { block_select(sKey, sPos, sVal, n, a.k, HAS_VALUE, sHist, sMove); n = a.k; }
+        block_sort(sKey, sPos, sVal, n, HAS_VALUE);                       // <= k (<= 1,024) entries
         float* ok = a.outKey + ((size_t)b * a.segs + seg) * a.k;
         uint32_t* ov = a.outValue + ((size_t)b * a.segs + seg) * a.k;
         for (uint32_t i = tid; i < a.k; i += kKThreads) {
@@ -199,7 +289,7 @@ static int topk_impl(dsb200_ctx* ctx, const float* key, const uint32_t* value, u
     }
     a.outKey = candKey; a.outValue = candVal;
     const bool hasVal = value != nullptr, hasFilter = fs != nullptr;
-    size_t smem = (size_t)kKCap * 8 + (hasVal ? (size_t)kKCap * 4 : 0) + (hasFilter ? (size_t)(segLen / 32 + 1) * 4 : 0);
+    size_t smem = (size_t)kKCap * 8 + (hasVal ? (size_t)kKCap * 4 : 0) + (260 + 2 * (size_t)k) * 4 + (hasFilter ? (size_t)(segLen / 32 + 1) * 4 : 0);
     uint64_t grid = (uint64_t)batch * segs;
     const uint64_t cap = (uint64_t)ctx->numSMs * 6;
     if (grid > cap) grid = cap;
@@ -217,7 +307,7 @@ static int topk_impl(dsb200_ctx* ctx, const float* key, const uint32_t* value, u
         m.key = candKey; m.value = candVal; m.batch = batch; m.width = segs * k; m.k = k; m.segs = 1;
         m.segLen = ((segs * k + kKChunk - 1) / kKChunk) * kKChunk;
         m.outKey = outKey; m.outValue = outValue;
-        smem = (size_t)kKCap * 12;
+        smem = (size_t)kKCap * 12 + (260 + 2 * (size_t)k) * 4;
         grid = batch; if (grid > cap) grid = cap;
         DSB_CUDA_OK(cudaFuncSetAttribute(topk_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
         topk_kernel<true, false><<<(unsigned)grid, kKThreads, smem, ctx->stream>>>(m);

@@ -37,7 +37,7 @@ NNLayer::NNLayer(NNLayerDescriptor& d, uint32_t batch)
       _bSparse(d._attributes & NNLayer::Attributes::Sparse), _bFastSparse(false), _sparsenessPenalty_p(d._sparsenessPenalty_p),
       _sparsenessPenalty_beta(d._sparsenessPenalty_beta), _bDenoising(d._attributes & NNLayer::Attributes::Denoising),
       _weightNorm(d._weightNorm), _deltaNorm(d._deltaNorm), _parallelization(Serial), _bDirty(true), _bActivationPending(false),
-      _bDeltaReady(false), _priority(-1), _dropoutCalls(0)
+      _bDeltaReady(false), _bUnitsArePreActivation(false), _preActivationBatch(0), _priority(-1), _dropoutCalls(0)
 {
     if (_type != FullyConnected) throw DsbEngineError("NNLayer: layer " + _name + ": only FullyConnected layers are on the dsstne_b200 hot path");
     if (_attributes & BatchNormalization) throw DsbEngineError("NNLayer: layer " + _name + ": batch normalisation is outside the hot path");
@@ -156,8 +156,16 @@ void NNLayer::CalculateDropout(uint32_t batch)
                                   _ELUAlpha, _SELULambda, (uint64_t)getGpu()._seed, stream), "dsb200_dropout");
 }
 
+void NNLayer::MaterializeUnits()
+{
+    if (!_bUnitsArePreActivation) return;
+    _bUnitsArePreActivation = false;
+    CalculateActivation(_preActivationBatch);
+}
+
 void NNLayer::ForwardPropagateFullyConnected(uint32_t position, uint32_t batch, bool bTraining)
 {
+    _bUnitsArePreActivation = false;                 // the unit buffer is about to be rewritten
     dsb200_ctx* ctx = getGpu()._ctx;
     NNNetwork* net = getGpu()._pNetwork;
     const bool deferActivation = bTraining && net && FusedOutputEligible(net->GetErrorFunction());
@@ -285,7 +293,11 @@ bool NNLayer::CalculateErrorAsync(uint32_t position, uint32_t batch, ErrorFuncti
     if (_bActivationPending) {
         // ONE pass: a = f(z) in place, loss into the accumulator, delta written -- replaces kCalculate*Activation,
         // the Raw + NonZero error kernels and the Raw + NonZero delta kernels (six passes over [batch][N])
-        _pDataSet->CalculateFusedOutput(ef, _activation, position, batch, _localStride, GetUnitBuffer(), GetIncomingDeltaBuffer(), pDevAccumulator);
+        // training only needs the delta of a sparse-target output layer: the activations are not stored (a third of this
+        // pass's HBM traffic); anyone who reads the units afterwards gets them materialised first (MaterializeUnits)
+        _pDataSet->CalculateFusedOutput(ef, _activation, position, batch, _localStride, GetUnitBuffer(), GetIncomingDeltaBuffer(), pDevAccumulator, false);
+        _bUnitsArePreActivation = true;
+        _preActivationBatch = batch;
         _bActivationPending = false;
         _bDeltaReady = true;
         return true;
@@ -444,11 +456,12 @@ void NNLayer::Gather(uint32_t batch, uint32_t stride, NNFloat* pBuffer, uint32_t
 bool NNLayer::GetUnits(vector<NNFloat>& vUnit)
 {
     if (!_pbUnit) return false;
+    MaterializeUnits();
     vUnit.resize(_pbUnit->_length);
     _pbUnit->Download(vUnit.data());
     return true;
 }
-bool NNLayer::GetUnits(NNFloat* pUnit) { if (!_pbUnit) return false; _pbUnit->Download(pUnit); return true; }
+bool NNLayer::GetUnits(NNFloat* pUnit) { if (!_pbUnit) return false; MaterializeUnits(); _pbUnit->Download(pUnit); return true; }
 bool NNLayer::SetUnits(const vector<NNFloat>& vUnit)
 {
     if (!_pbUnit || vUnit.size() < _pbUnit->_length) return false;

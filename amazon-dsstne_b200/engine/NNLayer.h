@@ -51,6 +51,8 @@ private:
     // B200 fusion state
     bool                    _bActivationPending;  // unit buffer holds Z; the fused output pass will apply f(), loss, delta
     bool                    _bDeltaReady;         // output delta already produced by the fused pass
+    bool                    _bUnitsArePreActivation;  // the fused output pass did not store a = f(z): the unit buffer still holds z
+    uint32_t                _preActivationBatch;
 
     vector<NNLayer*>        _vIncomingLayer;
     vector<NNWeight*>       _vIncomingWeight;
@@ -91,6 +93,7 @@ private:
     void Gather(uint32_t batch, uint32_t stride, NNFloat* pBuffer, uint32_t localStride);
     void ClearUpdates();
     bool FusedOutputEligible(ErrorFunction ef) const;
+    void MaterializeUnits();                              // apply the activation now if the fused training pass skipped storing it
     NNFloat* GetIncomingUnitBuffer() { return _pbUnit ? _pbUnit->_pDevData : NULL; }
     NNFloat* GetUnitBuffer() { return _pbUnit ? _pbUnit->_pDevData : NULL; }
     NNFloat* GetIncomingDeltaBuffer() { return _pbDelta ? _pbDelta->_pDevData : NULL; }

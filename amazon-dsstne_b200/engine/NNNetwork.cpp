@@ -249,7 +249,12 @@ NNWeight* NNNetwork::GetWeight(const string& inputLayer, const string& outputLay
 }
 
 uint64_t NNNetwork::GetBufferSize(const string& layer) const { NNLayer* l = GetLayer(layer); return l ? l->GetBufferSize() : 0; }
-NNFloat* NNNetwork::GetUnitBuffer(const string& layer) { NNLayer* l = GetLayer(layer); return l ? l->GetUnitBuffer() : NULL; }
+NNFloat* NNNetwork::GetUnitBuffer(const string& layer)
+{
+    NNLayer* l = GetLayer(layer);
+    if (l) l->MaterializeUnits();
+    return l ? l->GetUnitBuffer() : NULL;
+}
 NNFloat* NNNetwork::GetDeltaBuffer(const string& layer) { NNLayer* l = GetLayer(layer); return l ? l->GetDeltaBuffer() : NULL; }
 NNFloat* NNNetwork::GetWeightBuffer(const string& inputLayer, const string& outputLayer)
 {
@@ -604,6 +609,7 @@ void NNNetwork::CalculateTopKFiltered(const string& layer, uint32_t k, NNDataSet
 {
     NNLayer* pLayer = GetLayer(layer);
     if (!pLayer) { if (getGpu()._id == 0) printf("NNNetwork::CalculateTopK: Unknown layer %s.\n", layer.c_str()); return; }
+    pLayer->MaterializeUnits();
     uint32_t batch = _batch;
     if (_position + batch > _examples) batch = _examples - _position;
     if (!pbKey || !pbValue || pbKey->_length < (size_t)batch * k || pbValue->_length < (size_t)batch * k)

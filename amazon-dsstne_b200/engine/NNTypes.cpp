@@ -509,10 +509,11 @@ bool NNDataSet<T>::CalculateErrorAsync(ErrorFunction ef, Activation activation, 
 
 template <typename T>
 bool NNDataSet<T>::CalculateFusedOutput(ErrorFunction ef, Activation activation, uint32_t position, uint32_t batch, uint32_t stride,
-                                        NNFloat* pUnit, NNFloat* pDelta, unsigned long long* pDevAccumulator)
+                                        NNFloat* pUnit, NNFloat* pDelta, unsigned long long* pDevAccumulator, bool writeUnits)
 {
     dsb200_sparse v = View();
-    getGpu().Check(dsb200_output_pass(getGpu()._ctx, &v, (int)ef, (int)activation, position, batch, stride, pUnit, pUnit, pDelta, pDevAccumulator),
+    getGpu().Check(dsb200_output_pass(getGpu()._ctx, &v, (int)ef, (int)activation, position, batch, stride, pUnit, writeUnits ? pUnit : NULL, pDelta,
+                                      pDevAccumulator),
                    "dsb200_output_pass");
     return true;
 }

@@ -173,8 +173,9 @@ struct NNDataSetBase {
     // device view of this dataset for the C ABI
     virtual dsb200_sparse View() = 0;
     // fused activation + loss + delta for a sparse-target output layer (dsb200_output_pass)
+    // writeUnits == false: the activations are not stored (training needs only the delta); pUnit keeps Z
     virtual bool CalculateFusedOutput(ErrorFunction ef, Activation activation, uint32_t position, uint32_t batch, uint32_t stride,
-                                      NNFloat* pUnit, NNFloat* pDelta, unsigned long long* pDevAccumulator) = 0;
+                                      NNFloat* pUnit, NNFloat* pDelta, unsigned long long* pDevAccumulator, bool writeUnits = true) = 0;
     // asynchronous loss (fixed-point accumulate on the device, no host sync)
     virtual bool CalculateErrorAsync(ErrorFunction ef, Activation activation, uint32_t position, uint32_t batch, uint32_t stride,
                                      NNFloat* pUnit, unsigned long long* pDevAccumulator) = 0;
@@ -232,7 +233,7 @@ public:
 
     dsb200_sparse View();
     bool CalculateFusedOutput(ErrorFunction ef, Activation activation, uint32_t position, uint32_t batch, uint32_t stride,
-                              NNFloat* pUnit, NNFloat* pDelta, unsigned long long* pDevAccumulator);
+                              NNFloat* pUnit, NNFloat* pDelta, unsigned long long* pDevAccumulator, bool writeUnits = true);
     bool CalculateErrorAsync(ErrorFunction ef, Activation activation, uint32_t position, uint32_t batch, uint32_t stride,
                              NNFloat* pUnit, unsigned long long* pDevAccumulator);
     bool CalculateSparseZBiasActivation(uint32_t position, uint32_t batch, uint32_t stride, NNFloat* pWeight, NNFloat* pBias,

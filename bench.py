@@ -106,8 +106,8 @@ def algorithmic_bytes(wl, nnz_batch, P=1):
         # gathered delta rows + W read/write (fused SGD: no dW) + TIndex + start/end
         "sparse_wgrad_update": 4 * S * nnz_batch + 2 * 4 * S * N + 4 * nnz_batch + 8 * N,
         "sparse_wgrad": 4 * S * nnz_batch + 4 * S * N + 4 * nnz_batch + 8 * N,
-        # read Z, write unit (in place), write delta + target CSR
-        "output_pass": 3 * 4 * B * N + 4 * nnz_batch + 16 * B,
+        # read Z, write delta + target CSR (the activations are not stored during training)
+        "output_pass": 2 * 4 * B * N + 4 * nnz_batch + 16 * B,
         # read g, read w, write w
         "update_weights": 3 * 4 * wl["hidden"][-1] * N,
         # delta read (dominated by the output layer) + bias r/w

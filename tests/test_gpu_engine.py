@@ -87,6 +87,9 @@ def test_config1_train_steps_match_oracle(eng, orc, mode):
     # implementations that sum the dense GEMMs in a different order (cuBLAS vs the oracle's loops) legitimately differ
     # by more than 1e-5 after a few steps.  With identical gradients the kernels agree to 1e-5 for every mode
     # (test_gpu_kernels.py::test_update_weights_and_biases, ::test_sparse_wgrad_update_fused_equals_unfused).
+    # the fused training pass does not store the output activations (only the delta is needed); reading them afterwards
+    # must still give a = f(z) of the last forward pass (NNLayer::MaterializeUnits)
+    assert rel_err(net.get_units("Output").reshape(batch, 2048), onet.unit(2, batch)) < TOL
     tol = {orc.ADAGRAD: 2e-4, orc.RMSPROP: 2e-4, orc.ADAM: 2e-3}.get(mode, TOL)
     for i in range(2):
         W, b = net.get_weights(names[i], names[i + 1])
