@@ -39,7 +39,9 @@ struct OArgs {
 // path's value ranges, well inside the 1e-5 parity bound) which take the pass from instruction-bound to HBM-bound
 __device__ __forceinline__ float dexp(float x, int fast) { return fast ? __expf(x) : expf(x); }
 __device__ __forceinline__ float dlog(float x, int fast) { return fast ? __logf(x) : logf(x); }
-__device__ __forceinline__ float drcp(float x, int fast) { return fast ? __frcp_rn(x) : 1.0f / x; }
+// MUFU.RCP (1 ulp): __frcp_rn would expand to a correctly-rounded Newton sequence of ~10 instructions
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float drcp(float x, int fast) { return fast ? rcp_approx(x) : 1.0f / x; }
 
 __device__ __forceinline__ float act_forward(int act, float z, float slope, float alpha, float lambda, int fast)
 {
@@ -236,7 +238,7 @@ constexpr int kRowThreads = 512;
 template <int EF, bool FAST>
 __device__ __forceinline__ float raw_sigmoid(const OArgs& a, float z, float wd, float wz, float& loss, float& d)
 {
-    const float x = FAST ? __frcp_rn(1.0f + __expf(-z)) : 1.0f / (1.0f + expf(-z));
+    const float x = FAST ? rcp_approx(1.0f + __expf(-z)) : 1.0f / (1.0f + expf(-z));
     if (EF == DSB200_ERR_SMCE) {                                          // wz = SMCE_zeroScale * wd
         const float lg = FAST ? __logf(fmaxf(kMinError, 1.0f - x)) : logf(fmaxf(kMinError, 1.0f - x));
         const bool on = x > a.P.SMCE_zeroTarget;
