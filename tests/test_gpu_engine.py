@@ -127,6 +127,30 @@ def test_three_hidden_layers_with_penalty(eng, orc, error, gemm_mode, tol):
         net.close()
 
 
+@pytest.mark.parametrize("gemm_mode,tol", [(0, TOL), (2, 3e-5)], ids=["fp32", "tf32x3"])
+def test_wide_hidden_layers_like_config4(eng, orc, gemm_mode, tol):
+    """BASELINE config 4 in miniature: 1,024-wide hidden layers (sparse-Z / sparse gradient with an 8-block column loop,
+    dense layers large enough for the tcgen05 kernels with their fused bias + activation epilogue)."""
+    sizes, batch = [4096, 1024, 1024, 4096], 256
+    h = tiny(examples=512, width=4096, mean=40.0)
+    net, onet, names, _ = build_pair(eng, orc, sizes, h, batch, orc.MOMENTUM)
+    net.set_gemm_mode(gemm_mode)
+    oc = to_oracle(orc, h)
+    onet.set_input(oc, batch)
+    try:
+        for pos in (0, 256):
+            got = net.train_step(pos, 0.01, 1e-4, 0.0, 0.5, 0.0)
+            want, _ = onet.train_step(oc, oc, pos, batch, 0.01, 1e-4, 0.0, 0.5, 0.0)
+            assert abs(got - want) <= tol * abs(want)
+        for i in range(3):
+            W, b = net.get_weights(names[i], names[i + 1])
+            assert rel_err(W.reshape(onet.W(i).shape), onet.W(i)) < tol
+            assert rel_err(b, onet.b(i)) < max(tol, 5e-5)
+    finally:
+        net.set_gemm_mode(0)
+        net.close()
+
+
 def test_fused_and_unfused_engine_agree(eng, orc):
     sizes, batch = [2048, 128, 2048], 256
     h = tiny(examples=256, width=2048)
