@@ -56,10 +56,10 @@ extern "C" {
 
 int dsb200_gemm_fwd(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, const float* A, const float* W, float beta, float* C)
 {
-    DSB_PROFILE(ctx, "gemm_fwd");
     using namespace dsb;
     if (!ctx || !A || !W || !C) return fail(ctx, DSB200_EINVAL, "gemm_fwd: null argument");
     if (!B || !k || !n) return 0;
+    DSB_PROFILE(ctx, use_tc(ctx, B, n, k) ? "gemm_fwd_tc" : "gemm_fwd");
     if (use_tc(ctx, B, n, k)) return gemm_tc_launch(ctx, A, 0, k, W, 1, n, C, n, B, n, k, 1.0f, beta, nullptr, DSB200_ACT_LINEAR, 0.f, 0.f, 0.f);
     cublasHandle_t h; int rc = cublas_of(ctx, &h); if (rc) return rc;
     const float one = 1.0f;
@@ -71,10 +71,10 @@ int dsb200_gemm_fwd(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, const f
 
 int dsb200_gemm_dw(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, float alpha, const float* A, const float* D, float beta, float* G)
 {
-    DSB_PROFILE(ctx, "gemm_dw");
     using namespace dsb;
     if (!ctx || !A || !D || !G) return fail(ctx, DSB200_EINVAL, "gemm_dw: null argument");
     if (!B || !k || !n) return 0;
+    DSB_PROFILE(ctx, use_tc(ctx, k, n, B) ? "gemm_dw_tc" : "gemm_dw");
     if (use_tc(ctx, k, n, B)) return gemm_tc_launch(ctx, A, 1, k, D, 1, n, G, n, k, n, B, alpha, beta, nullptr, DSB200_ACT_LINEAR, 0.f, 0.f, 0.f);
     cublasHandle_t h; int rc = cublas_of(ctx, &h); if (rc) return rc;
     // G^T (n x k) = D^T (n x B) * A (B x k)   (E/NNLayer.cpp:2223-2236)
@@ -85,10 +85,10 @@ int dsb200_gemm_dw(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, float al
 
 int dsb200_gemm_dx(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, const float* D, const float* W, float beta, float* Dp)
 {
-    DSB_PROFILE(ctx, "gemm_dx");
     using namespace dsb;
     if (!ctx || !D || !W || !Dp) return fail(ctx, DSB200_EINVAL, "gemm_dx: null argument");
     if (!B || !k || !n) return 0;
+    DSB_PROFILE(ctx, use_tc(ctx, B, k, n) ? "gemm_dx_tc" : "gemm_dx");
     if (use_tc(ctx, B, k, n)) return gemm_tc_launch(ctx, D, 0, n, W, 0, n, Dp, k, B, k, n, 1.0f, beta, nullptr, DSB200_ACT_LINEAR, 0.f, 0.f, 0.f);
     cublasHandle_t h; int rc = cublas_of(ctx, &h); if (rc) return rc;
     const float one = 1.0f;
@@ -107,7 +107,7 @@ int dsb200_gemm_fwd_bias_act(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n
     if (!ctx || !A || !W || !C || !pBias) return fail(ctx, DSB200_EINVAL, "gemm_fwd_bias_act: null argument");
     if (!B || !k || !n) return 0;
     if (use_tc(ctx, B, n, k) && activation != DSB200_ACT_SOFTMAX) {
-        DSB_PROFILE(ctx, "gemm_fwd_bias_act");
+        DSB_PROFILE(ctx, "gemm_fwd_bias_act_tc");
         return gemm_tc_launch(ctx, A, 0, k, W, 1, n, C, n, B, n, k, 1.0f, 0.0f, pBias, activation, slope, alpha, lambda);
     }
     int rc = dsb200_clear_unit(ctx, C, pBias, n, B);

@@ -113,8 +113,23 @@ template <typename T>
 void NNDataSet<T>::LoadSparseData(const uint64_t* srcSparseStart, const uint64_t* srcSparseEnd, const void* srcSparseData,
                                   const uint32_t* srcSparseIndex)
 {
+    if (_sharding == NNDataSetEnums::Model && getGpu()._numprocs > 1) {
+        // model parallel: every rank receives the full batch, keeps it as the un-sharded host copy and re-slices its columns
+        if (srcSparseStart[0] != 0) throw std::runtime_error("Sparse data should be zero indexed; srcSparseStart[0] != 0");
+        const uint64_t dataLength = srcSparseEnd[_uniqueExamples - 1];
+        if (dataLength > _sparseDataSize) {
+            stringstream msg; msg << "Not enough space to store sparse data. Allocated: " << _sparseDataSize << " Required: " << dataLength;
+            throw std::length_error(msg.str());
+        }
+        _vFullSparseStart.assign(srcSparseStart, srcSparseStart + _uniqueExamples);
+        _vFullSparseEnd.assign(srcSparseEnd, srcSparseEnd + _uniqueExamples);
+        _vFullSparseIndex.assign(srcSparseIndex, srcSparseIndex + dataLength);
+        if (srcSparseData) { const T* typed = static_cast<const T*>(srcSparseData); _vFullSparseData.assign(typed, typed + dataLength); }
+        else _attributes |= NNDataSetEnums::Boolean;
+        SliceFromFull();
+        return;
+    }
     CopySparseData(srcSparseStart, srcSparseEnd, srcSparseData, srcSparseIndex);
-    if (_sharding == NNDataSetEnums::Model && getGpu()._numprocs > 1) { UploadSparse(); return; }   // column shards are rebuilt on the host
     UploadSparseAsync(srcSparseStart, srcSparseEnd, srcSparseData, srcSparseIndex, srcSparseEnd[_uniqueExamples - 1]);
 }
 
@@ -216,8 +231,17 @@ bool NNDataSet<T>::Shard(NNDataSetEnums::Sharding sharding)
     _maxX = (uint32_t)(((size_t)_width * (r + 1)) / P);
     if (P == 1) { UploadSparse(); return true; }
     _vFullSparseStart = _vSparseStart; _vFullSparseEnd = _vSparseEnd; _vFullSparseIndex = _vSparseIndex; _vFullSparseData = _vSparseData;
+    SliceFromFull();
+    return true;
+}
+
+// local column slice [_minX, _maxX) of the full host copy, indices rebased to the shard, uploaded
+template <typename T>
+void NNDataSet<T>::SliceFromFull()
+{
     const bool analog = !(_attributes & NNDataSetEnums::Boolean);
     vector<uint32_t> idx; vector<T> dat;
+    _vSparseStart.resize(_uniqueExamples); _vSparseEnd.resize(_uniqueExamples);
     for (uint32_t j = 0; j < _uniqueExamples; j++) {
         const uint64_t s = _vFullSparseStart[j], e = _vFullSparseEnd[j];
         _vSparseStart[j] = idx.size();
@@ -229,11 +253,17 @@ bool NNDataSet<T>::Shard(NNDataSetEnums::Sharding sharding)
     }
     _vSparseIndex.swap(idx);
     if (analog) _vSparseData.swap(dat);
-    _pbSparseIndex.reset(new GpuBuffer<uint32_t>(_vSparseIndex.size()));
-    if (analog) _pbSparseData.reset(new GpuBuffer<T>(_vSparseData.size()));
-    UploadSparse();
+    if (!_pbSparseIndex || _pbSparseIndex->_length < _vSparseIndex.size()) _pbSparseIndex.reset(new GpuBuffer<uint32_t>(_vSparseIndex.size()));
+    if (analog && (!_pbSparseData || _pbSparseData->_length < _vSparseData.size())) _pbSparseData.reset(new GpuBuffer<T>(_vSparseData.size()));
+    // the device buffers may be longer than the shard: upload the used part
+    RTERROR(cudaMemcpyAsync(_pbSparseStart->_pDevData, _vSparseStart.data(), _uniqueExamples * sizeof(uint64_t), cudaMemcpyHostToDevice, getGpu().GetStream()), "NNDataSet shard upload");
+    RTERROR(cudaMemcpyAsync(_pbSparseEnd->_pDevData, _vSparseEnd.data(), _uniqueExamples * sizeof(uint64_t), cudaMemcpyHostToDevice, getGpu().GetStream()), "NNDataSet shard upload");
+    if (!_vSparseIndex.empty())
+        RTERROR(cudaMemcpyAsync(_pbSparseIndex->_pDevData, _vSparseIndex.data(), _vSparseIndex.size() * sizeof(uint32_t), cudaMemcpyHostToDevice, getGpu().GetStream()), "NNDataSet shard upload");
+    if (analog && !_vSparseData.empty())
+        RTERROR(cudaMemcpyAsync(_pbSparseData->_pDevData, _vSparseData.data(), _vSparseData.size() * sizeof(T), cudaMemcpyHostToDevice, getGpu().GetStream()), "NNDataSet shard upload");
+    RTERROR(cudaStreamSynchronize(getGpu().GetStream()), "NNDataSet shard upload sync");
     _bDirty = true;
-    return true;
 }
 
 template <typename T>

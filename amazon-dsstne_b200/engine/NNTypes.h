@@ -244,6 +244,7 @@ public:
 
 private:
     void UploadSparse();
+    void SliceFromFull();
     // streaming path of LoadSparseData: pinned double-buffered staging + asynchronous copies of the used part only
     void UploadSparseAsync(const uint64_t* srcStart, const uint64_t* srcEnd, const void* srcData, const uint32_t* srcIndex, uint64_t dataLength);
     struct Staging {

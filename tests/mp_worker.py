@@ -49,6 +49,17 @@ def main():
     hp = dict(alpha=0.025, lam=1e-4, lam1=0.0, mu=0.5, mu1=0.999)
     losses = [net.train_step((s % 2) * batch, hp["alpha"], hp["lam"], hp["lam1"], hp["mu"], hp["mu1"]) for s in range(steps)]
 
+    # streaming path while model parallel: every rank re-loads the whole dataset with its two halves exchanged
+    # (NNDataSet::LoadSparseData re-slices the rank's column shard) and runs one more step at position 0
+    lens = (h.end - h.start).astype(np.uint64)
+    order = np.concatenate([np.arange(batch, 2 * batch), np.arange(0, batch)])
+    s_end = np.cumsum(lens[order]).astype(np.uint64)
+    s_start = np.concatenate([[0], s_end[:-1]]).astype(np.uint64)
+    s_index = np.concatenate([h.index[int(h.start[r]):int(h.end[r])] for r in order]).astype(np.uint32)
+    ds_in.load_sparse(s_start, s_end, s_index)
+    ds_out.load_sparse(s_start, s_end, s_index)
+    stream_loss = net.train_step(0, hp["alpha"], hp["lam"], hp["lam1"], hp["mu"], hp["mu1"])
+
     # re-assemble the sharded weights on rank 0
     shards = []
     for i in range(len(sizes) - 1):
@@ -70,6 +81,7 @@ def main():
         onet.set_input(oc, batch)
         want_losses = [onet.train_step(oc, oc, (s % 2) * batch, batch, hp["alpha"], hp["lam"], hp["lam1"], hp["mu"], hp["mu1"])[0]
                        for s in range(steps)]
+        want_stream = onet.train_step(oc, oc, batch, batch, hp["alpha"], hp["lam"], hp["lam1"], hp["mu"], hp["mu1"])[0]   # the exchanged first half
         errs = {}
         for i in range(len(sizes) - 1):
             n_in, n_out = sizes[i], sizes[i + 1]
@@ -88,7 +100,8 @@ def main():
             errs[f"W{i}"] = rel_err(full, onet.W(i))
             errs[f"b{i}"] = rel_err(fullb, onet.b(i))
         out = {"world": world, "losses": losses, "want_losses": want_losses, "errs": errs,
-               "loss_err": max(abs(a - b) / abs(b) for a, b in zip(losses, want_losses))}
+               "loss_err": max(abs(a - b) / abs(b) for a, b in zip(losses, want_losses)),
+               "stream_loss_err": abs(stream_loss - want_stream) / abs(want_stream)}
     net.close()
     dist.barrier()
     dist.destroy_process_group()

@@ -30,6 +30,7 @@ def run_world(world, extra_env=None, port=29611):
 def test_model_parallel_sgd_matches_oracle(world):
     r = run_world(world, {"MP_MODE": "0"}, port=29611 + world)
     assert r["loss_err"] < 1e-5, r
+    assert r["stream_loss_err"] < 1e-5, r                     # LoadSparseData while model parallel (the e2e path of bench.py at N > 1)
     for k, v in r["errs"].items():
         assert v < (5e-5 if k.startswith("b") else 1e-5), (k, v, r)
 

@@ -58,8 +58,45 @@ def full(rep, out):
             w.writerow([short(r[idx["Kernel Name"]])] + [r[idx[c]] for c in cols])
 
 
+def traffic(rep, out):
+    """DRAM bytes (read + write) per launch of the kernels bench.py reports, keyed by bench.py's kernel names."""
+    import json
+    txt = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+    rd = list(csv.reader(io.StringIO(txt)))
+    hdr, units = rd[0], rd[1]
+    idx = {h: i for i, h in enumerate(hdr)}
+    scale = {"byte": 1.0, "Kbyte": 1e3, "Mbyte": 1e6, "Gbyte": 1e9}
+    per = collections.defaultdict(list)
+    for r in rd[2:]:
+        name = r[idx["Kernel Name"]]
+        b = float(r[idx["dram__bytes_read.sum"]]) * scale[units[idx["dram__bytes_read.sum"]]] + \
+            float(r[idx["dram__bytes_write.sum"]]) * scale[units[idx["dram__bytes_write.sum"]]]
+        key = None
+        if "output_row_kernel" in name or "output_tile_kernel" in name: key = "output_pass"
+        elif "sparse_z" in name: key = "sparse_z_bias_act"
+        elif "sparse_wgrad_light" in name: key = "sparse_wgrad_update:light"
+        elif "sparse_wgrad_heavy" in name: key = "sparse_wgrad_update:heavy"
+        elif "transpose_scatter" in name: key = "sparse_transpose"
+        elif "gemm_tc_kernel<0, 1>" in name or "gemm_tc_kernel<(bool)0, (bool)1>" in name: key = "gemm_fwd_bias_act_tc"
+        elif "gemm_tc_kernel<1, 1>" in name or "gemm_tc_kernel<(bool)1, (bool)1>" in name: key = "gemm_dw_tc"
+        elif "gemm_tc_kernel<0, 0>" in name or "gemm_tc_kernel<(bool)0, (bool)0>" in name: key = "gemm_dx_tc"
+        elif "update_biases" in name: key = "update_biases:max"
+        if key: per[key].append(b)
+    res = {}
+    for k, v in per.items():
+        if k.endswith(":max"): res[k[:-4]] = max(v)
+        else: res[k] = sum(v) / len(v)
+    if "sparse_wgrad_update:light" in res:
+        res["sparse_wgrad_update"] = res.pop("sparse_wgrad_update:light") + res.pop("sparse_wgrad_update:heavy", 0.0)
+    res = {k: int(v) for k, v in res.items()}
+    res["_source"] = f"ncu --set full --clock-control none, {rep.split('/')[-1]}, bench.py workload c2 on one B200; dram__bytes_read.sum + dram__bytes_write.sum per launch"
+    json.dump(res, open(out, "w"), indent=1, sort_keys=True)
+
+
 if __name__ == "__main__":
     if sys.argv[1] == "launches":
         launches(sys.argv[2], sys.argv[3], int(sys.argv[4]) if len(sys.argv) > 4 else 0)
+    elif sys.argv[1] == "traffic":
+        traffic(sys.argv[2], sys.argv[3])
     else:
         full(sys.argv[2], sys.argv[3])
