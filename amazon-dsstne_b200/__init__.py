@@ -213,6 +213,11 @@ class Context:
         self.check(lib().dsb200_gemm_fwd_bias_act(self.h, C.c_uint32(B), C.c_uint32(k), C.c_uint32(W.shape[1]), _ptr(A), _ptr(W),
                                                   _ptr(bias), C.c_int(act), _ptr(Cm), C.c_float(slope), C.c_float(alpha), C.c_float(lam)))
 
+    def gemm_dx_hadamard(self, D, W, act, unit, Dp, scale=1.0, slope=0.0, alpha=0.0, lam=0.0):
+        B, n = D.shape
+        self.check(lib().dsb200_gemm_dx_hadamard(self.h, C.c_uint32(B), C.c_uint32(W.shape[0]), C.c_uint32(n), _ptr(D), _ptr(W), C.c_int(act),
+                                                 C.c_float(scale), _ptr(unit), _ptr(Dp), C.c_float(slope), C.c_float(alpha), C.c_float(lam)))
+
     def gemm_dw(self, A, D, G, alpha, beta=0.0):
         B, k = A.shape
         self.check(lib().dsb200_gemm_dw(self.h, C.c_uint32(B), C.c_uint32(k), C.c_uint32(D.shape[1]), C.c_float(alpha),

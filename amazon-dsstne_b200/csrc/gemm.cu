@@ -38,6 +38,9 @@ int gemm_tc_launch(dsb200_ctx* ctx, const float* A, int aMN, uint32_t lda, const
 // The persistent tcgen05 kernel pays ~15 us of fixed latency (launch, TMEM allocation, pipeline fill, epilogue); a GEMM
 // that covers only a handful of 128 x 128 tiles (the 128 x 128 hidden weights of BASELINE config 2: 8 tiles) is
 // latency bound and stays on the plain library SGEMM, which is also the exact-fp32 path.  Option "gemm_tc_min_tiles".
+int dense_small_fwd(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, const float* A, const float* W, const float* bias, int act, float* C,
+                    float slope, float alpha, float lambda);
+
 static inline bool use_tc(const dsb200_ctx* ctx, uint64_t M, uint64_t N, uint64_t K)
 {
     if (ctx->gemmMode != DSB200_GEMM_TF32 && ctx->gemmMode != DSB200_GEMM_TF32X3) return false;
@@ -109,6 +112,10 @@ int dsb200_gemm_fwd_bias_act(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n
     if (use_tc(ctx, B, n, k) && activation != DSB200_ACT_SOFTMAX) {
         DSB_PROFILE(ctx, "gemm_fwd_bias_act_tc");
         return gemm_tc_launch(ctx, A, 0, k, W, 1, n, C, n, B, n, k, 1.0f, 0.0f, pBias, activation, slope, alpha, lambda);
+    }
+    if ((uint64_t)B * k * n <= (1ull << 27) && activation != DSB200_ACT_SOFTMAX && !ctx->noSmallDense) {
+        DSB_PROFILE(ctx, "gemm_fwd_bias_act_small");           // one SIMT launch instead of three (dense_small.cu)
+        return dense_small_fwd(ctx, B, k, n, A, W, pBias, activation, C, slope, alpha, lambda);
     }
     int rc = dsb200_clear_unit(ctx, C, pBias, n, B);
     if (!rc) rc = dsb200_gemm_fwd(ctx, B, k, n, A, W, 1.0f, C);

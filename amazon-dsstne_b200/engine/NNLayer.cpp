@@ -37,7 +37,7 @@ NNLayer::NNLayer(NNLayerDescriptor& d, uint32_t batch)
       _bSparse(d._attributes & NNLayer::Attributes::Sparse), _bFastSparse(false), _sparsenessPenalty_p(d._sparsenessPenalty_p),
       _sparsenessPenalty_beta(d._sparsenessPenalty_beta), _bDenoising(d._attributes & NNLayer::Attributes::Denoising),
       _weightNorm(d._weightNorm), _deltaNorm(d._deltaNorm), _parallelization(Serial), _bDirty(true), _bActivationPending(false),
-      _bDeltaReady(false), _bUnitsArePreActivation(false), _preActivationBatch(0), _priority(-1), _dropoutCalls(0)
+      _bDeltaReady(false), _bHadamardDone(false), _bUnitsArePreActivation(false), _preActivationBatch(0), _priority(-1), _dropoutCalls(0)
 {
     if (_type != FullyConnected) throw DsbEngineError("NNLayer: layer " + _name + ": only FullyConnected layers are on the dsstne_b200 hot path");
     if (_attributes & BatchNormalization) throw DsbEngineError("NNLayer: layer " + _name + ": batch normalisation is outside the hot path");
@@ -337,8 +337,10 @@ void NNLayer::BackPropagateFullyConnected(uint32_t position, uint32_t batch)
             getGpu().Check(dsb200_sparseness_penalty(ctx, batch, _localStride, GetUnitBuffer(), GetIncomingDeltaBuffer(), p, beta), "dsb200_sparseness_penalty");
         }
         const NNFloat scale = (NNFloat)1.0 / ((NNFloat)1.0 - _pDropout);
-        getGpu().Check(dsb200_hadamard(ctx, (int)_activation, (uint64_t)batch * _localStride, scale, GetUnitBuffer(), GetIncomingDeltaBuffer(),
-                                       _RELUSlope, _ELUAlpha, _SELULambda), "dsb200_hadamard");
+        if (_bHadamardDone) _bHadamardDone = false;              // applied by dsb200_gemm_dx_hadamard of the layer above
+        else
+            getGpu().Check(dsb200_hadamard(ctx, (int)_activation, (uint64_t)batch * _localStride, scale, GetUnitBuffer(), GetIncomingDeltaBuffer(),
+                                           _RELUSlope, _ELUAlpha, _SELULambda), "dsb200_hadamard");
         if (_deltaNorm > (NNFloat)0.0) throw DsbEngineError("NNLayer::BackPropagate: DeltaNorm is outside the hot path");
     };
 
@@ -366,8 +368,20 @@ void NNLayer::BackPropagateFullyConnected(uint32_t position, uint32_t batch)
             }
             if (in->_kind != Input) {
                 const NNFloat sgemm_beta = (in->_deltaUpdateCount == 0) ? (NNFloat)0.0 : (NNFloat)1.0;
-                getGpu().Check(dsb200_gemm_dx(ctx, batch, in->_localStride, _localStride, GetDeltaBuffer(), w->_pbWeight->_pDevData, sgemm_beta,
-                                              in->GetIncomingDeltaBuffer()), "dsb200_gemm_dx");
+                // small dense layer below with this layer as its only consumer, no sparseness penalty in between: the input
+                // delta and its Hadamard product with f'(x) in one launch (E/NNLayer.cpp:2274 + 2137)
+                const bool fuse = net->FusionEnabled() && in->_kind == Hidden && in->_vOutgoingLayer.size() == 1 && sgemm_beta == (NNFloat)0.0 &&
+                                  !(in->_bSparse && net->_bSparsenessPenalty) && in->_deltaNorm <= (NNFloat)0.0 &&
+                                  (uint64_t)batch * in->_localStride * _localStride <= (1ull << 27);
+                if (fuse) {
+                    getGpu().Check(dsb200_gemm_dx_hadamard(ctx, batch, in->_localStride, _localStride, GetDeltaBuffer(), w->_pbWeight->_pDevData,
+                                                           (int)in->_activation, (NNFloat)1.0 / ((NNFloat)1.0 - in->_pDropout), in->GetUnitBuffer(),
+                                                           in->GetIncomingDeltaBuffer(), in->_RELUSlope, in->_ELUAlpha, in->_SELULambda),
+                                   "dsb200_gemm_dx_hadamard");
+                    in->_bHadamardDone = true;
+                } else
+                    getGpu().Check(dsb200_gemm_dx(ctx, batch, in->_localStride, _localStride, GetDeltaBuffer(), w->_pbWeight->_pDevData, sgemm_beta,
+                                                  in->GetIncomingDeltaBuffer()), "dsb200_gemm_dx");
                 in->_deltaUpdateCount++;
             }
         }

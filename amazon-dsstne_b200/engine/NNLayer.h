@@ -51,6 +51,7 @@ private:
     // B200 fusion state
     bool                    _bActivationPending;  // unit buffer holds Z; the fused output pass will apply f(), loss, delta
     bool                    _bDeltaReady;         // output delta already produced by the fused pass
+    bool                    _bHadamardDone;       // f'(x) already applied by the fused input-delta kernel of the layer above
     bool                    _bUnitsArePreActivation;  // the fused output pass did not store a = f(z): the unit buffer still holds z
     uint32_t                _preActivationBatch;
 

@@ -204,6 +204,10 @@ int dsb200_hadamard(dsb200_ctx*, int activation, uint64_t size, float scale, con
 int dsb200_gemm_fwd(dsb200_ctx*, uint32_t B, uint32_t k, uint32_t n, const float* A, const float* W, float beta, float* C);
 int dsb200_gemm_dw(dsb200_ctx*, uint32_t B, uint32_t k, uint32_t n, float alpha, const float* A, const float* D, float beta, float* G);
 int dsb200_gemm_dx(dsb200_ctx*, uint32_t B, uint32_t k, uint32_t n, const float* D, const float* W, float beta, float* Dp);
+/* fused input delta of a SMALL dense layer: Dp = (D * W^T) (.) f'(pUnit) * scale -- cublasSgemm (E/NNLayer.cpp:2274) +
+ * kCalculateHadamardProduct of the layer below (E/NNLayer.cpp:2137) in one SIMT launch (csrc/dense_small.cu)            */
+int dsb200_gemm_dx_hadamard(dsb200_ctx*, uint32_t B, uint32_t k, uint32_t n, const float* D, const float* W, int activation, float scale,
+                            const float* pUnit, float* Dp, float slope, float alpha, float lambda);
 /* fused dense forward C = act(A*W + bias): kClearUnit + cublasSgemm(beta=1) + activation (E/NNLayer.cpp:1009,1073,1157) */
 int dsb200_gemm_fwd_bias_act(dsb200_ctx*, uint32_t B, uint32_t k, uint32_t n, const float* A, const float* W, const float* pBias,
                              int activation, float* C, float slope, float alpha, float lambda);

@@ -76,6 +76,29 @@ def test_fused_bias_activation_forward(ctx, orc, mode, act):
     assert rel_err(C.cpu().numpy(), want) < BOUND[mode]
 
 
+@pytest.mark.parametrize("act", [0, 1, 2, 3, 10, 11, 12], ids=["sigmoid", "tanh", "relu", "linear", "elu", "lrelu", "selu"])
+@pytest.mark.parametrize("B,k,n", [(1024, 128, 128), (100, 70, 33), (256, 64, 200)])
+def test_small_dense_fused_kernels(ctx, orc, act, B, k, n):
+    """csrc/dense_small.cu: forward bias + GEMM + activation and input delta + Hadamard product, one SIMT launch each, against
+    the oracle's separate steps (exact fp32: 1e-5)."""
+    g = torch.Generator(device="cuda").manual_seed(B + act)
+    A = torch.randn(B, k, device="cuda", generator=g)
+    W = torch.randn(k, n, device="cuda", generator=g) * 0.1
+    bias = torch.randn(n, device="cuda", generator=g)
+    D = torch.randn(B, n, device="cuda", generator=g) * 0.1
+    C = torch.empty(B, n, device="cuda")
+    ctx.gemm_fwd_bias_act(A, W, bias, act, C, 0.01, 1.6733, 1.0507)
+    unit = torch.rand(B, k, device="cuda", generator=g) * 2 - 0.5                # activation values of the layer below
+    Dp = torch.empty(B, k, device="cuda")
+    ctx.gemm_dx_hadamard(D, W, act, unit, Dp, 2.0, 0.01, 1.6733, 1.0507)
+    ctx.sync()
+    z = (ref64(A) @ ref64(W) + ref64(bias)[None, :]).astype(np.float32)
+    assert rel_err(C.cpu().numpy(), orc.activation(act, np.ascontiguousarray(z), 0.01, 1.6733, 1.0507)) < 1e-5
+    dx = (ref64(D) @ ref64(W).T).astype(np.float32)
+    want = orc.hadamard(act, unit.cpu().numpy(), np.ascontiguousarray(dx), 2.0, 0.01, 1.6733, 1.0507)
+    assert rel_err(Dp.cpu().numpy(), want) < 1e-5
+
+
 def test_tensor_core_gemm_is_deterministic(ctx):
     B, k, n = 1024, 128, 27278
     g = torch.Generator(device="cuda").manual_seed(5)
