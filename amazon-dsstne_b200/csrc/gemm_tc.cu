@@ -284,6 +284,65 @@ __device__ __forceinline__ Tile tile_of(const Args& a, uint32_t t)
     return x;
 }
 
+// ---------------------------------------------------------------- epilogue warps (shared by both kernels)
+__device__ __forceinline__ void epilogue_role(const Args& a, uint32_t tmem, float* epiStage, uint64_t* accFullBar, uint64_t* accEmptyBar,
+                                              uint32_t warp, uint32_t lane, uint32_t numTiles)
+{
+    // ---------------------------------------------------------------- epilogue warps
+    // warp w may read TMEM lanes 32*(w%4) .. +31 = accumulator rows; thread = row
+    const uint32_t rowBase = (warp & 3) * 32;
+    float* stage = epiStage + (warp - EPI_WARP0) * (32 * EPI_LD);
+    uint32_t seq = 0;
+    for (uint32_t t = blockIdx.x; t < numTiles; t += gridDim.x, seq++) {
+        const Tile tl = tile_of(a, t);
+        const uint32_t acc = seq & 1;
+        mbar_wait(&accFullBar[acc], (seq >> 1) & 1);
+        tc_fence_after();
+        const uint32_t mBase = tl.m0 + rowBase;
+        const uint32_t rows = (mBase < a.M) ? min(32u, a.M - mBase) : 0u;
+        const uint32_t ldo = a.partial ? a.N : a.ldc;
+        float* outBase = a.partial ? a.partial + (size_t)tl.split * a.M * a.N : a.C;
+#pragma unroll 1
+        for (int half = 0; half < BN / EPI_COLS; half++) {
+            {
+                float v[32];
+                tmem_ld32(tmem + (rowBase << 16) + acc * BN + half * EPI_COLS, v);
+#pragma unroll
+                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(stage + lane * EPI_LD + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+            }
+            if (half == BN / EPI_COLS - 1) {                                  // accumulator fully read: the MMA warp may reuse it
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&accEmptyBar[acc]);
+            }
+            __syncwarp();
+            // 32 columns per pass: lanes 0-15 take the even rows, lanes 16-31 the odd rows, 2 columns each
+            const uint32_t c0 = half * EPI_COLS + (lane & 15) * 2, nc = tl.n0 + c0;
+            const uint32_t ncol = (nc < a.N) ? min(2u, a.N - nc) : 0u;
+            const uint32_t rsel = lane >> 4;
+            if (ncol && !(a.debug & 16)) {
+                float bias0 = 0.f, bias1 = 0.f;
+                if (a.bias && !a.partial) {
+                    bias0 = __ldg(a.bias + nc);
+                    if (ncol > 1) bias1 = __ldg(a.bias + nc + 1);
+                }
+                const bool vec2 = ncol == 2 && (a.partial ? ((a.N & 1) == 0) : (a.vecC >= 2));
+                float* o = outBase + (size_t)(mBase + rsel) * ldo + nc;
+                const float* sp = stage + rsel * EPI_LD + (lane & 15) * 2;
+                if (a.partial)                        store_rows<-1>(sp, o, rsel, rows, ldo, ncol, vec2, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f);
+                else if (a.act == DSB200_ACT_LINEAR)  store_rows<DSB200_ACT_LINEAR>(sp, o, rsel, rows, ldo, ncol, vec2, a.alpha, a.beta, bias0, bias1, 0.f, 0.f, 0.f);
+                else if (a.act == DSB200_ACT_SIGMOID) store_rows<DSB200_ACT_SIGMOID>(sp, o, rsel, rows, ldo, ncol, vec2, a.alpha, a.beta, bias0, bias1, 0.f, 0.f, 0.f);
+                else if (a.act == DSB200_ACT_TANH)    store_rows<DSB200_ACT_TANH>(sp, o, rsel, rows, ldo, ncol, vec2, a.alpha, a.beta, bias0, bias1, 0.f, 0.f, 0.f);
+                else if (a.act == DSB200_ACT_RELU)    store_rows<DSB200_ACT_RELU>(sp, o, rsel, rows, ldo, ncol, vec2, a.alpha, a.beta, bias0, bias1, 0.f, 0.f, 0.f);
+                else if (a.act == DSB200_ACT_LRELU)   store_rows<DSB200_ACT_LRELU>(sp, o, rsel, rows, ldo, ncol, vec2, a.alpha, a.beta, bias0, bias1, a.slope, 0.f, 0.f);
+                else if (a.act == DSB200_ACT_ELU)     store_rows<DSB200_ACT_ELU>(sp, o, rsel, rows, ldo, ncol, vec2, a.alpha, a.beta, bias0, bias1, 0.f, a.ealpha, 0.f);
+                else                                  store_rows<DSB200_ACT_SELU>(sp, o, rsel, rows, ldo, ncol, vec2, a.alpha, a.beta, bias0, bias1, 0.f, a.ealpha, a.lambda);
+            }
+            __syncwarp();                                                     // staging tile free for the next half
+        }
+    }
+}
+
 template <bool AMN, bool BMN>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_kernel(const Args a)
@@ -411,59 +470,242 @@ gemm_tc_kernel(const Args a)
             }
         }
     } else {
-        // ---------------------------------------------------------------- epilogue warps
-        // warp w may read TMEM lanes 32*(w%4) .. +31 = accumulator rows; thread = row
-        const uint32_t rowBase = (warp & 3) * 32;
-        float* stage = epiStage + (warp - EPI_WARP0) * (32 * EPI_LD);
-        uint32_t seq = 0;
-        for (uint32_t t = blockIdx.x; t < numTiles; t += gridDim.x, seq++) {
-            const Tile tl = tile_of(a, t);
-            const uint32_t acc = seq & 1;
-            mbar_wait(&accFullBar[acc], (seq >> 1) & 1);
-            tc_fence_after();
-            const uint32_t mBase = tl.m0 + rowBase;
-            const uint32_t rows = (mBase < a.M) ? min(32u, a.M - mBase) : 0u;
-            const uint32_t ldo = a.partial ? a.N : a.ldc;
-            float* outBase = a.partial ? a.partial + (size_t)tl.split * a.M * a.N : a.C;
-#pragma unroll 1
-            for (int half = 0; half < BN / EPI_COLS; half++) {
-                {
-                    float v[32];
-                    tmem_ld32(tmem + (rowBase << 16) + acc * BN + half * EPI_COLS, v);
+        epilogue_role(a, tmem, epiStage, accFullBar, accEmptyBar, warp, lane, numTiles);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) tmem_dealloc(tmem, 2 * BN);
+}
+
+// =====================================================================================================================
+// Register-staged loader (option "gemm_loader": -1 = chosen per shape (default), 1 = always, 0 = never).
+// ncu on the cp.async kernel above (profiles/r1c_gemm_smem_pipe.md): the shared-memory data pipe is the bound -- one
+// 128 x 128 x 8 tf32 MMA reads its operands at the pipe's full 128 bytes / clock, so every other wavefront competes with
+// the tensor core -- and LDGSTS is the worst customer: its shared-memory writes land sector by sector, 4.2 x the
+// wavefronts of the same bytes written with 128-bit stores (7.3 M of the 15 M LSU wavefronts of the forward GEMM),
+// before the split warps read every panel again.  Here 16 loader warps bring the operands through REGISTERS instead:
+//   ld.global.nc (128 / 64 / 32-bit by alignment, one k-iteration ahead)  ->  hi = raw words, lo = a - trunc_tf32(a)
+//   ->  two conflict-free st.shared.v4 per 16-byte chunk, straight into the UMMA layouts of a 3-deep ring
+// i.e. 2 wavefront-bytes per operand byte instead of ~6, no cp.async, no separate split pass.  MMA and epilogue roles
+// are unchanged; a ring slot is raw A | raw B | lo A | lo B (64 KB).
+constexpr int RSLOTS = 3, RSLOT_BYTES = 4 * PANEL, LOAD_WARPS = 16;
+constexpr int RSMEM_BYTES = RSLOTS * RSLOT_BYTES + EPI_BYTES + 1024;
+static_assert(LOAD_WARPS == MMA_WARP, "the MMA warp follows the loader warps");
+
+__device__ __forceinline__ float4 ldg_nc4(const float* p)
+{
+    float4 r;
+    asm volatile("ld.global.nc.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float2 ldg_nc2(const float* p)
+{
+    float2 r;
+    asm volatile("ld.global.nc.v2.f32 {%0,%1}, [%2];" : "=f"(r.x), "=f"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ float ldg_nc1(const float* p)
+{
+    float r;
+    asm volatile("ld.global.nc.f32 %0, [%1];" : "=f"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void sts4(uint32_t addr, float4 v)
+{
+    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(addr), "f"(v.x), "f"(v.y), "f"(v.z), "f"(v.w) : "memory");
+}
+// one 16-byte chunk of an operand: v = floats inside the matrix (0..4), vec = widest aligned access of the operand
+__device__ __forceinline__ float4 load_chunk(const float* p, uint32_t v, int vec)
+{
+    float4 r = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (v == 0) return r;
+    if (vec == 4 && v == 4) return ldg_nc4(p);
+    if (vec >= 2) {
+        if (v >= 2) { const float2 t = ldg_nc2(p); r.x = t.x; r.y = t.y; } else r.x = ldg_nc1(p);
+        if (v == 4) { const float2 t = ldg_nc2(p + 2); r.z = t.x; r.w = t.y; } else if (v == 3) r.z = ldg_nc1(p + 2);
+        return r;
+    }
+    r.x = ldg_nc1(p);
+    if (v > 1) r.y = ldg_nc1(p + 1);
+    if (v > 2) r.z = ldg_nc1(p + 2);
+    if (v > 3) r.w = ldg_nc1(p + 3);
+    return r;
+}
+__device__ __forceinline__ float lo_of(float x) { return x - __uint_as_float(__float_as_uint(x) & 0xFFFFE000u); }
+
+// Per-thread plan of one operand of one tile: a 128 x 32 panel is 1,024 16-byte chunks, two per loader thread.
+//   K-major  (rows = mn, 128 bytes each): piece i = row i * 64 + warp * 4 + lane / 8, chunk lane % 8 -- a warp reads 4
+//            whole 128-byte rows and writes 4 whole swizzled rows (a quarter-warp = one row: conflict free)
+//   MN-major (rows = k, 512 bytes each):  piece i = atom (warp / 8) * 2 + i (32 columns), k-row (warp % 8) * 4 + lane % 4,
+//            chunk lane / 4 -- a warp reads 4 k-rows x 128 bytes; a quarter-warp writes 4 rows x 32 bytes on 32 distinct banks
+template <bool MN>
+struct RegPlan {
+    static constexpr uint32_t SPIECE = MN ? 4096u : 8192u;   // shared-memory bytes between the two pieces
+    const float* ptr;                          // global address of piece 0 in the next k-iteration to load
+    size_t       pieceStride, step;            // floats between the pieces / pointer advance per k-iteration
+    uint32_t     soff;                         // byte offset of piece 0 inside a panel (the same for every tile)
+    uint32_t     v0, v1;                       // floats of the chunk inside the matrix along mn (K-major: 4 or 0 by row)
+    uint32_t     kOff;                         // first k of this thread's chunk inside the panel
+
+    __device__ __forceinline__ void init(const float* b, uint32_t ld, uint32_t mn0, uint32_t kBegin, uint32_t mnLimit, uint32_t warp, uint32_t lane)
+    {
+        if (MN) {
+            const uint32_t kg = warp & 7, atom0 = (warp >> 3) * 2;
+            const uint32_t k = kg * 4 + (lane & 3), mn = mn0 + atom0 * 32 + (lane >> 2) * 4;
+            kOff = k;
+            soff = atom0 * 4096 + kg * 512 + (lane & 3) * 128 + (((lane >> 3) ^ (lane & 3)) * 32) + ((lane >> 2) & 1) * 16;
+            pieceStride = 32;
+            step = (size_t)BK * ld;
+            v0 = mn < mnLimit ? min(4u, mnLimit - mn) : 0u;
+            v1 = mn + 32 < mnLimit ? min(4u, mnLimit - mn - 32) : 0u;
+            ptr = b + (size_t)(kBegin + k) * ld + mn;                            // may point past the matrix: only dereferenced when valid
+        } else {
+            const uint32_t r = warp * 4 + (lane >> 3), c = lane & 7, row = mn0 + r;
+            kOff = c * 4;
+            soff = (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) * 16);
+            pieceStride = (size_t)64 * ld;
+            step = BK;
+            v0 = row < mnLimit ? 4u : 0u;
+            v1 = row + 64 < mnLimit ? 4u : 0u;
+            ptr = b + (size_t)row * ld + kBegin + c * 4;
+        }
+    }
+    // this thread's two chunks of the panel that starts at k0; `full`: the whole panel lies inside [kBegin, kEnd)
+    __device__ __forceinline__ void load(float4 (&r)[2], uint32_t k0, uint32_t kEnd, bool full, int vec)
+    {
+        if (MN) {
+            const bool rowIn = full || (k0 + kOff < kEnd);
+            r[0] = load_chunk(ptr, rowIn ? v0 : 0u, vec);
+            r[1] = load_chunk(ptr + pieceStride, rowIn ? v1 : 0u, vec);
+        } else {
+            const uint32_t kv = full ? 4u : (k0 + kOff < kEnd ? min(4u, kEnd - k0 - kOff) : 0u);
+            r[0] = load_chunk(ptr, v0 ? kv : 0u, vec);
+            r[1] = load_chunk(ptr + pieceStride, v1 ? kv : 0u, vec);
+        }
+        ptr += step;
+    }
+    __device__ __forceinline__ void store(uint32_t rawPanel, uint32_t loPanel, const float4 (&r)[2], bool lo) const
+    {
 #pragma unroll
-                    for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(stage + lane * EPI_LD + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+        for (int i = 0; i < 2; i++) {
+            sts4(rawPanel + soff + i * SPIECE, r[i]);
+            if (lo) sts4(loPanel + soff + i * SPIECE, make_float4(lo_of(r[i].x), lo_of(r[i].y), lo_of(r[i].z), lo_of(r[i].w)));
+        }
+    }
+};
+
+template <bool AMN, bool BMN, int DEPTH>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_tc_reg_kernel(const Args a)
+{
+    extern __shared__ uint8_t smemRaw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smemRaw + 1023) & ~(uintptr_t)1023);
+    float* epiStage = reinterpret_cast<float*>(smem + RSLOTS * RSLOT_BYTES);
+    __shared__ uint64_t fullBar[RSLOTS], emptyBar[RSLOTS], accFullBar[2], accEmptyBar[2];
+    __shared__ uint32_t tmemBase;
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t numTiles = a.tilesM * a.tilesN * a.splits;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < RSLOTS; s++) { mbar_init(&fullBar[s], LOAD_WARPS); mbar_init(&emptyBar[s], 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(&accFullBar[s], 1); mbar_init(&accEmptyBar[s], EPI_WARPS); }
+        mbar_fence_init();
+    }
+    if (warp == MMA_WARP) tmem_alloc(&tmemBase, 2 * BN);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmemBase;
+    const uint32_t ringAddr = smem_u32(smem);
+
+    if (warp < LOAD_WARPS) {
+        // ---------------------------------------------------------------- loader warps
+        // The (tile, k-iteration) sequence of this CTA is walked by a load cursor that runs one iteration ahead of the
+        // stores: the loads of iteration i + 1 are in flight while iteration i waits for its ring slot.
+        RegPlan<AMN> pa;
+        RegPlan<BMN> pb;
+        uint32_t lt = blockIdx.x, lkt = 0, slot = 0, parity = 1;
+        Tile ltl = tile_of(a, min(lt, numTiles - 1));
+        bool more = lt < numTiles;
+        pa.init(a.A, a.lda, ltl.m0, ltl.kBegin, a.M, warp, lane);
+        pb.init(a.B, a.ldb, ltl.n0, ltl.kBegin, a.N, warp, lane);
+        const bool lo = a.passes == 3 && !(a.debug & 8);
+        auto fetch = [&](float4 (&ra)[2], float4 (&rb)[2]) {
+            const uint32_t k0 = ltl.kBegin + lkt * BK;
+            const bool full = k0 + BK <= ltl.kEnd;
+            const uint32_t kLim = (a.debug & 32) ? k0 : ltl.kEnd;                  // bring-up switch 32: no global loads (zero panels)
+            pa.load(ra, k0, kLim, full && !(a.debug & 32), a.vecA);
+            pb.load(rb, k0, kLim, full && !(a.debug & 32), a.vecB);
+            if (++lkt == ltl.numK) {
+                lkt = 0; lt += gridDim.x; more = lt < numTiles;
+                if (more) {
+                    ltl = tile_of(a, lt);
+                    pa.init(a.A, a.lda, ltl.m0, ltl.kBegin, a.M, warp, lane);
+                    pb.init(a.B, a.ldb, ltl.n0, ltl.kBegin, a.N, warp, lane);
                 }
-                if (half == BN / EPI_COLS - 1) {                                  // accumulator fully read: the MMA warp may reuse it
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&accEmptyBar[acc]);
-                }
-                __syncwarp();
-                // 32 columns per pass: lanes 0-15 take the even rows, lanes 16-31 the odd rows, 2 columns each
-                const uint32_t c0 = half * EPI_COLS + (lane & 15) * 2, nc = tl.n0 + c0;
-                const uint32_t ncol = (nc < a.N) ? min(2u, a.N - nc) : 0u;
-                const uint32_t rsel = lane >> 4;
-                if (ncol && !(a.debug & 16)) {
-                    float bias0 = 0.f, bias1 = 0.f;
-                    if (a.bias && !a.partial) {
-                        bias0 = __ldg(a.bias + nc);
-                        if (ncol > 1) bias1 = __ldg(a.bias + nc + 1);
-                    }
-                    const bool vec2 = ncol == 2 && (a.partial ? ((a.N & 1) == 0) : (a.vecC >= 2));
-                    float* o = outBase + (size_t)(mBase + rsel) * ldo + nc;
-                    const float* sp = stage + rsel * EPI_LD + (lane & 15) * 2;
-                    if (a.partial)                        store_rows<-1>(sp, o, rsel, rows, ldo, ncol, vec2, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f);
-                    else if (a.act == DSB200_ACT_LINEAR)  store_rows<DSB200_ACT_LINEAR>(sp, o, rsel, rows, ldo, ncol, vec2, a.alpha, a.beta, bias0, bias1, 0.f, 0.f, 0.f);
-                    else if (a.act == DSB200_ACT_SIGMOID) store_rows<DSB200_ACT_SIGMOID>(sp, o, rsel, rows, ldo, ncol, vec2, a.alpha, a.beta, bias0, bias1, 0.f, 0.f, 0.f);
-                    else if (a.act == DSB200_ACT_TANH)    store_rows<DSB200_ACT_TANH>(sp, o, rsel, rows, ldo, ncol, vec2, a.alpha, a.beta, bias0, bias1, 0.f, 0.f, 0.f);
-                    else if (a.act == DSB200_ACT_RELU)    store_rows<DSB200_ACT_RELU>(sp, o, rsel, rows, ldo, ncol, vec2, a.alpha, a.beta, bias0, bias1, 0.f, 0.f, 0.f);
-                    else if (a.act == DSB200_ACT_LRELU)   store_rows<DSB200_ACT_LRELU>(sp, o, rsel, rows, ldo, ncol, vec2, a.alpha, a.beta, bias0, bias1, a.slope, 0.f, 0.f);
-                    else if (a.act == DSB200_ACT_ELU)     store_rows<DSB200_ACT_ELU>(sp, o, rsel, rows, ldo, ncol, vec2, a.alpha, a.beta, bias0, bias1, 0.f, a.ealpha, 0.f);
-                    else                                  store_rows<DSB200_ACT_SELU>(sp, o, rsel, rows, ldo, ncol, vec2, a.alpha, a.beta, bias0, bias1, 0.f, a.ealpha, a.lambda);
-                }
-                __syncwarp();                                                     // staging tile free for the next half
+            }
+        };
+        auto publish = [&](const float4 (&ra)[2], const float4 (&rb)[2]) {
+            mbar_wait(&emptyBar[slot], parity);                                   // the MMAs that read this slot have retired
+            const uint32_t st = ringAddr + slot * RSLOT_BYTES;
+            pa.store(st, st + 2 * PANEL, ra, lo);
+            pb.store(st + PANEL, st + 3 * PANEL, rb, lo);
+            if (!(a.debug & 1)) fence_async_smem();                               // generic-proxy stores -> visible to the tensor core
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&fullBar[slot]);
+            if (++slot == RSLOTS) { slot = 0; parity ^= 1; }
+        };
+        float4 ra[DEPTH][2], rb[DEPTH][2];
+        uint32_t pending = 0;
+#pragma unroll
+        for (int s = 0; s < DEPTH - 1; s++)
+            if (more) { fetch(ra[s], rb[s]); pending++; }
+        while (pending) {
+#pragma unroll
+            for (int s = 0; s < DEPTH; s++) {
+                if (more) { fetch(ra[(s + DEPTH - 1) % DEPTH], rb[(s + DEPTH - 1) % DEPTH]); pending++; }
+                publish(ra[s], rb[s]);
+                if (--pending == 0) break;
             }
         }
+    } else if (warp == MMA_WARP) {
+        // ---------------------------------------------------------------- MMA issuer
+        if (lane == 0) {
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((AMN ? 1u : 0u) << 15) | ((BMN ? 1u : 0u) << 16) |
+                                   ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            uint32_t slot = 0, ph = 0, seq = 0;
+            for (uint32_t t = blockIdx.x; t < numTiles; t += gridDim.x, seq++) {
+                const Tile tl = tile_of(a, t);
+                const uint32_t acc = seq & 1, d = tmem + acc * BN;
+                mbar_wait(&accEmptyBar[acc], ((seq >> 1) & 1) ^ 1);               // the epilogue has drained this accumulator
+                tc_fence_after();
+                for (uint32_t kt = 0; kt < tl.numK; kt++) {
+                    mbar_wait(&fullBar[slot], ph);
+                    tc_fence_after();
+                    const uint32_t ra = ringAddr + slot * RSLOT_BYTES, la = ra + 2 * PANEL;
+#pragma unroll
+                    for (int j = 0; j < BK / 8; j++) {
+                        const uint64_t aHi = panel_desc<AMN>(ra, j), bHi = panel_desc<BMN>(ra + PANEL, j);
+                        const uint32_t first = (kt == 0 && j == 0) ? 0u : 1u;
+                        if (a.debug & 4) {
+                        } else if (a.passes == 3) {
+                            const uint64_t aLo = panel_desc<AMN>(la, j), bLo = panel_desc<BMN>(la + PANEL, j);
+                            tc_mma_tf32(d, aLo, bHi, idesc, first);               // small terms first
+                            tc_mma_tf32(d, aHi, bLo, idesc, 1u);
+                            tc_mma_tf32(d, aHi, bHi, idesc, 1u);
+                        } else {
+                            tc_mma_tf32(d, aHi, bHi, idesc, first);
+                        }
+                    }
+                    tc_commit(&emptyBar[slot]);                                   // slot reusable once these MMAs have read it
+                    if (++slot == RSLOTS) { slot = 0; ph ^= 1; }
+                }
+                tc_commit(&accFullBar[acc]);
+            }
+        }
+    } else {
+        epilogue_role(a, tmem, epiStage, accFullBar, accEmptyBar, warp, lane, numTiles);
     }
     tc_fence_before();
     __syncthreads();
@@ -510,6 +752,10 @@ int gemm_tc_launch(dsb200_ctx* ctx, const float* A, int aMN, uint32_t lda, const
         DSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         DSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
         DSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+        DSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_reg_kernel<false, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, RSMEM_BYTES));
+        DSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_reg_kernel<false, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, RSMEM_BYTES));
+        DSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_reg_kernel<true, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, RSMEM_BYTES));
+        DSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_reg_kernel<true, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, RSMEM_BYTES));
         attrSet = true;
     }
     Args a;
@@ -547,7 +793,19 @@ int gemm_tc_launch(dsb200_ctx* ctx, const float* A, int aMN, uint32_t lda, const
         a.partial = ctx->dGemmWs;
     }
     const uint32_t grid = min(sms, tilesMN * splits);
-    if (aMN) {
+    // operand path: measured on the three output-layer GEMMs of BASELINE config 2 (gpurun_out/gemm_debug_matrix.log), the
+    // register loader wins when an operand is MN-major (forward 92 -> 82 us, weight gradient 97 -> 80 us) and loses
+    // slightly when both are K-major with 8-byte rows (input delta 85 -> 90 us)
+    const bool regLoader = ctx->gemmLoader < 0 ? (aMN || bMN) : ctx->gemmLoader >= 1;
+    if (regLoader) {
+        if (aMN) {
+            if (bMN) gemm_tc_reg_kernel<true, true, 2><<<grid, THREADS, RSMEM_BYTES, ctx->stream>>>(a);
+            else     gemm_tc_reg_kernel<true, false, 2><<<grid, THREADS, RSMEM_BYTES, ctx->stream>>>(a);
+        } else {
+            if (bMN) gemm_tc_reg_kernel<false, true, 2><<<grid, THREADS, RSMEM_BYTES, ctx->stream>>>(a);
+            else     gemm_tc_reg_kernel<false, false, 2><<<grid, THREADS, RSMEM_BYTES, ctx->stream>>>(a);
+        }
+    } else if (aMN) {
         if (bMN) gemm_tc_kernel<true, true><<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(a);
         else     gemm_tc_kernel<true, false><<<grid, THREADS, SMEM_BYTES, ctx->stream>>>(a);
     } else {

@@ -16,16 +16,18 @@ from helpers import rel_err
 
 pytestmark = pytest.mark.gpu
 BOUND = {0: 1e-5, 2: 3e-5, 1: 3e-3}
-SHAPES = [(1024, 128, 27278), (1024, 128, 128), (256, 128, 256), (300, 70, 1000), (130, 33, 259), (64, 1024, 2000), (1, 5, 7)]
+SHAPES = [(1024, 128, 27278), (1024, 128, 128), (256, 128, 256), (300, 70, 1000), (130, 33, 259), (64, 1024, 2000), (1, 5, 7),
+          (200, 36, 516), (257, 129, 131)]   # 16-byte aligned rows with ragged K / N; every dimension odd
 
 
 def ref64(a):
     return a.double().cpu().numpy()
 
 
-@pytest.mark.parametrize("mode", [0, 2, 1], ids=["fp32", "tf32x3", "tf32"])
+@pytest.mark.parametrize("mode,loader", [(0, 1), (2, 1), (2, 0), (1, 1), (1, 0)],
+                         ids=["fp32", "tf32x3-regload", "tf32x3-cpasync", "tf32-regload", "tf32-cpasync"])
 @pytest.mark.parametrize("B,k,n", SHAPES)
-def test_gemm_fwd_dw_dx(ctx, mode, B, k, n):
+def test_gemm_fwd_dw_dx(ctx, mode, loader, B, k, n):
     g = torch.Generator(device="cuda").manual_seed(B * 7 + k * 3 + n)
     A = torch.randn(B, k, device="cuda", generator=g)
     W = torch.randn(k, n, device="cuda", generator=g) * 0.1
@@ -33,6 +35,7 @@ def test_gemm_fwd_dw_dx(ctx, mode, B, k, n):
     C0 = torch.randn(B, n, device="cuda", generator=g)
     ctx.set_option("gemm_mode", mode)
     ctx.set_option("gemm_tc_min_work", 0)                       # force the tensor-core kernel for every shape
+    ctx.set_option("gemm_loader", loader)                       # operand path: registers (default) or cp.async + split warps
     try:
         C = C0.clone()
         ctx.gemm_fwd(A, W, C, beta=1.0)
@@ -46,6 +49,7 @@ def test_gemm_fwd_dw_dx(ctx, mode, B, k, n):
     finally:
         ctx.set_option("gemm_mode", 0)
         ctx.set_option("gemm_tc_min_work", 2048)
+        ctx.set_option("gemm_loader", -1)
     a, w, d = ref64(A), ref64(W), ref64(D)
     tol = BOUND[mode]
     assert rel_err(C.cpu().numpy(), ref64(C0) + a @ w) < tol

@@ -46,8 +46,9 @@ def main():
     G = torch.zeros(k, n, device="cuda")
     Dp = torch.zeros(B, k, device="cuda")
     bias = torch.randn(n, device="cuda", generator=g)
-    for mode, name in ((0, "fp32-cublas"), (2, "tf32x3"), (1, "tf32")):
+    for mode, loader, name in ((0, -1, "fp32-cublas"), (2, -1, "tf32x3-auto"), (2, 1, "tf32x3-regload"), (2, 0, "tf32x3-cpasync"), (1, -1, "tf32-auto")):
         ctx.set_option("gemm_mode", mode)
+        ctx.set_option("gemm_loader", loader)
         for fn, label in ((lambda: ctx.gemm_fwd(A, W, C, beta=0.0), "fwd"), (lambda: ctx.gemm_dw(A, D, G, -1.0 / B), "dw"),
                           (lambda: ctx.gemm_dx(D, W, Dp), "dx"), (lambda: ctx.gemm_fwd_bias_act(A, W, bias, 0, C), "fwd+bias+sigmoid")):
             for _ in range(3):
