@@ -10,7 +10,10 @@
 //    (dsb200_sparse_wgrad_update) when BackPropagate deferred the gradient.
 #include "NNWeight.h"
 
+#include <algorithm>
 #include <cmath>
+#include <thread>
+#include <vector>
 
 #include "NNLayer.h"
 #include "NNNetwork.h"
@@ -85,17 +88,31 @@ void NNWeight::Randomize()
     case SELU:        gaussian = true; sigma = 1.0f / _inputLayer._stride; break;
     case Constant:    constant = true; break;
     }
-    for (uint64_t r = 0; r < _height; r++) {
-        for (uint64_t c = 0; c < _width; c++) {
-            const uint64_t g = (uint64_t)(inMin + r) * _outputLayer._stride + (outMin + c);      // global element index
-            NNFloat w;
-            if (constant) w = _outputLayer._weightInitScale;
-            else if (gaussian) {
-                const float u1 = u01(key, 2 * g), u2 = u01(key, 2 * g + 1);
-                w = sigma * sqrtf(-2.0f * logf(u1)) * cosf(6.28318530718f * u2);
-            } else w = scale * u01(key, g) - bias;
-            _vWeight[r * _width + c] = w;
+    // every element depends only on its global index, so rows are filled by independent host threads (the 1M x 1,024
+    // matrices of BASELINE config 4 are 10^9 Box-Muller draws each)
+    auto fillRows = [&](uint64_t r0, uint64_t r1) {
+        for (uint64_t r = r0; r < r1; r++) {
+            for (uint64_t c = 0; c < _width; c++) {
+                const uint64_t g = (uint64_t)(inMin + r) * _outputLayer._stride + (outMin + c);  // global element index
+                NNFloat w;
+                if (constant) w = _outputLayer._weightInitScale;
+                else if (gaussian) {
+                    const float u1 = u01(key, 2 * g), u2 = u01(key, 2 * g + 1);
+                    w = sigma * sqrtf(-2.0f * logf(u1)) * cosf(6.28318530718f * u2);
+                } else w = scale * u01(key, g) - bias;
+                _vWeight[r * _width + c] = w;
+            }
         }
+    };
+    const uint64_t work = (uint64_t)_height * _width;
+    const unsigned hw = std::max(1u, std::thread::hardware_concurrency());
+    const uint64_t nThreads = work < (1ull << 20) ? 1 : std::min<uint64_t>({(uint64_t)hw, (uint64_t)_height, 64ull});
+    if (nThreads <= 1) fillRows(0, _height);
+    else {
+        std::vector<std::thread> pool;
+        for (uint64_t t = 0; t < nThreads; t++)
+            pool.emplace_back(fillRows, (uint64_t)_height * t / nThreads, (uint64_t)_height * (t + 1) / nThreads);
+        for (auto& th : pool) th.join();
     }
     _pbWeight->Upload(_vWeight.data());
     std::fill(_vBias.begin(), _vBias.end(), _outputLayer._biasInit);                             // E/NNWeight.cpp:556-557

@@ -239,7 +239,10 @@ def run_ours(args, wl, rank, world, local_rank):
                   "clocks": sampler.summary(), "gpu_launches": int(launches), "roofline": roof, "kernels": kern}
         if e2e:
             result["e2e"] = e2e
-        result["cpu_baseline"] = cpu_baseline(wl, data, sample_steps=max(1, args.cpu_steps))
+        if args.cpu_steps > 0:
+            result["cpu_baseline"] = cpu_baseline(wl, data, sample_steps=args.cpu_steps)
+        else:                                            # --cpu-steps 0: only for the side workloads (one c4 oracle step is minutes of host time)
+            result["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "skipped (--cpu-steps 0)"}
     net.close()
     if world > 1:
         import torch.distributed as dist
