@@ -478,7 +478,7 @@ gemm_tc_kernel(const Args a)
 }
 
 // =====================================================================================================================
-// Register-staged loader (option "gemm_loader": -1 = chosen per shape (default), 1 = always, 0 = never).
+// Register-staged loader (option "gemm_loader" = 1).
 // ncu on the cp.async kernel above (profiles/r1c_gemm_smem_pipe.md): the shared-memory data pipe is the bound -- one
 // 128 x 128 x 8 tf32 MMA reads its operands at the pipe's full 128 bytes / clock, so every other wavefront competes with
 // the tensor core -- and LDGSTS is the worst customer: its shared-memory writes land sector by sector, 4.2 x the
@@ -538,56 +538,58 @@ __device__ __forceinline__ float lo_of(float x) { return x - __uint_as_float(__f
 //            whole 128-byte rows and writes 4 whole swizzled rows (a quarter-warp = one row: conflict free)
 //   MN-major (rows = k, 512 bytes each):  piece i = atom (warp / 8) * 2 + i (32 columns), k-row (warp % 8) * 4 + lane % 4,
 //            chunk lane / 4 -- a warp reads 4 k-rows x 128 bytes; a quarter-warp writes 4 rows x 32 bytes on 32 distinct banks
-template <bool MN>
+template <bool MN, int NW>
 struct RegPlan {
-    static constexpr uint32_t SPIECE = MN ? 4096u : 8192u;   // shared-memory bytes between the two pieces
+    static constexpr int PIECES = 32 / NW;                    // 16-byte chunks per thread and panel: 2 with 16 loader warps, 4 with 8
+    static constexpr uint32_t SPIECE = MN ? 4096u : 512u * NW;   // shared-memory bytes between consecutive pieces
     const float* ptr;                          // global address of piece 0 in the next k-iteration to load
     size_t       pieceStride, step;            // floats between the pieces / pointer advance per k-iteration
     uint32_t     soff;                         // byte offset of piece 0 inside a panel (the same for every tile)
-    uint32_t     v0, v1;                       // floats of the chunk inside the matrix along mn (K-major: 4 or 0 by row)
+    uint32_t     v[PIECES];                    // floats of the chunk inside the matrix along mn (K-major: 4 or 0 by row)
     uint32_t     kOff;                         // first k of this thread's chunk inside the panel
 
+    // `warp` = index inside the loader group, 0 .. NW-1
     __device__ __forceinline__ void init(const float* b, uint32_t ld, uint32_t mn0, uint32_t kBegin, uint32_t mnLimit, uint32_t warp, uint32_t lane)
     {
         if (MN) {
-            const uint32_t kg = warp & 7, atom0 = (warp >> 3) * 2;
+            const uint32_t kg = warp & 7, atom0 = (warp >> 3) * PIECES;
             const uint32_t k = kg * 4 + (lane & 3), mn = mn0 + atom0 * 32 + (lane >> 2) * 4;
             kOff = k;
             soff = atom0 * 4096 + kg * 512 + (lane & 3) * 128 + (((lane >> 3) ^ (lane & 3)) * 32) + ((lane >> 2) & 1) * 16;
             pieceStride = 32;
             step = (size_t)BK * ld;
-            v0 = mn < mnLimit ? min(4u, mnLimit - mn) : 0u;
-            v1 = mn + 32 < mnLimit ? min(4u, mnLimit - mn - 32) : 0u;
+#pragma unroll
+            for (int i = 0; i < PIECES; i++) v[i] = mn + 32 * i < mnLimit ? min(4u, mnLimit - mn - 32 * i) : 0u;
             ptr = b + (size_t)(kBegin + k) * ld + mn;                            // may point past the matrix: only dereferenced when valid
         } else {
             const uint32_t r = warp * 4 + (lane >> 3), c = lane & 7, row = mn0 + r;
             kOff = c * 4;
             soff = (r >> 3) * 1024 + (r & 7) * 128 + ((c ^ (r & 7)) * 16);
-            pieceStride = (size_t)64 * ld;
+            pieceStride = (size_t)(4 * NW) * ld;
             step = BK;
-            v0 = row < mnLimit ? 4u : 0u;
-            v1 = row + 64 < mnLimit ? 4u : 0u;
+#pragma unroll
+            for (int i = 0; i < PIECES; i++) v[i] = row + 4 * NW * i < mnLimit ? 4u : 0u;
             ptr = b + (size_t)row * ld + kBegin + c * 4;
         }
     }
-    // this thread's two chunks of the panel that starts at k0; `full`: the whole panel lies inside [kBegin, kEnd)
-    __device__ __forceinline__ void load(float4 (&r)[2], uint32_t k0, uint32_t kEnd, bool full, int vec)
+    // this thread's chunks of the panel that starts at k0; `full`: the whole panel lies inside [kBegin, kEnd)
+    __device__ __forceinline__ void load(float4 (&r)[PIECES], uint32_t k0, uint32_t kEnd, bool full, int vec)
     {
         if (MN) {
             const bool rowIn = full || (k0 + kOff < kEnd);
-            r[0] = load_chunk(ptr, rowIn ? v0 : 0u, vec);
-            r[1] = load_chunk(ptr + pieceStride, rowIn ? v1 : 0u, vec);
+#pragma unroll
+            for (int i = 0; i < PIECES; i++) r[i] = load_chunk(ptr + i * pieceStride, rowIn ? v[i] : 0u, vec);
         } else {
             const uint32_t kv = full ? 4u : (k0 + kOff < kEnd ? min(4u, kEnd - k0 - kOff) : 0u);
-            r[0] = load_chunk(ptr, v0 ? kv : 0u, vec);
-            r[1] = load_chunk(ptr + pieceStride, v1 ? kv : 0u, vec);
+#pragma unroll
+            for (int i = 0; i < PIECES; i++) r[i] = load_chunk(ptr + i * pieceStride, v[i] ? kv : 0u, vec);
         }
         ptr += step;
     }
-    __device__ __forceinline__ void store(uint32_t rawPanel, uint32_t loPanel, const float4 (&r)[2], bool lo) const
+    __device__ __forceinline__ void store(uint32_t rawPanel, uint32_t loPanel, const float4 (&r)[PIECES], bool lo) const
     {
 #pragma unroll
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < PIECES; i++) {
             sts4(rawPanel + soff + i * SPIECE, r[i]);
             if (lo) sts4(loPanel + soff + i * SPIECE, make_float4(lo_of(r[i].x), lo_of(r[i].y), lo_of(r[i].z), lo_of(r[i].w)));
         }
@@ -623,8 +625,8 @@ gemm_tc_reg_kernel(const Args a)
         // ---------------------------------------------------------------- loader warps
         // The (tile, k-iteration) sequence of this CTA is walked by a load cursor that runs one iteration ahead of the
         // stores: the loads of iteration i + 1 are in flight while iteration i waits for its ring slot.
-        RegPlan<AMN> pa;
-        RegPlan<BMN> pb;
+        RegPlan<AMN, LOAD_WARPS> pa;
+        RegPlan<BMN, LOAD_WARPS> pb;
         uint32_t lt = blockIdx.x, lkt = 0, slot = 0, parity = 1;
         Tile ltl = tile_of(a, min(lt, numTiles - 1));
         bool more = lt < numTiles;
@@ -712,6 +714,242 @@ gemm_tc_reg_kernel(const Args a)
     if (warp == MMA_WARP) tmem_dealloc(tmem, 2 * BN);
 }
 
+// =====================================================================================================================
+// A operand through TENSOR MEMORY (option "gemm_loader" = 2, and the default -1).
+// The register loader above still pushes 224 KB through the L1 / shared-memory data array per 128 x 128 x 32 k-iteration
+// (fill, read to registers, raw + lo stores, 96 KB of MMA operand reads) and that array is the bound
+// (profiles/r1c_gemm_smem_pipe.md).  tcgen05.mma accepts A from tensor memory (tools/umma_ts_probe.cu: lane = row m,
+// one tf32 per column, consecutive columns = consecutive k), so here A never touches shared memory:
+//   warps 0-7    A loaders: thread = (row m, 16 of the 32 k of the panel): ld.global.nc -> registers -> hi / lo split ->
+//                tcgen05.st.32x32b.x16 into a 4-deep ring of (32 hi | 32 lo) columns behind the two accumulators
+//   warps 8-15   B loaders: the register loader of gemm_tc_reg_kernel for the B panel only (raw | lo, 32 KB per slot)
+//   warp 16      MMA: aLo*bHi + aHi*bLo + aHi*bHi with A addressed in TMEM, B by shared-memory descriptor
+//   warps 17-20  epilogue (unchanged)
+// Data-array bytes per k-iteration: A 16 (fill) + 16 (read); B 16 + 16 + 32 (stores); MMA 48 (B only) = 144 KB.
+constexpr int TS_SLOTS = 4, TS_SLOT_BYTES = 2 * PANEL, TS_A_WARPS = 8, TS_B_WARPS = 8;
+constexpr int TS_SMEM_BYTES = TS_SLOTS * TS_SLOT_BYTES + EPI_BYTES + 1024;
+constexpr uint32_t TS_ACC_COLS = 2 * BN, TS_A_COLS = 2 * BK, TS_TMEM_COLS = 512;
+static_assert(TS_ACC_COLS + TS_SLOTS * TS_A_COLS <= TS_TMEM_COLS, "tensor memory budget");
+static_assert(TS_A_WARPS + TS_B_WARPS == MMA_WARP, "the MMA warp follows the loader warps");
+
+__device__ __forceinline__ uint32_t ldg_nc1u(const float* p)
+{
+    uint32_t r;
+    asm volatile("ld.global.nc.b32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t (&r)[16])
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+                    "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+__device__ __forceinline__ void tc_mma_tf32_ts(uint32_t tmemD, uint32_t tmemA, uint64_t descB, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}" :: "r"(tmemD), "r"(tmemA), "l"(descB), "r"(idesc), "r"(accumulate) : "memory");
+}
+
+// one thread's 16 consecutive k of one row of the A panel
+template <bool MN>
+struct TmemAPlan {
+    const float* ptr;                          // (row, first k of this thread) in the next k-iteration to load
+    size_t       step, ld;
+    uint32_t     kOff;
+    bool         rowIn;
+    __device__ __forceinline__ void init(const float* A, uint32_t lda, uint32_t m0, uint32_t kBegin, uint32_t M, uint32_t quadrant, uint32_t khalf, uint32_t lane)
+    {
+        const uint32_t m = m0 + quadrant * 32 + lane;
+        rowIn = m < M; kOff = khalf * 16; ld = lda;
+        if (MN) { ptr = A + (size_t)(kBegin + kOff) * lda + m; step = (size_t)BK * lda; }    // lanes = consecutive m: coalesced
+        else    { ptr = A + (size_t)m * lda + kBegin + kOff;   step = BK; }                   // a thread reads 64 contiguous bytes of its row
+    }
+    __device__ __forceinline__ void load(uint32_t (&r)[16], uint32_t k0, uint32_t kEnd, int vec)
+    {
+        const uint32_t kb = k0 + kOff;
+        const uint32_t nv = (rowIn && kb < kEnd) ? min(16u, kEnd - kb) : 0u;
+        if (!MN && nv == 16 && vec == 4) {
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const float4 t = ldg_nc4(ptr + 4 * i);
+                r[4 * i] = __float_as_uint(t.x); r[4 * i + 1] = __float_as_uint(t.y); r[4 * i + 2] = __float_as_uint(t.z); r[4 * i + 3] = __float_as_uint(t.w);
+            }
+        } else if (!MN && nv == 16 && vec == 2) {
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const float2 t = ldg_nc2(ptr + 2 * i);
+                r[2 * i] = __float_as_uint(t.x); r[2 * i + 1] = __float_as_uint(t.y);
+            }
+        } else if (nv == 16) {
+#pragma unroll
+            for (int e = 0; e < 16; e++) r[e] = ldg_nc1u(MN ? ptr + e * ld : ptr + e);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 16; e++) r[e] = (uint32_t)e < nv ? ldg_nc1u(MN ? ptr + e * ld : ptr + e) : 0u;
+        }
+        ptr += step;
+    }
+};
+
+template <bool AMN, bool BMN>
+__global__ void __launch_bounds__(THREADS, 1)
+gemm_tc_ts_kernel(const Args a)
+{
+    extern __shared__ uint8_t smemRaw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smemRaw + 1023) & ~(uintptr_t)1023);
+    float* epiStage = reinterpret_cast<float*>(smem + TS_SLOTS * TS_SLOT_BYTES);
+    __shared__ uint64_t fullBar[TS_SLOTS], emptyBar[TS_SLOTS], accFullBar[2], accEmptyBar[2];
+    __shared__ uint32_t tmemBase;
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t numTiles = a.tilesM * a.tilesN * a.splits;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TS_SLOTS; s++) { mbar_init(&fullBar[s], TS_A_WARPS + TS_B_WARPS); mbar_init(&emptyBar[s], 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(&accFullBar[s], 1); mbar_init(&accEmptyBar[s], EPI_WARPS); }
+        mbar_fence_init();
+    }
+    if (warp == MMA_WARP) tmem_alloc(&tmemBase, TS_TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmemBase;
+    const uint32_t ringAddr = smem_u32(smem);
+    const bool lo = a.passes == 3 && !(a.debug & 8);
+
+    if (warp < TS_A_WARPS) {
+        // ---------------------------------------------------------------- A loaders: global -> registers -> tensor memory
+        const uint32_t quadrant = warp & 3, khalf = warp >> 2;                    // a warp may only touch TMEM lanes 32 * (warp % 4) ..
+        TmemAPlan<AMN> pa;
+        uint32_t lt = blockIdx.x, lkt = 0, slot = 0, parity = 1;
+        Tile ltl = tile_of(a, min(lt, numTiles - 1));
+        bool more = lt < numTiles;
+        pa.init(a.A, a.lda, ltl.m0, ltl.kBegin, a.M, quadrant, khalf, lane);
+        auto fetch = [&](uint32_t (&r)[16]) {
+            const uint32_t k0 = ltl.kBegin + lkt * BK;
+            pa.load(r, k0, (a.debug & 32) ? k0 : ltl.kEnd, a.vecA);
+            if (++lkt == ltl.numK) {
+                lkt = 0; lt += gridDim.x; more = lt < numTiles;
+                if (more) { ltl = tile_of(a, lt); pa.init(a.A, a.lda, ltl.m0, ltl.kBegin, a.M, quadrant, khalf, lane); }
+            }
+        };
+        auto publish = [&](uint32_t (&r)[16]) {
+            mbar_wait(&emptyBar[slot], parity);                                   // the MMAs that read this slot have retired
+            tc_fence_after();
+            const uint32_t ta = tmem + ((quadrant * 32) << 16) + TS_ACC_COLS + slot * TS_A_COLS + khalf * 16;
+            uint32_t hi[16];
+#pragma unroll
+            for (int e = 0; e < 16; e++) hi[e] = r[e] & 0xFFFFE000u;
+            tmem_st16(ta, hi);
+            if (lo) {
+#pragma unroll
+                for (int e = 0; e < 16; e++) hi[e] = __float_as_uint(__uint_as_float(r[e]) - __uint_as_float(hi[e]));
+                tmem_st16(ta + BK, hi);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&fullBar[slot]);
+            if (++slot == TS_SLOTS) { slot = 0; parity ^= 1; }
+        };
+        uint32_t r0[16], r1[16];
+        bool have0 = more;
+        if (have0) fetch(r0);
+        while (have0) {
+            const bool have1 = more;
+            if (have1) fetch(r1);
+            publish(r0);
+            if (!have1) break;
+            have0 = more;
+            if (have0) fetch(r0);
+            publish(r1);
+        }
+    } else if (warp < MMA_WARP) {
+        // ---------------------------------------------------------------- B loaders: global -> registers -> shared memory
+        const uint32_t bw = warp - TS_A_WARPS;
+        RegPlan<BMN, TS_B_WARPS> pb;
+        constexpr int PB = RegPlan<BMN, TS_B_WARPS>::PIECES;
+        uint32_t lt = blockIdx.x, lkt = 0, slot = 0, parity = 1;
+        Tile ltl = tile_of(a, min(lt, numTiles - 1));
+        bool more = lt < numTiles;
+        pb.init(a.B, a.ldb, ltl.n0, ltl.kBegin, a.N, bw, lane);
+        auto fetch = [&](float4 (&rb)[PB]) {
+            const uint32_t k0 = ltl.kBegin + lkt * BK;
+            const bool full = k0 + BK <= ltl.kEnd && !(a.debug & 32);
+            pb.load(rb, k0, (a.debug & 32) ? k0 : ltl.kEnd, full, a.vecB);
+            if (++lkt == ltl.numK) {
+                lkt = 0; lt += gridDim.x; more = lt < numTiles;
+                if (more) { ltl = tile_of(a, lt); pb.init(a.B, a.ldb, ltl.n0, ltl.kBegin, a.N, bw, lane); }
+            }
+        };
+        auto publish = [&](const float4 (&rb)[PB]) {
+            mbar_wait(&emptyBar[slot], parity);
+            const uint32_t st = ringAddr + slot * TS_SLOT_BYTES;
+            pb.store(st, st + PANEL, rb, lo);
+            if (!(a.debug & 1)) fence_async_smem();                               // generic-proxy stores -> visible to the tensor core
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&fullBar[slot]);
+            if (++slot == TS_SLOTS) { slot = 0; parity ^= 1; }
+        };
+        float4 b0[PB], b1[PB];
+        bool have0 = more;
+        if (have0) fetch(b0);
+        while (have0) {
+            const bool have1 = more;
+            if (have1) fetch(b1);
+            publish(b0);
+            if (!have1) break;
+            have0 = more;
+            if (have0) fetch(b0);
+            publish(b1);
+        }
+    } else if (warp == MMA_WARP) {
+        // ---------------------------------------------------------------- MMA issuer
+        if (lane == 0) {
+            // D = F32, A = B = TF32, A from tensor memory (K-major by construction), B major from the template
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((BMN ? 1u : 0u) << 16) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+            uint32_t slot = 0, ph = 0, seq = 0;
+            for (uint32_t t = blockIdx.x; t < numTiles; t += gridDim.x, seq++) {
+                const Tile tl = tile_of(a, t);
+                const uint32_t acc = seq & 1, d = tmem + acc * BN;
+                mbar_wait(&accEmptyBar[acc], ((seq >> 1) & 1) ^ 1);               // the epilogue has drained this accumulator
+                tc_fence_after();
+                for (uint32_t kt = 0; kt < tl.numK; kt++) {
+                    mbar_wait(&fullBar[slot], ph);
+                    tc_fence_after();
+                    const uint32_t sb = ringAddr + slot * TS_SLOT_BYTES, ta = tmem + TS_ACC_COLS + slot * TS_A_COLS;
+#pragma unroll
+                    for (int j = 0; j < BK / 8; j++) {
+                        const uint64_t bHi = panel_desc<BMN>(sb, j);
+                        const uint32_t aHi = ta + j * 8, first = (kt == 0 && j == 0) ? 0u : 1u;
+                        if (a.debug & 4) {
+                        } else if (a.passes == 3) {
+                            const uint64_t bLo = panel_desc<BMN>(sb + PANEL, j);
+                            tc_mma_tf32_ts(d, aHi + BK, bHi, idesc, first);       // small terms first
+                            tc_mma_tf32_ts(d, aHi, bLo, idesc, 1u);
+                            tc_mma_tf32_ts(d, aHi, bHi, idesc, 1u);
+                        } else {
+                            tc_mma_tf32_ts(d, aHi, bHi, idesc, first);
+                        }
+                    }
+                    tc_commit(&emptyBar[slot]);                                   // slot (shared and tensor memory) reusable once these MMAs retire
+                    if (++slot == TS_SLOTS) { slot = 0; ph ^= 1; }
+                }
+                tc_commit(&accFullBar[acc]);
+            }
+        }
+    } else {
+        epilogue_role(a, tmem, epiStage, accFullBar, accEmptyBar, warp, lane, numTiles);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == MMA_WARP) tmem_dealloc(tmem, TS_TMEM_COLS);
+}
+
 // out = alpha * sum_z partial[z] (+ beta * out) (+ bias) -> activation; fixed summation order
 __global__ void __launch_bounds__(256)
 gemm_reduce_kernel(const float* __restrict__ partial, uint32_t splits, uint32_t M, uint32_t N, uint32_t ldc, float alpha, float beta,
@@ -756,6 +994,10 @@ int gemm_tc_launch(dsb200_ctx* ctx, const float* A, int aMN, uint32_t lda, const
         DSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_reg_kernel<false, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, RSMEM_BYTES));
         DSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_reg_kernel<true, false, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, RSMEM_BYTES));
         DSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_reg_kernel<true, true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, RSMEM_BYTES));
+        DSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_ts_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES));
+        DSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_ts_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES));
+        DSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_ts_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES));
+        DSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_ts_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES));
         attrSet = true;
     }
     Args a;
@@ -793,11 +1035,21 @@ int gemm_tc_launch(dsb200_ctx* ctx, const float* A, int aMN, uint32_t lda, const
         a.partial = ctx->dGemmWs;
     }
     const uint32_t grid = min(sms, tilesMN * splits);
-    // operand path: measured on the three output-layer GEMMs of BASELINE config 2 (gpurun_out/gemm_debug_matrix.log), the
-    // register loader wins when an operand is MN-major (forward 92 -> 82 us, weight gradient 97 -> 80 us) and loses
-    // slightly when both are K-major with 8-byte rows (input delta 85 -> 90 us)
-    const bool regLoader = ctx->gemmLoader < 0 ? (aMN || bMN) : ctx->gemmLoader >= 1;
-    if (regLoader) {
+    // operand path (option "gemm_loader"): measured on the three output-layer GEMMs of BASELINE config 2
+    // (gpurun_out/gemm_debug_matrix2.log, us per launch: forward / weight gradient / input delta)
+    //   0 cp.async + split warps      92.5 / 96.6 / 85.1
+    //   1 register loader             82.4 / 80.3 / 90.6
+    //   2 A through tensor memory     81.0 / 67.7 / 65.5     <- default (-1)
+    const bool regLoader = ctx->gemmLoader == 1;
+    if (ctx->gemmLoader == 2 || ctx->gemmLoader < 0) {
+        if (aMN) {
+            if (bMN) gemm_tc_ts_kernel<true, true><<<grid, THREADS, TS_SMEM_BYTES, ctx->stream>>>(a);
+            else     gemm_tc_ts_kernel<true, false><<<grid, THREADS, TS_SMEM_BYTES, ctx->stream>>>(a);
+        } else {
+            if (bMN) gemm_tc_ts_kernel<false, true><<<grid, THREADS, TS_SMEM_BYTES, ctx->stream>>>(a);
+            else     gemm_tc_ts_kernel<false, false><<<grid, THREADS, TS_SMEM_BYTES, ctx->stream>>>(a);
+        }
+    } else if (regLoader) {
         if (aMN) {
             if (bMN) gemm_tc_reg_kernel<true, true, 2><<<grid, THREADS, RSMEM_BYTES, ctx->stream>>>(a);
             else     gemm_tc_reg_kernel<true, false, 2><<<grid, THREADS, RSMEM_BYTES, ctx->stream>>>(a);

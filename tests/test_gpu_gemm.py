@@ -24,8 +24,8 @@ def ref64(a):
     return a.double().cpu().numpy()
 
 
-@pytest.mark.parametrize("mode,loader", [(0, 1), (2, 1), (2, 0), (1, 1), (1, 0)],
-                         ids=["fp32", "tf32x3-regload", "tf32x3-cpasync", "tf32-regload", "tf32-cpasync"])
+@pytest.mark.parametrize("mode,loader", [(0, -1), (2, -1), (2, 2), (2, 1), (2, 0), (1, 2), (1, 1), (1, 0)],
+                         ids=["fp32", "tf32x3-auto", "tf32x3-tmemA", "tf32x3-regload", "tf32x3-cpasync", "tf32-tmemA", "tf32-regload", "tf32-cpasync"])
 @pytest.mark.parametrize("B,k,n", SHAPES)
 def test_gemm_fwd_dw_dx(ctx, mode, loader, B, k, n):
     g = torch.Generator(device="cuda").manual_seed(B * 7 + k * 3 + n)
@@ -35,7 +35,7 @@ def test_gemm_fwd_dw_dx(ctx, mode, loader, B, k, n):
     C0 = torch.randn(B, n, device="cuda", generator=g)
     ctx.set_option("gemm_mode", mode)
     ctx.set_option("gemm_tc_min_work", 0)                       # force the tensor-core kernel for every shape
-    ctx.set_option("gemm_loader", loader)                       # operand path: registers (default) or cp.async + split warps
+    ctx.set_option("gemm_loader", loader)                       # operand path: -1 per shape, 2 A through tensor memory, 1 registers, 0 cp.async + split warps
     try:
         C = C0.clone()
         ctx.gemm_fwd(A, W, C, beta=1.0)
