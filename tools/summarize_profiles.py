@@ -77,9 +77,9 @@ def traffic(rep, out):
         elif "sparse_wgrad_light" in name: key = "sparse_wgrad_update:light"
         elif "sparse_wgrad_heavy" in name: key = "sparse_wgrad_update:heavy"
         elif "transpose_scatter" in name: key = "sparse_transpose"
-        elif "gemm_tc_kernel<0, 1>" in name or "gemm_tc_kernel<(bool)0, (bool)1>" in name: key = "gemm_fwd_bias_act_tc"
-        elif "gemm_tc_kernel<1, 1>" in name or "gemm_tc_kernel<(bool)1, (bool)1>" in name: key = "gemm_dw_tc"
-        elif "gemm_tc_kernel<0, 0>" in name or "gemm_tc_kernel<(bool)0, (bool)0>" in name: key = "gemm_dx_tc"
+        elif re.search(r"gemm_tc(_ts|_reg)?_kernel<", name):
+            m = re.search(r"gemm_tc(?:_ts|_reg)?_kernel<(?:\(bool\))?([01]), (?:\(bool\))?([01])", name)
+            key = {("0", "1"): "gemm_fwd_bias_act_tc", ("1", "1"): "gemm_dw_tc", ("0", "0"): "gemm_dx_tc"}.get(m.groups()) if m else None
         elif "update_biases" in name: key = "update_biases:max"
         if key: per[key].append(b)
     res = {}
