@@ -250,21 +250,33 @@ struct OperandPlan {
 };
 
 // row loop of the epilogue: staging tile (2 columns per lane) -> global, ACT < 0 = raw copy (split-K partials)
+// `sp` is a shared-space address: the staging tile is reached through pointer arithmetic the compiler cannot trace back to
+// shared memory, and generic LD / ST on it were the slowest instructions of the epilogue (ncu source page, round 1c)
 template <int ACT>
-__device__ __forceinline__ void store_rows(const float* __restrict__ sp, float* __restrict__ o, uint32_t r0, uint32_t rows, uint32_t ldo, uint32_t ncol,
+__device__ __forceinline__ void store_rows(uint32_t sp, float* __restrict__ o, uint32_t r0, uint32_t rows, uint32_t ldo, uint32_t ncol,
                                            bool vec2, float alpha, float beta, float bias0, float bias1, float slope, float ealpha, float lambda)
 {
-#pragma unroll 4
-    for (uint32_t r = r0; r < rows; r += 2, o += 2 * (size_t)ldo, sp += 2 * EPI_LD) {
-        const float2 t = *reinterpret_cast<const float2*>(sp);
-        float x0 = t.x, x1 = t.y;
-        if (ACT >= 0) {
-            x0 = alpha * x0 + bias0; x1 = alpha * x1 + bias1;
-            if (beta != 0.0f) { x0 += beta * o[0]; if (ncol > 1) x1 += beta * o[1]; }
-            x0 = act_apply(ACT, x0, slope, ealpha, lambda); x1 = act_apply(ACT, x1, slope, ealpha, lambda);
+    // four row pairs per trip: the four staging reads are issued back to back, then the four results are finished and stored
+    for (uint32_t r = r0; r < rows; r += 8, o += 8 * (size_t)ldo, sp += 8 * EPI_LD * 4) {
+        float x[4][2];
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            x[u][0] = x[u][1] = 0.0f;
+            if (r + 2 * u < 32) asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(x[u][0]), "=f"(x[u][1]) : "r"(sp + u * 2 * EPI_LD * 4));
         }
-        if (vec2) *reinterpret_cast<float2*>(o) = make_float2(x0, x1);
-        else { o[0] = x0; if (ncol > 1) o[1] = x1; }
+#pragma unroll
+        for (int u = 0; u < 4; u++) {
+            if (r + 2 * u >= rows) break;
+            float* ou = o + (size_t)(2 * u) * ldo;
+            float x0 = x[u][0], x1 = x[u][1];
+            if (ACT >= 0) {
+                x0 = alpha * x0 + bias0; x1 = alpha * x1 + bias1;
+                if (beta != 0.0f) { x0 += beta * ou[0]; if (ncol > 1) x1 += beta * ou[1]; }
+                x0 = act_apply(ACT, x0, slope, ealpha, lambda); x1 = act_apply(ACT, x1, slope, ealpha, lambda);
+            }
+            if (vec2) *reinterpret_cast<float2*>(ou) = make_float2(x0, x1);
+            else { ou[0] = x0; if (ncol > 1) ou[1] = x1; }
+        }
     }
 }
 
@@ -291,7 +303,7 @@ __device__ __forceinline__ void epilogue_role(const Args& a, uint32_t tmem, floa
     // ---------------------------------------------------------------- epilogue warps
     // warp w may read TMEM lanes 32*(w%4) .. +31 = accumulator rows; thread = row
     const uint32_t rowBase = (warp & 3) * 32;
-    float* stage = epiStage + (warp - EPI_WARP0) * (32 * EPI_LD);
+    const uint32_t stageAddr = smem_u32(epiStage + (warp - EPI_WARP0) * (32 * EPI_LD));
     uint32_t seq = 0;
     for (uint32_t t = blockIdx.x; t < numTiles; t += gridDim.x, seq++) {
         const Tile tl = tile_of(a, t);
@@ -308,7 +320,8 @@ __device__ __forceinline__ void epilogue_role(const Args& a, uint32_t tmem, floa
                 float v[32];
                 tmem_ld32(tmem + (rowBase << 16) + acc * BN + half * EPI_COLS, v);
 #pragma unroll
-                for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(stage + lane * EPI_LD + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                for (int j = 0; j < 32; j += 4)
+                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(stageAddr + (lane * EPI_LD + j) * 4), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
             }
             if (half == BN / EPI_COLS - 1) {                                  // accumulator fully read: the MMA warp may reuse it
                 tc_fence_before();
@@ -328,7 +341,7 @@ __device__ __forceinline__ void epilogue_role(const Args& a, uint32_t tmem, floa
                 }
                 const bool vec2 = ncol == 2 && (a.partial ? ((a.N & 1) == 0) : (a.vecC >= 2));
                 float* o = outBase + (size_t)(mBase + rsel) * ldo + nc;
-                const float* sp = stage + rsel * EPI_LD + (lane & 15) * 2;
+                const uint32_t sp = stageAddr + (rsel * EPI_LD + (lane & 15) * 2) * 4;
                 if (a.partial)                        store_rows<-1>(sp, o, rsel, rows, ldo, ncol, vec2, 1.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f);
                 else if (a.act == DSB200_ACT_LINEAR)  store_rows<DSB200_ACT_LINEAR>(sp, o, rsel, rows, ldo, ncol, vec2, a.alpha, a.beta, bias0, bias1, 0.f, 0.f, 0.f);
                 else if (a.act == DSB200_ACT_SIGMOID) store_rows<DSB200_ACT_SIGMOID>(sp, o, rsel, rows, ldo, ncol, vec2, a.alpha, a.beta, bias0, bias1, 0.f, 0.f, 0.f);
@@ -547,6 +560,7 @@ struct RegPlan {
     uint32_t     soff;                         // byte offset of piece 0 inside a panel (the same for every tile)
     uint32_t     v[PIECES];                    // floats of the chunk inside the matrix along mn (K-major: 4 or 0 by row)
     uint32_t     kOff;                         // first k of this thread's chunk inside the panel
+    bool         inside;                       // every chunk of this thread lies inside the matrix along mn (interior tile)
 
     // `warp` = index inside the loader group, 0 .. NW-1
     __device__ __forceinline__ void init(const float* b, uint32_t ld, uint32_t mn0, uint32_t kBegin, uint32_t mnLimit, uint32_t warp, uint32_t lane)
@@ -571,10 +585,36 @@ struct RegPlan {
             for (int i = 0; i < PIECES; i++) v[i] = row + 4 * NW * i < mnLimit ? 4u : 0u;
             ptr = b + (size_t)row * ld + kBegin + c * 4;
         }
+        inside = true;
+#pragma unroll
+        for (int i = 0; i < PIECES; i++) inside = inside && v[i] == 4u;
     }
     // this thread's chunks of the panel that starts at k0; `full`: the whole panel lies inside [kBegin, kEnd)
     __device__ __forceinline__ void load(float4 (&r)[PIECES], uint32_t k0, uint32_t kEnd, bool full, int vec)
     {
+        if (full && inside) {
+            // interior panel (all but the edge tiles and the ragged last k-iteration): straight-line loads, one branch on the
+            // alignment class -- the general path below costs ~10 instructions and 3 branches per chunk, and the loader
+            // warps' serial instruction stream is what paces a k-iteration (ncu source page, round 1c)
+            if (vec == 4) {
+#pragma unroll
+                for (int i = 0; i < PIECES; i++) r[i] = ldg_nc4(ptr + i * pieceStride);
+            } else if (vec == 2) {
+#pragma unroll
+                for (int i = 0; i < PIECES; i++) {
+                    const float2 t0 = ldg_nc2(ptr + i * pieceStride), t1 = ldg_nc2(ptr + i * pieceStride + 2);
+                    r[i] = make_float4(t0.x, t0.y, t1.x, t1.y);
+                }
+            } else {
+#pragma unroll
+                for (int i = 0; i < PIECES; i++) {
+                    const float* p = ptr + i * pieceStride;
+                    r[i] = make_float4(ldg_nc1(p), ldg_nc1(p + 1), ldg_nc1(p + 2), ldg_nc1(p + 3));
+                }
+            }
+            ptr += step;
+            return;
+        }
         if (MN) {
             const bool rowIn = full || (k0 + kOff < kEnd);
 #pragma unroll
@@ -726,7 +766,7 @@ gemm_tc_reg_kernel(const Args a)
 //   warp 16      MMA: aLo*bHi + aHi*bLo + aHi*bHi with A addressed in TMEM, B by shared-memory descriptor
 //   warps 17-20  epilogue (unchanged)
 // Data-array bytes per k-iteration: A 16 (fill) + 16 (read); B 16 + 16 + 32 (stores); MMA 48 (B only) = 144 KB.
-constexpr int TS_SLOTS = 4, TS_SLOT_BYTES = 2 * PANEL, TS_A_WARPS = 8, TS_B_WARPS = 8;
+constexpr int TS_SLOTS = 4, TS_SLOT_BYTES = 2 * PANEL, TS_A_WARPS = 8, TS_B_WARPS = 8, TS_B_DEPTH = 3;
 constexpr int TS_SMEM_BYTES = TS_SLOTS * TS_SLOT_BYTES + EPI_BYTES + 1024;
 constexpr uint32_t TS_ACC_COLS = 2 * BN, TS_A_COLS = 2 * BK, TS_TMEM_COLS = 512;
 static_assert(TS_ACC_COLS + TS_SLOTS * TS_A_COLS <= TS_TMEM_COLS, "tensor memory budget");
@@ -895,17 +935,20 @@ gemm_tc_ts_kernel(const Args a)
             if (lane == 0) mbar_arrive(&fullBar[slot]);
             if (++slot == TS_SLOTS) { slot = 0; parity ^= 1; }
         };
-        float4 b0[PB], b1[PB];
-        bool have0 = more;
-        if (have0) fetch(b0);
-        while (have0) {
-            const bool have1 = more;
-            if (have1) fetch(b1);
-            publish(b0);
-            if (!have1) break;
-            have0 = more;
-            if (have0) fetch(b0);
-            publish(b1);
+        // loads run TS_B_DEPTH - 1 k-iterations ahead of the stores (the first use of a loaded register was the B loaders'
+        // largest single stall with one iteration of prefetch)
+        float4 rb[TS_B_DEPTH][PB];
+        uint32_t pending = 0;
+#pragma unroll
+        for (int s = 0; s < TS_B_DEPTH - 1; s++)
+            if (more) { fetch(rb[s]); pending++; }
+        while (pending) {
+#pragma unroll
+            for (int s = 0; s < TS_B_DEPTH; s++) {
+                if (more) { fetch(rb[(s + TS_B_DEPTH - 1) % TS_B_DEPTH]); pending++; }
+                publish(rb[s]);
+                if (--pending == 0) break;
+            }
         }
     } else if (warp == MMA_WARP) {
         // ---------------------------------------------------------------- MMA issuer

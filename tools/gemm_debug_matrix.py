@@ -24,7 +24,7 @@ def main():
     fns = (("fwd", lambda: ctx.gemm_fwd(A, W, C, beta=0.0)), ("dw", lambda: ctx.gemm_dw(A, D, G, -1.0 / B)), ("dx", lambda: ctx.gemm_dx(D, W, Dp)))
     ctx.set_option("gemm_mode", 2)
     print("loader debug " + " ".join(f"{l:>8s}" for l, _ in fns), flush=True)
-    for loader in (0, 1, 2):
+    for loader in ([int(x) for x in sys.argv[1:]] or [0, 1, 2]):
         for debug in (0, 4, 16, 32, 36, 52):
             if loader == 0 and debug >= 32:
                 continue
