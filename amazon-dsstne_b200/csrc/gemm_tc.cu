@@ -1083,8 +1083,12 @@ int gemm_tc_launch(dsb200_ctx* ctx, const float* A, int aMN, uint32_t lda, const
     //   0 cp.async + split warps      92.5 / 96.6 / 85.1
     //   1 register loader             82.4 / 80.3 / 90.6
     //   2 A through tensor memory     81.0 / 67.7 / 65.5     <- default (-1)
+    //   exception: a K-major A whose rows are far apart (the 1M-column delta of BASELINE config 4, 4 MB between rows): the
+    //   tensor-memory loader reads one row per thread, i.e. 32 pages per load instruction, and measured 23.5 ms against
+    //   15 ms for cp.async on the 1,024 x 1,024 x 1M input-delta GEMM (gpurun_out/bench_c4_1.json, two runs)
+    const bool farRows = !aMN && lda > 65536u;
     const bool regLoader = ctx->gemmLoader == 1;
-    if (ctx->gemmLoader == 2 || ctx->gemmLoader < 0) {
+    if (ctx->gemmLoader == 2 || (ctx->gemmLoader < 0 && !farRows)) {
         if (aMN) {
             if (bMN) gemm_tc_ts_kernel<true, true><<<grid, THREADS, TS_SMEM_BYTES, ctx->stream>>>(a);
             else     gemm_tc_ts_kernel<true, false><<<grid, THREADS, TS_SMEM_BYTES, ctx->stream>>>(a);
