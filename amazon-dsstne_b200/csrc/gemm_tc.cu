@@ -5,29 +5,29 @@
 // tensor core reads, lo = the exact fp32 remainder, and lo*hi + hi*lo + hi*hi accumulate in fp32 in TMEM) or
 // DSB200_GEMM_TF32 (hi*hi only).
 //
-// Persistent kernel, one CTA per SM, 128 x 128 output tiles, 17 warps with separate roles so that no warp's serial
-// chain (wait -> work -> fence -> signal) sits on the critical path of every k-iteration:
-//   warps 0-3    copy:     operand rows are not 16-byte aligned in general (N = 27,278 floats), so TMA tensor maps are
-//                          not usable; each thread copies its 16-byte chunks global -> shared with cp.async (16 / 8 /
-//                          4-byte pieces by alignment, zero fill at the edges) straight into the UMMA layouts of a
-//                          7-deep ring of raw panels and lets the copies signal an mbarrier when they land
-//                          (cp.async.mbarrier.arrive.noinc) -- the copy warps never wait for data.
-//   warps 4-11   split:    two groups taking alternate k-iterations: wait for the panel, derive the "lo" panel of the
-//                          3xTF32 split (elementwise, a - trunc_tf32(a)) into a 3-deep ring, make both visible to the
-//                          tensor core (fence.proxy.async) and hand the iteration to the MMA warp.
-//   warp 12      MMA:      TMEM allocation; lane 0 issues every tcgen05.mma (3 per K = 8 step) into one of two 128-column
-//                          accumulators and releases ring slots / publishes accumulators with tcgen05.commit.
-//   warps 13-16  epilogue: TMEM -> registers -> padded shared-memory tile -> row-contiguous global stores with the
-//                          alpha / beta / bias / activation epilogue, overlapped with the next tile's main loop.
-// Shared-memory layouts of one 128 x 16 operand panel (16-byte chunks = 4 floats along the contiguous dimension):
-//   K-major operand (k contiguous in memory): no swizzle, core matrix = 8 mn-rows x 16 bytes,
-//       chunk(mn, kc) at (mn/8)*128 + (mn%8)*16 + kc*2048                                   LBO=2048 SBO=128
-//       lanes of a copy: 8 rows x 4 chunks -- a quarter-warp writes one whole core matrix (conflict free).
-//   MN-major operand (mn contiguous in memory): the 32-bit "128B, 32B-base" swizzle, the only layout the tensor core
+// Persistent kernels, one CTA per SM, 128 x 128 output tiles, 128 x 32 operand panels per k-iteration, 21 warps with
+// separate roles (loaders / one MMA-issuing warp / four epilogue warps), two 128-column accumulators in tensor memory so
+// that the epilogue of a tile overlaps the main loop of the next.  Operand rows are not 16-byte aligned in general
+// (N = 27,278 floats), so TMA tensor maps do not apply; three operand paths exist (option "gemm_loader"), in the order
+// they were written -- each was measured against the one before (profiles/r1c_gemm_smem_pipe.md):
+//   gemm_tc_kernel      (0) cp.async straight into the UMMA layouts (8 copy warps), 8 split warps derive the lo panels
+//                           in shared memory
+//   gemm_tc_reg_kernel  (1) 16 loader warps: ld.global.nc -> registers -> hi / lo -> st.shared.v4 (no cp.async, no
+//                           second pass over shared memory)
+//   gemm_tc_ts_kernel   (2, default) the A operand never enters shared memory: 8 A-loader warps write hi / lo with
+//                           tcgen05.st into a ring in TENSOR MEMORY behind the accumulators and the MMAs take A from
+//                           there; 8 B-loader warps fill shared memory as in (1)
+// The default (-1) is (2), except for a K-major A whose rows are more than 256 KB apart (see gemm_tc_launch).
+//
+// Shared-memory layouts of one 128 x 32 operand panel (16-byte chunks = 4 floats along the contiguous dimension):
+//   K-major operand (k contiguous in memory): the standard 128-byte swizzle, rows of 32 floats,
+//       chunk(mn, kc) at (mn/8)*1024 + (mn%8)*128 + ((kc ^ (mn%8))*16)                      layout 2, SBO = 1024
+//   MN-major operand (mn contiguous in memory): the "128B swizzle, 32-byte base" layout, the only one the tensor core
 //       accepts for transposed tf32 operands (every other layout type returns zeros -- measured, tools/umma_probe.cu):
-//       atom = 4 k-rows x 128 bytes (32 mn), 32-byte granules XOR-ed with k%4,
-//       chunk(k, mc) at (mc/8)*2048 + (k/4)*512 + (k%4)*128 + ((((mc%8)/2) ^ (k%4))*32) + (mc%2)*16   LBO=2048 SBO=512
-//       lanes of a copy: 4 k-rows x 8 chunks (128 contiguous bytes per row) -- conflict free as well.
+//       atom = 32 mn x 32 k = 4,096 bytes, 4 k-rows x 128 bytes per 512-byte group, 32-byte granules XOR-ed with k%4,
+//       chunk(k, mc) at (mc/8)*4096 + (k/4)*512 + (k%4)*128 + ((((mc%8)/2) ^ (k%4))*32) + (mc%2)*16   layout 1, LBO = 4096, SBO = 512
+// Tensor-memory layout of the A ring (tools/umma_ts_probe.cu): lane = row m, one tf32 word per column, consecutive
+// columns = consecutive k; one K = 8 MMA step advances the A address by 8 columns.
 // Split-K (K = 27,278 for the input-delta GEMM of the output layer) writes raw partial tiles to a workspace that
 // gemm_reduce_kernel sums in a fixed order -- deterministic, no float atomics.
 #include "common.cuh"
