@@ -256,6 +256,10 @@ class Context:
         self.check(lib().dsb200_topk_kv(self.h, _ptr(key), _ptr(value), C.c_uint32(b), C.c_uint32(width), C.c_uint32(k),
                                         _ptr(out_key), _ptr(out_val)))
 
+    def topk_offset(self, value, offset):
+        """value[i] += offset in place (local column ids -> global ids before the cross-rank merge)."""
+        self.check(lib().dsb200_topk_offset(self.h, _ptr(value), C.c_uint64(value.numel()), C.c_uint32(offset)))
+
 
 class DeviceCsr:
     """A sparse dataset resident in HBM, in DSSTNE's layout (E/NNTypes.h:213-236)."""

@@ -14,6 +14,8 @@
 //   pass 2  CTA = row: the same selection over the segs*k candidates.
 // Rule (fixed, unlike the reference's arrival-order ties): descending key, ties by ascending
 // column; a candidate must be > -MAX_VALUE; unused slots hold (-MAX_VALUE, 0) (E/NNTypes.h:49).
+#include <algorithm>
+
 #include "common.cuh"
 #include "launch.h"
 
@@ -318,9 +320,28 @@ static int topk_impl(dsb200_ctx* ctx, const float* key, const uint32_t* value, u
     return 0;
 }
 
+// value[i] += offset: turns the column ids of a rank's local top-K into global ids before the cross-rank merge
+__global__ void __launch_bounds__(256)
+topk_offset_kernel(uint32_t* __restrict__ value, uint64_t n, uint32_t offset)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (uint64_t)gridDim.x * blockDim.x) value[i] += offset;
+}
+
 }  // namespace dsb
 
 extern "C" {
+
+int dsb200_topk_offset(dsb200_ctx* ctx, uint32_t* pValue, uint64_t n, uint32_t offset)
+{
+    DSB_PROFILE(ctx, "topk_offset");
+    if (!ctx || !pValue) return dsb::fail(ctx, DSB200_EINVAL, "topk_offset: null argument");
+    if (!n || !offset) return 0;
+    const unsigned blocks = (unsigned)std::min<uint64_t>((n + 255) / 256, (uint64_t)ctx->numSMs * 8);
+    dsb::topk_offset_kernel<<<blocks, 256, 0, ctx->stream>>>(pValue, n, offset);
+    dsb::count_launch();
+    DSB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
 
 int dsb200_topk(dsb200_ctx* ctx, const float* pScores, uint32_t batch, uint32_t width, uint32_t k,
                 const uint64_t* fs, const uint64_t* fe, const uint32_t* fi, float* pOutKey, uint32_t* pOutValue)

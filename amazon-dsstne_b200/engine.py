@@ -204,6 +204,13 @@ class Network:
         _check(lib().dsb200_network_topk(self.h, layer.encode(), C.c_uint32(k), None if filt is None else filt.h, _p(key), _p(val)))
         return key, val
 
+    def topk_global(self, layer, k, batch, filt=None):
+        """Model parallel: top-K of the whole layer with global unit ids, the same on every rank."""
+        key = np.empty((batch, k), dtype=np.float32)
+        val = np.empty((batch, k), dtype=np.uint32)
+        _check(lib().dsb200_network_topk_global(self.h, layer.encode(), C.c_uint32(k), None if filt is None else filt.h, _p(key), _p(val)))
+        return key, val
+
     def set_weights(self, src, dst, W=None, b=None):
         W = None if W is None else np.ascontiguousarray(W, dtype=np.float32)
         b = None if b is None else np.ascontiguousarray(b, dtype=np.float32)

@@ -605,6 +605,34 @@ void NNNetwork::CalculateTopK(const string& layer, uint32_t k, GpuBuffer<NNFloat
     CalculateTopKFiltered(layer, k, NULL, pbKey, pbValue);
 }
 
+// SURVEY 8e "Top-K, P > 1": local top-K on [batch][N/P] (K' = K is sufficient for exactness) -> all-gather of (score, global id)
+// [batch][K] -> final top-K over the P * K candidates of every row, on every rank.  Order: descending score, ties by ascending
+// global id -- the gathered row is rank-major and every rank's list is already in that order, so the positional tie-break of
+// dsb200_topk_kv is the global one.
+void NNNetwork::CalculateTopKGlobal(const string& layer, uint32_t k, NNDataSetBase* pFilter, GpuBuffer<NNFloat>* pbKey, GpuBuffer<uint32_t>* pbValue)
+{
+    NNLayer* pLayer = GetLayer(layer);
+    if (!pLayer) { if (getGpu()._id == 0) printf("NNNetwork::CalculateTopKGlobal: Unknown layer %s.\n", layer.c_str()); return; }
+    const uint32_t P = (uint32_t)getGpu()._numprocs;
+    if (P <= 1 || pLayer->_localStride == pLayer->_stride) { CalculateTopKFiltered(layer, k, pFilter, pbKey, pbValue); return; }
+    uint32_t batch = _batch;
+    if (_position + batch > _examples) batch = _examples - _position;
+    if (!pbKey || !pbValue || pbKey->_length < (size_t)batch * k || pbValue->_length < (size_t)batch * k)
+        throw DsbEngineError("NNNetwork::CalculateTopKGlobal: output buffers are too small");
+    const size_t local = (size_t)batch * k, full = local * P;
+    GpuBuffer<NNFloat> localKey(local), fullKey(full);
+    GpuBuffer<uint32_t> localValue(local), fullValue(full);
+    CalculateTopKFiltered(layer, k, pFilter, &localKey, &localValue);
+    dsb200_ctx* ctx = getGpu()._ctx;
+    getGpu().Check(dsb200_topk_offset(ctx, localValue._pDevData, local, pLayer->_minX), "dsb200_topk_offset");
+    // [batch][k] of rank r lands in columns [k r, k (r + 1)) of [batch][P k]; ids travel as raw 32-bit words
+    getGpu().Check(dsb200_all_gather(ctx, batch, P * k, localKey._pDevData, fullKey._pDevData), "dsb200_all_gather (top-K scores)");
+    getGpu().Check(dsb200_all_gather(ctx, batch, P * k, reinterpret_cast<const float*>(localValue._pDevData),
+                                     reinterpret_cast<float*>(fullValue._pDevData)), "dsb200_all_gather (top-K ids)");
+    getGpu().Check(dsb200_topk_kv(ctx, fullKey._pDevData, fullValue._pDevData, batch, P * k, k, pbKey->_pDevData, pbValue->_pDevData), "dsb200_topk_kv");
+    getGpu().Check(dsb200_ctx_sync(ctx), "dsb200_ctx_sync");          // the temporaries above are freed on return
+}
+
 void NNNetwork::CalculateTopKFiltered(const string& layer, uint32_t k, NNDataSetBase* pFilter, GpuBuffer<NNFloat>* pbKey, GpuBuffer<uint32_t>* pbValue)
 {
     NNLayer* pLayer = GetLayer(layer);

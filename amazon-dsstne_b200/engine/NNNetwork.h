@@ -89,6 +89,9 @@ public:
     void CalculateTopK(const string& layer, uint32_t k, GpuBuffer<NNFloat>* pbKey, GpuBuffer<uint32_t>* pbValue);
     // top-K with the exclusion filter applied on the device (replaces the host round trip of U/NNRecsGenerator.cpp:132-150)
     void CalculateTopKFiltered(const string& layer, uint32_t k, NNDataSetBase* pFilter, GpuBuffer<NNFloat>* pbKey, GpuBuffer<uint32_t>* pbValue);
+    // model parallel: every rank's local top-K (local ids + this rank's first unit) is all-gathered and merged, so that every rank
+    // holds the top-K of the WHOLE layer with global ids -- the role of the MPI gather + host merge of U/NNRecsGenerator.cpp:150-244
+    void CalculateTopKGlobal(const string& layer, uint32_t k, NNDataSetBase* pFilter, GpuBuffer<NNFloat>* pbKey, GpuBuffer<uint32_t>* pbValue);
     bool LockWeights(const string& inputLayer, const string& outputLayer);
     bool UnlockWeights(const string& inputLayer, const string& outputLayer);
     void SetBatch(uint32_t batch);

@@ -329,6 +329,20 @@ int dsb200_network_topk(dsb200_network* n, const char* layer, uint32_t k, dsb200
     DSB_ENGINE_CATCH
 }
 
+int dsb200_network_topk_global(dsb200_network* n, const char* layer, uint32_t k, dsb200_dataset* filter, float* outKey, uint32_t* outValue)
+{
+    DSB_ENGINE_TRY
+    NNNetwork* net = NET(n);
+    uint32_t batch = net->GetBatch();
+    if (net->GetPosition() + batch > net->GetExamples()) batch = net->GetExamples() - net->GetPosition();
+    GpuBuffer<NNFloat> key((size_t)batch * k);
+    GpuBuffer<uint32_t> val((size_t)batch * k);
+    net->CalculateTopKGlobal(layer, k, DS(filter), &key, &val);
+    key.Download(outKey);
+    val.Download(outValue);
+    DSB_ENGINE_CATCH
+}
+
 int dsb200_network_set_weights(dsb200_network* n, const char* inputLayer, const char* outputLayer, const float* w, uint64_t nW, const float* b, uint64_t nB)
 {
     DSB_ENGINE_TRY

@@ -237,6 +237,9 @@ int dsb200_topk(dsb200_ctx*, const float* pScores, uint32_t batch, uint32_t widt
                 float* pOutKey, uint32_t* pOutValue);
 int dsb200_topk_kv(dsb200_ctx*, const float* pKey, const uint32_t* pValue, uint32_t batch, uint32_t width, uint32_t k,
                    float* pOutKey, uint32_t* pOutValue);
+/* pValue[i] += offset for i < n: local column ids -> global ids (the reference rebuilds them on the host as
+ * gpuId * localStride + local, U/NNRecsGenerator.cpp:214) before the per-rank lists are merged with dsb200_topk_kv */
+int dsb200_topk_offset(dsb200_ctx*, uint32_t* pValue, uint64_t n, uint32_t offset);
 
 /* ------------------------------------------------------------------ denoising randoms ("next" row 4)
  * replaces the whole-dataset curandGenerateUniform fill of NNDataSet::GenerateDenoisingData

@@ -91,6 +91,9 @@ int dsb200_network_train_step(dsb200_network* n, uint32_t position, float alpha,
 int dsb200_network_predict_batch(dsb200_network* n);
 /* NNNetwork::CalculateTopK (+ device-side exclusion filter when filter != NULL); HOST outputs [batch][k] */
 int dsb200_network_topk(dsb200_network* n, const char* layer, uint32_t k, dsb200_dataset* filter, float* outKey, uint32_t* outValue);
+/* model parallel: top-K of the whole layer with GLOBAL unit ids on every rank (what U/NNRecsGenerator.cpp:150-244 assembles on
+ * the host from the per-GPU lists); identical to dsb200_network_topk on one GPU */
+int dsb200_network_topk_global(dsb200_network* n, const char* layer, uint32_t k, dsb200_dataset* filter, float* outKey, uint32_t* outValue);
 
 /* NNWeight::SetWeights / SetBiases / GetWeights / GetBiases; NNLayer::GetUnits / GetDeltas (HOST buffers).
  * set_* take the FULL [inputStride][outputStride] matrix; get_* return this rank's shard (see NNWeight.h). */

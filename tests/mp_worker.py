@@ -60,6 +60,23 @@ def main():
     ds_out.load_sparse(s_start, s_end, s_index)
     stream_loss = net.train_step(0, hp["alpha"], hp["lam"], hp["lam1"], hp["mu"], hp["mu1"])
 
+    # model-parallel top-K (MP_TOPK = K): the engine's own output scores, re-assembled from the shards, give the expected global
+    # top-K through the oracle; NNNetwork::CalculateTopKGlobal must return exactly that on EVERY rank (exclusion filter = input set)
+    topk, topk_ok = int(os.environ.get("MP_TOPK", "0")), None
+    if topk:
+        net.set_position(0)
+        net.predict_batch()
+        units = net.get_units("Output")
+        units = np.asarray(units, dtype=np.float32).reshape(batch, -1)
+        got_k, got_v = net.topk_global("Output", topk, batch, filt=ds_in)
+        parts = [None] * world
+        dist.all_gather_object(parts, (units, got_k, got_v))
+        if rank == 0:
+            full = np.ascontiguousarray(np.concatenate([p[0] for p in parts], axis=1))
+            sl = slice(0, batch)
+            want_k, want_v = orc.topk(full, topk, filt=(s_start[sl], s_end[sl], s_index))
+            topk_ok = all(np.array_equal(p[1], want_k) and np.array_equal(p[2], want_v) for p in parts)
+
     # re-assemble the sharded weights on rank 0
     shards = []
     for i in range(len(sizes) - 1):
@@ -101,7 +118,7 @@ def main():
             errs[f"b{i}"] = rel_err(fullb, onet.b(i))
         out = {"world": world, "losses": losses, "want_losses": want_losses, "errs": errs,
                "loss_err": max(abs(a - b) / abs(b) for a, b in zip(losses, want_losses)),
-               "stream_loss_err": abs(stream_loss - want_stream) / abs(want_stream)}
+               "stream_loss_err": abs(stream_loss - want_stream) / abs(want_stream), "topk_ok": topk_ok}
     net.close()
     dist.barrier()
     dist.destroy_process_group()

@@ -2,6 +2,8 @@
 on the same seeded inputs.  Integer outputs must be bit-exact; fp32 outputs within 1e-5 relative
 (the tolerance BASELINE.json:north_star states), measured against max(|ref|, 1e-3*max|ref|).
 """
+import os
+
 import numpy as np
 import pytest
 
@@ -478,6 +480,36 @@ def test_topk_kv_merge_variant(ctx, orc, dsb):
     ctx.sync()
     np.testing.assert_array_equal(host(ok), ref_k)
     np.testing.assert_array_equal(u32(ov), ref_v)
+
+
+@pytest.mark.skipif(not os.environ.get("DSB200_RUN_UNVERIFIED"), reason="not yet run on a GPU (round 1 budget); set DSB200_RUN_UNVERIFIED=1")
+@pytest.mark.parametrize("shards", [2, 8])
+def test_topk_sharded_merge_on_one_gpu(ctx, orc, dsb, shards):
+    """The model-parallel top-K scheme (NNNetwork::CalculateTopKGlobal) with the column shards of `shards` ranks taken one
+    after the other on ONE GPU: local dsb200_topk, dsb200_topk_offset, rank-major concatenation, dsb200_topk_kv -- bit-exact
+    against the oracle's top-K of the whole rows, heavy ties included (CPU restatement: tests/test_topk_global_scheme.py)."""
+    import torch
+    rng = np.random.default_rng(79)
+    B, N, K = 32, 20011, 64
+    scores = rng.integers(0, 40, size=(B, N)).astype(np.float32)
+    want_k, want_v = orc.topk(scores, K)
+    d = dev(scores)
+    keys, vals = [], []
+    for r in range(shards):
+        lo, hi = orc.shard_range(N, r, shards)
+        ok = torch.empty((B, K), dtype=torch.float32, device="cuda")
+        ov = torch.empty((B, K), dtype=torch.int32, device="cuda")
+        ctx.topk(d[:, lo:hi].contiguous(), K, ok, ov)
+        ctx.topk_offset(ov, lo)
+        keys.append(ok)
+        vals.append(ov)
+    fk, fv = torch.cat(keys, dim=1).contiguous(), torch.cat(vals, dim=1).contiguous()
+    ok = torch.empty((B, K), dtype=torch.float32, device="cuda")
+    ov = torch.empty((B, K), dtype=torch.int32, device="cuda")
+    ctx.topk_kv(fk, fv, K, ok, ov)
+    ctx.sync()
+    np.testing.assert_array_equal(host(ok), want_k)
+    np.testing.assert_array_equal(u32(ov), want_v)
 
 
 @pytest.mark.parametrize("act", [0, 1, 2, 10, 12], ids=["sigmoid", "tanh", "relu", "elu", "selu"])

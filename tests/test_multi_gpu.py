@@ -44,3 +44,16 @@ def test_model_parallel_momentum_odd_and_uneven_units(world):
     assert r["loss_err"] < 1e-5, r
     for k, v in r["errs"].items():
         assert v < (5e-5 if k.startswith("b") else 1e-5), (k, v, r)
+
+
+# Written at the end of round 1 after the GPU budget was spent: the scheme is pinned bit-exactly on the CPU
+# (tests/test_topk_global_scheme.py) but this GPU path has not run yet -- enable with DSB200_RUN_UNVERIFIED=1 and drop the
+# gate after the first green run.
+unverified = pytest.mark.skipif(not os.environ.get("DSB200_RUN_UNVERIFIED"), reason="not yet run on GPUs (round 1 budget); set DSB200_RUN_UNVERIFIED=1")
+
+
+@unverified
+@pytest.mark.parametrize("world", [2, 4])
+def test_model_parallel_topk_global_matches_single_process(world):
+    r = run_world(world, {"MP_MODE": "0", "MP_TOPK": "50"}, port=29651 + world)
+    assert r["topk_ok"] is True, r
