@@ -30,6 +30,8 @@
 // columns = consecutive k; one K = 8 MMA step advances the A address by 8 columns.
 // Split-K (K = 27,278 for the input-delta GEMM of the output layer) writes raw partial tiles to a workspace that
 // gemm_reduce_kernel sums in a fixed order -- deterministic, no float atomics.
+#include <type_traits>
+
 #include "common.cuh"
 #include "launch.h"
 
@@ -835,7 +837,59 @@ struct TmemAPlan {
     }
 };
 
-template <bool AMN, bool BMN>
+// ---- option "gemm_loader" = 3 (EXPERIMENTAL, written at the end of round 1 without GPU time left: not yet run) -------------------
+// K-major A read COALESCED for the tcgen05.st.16x256b shape, whose register mapping was probed on the B200
+// (tools/umma_st16x256_probe.cu):  .x2 register s of thread t -> TMEM lane t / 4 + 8 * ((s >> 1) & 1), column 2 * (t % 4) + 8 * (s >> 2)
+// + (s & 1); the instruction covers 16 lanes, lanes 16-31 of the quadrant take a second store at address + (16 << 16).
+// Four consecutive threads therefore hold one 32-byte sector of a row and a load instruction touches 8 rows (8 pages when
+// rows are far apart) instead of the 32 of the row-per-thread plan above -- the C4 input-delta case of gemm_tc_launch.
+// r[8 j + s]: row t / 4 + 8 * (2 j + ((s >> 1) & 1)) of the quadrant, k = 16 khalf + 2 (t % 4) + 8 (s >> 2) + (s & 1).
+__device__ __forceinline__ void tmem_st16x256_x2(uint32_t taddr, const uint32_t* r)
+{
+    asm volatile("tcgen05.st.sync.aligned.16x256b.x2.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+struct TmemAPlanCoal {
+    const float* ptr;                          // (row m0 + 32 q + t / 4, k = kBegin + 16 khalf + 2 (t % 4)) in the next k-iteration to load
+    size_t       ld8;                          // floats between row groups (8 rows)
+    uint32_t     kOff, rowMask;                // first k of the thread inside the panel / bit g: row t / 4 + 8 g is inside the matrix
+    __device__ __forceinline__ void init(const float* A, uint32_t lda, uint32_t m0, uint32_t kBegin, uint32_t M, uint32_t quadrant, uint32_t khalf, uint32_t lane)
+    {
+        const uint32_t m = m0 + quadrant * 32 + (lane >> 2);
+        kOff = khalf * 16 + 2 * (lane & 3);
+        ld8 = (size_t)8 * lda;
+        rowMask = 0;
+#pragma unroll
+        for (uint32_t g = 0; g < 4; g++) if (m + 8 * g < M) rowMask |= 1u << g;
+        ptr = A + (size_t)m * lda + kBegin + kOff;                               // may point past the matrix: only dereferenced when valid
+    }
+    __device__ __forceinline__ void load(uint32_t (&r)[16], uint32_t k0, uint32_t kEnd, int vec)
+    {
+        if (rowMask == 15u && k0 + BK <= kEnd && vec >= 2) {                     // interior panel: eight straight 64-bit loads
+#pragma unroll
+            for (int j = 0; j < 2; j++)
+#pragma unroll
+                for (int s = 0; s < 8; s += 2) {
+                    const float2 t = ldg_nc2(ptr + (2 * j + ((s >> 1) & 1)) * ld8 + 8 * (s >> 2));
+                    r[8 * j + s] = __float_as_uint(t.x); r[8 * j + s + 1] = __float_as_uint(t.y);
+                }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 2; j++)
+#pragma unroll
+                for (int s = 0; s < 8; s += 2) {
+                    const uint32_t g = 2 * j + ((s >> 1) & 1), kk = k0 + kOff + 8 * (s >> 2);
+                    const float* p = ptr + g * ld8 + 8 * (s >> 2);
+                    const uint32_t n = (((rowMask >> g) & 1u) && kk < kEnd) ? min(2u, kEnd - kk) : 0u;
+                    r[8 * j + s] = n > 0 ? ldg_nc1u(p) : 0u;
+                    r[8 * j + s + 1] = n > 1 ? ldg_nc1u(p + 1) : 0u;
+                }
+        }
+        ptr += BK;
+    }
+};
+
+template <bool AMN, bool BMN, bool COAL = false>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_ts_kernel(const Args a)
 {
@@ -864,7 +918,8 @@ gemm_tc_ts_kernel(const Args a)
     if (warp < TS_A_WARPS) {
         // ---------------------------------------------------------------- A loaders: global -> registers -> tensor memory
         const uint32_t quadrant = warp & 3, khalf = warp >> 2;                    // a warp may only touch TMEM lanes 32 * (warp % 4) ..
-        TmemAPlan<AMN> pa;
+        constexpr bool COALESCED = COAL && !AMN;                                  // MN-major A is coalesced in the row-per-thread plan already
+        typename std::conditional<COALESCED, TmemAPlanCoal, TmemAPlan<AMN>>::type pa;
         uint32_t lt = blockIdx.x, lkt = 0, slot = 0, parity = 1;
         Tile ltl = tile_of(a, min(lt, numTiles - 1));
         bool more = lt < numTiles;
@@ -884,11 +939,13 @@ gemm_tc_ts_kernel(const Args a)
             uint32_t hi[16];
 #pragma unroll
             for (int e = 0; e < 16; e++) hi[e] = r[e] & 0xFFFFE000u;
-            tmem_st16(ta, hi);
+            if (COALESCED) { tmem_st16x256_x2(ta, hi); tmem_st16x256_x2(ta + (16u << 16), hi + 8); }
+            else tmem_st16(ta, hi);
             if (lo) {
 #pragma unroll
                 for (int e = 0; e < 16; e++) hi[e] = __float_as_uint(__uint_as_float(r[e]) - __uint_as_float(hi[e]));
-                tmem_st16(ta + BK, hi);
+                if (COALESCED) { tmem_st16x256_x2(ta + BK, hi); tmem_st16x256_x2(ta + BK + (16u << 16), hi + 8); }
+                else tmem_st16(ta + BK, hi);
             }
             asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
             tc_fence_before();
@@ -1041,6 +1098,8 @@ int gemm_tc_launch(dsb200_ctx* ctx, const float* A, int aMN, uint32_t lda, const
         DSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_ts_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES));
         DSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_ts_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES));
         DSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_ts_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES));
+        DSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_ts_kernel<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES));
+        DSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_ts_kernel<false, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES));
         attrSet = true;
     }
     Args a;
@@ -1088,7 +1147,10 @@ int gemm_tc_launch(dsb200_ctx* ctx, const float* A, int aMN, uint32_t lda, const
     //   15 ms for cp.async on the 1,024 x 1,024 x 1M input-delta GEMM (gpurun_out/bench_c4_1.json, two runs)
     const bool farRows = !aMN && lda > 65536u;
     const bool regLoader = ctx->gemmLoader == 1;
-    if (ctx->gemmLoader == 2 || (ctx->gemmLoader < 0 && !farRows)) {
+    if (ctx->gemmLoader == 3 && !aMN) {                                           // experimental coalesced tensor-memory A loader
+        if (bMN) gemm_tc_ts_kernel<false, true, true><<<grid, THREADS, TS_SMEM_BYTES, ctx->stream>>>(a);
+        else     gemm_tc_ts_kernel<false, false, true><<<grid, THREADS, TS_SMEM_BYTES, ctx->stream>>>(a);
+    } else if (ctx->gemmLoader >= 2 || (ctx->gemmLoader < 0 && !farRows)) {
         if (aMN) {
             if (bMN) gemm_tc_ts_kernel<true, true><<<grid, THREADS, TS_SMEM_BYTES, ctx->stream>>>(a);
             else     gemm_tc_ts_kernel<true, false><<<grid, THREADS, TS_SMEM_BYTES, ctx->stream>>>(a);

@@ -8,6 +8,8 @@ Stated bounds (helpers.rel_err = max |a-b| / (|b| + rms(b))):
   DSB200_GEMM_TF32    tcgen05, one tf32 MMA per k-step                  3e-3
 Shapes: BASELINE.json config 2's output layer (1,024 x 128 x 27,278), its hidden layers, and ragged / odd sizes that
 exercise zero fill, 8- and 4-byte copy paths and partial tiles."""
+import os
+
 import numpy as np
 import pytest
 import torch
@@ -24,8 +26,15 @@ def ref64(a):
     return a.double().cpu().numpy()
 
 
-@pytest.mark.parametrize("mode,loader", [(0, -1), (2, -1), (2, 2), (2, 1), (2, 0), (1, 2), (1, 1), (1, 0)],
-                         ids=["fp32", "tf32x3-auto", "tf32x3-tmemA", "tf32x3-regload", "tf32x3-cpasync", "tf32-tmemA", "tf32-regload", "tf32-cpasync"])
+LOADERS = [(0, -1), (2, -1), (2, 2), (2, 1), (2, 0), (1, 2), (1, 1), (1, 0)]
+LOADER_IDS = ["fp32", "tf32x3-auto", "tf32x3-tmemA", "tf32x3-regload", "tf32x3-cpasync", "tf32-tmemA", "tf32-regload", "tf32-cpasync"]
+if os.environ.get("DSB200_RUN_UNVERIFIED"):
+    # gemm_loader = 3 (coalesced tensor-memory A loader on tcgen05.st.16x256b) was written after round 1's GPU budget was spent
+    LOADERS += [(2, 3), (1, 3)]
+    LOADER_IDS += ["tf32x3-tmemA16x256", "tf32-tmemA16x256"]
+
+
+@pytest.mark.parametrize("mode,loader", LOADERS, ids=LOADER_IDS)
 @pytest.mark.parametrize("B,k,n", SHAPES)
 def test_gemm_fwd_dw_dx(ctx, mode, loader, B, k, n):
     g = torch.Generator(device="cuda").manual_seed(B * 7 + k * 3 + n)

@@ -1,5 +1,6 @@
 """Bring-up timing matrix for the tcgen05 GEMM (run on the GPU box): the three output-layer GEMMs of BASELINE config 2
-under every operand loader and the kernel's bring-up switches (option "gemm_debug": 1 no proxy fence, 4 no MMA, 8 no lo
+under every operand loader and the kernel's bring-up switches (loaders: 0 cp.async, 1 registers, 2 tensor-memory A, 3 coalesced tensor-memory A -- pass the ones to time as
+arguments; option "gemm_debug": 1 no proxy fence, 4 no MMA, 8 no lo
 pass, 16 no stores, 32 no global loads).  Results of the switched runs are wrong by construction -- only the time matters:
 it tells which stage of the pipeline paces a k-iteration.  Not a test."""
 import os
