@@ -99,7 +99,17 @@ int  dsb200_ctx_set_stream(dsb200_ctx* ctx, void* cudaStream);
 int  dsb200_ctx_set_params(dsb200_ctx* ctx, const dsb200_params* p);
 void dsb200_params_default(dsb200_params* p);                 /* E/NNNetwork.cpp:27-58 */
 int  dsb200_ctx_reserve(dsb200_ctx* ctx, uint32_t maxBatch, size_t partialFloats);
-int  dsb200_ctx_set_option(dsb200_ctx* ctx, const char* name, int value);  /* "no_tma", "transpose_sort", "gemm_mode" */
+/* Options (all have working defaults; the alternative kernels stay selectable because the parity tests run every one of them):
+ *   "gemm_mode"          DSB200_GEMM_FP32 (default: cuBLAS SGEMM, the 1e-5 parity mode) | DSB200_GEMM_TF32 | DSB200_GEMM_TF32X3
+ *   "gemm_loader"        operand path of the tcgen05 GEMM: -1 per shape (default) | 0 cp.async + split warps | 1 registers ->
+ *                        shared memory | 2 A operand through tensor memory | 3 the same with a coalesced A loader (experimental)
+ *   "gemm_tc_min_work"   tiles x k-iterations below which a GEMM stays off the tensor-core kernel (default 2048)
+ *   "gemm_splits"        split-K factor, 0 = automatic;   "gemm_debug"  bring-up switches of csrc/gemm_tc.cu (wrong results)
+ *   "transpose_sort"     1 = sort every column of the transposed matrix (canonical order for bit-exact comparison)
+ *   "fast_math"          1 (default) = MUFU exp / log / reciprocal in the output pass, as the reference (-use_fast_math); 0 = libm grade
+ *   "no_tma" / "z_staged_kernel" / "wgrad_tile_kernel" / "output_tile_kernel" / "no_small_dense"   earlier kernels of a family
+ *   "profile"            1 = bracket every entry point with CUDA events (dsb200_profile_report)                              */
+int  dsb200_ctx_set_option(dsb200_ctx* ctx, const char* name, int value);
 int  dsb200_ctx_sync(dsb200_ctx* ctx);
 const char* dsb200_last_error(dsb200_ctx* ctx);
 uint64_t dsb200_launch_count(void);      /* kernels of this library launched so far */
