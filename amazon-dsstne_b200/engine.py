@@ -72,6 +72,17 @@ def sync():
     _check(lib().dsb200_engine_sync())
 
 
+def describe_json(json_text, datasets=None):
+    """HOST ONLY: what the JSON (LDL) loader understands of a network description, one line per network / layer / weight.
+    `datasets` = {name: width} for auto-sized layers.  Raises EngineError exactly where LoadNeuralNetworkJSON would fail."""
+    datasets = datasets or {}
+    names = (C.c_char_p * len(datasets))(*[n.encode() for n in datasets])
+    widths = (C.c_uint32 * len(datasets))(*[int(w) for w in datasets.values()])
+    buf = C.create_string_buffer(1 << 16)
+    _check(lib().dsb200_describe_network_json(json_text.encode(), names, widths, C.c_int(len(datasets)), buf, C.c_size_t(len(buf))))
+    return buf.value.decode()
+
+
 class Dataset:
     """NNDataSet<T> (sparse): Boolean when data is None."""
 

@@ -173,6 +173,11 @@ struct NNNetworkDescriptor {
     NNNetworkDescriptor();
 };
 
+// name and dimensions of a data set: all the JSON loader needs from it (auto-sized layers)
+struct NNDataSetShape { string _name; uint32_t _width, _height, _length, _dimensions; };
+// host-only stages of LoadNeuralNetworkJSON (no GPU context needed)
+NNNetworkDescriptor ParseNeuralNetworkJSON(const string& json, const vector<NNDataSetShape>& vDataSet);
+string DescribeNeuralNetworkJSON(const string& json, const vector<NNDataSetShape>& vDataSet);
 NNNetwork* CreateNeuralNetwork(NNNetworkDescriptor& nd, uint32_t batch = DefaultBatch);
 NNNetwork* LoadNeuralNetworkNetCDF(const string& fname, const uint32_t batch = DefaultBatch);
 NNNetwork* LoadNeuralNetworkJSON(const string& fname, const uint32_t batch = DefaultBatch,

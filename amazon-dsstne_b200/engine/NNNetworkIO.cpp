@@ -148,7 +148,10 @@ WeightInitialization parseScheme(const string& v)
 
 }  // namespace
 
-NNNetwork* LoadNeuralNetworkJSONString(const string& json, const uint32_t batch, const vector<NNDataSetBase*>& vDataSet)
+// The JSON text -> NNNetworkDescriptor stage needs no GPU: the only thing it takes from the data sets is their dimensions
+// (auto-sized input / output layers, E/NNNetwork.cpp:3600-3622).  DescribeNeuralNetworkJSON runs it alone, so that the
+// reference's own sample configurations can be checked on a machine without a device.
+NNNetworkDescriptor ParseNeuralNetworkJSON(const string& json, const vector<NNDataSetShape>& vDataSet)
 {
     JParser parser(json);
     JValue root = parser.parse();
@@ -298,8 +301,8 @@ NNNetwork* LoadNeuralNetworkJSONString(const string& json, const uint32_t batch,
                 }
                 if (bAutoSize) {                                               // E/NNNetwork.cpp:3600-3622
                     bool bFound = false;
-                    for (auto p : vDataSet)
-                        if (p->_name == ldl._dataSet) { ldl._Nx = p->_width; ldl._Ny = p->_height; ldl._Nz = p->_length; ldl._dimensions = p->_dimensions; bFound = true; }
+                    for (auto& p : vDataSet)
+                        if (p._name == ldl._dataSet) { ldl._Nx = p._width; ldl._Ny = p._height; ldl._Nz = p._length; ldl._dimensions = p._dimensions; bFound = true; }
                     if (!bFound) bad("Unable to find data set " + ldl._dataSet + " to determine dimensions for layer: " + ldl._name);
                 }
                 if (!bSource && ldl._kind != NNLayer::Kind::Input) {
@@ -321,7 +324,58 @@ NNNetwork* LoadNeuralNetworkJSONString(const string& json, const uint32_t batch,
         for (auto& l : nd._vLayerDescriptor)
             if (l._kind == NNLayer::Kind::Input && (l._attributes & NNLayer::Attributes::Sparse)) l._attributes |= NNLayer::Attributes::Denoising;
     }
+    return nd;
+}
+
+NNNetwork* LoadNeuralNetworkJSONString(const string& json, const uint32_t batch, const vector<NNDataSetBase*>& vDataSet)
+{
+    vector<NNDataSetShape> vShape;
+    for (auto p : vDataSet) vShape.push_back(NNDataSetShape{p->_name, p->_width, p->_height, p->_length, p->_dimensions});
+    NNNetworkDescriptor nd = ParseNeuralNetworkJSON(json, vShape);
     return new NNNetwork(nd, batch);
+}
+
+static const char* kindName(NNLayer::Kind k)
+{
+    switch (k) { case NNLayer::Kind::Input: return "Input"; case NNLayer::Kind::Hidden: return "Hidden"; case NNLayer::Kind::Output: return "Output"; default: return "Target"; }
+}
+static const char* activationName(Activation a)
+{
+    static const char* n[] = {"Sigmoid", "Tanh", "RectifiedLinear", "Linear", "ParametricRectifiedLinear", "SoftPlus", "SoftSign", "SoftMax", "RELUMax",
+                              "LinearMax", "ExponentialLinear", "LeakyRectifiedLinear", "ScaledExponentialLinear"};
+    return n[(int)a];
+}
+static const char* errorName(ErrorFunction e)
+{
+    static const char* n[] = {"L1", "L2", "CrossEntropy", "ScaledMarginalCrossEntropy", "DataScaledMarginalCrossEntropy", "Hinge", "L2Hinge"};
+    return n[(int)e];
+}
+static const char* initName(WeightInitialization w)
+{
+    static const char* n[] = {"Xavier", "CaffeXavier", "Gaussian", "Uniform", "UnitBall", "Constant", "SELU"};
+    return n[(int)w];
+}
+
+// One line per network / layer / weight, in declaration order -- what the parser understood, for tests and for `train -describe`
+string DescribeNeuralNetworkJSON(const string& json, const vector<NNDataSetShape>& vDataSet)
+{
+    const NNNetworkDescriptor nd = ParseNeuralNetworkJSON(json, vDataSet);
+    ostringstream o;
+    o << "network name=" << nd._name << " kind=" << (nd._kind == NNNetwork::Kind::AutoEncoder ? "AutoEncoder" : "FeedForward")
+      << " error=" << errorName(nd._errorFunction) << " shuffle=" << (nd._bShuffleIndices ? 1 : 0) << " decay=" << nd._decay
+      << " denoising_p=" << nd._denoising_p << " sparseness=(" << nd._sparsenessPenalty_p << "," << nd._sparsenessPenalty_beta << ")"
+      << " deltaBoost=(" << nd._deltaBoost_one << "," << nd._deltaBoost_zero << ")"
+      << " smce=(" << nd._SMCE_oneTarget << "," << nd._SMCE_zeroTarget << "," << nd._SMCE_oneScale << "," << nd._SMCE_zeroScale << ")\n";
+    for (auto& l : nd._vLayerDescriptor) {
+        o << "layer name=" << l._name << " kind=" << kindName(l._kind) << " N=" << l._Nx << " activation=" << activationName(l._activation)
+          << " sparse=" << ((l._attributes & NNLayer::Attributes::Sparse) ? 1 : 0) << " denoising=" << ((l._attributes & NNLayer::Attributes::Denoising) ? 1 : 0)
+          << " pDropout=" << l._pDropout << " init=" << initName(l._weightInit) << ":" << l._weightInitScale << ":" << l._biasInit
+          << " dataset=" << l._dataSet << " sources=";
+        for (size_t i = 0; i < l._vSource.size(); i++) o << (i ? "," : "") << l._vSource[i];
+        o << "\n";
+    }
+    for (auto& w : nd._vWeightDescriptor) o << "weight " << w._inputLayer << " -> " << w._outputLayer << "\n";
+    return o.str();
 }
 
 NNNetwork* LoadNeuralNetworkJSON(const string& fname, const uint32_t batch, const vector<NNDataSetBase*>& vDataSet)

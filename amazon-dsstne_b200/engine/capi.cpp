@@ -313,6 +313,18 @@ int dsb200_network_train_step(dsb200_network* n, uint32_t position, float alpha,
     DSB_ENGINE_CATCH
 }
 
+int dsb200_describe_network_json(const char* jsonText, const char* const* dataSetNames, const uint32_t* dataSetWidths, int nSets, char* buf, size_t cap)
+{
+    DSB_ENGINE_TRY
+    if (!jsonText || !buf || !cap) throw DsbEngineError("describe_network_json: null argument");
+    vector<NNDataSetShape> v;
+    for (int i = 0; i < nSets; i++) v.push_back(NNDataSetShape{dataSetNames[i], dataSetWidths[i], 1, 1, 1});
+    const string d = DescribeNeuralNetworkJSON(jsonText, v);
+    if (d.size() + 1 > cap) throw DsbEngineError("describe_network_json: buffer too small");
+    memcpy(buf, d.c_str(), d.size() + 1);
+    DSB_ENGINE_CATCH
+}
+
 int dsb200_network_predict_batch(dsb200_network* n) { DSB_ENGINE_TRY NET(n)->PredictBatch(); DSB_ENGINE_CATCH }
 
 int dsb200_network_topk(dsb200_network* n, const char* layer, uint32_t k, dsb200_dataset* filter, float* outKey, uint32_t* outValue)

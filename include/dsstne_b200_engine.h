@@ -67,6 +67,11 @@ int dsb200_netcdf_write_sparse(const char* fname, int version, const char* name,
 
 /* LoadNeuralNetworkJSON / LoadNeuralNetworkNetCDF / SaveNetCDF / delete (E/NNNetwork.h:287-291) */
 int dsb200_network_load_json(dsb200_network** out, const char* jsonText, uint32_t batch, dsb200_dataset** sets, int nSets);
+/* HOST ONLY (no GPU needed): parses a network description exactly as dsb200_network_load_json does and writes what it understood,
+ * one line per network / layer / weight, into buf.  dataSetNames / dataSetWidths give the dimensions auto-sized layers take from
+ * their data sets.  Unknown keys and features outside the hot path fail as in the loader (message: dsb200_engine_last_error).  */
+int dsb200_describe_network_json(const char* jsonText, const char* const* dataSetNames, const uint32_t* dataSetWidths, int nSets,
+                                 char* buf, size_t cap);
 int dsb200_network_load_json_file(dsb200_network** out, const char* fname, uint32_t batch, dsb200_dataset** sets, int nSets);
 int dsb200_network_load_netcdf(dsb200_network** out, const char* fname, uint32_t batch);
 int dsb200_network_save_netcdf(dsb200_network* n, const char* fname);
