@@ -34,6 +34,8 @@ def main():
     dist.broadcast(buf, 0)
     engine.startup(rank, world, local, bytes(buf.cpu().tolist()), seed=12134)
     engine.use_torch_stream(local)
+    if os.environ.get("MP_P2P"):
+        engine.set_option("p2p_exchange", 1)          # exchange steps as one kernel over peer memory instead of NCCL (csrc/comm.cu)
 
     h = tiny(examples=2 * batch, width=sizes[0])
     ds_in = engine.Dataset.from_host_csr("gl_input", h)

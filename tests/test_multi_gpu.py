@@ -57,3 +57,14 @@ unverified = pytest.mark.skipif(not os.environ.get("DSB200_RUN_UNVERIFIED"), rea
 def test_model_parallel_topk_global_matches_single_process(world):
     r = run_world(world, {"MP_MODE": "0", "MP_TOPK": "50"}, port=29651 + world)
     assert r["topk_ok"] is True, r
+
+
+@unverified
+@pytest.mark.parametrize("world", [2, 4])
+def test_peer_memory_exchange_matches_oracle(world):
+    """option "p2p_exchange": NNLayer::Reduce / Gather as one kernel over cudaIpc-mapped peer buffers (uneven unit ranges too)."""
+    r = run_world(world, {"MP_MODE": "1", "MP_P2P": "1", "MP_SIZES": "[2050, 130, 66, 130, 2050]", "MP_TOPK": "20"}, port=29671 + world)
+    assert r["loss_err"] < 1e-5, r
+    assert r["topk_ok"] is True, r
+    for k, v in r["errs"].items():
+        assert v < (5e-5 if k.startswith("b") else 1e-5), (k, v, r)
