@@ -48,6 +48,8 @@ struct GpuContext {
     NNNetwork*      _pNetwork;
     unsigned long   _seed;
     bool            _bStarted;
+    bool            _bPinnedMirror = false;   // engine option "pinned_mirror" (experimental): NNDataSet::LoadSparseData uploads straight from
+                                              // the page-locked host mirror instead of copying every batch a second time into staging
     long long       _totalGPUMemory, _totalCPUMemory;
 
     GpuContext();

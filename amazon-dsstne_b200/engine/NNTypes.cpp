@@ -129,8 +129,50 @@ void NNDataSet<T>::LoadSparseData(const uint64_t* srcSparseStart, const uint64_t
         SliceFromFull();
         return;
     }
+    if (getGpu()._bPinnedMirror && !_mirror.unavailable) {
+        // the previous batch's asynchronous copies read the mirror: they must have finished before it is overwritten (a whole
+        // training step has passed in a streaming loop, so this wait is normally free)
+        if (_mirror.pending) { RTERROR(cudaEventSynchronize(_mirror.done), "NNDataSet mirror wait"); _mirror.pending = false; }
+        CopySparseData(srcSparseStart, srcSparseEnd, srcSparseData, srcSparseIndex);
+        if (UploadMirrorAsync(srcSparseEnd[_uniqueExamples - 1])) return;
+        UploadSparseAsync(srcSparseStart, srcSparseEnd, srcSparseData, srcSparseIndex, srcSparseEnd[_uniqueExamples - 1]);
+        return;
+    }
     CopySparseData(srcSparseStart, srcSparseEnd, srcSparseData, srcSparseIndex);
     UploadSparseAsync(srcSparseStart, srcSparseEnd, srcSparseData, srcSparseIndex, srcSparseEnd[_uniqueExamples - 1]);
+}
+
+// Engine option "pinned_mirror" (EXPERIMENTAL, written at the end of round 1 without GPU time left: not yet run).  The default
+// path above copies every batch twice on the host (mirror, then pinned staging); here the mirror vectors are page-locked in
+// place (cudaHostRegister, once -- their storage never moves after construction) and are themselves the source of the
+// asynchronous copies, so a batch is copied once.
+template <typename T>
+bool NNDataSet<T>::UploadMirrorAsync(uint64_t dataLength)
+{
+    void* want[4] = {_vSparseStart.data(), _vSparseEnd.data(), _vSparseIndex.data(), _vSparseData.data()};
+    const size_t bytes[4] = {_vSparseStart.size() * sizeof(uint64_t), _vSparseEnd.size() * sizeof(uint64_t), _vSparseIndex.size() * sizeof(uint32_t),
+                             _vSparseData.size() * sizeof(T)};
+    for (int i = 0; i < 4; i++) {
+        if (_mirror.ptr[i] == want[i] || !bytes[i]) continue;
+        if (_mirror.ptr[i]) { cudaHostUnregister(_mirror.ptr[i]); _mirror.ptr[i] = nullptr; }
+        if (cudaHostRegister(want[i], bytes[i], cudaHostRegisterDefault) != cudaSuccess) {
+            cudaGetLastError();
+            for (int j = 0; j < 4; j++) if (_mirror.ptr[j]) { cudaHostUnregister(_mirror.ptr[j]); _mirror.ptr[j] = nullptr; }
+            _mirror.unavailable = true;
+            return false;
+        }
+        _mirror.ptr[i] = want[i];
+    }
+    if (!_mirror.done) RTERROR(cudaEventCreateWithFlags(&_mirror.done, cudaEventDisableTiming), "NNDataSet mirror event");
+    cudaStream_t stream = getGpu().GetStream();
+    RTERROR(cudaMemcpyAsync(_pbSparseStart->_pDevData, _vSparseStart.data(), _uniqueExamples * sizeof(uint64_t), cudaMemcpyHostToDevice, stream), "NNDataSet upload");
+    RTERROR(cudaMemcpyAsync(_pbSparseEnd->_pDevData, _vSparseEnd.data(), _uniqueExamples * sizeof(uint64_t), cudaMemcpyHostToDevice, stream), "NNDataSet upload");
+    if (dataLength) RTERROR(cudaMemcpyAsync(_pbSparseIndex->_pDevData, _vSparseIndex.data(), dataLength * sizeof(uint32_t), cudaMemcpyHostToDevice, stream), "NNDataSet upload");
+    if (!(_attributes & NNDataSetEnums::Boolean) && dataLength)
+        RTERROR(cudaMemcpyAsync(_pbSparseData->_pDevData, _vSparseData.data(), dataLength * sizeof(T), cudaMemcpyHostToDevice, stream), "NNDataSet upload");
+    RTERROR(cudaEventRecord(_mirror.done, stream), "NNDataSet mirror record");
+    _mirror.pending = true;
+    return true;
 }
 
 // The call a serving / streaming caller makes once per batch (the reference's JNI binding, java/.../dsstne.cpp): the source
@@ -167,6 +209,9 @@ void NNDataSet<T>::UploadSparseAsync(const uint64_t* srcStart, const uint64_t* s
 template <typename T>
 NNDataSet<T>::~NNDataSet()
 {
+    if (_mirror.pending) cudaEventSynchronize(_mirror.done);
+    for (void* p : _mirror.ptr) if (p) cudaHostUnregister(p);
+    if (_mirror.done) cudaEventDestroy(_mirror.done);
     for (Staging& st : _staging) {
         if (st.pending) cudaEventSynchronize(st.done);
         if (st.start) cudaFreeHost(st.start);

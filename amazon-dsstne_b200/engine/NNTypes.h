@@ -252,6 +252,12 @@ private:
         cudaEvent_t done = nullptr; bool pending = false;
     } _staging[2];
     int _stagingCur = 0;
+    // experimental single-copy path (engine option "pinned_mirror"): the host mirror itself is page-locked and is the copy source
+    struct Mirror {
+        void* ptr[4] = {nullptr, nullptr, nullptr, nullptr};      // registered storage of _vSparseStart / End / Index / Data
+        cudaEvent_t done = nullptr; bool pending = false; bool unavailable = false;
+    } _mirror;
+    bool UploadMirrorAsync(uint64_t dataLength);              // false: page-locking failed, the caller takes the staging path
     unique_ptr<GpuBuffer<uint32_t>> _pbColumnCount;        // scratch of the device-side capacity table
 public:
     ~NNDataSet();

@@ -277,6 +277,8 @@ def run_e2e(args, wl, data, engine, dsstne_b200, stream, world=1):
     net.set_training_mode(dsstne_b200.SGD)
     net.set_gemm_mode(args.gemm_mode)
     h2d = d2h = 0
+    if args.pinned_mirror:
+        engine.set_option("pinned_mirror", 1)
 
     def step(i):
         nonlocal h2d, d2h
@@ -356,6 +358,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c2", "c4"])
     ap.add_argument("--gemm-mode", type=int, default=2, help="dense GEMMs: 0 cuBLAS fp32, 1 tcgen05 TF32, 2 tcgen05 3xTF32 (fp32-grade)")
     ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--pinned-mirror", type=int, default=0, help="e2e path: 1 = LoadSparseData uploads from the page-locked host mirror (experimental single-copy path)")
     ap.add_argument("--p2p", type=int, default=0, help="N > 1: 1 = exchange steps as one kernel over peer memory (experimental) instead of NCCL")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
