@@ -145,6 +145,7 @@ int dsb200_ctx_set_option(dsb200_ctx* ctx, const char* name, int value)
     if (!strcmp(name, "gemm_splits")) { ctx->gemmSplits = value; return 0; }
     if (!strcmp(name, "gemm_loader")) { ctx->gemmLoader = value; return 0; }
     if (!strcmp(name, "p2p_exchange")) { ctx->p2pExchange = value; return 0; }
+    if (!strcmp(name, "wgrad_light_blocks")) { ctx->wgradLightBlocks = value; return 0; }
     if (!strcmp(name, "gemm_tc_min_work")) { ctx->gemmTcMinWork = value; return 0; }
     if (!strcmp(name, "gemm_debug")) { ctx->gemmDebug = value; return 0; }
     return dsb::fail(ctx, DSB200_EINVAL, "unknown option");

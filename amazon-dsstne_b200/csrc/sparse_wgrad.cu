@@ -416,7 +416,19 @@ static int launch_wgrad2(dsb200_ctx* ctx, const GArgs& a)
     uint32_t* count = ctx->dHeavy;                                            // [0] = count, [1..] = list
     DSB_CUDA_OK(cudaMemsetAsync(count, 0, sizeof(uint32_t), ctx->stream));
     const uint32_t warps = kGThreads / 32;
-    int grid = ctx->numSMs * 4;
+    // One resident wave: the kernel is grid-strided over warps, so blocks beyond what fits on the GPU at once only form a second,
+    // thinly occupied wave (ncu, round 1: 592 blocks launched, 3 per SM resident at 80 registers -> 25 % of the warp slots
+    // active on average).  Option "wgrad_light_blocks" overrides the blocks per SM (0 = ask the occupancy calculator).
+    static int blocksPerSM = 0;                                               // per instantiation
+    if (!blocksPerSM) {
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sparse_wgrad_light_kernel<ANALOG, FUSED_MODE>, kGThreads, 0) != cudaSuccess || occ < 1) {
+            cudaGetLastError();
+            occ = 4;                                                          // the former fixed choice
+        }
+        blocksPerSM = occ;
+    }
+    int grid = ctx->numSMs * (ctx->wgradLightBlocks > 0 ? ctx->wgradLightBlocks : blocksPerSM);
     if ((uint32_t)grid > (a.m + warps - 1) / warps) grid = (int)((a.m + warps - 1) / warps);
     if (grid < 1) grid = 1;
     sparse_wgrad_light_kernel<ANALOG, FUSED_MODE><<<grid, kGThreads, 0, ctx->stream>>>(a, count + 1, count);
