@@ -1138,13 +1138,13 @@ int gemm_tc_launch(dsb200_ctx* ctx, const float* A, int aMN, uint32_t lda, const
     }
     const uint32_t grid = min(sms, tilesMN * splits);
     // operand path (option "gemm_loader"): measured on the three output-layer GEMMs of BASELINE config 2
-    // (gpurun_out/gemm_debug_matrix2.log, us per launch: forward / weight gradient / input delta)
+    // (profiles/r1c_logs/gemm_debug_matrix2.log, us per launch: forward / weight gradient / input delta)
     //   0 cp.async + split warps      92.5 / 96.6 / 85.1
     //   1 register loader             82.4 / 80.3 / 90.6
     //   2 A through tensor memory     81.0 / 67.7 / 65.5     <- default (-1)
     //   exception: a K-major A whose rows are far apart (the 1M-column delta of BASELINE config 4, 4 MB between rows): the
     //   tensor-memory loader reads one row per thread, i.e. 32 pages per load instruction, and measured 23.5 ms against
-    //   15 ms for cp.async on the 1,024 x 1,024 x 1M input-delta GEMM (gpurun_out/bench_c4_1.json, two runs)
+    //   15 ms for cp.async on the 1,024 x 1,024 x 1M input-delta GEMM (profiles/r1c_logs/bench_c4_1.json, two runs)
     const bool farRows = !aMN && lda > 65536u;
     const bool regLoader = ctx->gemmLoader == 1;
     if (ctx->gemmLoader == 3 && !aMN) {                                           // experimental coalesced tensor-memory A loader

@@ -55,6 +55,12 @@ def main():
         diff = [k for k in a if k in b and a[k] != b[k]]
         gone = [k for k in a if k not in b]
         new = [k for k in b if k not in a]
+        # a kernel that only changed its name (e.g. a new defaulted template parameter) keeps its instruction stream
+        renamed = [(k, n) for k in gone for n in new if a[k] == b[n]]
+        for k, n in renamed:
+            if k in gone and n in new:
+                gone.remove(k); new.remove(n); same.append(k)
+                print(f"   renamed, identical body: {k} -> {n}")
         changed += len(diff) + len(gone)
         print(f"{tu}: {len(same)} identical, {len(diff)} changed, {len(gone)} removed or renamed, {len(new)} new")
         for k in diff:
