@@ -352,8 +352,8 @@ def run_reference(args, wl, rank):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=100)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=500)            # 0.25 s timed region on c2: several nvidia-smi clock samples fall inside it
+    ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c2", "c4"])
     ap.add_argument("--gemm-mode", type=int, default=2, help="dense GEMMs: 0 cuBLAS fp32, 1 tcgen05 TF32, 2 tcgen05 3xTF32 (fp32-grade)")
