@@ -188,6 +188,14 @@ class Context:
                                             C.c_uint32(batch), C.c_uint32(z.shape[1]), _ptr(z), _ptr(unit_out),
                                             _ptr(delta), _ptr(acc)))
 
+    def gemm_fwd_output_pass(self, ds, ef, act, position, A, W, bias, unit_out, delta, acc=None):
+        """EXPERIMENTAL: forward GEMM of the output layer with the fused output pass in its epilogue (Z is never written)."""
+        v = ds.view()
+        B, k = A.shape
+        self.check(lib().dsb200_gemm_fwd_output_pass(self.h, C.byref(v), C.c_int(ef), C.c_int(act), C.c_uint32(position), C.c_uint32(B),
+                                                     C.c_uint32(k), C.c_uint32(W.shape[1]), _ptr(A), _ptr(W), _ptr(bias), _ptr(unit_out),
+                                                     _ptr(delta), _ptr(acc)))
+
     def sparseness_penalty(self, unit, delta, p, beta):
         b, s = unit.shape
         self.check(lib().dsb200_sparseness_penalty(self.h, C.c_uint32(b), C.c_uint32(s), _ptr(unit), _ptr(delta),

@@ -91,6 +91,7 @@ int dsb200_ctx_destroy(dsb200_ctx* ctx)
     cudaFree(ctx->dPartials);
     cudaFree(ctx->dGemmWs);
     cudaFree(ctx->dHeavy);
+    cudaFree(ctx->dFuseBits);
     delete ctx;
     return 0;
 }

@@ -31,6 +31,8 @@ static int cublas_of(dsb200_ctx* ctx, cublasHandle_t* out)
     return 0;
 }
 
+int gemm_tc_fwd_output_pass(dsb200_ctx* ctx, const dsb200_sparse* s, int ef, uint32_t position, uint32_t batch, uint32_t k, uint32_t n,
+                            const float* A, const float* W, const float* bias, float* unitOut, float* delta, unsigned long long* acc);
 int gemm_tc_launch(dsb200_ctx* ctx, const float* A, int aMN, uint32_t lda, const float* B, int bMN, uint32_t ldb, float* C, uint32_t ldc,
                    uint32_t M, uint32_t N, uint32_t K, float alpha, float beta, const float* bias, int act, float slope, float ealpha,
                    float lambda);
@@ -121,6 +123,24 @@ int dsb200_gemm_fwd_bias_act(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n
     if (!rc) rc = dsb200_gemm_fwd(ctx, B, k, n, A, W, 1.0f, C);
     if (!rc && activation != DSB200_ACT_LINEAR) rc = dsb200_activation(ctx, activation, C, B, n, slope, alpha, lambda);
     return rc;
+}
+
+// EXPERIMENTAL (written at the end of round 1 without GPU time left: not yet run).  Forward GEMM of a sparse-target output layer
+// with dsb200_output_pass folded into its epilogue: C = delta, Z is never written.  DSB200_EUNSUPPORTED = take the two-call path.
+int dsb200_gemm_fwd_output_pass(dsb200_ctx* ctx, const dsb200_sparse* s, int errorFunction, int activation, uint32_t position, uint32_t batch,
+                                uint32_t k, uint32_t n, const float* A, const float* W, const float* pBias, float* pUnitOut, float* pDelta,
+                                unsigned long long* pDevAccumulator)
+{
+    using namespace dsb;
+    if (!ctx || !s || !A || !W || !pDelta) return fail(ctx, DSB200_EINVAL, "gemm_fwd_output_pass: null argument");
+    if (!s->sparseStart || !s->sparseEnd || !s->sparseIndex) return fail(ctx, DSB200_EINVAL, "gemm_fwd_output_pass: incomplete target data set");
+    if (activation != DSB200_ACT_SIGMOID || s->sparseData ||
+        (errorFunction != DSB200_ERR_L2 && errorFunction != DSB200_ERR_CROSS_ENTROPY && errorFunction != DSB200_ERR_SMCE))
+        return fail(ctx, DSB200_EUNSUPPORTED, "gemm_fwd_output_pass: sigmoid with L2 / CrossEntropy / ScaledMarginalCrossEntropy over Boolean targets only");
+    if (!use_tc(ctx, batch, n, k)) return fail(ctx, DSB200_EUNSUPPORTED, "gemm_fwd_output_pass: this shape / gemm_mode does not run on the tensor-core kernel");
+    if (!batch || !k || !n) return 0;
+    DSB_PROFILE(ctx, "gemm_fwd_output_pass");
+    return gemm_tc_fwd_output_pass(ctx, s, errorFunction, position, batch, k, n, A, W, pBias, pUnitOut, pDelta, pDevAccumulator);
 }
 
 }  // extern "C"

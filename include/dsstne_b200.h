@@ -198,6 +198,13 @@ int dsb200_sparse_output_delta(dsb200_ctx*, const dsb200_sparse* s, int errorFun
 int dsb200_output_pass(dsb200_ctx*, const dsb200_sparse* s, int errorFunction, int activation,
                        uint32_t position, uint32_t batch, uint32_t stride, const float* pZ,
                        float* pUnitOut, float* pDelta, unsigned long long* pDevAccumulator);
+/* EXPERIMENTAL: cublasSgemm of the output layer (E/NNLayer.cpp:1073) + the fused output pass above in ONE kernel -- the tcgen05
+ * GEMM's epilogue turns z into (activation,) loss and delta, so Z is never written or re-read.  A [batch][k], W [k][n], bias [n];
+ * sigmoid with L2 / CrossEntropy / ScaledMarginalCrossEntropy over Boolean targets and a tensor-core gemm_mode only: any other
+ * combination returns DSB200_EUNSUPPORTED and the caller makes the two calls.  Not yet run on a GPU (round 1).                     */
+int dsb200_gemm_fwd_output_pass(dsb200_ctx*, const dsb200_sparse* s, int errorFunction, int activation, uint32_t position, uint32_t batch,
+                                uint32_t k, uint32_t n, const float* A, const float* W, const float* pBias, float* pUnitOut, float* pDelta,
+                                unsigned long long* pDevAccumulator);
 
 /* ------------------------------------------------------------------ a10
  * kCalculateSparsenessPenalty / kCalculateHadamardProduct, E/kernels.h:202,205            */

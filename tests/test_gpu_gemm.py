@@ -129,3 +129,44 @@ def test_tensor_core_gemm_is_deterministic(ctx):
         ctx.set_option("gemm_mode", 0)
     np.testing.assert_array_equal(outs[0], outs[1])
     np.testing.assert_array_equal(outs[0], outs[2])
+
+
+@pytest.mark.skipif(not os.environ.get("DSB200_RUN_UNVERIFIED"), reason="not yet run on a GPU (round 1 budget); set DSB200_RUN_UNVERIFIED=1")
+@pytest.mark.parametrize("ef", [3, 2, 1], ids=["smce", "ce", "l2"])
+@pytest.mark.parametrize("want_unit", [False, True])
+@pytest.mark.parametrize("B,k,n", [(1024, 128, 27278), (256, 128, 4099)])
+def test_forward_gemm_with_fused_output_pass(ctx, dsb, ef, want_unit, B, k, n):
+    """dsb200_gemm_fwd_output_pass against the two calls it replaces (dsb200_gemm_fwd_bias_act with the activation deferred, then
+    dsb200_output_pass), both on the 3xTF32 tensor-core kernel: the same z, so delta / activations within 1e-6 and the loss within
+    1e-6 relative (its fixed-point sum is taken over a different partition of the elements)."""
+    from helpers import ml20m, to_device
+    g = torch.Generator(device="cuda").manual_seed(ef * 10 + want_unit)
+    A = torch.rand(B, k, device="cuda", generator=g)
+    W = torch.randn(k, n, device="cuda", generator=g) * 0.1
+    bias = torch.randn(n, device="cuda", generator=g) * 0.5 - 2.0
+    h = ml20m(examples=B, width=n)
+    ds = to_device(dsb, h)
+    ctx.set_params(smce=(1.0, 0.0, 30.0, 1.0))
+    ctx.set_option("gemm_mode", 2)
+    ctx.set_option("gemm_tc_min_work", 0)
+    try:
+        z = torch.empty(B, n, device="cuda")
+        ctx.gemm_fwd_bias_act(A, W, bias, 3, z)                          # 3 = Linear: activation deferred to the output pass
+        unit0 = torch.empty_like(z) if want_unit else None
+        delta0 = torch.empty_like(z)
+        acc0 = torch.zeros(1, dtype=torch.int64, device="cuda")
+        ctx.output_pass(ds, ef, dsb.ACT_SIGMOID, 0, B, z, unit0, delta0, acc0)
+        unit1 = torch.empty_like(z) if want_unit else None
+        delta1 = torch.empty_like(z)
+        acc1 = torch.zeros(1, dtype=torch.int64, device="cuda")
+        ctx.gemm_fwd_output_pass(ds, ef, dsb.ACT_SIGMOID, 0, A, W, bias, unit1, delta1, acc1)
+        ctx.sync()
+    finally:
+        ctx.set_option("gemm_mode", 0)
+        ctx.set_option("gemm_tc_min_work", 2048)
+        ctx.set_params()
+    assert rel_err(delta1.cpu().numpy(), delta0.cpu().numpy()) < 1e-6
+    if want_unit:
+        assert rel_err(unit1.cpu().numpy(), unit0.cpu().numpy()) < 1e-6
+    l0, l1 = float(acc0.item()), float(acc1.item())
+    assert abs(l1 - l0) <= 1e-6 * abs(l0)
