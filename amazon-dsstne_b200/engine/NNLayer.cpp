@@ -101,7 +101,7 @@ void NNLayer::RefreshState(NNNetwork* pNetwork, TrainingMode trainingMode, bool 
 
 void NNLayer::ClearUpdates()
 {
-    _unitUpdateCount = 0; _deltaUpdateCount = 0; _bActivationPending = false; _bDeltaReady = false;
+    _unitUpdateCount = 0; _deltaUpdateCount = 0; _bActivationPending = false; _bDeltaReady = false; _bForwardDeferred = false;
 }
 
 void NNLayer::LoadPredictionBatch(uint32_t position, uint32_t batch)
@@ -156,8 +156,24 @@ void NNLayer::CalculateDropout(uint32_t batch)
                                   _ELUAlpha, _SELULambda, (uint64_t)getGpu()._seed, stream), "dsb200_dropout");
 }
 
+// the deferred forward GEMM of an output layer, run on its own (the units are wanted, or the fused kernel declined the combination)
+void NNLayer::RunDeferredForward(bool applyActivation)
+{
+    NNLayer* in = _vIncomingLayer[0];
+    getGpu().Check(dsb200_gemm_fwd_bias_act(getGpu()._ctx, _preActivationBatch, in->_stride, _localStride, in->GetUnitBuffer(),
+                                            _vIncomingWeight[0]->_pbWeight->_pDevData, _vIncomingWeight[0]->_pbBias->_pDevData,
+                                            applyActivation ? (int)_activation : (int)Linear, GetIncomingUnitBuffer(), _RELUSlope, _ELUAlpha, _SELULambda),
+                   "dsb200_gemm_fwd_bias_act (deferred)");
+    _bForwardDeferred = false;
+}
+
 void NNLayer::MaterializeUnits()
 {
+    if (_bForwardDeferred) {                         // the fused kernel never wrote z or a: run the layer now, activation included
+        RunDeferredForward(true);
+        _bUnitsArePreActivation = false;
+        return;
+    }
     if (!_bUnitsArePreActivation) return;
     _bUnitsArePreActivation = false;
     CalculateActivation(_preActivationBatch);
@@ -166,6 +182,7 @@ void NNLayer::MaterializeUnits()
 void NNLayer::ForwardPropagateFullyConnected(uint32_t position, uint32_t batch, bool bTraining)
 {
     _bUnitsArePreActivation = false;                 // the unit buffer is about to be rewritten
+    _bForwardDeferred = false;
     dsb200_ctx* ctx = getGpu()._ctx;
     NNNetwork* net = getGpu()._pNetwork;
     const bool deferActivation = bTraining && net && FusedOutputEligible(net->GetErrorFunction());
@@ -187,9 +204,15 @@ void NNLayer::ForwardPropagateFullyConnected(uint32_t position, uint32_t batch, 
             // dense layer with a single source: bias + GEMM (+ activation unless the fused loss pass applies it) in one
             // call -- one tcgen05 kernel in the tensor-core GEMM modes (E/NNLayer.cpp:1009 + 1073 + 1157)
             NNLayer* in = _vIncomingLayer[0];
-            getGpu().Check(dsb200_gemm_fwd_bias_act(ctx, batch, in->_stride, _localStride, in->GetUnitBuffer(), _vIncomingWeight[0]->_pbWeight->_pDevData,
-                                                    _vIncomingWeight[0]->_pbBias->_pDevData, deferActivation ? (int)Linear : (int)_activation,
-                                                    GetIncomingUnitBuffer(), _RELUSlope, _ELUAlpha, _SELULambda), "dsb200_gemm_fwd_bias_act");
+            if (deferActivation && getGpu()._bFuseOutputGemm && _activation == Sigmoid && _pDataSet && (_pDataSet->_attributes & NNDataSetEnums::Boolean)) {
+                // experimental: nothing runs now -- CalculateErrorAsync runs GEMM + activation + loss + delta as one kernel
+                _bForwardDeferred = true;
+                _preActivationBatch = batch;
+            } else {
+                getGpu().Check(dsb200_gemm_fwd_bias_act(ctx, batch, in->_stride, _localStride, in->GetUnitBuffer(), _vIncomingWeight[0]->_pbWeight->_pDevData,
+                                                        _vIncomingWeight[0]->_pbBias->_pDevData, deferActivation ? (int)Linear : (int)_activation,
+                                                        GetIncomingUnitBuffer(), _RELUSlope, _ELUAlpha, _SELULambda), "dsb200_gemm_fwd_bias_act");
+            }
             activated = !deferActivation;
         } else {
             // E/NNLayer.cpp:1002-1044: units start as the (sum of the) incoming biases
@@ -290,6 +313,22 @@ NNFloat NNLayer::CalculateError(uint32_t position, uint32_t batch, ErrorFunction
 bool NNLayer::CalculateErrorAsync(uint32_t position, uint32_t batch, ErrorFunction ef, unsigned long long* pDevAccumulator)
 {
     if (_kind != Output) throw DsbEngineError("NNLayer::CalculateError: Attempt to calculate error on non-output layer " + _name);
+    if (_bActivationPending && _bForwardDeferred) {
+        // experimental (engine option "fuse_output_gemm"): forward GEMM + activation + loss + delta as ONE tcgen05 kernel; the units
+        // are not produced at all (MaterializeUnits re-runs the layer if somebody asks for them)
+        NNLayer* in = _vIncomingLayer[0];
+        dsb200_sparse v = _pDataSet->View();
+        const int rc = dsb200_gemm_fwd_output_pass(getGpu()._ctx, &v, (int)ef, (int)_activation, position, batch, in->_stride, _localStride, in->GetUnitBuffer(),
+                                                   _vIncomingWeight[0]->_pbWeight->_pDevData, _vIncomingWeight[0]->_pbBias->_pDevData, NULL,
+                                                   GetIncomingDeltaBuffer(), pDevAccumulator);
+        if (rc == 0) {
+            _bActivationPending = false;             // _bForwardDeferred stays set: the unit buffer holds nothing of this batch
+            _bDeltaReady = true;
+            return true;
+        }
+        if (rc != DSB200_EUNSUPPORTED) getGpu().Check(rc, "dsb200_gemm_fwd_output_pass");
+        RunDeferredForward(false);                   // the kernel declined the combination: z now, then the usual fused pass below
+    }
     if (_bActivationPending) {
         // ONE pass: a = f(z) in place, loss into the accumulator, delta written -- replaces kCalculate*Activation,
         // the Raw + NonZero error kernels and the Raw + NonZero delta kernels (six passes over [batch][N])

@@ -54,6 +54,9 @@ private:
     bool                    _bHadamardDone;       // f'(x) already applied by the fused input-delta kernel of the layer above
     bool                    _bUnitsArePreActivation;  // the fused output pass did not store a = f(z): the unit buffer still holds z
     uint32_t                _preActivationBatch;
+    bool                    _bForwardDeferred = false;    // engine option "fuse_output_gemm": the forward GEMM of this (output) layer has not run; the
+                                                          // loss / delta pass runs it fused, or RunDeferredForward() runs it when the units are needed
+    void                    RunDeferredForward(bool applyActivation);
 
     vector<NNLayer*>        _vIncomingLayer;
     vector<NNWeight*>       _vIncomingWeight;

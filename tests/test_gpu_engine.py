@@ -153,6 +153,37 @@ def test_wide_hidden_layers_like_config4(eng, orc, gemm_mode, tol):
         net.close()
 
 
+@pytest.mark.skipif(not os.environ.get("DSB200_RUN_UNVERIFIED"), reason="not yet run on a GPU (round 1 budget); set DSB200_RUN_UNVERIFIED=1")
+@pytest.mark.parametrize("error", ["ScaledMarginalCrossEntropy", "CrossEntropy", "L2"])
+def test_output_gemm_fused_with_the_output_pass(eng, orc, error):
+    """engine option "fuse_output_gemm": the output layer's forward GEMM is deferred into the loss / delta pass and runs as
+    dsb200_gemm_fwd_output_pass (3xTF32 mode).  Losses and weights against the oracle at the tensor-core bound, and the units
+    a later reader gets (top-K after a training step) are materialised by re-running the layer."""
+    sizes, batch = [4096, 1024, 1024, 4096], 256
+    h = tiny(examples=512, width=4096, mean=40.0)
+    net, onet, names, _ = build_pair(eng, orc, sizes, h, batch, orc.MOMENTUM, error=error)
+    net.set_gemm_mode(2)
+    eng.set_option("fuse_output_gemm", 1)
+    oc = to_oracle(orc, h)
+    onet.set_input(oc, batch)
+    tol = 3e-5
+    try:
+        for pos in (0, 256):
+            got = net.train_step(pos, 0.01, 1e-4, 0.0, 0.5, 0.0)
+            want, _ = onet.train_step(oc, oc, pos, batch, 0.01, 1e-4, 0.0, 0.5, 0.0)
+            assert abs(got - want) <= tol * abs(want)
+        units = np.asarray(net.get_units("Output")).reshape(batch, -1)        # MaterializeUnits after a deferred forward
+        assert np.isfinite(units).all() and units.min() >= 0.0 and units.max() <= 1.0
+        for i in range(3):
+            W, b = net.get_weights(names[i], names[i + 1])
+            assert rel_err(W.reshape(onet.W(i).shape), onet.W(i)) < tol
+            assert rel_err(b, onet.b(i)) < max(tol, 5e-5)
+    finally:
+        eng.set_option("fuse_output_gemm", 0)
+        net.set_gemm_mode(0)
+        net.close()
+
+
 def test_fused_and_unfused_engine_agree(eng, orc):
     sizes, batch = [2048, 128, 2048], 256
     h = tiny(examples=256, width=2048)

@@ -22,6 +22,8 @@ fi
 DSB200_RUN_UNVERIFIED=1 timeout 600 python -m pytest tests -q -m gpu 2>&1 | tail -15 | tee gpurun_out/unverified_single.log
 timeout 120 python tools/gemm_debug_matrix.py 2 3 2>&1 | grep -E "loader|^ +[23] +0 " | tee gpurun_out/gemm_loader3.log
 timeout 120 python tools/fused_output_bench.py 2>&1 | tee gpurun_out/fused_output_bench.log
+timeout 300 python bench.py --steps 100 --warmup 10 --cpu-steps 0 --fuse-output 1 > gpurun_out/bench_fuse1.json 2> gpurun_out/bench_fuse1.err
+python -c "import json; d=json.load(open('gpurun_out/bench_fuse1.json')); print('fuse_output_gemm=1: value', d['value'], 'ms', d['ms_per_step'])"
 for pm in 0 1; do
     timeout 300 python bench.py --steps 100 --warmup 10 --cpu-steps 0 --pinned-mirror $pm > gpurun_out/bench_pm${pm}.json 2> gpurun_out/bench_pm${pm}.err
     python -c "import json; d=json.load(open('gpurun_out/bench_pm${pm}.json')); print('pinned_mirror=${pm}: value', d['value'], 'e2e', d['e2e'])"
