@@ -188,13 +188,21 @@ class Context:
                                             C.c_uint32(batch), C.c_uint32(z.shape[1]), _ptr(z), _ptr(unit_out),
                                             _ptr(delta), _ptr(acc)))
 
-    def gemm_fwd_output_pass(self, ds, ef, act, position, A, W, bias, unit_out, delta, acc=None):
-        """EXPERIMENTAL: forward GEMM of the output layer with the fused output pass in its epilogue (Z is never written)."""
+    def gemm_fwd_output_pass(self, ds, ef, act, position, A, W, bias, unit_out, delta, acc=None, col_partials=None):
+        """Forward GEMM of a sigmoid output layer with loss + delta in its epilogue (Z is never written).  Returns the number of
+        rows of column-sum partials written into col_partials ([2 * ceil(B / 128)][n], optional)."""
         v = ds.view()
         B, k = A.shape
+        n_part = C.c_uint32(0)
         self.check(lib().dsb200_gemm_fwd_output_pass(self.h, C.byref(v), C.c_int(ef), C.c_int(act), C.c_uint32(position), C.c_uint32(B),
                                                      C.c_uint32(k), C.c_uint32(W.shape[1]), _ptr(A), _ptr(W), _ptr(bias), _ptr(unit_out),
-                                                     _ptr(delta), _ptr(acc)))
+                                                     _ptr(delta), _ptr(acc), _ptr(col_partials), C.byref(n_part)))
+        return n_part.value
+
+    def update_biases_partials(self, mode, alpha, mu, mu1, t, batch, partials, n_partials, v, gv, bias):
+        self.check(lib().dsb200_update_biases_partials(self.h, C.c_int(mode), C.c_float(alpha), C.c_float(mu), C.c_float(mu1), C.c_float(t),
+                                                       C.c_uint32(batch), C.c_uint32(bias.numel()), _ptr(partials), C.c_uint32(n_partials),
+                                                       _ptr(v), _ptr(gv), _ptr(bias)))
 
     def sparseness_penalty(self, unit, delta, p, beta):
         b, s = unit.shape

@@ -62,11 +62,12 @@ struct dsb200_ctx {
     int            outputTileKernel = 0;          // option "output_tile_kernel": force the two-phase tile kernel in dsb200_output_pass
     int            fastMath    = 1;               // option "fast_math": MUFU exp/log/rcp in the output pass (default on)
     int            profile     = 0;               // option "profile": event pairs around every kernel entry
-    uint32_t*      dFuseBits   = nullptr;         // dsb200_gemm_fwd_output_pass: target bitmap [batch][words] followed by the row weights
-    size_t         fuseBitsCap = 0;               // in 32-bit words
     int            wgradLightBlocks = 0;          // option "wgrad_light_blocks": blocks per SM of the light-column gradient kernel, 0 = by occupancy
     int            p2pExchange = 0;               // option "p2p_exchange": 1 = exchange steps as one kernel over peer memory (comm.cu, experimental)
     void*          p2p         = nullptr;         // dsb::P2PState, owned by comm.cu
+    int            gemmStream  = 1;               // option "gemm_stream": output-layer shapes on the TMA / tensor-memory kernels of gemm_stream.cu
+    void*          dGsWs       = nullptr;         // gemm_stream.cu: operand copies, split-K partials, target bitmap (grow only)
+    size_t         gsWsBytes   = 0;
     char           lastError[256];
 };
 

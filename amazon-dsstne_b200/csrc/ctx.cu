@@ -91,7 +91,7 @@ int dsb200_ctx_destroy(dsb200_ctx* ctx)
     cudaFree(ctx->dPartials);
     cudaFree(ctx->dGemmWs);
     cudaFree(ctx->dHeavy);
-    cudaFree(ctx->dFuseBits);
+    cudaFree(ctx->dGsWs);
     delete ctx;
     return 0;
 }
@@ -149,6 +149,7 @@ int dsb200_ctx_set_option(dsb200_ctx* ctx, const char* name, int value)
     if (!strcmp(name, "wgrad_light_blocks")) { ctx->wgradLightBlocks = value; return 0; }
     if (!strcmp(name, "gemm_tc_min_work")) { ctx->gemmTcMinWork = value; return 0; }
     if (!strcmp(name, "gemm_debug")) { ctx->gemmDebug = value; return 0; }
+    if (!strcmp(name, "gemm_stream")) { ctx->gemmStream = value; return 0; }
     return dsb::fail(ctx, DSB200_EINVAL, "unknown option");
 }
 

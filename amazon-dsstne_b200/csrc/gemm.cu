@@ -31,8 +31,15 @@ static int cublas_of(dsb200_ctx* ctx, cublasHandle_t* out)
     return 0;
 }
 
-int gemm_tc_fwd_output_pass(dsb200_ctx* ctx, const dsb200_sparse* s, int ef, uint32_t position, uint32_t batch, uint32_t k, uint32_t n,
-                            const float* A, const float* W, const float* bias, float* unitOut, float* delta, unsigned long long* acc);
+// gemm_stream.cu: output-layer shapes (one dimension = the hidden width) on the TMA + tensor-memory kernels
+bool gemm_stream_available();
+int gemm_stream_dw(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, float alpha, const float* X, const float* D, uint32_t ldd, float beta,
+                   float* G, uint32_t ldg);
+int gemm_stream_dx(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, const float* D, uint32_t ldd, const float* W, uint32_t ldw, float beta,
+                   float* Dp, uint32_t ldp);
+int gemm_stream_out_fwd(dsb200_ctx* ctx, const dsb200_sparse* s, int ef, uint32_t position, uint32_t batch, uint32_t k, uint32_t n, const float* X,
+                        const float* W, uint32_t ldw, const float* bias, float* unitOut, float* delta, uint32_t ldd, unsigned long long* acc,
+                        float* pColPartials, uint32_t* pNumPartials);
 int gemm_tc_launch(dsb200_ctx* ctx, const float* A, int aMN, uint32_t lda, const float* B, int bMN, uint32_t ldb, float* C, uint32_t ldc,
                    uint32_t M, uint32_t N, uint32_t K, float alpha, float beta, const float* bias, int act, float slope, float ealpha,
                    float lambda);
@@ -48,6 +55,13 @@ static inline bool use_tc(const dsb200_ctx* ctx, uint64_t M, uint64_t N, uint64_
     if (ctx->gemmMode != DSB200_GEMM_TF32 && ctx->gemmMode != DSB200_GEMM_TF32X3) return false;
     const uint64_t tiles = ((M + 127) / 128) * ((N + 127) / 128);
     return tiles * ((K + 15) / 16) >= (uint64_t)ctx->gemmTcMinWork;
+}
+
+// weight gradient / input delta of a layer whose narrow side (k, the hidden width) fits one or two 128-column tiles while the
+// other side (n) is the long one: the streamed kernels read the big delta operand exactly once
+static inline bool use_stream(const dsb200_ctx* ctx, uint64_t B, uint64_t k, uint64_t n)
+{
+    return ctx->gemmStream && k <= 256 && n >= 512 && B >= 1 && gemm_stream_available();
 }
 
 void gemm_release(dsb200_ctx* ctx)
@@ -79,6 +93,10 @@ int dsb200_gemm_dw(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, float al
     using namespace dsb;
     if (!ctx || !A || !D || !G) return fail(ctx, DSB200_EINVAL, "gemm_dw: null argument");
     if (!B || !k || !n) return 0;
+    if (use_tc(ctx, k, n, B) && use_stream(ctx, B, k, n)) {
+        DSB_PROFILE(ctx, "gemm_dw_stream");
+        return gemm_stream_dw(ctx, B, k, n, alpha, A, D, n, beta, G, n);
+    }
     DSB_PROFILE(ctx, use_tc(ctx, k, n, B) ? "gemm_dw_tc" : "gemm_dw");
     if (use_tc(ctx, k, n, B)) return gemm_tc_launch(ctx, A, 1, k, D, 1, n, G, n, k, n, B, alpha, beta, nullptr, DSB200_ACT_LINEAR, 0.f, 0.f, 0.f);
     cublasHandle_t h; int rc = cublas_of(ctx, &h); if (rc) return rc;
@@ -93,6 +111,10 @@ int dsb200_gemm_dx(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, const fl
     using namespace dsb;
     if (!ctx || !D || !W || !Dp) return fail(ctx, DSB200_EINVAL, "gemm_dx: null argument");
     if (!B || !k || !n) return 0;
+    if (use_tc(ctx, B, k, n) && use_stream(ctx, B, k, n)) {
+        DSB_PROFILE(ctx, "gemm_dx_stream");
+        return gemm_stream_dx(ctx, B, k, n, D, n, W, n, beta, Dp, k);
+    }
     DSB_PROFILE(ctx, use_tc(ctx, B, k, n) ? "gemm_dx_tc" : "gemm_dx");
     if (use_tc(ctx, B, k, n)) return gemm_tc_launch(ctx, D, 0, n, W, 0, n, Dp, k, B, k, n, 1.0f, beta, nullptr, DSB200_ACT_LINEAR, 0.f, 0.f, 0.f);
     cublasHandle_t h; int rc = cublas_of(ctx, &h); if (rc) return rc;
@@ -125,22 +147,27 @@ int dsb200_gemm_fwd_bias_act(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n
     return rc;
 }
 
-// EXPERIMENTAL (written at the end of round 1 without GPU time left: not yet run).  Forward GEMM of a sparse-target output layer
-// with dsb200_output_pass folded into its epilogue: C = delta, Z is never written.  DSB200_EUNSUPPORTED = take the two-call path.
+// Forward pass of a sigmoid output layer over Boolean sparse targets with loss + delta in the GEMM epilogue (gemm_stream.cu,
+// out_fwd_kernel): Z and the activations never exist.  DSB200_EUNSUPPORTED = take the two-call path.
 int dsb200_gemm_fwd_output_pass(dsb200_ctx* ctx, const dsb200_sparse* s, int errorFunction, int activation, uint32_t position, uint32_t batch,
                                 uint32_t k, uint32_t n, const float* A, const float* W, const float* pBias, float* pUnitOut, float* pDelta,
-                                unsigned long long* pDevAccumulator)
+                                unsigned long long* pDevAccumulator, float* pColumnSumPartials, uint32_t* pNumPartials)
 {
     using namespace dsb;
     if (!ctx || !s || !A || !W || !pDelta) return fail(ctx, DSB200_EINVAL, "gemm_fwd_output_pass: null argument");
     if (!s->sparseStart || !s->sparseEnd || !s->sparseIndex) return fail(ctx, DSB200_EINVAL, "gemm_fwd_output_pass: incomplete target data set");
+    if (pNumPartials) *pNumPartials = 0;
     if (activation != DSB200_ACT_SIGMOID || s->sparseData ||
         (errorFunction != DSB200_ERR_L2 && errorFunction != DSB200_ERR_CROSS_ENTROPY && errorFunction != DSB200_ERR_SMCE))
         return fail(ctx, DSB200_EUNSUPPORTED, "gemm_fwd_output_pass: sigmoid with L2 / CrossEntropy / ScaledMarginalCrossEntropy over Boolean targets only");
-    if (!use_tc(ctx, batch, n, k)) return fail(ctx, DSB200_EUNSUPPORTED, "gemm_fwd_output_pass: this shape / gemm_mode does not run on the tensor-core kernel");
+    if ((ctx->gemmMode != DSB200_GEMM_TF32 && ctx->gemmMode != DSB200_GEMM_TF32X3) || !ctx->gemmStream || !gemm_stream_available())
+        return fail(ctx, DSB200_EUNSUPPORTED, "gemm_fwd_output_pass: needs a tensor-core gemm_mode");
     if (!batch || !k || !n) return 0;
     DSB_PROFILE(ctx, "gemm_fwd_output_pass");
-    return gemm_tc_fwd_output_pass(ctx, s, errorFunction, position, batch, k, n, A, W, pBias, pUnitOut, pDelta, pDevAccumulator);
+    const int rc = gemm_stream_out_fwd(ctx, s, errorFunction, position, batch, k, n, A, W, n, pBias, pUnitOut, pDelta, n, pDevAccumulator,
+                                       pColumnSumPartials, pNumPartials);
+    if (rc == DSB200_EUNSUPPORTED) return fail(ctx, DSB200_EUNSUPPORTED, "gemm_fwd_output_pass: hidden width above 128 or rows not 16-byte aligned");
+    return rc;
 }
 
 }  // extern "C"

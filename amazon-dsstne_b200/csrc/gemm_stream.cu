@@ -1,0 +1,994 @@
+// gemm_stream.cu -- tcgen05 / TMEM / TMA kernels for the OUTPUT layer of a sparse-target network (hot-path rows a11 + a7-a9),
+// sm_100a only.  Second generation of the dense path: gemm_tc.cu stays the general kernel (any shape), this file holds the
+// kernels for the shape that dominates the training step -- one dimension is the hidden width (<= a few hundred), the
+// other two are the batch and the 10^4..10^6 output units:
+//
+//   fwd  (E/NNLayer.cpp:1073 + kActivation.cu:46-64 + kLoss.cu:595-2352 + kDelta.cu:2193-7305)
+//        delta[b][n] = f(sigmoid(X[b][:] . W[:][n] + bias[n]), target[b][n])        out_fwd_kernel      (Z and A never exist)
+//   dW   (E/NNLayer.cpp:2223)   G[k][n] = alpha * sum_b X[b][k] * delta[b][n]          stream_kernel<A_MN, EPI_T>
+//   dX   (E/NNLayer.cpp:2274)   Dp[b][k] = sum_n delta[b][n] * W[k][n]                 stream_kernel<A_K,  EPI_N>  (split-K)
+//
+// What round 1's ncu captures said (profiles/r1c_gemm_smem_pipe.md): the 3xTF32 kernels are bound by bytes through the
+// L1 / shared-memory data array (st.shared at half rate, operand re-reads by the tensor core), not by HBM or the tensor
+// pipe.  The design rule here follows from that:
+//   * the BIG operand (delta, or W in the forward pass) is the A operand and never touches shared memory:
+//     global -> registers (coalesced) -> hi / lo split -> tcgen05.st -> TENSOR MEMORY -> tcgen05.mma [d], [a_tmem], b_desc;
+//   * the SMALL operand (X, X^T or W: <= 14 MB, L2 resident) is the B operand and is moved by the TMA engine only:
+//     cp.async.bulk.tensor.2d with a 128-byte-swizzle tensor map drops 128 x 32 panels straight into the UMMA K-major
+//     layout -- no loader warps, no st.shared, no proxy fence.  Its "lo" half (x - trunc_tf32(x), 3xTF32) is a second
+//     array written once per call by a streaming kernel, in a pitch-padded copy, so the 8-byte-aligned rows of the
+//     27,278-wide weight matrix are no obstacle (tensor-map pitches must be multiples of 16 bytes);
+//   * "swapped" orientation: the output unit index is the M dimension (TMEM lane = thread), so every global store of the
+//     epilogue is a fully coalesced 128-byte row segment straight from the tcgen05.ld registers -- no staging tile;
+//   * forward pass: the W slice of a work unit (128 outputs x K <= 128) is split ONCE and stays resident in tensor memory
+//     (256 columns) for all batch tiles of the unit; eight epilogue warps finish the element (bias, sigmoid, loss, delta,
+//     column sums of delta for the bias gradient) because the epilogue, not the MMA, is the long pole of that kernel.
+#include <cuda.h>
+
+#include <algorithm>
+#include <type_traits>
+
+#include "common.cuh"
+#include "launch.h"
+
+namespace dsb {
+namespace gs {
+
+constexpr int BM = 128, BN = 128, BK = 32;
+constexpr int PANEL = BN * BK * 4;             // one 128 x 32 fp32 operand panel: 16 KB
+constexpr int SLOT = 2 * PANEL;                // hi panel | lo panel
+constexpr uint32_t TMEM_COLS = 512;
+
+// ---------------------------------------------------------------- tcgen05 / TMA wrappers
+__device__ __forceinline__ void tmem_alloc(uint32_t* smemResult, uint32_t cols)
+{
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" :: "r"(smem_u32(smemResult)), "r"(cols) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols)
+{
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" :: "r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint64_t* bar)
+{
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+// D[tmem] (+)= A[tmem] * B[smem descriptor], tf32 inputs, fp32 accumulation
+__device__ __forceinline__ void mma_tf32_ts(uint32_t tmemD, uint32_t tmemA, uint64_t descB, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t"
+        "}" :: "r"(tmemD), "r"(tmemA), "l"(descB), "r"(idesc), "r"(accumulate) : "memory");
+}
+// shared-memory matrix descriptor (version 1), K-major operand in the standard 128-byte swizzle: rows of 32 floats, groups of
+// 8 rows 1,024 bytes apart; one K = 8 step = 32 bytes along the row.  Exactly what a SWIZZLE_128B tensor map writes.
+__device__ __forceinline__ uint64_t kmajor_desc(uint32_t panelAddr, int kStep)
+{
+    const uint32_t saddr = panelAddr + kStep * 32;
+    return (uint64_t)((saddr & 0x3FFFFu) >> 4) | ((uint64_t)(16u >> 4) << 16) | ((uint64_t)(1024u >> 4) << 32) | (1ull << 46) | (2ull << 61);
+}
+// instruction descriptor: D = F32, A = B = TF32, A from tensor memory, B K-major, M = 128, N = 128
+constexpr uint32_t kIdesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(BM >> 4) << 24);
+
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v)
+{
+    uint32_t r[32];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]),
+          "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]),
+          "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
+}
+// 32 lanes x 16 consecutive columns: thread t writes TMEM lane (quadrant base + t)
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r)
+{
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16};"
+                 :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+                    "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
+}
+// 16 lanes x 256 bits, twice (columns c..c+7 and c+8..c+15): register s of thread t -> lane t / 4 + 8 * ((s >> 1) & 1),
+// column 2 * (t % 4) + 8 * (s >> 2) + (s & 1)   (probed on the B200: tools/umma_st16x256_probe.cu)
+__device__ __forceinline__ void tmem_st16x256_x2(uint32_t taddr, const uint32_t* r)
+{
+    asm volatile("tcgen05.st.sync.aligned.16x256b.x2.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};"
+                 :: "r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]) : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+// one box of a 2-D tensor map -> shared memory, completion on an mbarrier (SASS: UTMALDG)
+__device__ __forceinline__ void tma_load_2d(uint32_t smemDst, const CUtensorMap* map, uint32_t c0, uint32_t c1, uint64_t* bar)
+{
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 :: "r"(smemDst), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1) : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map)
+{
+    asm volatile("prefetch.tensormap [%0];" :: "l"(map) : "memory");
+}
+
+__device__ __forceinline__ uint32_t ldg_nc_u32(const float* p)
+{
+    uint32_t r;
+    asm volatile("ld.global.nc.L1::no_allocate.b32 %0, [%1];" : "=r"(r) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint2 ldg_nc_u32x2(const float* p)
+{
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.b32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint32_t hi_of(uint32_t x) { return x & 0xFFFFE000u; }                 // the 19 bits a tf32 operand keeps
+__device__ __forceinline__ uint32_t lo_of(uint32_t x) { return __float_as_uint(__uint_as_float(x) - __uint_as_float(x & 0xFFFFE000u)); }
+
+// =====================================================================================================================
+// stream_kernel: D[M][N] = sum_k A(m, k) * B(k, n),  A streamed through registers into a tensor-memory ring, B by TMA.
+//   AMODE 0  A(m, k) = A[k * lda + m]   (m contiguous: lanes = consecutive m, 32-bit loads, any alignment)       -- dW
+//   AMODE 1  A(m, k) = A[m * lda + k]   (k contiguous: the 16x256b store shape, 4 threads = one 32-byte sector)  -- dX
+//   EPI 0    C[n * ldc + m] = alpha * D + beta * C     (transposed store, coalesced over the lanes)
+//   EPI 1    C[m * ldc + n] = alpha * D + beta * C, or the raw partial tile [split][m][n] when K is split
+// B is given as two tensor maps over K-major arrays Bhi / Blo [N rows][K] (box 32 x 128, 128-byte swizzle, zero fill
+// outside), so ragged N and K need no code.
+// Warps: 0-7 A loaders (quadrant = warp % 4, k-half = warp / 4), 8-11 epilogue, 12 TMA producer, 13 MMA issuer.
+// Tensor memory: 2 x 128 accumulator columns + 4 ring slots of (32 hi | 32 lo) A columns.
+// =====================================================================================================================
+constexpr int S_LOAD_WARPS = 8, S_EPI_WARP0 = 8, S_EPI_WARPS = 4, S_TMA_WARP = 12, S_MMA_WARP = 13;
+constexpr int S_THREADS = 14 * 32;
+constexpr int S_SLOTS = 4, S_DEPTH = 3;        // ring depth / register panels in flight per loader thread
+constexpr uint32_t S_ACC_COLS = 2 * BN, S_A_COLS = 2 * BK;
+constexpr int S_SMEM_BYTES = S_SLOTS * SLOT + 1024;
+static_assert(S_ACC_COLS + S_SLOTS * S_A_COLS <= TMEM_COLS, "tensor memory budget");
+
+struct SArgs {
+    const float* A; uint32_t lda;
+    uint32_t M, N, K;
+    uint32_t tilesM, tilesN, splits, kPerSplit;    // kPerSplit: multiple of BK
+    float* C; uint32_t ldc;
+    float* partial;                                // [splits][M][N] when splits > 1
+    float alpha, beta;
+    int passes;                                    // 3 = 3xTF32, 1 = TF32
+    int debug;                                     // option "gemm_debug" (bring-up, wrong results): 512 = no global loads of A, 1024 = no MMAs
+};
+
+struct STile { uint32_t m0, n0, split, kBegin, kEnd, numK; };
+__device__ __forceinline__ STile stile_of(const SArgs& a, uint32_t t)
+{
+    STile x;
+    const uint32_t mn = a.tilesM * a.tilesN;
+    x.split = t / mn;
+    const uint32_t r = t - x.split * mn;
+    x.n0 = (r / a.tilesM) * BN;
+    x.m0 = (r % a.tilesM) * BM;
+    x.kBegin = x.split * a.kPerSplit;
+    x.kEnd = min(a.K, x.kBegin + a.kPerSplit);
+    x.numK = (x.kEnd - x.kBegin + BK - 1) / BK;
+    return x;
+}
+
+// A loader plans: 16 values of one thread per 128 x 32 panel
+struct PlanMN {                                    // thread = row m, 16 consecutive k, stride lda
+    const float* ptr; size_t lda; uint32_t kOff; bool rowIn;
+    __device__ __forceinline__ void init(const float* A, uint32_t ld, uint32_t m0, uint32_t kBegin, uint32_t M, uint32_t q, uint32_t khalf, uint32_t lane)
+    {
+        const uint32_t m = m0 + q * 32 + lane;
+        rowIn = m < M; kOff = khalf * 16; lda = ld;
+        ptr = A + (size_t)(kBegin + kOff) * ld + m;
+    }
+    __device__ __forceinline__ void load(uint32_t (&r)[16], uint32_t k0, uint32_t kEnd)
+    {
+        const uint32_t kb = k0 + kOff;
+        const uint32_t nv = (rowIn && kb < kEnd) ? min(16u, kEnd - kb) : 0u;
+        if (nv == 16) {
+#pragma unroll
+            for (int e = 0; e < 16; e++) r[e] = ldg_nc_u32(ptr + e * lda);
+        } else {
+#pragma unroll
+            for (int e = 0; e < 16; e++) r[e] = (uint32_t)e < nv ? ldg_nc_u32(ptr + e * lda) : 0u;
+        }
+        ptr += (size_t)BK * lda;
+    }
+    __device__ __forceinline__ void store(uint32_t ta, const uint32_t (&r)[16], bool lo) const
+    {
+        uint32_t t[16];
+#pragma unroll
+        for (int e = 0; e < 16; e++) t[e] = hi_of(r[e]);
+        tmem_st16(ta, t);
+        if (lo) {
+#pragma unroll
+            for (int e = 0; e < 16; e++) t[e] = lo_of(r[e]);
+            tmem_st16(ta + BK, t);
+        }
+    }
+};
+struct PlanK {                                     // r[8 j + s]: row t / 4 + 8 * (2 j + ((s >> 1) & 1)), k = 16 khalf + 2 (t % 4) + 8 (s >> 2) + (s & 1)
+    const float* ptr; size_t ld8; uint32_t kOff, rowMask; bool pair;
+    __device__ __forceinline__ void init(const float* A, uint32_t ld, uint32_t m0, uint32_t kBegin, uint32_t M, uint32_t q, uint32_t khalf, uint32_t lane)
+    {
+        const uint32_t m = m0 + q * 32 + (lane >> 2);
+        kOff = khalf * 16 + 2 * (lane & 3);
+        ld8 = (size_t)8 * ld;
+        rowMask = 0;
+#pragma unroll
+        for (uint32_t g = 0; g < 4; g++) if (m + 8 * g < M) rowMask |= 1u << g;
+        ptr = A + (size_t)m * ld + kBegin + kOff;
+        pair = ((ld & 1u) == 0) && ((((uintptr_t)A) & 7u) == 0) && ((kBegin & 1u) == 0);     // 64-bit loads stay aligned
+    }
+    __device__ __forceinline__ void load(uint32_t (&r)[16], uint32_t k0, uint32_t kEnd)
+    {
+        if (rowMask == 15u && k0 + BK <= kEnd && pair) {
+#pragma unroll
+            for (int j = 0; j < 2; j++)
+#pragma unroll
+                for (int s = 0; s < 8; s += 2) {
+                    const uint2 t = ldg_nc_u32x2(ptr + (2 * j + ((s >> 1) & 1)) * ld8 + 8 * (s >> 2));
+                    r[8 * j + s] = t.x; r[8 * j + s + 1] = t.y;
+                }
+        } else {
+#pragma unroll
+            for (int j = 0; j < 2; j++)
+#pragma unroll
+                for (int s = 0; s < 8; s += 2) {
+                    const uint32_t g = 2 * j + ((s >> 1) & 1), kk = k0 + kOff + 8 * (s >> 2);
+                    const float* p = ptr + g * ld8 + 8 * (s >> 2);
+                    const uint32_t n = (((rowMask >> g) & 1u) && kk < kEnd) ? min(2u, kEnd - kk) : 0u;
+                    r[8 * j + s] = n > 0 ? ldg_nc_u32(p) : 0u;
+                    r[8 * j + s + 1] = n > 1 ? ldg_nc_u32(p + 1) : 0u;
+                }
+        }
+        ptr += BK;
+    }
+    __device__ __forceinline__ void store(uint32_t ta, const uint32_t (&r)[16], bool lo) const
+    {
+        uint32_t t[16];
+#pragma unroll
+        for (int e = 0; e < 16; e++) t[e] = hi_of(r[e]);
+        tmem_st16x256_x2(ta, t); tmem_st16x256_x2(ta + (16u << 16), t + 8);
+        if (lo) {
+#pragma unroll
+            for (int e = 0; e < 16; e++) t[e] = lo_of(r[e]);
+            tmem_st16x256_x2(ta + BK, t); tmem_st16x256_x2(ta + BK + (16u << 16), t + 8);
+        }
+    }
+};
+
+template <int AMODE, int EPI>
+__global__ void __launch_bounds__(S_THREADS, 1)
+stream_kernel(const SArgs a, const __grid_constant__ CUtensorMap mapHi, const __grid_constant__ CUtensorMap mapLo)
+{
+    extern __shared__ uint8_t smemRaw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smemRaw + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t aFull[S_SLOTS], bFull[S_SLOTS], slotEmpty[S_SLOTS], accFull[2], accEmpty[2];
+    __shared__ uint32_t tmemBase;
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t numTiles = a.tilesM * a.tilesN * a.splits;
+    const bool lo = a.passes == 3;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < S_SLOTS; s++) { mbar_init(&aFull[s], S_LOAD_WARPS); mbar_init(&bFull[s], 1); mbar_init(&slotEmpty[s], 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(&accFull[s], 1); mbar_init(&accEmpty[s], S_EPI_WARPS); }
+        mbar_fence_init();
+    }
+    if (warp == S_TMA_WARP && lane == 0) { tma_prefetch_desc(&mapHi); tma_prefetch_desc(&mapLo); }
+    if (warp == S_MMA_WARP) tmem_alloc(&tmemBase, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmemBase;
+    const uint32_t ringAddr = smem_u32(smem);
+
+    if (warp < S_LOAD_WARPS) {
+        // ------------------------------------------------------------ A loaders: global -> registers -> tensor memory
+        const uint32_t q = warp & 3, khalf = warp >> 2;
+        typename std::conditional<AMODE == 0, PlanMN, PlanK>::type pa;
+        uint32_t lt = blockIdx.x, lkt = 0, slot = 0, parity = 1;
+        STile ltl = stile_of(a, min(lt, numTiles - 1));
+        bool more = lt < numTiles;
+        pa.init(a.A, a.lda, ltl.m0, ltl.kBegin, a.M, q, khalf, lane);
+        auto fetch = [&](uint32_t (&r)[16]) {
+            pa.load(r, ltl.kBegin + lkt * BK, (a.debug & 512) ? ltl.kBegin : ltl.kEnd);   // bring-up switch 512: no global loads (zero panels)
+            if (++lkt == ltl.numK) {
+                lkt = 0; lt += gridDim.x; more = lt < numTiles;
+                if (more) { ltl = stile_of(a, lt); pa.init(a.A, a.lda, ltl.m0, ltl.kBegin, a.M, q, khalf, lane); }
+            }
+        };
+        auto publish = [&](const uint32_t (&r)[16]) {
+            mbar_wait(&slotEmpty[slot], parity);                                  // the MMAs that read this slot have retired
+            tc_fence_after();
+            pa.store(tmem + ((q * 32) << 16) + S_ACC_COLS + slot * S_A_COLS + khalf * 16, r, lo);
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&aFull[slot]);
+            if (++slot == S_SLOTS) { slot = 0; parity ^= 1; }
+        };
+        // loads run S_DEPTH - 1 panels ahead of the tensor-memory stores
+        uint32_t r[S_DEPTH][16];
+        uint32_t pending = 0;
+#pragma unroll
+        for (int s = 0; s < S_DEPTH - 1; s++)
+            if (more) { fetch(r[s]); pending++; }
+        while (pending) {
+#pragma unroll
+            for (int s = 0; s < S_DEPTH; s++) {
+                if (more) { fetch(r[(s + S_DEPTH - 1) % S_DEPTH]); pending++; }
+                publish(r[s]);
+                if (--pending == 0) break;
+            }
+        }
+    } else if (warp == S_TMA_WARP) {
+        // ------------------------------------------------------------ B producer: one thread drives the TMA engine.
+        // (Measured and dropped, profiles/r2_gemm_stream.md: pulling the streamed A operand into L2 ahead of the loaders with
+        // cp.async.bulk.prefetch.L2 doubled the kernel time -- 32 small bulk operations per k-iteration queue in front of the
+        // B boxes in the TMA unit -- and per-line prefetch.global.L2 changed nothing: the loaders are not DRAM-latency bound.)
+        if (lane == 0) {
+            uint32_t slot = 0, parity = 1;
+            for (uint32_t t = blockIdx.x; t < numTiles; t += gridDim.x) {
+                const STile tl = stile_of(a, t);
+                for (uint32_t kt = 0; kt < tl.numK; kt++) {
+                    mbar_wait(&slotEmpty[slot], parity);
+                    const uint32_t st = ringAddr + slot * SLOT, k0 = tl.kBegin + kt * BK;
+                    mbar_arrive_expect_tx(&bFull[slot], lo ? SLOT : PANEL);
+                    tma_load_2d(st, &mapHi, k0, tl.n0, &bFull[slot]);
+                    if (lo) tma_load_2d(st + PANEL, &mapLo, k0, tl.n0, &bFull[slot]);
+                    if (++slot == S_SLOTS) { slot = 0; parity ^= 1; }
+                }
+            }
+        }
+    } else if (warp == S_MMA_WARP) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            uint32_t slot = 0, ph = 0, seq = 0;
+            for (uint32_t t = blockIdx.x; t < numTiles; t += gridDim.x, seq++) {
+                const STile tl = stile_of(a, t);
+                const uint32_t acc = seq & 1, d = tmem + acc * BN;
+                mbar_wait(&accEmpty[acc], ((seq >> 1) & 1) ^ 1);                  // the epilogue has drained this accumulator
+                tc_fence_after();
+                for (uint32_t kt = 0; kt < tl.numK; kt++) {
+                    mbar_wait(&aFull[slot], ph);
+                    mbar_wait(&bFull[slot], ph);
+                    tc_fence_after();
+                    const uint32_t sb = ringAddr + slot * SLOT, ta = tmem + S_ACC_COLS + slot * S_A_COLS;
+#pragma unroll
+                    for (int j = 0; j < BK / 8; j++) {
+                        const uint64_t bHi = kmajor_desc(sb, j);
+                        const uint32_t aHi = ta + j * 8, first = (kt == 0 && j == 0) ? 0u : 1u;
+                        if (a.debug & 1024) {                                     // bring-up switch 1024: no MMAs
+                        } else if (lo) {
+                            const uint64_t bLo = kmajor_desc(sb + PANEL, j);
+                            mma_tf32_ts(d, aHi + BK, bHi, kIdesc, first);         // small terms first
+                            mma_tf32_ts(d, aHi, bLo, kIdesc, 1u);
+                            mma_tf32_ts(d, aHi, bHi, kIdesc, 1u);
+                        } else {
+                            mma_tf32_ts(d, aHi, bHi, kIdesc, first);
+                        }
+                    }
+                    tc_commit(&slotEmpty[slot]);                                  // shared and tensor memory of the slot reusable once these retire
+                    if (++slot == S_SLOTS) { slot = 0; ph ^= 1; }
+                }
+                tc_commit(&accFull[acc]);
+            }
+        }
+    } else {
+        // ------------------------------------------------------------ epilogue: thread = accumulator row m
+        const uint32_t q = warp & 3;
+        uint32_t seq = 0;
+        for (uint32_t t = blockIdx.x; t < numTiles; t += gridDim.x, seq++) {
+            const STile tl = stile_of(a, t);
+            const uint32_t acc = seq & 1;
+            mbar_wait(&accFull[acc], (seq >> 1) & 1);
+            tc_fence_after();
+            const uint32_t m = tl.m0 + q * 32 + lane;
+            const bool mIn = m < a.M;
+#pragma unroll 1
+            for (int c = 0; c < BN / 32; c++) {
+                float v[32];
+                __syncwarp();                                                     // lanes diverge below (ragged edges): re-converge for the .aligned load
+                tmem_ld32(tmem + ((q * 32) << 16) + acc * BN + c * 32, v);
+                if (c == BN / 32 - 1) {                                           // accumulator fully read: the MMA warp may reuse it
+                    tc_fence_before();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&accEmpty[acc]);
+                }
+                const uint32_t nb = tl.n0 + c * 32;
+                if (!mIn || nb >= a.N) continue;
+                const uint32_t ncol = min(32u, a.N - nb);
+                if (EPI == 0) {
+                    float* o = a.C + (size_t)nb * a.ldc + m;
+                    if (a.beta != 0.0f) {
+#pragma unroll
+                        for (int j = 0; j < 32; j++)
+                            if ((uint32_t)j < ncol) o[(size_t)j * a.ldc] = a.alpha * v[j] + a.beta * o[(size_t)j * a.ldc];
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j++)
+                            if ((uint32_t)j < ncol) o[(size_t)j * a.ldc] = a.alpha * v[j];
+                    }
+                } else if (a.partial) {
+                    float* o = a.partial + ((size_t)tl.split * a.M + m) * a.N + nb;
+                    if (ncol == 32 && (a.N & 3u) == 0) {
+#pragma unroll
+                        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 32; j++) if ((uint32_t)j < ncol) o[j] = v[j];
+                    }
+                } else {
+                    float* o = a.C + (size_t)m * a.ldc + nb;
+#pragma unroll
+                    for (int j = 0; j < 32; j++)
+                        if ((uint32_t)j < ncol) o[j] = a.alpha * v[j] + (a.beta != 0.0f ? a.beta * o[j] : 0.0f);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == S_MMA_WARP) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+// C = alpha * sum_z partial[z] + beta * C, optionally times f'(unit) (kCalculateHadamardProduct, E/kDelta.cu:8979-9032);
+// fixed summation order -> deterministic
+__global__ void __launch_bounds__(256)
+stream_reduce_kernel(const float* __restrict__ partial, uint32_t splits, uint32_t M, uint32_t N, uint32_t ldc, float alpha, float beta, float* __restrict__ C)
+{
+    const size_t total = (size_t)M * N;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t m = (uint32_t)(i / N), n = (uint32_t)(i % N);
+        float s = 0.f;
+        for (uint32_t z = 0; z < splits; z++) s += partial[(size_t)z * total + i];
+        float* c = C + (size_t)m * ldc + n;
+        float x = alpha * s;
+        if (beta != 0.0f) x += beta * *c;
+        *c = x;
+    }
+}
+
+// ---------------------------------------------------------------- operand preparation (streaming, once per call)
+// lo[r][c] = x - trunc_tf32(x) (and optionally hi[r][c] = x) into a pitch-padded copy; columns [cols, ldp) are zeroed
+__global__ void __launch_bounds__(256)
+split_pitch_kernel(const float* __restrict__ src, uint32_t ld, uint32_t rows, uint32_t cols, float* __restrict__ hi, float* __restrict__ lo, uint32_t ldp)
+{
+    const size_t total = (size_t)rows * ldp;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t r = (uint32_t)(i / ldp), c = (uint32_t)(i % ldp);
+        const float x = c < cols ? __ldg(src + (size_t)r * ld + c) : 0.0f;
+        if (hi) hi[i] = x;
+        lo[i] = __uint_as_float(lo_of(__float_as_uint(x)));
+    }
+}
+// XT_hi[c][r] = X[r][c], XT_lo[c][r] = lo(X[r][c]); 32 x 32 tiles through shared memory, pitch ldt >= rows
+__global__ void __launch_bounds__(256)
+transpose_split_kernel(const float* __restrict__ X, uint32_t ldx, uint32_t rows, uint32_t cols, float* __restrict__ hi, float* __restrict__ lo, uint32_t ldt)
+{
+    __shared__ float tile[32][33];
+    const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const uint32_t tilesC = (cols + 31) / 32, tilesR = (ldt + 31) / 32;
+    for (uint32_t t = blockIdx.x; t < tilesC * tilesR; t += gridDim.x) {
+        const uint32_t r0 = (t / tilesC) * 32, c0 = (t % tilesC) * 32;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t r = r0 + ty + 8 * i, c = c0 + tx;
+            tile[ty + 8 * i][tx] = (r < rows && c < cols) ? __ldg(X + (size_t)r * ldx + c) : 0.0f;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t c = c0 + ty + 8 * i, r = r0 + tx;
+            if (c < cols && r < ldt) {
+                const float x = tile[tx][ty + 8 * i];
+                hi[(size_t)c * ldt + r] = x;
+                lo[(size_t)c * ldt + r] = __uint_as_float(lo_of(__float_as_uint(x)));
+            }
+        }
+        __syncthreads();
+    }
+}
+
+// =====================================================================================================================
+// out_fwd_kernel: forward pass of a sigmoid output layer over Boolean sparse targets, loss and delta in the epilogue.
+//   M dimension = output units (TMEM lane = thread = one output column n), N dimension = batch rows, K = hidden units <= 128.
+//   A = W^T slice [128 outputs][K]: read once per work unit with coalesced 32-bit loads, split, RESIDENT in tensor memory
+//       (columns 0..127 hi, 128..255 lo); accumulators in columns 256..511.
+//   B = X batch tile [128 rows][K] (hi = X itself, lo = second array), TMA, ring of 32-k panels.
+//   work unit = (output slice, group of batch tiles); units are dealt round robin to the persistent CTAs.
+//   Epilogue (8 warps: quadrant = warp % 4, batch half of the tile = warp / 4): z = acc + bias[n] -> a = sigmoid(z) -> loss and
+//   delta by the target-is-zero formulas, corrected where the TRANSPOSED target bitmap (one word = 32 batch rows of output n)
+//   says so; delta[b][n] stored as 128-byte rows (32 lanes = 32 consecutive n).  Column sums of delta (the bias gradient,
+//   E/NNWeight.cpp:760-794) accumulate in the thread that owns the column and leave as one partial per (group, half).
+// Warps: 0-7 workers (A load + epilogue), 8 TMA producer, 9 MMA issuer.
+// =====================================================================================================================
+constexpr int F_WORKERS = 8, F_TMA_WARP = 8, F_MMA_WARP = 9, F_THREADS = 10 * 32, F_SLOTS = 6;
+constexpr int F_SMEM_BYTES = F_SLOTS * SLOT + 1024;
+constexpr uint32_t F_A_LO = 128, F_ACC0 = 256;
+
+struct FArgs {
+    const float* W; uint32_t ldw;
+    const float* bias;
+    uint32_t N, K, batch;
+    uint32_t tilesM, tilesB, groups, tilesPerGroup;
+    float* delta; float* unit; uint32_t ldd;
+    const uint32_t* bitsT; uint32_t wordsB;
+    const float* rowW;
+    unsigned long long* acc;
+    float* colPartials;                            // [groups * 2][N] or NULL
+    int passes;
+    float zeroTarget, oneTarget, zeroScale, oneScale, boostZero, boostOne;
+};
+
+__device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+// MUFU exp / log without the denormal fix-up sequences of __expf / __logf (their arguments here are never denormal: log sees
+// max(1e-12, .), and an exp that underflows gives sigmoid = 1 either way)
+__device__ __forceinline__ float exp_fast(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f)); return r; }
+__device__ __forceinline__ float log_fast(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r * 0.6931471805599453f; }
+
+// The hot path: the same values WITHOUT control flow, so that the elements a thread works on interleave and hide the MUFU latency
+// and the unrolled epilogue stays inside the instruction cache (round-2 ncu of the branchy form: 20 % of the stall samples were
+// instruction fetch).  At a non-zero target the reference's Raw and NonZero terms are merged algebraically:
+//   SMCE  zero target: on = x > zeroTarget:  loss -= wz * log(1 - x),        d = wz * x
+//         one  target: on = x < oneTarget:   loss -= wd * oneScale * log(x), d = wd * oneScale * (x - 1)
+//         (the -wz*log(1-x) of the Raw kernel and the +wd*zeroScale*log(1-x) of the NonZero kernel cancel exactly)
+//   CE    loss -= wd * log(nz ? x : 1 - x),  d = wd * (nz ? boostOne * (x - 1) : boostZero * x)
+//   L2    t = nz ? x - 1 : x:  loss += wd/2 * t^2,  d = wd * boost * t * x * (1 - x)
+// so one exp, one reciprocal and one log per element whatever the target.
+template <int EF, bool FAST>
+__device__ __forceinline__ void out_elem_flat(const FArgs& f, float z, bool nz, float wd, float& loss, float& x, float& d)
+{
+    x = FAST ? rcp_approx(1.0f + exp_fast(-z)) : 1.0f / (1.0f + expf(-z));
+    if (EF == DSB200_ERR_L2) {
+        const float t = nz ? x - 1.0f : x;
+        loss += 0.5f * wd * t * t;
+        d = (nz ? f.boostOne : f.boostZero) * wd * t * x * (1.0f - x);
+    } else {
+        const float arg = fmaxf(kMinError, nz ? x : 1.0f - x);
+        const float lg = FAST ? log_fast(arg) : logf(arg);
+        if (EF == DSB200_ERR_SMCE) {
+            const bool on = nz ? (x < f.oneTarget) : (x > f.zeroTarget);
+            const float sc = (nz ? f.oneScale : f.zeroScale) * wd;
+            loss += on ? -sc * lg : 0.0f;
+            d = on ? sc * (nz ? x - 1.0f : x) : 0.0f;
+        } else {
+            loss += -wd * lg;
+            d = wd * (nz ? f.boostOne * (x - 1.0f) : f.boostZero * x);
+        }
+    }
+}
+
+template <int EF, bool FAST, bool HASW>
+__global__ void __launch_bounds__(F_THREADS, 1)
+out_fwd_kernel(const FArgs f, const __grid_constant__ CUtensorMap mapHi, const __grid_constant__ CUtensorMap mapLo)
+{
+    extern __shared__ uint8_t smemRaw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>(((uintptr_t)smemRaw + 1023) & ~(uintptr_t)1023);
+    __shared__ uint64_t bFull[F_SLOTS], bEmpty[F_SLOTS], accFull[2], accEmpty[2], aReady;
+    __shared__ uint32_t tmemBase;
+
+    const uint32_t warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t numUnits = f.tilesM * f.groups;
+    const uint32_t numK = (f.K + BK - 1) / BK;                                   // <= 4
+    const bool lo = f.passes == 3;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < F_SLOTS; s++) { mbar_init(&bFull[s], 1); mbar_init(&bEmpty[s], 1); }
+        for (int s = 0; s < 2; s++) { mbar_init(&accFull[s], 1); mbar_init(&accEmpty[s], F_WORKERS); }
+        mbar_init(&aReady, F_WORKERS);
+        mbar_fence_init();
+    }
+    if (warp == F_TMA_WARP && lane == 0) { tma_prefetch_desc(&mapHi); tma_prefetch_desc(&mapLo); }
+    if (warp == F_MMA_WARP) tmem_alloc(&tmemBase, TMEM_COLS);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = tmemBase;
+    const uint32_t ringAddr = smem_u32(smem);
+
+    if (warp < F_WORKERS) {
+        // ------------------------------------------------------------ workers
+        const uint32_t q = warp & 3, h = warp >> 2;
+        const uint32_t laneBase = (q * 32) << 16;
+        float loss = 0.0f;
+        uint32_t seq = 0;
+        // this thread's part of a unit's W^T slice: row n = m0 + 32 q + lane, k in [64 h, 64 h + 64)
+        uint32_t ra[64];
+        auto fetchA = [&](uint32_t unit) {
+            const uint32_t n = (unit / f.groups) * BM + q * 32 + lane;
+            const float* p = f.W + (size_t)(64 * h) * f.ldw + n;
+            const bool nIn = n < f.N;
+#pragma unroll
+            for (int e = 0; e < 64; e++) ra[e] = (nIn && 64 * h + e < f.K) ? ldg_nc_u32(p + (size_t)e * f.ldw) : 0u;
+        };
+        auto storeA = [&]() {
+#pragma unroll
+            for (int g = 0; g < 4; g++) {
+                uint32_t t[16];
+#pragma unroll
+                for (int e = 0; e < 16; e++) t[e] = hi_of(ra[16 * g + e]);
+                tmem_st16(tmem + laneBase + 64 * h + 16 * g, t);
+                if (lo) {
+#pragma unroll
+                    for (int e = 0; e < 16; e++) t[e] = lo_of(ra[16 * g + e]);
+                    tmem_st16(tmem + laneBase + F_A_LO + 64 * h + 16 * g, t);
+                }
+            }
+            tmem_st_wait();
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&aReady);
+        };
+        uint32_t unit = blockIdx.x;
+        if (unit < numUnits) { fetchA(unit); storeA(); }
+        for (; unit < numUnits; unit += gridDim.x) {
+            const uint32_t next = unit + gridDim.x;
+            if (next < numUnits) fetchA(next);                                    // in flight during this unit's epilogues
+            const uint32_t mT = unit / f.groups, g = unit % f.groups;
+            const uint32_t n = mT * BM + q * 32 + lane;
+            const bool nIn = n < f.N;
+            const float bias = (nIn && f.bias) ? __ldg(f.bias + n) : 0.0f;
+            const uint32_t bt0 = g * f.tilesPerGroup, bt1 = min(f.tilesB, bt0 + f.tilesPerGroup);
+            float colSum = 0.0f;
+            for (uint32_t bt = bt0; bt < bt1; bt++, seq++) {
+                const uint32_t acc = seq & 1;
+                // this thread's two target words of the tile (32 batch rows each), requested before the accumulator is waited for
+                const uint32_t w0 = (bt * BN + h * 64) >> 5;
+                const uint32_t bits0 = (nIn && w0 < f.wordsB) ? __ldg(f.bitsT + (size_t)n * f.wordsB + w0) : 0u;
+                const uint32_t bits1 = (nIn && w0 + 1 < f.wordsB) ? __ldg(f.bitsT + (size_t)n * f.wordsB + w0 + 1) : 0u;
+                __syncwarp();
+                mbar_wait(&accFull[acc], (seq >> 1) & 1);
+                tc_fence_after();
+                if (bt + 1 == bt1 && next < numUnits) storeA();                   // every MMA of this unit has retired: A may be replaced
+#pragma unroll 1
+                for (int c = 0; c < 2; c++) {
+                    float v[32];
+                    __syncwarp();                                                 // lanes diverge below (ragged edges): re-converge for the .aligned load
+                    tmem_ld32(tmem + laneBase + F_ACC0 + acc * BN + h * 64 + c * 32, v);
+                    if (c == 1) {                                                 // this warp's half of the accumulator is in registers
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&accEmpty[acc]);
+                    }
+                    const uint32_t b0 = bt * BN + h * 64 + c * 32;
+                    if (!nIn || b0 >= f.batch) continue;
+                    const uint32_t bits = c ? bits1 : bits0;                  // the host guarantees batch % 32 == 0: all 32 rows exist
+                    float* o = f.delta + (size_t)b0 * f.ldd + n;
+                    float l0 = 0.0f, l1 = 0.0f;
+#pragma unroll
+                    for (int hh = 0; hh < 2; hh++) {
+                        float x[16], d[16];
+#pragma unroll
+                        for (int j = 0; j < 16; j++) {
+                            const float wd = HASW ? __ldg(f.rowW + b0 + 16 * hh + j) : 1.0f;
+                            out_elem_flat<EF, FAST>(f, v[16 * hh + j] + bias, (bits >> (16 * hh + j)) & 1u, wd, (j & 1) ? l1 : l0, x[j], d[j]);
+                        }
+#pragma unroll
+                        for (int j = 0; j < 16; j++) { *o = d[j]; o += f.ldd; colSum += d[j]; }
+                        if (f.unit) {
+                            float* u = f.unit + (size_t)(b0 + 16 * hh) * f.ldd + n;
+#pragma unroll
+                            for (int j = 0; j < 16; j++) { *u = x[j]; u += f.ldd; }
+                        }
+                    }
+                    loss += l0 + l1;
+                }
+            }
+            if (f.colPartials && nIn) f.colPartials[(size_t)(g * 2 + h) * f.N + n] = colSum;
+        }
+        if (f.acc) {
+            const double e = warp_sum((double)loss);
+            if (lane == 0 && e != 0.0) atomicAdd(f.acc, (unsigned long long)llrint(e * (double)kErrorScaleF));
+        }
+    } else if (warp == F_TMA_WARP) {
+        // ------------------------------------------------------------ B producer
+        if (lane == 0) {
+            uint32_t slot = 0, parity = 1;
+            for (uint32_t unit = blockIdx.x; unit < numUnits; unit += gridDim.x) {
+                const uint32_t g = unit % f.groups;
+                const uint32_t bt0 = g * f.tilesPerGroup, bt1 = min(f.tilesB, bt0 + f.tilesPerGroup);
+                for (uint32_t bt = bt0; bt < bt1; bt++)
+                    for (uint32_t kt = 0; kt < numK; kt++) {
+                        mbar_wait(&bEmpty[slot], parity);
+                        const uint32_t st = ringAddr + slot * SLOT;
+                        mbar_arrive_expect_tx(&bFull[slot], lo ? SLOT : PANEL);
+                        tma_load_2d(st, &mapHi, kt * BK, bt * BN, &bFull[slot]);
+                        if (lo) tma_load_2d(st + PANEL, &mapLo, kt * BK, bt * BN, &bFull[slot]);
+                        if (++slot == F_SLOTS) { slot = 0; parity ^= 1; }
+                    }
+            }
+        }
+    } else if (warp == F_MMA_WARP) {
+        // ------------------------------------------------------------ MMA issuer
+        if (lane == 0) {
+            uint32_t slot = 0, ph = 0, seq = 0, ui = 0;
+            for (uint32_t unit = blockIdx.x; unit < numUnits; unit += gridDim.x, ui++) {
+                const uint32_t g = unit % f.groups;
+                const uint32_t bt0 = g * f.tilesPerGroup, bt1 = min(f.tilesB, bt0 + f.tilesPerGroup);
+                mbar_wait(&aReady, ui & 1);                                       // this unit's W^T slice is in tensor memory
+                tc_fence_after();
+                for (uint32_t bt = bt0; bt < bt1; bt++, seq++) {
+                    const uint32_t acc = seq & 1, d = tmem + F_ACC0 + acc * BN;
+                    mbar_wait(&accEmpty[acc], ((seq >> 1) & 1) ^ 1);
+                    tc_fence_after();
+                    for (uint32_t kt = 0; kt < numK; kt++) {
+                        mbar_wait(&bFull[slot], ph);
+                        tc_fence_after();
+                        const uint32_t sb = ringAddr + slot * SLOT;
+#pragma unroll
+                        for (int j = 0; j < BK / 8; j++) {
+                            const uint64_t bHi = kmajor_desc(sb, j);
+                            const uint32_t aHi = tmem + kt * BK + j * 8, first = (kt == 0 && j == 0) ? 0u : 1u;
+                            if (lo) {
+                                const uint64_t bLo = kmajor_desc(sb + PANEL, j);
+                                mma_tf32_ts(d, aHi + F_A_LO, bHi, kIdesc, first); // small terms first
+                                mma_tf32_ts(d, aHi, bLo, kIdesc, 1u);
+                                mma_tf32_ts(d, aHi, bHi, kIdesc, 1u);
+                            } else {
+                                mma_tf32_ts(d, aHi, bHi, kIdesc, first);
+                            }
+                        }
+                        tc_commit(&bEmpty[slot]);
+                        if (++slot == F_SLOTS) { slot = 0; ph ^= 1; }
+                    }
+                    tc_commit(&accFull[acc]);
+                }
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == F_MMA_WARP) tmem_dealloc(tmem, TMEM_COLS);
+}
+
+// transposed target bitmap: bit (b % 32) of bitsT[c][b / 32] = output c is a non-zero target of batch row b (cleared by the caller)
+__global__ void __launch_bounds__(256)
+target_bitmap_t_kernel(const dsb200_params P, const dsb200_sparse S, uint32_t position, uint32_t batch, uint32_t width, uint32_t wordsB,
+                       uint32_t* __restrict__ bitsT, float* __restrict__ rowW)
+{
+    for (uint32_t b = blockIdx.x; b < batch; b += gridDim.x) {
+        const uint32_t ex = example_of(P, S.index, position, b);
+        const uint64_t rs = __ldg(S.sparseStart + ex), re = __ldg(S.sparseEnd + ex);
+        for (uint64_t j = rs + threadIdx.x; j < re; j += blockDim.x) {
+            const uint32_t c = __ldg(S.sparseIndex + j);
+            if (c < width) atomicOr(bitsT + (size_t)c * wordsB + (b >> 5), 1u << (b & 31));
+        }
+        if (threadIdx.x == 0 && rowW) rowW[b] = S.dataWeight ? __ldg(S.dataWeight + ex) : 1.0f;
+    }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                  const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn()
+{
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult qr;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qr) == cudaSuccess && qr == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+
+// K-major operand [rows][cols] (cols contiguous, pitch ld floats, ld % 4 == 0, base 16-byte aligned): boxes of 32 x 128
+static bool make_map(CUtensorMap* m, const float* base, uint32_t rows, uint32_t cols, uint32_t ld)
+{
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    const cuuint64_t dims[2] = {cols, rows};
+    const cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(float)};
+    const cuuint32_t box[2] = {BK, BN};
+    const cuuint32_t estr[2] = {1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+              CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+static inline uint32_t up4(uint32_t x) { return (x + 3u) & ~3u; }
+static inline bool tma_ok(const float* p, uint32_t ld) { return (((uintptr_t)p) & 15u) == 0 && (ld & 3u) == 0; }
+
+}  // namespace gs
+
+// grow-only scratch of the streamed GEMMs (operand copies, split-K partials, target bitmap), carved per call
+static int gs_reserve(dsb200_ctx* ctx, size_t bytes)
+{
+    if (bytes <= ctx->gsWsBytes) return 0;
+    if (ctx->dGsWs) { DSB_CUDA_OK(cudaStreamSynchronize(ctx->stream)); DSB_CUDA_OK(cudaFree(ctx->dGsWs)); ctx->dGsWs = nullptr; ctx->gsWsBytes = 0; }
+    bytes += bytes / 8;
+    DSB_CUDA_OK(cudaMalloc(&ctx->dGsWs, bytes));
+    ctx->gsWsBytes = bytes;
+    return 0;
+}
+static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+
+bool gemm_stream_available() { return gs::encode_fn() != nullptr; }
+
+// G[k][n] = beta * G + alpha * X[B][k]^T * D[B][n]      (swapped: M = n, N = k, K = B; A = D read with m contiguous)
+int gemm_stream_dw(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, float alpha, const float* X, const float* D, uint32_t ldd, float beta,
+                   float* G, uint32_t ldg)
+{
+    using namespace gs;
+    static bool attrSet = false;
+    if (!attrSet) {
+        DSB_CUDA_OK(cudaFuncSetAttribute(stream_kernel<0, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, S_SMEM_BYTES));
+        attrSet = true;
+    }
+    const uint32_t ldt = up4(B);
+    const size_t opBytes = al256((size_t)k * ldt * sizeof(float));
+    int rc = gs_reserve(ctx, 2 * opBytes);
+    if (rc) return rc;
+    float* xtHi = reinterpret_cast<float*>(ctx->dGsWs);
+    float* xtLo = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ctx->dGsWs) + opBytes);
+    {
+        const uint32_t tiles = ((k + 31) / 32) * ((ldt + 31) / 32);
+        transpose_split_kernel<<<std::min<uint32_t>(tiles, (uint32_t)ctx->numSMs * 8), 256, 0, ctx->stream>>>(X, k, B, k, xtHi, xtLo, ldt);
+        count_launch();
+    }
+    CUtensorMap mh, ml;
+    if (!make_map(&mh, xtHi, k, B, ldt) || !make_map(&ml, xtLo, k, B, ldt)) return fail(ctx, DSB200_ESTATE, "gemm_stream_dw: cuTensorMapEncodeTiled failed");
+    SArgs a{};
+    a.A = D; a.lda = ldd; a.M = n; a.N = k; a.K = B;
+    a.tilesM = (n + BM - 1) / BM; a.tilesN = (k + BN - 1) / BN; a.splits = 1; a.kPerSplit = ((B + BK - 1) / BK) * BK;
+    a.C = G; a.ldc = ldg; a.partial = nullptr; a.alpha = alpha; a.beta = beta;
+    a.passes = (ctx->gemmMode == DSB200_GEMM_TF32) ? 1 : 3;
+    a.debug = ctx->gemmDebug;
+    const uint32_t grid = std::min<uint32_t>((uint32_t)ctx->numSMs, a.tilesM * a.tilesN);
+    stream_kernel<0, 0><<<grid, S_THREADS, S_SMEM_BYTES, ctx->stream>>>(a, mh, ml);
+    DSB_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+// Dp[B][k] = beta * Dp + D[B][n] * W[k][n]^T            (M = B, N = k, K = n split; A = D read with k contiguous)
+int gemm_stream_dx(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, const float* D, uint32_t ldd, const float* W, uint32_t ldw, float beta,
+                   float* Dp, uint32_t ldp)
+{
+    using namespace gs;
+    static bool attrSet = false;
+    if (!attrSet) {
+        DSB_CUDA_OK(cudaFuncSetAttribute(stream_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, S_SMEM_BYTES));
+        attrSet = true;
+    }
+    SArgs a{};
+    a.A = D; a.lda = ldd; a.M = B; a.N = k; a.K = n;
+    a.tilesM = (B + BM - 1) / BM; a.tilesN = (k + BN - 1) / BN;
+    const uint32_t tilesMN = a.tilesM * a.tilesN, kTiles = (n + BK - 1) / BK, sms = (uint32_t)ctx->numSMs;
+    // split K so that the persistent grid runs whole rounds: minimise rounds * (k-iterations + fixed tile cost)
+    uint32_t splits = 1;
+    if (ctx->gemmSplits > 0) splits = std::min<uint32_t>((uint32_t)ctx->gemmSplits, kTiles);
+    else {
+        uint64_t best = ~0ull;
+        for (uint32_t s = 1; s <= 64 && s * 8 <= std::max(kTiles, 8u); s++) {
+            const uint32_t per = (kTiles + s - 1) / s, real = (kTiles + per - 1) / per;
+            const uint64_t rounds = ((uint64_t)tilesMN * real + sms - 1) / sms;
+            const uint64_t cost = rounds * (per + 12) + (real > 1 ? (uint64_t)real * tilesMN / sms + 4 : 0);
+            if (cost < best) { best = cost; splits = real; }
+        }
+    }
+    const uint32_t per = (kTiles + splits - 1) / splits;
+    splits = (kTiles + per - 1) / per;
+    a.splits = splits; a.kPerSplit = per * BK;
+    // operand copies: lo always; hi only when W itself cannot be a tensor map (pitch not a multiple of 16 bytes)
+    const bool direct = tma_ok(W, ldw);
+    const uint32_t ldc = up4(n);
+    const size_t opBytes = al256((size_t)k * ldc * sizeof(float));
+    const size_t partBytes = splits > 1 ? al256((size_t)splits * B * k * sizeof(float)) : 0;
+    int rc = gs_reserve(ctx, 2 * opBytes + partBytes);
+    if (rc) return rc;
+    uint8_t* ws = reinterpret_cast<uint8_t*>(ctx->dGsWs);
+    float* wLo = reinterpret_cast<float*>(ws);
+    float* wHi = direct ? nullptr : reinterpret_cast<float*>(ws + opBytes);
+    a.partial = splits > 1 ? reinterpret_cast<float*>(ws + 2 * opBytes) : nullptr;
+    {
+        const size_t total = (size_t)k * ldc;
+        const uint32_t blocks = (uint32_t)std::min<size_t>((total + 255) / 256, (size_t)ctx->numSMs * 16);
+        split_pitch_kernel<<<blocks, 256, 0, ctx->stream>>>(W, ldw, k, n, wHi, wLo, ldc);
+        count_launch();
+    }
+    CUtensorMap mh, ml;
+    const bool ok = (direct ? make_map(&mh, W, k, n, ldw) : make_map(&mh, wHi, k, n, ldc)) && make_map(&ml, wLo, k, n, ldc);
+    if (!ok) return fail(ctx, DSB200_ESTATE, "gemm_stream_dx: cuTensorMapEncodeTiled failed");
+    a.C = Dp; a.ldc = ldp; a.alpha = 1.0f; a.beta = beta;
+    a.passes = (ctx->gemmMode == DSB200_GEMM_TF32) ? 1 : 3;
+    a.debug = ctx->gemmDebug;
+    const uint32_t grid = std::min<uint32_t>(sms, tilesMN * splits);
+    stream_kernel<1, 1><<<grid, S_THREADS, S_SMEM_BYTES, ctx->stream>>>(a, mh, ml);
+    DSB_CUDA_OK(cudaGetLastError());
+    count_launch();
+    if (splits > 1) {
+        const size_t total = (size_t)B * k;
+        const uint32_t blocks = (uint32_t)std::min<size_t>((total + 255) / 256, (size_t)ctx->numSMs * 8);
+        stream_reduce_kernel<<<blocks, 256, 0, ctx->stream>>>(a.partial, splits, B, k, ldp, 1.0f, beta, Dp);
+        DSB_CUDA_OK(cudaGetLastError());
+        count_launch();
+    }
+    return 0;
+}
+
+// forward + loss + delta of a sigmoid output layer (see out_fwd_kernel).  pColPartials: optional [*pNumPartials][n] column sums of delta.
+int gemm_stream_out_fwd(dsb200_ctx* ctx, const dsb200_sparse* s, int ef, uint32_t position, uint32_t batch, uint32_t k, uint32_t n, const float* X,
+                        const float* W, uint32_t ldw, const float* bias, float* unitOut, float* delta, uint32_t ldd, unsigned long long* acc,
+                        float* pColPartials, uint32_t* pNumPartials)
+{
+    using namespace gs;
+    if (k > 128 || !tma_ok(X, k) || (batch & 31u)) return DSB200_EUNSUPPORTED;
+    static bool attrSet = false;
+    if (!attrSet) {
+#define DSB_ATTR(EF) \
+        DSB_CUDA_OK(cudaFuncSetAttribute(out_fwd_kernel<EF, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_BYTES)); \
+        DSB_CUDA_OK(cudaFuncSetAttribute(out_fwd_kernel<EF, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_BYTES)); \
+        DSB_CUDA_OK(cudaFuncSetAttribute(out_fwd_kernel<EF, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_BYTES)); \
+        DSB_CUDA_OK(cudaFuncSetAttribute(out_fwd_kernel<EF, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_BYTES));
+        DSB_ATTR(DSB200_ERR_SMCE) DSB_ATTR(DSB200_ERR_CROSS_ENTROPY) DSB_ATTR(DSB200_ERR_L2)
+#undef DSB_ATTR
+        attrSet = true;
+    }
+    FArgs f{};
+    f.W = W; f.ldw = ldw; f.bias = bias; f.N = n; f.K = k; f.batch = batch;
+    f.tilesM = (n + BM - 1) / BM; f.tilesB = (batch + BN - 1) / BN;
+    // groups of batch tiles per output slice: minimise rounds * (tiles per unit + unit overhead)
+    uint32_t bestG = 1; double bestCost = 1e30;
+    for (uint32_t g = 1; g <= f.tilesB; g++) {
+        const uint32_t tpg = (f.tilesB + g - 1) / g, real = (f.tilesB + tpg - 1) / tpg;
+        const uint32_t rounds = (f.tilesM * real + (uint32_t)ctx->numSMs - 1) / (uint32_t)ctx->numSMs;
+        const double cost = rounds * (tpg + 0.35);
+        if (cost < bestCost - 1e-9) { bestCost = cost; bestG = real; }
+    }
+    f.tilesPerGroup = (f.tilesB + bestG - 1) / bestG;
+    f.groups = (f.tilesB + f.tilesPerGroup - 1) / f.tilesPerGroup;
+    f.delta = delta; f.unit = unitOut; f.ldd = ldd;
+    f.wordsB = (batch + 31) / 32;
+    const size_t bitsBytes = al256((size_t)n * f.wordsB * sizeof(uint32_t));
+    const size_t rowBytes = al256((size_t)batch * sizeof(float));
+    const size_t loBytes = al256((size_t)batch * k * sizeof(float));
+    int rc = gs_reserve(ctx, bitsBytes + rowBytes + loBytes);
+    if (rc) return rc;
+    uint8_t* ws = reinterpret_cast<uint8_t*>(ctx->dGsWs);
+    uint32_t* bitsT = reinterpret_cast<uint32_t*>(ws);
+    float* rowW = s->dataWeight ? reinterpret_cast<float*>(ws + bitsBytes) : nullptr;
+    float* xLo = reinterpret_cast<float*>(ws + bitsBytes + rowBytes);
+    DSB_CUDA_OK(cudaMemsetAsync(bitsT, 0, (size_t)n * f.wordsB * sizeof(uint32_t), ctx->stream));
+    target_bitmap_t_kernel<<<std::min<uint32_t>(batch, (uint32_t)ctx->numSMs * 8), 256, 0, ctx->stream>>>(ctx->params, *s, position, batch, n, f.wordsB, bitsT, rowW);
+    count_launch();
+    f.passes = (ctx->gemmMode == DSB200_GEMM_TF32) ? 1 : 3;
+    if (f.passes == 3) {
+        const size_t total = (size_t)batch * k;
+        split_pitch_kernel<<<(uint32_t)std::min<size_t>((total + 255) / 256, (size_t)ctx->numSMs * 8), 256, 0, ctx->stream>>>(X, k, batch, k, nullptr, xLo, k);
+        count_launch();
+    }
+    CUtensorMap mh, ml;
+    if (!make_map(&mh, X, batch, k, k) || !make_map(&ml, xLo, batch, k, k)) return fail(ctx, DSB200_ESTATE, "gemm_stream_out_fwd: cuTensorMapEncodeTiled failed");
+    f.bitsT = bitsT; f.rowW = rowW; f.acc = acc; f.colPartials = pColPartials;
+    if (pNumPartials) *pNumPartials = f.groups * 2;
+    f.zeroTarget = ctx->params.SMCE_zeroTarget; f.oneTarget = ctx->params.SMCE_oneTarget;
+    f.zeroScale = ctx->params.SMCE_zeroScale; f.oneScale = ctx->params.SMCE_oneScale;
+    f.boostZero = ctx->params.deltaBoost_zero; f.boostOne = ctx->params.deltaBoost_one;
+    const uint32_t grid = std::min<uint32_t>((uint32_t)ctx->numSMs, f.tilesM * f.groups);
+#define DSB_GO(EF)                                                                                                       \
+    do {                                                                                                                 \
+        if (ctx->fastMath) { if (rowW) out_fwd_kernel<EF, true, true><<<grid, F_THREADS, F_SMEM_BYTES, ctx->stream>>>(f, mh, ml);    \
+                             else      out_fwd_kernel<EF, true, false><<<grid, F_THREADS, F_SMEM_BYTES, ctx->stream>>>(f, mh, ml); } \
+        else               { if (rowW) out_fwd_kernel<EF, false, true><<<grid, F_THREADS, F_SMEM_BYTES, ctx->stream>>>(f, mh, ml);   \
+                             else      out_fwd_kernel<EF, false, false><<<grid, F_THREADS, F_SMEM_BYTES, ctx->stream>>>(f, mh, ml); }\
+    } while (0)
+    if (ef == DSB200_ERR_SMCE) DSB_GO(DSB200_ERR_SMCE);
+    else if (ef == DSB200_ERR_CROSS_ENTROPY) DSB_GO(DSB200_ERR_CROSS_ENTROPY);
+    else DSB_GO(DSB200_ERR_L2);
+#undef DSB_GO
+    DSB_CUDA_OK(cudaGetLastError());
+    count_launch();
+    return 0;
+}
+
+}  // namespace dsb

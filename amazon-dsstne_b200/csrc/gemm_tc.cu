@@ -286,70 +286,6 @@ __device__ __forceinline__ void store_rows(uint32_t sp, float* __restrict__ o, u
 struct Tile { uint32_t m0, n0, split, kBegin, kEnd, numK; };
 __device__ __forceinline__ Tile tile_of(const Args& a, uint32_t t);
 
-// ---- fused output pass (EXPERIMENTAL, written at the end of round 1 without GPU time left: not yet run) ----------------------
-// The forward GEMM of a sparse-target output layer followed by dsb200_output_pass writes Z (112 MB on BASELINE config 2), reads
-// it back, and writes delta.  In the FUSED instantiation of gemm_tc_ts_kernel the epilogue finishes the element itself:
-// z = acc + bias -> a = sigmoid(z) -> loss and delta with the target-is-zero formulas, corrected where the row's target bitmap
-// says so (the expressions of raw_sigmoid / nz_elem in output_pass.cu, i.e. E/kLoss.cu:595-691,1749-1865,2213-2352 and
-// E/kDelta.cu:2193-2232,6533-6572,7182-7227, for Boolean targets without SparseIgnoreZero).  Z never exists.
-// The parameters live in constant memory and not in Args: growing the kernel parameter block changes the code generated for
-// EVERY instantiation, and the default kernels are kept instruction-identical to the ones the GPU test runs have covered.
-struct FusedOut {
-    const uint32_t* bits;                      // [M][words]: bit n of row b = output n is a non-zero (Boolean) target of batch row b
-    const float*    rowW;                      // [M] data weight of the row's example, or NULL
-    uint32_t        words;
-    int             ef, fast;                  // DSB200_ERR_*, option "fast_math"
-    float           zeroTarget, oneTarget, zeroScale, oneScale, boostZero, boostOne;
-    float*          unit;                      // optional activations [M][N]
-    unsigned long long* acc;                   // optional fixed-point loss accumulator
-};
-__constant__ FusedOut c_fused;
-
-__device__ __forceinline__ float fused_rcp(float v) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(v)); return r; }   // as output_pass.cu
-__device__ __forceinline__ float fused_elem(float z, bool nz, float wd, float& loss, float& x)
-{
-    const FusedOut& f = c_fused;
-    const bool fast = f.fast != 0;
-    x = fast ? fused_rcp(1.0f + __expf(-z)) : 1.0f / (1.0f + expf(-z));
-    const float l1mx = fast ? __logf(fmaxf(kMinError, 1.0f - x)) : logf(fmaxf(kMinError, 1.0f - x));
-    float d;
-    if (f.ef == DSB200_ERR_SMCE) {
-        const float wz = f.zeroScale * wd;
-        const bool on = x > f.zeroTarget;
-        loss += on ? -wz * l1mx : 0.0f;
-        d = on ? wz * x : 0.0f;
-        if (nz) {
-            if (on) loss += wd * f.zeroScale * l1mx;
-            if (x < f.oneTarget) {
-                const float lx = fast ? __logf(fmaxf(kMinError, x)) : logf(fmaxf(kMinError, x));
-                loss += -wd * f.oneScale * lx;
-                d = f.oneScale * wd * (x - 1.0f);
-            } else d = 0.0f;
-        }
-    } else if (f.ef == DSB200_ERR_CROSS_ENTROPY) {
-        loss += -wd * l1mx;
-        d = f.boostZero * wd * x;
-        if (nz) {
-            const float lx = fast ? __logf(fmaxf(kMinError, x)) : logf(fmaxf(kMinError, x));
-            loss += wd * (-lx + l1mx);
-            d = f.boostOne * wd * (x - 1.0f);
-        }
-    } else {                                                                  // L2
-        loss += 0.5f * wd * x * x;
-        d = f.boostZero * wd * x * x * (1.0f - x);
-        if (nz) {
-            loss += 0.5f * wd * ((x - 1.0f) * (x - 1.0f) - x * x);
-            d = f.boostOne * wd * (x - 1.0f) * x * (1.0f - x);
-        }
-    }
-    return d;
-}
-
-// the epilogue role of the FUSED instantiation: the structure of epilogue_role below (kept separate so that its code is untouched)
-__device__ __forceinline__ void epilogue_role_fused(const Args& a, uint32_t tmem, float* epiStage, uint64_t* accFullBar, uint64_t* accEmptyBar,
-                                                    uint32_t warp, uint32_t lane, uint32_t numTiles);
-
-
 __device__ __forceinline__ Tile tile_of(const Args& a, uint32_t t)
 {
     // m fastest: CTAs running at the same time share the B (weight / delta column) tile through L2
@@ -422,73 +358,6 @@ __device__ __forceinline__ void epilogue_role(const Args& a, uint32_t tmem, floa
             }
             __syncwarp();                                                     // staging tile free for the next half
         }
-    }
-}
-
-__device__ __forceinline__ void epilogue_role_fused(const Args& a, uint32_t tmem, float* epiStage, uint64_t* accFullBar, uint64_t* accEmptyBar,
-                                                    uint32_t warp, uint32_t lane, uint32_t numTiles)
-{
-    const FusedOut& f = c_fused;
-    const uint32_t rowBase = (warp & 3) * 32;
-    const uint32_t stageAddr = smem_u32(epiStage + (warp - EPI_WARP0) * (32 * EPI_LD));
-    float loss = 0.0f;
-    uint32_t seq = 0;
-    for (uint32_t t = blockIdx.x; t < numTiles; t += gridDim.x, seq++) {
-        const Tile tl = tile_of(a, t);
-        const uint32_t acc = seq & 1;
-        mbar_wait(&accFullBar[acc], (seq >> 1) & 1);
-        tc_fence_after();
-        const uint32_t mBase = tl.m0 + rowBase;
-        const uint32_t rows = (mBase < a.M) ? min(32u, a.M - mBase) : 0u;
-#pragma unroll 1
-        for (int half = 0; half < BN / EPI_COLS; half++) {
-            {
-                float v[32];
-                tmem_ld32(tmem + (rowBase << 16) + acc * BN + half * EPI_COLS, v);
-#pragma unroll
-                for (int j = 0; j < 32; j += 4)
-                    asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(stageAddr + (lane * EPI_LD + j) * 4), "f"(v[j]), "f"(v[j + 1]), "f"(v[j + 2]), "f"(v[j + 3]) : "memory");
-            }
-            if (half == BN / EPI_COLS - 1) {                                  // accumulator fully read: the MMA warp may reuse it
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&accEmptyBar[acc]);
-            }
-            __syncwarp();
-            // 32 columns per pass = ONE word of a row's target bitmap: lanes 0-15 take the even rows, lanes 16-31 the odd rows, 2 columns each
-            const uint32_t c0 = half * EPI_COLS + (lane & 15) * 2, nc = tl.n0 + c0;
-            const uint32_t ncol = (nc < a.N) ? min(2u, a.N - nc) : 0u;
-            const uint32_t rsel = lane >> 4, word = (tl.n0 + half * EPI_COLS) >> 5, shift = (lane & 15) * 2;
-            if (ncol) {
-                const float bias0 = a.bias ? __ldg(a.bias + nc) : 0.0f;
-                const float bias1 = (a.bias && ncol > 1) ? __ldg(a.bias + nc + 1) : 0.0f;
-                const bool vec2 = ncol == 2 && a.vecC >= 2;
-                uint32_t sp = stageAddr + (rsel * EPI_LD + (lane & 15) * 2) * 4;
-                for (uint32_t r = rsel; r < rows; r += 2, sp += 2 * EPI_LD * 4) {
-                    float z0, z1;
-                    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(z0), "=f"(z1) : "r"(sp));
-                    const uint32_t b = mBase + r;
-                    const uint32_t bits = (__ldg(f.bits + (size_t)b * f.words + word) >> shift) & 3u;
-                    const float wd = f.rowW ? __ldg(f.rowW + b) : 1.0f;
-                    float x0 = 0.0f, x1 = 0.0f, d1 = 0.0f;
-                    const float d0 = fused_elem(z0 + bias0, (bits & 1u) != 0, wd, loss, x0);
-                    if (ncol > 1) d1 = fused_elem(z1 + bias1, (bits & 2u) != 0, wd, loss, x1);
-                    float* o = a.C + (size_t)b * a.ldc + nc;                  // C = delta
-                    if (vec2) *reinterpret_cast<float2*>(o) = make_float2(d0, d1);
-                    else { o[0] = d0; if (ncol > 1) o[1] = d1; }
-                    if (f.unit) {
-                        float* u = f.unit + (size_t)b * a.ldc + nc;
-                        if (vec2) *reinterpret_cast<float2*>(u) = make_float2(x0, x1);
-                        else { u[0] = x0; if (ncol > 1) u[1] = x1; }
-                    }
-                }
-            }
-            __syncwarp();                                                     // staging tile free for the next half
-        }
-    }
-    if (f.acc) {
-        const double e = warp_sum((double)loss);
-        if (lane == 0 && e != 0.0) atomicAdd(f.acc, (unsigned long long)llrint(e * (double)kErrorScaleF));
     }
 }
 
@@ -1023,7 +892,7 @@ struct TmemAPlanCoal {
     }
 };
 
-template <bool AMN, bool BMN, bool COAL = false, bool FUSED = false>
+template <bool AMN, bool BMN, bool COAL = false>
 __global__ void __launch_bounds__(THREADS, 1)
 gemm_tc_ts_kernel(const Args a)
 {
@@ -1177,8 +1046,7 @@ gemm_tc_ts_kernel(const Args a)
             }
         }
     } else {
-        if (FUSED) epilogue_role_fused(a, tmem, epiStage, accFullBar, accEmptyBar, warp, lane, numTiles);
-        else       epilogue_role(a, tmem, epiStage, accFullBar, accEmptyBar, warp, lane, numTiles);
+        epilogue_role(a, tmem, epiStage, accFullBar, accEmptyBar, warp, lane, numTiles);
     }
     tc_fence_before();
     __syncthreads();
@@ -1317,79 +1185,6 @@ int gemm_tc_launch(dsb200_ctx* ctx, const float* A, int aMN, uint32_t lda, const
         DSB_CUDA_OK(cudaGetLastError());
         count_launch();
     }
-    return 0;
-}
-
-// ---- fused forward + output pass: host side -------------------------------------------------------------------------------------
-namespace tc {
-
-// one block per batch row: clear the row's bitmap, set the bits of its (Boolean) targets, note its data weight
-__global__ void __launch_bounds__(256)
-target_bitmap_kernel(const dsb200_params P, const dsb200_sparse S, uint32_t position, uint32_t batch, uint32_t width, uint32_t words,
-                     uint32_t* __restrict__ bits, float* __restrict__ rowW)
-{
-    for (uint32_t b = blockIdx.x; b < batch; b += gridDim.x) {
-        const uint32_t ex = example_of(P, S.index, position, b);
-        uint32_t* row = bits + (size_t)b * words;
-        for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) row[i] = 0u;
-        __syncthreads();
-        const uint64_t rs = __ldg(S.sparseStart + ex), re = __ldg(S.sparseEnd + ex);
-        for (uint64_t j = rs + threadIdx.x; j < re; j += blockDim.x) {
-            const uint32_t c = __ldg(S.sparseIndex + j);
-            if (c < width) atomicOr(row + (c >> 5), 1u << (c & 31));
-        }
-        if (threadIdx.x == 0) rowW[b] = S.dataWeight ? __ldg(S.dataWeight + ex) : 1.0f;
-        __syncthreads();
-    }
-}
-
-}  // namespace tc
-
-int gemm_tc_fwd_output_pass(dsb200_ctx* ctx, const dsb200_sparse* s, int ef, uint32_t position, uint32_t batch, uint32_t k, uint32_t n,
-                            const float* A, const float* W, const float* bias, float* unitOut, float* delta, unsigned long long* acc)
-{
-    using namespace tc;
-    static bool attrSet = false;
-    if (!attrSet) {
-        DSB_CUDA_OK(cudaFuncSetAttribute(gemm_tc_ts_kernel<false, true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, TS_SMEM_BYTES));
-        attrSet = true;
-    }
-    // target bitmap + row weights in the context's workspace
-    const uint32_t words = (n + 31) / 32;
-    const size_t need = (size_t)batch * words + batch;
-    if (need > ctx->fuseBitsCap) {
-        if (ctx->dFuseBits) { DSB_CUDA_OK(cudaStreamSynchronize(ctx->stream)); DSB_CUDA_OK(cudaFree(ctx->dFuseBits)); ctx->dFuseBits = nullptr; ctx->fuseBitsCap = 0; }
-        DSB_CUDA_OK(cudaMalloc(&ctx->dFuseBits, need * sizeof(uint32_t)));
-        ctx->fuseBitsCap = need;
-    }
-    uint32_t* bits = ctx->dFuseBits;
-    float* rowW = reinterpret_cast<float*>(ctx->dFuseBits + (size_t)batch * words);
-    target_bitmap_kernel<<<std::min<uint32_t>(batch, (uint32_t)ctx->numSMs * 8), 256, 0, ctx->stream>>>(ctx->params, *s, position, batch, n, words, bits, rowW);
-    count_launch();
-    DSB_CUDA_OK(cudaGetLastError());
-
-    FusedOut f;
-    f.bits = bits; f.rowW = rowW; f.words = words; f.ef = ef; f.fast = ctx->fastMath;
-    f.zeroTarget = ctx->params.SMCE_zeroTarget; f.oneTarget = ctx->params.SMCE_oneTarget;
-    f.zeroScale = ctx->params.SMCE_zeroScale; f.oneScale = ctx->params.SMCE_oneScale;
-    f.boostZero = ctx->params.deltaBoost_zero; f.boostOne = ctx->params.deltaBoost_one;
-    f.unit = unitOut; f.acc = acc;
-    DSB_CUDA_OK(cudaMemcpyToSymbolAsync(c_fused, &f, sizeof(f), 0, cudaMemcpyHostToDevice, ctx->stream));   // pageable source: staged before the call returns
-
-    Args a;
-    a.A = A; a.B = W; a.C = delta; a.M = batch; a.N = n; a.K = k; a.lda = k; a.ldb = n; a.ldc = n;
-    a.vecA = vec_of(A, k); a.vecB = vec_of(W, n); a.vecC = std::min(vec_of(delta, n), unitOut ? vec_of(unitOut, n) : 4);
-    a.alpha = 1.0f; a.beta = 0.0f; a.bias = bias; a.act = DSB200_ACT_LINEAR; a.slope = 0.f; a.ealpha = 0.f; a.lambda = 0.f;
-    a.passes = (ctx->gemmMode == DSB200_GEMM_TF32) ? 1 : 3;
-    a.debug = 0;
-    a.tilesM = (batch + BM - 1) / BM; a.tilesN = (n + BN - 1) / BN;
-    a.splits = 1;                                                              // the epilogue finishes the element: no split-K
-    a.kPerSplit = ((k + BK - 1) / BK) * BK;
-    a.partial = nullptr;
-    const uint32_t grid = std::min<uint32_t>((uint32_t)ctx->numSMs, a.tilesM * a.tilesN);
-    gemm_tc_ts_kernel<false, true, false, true><<<grid, THREADS, TS_SMEM_BYTES, ctx->stream>>>(a);
-    DSB_CUDA_OK(cudaGetLastError());
-    count_launch();
     return 0;
 }
 

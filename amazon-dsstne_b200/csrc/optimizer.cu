@@ -170,6 +170,34 @@ static int launch_biases(dsb200_ctx* ctx, const OptArgs& o, uint32_t batch, uint
     return 0;
 }
 
+// bias update from column-sum partials [nPartials][width] (written by the fused output-layer forward pass, which sees every delta
+// element anyway): fixed summation order -> deterministic
+template <int MODE>
+__global__ void __launch_bounds__(256)
+update_biases_partials_kernel(const OptArgs o, uint32_t batch, uint32_t width, const float* __restrict__ partials, uint32_t nPartials,
+                              float* __restrict__ v, float* __restrict__ gv, float* __restrict__ bias)
+{
+    const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= width) return;
+    float tot = 0.0f;
+    for (uint32_t y = 0; y < nPartials; y++) tot += __ldg(partials + (size_t)y * width + c);
+    const float gbar = tot / (float)batch;
+    float vv = opt_uses_v(MODE) ? v[c] : 0.0f, ss = opt_uses_gv(MODE) ? gv[c] : 0.0f;
+    bias[c] = opt_bias<MODE>(o, gbar, bias[c], vv, ss);
+    if (opt_uses_v(MODE)) v[c] = vv;
+    if (opt_uses_gv(MODE)) gv[c] = ss;
+}
+
+template <int MODE>
+static int launch_biases_partials(dsb200_ctx* ctx, const OptArgs& o, uint32_t batch, uint32_t width, const float* partials, uint32_t nPartials,
+                                  float* v, float* gv, float* bias)
+{
+    update_biases_partials_kernel<MODE><<<(width + 255) / 256, 256, 0, ctx->stream>>>(o, batch, width, partials, nPartials, v, gv, bias);
+    count_launch();
+    DSB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 }  // namespace dsb
 
 extern "C" {
@@ -215,6 +243,28 @@ int dsb200_update_biases(dsb200_ctx* ctx, int mode, float alpha, float mu, float
     case DSB200_RMSPROP:  return launch_biases<DSB200_RMSPROP>(ctx, o, batch, width, delta, v, nullptr, bias);
     case DSB200_ADADELTA: return launch_biases<DSB200_ADADELTA>(ctx, o, batch, width, delta, v, gv, bias);
     default:              return launch_biases<DSB200_ADAM>(ctx, o, batch, width, delta, v, gv, bias);
+    }
+}
+
+int dsb200_update_biases_partials(dsb200_ctx* ctx, int mode, float alpha, float mu, float mu1, float t, uint32_t batch, uint32_t width,
+                                  const float* partials, uint32_t nPartials, float* v, float* gv, float* bias)
+{
+    DSB_PROFILE(ctx, "update_biases_partials");
+    using namespace dsb;
+    if (!ctx || !partials || !bias) return fail(ctx, DSB200_EINVAL, "update_biases_partials: null argument");
+    if (mode < 0 || mode > DSB200_ADAM) return fail(ctx, DSB200_EINVAL, "update_biases_partials: bad mode");
+    if (opt_uses_v(mode) && !v) return fail(ctx, DSB200_EINVAL, "update_biases_partials: velocity buffer missing");
+    if (opt_uses_gv(mode) && !gv) return fail(ctx, DSB200_EINVAL, "update_biases_partials: gradient-velocity buffer missing");
+    if (!width || !batch) return 0;
+    const OptArgs o = make_opt(mode, alpha, 0.0f, 0.0f, mu, mu1, t);
+    switch (mode) {
+    case DSB200_SGD:      return launch_biases_partials<DSB200_SGD>(ctx, o, batch, width, partials, nPartials, nullptr, nullptr, bias);
+    case DSB200_MOMENTUM: return launch_biases_partials<DSB200_MOMENTUM>(ctx, o, batch, width, partials, nPartials, v, nullptr, bias);
+    case DSB200_ADAGRAD:  return launch_biases_partials<DSB200_ADAGRAD>(ctx, o, batch, width, partials, nPartials, v, nullptr, bias);
+    case DSB200_NESTEROV: return launch_biases_partials<DSB200_NESTEROV>(ctx, o, batch, width, partials, nPartials, v, nullptr, bias);
+    case DSB200_RMSPROP:  return launch_biases_partials<DSB200_RMSPROP>(ctx, o, batch, width, partials, nPartials, v, nullptr, bias);
+    case DSB200_ADADELTA: return launch_biases_partials<DSB200_ADADELTA>(ctx, o, batch, width, partials, nPartials, v, gv, bias);
+    default:              return launch_biases_partials<DSB200_ADAM>(ctx, o, batch, width, partials, nPartials, v, gv, bias);
     }
 }
 

@@ -48,8 +48,8 @@ struct GpuContext {
     NNNetwork*      _pNetwork;
     unsigned long   _seed;
     bool            _bStarted;
-    bool            _bFuseOutputGemm = false; // engine option "fuse_output_gemm" (experimental): the output layer's forward GEMM is deferred into
-                                              // the loss / delta pass and runs as dsb200_gemm_fwd_output_pass (Z never written)
+    bool            _bFuseOutputGemm = true;  // engine option "fuse_output_gemm" (default on): the forward GEMM of a sigmoid output layer over Boolean
+                                              // sparse targets is deferred into the loss / delta pass and runs as dsb200_gemm_fwd_output_pass (Z never written)
     bool            _bPinnedMirror = false;   // engine option "pinned_mirror" (experimental): NNDataSet::LoadSparseData uploads straight from
                                               // the page-locked host mirror instead of copying every batch a second time into staging
     long long       _totalGPUMemory, _totalCPUMemory;

@@ -205,7 +205,7 @@ void NNLayer::ForwardPropagateFullyConnected(uint32_t position, uint32_t batch, 
             // call -- one tcgen05 kernel in the tensor-core GEMM modes (E/NNLayer.cpp:1009 + 1073 + 1157)
             NNLayer* in = _vIncomingLayer[0];
             if (deferActivation && getGpu()._bFuseOutputGemm && _activation == Sigmoid && _pDataSet && (_pDataSet->_attributes & NNDataSetEnums::Boolean)) {
-                // experimental: nothing runs now -- CalculateErrorAsync runs GEMM + activation + loss + delta as one kernel
+                // nothing runs now -- CalculateErrorAsync runs GEMM + activation + loss + delta as one kernel
                 _bForwardDeferred = true;
                 _preActivationBatch = batch;
             } else {
@@ -314,14 +314,18 @@ bool NNLayer::CalculateErrorAsync(uint32_t position, uint32_t batch, ErrorFuncti
 {
     if (_kind != Output) throw DsbEngineError("NNLayer::CalculateError: Attempt to calculate error on non-output layer " + _name);
     if (_bActivationPending && _bForwardDeferred) {
-        // experimental (engine option "fuse_output_gemm"): forward GEMM + activation + loss + delta as ONE tcgen05 kernel; the units
-        // are not produced at all (MaterializeUnits re-runs the layer if somebody asks for them)
+        // forward GEMM + activation + loss + delta as ONE tcgen05 kernel (csrc/gemm_stream.cu); the units are not produced at all
+        // (MaterializeUnits re-runs the layer if somebody asks for them).  The kernel also leaves the column sums of delta, i.e.
+        // the bias gradient, so NNWeight::UpdateWeights does not read delta again.
         NNLayer* in = _vIncomingLayer[0];
+        NNWeight* w = _vIncomingWeight[0];
         dsb200_sparse v = _pDataSet->View();
+        uint32_t nPartials = 0;
         const int rc = dsb200_gemm_fwd_output_pass(getGpu()._ctx, &v, (int)ef, (int)_activation, position, batch, in->_stride, _localStride, in->GetUnitBuffer(),
-                                                   _vIncomingWeight[0]->_pbWeight->_pDevData, _vIncomingWeight[0]->_pbBias->_pDevData, NULL,
-                                                   GetIncomingDeltaBuffer(), pDevAccumulator);
+                                                   w->_pbWeight->_pDevData, w->_pbBias->_pDevData, NULL, GetIncomingDeltaBuffer(), pDevAccumulator,
+                                                   w->BiasPartialsBuffer(batch), &nPartials);
         if (rc == 0) {
+            w->_nBiasPartials = nPartials;
             _bActivationPending = false;             // _bForwardDeferred stays set: the unit buffer holds nothing of this batch
             _bDeltaReady = true;
             return true;

@@ -376,7 +376,7 @@ void NNNetwork::ShuffleIndices()
 
 void NNNetwork::ClearUpdates()
 {
-    for (auto w : _vWeight) { w->_updateCount = 0; w->_bDeferredSparseGradient = false; }
+    for (auto w : _vWeight) { w->_updateCount = 0; w->_bDeferredSparseGradient = false; w->_nBiasPartials = 0; }
     for (auto l : _vLayer) l->ClearUpdates();
 }
 

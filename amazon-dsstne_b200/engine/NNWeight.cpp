@@ -23,7 +23,7 @@ using namespace std;
 NNWeight::NNWeight(NNLayer& inputLayer, NNLayer& outputLayer, bool bShared, bool bTransposed, bool bLocked, NNFloat maxNorm)
     : _inputLayer(inputLayer), _outputLayer(outputLayer), _bShared(bShared), _bTransposed(bTransposed), _transform(Linear),
       _bLocked(bLocked), _pSharedWeight(NULL), _sharingCount(1), _updateCount(0), _width(0), _height(0), _size(0), _biasSize(0),
-      _localSize(0), _localBiasSize(0), _bOutgoingLarger(false), _norm(maxNorm), _bDeferredSparseGradient(false), _pDeferredDelta(NULL)
+      _localSize(0), _localBiasSize(0), _bOutgoingLarger(false), _norm(maxNorm), _bDeferredSparseGradient(false), _pDeferredDelta(NULL), _nBiasPartials(0)
 {
     if (bShared || bTransposed) throw DsbEngineError("NNWeight: shared / transposed weights are outside the hot path");
     if (maxNorm > (NNFloat)0.0) throw DsbEngineError("NNWeight: WeightNorm is outside the hot path");
@@ -169,9 +169,26 @@ void NNWeight::UpdateWeights(TrainingMode mode, uint32_t batch, NNFloat alpha, N
                                              _pbWeight->_pDevData), "dsb200_update_weights");
     }
     // biases: column mean of the output layer's delta (E/NNWeight.cpp:760-794)
+    if (_nBiasPartials > 0) {
+        // the fused forward pass of the output layer already reduced delta to a few rows of column sums
+        getGpu().Check(dsb200_update_biases_partials(ctx, (int)mode, alpha, mu, mu1, t, batch, (uint32_t)_localBiasSize, _pbBiasPartials->_pDevData, _nBiasPartials,
+                                                     _pbBiasVelocity ? _pbBiasVelocity->_pDevData : NULL,
+                                                     _pbBiasGradientVelocity ? _pbBiasGradientVelocity->_pDevData : NULL, _pbBias->_pDevData),
+                       "dsb200_update_biases_partials");
+        _nBiasPartials = 0;
+        return;
+    }
     getGpu().Check(dsb200_update_biases(ctx, (int)mode, alpha, mu, mu1, t, batch, (uint32_t)_localBiasSize, _outputLayer.GetDeltaBuffer(),
                                         _pbBiasVelocity ? _pbBiasVelocity->_pDevData : NULL,
                                         _pbBiasGradientVelocity ? _pbBiasGradientVelocity->_pDevData : NULL, _pbBias->_pDevData), "dsb200_update_biases");
+}
+
+// [2 * ceil(batch / 128)][local bias size] floats for dsb200_gemm_fwd_output_pass
+NNFloat* NNWeight::BiasPartialsBuffer(uint32_t batch)
+{
+    const uint64_t need = (uint64_t)2 * ((batch + 127) / 128) * _localBiasSize;
+    if (!_pbBiasPartials || _pbBiasPartials->_length < need) _pbBiasPartials.reset(new GpuBuffer<NNFloat>(need));
+    return _pbBiasPartials->_pDevData;
 }
 
 bool NNWeight::CopyWeights(const NNWeight* pWeight)

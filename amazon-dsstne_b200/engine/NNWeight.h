@@ -28,6 +28,8 @@ private:
     NNFloat     _norm;
     bool        _bDeferredSparseGradient;   // gradient will be produced inside the fused update
     NNFloat*    _pDeferredDelta;            // delta [batch][outputStride] the fused update reads
+    uint32_t    _nBiasPartials;             // > 0: the fused output-layer forward pass left this many rows of column sums of delta
+    unique_ptr<GpuBuffer<NNFloat>> _pbBiasPartials;
     vector<NNFloat> _vWeight, _vBias;
     unique_ptr<GpuBuffer<NNFloat>> _pbWeight, _pbBias, _pbWeightGradient;
     unique_ptr<GpuBuffer<NNFloat>> _pbWeightVelocity, _pbBiasVelocity, _pbWeightGradientVelocity, _pbBiasGradientVelocity;
@@ -44,6 +46,7 @@ private:
     NNFloat* GetWeightBuffer() { return _pbWeight ? _pbWeight->_pDevData : NULL; }
     NNFloat* GetWeightGradientBuffer() { return _pbWeightGradient ? _pbWeightGradient->_pDevData : NULL; }
     uint64_t GetBufferSize() { return _localSize; }
+    NNFloat* BiasPartialsBuffer(uint32_t batch);
 
 public:
     bool CopyWeights(const NNWeight* pWeight);

@@ -142,8 +142,7 @@ def run_ours(args, wl, rank, world, local_rank):
     engine.set_stream(stream.cuda_stream)
     if world > 1 and args.p2p:
         engine.set_option("p2p_exchange", 1)
-    if args.fuse_output:
-        engine.set_option("fuse_output_gemm", 1)
+    engine.set_option("fuse_output_gemm", 1 if args.fuse_output else 0)
 
     n_batches = 16 if wl["name"] == "c2" else 4
     data = make_data(wl, n_batches)
@@ -360,7 +359,7 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c2", "c4"])
     ap.add_argument("--gemm-mode", type=int, default=2, help="dense GEMMs: 0 cuBLAS fp32, 1 tcgen05 TF32, 2 tcgen05 3xTF32 (fp32-grade)")
     ap.add_argument("--cpu-steps", type=int, default=3)
-    ap.add_argument("--fuse-output", type=int, default=0, help="1 = output layer forward GEMM fused with the output pass (experimental engine option fuse_output_gemm)")
+    ap.add_argument("--fuse-output", type=int, default=1, help="1 (default) = output layer forward GEMM fused with loss + delta (engine option fuse_output_gemm); 0 = two calls")
     ap.add_argument("--pinned-mirror", type=int, default=0, help="e2e path: 1 = LoadSparseData uploads from the page-locked host mirror (experimental single-copy path)")
     ap.add_argument("--p2p", type=int, default=0, help="N > 1: 1 = exchange steps as one kernel over peer memory (experimental) instead of NCCL")
     args = ap.parse_args()

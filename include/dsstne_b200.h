@@ -103,6 +103,8 @@ int  dsb200_ctx_reserve(dsb200_ctx* ctx, uint32_t maxBatch, size_t partialFloats
  *   "gemm_mode"          DSB200_GEMM_FP32 (default: cuBLAS SGEMM, the 1e-5 parity mode) | DSB200_GEMM_TF32 | DSB200_GEMM_TF32X3
  *   "gemm_loader"        operand path of the tcgen05 GEMM: -1 per shape (default) | 0 cp.async + split warps | 1 registers ->
  *                        shared memory | 2 A operand through tensor memory | 3 the same with a coalesced A loader (experimental)
+ *   "gemm_stream"        1 (default) = weight gradient / input delta of layers with a narrow side (<= 256 units) run on the TMA +
+ *                        tensor-memory kernels of csrc/gemm_stream.cu; 0 = the general kernel of csrc/gemm_tc.cu for every shape
  *   "gemm_tc_min_work"   tiles x k-iterations below which a GEMM stays off the tensor-core kernel (default 2048)
  *   "gemm_splits"        split-K factor, 0 = automatic;   "gemm_debug"  bring-up switches of csrc/gemm_tc.cu (wrong results)
  *   "transpose_sort"     1 = sort every column of the transposed matrix (canonical order for bit-exact comparison)
@@ -198,13 +200,17 @@ int dsb200_sparse_output_delta(dsb200_ctx*, const dsb200_sparse* s, int errorFun
 int dsb200_output_pass(dsb200_ctx*, const dsb200_sparse* s, int errorFunction, int activation,
                        uint32_t position, uint32_t batch, uint32_t stride, const float* pZ,
                        float* pUnitOut, float* pDelta, unsigned long long* pDevAccumulator);
-/* EXPERIMENTAL: cublasSgemm of the output layer (E/NNLayer.cpp:1073) + the fused output pass above in ONE kernel -- the tcgen05
- * GEMM's epilogue turns z into (activation,) loss and delta, so Z is never written or re-read.  A [batch][k], W [k][n], bias [n];
- * sigmoid with L2 / CrossEntropy / ScaledMarginalCrossEntropy over Boolean targets and a tensor-core gemm_mode only: any other
- * combination returns DSB200_EUNSUPPORTED and the caller makes the two calls.  Not yet run on a GPU (round 1).                     */
+/* cublasSgemm of the output layer (E/NNLayer.cpp:1073) + kCalculateSigmoidActivation (E/kActivation.cu:46-64) + the Raw / NonZero
+ * loss kernels (E/kLoss.cu:595-691, 1749-1865, 2213-2352) + the Raw / NonZero delta kernels (E/kDelta.cu:2193-2232, 6533-6572,
+ * 7182-7227) as ONE tcgen05 kernel (csrc/gemm_stream.cu): the epilogue turns the accumulator into loss and delta, so neither Z nor
+ * the activations are written or re-read (pUnitOut, optional, receives the activations).  A [batch][k], W [k][n], bias [n].
+ * Sigmoid with L2 / CrossEntropy / ScaledMarginalCrossEntropy over Boolean targets, k <= 128, a tensor-core gemm_mode: any other
+ * combination returns DSB200_EUNSUPPORTED and the caller makes the two calls (dsb200_gemm_fwd_bias_act, dsb200_output_pass).
+ * pColumnSumPartials (optional, device, capacity 2 * ceil(batch / 128) * n floats) receives *pNumPartials rows of [n] partial
+ * column sums of delta -- the bias gradient of E/NNWeight.cpp:760-794 -- for dsb200_update_biases_partials.                       */
 int dsb200_gemm_fwd_output_pass(dsb200_ctx*, const dsb200_sparse* s, int errorFunction, int activation, uint32_t position, uint32_t batch,
                                 uint32_t k, uint32_t n, const float* A, const float* W, const float* pBias, float* pUnitOut, float* pDelta,
-                                unsigned long long* pDevAccumulator);
+                                unsigned long long* pDevAccumulator, float* pColumnSumPartials, uint32_t* pNumPartials);
 
 /* ------------------------------------------------------------------ a10
  * kCalculateSparsenessPenalty / kCalculateHadamardProduct, E/kernels.h:202,205            */
@@ -238,6 +244,10 @@ int dsb200_update_weights(dsb200_ctx*, int mode, float alpha, float lambda, floa
                           float* pWeightGradientVelocity, float* pWeight);
 int dsb200_update_biases(dsb200_ctx*, int mode, float alpha, float mu, float mu1, float t, uint32_t batch, uint32_t width,
                          const float* pDelta, float* pBiasVelocity, float* pBiasGradientVelocity, float* pBias);
+/* k*UpdateBiases with the column sums of delta already reduced to nPartials rows of [width] (dsb200_gemm_fwd_output_pass):
+ * gbar[c] = sum_p pPartials[p][c] / batch, summed in a fixed order                                                         */
+int dsb200_update_biases_partials(dsb200_ctx*, int mode, float alpha, float mu, float mu1, float t, uint32_t batch, uint32_t width,
+                                  const float* pPartials, uint32_t nPartials, float* pBiasVelocity, float* pBiasGradientVelocity, float* pBias);
 int dsb200_regularization_error(dsb200_ctx*, float lambda, float lambda1, const float* pWeight, uint64_t size,
                                 float* pErrorOut);            /* synchronous, by value     */
 /* asynchronous variant: adds the fixed-point (2^30) value into *pDevAccumulator (device u64) */

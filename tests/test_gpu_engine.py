@@ -153,14 +153,15 @@ def test_wide_hidden_layers_like_config4(eng, orc, gemm_mode, tol):
         net.close()
 
 
-@pytest.mark.skipif(not os.environ.get("DSB200_RUN_UNVERIFIED"), reason="not yet run on a GPU (round 1 budget); set DSB200_RUN_UNVERIFIED=1")
 @pytest.mark.parametrize("error", ["ScaledMarginalCrossEntropy", "CrossEntropy", "L2"])
-def test_output_gemm_fused_with_the_output_pass(eng, orc, error):
-    """engine option "fuse_output_gemm": the output layer's forward GEMM is deferred into the loss / delta pass and runs as
-    dsb200_gemm_fwd_output_pass (3xTF32 mode).  Losses and weights against the oracle at the tensor-core bound, and the units
-    a later reader gets (top-K after a training step) are materialised by re-running the layer."""
-    sizes, batch = [4096, 1024, 1024, 4096], 256
-    h = tiny(examples=512, width=4096, mean=40.0)
+@pytest.mark.parametrize("sizes", [[4096, 128, 128, 4096], [4099, 96, 128, 4099], [4096, 1024, 1024, 4096]], ids=["fused", "fused-ragged", "declined-wide-hidden"])
+def test_output_gemm_fused_with_the_output_pass(eng, orc, error, sizes):
+    """engine option "fuse_output_gemm" (default on): the output layer's forward GEMM is deferred into the loss / delta pass and runs
+    as dsb200_gemm_fwd_output_pass (3xTF32 mode; the bias gradient comes out of the same kernel).  Hidden widths above 128 are
+    declined by the kernel and take the two-call path.  Losses and weights against the oracle at the tensor-core bound, and the
+    units a later reader gets (top-K after a training step) are materialised by re-running the layer."""
+    batch = 256
+    h = tiny(examples=512, width=sizes[0], mean=40.0)
     net, onet, names, _ = build_pair(eng, orc, sizes, h, batch, orc.MOMENTUM, error=error)
     net.set_gemm_mode(2)
     eng.set_option("fuse_output_gemm", 1)
@@ -179,7 +180,6 @@ def test_output_gemm_fused_with_the_output_pass(eng, orc, error):
             assert rel_err(W.reshape(onet.W(i).shape), onet.W(i)) < tol
             assert rel_err(b, onet.b(i)) < max(tol, 5e-5)
     finally:
-        eng.set_option("fuse_output_gemm", 0)
         net.set_gemm_mode(0)
         net.close()
 

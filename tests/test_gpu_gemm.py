@@ -131,20 +131,20 @@ def test_tensor_core_gemm_is_deterministic(ctx):
     np.testing.assert_array_equal(outs[0], outs[2])
 
 
-@pytest.mark.skipif(not os.environ.get("DSB200_RUN_UNVERIFIED"), reason="not yet run on a GPU (round 1 budget); set DSB200_RUN_UNVERIFIED=1")
 @pytest.mark.parametrize("ef", [3, 2, 1], ids=["smce", "ce", "l2"])
 @pytest.mark.parametrize("want_unit", [False, True])
-@pytest.mark.parametrize("B,k,n", [(1024, 128, 27278), (256, 128, 4099)])
+@pytest.mark.parametrize("B,k,n", [(1024, 128, 27278), (256, 128, 4099), (192, 100, 1000), (992, 64, 333)])
 def test_forward_gemm_with_fused_output_pass(ctx, dsb, ef, want_unit, B, k, n):
-    """dsb200_gemm_fwd_output_pass against the two calls it replaces (dsb200_gemm_fwd_bias_act with the activation deferred, then
-    dsb200_output_pass), both on the 3xTF32 tensor-core kernel: the same z, so delta / activations within 1e-6 and the loss within
-    1e-6 relative (its fixed-point sum is taken over a different partition of the elements)."""
+    """dsb200_gemm_fwd_output_pass (csrc/gemm_stream.cu) against the two calls it replaces (dsb200_gemm_fwd_bias_act with the
+    activation deferred, then dsb200_output_pass), both in 3xTF32: z agrees to the tensor-core bound (the two kernels sum the
+    products in different orders), so delta / activations within 3e-5 of each other and the loss within 1e-5 relative.  Also the
+    column sums of delta (the bias gradient) and dsb200_update_biases_partials against dsb200_update_biases."""
     from helpers import ml20m, to_device
     g = torch.Generator(device="cuda").manual_seed(ef * 10 + want_unit)
     A = torch.rand(B, k, device="cuda", generator=g)
     W = torch.randn(k, n, device="cuda", generator=g) * 0.1
     bias = torch.randn(n, device="cuda", generator=g) * 0.5 - 2.0
-    h = ml20m(examples=B, width=n)
+    h = ml20m(examples=B, width=n, mean=min(144.4, n / 8))
     ds = to_device(dsb, h)
     ctx.set_params(smce=(1.0, 0.0, 30.0, 1.0))
     ctx.set_option("gemm_mode", 2)
@@ -157,16 +157,82 @@ def test_forward_gemm_with_fused_output_pass(ctx, dsb, ef, want_unit, B, k, n):
         acc0 = torch.zeros(1, dtype=torch.int64, device="cuda")
         ctx.output_pass(ds, ef, dsb.ACT_SIGMOID, 0, B, z, unit0, delta0, acc0)
         unit1 = torch.empty_like(z) if want_unit else None
-        delta1 = torch.empty_like(z)
+        delta1 = torch.full_like(z, float("nan"))
         acc1 = torch.zeros(1, dtype=torch.int64, device="cuda")
-        ctx.gemm_fwd_output_pass(ds, ef, dsb.ACT_SIGMOID, 0, A, W, bias, unit1, delta1, acc1)
+        parts = torch.full((2 * ((B + 127) // 128), n), float("nan"), device="cuda")
+        n_parts = ctx.gemm_fwd_output_pass(ds, ef, dsb.ACT_SIGMOID, 0, A, W, bias, unit1, delta1, acc1, parts)
+        b0 = bias.clone(); b1 = bias.clone()
+        v0 = torch.zeros(n, device="cuda"); v1 = torch.zeros(n, device="cuda")
+        ctx.update_biases(dsb.MOMENTUM, 0.05, 0.5, 0.0, 0.0, delta1, v0, None, b0)
+        ctx.update_biases_partials(dsb.MOMENTUM, 0.05, 0.5, 0.0, 0.0, B, parts, n_parts, v1, None, b1)
         ctx.sync()
     finally:
         ctx.set_option("gemm_mode", 0)
         ctx.set_option("gemm_tc_min_work", 2048)
         ctx.set_params()
-    assert rel_err(delta1.cpu().numpy(), delta0.cpu().numpy()) < 1e-6
+    assert n_parts >= 2
+    assert rel_err(delta1.cpu().numpy(), delta0.cpu().numpy()) < 3e-5
     if want_unit:
-        assert rel_err(unit1.cpu().numpy(), unit0.cpu().numpy()) < 1e-6
+        assert rel_err(unit1.cpu().numpy(), unit0.cpu().numpy()) < 3e-5
     l0, l1 = float(acc0.item()), float(acc1.item())
-    assert abs(l1 - l0) <= 1e-6 * abs(l0)
+    assert abs(l1 - l0) <= 1e-5 * abs(l0)
+    sums = parts[:n_parts].sum(dim=0).cpu().numpy()
+    assert rel_err(sums, delta1.double().sum(dim=0).cpu().numpy()) < 1e-5
+    assert rel_err(b1.cpu().numpy(), b0.cpu().numpy()) < 1e-5
+    assert rel_err(v1.cpu().numpy(), v0.cpu().numpy()) < 1e-5
+
+
+def test_fused_output_pass_declines_what_it_does_not_cover(ctx, dsb):
+    """hidden width above 128 or the exact-fp32 mode: DSB200_EUNSUPPORTED, the caller makes the two calls"""
+    from helpers import ml20m, to_device
+    B, k, n = 128, 256, 1000
+    A = torch.rand(B, k, device="cuda"); W = torch.randn(k, n, device="cuda"); bias = torch.zeros(n, device="cuda")
+    ds = to_device(dsb, ml20m(examples=B, width=n, mean=20))
+    delta = torch.empty(B, n, device="cuda")
+    ctx.set_option("gemm_mode", 2)
+    try:
+        with pytest.raises(dsb.DsbError):
+            ctx.gemm_fwd_output_pass(ds, 3, dsb.ACT_SIGMOID, 0, A, W, bias, None, delta)
+    finally:
+        ctx.set_option("gemm_mode", 0)
+    with pytest.raises(dsb.DsbError):
+        ctx.gemm_fwd_output_pass(ds, 3, dsb.ACT_SIGMOID, 0, A[:, :128].contiguous(), W[:128].contiguous(), bias, None, delta)
+
+
+@pytest.mark.parametrize("mode", [2, 1], ids=["tf32x3", "tf32"])
+@pytest.mark.parametrize("B,k,n", [(1024, 128, 27278), (1000, 128, 5001), (333, 100, 2049), (64, 256, 700), (1024, 17, 999), (32, 130, 513)])
+def test_streamed_dw_dx_against_general_kernel_and_fp64(ctx, mode, B, k, n):
+    """csrc/gemm_stream.cu (option gemm_stream = 1, the default for narrow layers) vs float64, ragged shapes, alpha / beta, determinism"""
+    g = torch.Generator(device="cuda").manual_seed(B + k + n)
+    A = torch.randn(B, k, device="cuda", generator=g)
+    W = torch.randn(k, n, device="cuda", generator=g) * 0.1
+    D = torch.randn(B, n, device="cuda", generator=g) * 0.1
+    ctx.set_option("gemm_mode", mode)
+    ctx.set_option("gemm_tc_min_work", 0)
+    try:
+        outs = []
+        for stream in (1, 1, 0):
+            ctx.set_option("gemm_stream", stream)
+            G = torch.full((k, n), float("nan"), device="cuda")
+            ctx.gemm_dw(A, D, G, -1.0 / B)
+            G2 = G.clone()
+            ctx.gemm_dw(A, D, G2, -1.0 / B, beta=1.0)
+            Dp = torch.full((B, k), float("nan"), device="cuda")
+            ctx.gemm_dx(D, W, Dp)
+            Dp2 = Dp.clone()
+            ctx.gemm_dx(D, W, Dp2, beta=1.0)
+            ctx.sync()
+            outs.append((G.cpu().numpy(), G2.cpu().numpy(), Dp.cpu().numpy(), Dp2.cpu().numpy()))
+    finally:
+        ctx.set_option("gemm_mode", 0)
+        ctx.set_option("gemm_tc_min_work", 2048)
+        ctx.set_option("gemm_stream", 1)
+    a, w, d = ref64(A), ref64(W), ref64(D)
+    tol = BOUND[mode]
+    for G, G2, Dp, Dp2 in outs:
+        assert rel_err(G, (-1.0 / B) * (a.T @ d)) < tol
+        assert rel_err(G2, 2 * (-1.0 / B) * (a.T @ d)) < tol
+        assert rel_err(Dp, d @ w.T) < tol
+        assert rel_err(Dp2, 2 * (d @ w.T)) < tol
+    for x, y in zip(outs[0], outs[1]):
+        np.testing.assert_array_equal(x, y)                               # run to run
