@@ -90,6 +90,18 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v)
 #pragma unroll
     for (int i = 0; i < 32; i++) v[i] = __uint_as_float(r[i]);
 }
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v)
+{
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]),
+          "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr) : "memory");
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; i++) v[i] = __uint_as_float(r[i]);
+}
 // 32 lanes x 16 consecutive columns: thread t writes TMEM lane (quadrant base + t)
 __device__ __forceinline__ void tmem_st16(uint32_t taddr, const uint32_t* r)
 {
@@ -145,9 +157,16 @@ __device__ __forceinline__ uint32_t lo_of(uint32_t x) { return __float_as_uint(_
 // =====================================================================================================================
 constexpr int S_LOAD_WARPS = 8, S_EPI_WARP0 = 8, S_EPI_WARPS = 4, S_TMA_WARP = 12, S_MMA_WARP = 13;
 constexpr int S_THREADS = 14 * 32;
+// The tensor core's fp32 accumulator truncates, so the error of a product grows with the number of MMAs chained into one accumulator
+// (measured in round 1: 2e-6 at K <= 128, 1.8e-5 at K = 1,024; an engine test on the exact config-2 network saw 4e-5 on a hidden
+// weight after two steps, all of one sign).  Chains are therefore cut every S_CHUNK k-iterations (192 MMAs): the MMA warp switches to
+// the other accumulator, and the epilogue warps add the finished chunk into an fp32 tile in SHARED MEMORY (round to nearest; 64 KB,
+// layout [column / 4][row][4] so that the 32 rows of a warp are 32 consecutive 16-byte words) while the next chunk runs.
+constexpr int S_CHUNK = 16;
+constexpr int S_SUM_BYTES = BM * BN * 4;
 constexpr int S_SLOTS = 4, S_DEPTH = 3;        // ring depth / register panels in flight per loader thread
 constexpr uint32_t S_ACC_COLS = 2 * BN, S_A_COLS = 2 * BK;
-constexpr int S_SMEM_BYTES = S_SLOTS * SLOT + 1024;
+constexpr int S_SMEM_BYTES = S_SLOTS * SLOT + S_SUM_BYTES + 1024;
 static_assert(S_ACC_COLS + S_SLOTS * S_A_COLS <= TMEM_COLS, "tensor memory budget");
 
 struct SArgs {
@@ -350,12 +369,14 @@ stream_kernel(const SArgs a, const __grid_constant__ CUtensorMap mapHi, const __
         // ------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             uint32_t slot = 0, ph = 0, seq = 0;
-            for (uint32_t t = blockIdx.x; t < numTiles; t += gridDim.x, seq++) {
+            for (uint32_t t = blockIdx.x; t < numTiles; t += gridDim.x) {
                 const STile tl = stile_of(a, t);
-                const uint32_t acc = seq & 1, d = tmem + acc * BN;
-                mbar_wait(&accEmpty[acc], ((seq >> 1) & 1) ^ 1);                  // the epilogue has drained this accumulator
-                tc_fence_after();
                 for (uint32_t kt = 0; kt < tl.numK; kt++) {
+                    const uint32_t acc = seq & 1, d = tmem + acc * BN;
+                    if (kt % S_CHUNK == 0) {
+                        mbar_wait(&accEmpty[acc], ((seq >> 1) & 1) ^ 1);          // the epilogue has drained this accumulator
+                        tc_fence_after();
+                    }
                     mbar_wait(&aFull[slot], ph);
                     mbar_wait(&bFull[slot], ph);
                     tc_fence_after();
@@ -363,7 +384,7 @@ stream_kernel(const SArgs a, const __grid_constant__ CUtensorMap mapHi, const __
 #pragma unroll
                     for (int j = 0; j < BK / 8; j++) {
                         const uint64_t bHi = kmajor_desc(sb, j);
-                        const uint32_t aHi = ta + j * 8, first = (kt == 0 && j == 0) ? 0u : 1u;
+                        const uint32_t aHi = ta + j * 8, first = (kt % S_CHUNK == 0 && j == 0) ? 0u : 1u;
                         if (a.debug & 1024) {                                     // bring-up switch 1024: no MMAs
                         } else if (lo) {
                             const uint64_t bLo = kmajor_desc(sb + PANEL, j);
@@ -376,59 +397,79 @@ stream_kernel(const SArgs a, const __grid_constant__ CUtensorMap mapHi, const __
                     }
                     tc_commit(&slotEmpty[slot]);                                  // shared and tensor memory of the slot reusable once these retire
                     if (++slot == S_SLOTS) { slot = 0; ph ^= 1; }
+                    if ((kt + 1) % S_CHUNK == 0 || kt + 1 == tl.numK) { tc_commit(&accFull[acc]); seq++; }
                 }
-                tc_commit(&accFull[acc]);
             }
         }
     } else {
         // ------------------------------------------------------------ epilogue: thread = accumulator row m
-        const uint32_t q = warp & 3;
+        const uint32_t q = warp & 3, row = q * 32 + lane;
+        const uint32_t taddr = tmem + ((q * 32) << 16);
+        const uint32_t sumAddr = ringAddr + S_SLOTS * SLOT + row * 16;            // + (column / 4) * (BM * 16)
         uint32_t seq = 0;
-        for (uint32_t t = blockIdx.x; t < numTiles; t += gridDim.x, seq++) {
+        for (uint32_t t = blockIdx.x; t < numTiles; t += gridDim.x) {
             const STile tl = stile_of(a, t);
-            const uint32_t acc = seq & 1;
-            mbar_wait(&accFull[acc], (seq >> 1) & 1);
-            tc_fence_after();
-            const uint32_t m = tl.m0 + q * 32 + lane;
-            const bool mIn = m < a.M;
+            const uint32_t chunks = (tl.numK + S_CHUNK - 1) / S_CHUNK;
+            const uint32_t m = tl.m0 + row;
+            for (uint32_t ch = 0; ch < chunks; ch++, seq++) {
+                const uint32_t acc = seq & 1;
+                const bool firstCh = ch == 0, lastCh = ch + 1 == chunks;
+                __syncwarp();
+                mbar_wait(&accFull[acc], (seq >> 1) & 1);
+                tc_fence_after();
 #pragma unroll 1
-            for (int c = 0; c < BN / 32; c++) {
-                float v[32];
-                __syncwarp();                                                     // lanes diverge below (ragged edges): re-converge for the .aligned load
-                tmem_ld32(tmem + ((q * 32) << 16) + acc * BN + c * 32, v);
-                if (c == BN / 32 - 1) {                                           // accumulator fully read: the MMA warp may reuse it
-                    tc_fence_before();
-                    __syncwarp();
-                    if (lane == 0) mbar_arrive(&accEmpty[acc]);
-                }
-                const uint32_t nb = tl.n0 + c * 32;
-                if (!mIn || nb >= a.N) continue;
-                const uint32_t ncol = min(32u, a.N - nb);
-                if (EPI == 0) {
-                    float* o = a.C + (size_t)nb * a.ldc + m;
-                    if (a.beta != 0.0f) {
-#pragma unroll
-                        for (int j = 0; j < 32; j++)
-                            if ((uint32_t)j < ncol) o[(size_t)j * a.ldc] = a.alpha * v[j] + a.beta * o[(size_t)j * a.ldc];
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; j++)
-                            if ((uint32_t)j < ncol) o[(size_t)j * a.ldc] = a.alpha * v[j];
+                for (int c = 0; c < BN / 16; c++) {
+                    float v[16];
+                    __syncwarp();                                                 // lanes diverge in the stores below (ragged edges)
+                    tmem_ld16(taddr + acc * BN + c * 16, v);
+                    if (c == BN / 16 - 1) {                                       // accumulator fully read: the MMA warp may reuse it
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&accEmpty[acc]);
                     }
-                } else if (a.partial) {
-                    float* o = a.partial + ((size_t)tl.split * a.M + m) * a.N + nb;
-                    if (ncol == 32 && (a.N & 3u) == 0) {
+                    if (!firstCh) {                                               // running sum of the earlier chunks (only this thread touches its row)
 #pragma unroll
-                        for (int j = 0; j < 32; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
-                    } else {
-#pragma unroll
-                        for (int j = 0; j < 32; j++) if ((uint32_t)j < ncol) o[j] = v[j];
+                        for (int g = 0; g < 4; g++) {
+                            float4 p;
+                            asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(p.x), "=f"(p.y), "=f"(p.z), "=f"(p.w) : "r"(sumAddr + (c * 4 + g) * (BM * 16)));
+                            v[4 * g] += p.x; v[4 * g + 1] += p.y; v[4 * g + 2] += p.z; v[4 * g + 3] += p.w;
+                        }
                     }
-                } else {
-                    float* o = a.C + (size_t)m * a.ldc + nb;
+                    if (!lastCh) {
 #pragma unroll
-                    for (int j = 0; j < 32; j++)
-                        if ((uint32_t)j < ncol) o[j] = a.alpha * v[j] + (a.beta != 0.0f ? a.beta * o[j] : 0.0f);
+                        for (int g = 0; g < 4; g++)
+                            asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" :: "r"(sumAddr + (c * 4 + g) * (BM * 16)), "f"(v[4 * g]), "f"(v[4 * g + 1]), "f"(v[4 * g + 2]), "f"(v[4 * g + 3]) : "memory");
+                        continue;
+                    }
+                    const uint32_t nb = tl.n0 + c * 16;
+                    if (m >= a.M || nb >= a.N) continue;
+                    const uint32_t ncol = min(16u, a.N - nb);
+                    if (EPI == 0) {
+                        float* o = a.C + (size_t)nb * a.ldc + m;
+                        if (a.beta != 0.0f) {
+#pragma unroll
+                            for (int j = 0; j < 16; j++)
+                                if ((uint32_t)j < ncol) o[(size_t)j * a.ldc] = a.alpha * v[j] + a.beta * o[(size_t)j * a.ldc];
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; j++)
+                                if ((uint32_t)j < ncol) o[(size_t)j * a.ldc] = a.alpha * v[j];
+                        }
+                    } else if (a.partial) {
+                        float* o = a.partial + ((size_t)tl.split * a.M + m) * a.N + nb;
+                        if (ncol == 16 && (a.N & 3u) == 0) {
+#pragma unroll
+                            for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4*>(o + j) = make_float4(v[j], v[j + 1], v[j + 2], v[j + 3]);
+                        } else {
+#pragma unroll
+                            for (int j = 0; j < 16; j++) if ((uint32_t)j < ncol) o[j] = v[j];
+                        }
+                    } else {
+                        float* o = a.C + (size_t)m * a.ldc + nb;
+#pragma unroll
+                        for (int j = 0; j < 16; j++)
+                            if ((uint32_t)j < ncol) o[j] = a.alpha * v[j] + (a.beta != 0.0f ? a.beta * o[j] : 0.0f);
+                    }
                 }
             }
         }

@@ -21,8 +21,11 @@ namespace dsb {
 struct ProfileScope {
     dsb200_ctx* ctx;
     int slot;
-    ProfileScope(dsb200_ctx* c, const char* name);
+    ProfileScope(dsb200_ctx* c, const char* name, unsigned long long tag = 0);
     ~ProfileScope();
 };
 }
 #define DSB_PROFILE(ctx, name) dsb::ProfileScope _dsb_prof_scope((ctx), (name))
+// the same with a size tag: reported as "name@tag", so that call sites of one family with different operand sizes (the
+// output layer's 27,278 biases and a hidden layer's 128) are timed apart
+#define DSB_PROFILE_T(ctx, name, tag) dsb::ProfileScope _dsb_prof_scope((ctx), (name), (unsigned long long)(tag))

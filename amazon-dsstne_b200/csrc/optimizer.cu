@@ -205,7 +205,7 @@ extern "C" {
 int dsb200_update_weights(dsb200_ctx* ctx, int mode, float alpha, float lambda, float lambda1, float mu, float mu1, float t,
                           uint64_t size, float* v, const float* g, float* gv, float* w)
 {
-    DSB_PROFILE(ctx, "update_weights");
+    DSB_PROFILE_T(ctx, "update_weights", size);
     using namespace dsb;
     if (!ctx || !g || !w) return fail(ctx, DSB200_EINVAL, "update_weights: null argument");
     if (mode < 0 || mode > DSB200_ADAM) return fail(ctx, DSB200_EINVAL, "update_weights: bad mode");
@@ -227,7 +227,7 @@ int dsb200_update_weights(dsb200_ctx* ctx, int mode, float alpha, float lambda, 
 int dsb200_update_biases(dsb200_ctx* ctx, int mode, float alpha, float mu, float mu1, float t, uint32_t batch, uint32_t width,
                          const float* delta, float* v, float* gv, float* bias)
 {
-    DSB_PROFILE(ctx, "update_biases");
+    DSB_PROFILE_T(ctx, "update_biases", width);
     using namespace dsb;
     if (!ctx || !delta || !bias) return fail(ctx, DSB200_EINVAL, "update_biases: null argument");
     if (mode < 0 || mode > DSB200_ADAM) return fail(ctx, DSB200_EINVAL, "update_biases: bad mode");
@@ -249,7 +249,7 @@ int dsb200_update_biases(dsb200_ctx* ctx, int mode, float alpha, float mu, float
 int dsb200_update_biases_partials(dsb200_ctx* ctx, int mode, float alpha, float mu, float mu1, float t, uint32_t batch, uint32_t width,
                                   const float* partials, uint32_t nPartials, float* v, float* gv, float* bias)
 {
-    DSB_PROFILE(ctx, "update_biases_partials");
+    DSB_PROFILE_T(ctx, "update_biases_partials", width);
     using namespace dsb;
     if (!ctx || !partials || !bias) return fail(ctx, DSB200_EINVAL, "update_biases_partials: null argument");
     if (mode < 0 || mode > DSB200_ADAM) return fail(ctx, DSB200_EINVAL, "update_biases_partials: bad mode");
@@ -270,7 +270,7 @@ int dsb200_update_biases_partials(dsb200_ctx* ctx, int mode, float alpha, float 
 
 int dsb200_regularization_error_async(dsb200_ctx* ctx, float lambda, float lambda1, const float* w, uint64_t size, unsigned long long* pDevAcc)
 {
-    DSB_PROFILE(ctx, "regularization_error");
+    DSB_PROFILE_T(ctx, "regularization_error", size);
     using namespace dsb;
     if (!ctx || !w || !pDevAcc) return fail(ctx, DSB200_EINVAL, "regularization_error_async: null argument");
     if (!size) return 0;

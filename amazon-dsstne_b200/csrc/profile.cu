@@ -13,7 +13,7 @@
 
 namespace dsb {
 
-struct ProfileRecord { const char* name; cudaEvent_t start, stop; };
+struct ProfileRecord { const char* name; unsigned long long tag; cudaEvent_t start, stop; };
 struct ProfileState { std::vector<ProfileRecord> recs; std::vector<cudaEvent_t> pool; };
 static std::map<dsb200_ctx*, ProfileState> g_prof;
 
@@ -23,11 +23,11 @@ static cudaEvent_t get_event(ProfileState& st)
     cudaEvent_t e; cudaEventCreate(&e); return e;
 }
 
-ProfileScope::ProfileScope(dsb200_ctx* c, const char* name) : ctx(c), slot(-1)
+ProfileScope::ProfileScope(dsb200_ctx* c, const char* name, unsigned long long tag) : ctx(c), slot(-1)
 {
     if (!c || !c->profile) return;
     ProfileState& st = g_prof[c];
-    ProfileRecord r; r.name = name; r.start = get_event(st); r.stop = get_event(st);
+    ProfileRecord r; r.name = name; r.tag = tag; r.start = get_event(st); r.stop = get_event(st);
     cudaEventRecord(r.start, c->stream);
     slot = (int)st.recs.size();
     st.recs.push_back(r);
@@ -56,7 +56,7 @@ int dsb200_profile_report(dsb200_ctx* ctx, char* buf, size_t cap)
     for (auto& r : st.recs) {
         float ms = 0.0f;
         cudaEventElapsedTime(&ms, r.start, r.stop);
-        auto& t = tot[r.name];
+        auto& t = tot[r.tag ? std::string(r.name) + "@" + std::to_string(r.tag) : std::string(r.name)];
         t.first++; t.second += ms;
         st.pool.push_back(r.start); st.pool.push_back(r.stop);
     }

@@ -2,6 +2,8 @@
 // probing, cuBLAS/cuRAND/cuDNN handles) with: rank from the launcher, one dsb200_ctx, NCCL.
 #include "GpuTypes.h"
 
+#include <fcntl.h>
+
 #include <sys/stat.h>
 #include <time.h>
 #include <unistd.h>
@@ -44,13 +46,18 @@ void GpuContext::Startup(int argc, char** argv)
     else {
         const char* port = getenv("MASTER_PORT");
         const char* run = getenv("TORCHELASTIC_RUN_ID");
-        path = std::string("/tmp/dsb200_nccl_") + (port ? port : "0") + "_" + (run ? run : "default");
+        // every rank of one launch shares the launcher as parent process: its pid keeps the leftovers of a crashed earlier run
+        // (same port, same run id) from being picked up
+        path = std::string("/tmp/dsb200_nccl_") + (port ? port : "0") + "_" + (run ? run : "default") + "_" + std::to_string((long)getppid());
     }
     unsigned char id[128];
     if (rank == 0) {
         if (dsb200_comm_unique_id(id)) throw DsbEngineError("GpuContext::Startup: cannot create the NCCL unique id");
         const std::string tmp = path + ".tmp";
-        FILE* f = fopen(tmp.c_str(), "wb");
+        remove(path.c_str());                                                     // a leftover of a run with the same launcher pid cannot be ours
+        remove(tmp.c_str());
+        const int fd = open(tmp.c_str(), O_WRONLY | O_CREAT | O_EXCL, 0600);
+        FILE* f = fd >= 0 ? fdopen(fd, "wb") : nullptr;
         if (!f || fwrite(id, 1, sizeof(id), f) != sizeof(id)) throw DsbEngineError("GpuContext::Startup: cannot write " + tmp);
         fclose(f);
         if (rename(tmp.c_str(), path.c_str()) != 0) throw DsbEngineError("GpuContext::Startup: cannot publish " + path);

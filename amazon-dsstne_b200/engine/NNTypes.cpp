@@ -515,6 +515,9 @@ template <typename T>
 bool NNDataSet<T>::GenerateDenoisingData()
 {
     if (!(_attributes & NNDataSetEnums::Sparse) || !_pbDenoisingRandom) return false;
+    // the index array can have been replaced since SetDenoising (LoadSparseData while model parallel swaps in this rank's column
+    // shard, which can hold more non-zeros than the one before): the random buffer follows its length
+    if (_pbDenoisingRandom->_length < _vSparseIndex.size()) _pbDenoisingRandom.reset(new GpuBuffer<NNFloat>(_vSparseIndex.size()));
     // the reference refills the whole buffer with cuRAND XORWOW once per epoch (E/NNTypes.cpp:1617-1629);
     // here: counter-based generator keyed by (seed, rank, epoch), uniform in (0, 1]
     const uint64_t key = (uint64_t)getGpu()._seed + (uint64_t)getGpu()._id * 76801ull;

@@ -74,7 +74,12 @@ static inline float u01(uint64_t key, uint64_t i)          // (0, 1]
 void NNWeight::Randomize()
 {
     // formulas of E/NNWeight.cpp:500-558 (uniform u in (0,1]: w = scale*u - bias; Gaussian: N(0, sigma))
-    const uint64_t key = mix64((uint64_t)getGpu()._seed * 0x9e3779b97f4a7c15ull + mix64((uint64_t)_inputLayer._stride * 1000003ull + _outputLayer._stride));
+    // the key mixes in the names of the two layers: cuRAND's stream advances from one matrix to the next (E/NNWeight.cpp:500-558), so
+    // equal-shaped matrices of a stacked network must not start out identical; the element index stays GLOBAL, so model-parallel
+    // shards still hold exactly the slices of the single-GPU matrix
+    uint64_t nameHash = 0xcbf29ce484222325ull;
+    for (unsigned char ch : _inputLayer._name + "\x1f" + _outputLayer._name) nameHash = (nameHash ^ ch) * 0x100000001b3ull;
+    const uint64_t key = mix64((uint64_t)getGpu()._seed * 0x9e3779b97f4a7c15ull + mix64((uint64_t)_inputLayer._stride * 1000003ull + _outputLayer._stride) + mix64(nameHash));
     const uint32_t inMin = _bOutgoingLarger ? 0 : _inputLayer._minX;
     const uint32_t outMin = _bOutgoingLarger ? _outputLayer._minX : 0;
     NNFloat scale = 0.0f, bias = 0.0f, sigma = 0.0f;
@@ -95,7 +100,7 @@ void NNWeight::Randomize()
             for (uint64_t c = 0; c < _width; c++) {
                 const uint64_t g = (uint64_t)(inMin + r) * _outputLayer._stride + (outMin + c);  // global element index
                 NNFloat w;
-                if (constant) w = _outputLayer._weightInitScale;
+                if (constant) w = -_outputLayer._weightInitScale;      // kScaleAndBias(w = 0, scale 0, bias = scale) = 0 * w - scale (E/kernels.cu:48, E/NNWeight.cpp:550-554)
                 else if (gaussian) {
                     const float u1 = u01(key, 2 * g), u2 = u01(key, 2 * g + 1);
                     w = sigma * sqrtf(-2.0f * logf(u1)) * cosf(6.28318530718f * u2);
@@ -237,6 +242,11 @@ bool NNWeight::GetBiases(vector<NNFloat>& vBias)
 
 bool NNWeight::GetGradients(vector<NNFloat>& vGradient)
 {
+    // with fusion on, the gradient of a sparse-input weight is consumed inside dsb200_sparse_wgrad_update and never written to
+    // _pbWeightGradient: returning the buffer would hand out stale data
+    if (getGpu()._pNetwork && getGpu()._pNetwork->FusionEnabled() && _inputLayer._kind == NNLayer::Kind::Input && _inputLayer._bFastSparse)
+        throw DsbEngineError("NNWeight::GetGradients: the gradient of sparse-input weight " + _inputLayer._name + " -> " + _outputLayer._name +
+                             " is fused into the optimizer step and never materialised; call NNNetwork::SetFusion(false) first");
     vGradient.resize(_localSize);
     _pbWeightGradient->Download(vGradient.data());
     return true;

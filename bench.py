@@ -95,8 +95,9 @@ def peaks():
 
 
 def algorithmic_bytes(wl, nnz_batch, P=1):
-    """SURVEY.md section 8d per-launch ALGORITHMIC bytes of each hand-written kernel family (fp32)."""
-    B, N, S = wl["batch"], wl["items"] // P, wl["hidden"][0]
+    """SURVEY.md section 8d per-launch ALGORITHMIC bytes of each hand-written kernel family (fp32).  Families that are called
+    on several layers report per call site as "name@size" (csrc/profile.cu); those are resolved by alg_of() from the size."""
+    B, N, S, H = wl["batch"], wl["items"] // P, wl["hidden"][0], wl["hidden"][-1]
     return {
         # gathered weight rows + Z write (bias read) + indices + start/end
         "sparse_z_bias_act": 4 * S * nnz_batch + 4 * B * S + 4 * nnz_batch + 16 * B,
@@ -108,15 +109,32 @@ def algorithmic_bytes(wl, nnz_batch, P=1):
         "sparse_wgrad": 4 * S * nnz_batch + 4 * S * N + 4 * nnz_batch + 8 * N,
         # read Z, write delta + target CSR (the activations are not stored during training)
         "output_pass": 2 * 4 * B * N + 4 * nnz_batch + 16 * B,
-        # output-layer GEMMs on the tcgen05 kernel (7.15 GFLOP each on c2): operands read once + result written once
-        "gemm_fwd_bias_act_tc": 4 * (B * wl["hidden"][-1] + wl["hidden"][-1] * N + B * N + N),
-        "gemm_dw_tc": 4 * (B * wl["hidden"][-1] + B * N + wl["hidden"][-1] * N),
-        "gemm_dx_tc": 4 * (B * N + wl["hidden"][-1] * N + B * wl["hidden"][-1]),
-        # read g, read w, write w
-        "update_weights": 3 * 4 * wl["hidden"][-1] * N,
-        # delta read (dominated by the output layer) + bias r/w
-        "update_biases": 4 * B * N + 8 * N,
+        # forward GEMM + activation + loss + delta in one kernel: X and W read, delta written, target CSR read (Z never exists)
+        "gemm_fwd_output_pass": 4 * (B * H + H * N + B * N + N) + 4 * nnz_batch + 16 * B,
+        # output-layer GEMMs: operands read once + result written once (7.15 GFLOP each on c2)
+        "gemm_fwd_bias_act_tc": 4 * (B * H + H * N + B * N + N),
+        "gemm_dw_tc": 4 * (B * H + B * N + H * N), "gemm_dw_stream": 4 * (B * H + B * N + H * N),
+        "gemm_dx_tc": 4 * (B * N + H * N + B * H), "gemm_dx_stream": 4 * (B * N + H * N + B * H),
     }
+
+
+def alg_of(name, alg, batch):
+    """algorithmic bytes of one profiled call site, or None (library / bookkeeping call)"""
+    if name in alg:
+        return alg[name]
+    fam, _, tag = name.partition("@")
+    if not tag:
+        return None
+    n = int(tag)
+    if fam == "update_weights":
+        return 3 * 4 * n                                  # SGD: read g, read w, write w
+    if fam == "update_biases":
+        return 4 * batch * n + 8 * n                      # delta column sums + bias r/w
+    if fam == "update_biases_partials":
+        return 8 * 4 * n + 8 * n
+    if fam == "regularization_error":
+        return 4 * n
+    return None
 
 
 def run_ours(args, wl, rank, world, local_rank):
@@ -214,22 +232,26 @@ def run_ours(args, wl, rank, world, local_rank):
         for name, (calls, tot) in prof.items():
             per = tot / max(calls, 1)
             kern[name] = {"calls_per_step": calls / prof_steps, "ms_per_call": round(per, 5), "share": round(tot / prof_ms, 4)}
-            if name in alg:
-                kern[name]["algorithmic_GBs"] = round(alg[name] / (per * 1e-3) / 1e9, 1)
-        ours = {k: v for k, v in kern.items() if k in alg}
+            ab = alg_of(name, alg, B)
+            if ab is not None:
+                kern[name]["algorithmic_GBs"] = round(ab / (per * 1e-3) / 1e9, 1)
+                kern[name]["algorithmic_bytes"] = int(ab)
+        ours = {k: v for k, v in kern.items() if "algorithmic_GBs" in v}
         dom = max(ours, key=lambda k: ours[k]["share"]) if ours else None
         roof = None
         if dom:
             a = ours[dom]["algorithmic_GBs"]
-            traffic = None
+            traffic, tsrc = None, None
             tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "traffic_c2.json")
             if wl["name"] == "c2" and world == 1 and os.path.exists(tpath):
-                traffic = json.load(open(tpath)).get(dom)           # DRAM bytes per launch from the committed ncu capture
+                tj = json.load(open(tpath))
+                traffic = tj.get(dom)                               # DRAM bytes per launch from the committed ncu capture named in "_source"
+                tsrc = tj.get("_source")
             roof = {"kernel": dom, "bound": "hbm", "achieved": a, "peak": peak, "unit": "GB/s", "frac": round(a / peak, 4),
-                    "traffic": traffic, "peak_source": peak_src, "share_of_step": ours[dom]["share"],
-                    "algorithmic_bytes_per_launch": int(alg[dom]),
-                    "note": "tcgen05 3xTF32 GEMM of the output layer: 56 flop per algorithmic byte, below the machine balance of the tf32 pipe, so "
-                            "the HBM roofline is the bound that applies" if dom.startswith("gemm") else None}
+                    "traffic": traffic, "traffic_source": tsrc, "peak_source": peak_src, "share_of_step": ours[dom]["share"],
+                    "algorithmic_bytes_per_launch": ours[dom]["algorithmic_bytes"],
+                    "note": "3xTF32 tcgen05 kernel of the output layer: 56 flop per algorithmic byte, below the machine balance of the tf32 pipe, "
+                            "so the HBM roofline is the bound that applies" if dom.startswith("gemm") else None}
         value = args.steps * B / (ms * 1e-3)
         result = {"metric": METRIC, "value": round(value, 1), "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
                   "ms_per_step": round(ms / args.steps, 4), "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -242,17 +264,138 @@ def run_ours(args, wl, rank, world, local_rank):
                   "clocks": sampler.summary(), "gpu_launches": int(launches), "roofline": roof, "kernels": kern}
         if e2e:
             result["e2e"] = e2e
-        if args.cpu_steps > 0:
+        if args.cpu_steps > 0 and world == 1:
             result["cpu_baseline"] = cpu_baseline(wl, data, sample_steps=args.cpu_steps)
         else:                                            # --cpu-steps 0: only for the side workloads (one c4 oracle step is minutes of host time)
             result["cpu_baseline"] = {"value": None, "unit": UNIT, "cores": 0, "kind": "port", "sample": "skipped (--cpu-steps 0)"}
     net.close()
+    ds_in.close(); ds_out.close()
+    del data
+    # ---- side records (BASELINE configs 4 and 5): the 1M-item layer whose scaling target BASELINE.json states, and top-K ----
+    if args.side and wl["name"] == "c2":
+        for key, fn in (("c4", run_side_c4), ("c5", run_side_c5)):
+            try:
+                rec = fn(args, engine, dsstne_b200, stream, rank, world, local_rank)
+            except Exception as exc:
+                rec = {"error": repr(exc)[:300]}
+            if result is not None:
+                result[key] = rec
     if world > 1:
         import torch.distributed as dist
         dist.barrier()
         dist.destroy_process_group()
     engine.shutdown()
     return result
+
+
+def _max_over_ranks(ms, world):
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        t = torch.tensor([ms], device="cuda", dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+    return ms
+
+
+def run_side_c4(args, engine, dsstne_b200, stream, rank, world, local_rank):
+    """BASELINE config 4 (1M items, 3 x 1,024 hidden, batch 1,024; model parallel when N > 1): a short timed run after the
+    headline workload so that the driver's 1/2/4/8-GPU lines carry the config the 0.85 scaling target is quoted on."""
+    import torch
+    wl = workload("c4")
+    t0 = time.perf_counter()
+    data = make_data(wl, 2)
+    B = wl["batch"]
+    ds_in = engine.Dataset.from_host_csr("gl_input", data)
+    ds_out = engine.Dataset.from_host_csr("gl_output", data)
+    net = engine.Network(engine.autoencoder_json(wl["hidden"], smce=SMCE, init=("Gaussian", 0.01, 0.0)), B, [ds_in, ds_out])
+    net.set_training_mode(dsstne_b200.SGD)
+    net.set_gemm_mode(args.gemm_mode)
+    setup = time.perf_counter() - t0
+    steps, warm = args.c4_steps, 3
+
+    def step(i):
+        return net.train_step((i % 2) * B, HYPER["alpha"], HYPER["lam"], HYPER["lam1"], HYPER["mu"], HYPER["mu1"])
+
+    for i in range(warm):
+        step(i)
+    if world > 1:
+        import torch.distributed as dist
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record(stream)
+    for i in range(steps):
+        loss = step(warm + i)
+    ev1.record(stream)
+    torch.cuda.synchronize()
+    ms = _max_over_ranks(ev0.elapsed_time(ev1), world)
+    engine.set_option("profile", 1)
+    for i in range(2):
+        step(i)
+    prof = engine.profile_report()
+    engine.set_option("profile", 0)
+    net.close(); ds_in.close(); ds_out.close()
+    top = sorted(((n, t / max(c, 1)) for n, (c, t) in prof.items()), key=lambda x: -x[1])[:8]
+    return {"workload": wl["desc"], "metric": METRIC, "value": round(steps * B / (ms * 1e-3), 1), "unit": UNIT, "ms_per_step": round(ms / steps, 3),
+            "steps": steps, "warmup": warm, "n_gpus": world, "scaling": "strong", "setup_s": round(setup, 1), "last_loss": round(float(loss), 3),
+            "ms_per_call_top": {n: round(t, 3) for n, t in top}}
+
+
+def run_side_c5(args, engine, dsstne_b200, stream, rank, world, local_rank):
+    """BASELINE config 5: top-K = 100 over a 1M-item output with the exclusion filter (kCalculateTopK path), batch 4,096.
+    N > 1: every rank scores its column shard, the per-rank lists are all-gathered and merged (dsb200_topk_kv) on every rank --
+    the scheme of NNNetwork::CalculateTopKGlobal (tests/test_multi_gpu.py checks it against one process)."""
+    import torch
+    B, N, K = 4096, 1000000, 100
+    lo, hi = N * rank // world, N * (rank + 1) // world
+    width = hi - lo
+    g = torch.Generator(device="cuda").manual_seed(12134 + rank)
+    scores = torch.rand(B, width, device="cuda", generator=g)
+    # exclusion lists: ~144 columns per row (the user's own history, U/Filters.cpp:49-67), local ids of this shard
+    rng = np.random.Generator(np.random.PCG64(7 + rank))
+    per = max(1, 144 // world)
+    idx = np.sort(rng.integers(0, width, size=(B, per), dtype=np.int64), axis=1).astype(np.uint32).reshape(-1)
+    start = (np.arange(B, dtype=np.uint64) * per)
+    end = start + np.uint64(per)
+    fs = torch.from_numpy(start.view(np.int64)).cuda(); fe = torch.from_numpy(end.view(np.int64)).cuda(); fi = torch.from_numpy(idx.view(np.int32)).cuda()
+    ctx = dsstne_b200.Context(local_rank)
+    key = torch.empty(B, K, device="cuda"); val = torch.empty(B, K, dtype=torch.int32, device="cuda")
+    if world > 1:
+        import torch.distributed as dist
+        keys = torch.empty(world, B, K, device="cuda"); vals = torch.empty(world, B, K, dtype=torch.int32, device="cuda")
+        mk = torch.empty(B, world * K, device="cuda"); mv = torch.empty(B, world * K, dtype=torch.int32, device="cuda")
+        ok = torch.empty(B, K, device="cuda"); ov = torch.empty(B, K, dtype=torch.int32, device="cuda")
+
+    def call():
+        ctx.topk(scores, K, key, val, filt=(fs, fe, fi))
+        if world > 1:
+            ctx.topk_offset(val, lo)
+            dist.all_gather_into_tensor(keys, key); dist.all_gather_into_tensor(vals, val)
+            mk.copy_(keys.permute(1, 0, 2).reshape(B, world * K)); mv.copy_(vals.permute(1, 0, 2).reshape(B, world * K))
+            ctx.topk_kv(mk, mv, K, ok, ov)
+
+    for _ in range(2):
+        call()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    reps = 3
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for _ in range(reps):
+        call()
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = _max_over_ranks(ev0.elapsed_time(ev1) / reps, world)
+    alg = 4 * B * width + 8 * B * K + 4 * len(idx) + 16 * B           # SURVEY 8d, per GPU
+    peak, _ = peaks()
+    ctx.close()
+    return {"workload": "BASELINE config 5: top-K 100 of 4,096 x 1,000,000 scores with exclusion filter (~144 / row)", "metric": "top-K rows/s",
+            "value": round(B / (ms * 1e-3), 1), "unit": "rows/s", "ms_per_call": round(ms, 3), "n_gpus": world, "scaling": "strong",
+            "roofline": {"bound": "hbm", "achieved": round(alg / (ms * 1e-3) / 1e9, 1), "peak": peak, "unit": "GB/s",
+                         "frac": round(alg / (ms * 1e-3) / 1e9 / peak, 4), "algorithmic_bytes_per_gpu": int(alg),
+                         "note": "per GPU; N > 1 includes the NCCL all-gather of the per-rank lists and the merge"}}
 
 
 def run_e2e(args, wl, data, engine, dsstne_b200, stream, world=1):
@@ -314,6 +457,11 @@ def cpu_baseline(wl, data, sample_steps=3):
     sample of the same workload: `sample_steps` minibatches of the same network and data."""
     from oracle import oracle as orc
     from dsstne_b200 import datagen
+    # torch.distributed.run exports OMP_NUM_THREADS=1: the CPU arm uses every core this process may run on
+    try:
+        orc.set_num_threads(len(os.sched_getaffinity(0)))
+    except Exception:
+        pass
     B = wl["batch"]
     sizes = [wl["items"]] + wl["hidden"] + [wl["items"]]
     net = orc.Network(sizes, error=orc.ERR_SMCE, mode=orc.SGD, max_batch=B)
@@ -359,6 +507,8 @@ def main():
     ap.add_argument("--workload", default="c2", choices=["c2", "c4"])
     ap.add_argument("--gemm-mode", type=int, default=2, help="dense GEMMs: 0 cuBLAS fp32, 1 tcgen05 TF32, 2 tcgen05 3xTF32 (fp32-grade)")
     ap.add_argument("--cpu-steps", type=int, default=3)
+    ap.add_argument("--side", type=int, default=1, help="1 (default) = after the headline workload also time BASELINE config 4 (1M-item layers) and config 5 (top-K) and add them as \"c4\" / \"c5\" records")
+    ap.add_argument("--c4-steps", type=int, default=6)
     ap.add_argument("--fuse-output", type=int, default=1, help="1 (default) = output layer forward GEMM fused with loss + delta (engine option fuse_output_gemm); 0 = two calls")
     ap.add_argument("--pinned-mirror", type=int, default=0, help="e2e path: 1 = LoadSparseData uploads from the page-locked host mirror (experimental single-copy path)")
     ap.add_argument("--p2p", type=int, default=0, help="N > 1: 1 = exchange steps as one kernel over peer memory (experimental) instead of NCCL")

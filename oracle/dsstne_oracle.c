@@ -23,6 +23,7 @@
 #define ORC_MAX_ACT      0.999999f                /* E/NNTypes.h:48 */
 #define ORC_MAX_VALUE    999999999999999.0f       /* E/NNTypes.h:49 */
 
+void orc_set_num_threads(int n) { if (n > 0) omp_set_num_threads(n); }
 int orc_num_threads(void)
 {
 #ifdef _OPENMP

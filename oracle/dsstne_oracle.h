@@ -229,6 +229,8 @@ double orc_net_loss(orc_network* net, const orc_csr* in, const orc_csr* out, uin
 void   orc_net_backward(orc_network* net, const orc_csr* in, const orc_csr* out, uint32_t position, uint32_t batch);
 
 int orc_num_threads(void);
+/* torchrun exports OMP_NUM_THREADS=1: the CPU arm of bench.py sets the count back to the cores it may run on */
+void orc_set_num_threads(int n);
 
 #ifdef __cplusplus
 }

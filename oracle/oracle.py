@@ -75,6 +75,10 @@ def num_threads():
     return lib().orc_num_threads()
 
 
+def set_num_threads(n):
+    lib().orc_set_num_threads(C.c_int(int(n)))
+
+
 def make_params(shuffle=None, denoising_p=0.0, deltaBoost=(1.0, 1.0), smce=(0.9, 0.1, 1.0, 1.0)):
     """smce = (oneTarget, zeroTarget, oneScale, zeroScale)."""
     p = Params()

@@ -184,6 +184,63 @@ def test_output_gemm_fused_with_the_output_pass(eng, orc, error, sizes):
         net.close()
 
 
+@pytest.mark.parametrize("gemm_mode,tol", [(0, TOL), (2, 3e-5)], ids=["fp32", "tf32x3"])
+def test_baseline_config2_exact_network(eng, orc, gemm_mode, tol):
+    """The benchmarked network itself (BASELINE.json config 2, what bench.py times): 27,278 -> 128 -> 128 -> 128 -> 27,278,
+    batch 1,024, synthetic CSR at ML-20M density (log-normal rows, Zipf columns), sigmoid / SMCE(1,0,1,1), SGD with the CLI's
+    defaults.  Two steps: loss of each and every weight / bias afterwards against the oracle network.  In 3xTF32 mode this is
+    the fused output-layer forward (csrc/gemm_stream.cu) plus the streamed dW / dX kernels."""
+    from helpers import ml20m
+    sizes, batch = [27278, 128, 128, 128, 27278], 1024
+    h = ml20m(examples=2 * batch, width=sizes[0])
+    net, onet, names, _ = build_pair(eng, orc, sizes, h, batch, orc.SGD)
+    net.set_gemm_mode(gemm_mode)
+    oc = to_oracle(orc, h)
+    onet.set_input(oc, batch)
+    try:
+        for pos in (0, batch):
+            got = net.train_step(pos, 0.025, 1e-4, 0.0, 0.5, 0.0)
+            want, _ = onet.train_step(oc, oc, pos, batch, 0.025, 1e-4, 0.0, 0.5, 0.0)
+            assert abs(got - want) <= tol * abs(want), (pos, got, want)
+        for i in range(len(sizes) - 1):
+            W, b = net.get_weights(names[i], names[i + 1])
+            assert rel_err(W.reshape(onet.W(i).shape), onet.W(i)) < tol, names[i]
+            assert rel_err(b, onet.b(i)) < max(tol, 5e-5), names[i]
+    finally:
+        net.set_gemm_mode(0)
+        net.close()
+
+
+@pytest.mark.parametrize("gemm_mode,tol", [(0, TOL), (2, 3e-5)], ids=["fp32", "tf32x3"])
+def test_movielens_sample_configuration(eng, orc, gemm_mode, tol):
+    """The shipped sample (samples/movielens/config.json of the reference): ONE 128-unit sigmoid hidden layer with the sparseness
+    penalty, denoising p = 0.2 on the sparse input, ScaledMarginalCrossEntropy (1, 0, 1, 1), on ML-20M-shaped data.  The denoising
+    randoms are generated on the device and handed to the oracle (cuRAND's stream is "parity unpinned")."""
+    from helpers import ml20m
+    sizes, batch = [27278, 128, 27278], 1024
+    h = ml20m(examples=2 * batch, width=sizes[0])
+    net, onet, names, _ = build_pair(eng, orc, sizes, h, batch, orc.SGD, denoising_p=0.2, sparseness=(0.5, 2.0))
+    net.set_gemm_mode(gemm_mode)
+    rnd = fill_uniform_host(h.nnz, 12134, 0)                     # what NNDataSet::GenerateDenoisingData draws for epoch 0 on rank 0
+    oc = to_oracle(orc, h, random=rnd)
+    onet.set_input(oc, batch)
+    try:
+        got = net.train(1, 0.025)                                # one epoch = two minibatches (Train regenerates the randoms per epoch)
+        tot = 0.0
+        for pos in (0, batch):
+            e, _ = onet.train_step(oc, to_oracle(orc, h), pos, batch, 0.025)
+            tot += e
+        want = tot / (2 * batch)
+        assert abs(got - want) <= tol * abs(want), (got, want)
+        for i in range(len(sizes) - 1):
+            W, b = net.get_weights(names[i], names[i + 1])
+            assert rel_err(W.reshape(onet.W(i).shape), onet.W(i)) < tol, names[i]
+            assert rel_err(b, onet.b(i)) < max(tol, 5e-5), names[i]
+    finally:
+        net.set_gemm_mode(0)
+        net.close()
+
+
 def test_fused_and_unfused_engine_agree(eng, orc):
     sizes, batch = [2048, 128, 2048], 256
     h = tiny(examples=256, width=2048)

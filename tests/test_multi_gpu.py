@@ -20,7 +20,7 @@ def run_world(world, extra_env=None, port=29611):
     env.update(extra_env or {})
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", f"--nproc-per-node={world}", "--master-addr", "127.0.0.1",
            "--master-port", str(port), os.path.join(ROOT, "tests", "mp_worker.py")]
-    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=env, cwd=ROOT)
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=180, env=env, cwd=ROOT)
     lines = [l for l in p.stdout.splitlines() if l.startswith("MP_RESULT ")]
     assert p.returncode == 0 and lines, p.stdout[-2000:] + p.stderr[-4000:]
     return json.loads(lines[-1][len("MP_RESULT "):])

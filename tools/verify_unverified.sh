@@ -6,7 +6,7 @@
 mkdir -p gpurun_out
 if [ "$1" = "multi" ]; then
     N=${2:-2}
-    DSB200_RUN_UNVERIFIED=1 timeout 600 python -m pytest tests/test_multi_gpu.py -q -m gpu 2>&1 | tail -15 | tee gpurun_out/unverified_multi.log
+    DSB200_RUN_UNVERIFIED=1 timeout 900 python -m pytest tests/test_multi_gpu.py -q -m gpu 2>&1 | tail -15 | tee gpurun_out/unverified_multi.log
     for p2p in 0 1; do
         timeout 300 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port $((29700 + p2p)) \
             bench.py --gpus $N --steps 50 --warmup 5 --cpu-steps 0 --p2p $p2p > gpurun_out/bench_mp${N}_p2p${p2p}.json 2> gpurun_out/bench_mp${N}_p2p${p2p}.err
