@@ -114,32 +114,40 @@ static unsigned grid_of(dsb200_ctx* ctx, uint64_t n)
 }
 
 // =====================================================================================================================
-// Exchange steps as ONE kernel over peer memory (option "p2p_exchange" = 1; EXPERIMENTAL: written at the end of round 1
-// after the GPU budget was spent, not yet run -- the NCCL path above stays the default).
+// Exchange steps as ONE kernel over peer memory (dsb200_p2p_*; the engine uses them when option "p2p_exchange" is on and the
+// set-up succeeded on every rank, else the NCCL calls above).
 //
-// Why: on BASELINE config 2 the exchanged blocks are 512 KB and a training step has 11 of them; an NCCL collective plus the
-// repack kernel next to it costs 15-20 us, as much as the compute between two exchanges.  Over
-// NVSwitch every peer is one hop away, so a collective of this size is a few microseconds of loads / stores plus one flag
-// round trip.  Every rank owns an exchange buffer (two regions, used alternately) and a flag array, both exported with
-// cudaIpcGetMemHandle and mapped by every peer.  A collective is one kernel per rank:
-//   stage    copy my contribution into my own exchange region (local stores)
-//   publish  last block to finish: st.release.sys of the collective's epoch into slot `rank` of EVERY rank's flag array
-//   wait     thread 0 of every block polls its OWN flag array until all P slots carry the epoch (ld.acquire.sys)
-//   gather   all-gather: read every peer's region over NVLink straight into the caller's [batch][stride] rows
-//            reduce-scatter: sum the P regions' columns [lo, hi) in rank order (deterministic) into the caller's slice
-// No repack pass (the slices are addressed in place, uneven unit ranges included) and no second barrier: a rank can reuse
-// a region only two collectives later, and it cannot get there before every peer has published the collective in between,
-// which a peer does only after it has finished reading the older one.
+// Why: on BASELINE config 3 the exchanged blocks are 512 KB and a training step has 8-11 of them; an NCCL collective plus the
+// repack kernel next to it costs 20-28 us (driver-run SCALE_r01, round-2 profiles), as much as the compute between two
+// exchanges.  Over NVSwitch every peer is one hop away, so a collective of this size is a few microseconds of stores plus one
+// flag round trip.  Round 1's first attempt (stage locally, grid-wide arrival counter, every block polling, PULL over NVLink with
+// scalar loads and a 64-bit division per element) measured 30 us and is gone.  This version PUSHES:
+//   * every rank owns an ARENA of `slots` regions and an array of arrival counters, exported with cudaIpcGetMemHandle and mapped
+//     by every peer; a collective names the slot it delivers into (the engine gives every layer boundary its own slots, so a
+//     gathered operand stays valid until the same boundary is exchanged again in the next step);
+//   * all-gather: each thread reads 16 bytes of the local slice once and stores them into the slot of EVERY rank (remote stores are
+//     posted: nobody waits for a round trip); reduce-scatter: each rank stores the columns a peer owns into that peer's slot,
+//     rank-major, and the owner sums the P contributions in rank order (deterministic) with bias and activation applied on the
+//     way out (kAddBias + kCalculate*Activation, E/NNLayer.cpp:1257-1340, fused);
+//   * completion: after its stores a block does __threadfence_system and one red.release.sys.add per peer on the peer's counter
+//     [slot][source]; a consumer waits until every source has delivered `blocks` arrivals of this call (ld.acquire.sys).  In the
+//     all-gather only block 0 waits (the kernel's end is the delivery point); in the reduce-scatter every block waits before it
+//     sums, so the grid is at most one block per SM (co-resident: no block can wait for one that cannot run).
+// Re-use of a slot: a rank can push into slot s of a peer only after it has itself finished the previous exchange on s, which
+// needs every peer's contribution to THAT exchange, which a peer launches only after its consumers of the exchange before it
+// have been queued ahead in stream order -- and between two uses of a slot (one training step apart) every rank has taken
+// part in at least one other exchange.
 struct P2PState {
     int       P = 0, rank = 0;
-    float*    xbuf = nullptr;                       // own exchange buffer: 2 regions of `cap` floats
-    size_t    cap = 0;
-    unsigned long long* flags = nullptr;            // own flag array: P epochs + the block-arrival counter
-    float**   dPeerX = nullptr;                     // device tables [P] of the mapped peer buffers (own pointers at [rank])
+    uint32_t  slots = 0;
+    size_t    slotFloats = 0;
+    float*    arena = nullptr;
+    unsigned long long* flags = nullptr;            // [slots][P]: arrivals from source rank r on slot s
+    float**   dPeerArena = nullptr;                 // device tables [P] (own pointers at [rank])
     unsigned long long** dPeerFlags = nullptr;
-    std::vector<void*> opened;                      // cudaIpcOpenMemHandle mappings
-    unsigned long long epoch = 0;
-    bool      failed = false;                       // set-up failed on some rank: every rank stays on NCCL
+    std::vector<void*> opened;
+    std::vector<unsigned long long> expected;       // per slot: arrivals per source a finished call has seen
+    bool      failed = false;
 };
 
 __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p)
@@ -148,32 +156,31 @@ __device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long
     asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
     return v;
 }
-__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v)
-{
-    asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(p), "l"(v) : "memory");
-}
 
 struct P2PArgs {
-    float* const* peerX; unsigned long long* const* peerFlags; unsigned long long* myFlags;
-    uint32_t rank, P; unsigned long long epoch; size_t region;        // region = offset of this epoch's region in floats
+    float* const* peerArena; unsigned long long* const* peerFlags; unsigned long long* myFlags;
+    uint32_t rank, P, slot; size_t slotOff; unsigned long long target;
     uint32_t batch, stride;
 };
 
-// every block: my stores are done -> (last block) publish the epoch to all ranks -> wait until all ranks have published
-__device__ __forceinline__ void p2p_publish_and_wait(const P2PArgs& a)
+// this block's stores are out -> one arrival on every rank's counter [slot][me]
+__device__ __forceinline__ void p2p_signal(const P2PArgs& a)
 {
-    __threadfence_system();
+    // the block barrier orders every thread's stores before the signalling threads; their system-scope release is cumulative over
+    // them (one fence per signalling thread instead of one per storing thread)
     __syncthreads();
-    if (threadIdx.x == 0) {
-        unsigned long long* counter = a.myFlags + a.P;
-        const unsigned long long prev = atomicAdd(counter, 1ull);
-        if (prev == (unsigned long long)gridDim.x - 1) {
-            *counter = 0;                                                          // for the next collective on this stream
-            __threadfence_system();
-            for (uint32_t r = 0; r < a.P; r++) st_release_sys(a.peerFlags[r] + a.rank, a.epoch);
-        }
-        for (uint32_t r = 0; r < a.P; r++)
-            while (ld_acquire_sys(a.myFlags + r) < a.epoch) __nanosleep(32);
+    if (threadIdx.x < a.P) {
+        unsigned long long* f = a.peerFlags[threadIdx.x] + (size_t)a.slot * a.P + a.rank;
+        __threadfence_system();
+        asm volatile("red.release.sys.global.add.u64 [%0], %1;" :: "l"(f), "l"(1ull) : "memory");
+    }
+}
+// every source has delivered all its blocks of this call
+__device__ __forceinline__ void p2p_wait(const P2PArgs& a)
+{
+    if (threadIdx.x < a.P) {
+        const unsigned long long* f = a.myFlags + (size_t)a.slot * a.P + threadIdx.x;
+        while (ld_acquire_sys(f) < a.target) { }
     }
     __syncthreads();
 }
@@ -183,49 +190,91 @@ __device__ __forceinline__ void p2p_range(uint32_t stride, uint32_t r, uint32_t 
     lo = (uint32_t)((uint64_t)stride * r / P); hi = (uint32_t)((uint64_t)stride * (r + 1) / P);      // E/NNLayer.cpp:108-112
 }
 
-// local [batch][span_rank] of every rank -> full [batch][stride] on every rank
+// local [batch][span_me] -> columns [lo_me, hi_me) of the full [batch][stride] in the slot of every rank
+template <int VEC>
 __global__ void __launch_bounds__(256)
-p2p_all_gather_kernel(const P2PArgs a, const float* __restrict__ pLocal, float* __restrict__ pFull)
+p2p_all_gather_kernel(const P2PArgs a, const float* __restrict__ pLocal)
 {
     uint32_t lo, hi;
     p2p_range(a.stride, a.rank, a.P, lo, hi);
-    const uint64_t mine = (uint64_t)a.batch * (hi - lo), tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (uint64_t)gridDim.x * blockDim.x;
-    float* region = a.peerX[a.rank] + a.region;
-    for (uint64_t i = tid; i < mine; i += nth) region[i] = pLocal[i];
-    p2p_publish_and_wait(a);
-    for (uint32_t q = 0; q < a.P; q++) {
-        const uint32_t r = (a.rank + q) % a.P;                                     // start with the local slice, spread the peers
-        uint32_t rlo, rhi;
-        p2p_range(a.stride, r, a.P, rlo, rhi);
-        const uint32_t span = rhi - rlo;
-        if (!span) continue;
-        const float* src = (r == a.rank) ? pLocal : a.peerX[r] + a.region;
-        const uint64_t n = (uint64_t)a.batch * span;
-        for (uint64_t i = tid; i < n; i += nth) {
-            const uint32_t b = (uint32_t)(i / span), c = (uint32_t)(i % span);
-            pFull[(size_t)b * a.stride + rlo + c] = (r == a.rank) ? src[i] : __ldcg(src + i);
+    const uint32_t span = hi - lo, spanV = span / VEC;
+    const uint32_t total = a.batch * spanV;
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
+        const uint32_t b = i / spanV, c = (i - b * spanV) * VEC;
+        const size_t dst = a.slotOff + (size_t)b * a.stride + lo + c;
+        if (VEC == 4) {
+            const float4 v = *reinterpret_cast<const float4*>(pLocal + (size_t)b * span + c);
+            for (uint32_t q = 0; q < a.P; q++) *reinterpret_cast<float4*>(a.peerArena[(a.rank + q) % a.P] + dst) = v;
+        } else {
+            const float v = pLocal[(size_t)b * span + c];
+            for (uint32_t q = 0; q < a.P; q++) a.peerArena[(a.rank + q) % a.P][dst] = v;
         }
+    }
+    p2p_signal(a);
+    if (blockIdx.x == 0) p2p_wait(a);
+}
+
+__device__ __forceinline__ float p2p_act(int act, float z, float slope, float alpha, float lambda)
+{
+    switch (act) {
+    case DSB200_ACT_SIGMOID: return 1.0f / (1.0f + expf(-z));
+    case DSB200_ACT_TANH:    return tanhf(z);
+    case DSB200_ACT_RELU:    return fmaxf(0.0f, z);
+    case DSB200_ACT_LRELU:   return fmaxf(z, z * slope);
+    case DSB200_ACT_ELU:     return (z > 0.0f) ? z : alpha * (expf(z) - 1.0f);
+    case DSB200_ACT_SELU:    return (z > 0.0f) ? lambda * z : lambda * alpha * (expf(z) - 1.0f);
+    default:                 return z;
     }
 }
 
-// [batch][stride] of every rank summed; this rank keeps columns [lo, hi) as [batch][span]
+// [batch][stride] partial sums of every rank -> this rank's columns [lo, hi) summed over the ranks (+ bias, activation)
+struct P2PEpi { const float* bias; int act; float slope, alpha, lambda; };
+template <int VEC>
 __global__ void __launch_bounds__(256)
-p2p_reduce_scatter_kernel(const P2PArgs a, const float* __restrict__ pIn, float* __restrict__ pOut)
+p2p_reduce_scatter_kernel(const P2PArgs a, const float* __restrict__ pIn, float* __restrict__ pOut, const P2PEpi e)
 {
-    const uint64_t total = (uint64_t)a.batch * a.stride, tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (uint64_t)gridDim.x * blockDim.x;
-    float* region = a.peerX[a.rank] + a.region;
-    for (uint64_t i = tid; i < total; i += nth) region[i] = pIn[i];
-    p2p_publish_and_wait(a);
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    // push: the columns of peer q go to slot region [me][batch][span_q] of q
+    for (uint32_t k = 1; k < a.P; k++) {
+        const uint32_t q = (a.rank + k) % a.P;
+        uint32_t qlo, qhi;
+        p2p_range(a.stride, q, a.P, qlo, qhi);
+        const uint32_t span = qhi - qlo, spanV = span / VEC, total = a.batch * spanV;
+        float* dst = a.peerArena[q] + a.slotOff + (size_t)a.rank * a.batch * span;
+        for (uint32_t i = tid; i < total; i += nth) {
+            const uint32_t b = i / spanV, c = (i - b * spanV) * VEC;
+            if (VEC == 4) *reinterpret_cast<float4*>(dst + (size_t)b * span + c) = *reinterpret_cast<const float4*>(pIn + (size_t)b * a.stride + qlo + c);
+            else          dst[(size_t)b * span + c] = pIn[(size_t)b * a.stride + qlo + c];
+        }
+    }
+    p2p_signal(a);
+    p2p_wait(a);
     uint32_t lo, hi;
     p2p_range(a.stride, a.rank, a.P, lo, hi);
-    const uint32_t span = hi - lo;
-    const uint64_t n = (uint64_t)a.batch * span;
-    for (uint64_t i = tid; i < n; i += nth) {
-        const uint32_t b = (uint32_t)(i / span), c = (uint32_t)(i % span);
-        const size_t off = a.region + (size_t)b * a.stride + lo + c;
-        float acc = 0.0f;
-        for (uint32_t r = 0; r < a.P; r++) acc += (r == a.rank) ? pIn[(size_t)b * a.stride + lo + c] : __ldcg(a.peerX[r] + off);   // rank order: the same bits on every run
-        pOut[i] = acc;
+    const uint32_t span = hi - lo, spanV = span / VEC, total = a.batch * spanV;
+    const float* mine = a.peerArena[a.rank] + a.slotOff;
+    for (uint32_t i = tid; i < total; i += nth) {
+        const uint32_t b = i / spanV, c = (i - b * spanV) * VEC;
+        if (VEC == 4) {
+            float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+            for (uint32_t r = 0; r < a.P; r++) {                                   // rank order: the same bits on every run and every rank count
+                const float4 v = (r == a.rank) ? *reinterpret_cast<const float4*>(pIn + (size_t)b * a.stride + lo + c)
+                                               : __ldcg(reinterpret_cast<const float4*>(mine + ((size_t)r * a.batch + b) * span + c));
+                acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+            }
+            if (e.bias) { const float4 bb = *reinterpret_cast<const float4*>(e.bias + c); acc.x += bb.x; acc.y += bb.y; acc.z += bb.z; acc.w += bb.w; }
+            if (e.act != DSB200_ACT_LINEAR) {
+                acc.x = p2p_act(e.act, acc.x, e.slope, e.alpha, e.lambda); acc.y = p2p_act(e.act, acc.y, e.slope, e.alpha, e.lambda);
+                acc.z = p2p_act(e.act, acc.z, e.slope, e.alpha, e.lambda); acc.w = p2p_act(e.act, acc.w, e.slope, e.alpha, e.lambda);
+            }
+            *reinterpret_cast<float4*>(pOut + (size_t)b * span + c) = acc;
+        } else {
+            float acc = 0.f;
+            for (uint32_t r = 0; r < a.P; r++)
+                acc += (r == a.rank) ? pIn[(size_t)b * a.stride + lo + c] : __ldcg(mine + ((size_t)r * a.batch + b) * span + c);
+            if (e.bias) acc += e.bias[c];
+            pOut[(size_t)b * span + c] = p2p_act(e.act, acc, e.slope, e.alpha, e.lambda);
+        }
     }
 }
 
@@ -234,34 +283,34 @@ static void p2p_release(dsb200_ctx* ctx)
     P2PState* st = static_cast<P2PState*>(ctx->p2p);
     if (!st) return;
     for (void* p : st->opened) cudaIpcCloseMemHandle(p);
-    cudaFree(st->xbuf); cudaFree(st->flags); cudaFree(st->dPeerX); cudaFree(st->dPeerFlags);
+    cudaFree(st->arena); cudaFree(st->flags); cudaFree(st->dPeerArena); cudaFree(st->dPeerFlags);
     delete st;
     ctx->p2p = nullptr;
 }
 
-// Collective (every rank calls it at the same point with the same `need`): true when the peer-memory path can take a message
-// of `need` floats.  The first call maps the peers; a later, larger message than the mapped regions stays on NCCL.
-static bool p2p_ready(dsb200_ctx* ctx, size_t need)
+// Collective (every rank calls it with the same arguments): allocate the arena, exchange the IPC handles over NCCL, map the
+// peers, and VOTE -- a failure on any rank makes every rank report DSB200_EUNSUPPORTED (the caller stays on NCCL).
+static int p2p_setup(dsb200_ctx* ctx, uint32_t slots, size_t slotFloats)
 {
-    P2PState* st = static_cast<P2PState*>(ctx->p2p);
-    if (st) return !st->failed && st->cap >= need;
-    st = new P2PState;
+    p2p_release(ctx);
+    P2PState* st = new P2PState;
     ctx->p2p = st;
-    st->P = ctx->nranks; st->rank = ctx->rank;
+    st->P = ctx->nranks; st->rank = ctx->rank; st->slots = slots;
+    st->slotFloats = (slotFloats + 63) & ~(size_t)63;
+    st->expected.assign(slots, 0ull);
     const int P = st->P;
     struct Handles { cudaIpcMemHandle_t x, f; };
-    bool ok = true;
-    st->cap = std::max(need, (size_t)8 << 20);                                     // 2 x 32 MB by default
-    ok = ok && cudaMalloc(&st->xbuf, 2 * st->cap * sizeof(float)) == cudaSuccess;
-    ok = ok && cudaMalloc(&st->flags, (size_t)(P + 1) * sizeof(unsigned long long)) == cudaSuccess;
-    ok = ok && cudaMemsetAsync(st->flags, 0, (size_t)(P + 1) * sizeof(unsigned long long), ctx->stream) == cudaSuccess;
+    bool ok = P >= 2 && P <= 32 && slots > 0;
+    ok = ok && cudaMalloc(&st->arena, (size_t)slots * st->slotFloats * sizeof(float)) == cudaSuccess;
+    ok = ok && cudaMalloc(&st->flags, (size_t)slots * P * sizeof(unsigned long long)) == cudaSuccess;
+    ok = ok && cudaMemsetAsync(st->flags, 0, (size_t)slots * P * sizeof(unsigned long long), ctx->stream) == cudaSuccess;
     Handles mine;
     memset(&mine, 0, sizeof(mine));
-    ok = ok && cudaIpcGetMemHandle(&mine.x, st->xbuf) == cudaSuccess && cudaIpcGetMemHandle(&mine.f, st->flags) == cudaSuccess;
+    ok = ok && cudaIpcGetMemHandle(&mine.x, st->arena) == cudaSuccess && cudaIpcGetMemHandle(&mine.f, st->flags) == cudaSuccess;
     // the handle exchange is itself a collective, so it runs even on a rank whose allocation failed (that rank votes "no" below)
-    std::vector<Handles> all((size_t)P);
+    std::vector<Handles> all((size_t)std::max(P, 1));
     unsigned char* dH = nullptr;
-    bool exchanged = cudaMalloc(&dH, (size_t)P * sizeof(Handles)) == cudaSuccess;
+    bool exchanged = cudaMalloc(&dH, (size_t)std::max(P, 1) * sizeof(Handles)) == cudaSuccess;
     if (exchanged) {
         exchanged = cudaMemcpyAsync(dH + (size_t)st->rank * sizeof(Handles), &mine, sizeof(Handles), cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess &&
                     g_nccl.AllGather(dH + (size_t)st->rank * sizeof(Handles), dH, sizeof(Handles), ncclUint8, (ncclComm_t)ctx->comm, ctx->stream) == ncclSuccess &&
@@ -269,20 +318,22 @@ static bool p2p_ready(dsb200_ctx* ctx, size_t need)
                     cudaStreamSynchronize(ctx->stream) == cudaSuccess;
     }
     ok = ok && exchanged;
-    std::vector<float*> px((size_t)P, nullptr);
-    std::vector<unsigned long long*> pf((size_t)P, nullptr);
+    std::vector<float*> px((size_t)std::max(P, 1), nullptr);
+    std::vector<unsigned long long*> pf((size_t)std::max(P, 1), nullptr);
     for (int r = 0; ok && r < P; r++) {
-        if (r == st->rank) { px[r] = st->xbuf; pf[r] = st->flags; continue; }
+        if (r == st->rank) { px[r] = st->arena; pf[r] = st->flags; continue; }
         void* x = nullptr; void* f = nullptr;
         ok = cudaIpcOpenMemHandle(&x, all[r].x, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess;
         if (ok) { st->opened.push_back(x); ok = cudaIpcOpenMemHandle(&f, all[r].f, cudaIpcMemLazyEnablePeerAccess) == cudaSuccess; }
         if (ok) st->opened.push_back(f);
         px[r] = static_cast<float*>(x); pf[r] = static_cast<unsigned long long*>(f);
     }
-    ok = ok && cudaMalloc(&st->dPeerX, (size_t)P * sizeof(float*)) == cudaSuccess && cudaMalloc(&st->dPeerFlags, (size_t)P * sizeof(unsigned long long*)) == cudaSuccess;
-    ok = ok && cudaMemcpyAsync(st->dPeerX, px.data(), (size_t)P * sizeof(float*), cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess &&
+    ok = ok && cudaMalloc(&st->dPeerArena, (size_t)P * sizeof(float*)) == cudaSuccess && cudaMalloc(&st->dPeerFlags, (size_t)P * sizeof(unsigned long long*)) == cudaSuccess;
+    ok = ok && cudaMemcpyAsync(st->dPeerArena, px.data(), (size_t)P * sizeof(float*), cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess &&
          cudaMemcpyAsync(st->dPeerFlags, pf.data(), (size_t)P * sizeof(unsigned long long*), cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess;
-    // all ranks must agree: the vote is a sum of failures
+    int coop = 0;
+    ok = ok && cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->device) == cudaSuccess && coop;
+    // all ranks must agree: the vote is a sum of failures; it also orders every rank's flag memset before anybody's first push
     float* dVote = reinterpret_cast<float*>(dH);
     float vote = ok ? 0.0f : 1.0f;
     bool voted = dH && cudaMemcpyAsync(dVote, &vote, sizeof(float), cudaMemcpyHostToDevice, ctx->stream) == cudaSuccess &&
@@ -292,26 +343,31 @@ static bool p2p_ready(dsb200_ctx* ctx, size_t need)
     cudaFree(dH);
     cudaGetLastError();                                                            // a failed probe must not poison later calls
     st->failed = !(voted && vote == 0.0f);
-    return !st->failed && st->cap >= need;
+    if (st->failed) { p2p_release(ctx); return DSB200_EUNSUPPORTED; }
+    return 0;
 }
 
-static P2PArgs p2p_args(dsb200_ctx* ctx, uint32_t batch, uint32_t stride)
+static int p2p_args(dsb200_ctx* ctx, uint32_t slot, uint32_t batch, uint32_t stride, uint32_t blocks, P2PArgs* out)
 {
     P2PState* st = static_cast<P2PState*>(ctx->p2p);
-    st->epoch++;
+    if (!st || st->failed) return fail(ctx, DSB200_ESTATE, "p2p: dsb200_p2p_setup has not succeeded");
+    if (slot >= st->slots) return fail(ctx, DSB200_EINVAL, "p2p: slot out of range");
+    if ((size_t)batch * (stride + (uint32_t)st->P) > st->slotFloats) return fail(ctx, DSB200_EINVAL, "p2p: message larger than a slot");
+    st->expected[slot] += blocks;
     P2PArgs a;
-    a.peerX = st->dPeerX; a.peerFlags = st->dPeerFlags; a.myFlags = st->flags;
-    a.rank = (uint32_t)st->rank; a.P = (uint32_t)st->P; a.epoch = st->epoch; a.region = (st->epoch & 1ull) ? st->cap : 0;
+    a.peerArena = st->dPeerArena; a.peerFlags = st->dPeerFlags; a.myFlags = st->flags;
+    a.rank = (uint32_t)st->rank; a.P = (uint32_t)st->P; a.slot = slot; a.slotOff = (size_t)slot * st->slotFloats; a.target = st->expected[slot];
     a.batch = batch; a.stride = stride;
-    return a;
+    *out = a;
+    return 0;
 }
 
-static unsigned p2p_grid(dsb200_ctx* ctx, uint64_t n)
+// same block count on every rank (it is part of the arrival arithmetic): from the largest slice
+static uint32_t p2p_blocks(dsb200_ctx* ctx, uint64_t elems)
 {
-    // every block spins in p2p_publish_and_wait, so the whole grid must be resident: at most one block per SM
-    uint64_t g = (n + 1023) / 1024;
+    uint64_t g = (elems / 4 + 511) / 512;
     if (g > (uint64_t)ctx->numSMs) g = (uint64_t)ctx->numSMs;
-    return (unsigned)std::max<uint64_t>(g, 1);
+    return (uint32_t)std::max<uint64_t>(g, 1);
 }
 
 }  // namespace dsb
@@ -363,13 +419,6 @@ int dsb200_reduce_scatter(dsb200_ctx* ctx, uint32_t batch, uint32_t stride, cons
     }
     if (!ctx->comm) return fail(ctx, DSB200_ESTATE, "reduce_scatter: communicator not initialised");
     const uint64_t total = (uint64_t)batch * stride;
-    if (ctx->p2pExchange && total && p2p_ready(ctx, total)) {
-        const P2PArgs a = p2p_args(ctx, batch, stride);
-        p2p_reduce_scatter_kernel<<<p2p_grid(ctx, total), 256, 0, ctx->stream>>>(a, pIn, pOut);
-        count_launch();
-        DSB_CUDA_OK(cudaGetLastError());
-        return 0;
-    }
     int rc = dsb200_ctx_reserve(ctx, 0, total);
     if (rc) return rc;
     float* tmp = ctx->dPartials;
@@ -400,13 +449,6 @@ int dsb200_all_gather(dsb200_ctx* ctx, uint32_t batch, uint32_t stride, const fl
     }
     if (!ctx->comm) return fail(ctx, DSB200_ESTATE, "all_gather: communicator not initialised");
     const uint64_t total = (uint64_t)batch * stride;
-    if (ctx->p2pExchange && total && p2p_ready(ctx, total)) {
-        const P2PArgs a = p2p_args(ctx, batch, stride);
-        p2p_all_gather_kernel<<<p2p_grid(ctx, total), 256, 0, ctx->stream>>>(a, pLocal, pFull);
-        count_launch();
-        DSB_CUDA_OK(cudaGetLastError());
-        return 0;
-    }
     int rc = dsb200_ctx_reserve(ctx, 0, total);
     if (rc) return rc;
     float* tmp = ctx->dPartials;
@@ -438,6 +480,73 @@ int dsb200_all_gather(dsb200_ctx* ctx, uint32_t batch, uint32_t stride, const fl
         }
         DSB_CUDA_OK(cudaGetLastError());
     }
+    return 0;
+}
+
+int dsb200_p2p_setup(dsb200_ctx* ctx, uint32_t slots, size_t slotFloats)
+{
+    using namespace dsb;
+    if (!ctx) return DSB200_EINVAL;
+    if (ctx->nranks < 2 || !ctx->comm) return fail(ctx, DSB200_EUNSUPPORTED, "p2p_setup: needs an initialised communicator with at least two ranks");
+    const int rc = p2p_setup(ctx, slots, slotFloats);
+    if (rc) return fail(ctx, rc, "p2p_setup: peer mapping unavailable on at least one rank (the exchange steps stay on NCCL)");
+    return 0;
+}
+
+float* dsb200_p2p_slot(dsb200_ctx* ctx, uint32_t slot)
+{
+    using namespace dsb;
+    P2PState* st = ctx ? static_cast<P2PState*>(ctx->p2p) : nullptr;
+    if (!st || st->failed || slot >= st->slots) return nullptr;
+    return st->arena + (size_t)slot * st->slotFloats;
+}
+
+int dsb200_p2p_all_gather(dsb200_ctx* ctx, uint32_t slot, uint32_t batch, uint32_t stride, const float* pLocal)
+{
+    DSB_PROFILE_T(ctx, "p2p_all_gather", stride);
+    using namespace dsb;
+    if (!ctx || !pLocal) return fail(ctx, DSB200_EINVAL, "p2p_all_gather: null argument");
+    if (!batch || !stride) return 0;
+    const uint32_t P = (uint32_t)ctx->nranks;
+    const uint32_t spanMax = (stride + P - 1) / P;
+    const uint32_t blocks = p2p_blocks(ctx, (uint64_t)batch * spanMax);
+    P2PArgs a;
+    int rc = p2p_args(ctx, slot, batch, stride, blocks, &a);
+    if (rc) return rc;
+    uint32_t lo, hi; dsb200_shard_range(stride, (uint32_t)ctx->rank, P, &lo, &hi);
+    const P2PState* st = static_cast<P2PState*>(ctx->p2p);
+    // every rank must take the same path only for the block count; the vector width is a local matter
+    const bool vec = ((hi - lo) % 4 == 0) && (lo % 4 == 0) && (stride % 4 == 0) && (((uintptr_t)pLocal) % 16 == 0) && (st->slotFloats % 4 == 0);
+    if (vec) p2p_all_gather_kernel<4><<<blocks, 256, 0, ctx->stream>>>(a, pLocal);
+    else     p2p_all_gather_kernel<1><<<blocks, 256, 0, ctx->stream>>>(a, pLocal);
+    count_launch();
+    DSB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+int dsb200_p2p_reduce_scatter(dsb200_ctx* ctx, uint32_t slot, uint32_t batch, uint32_t stride, const float* pIn, float* pOut, const float* pBias,
+                              int activation, float slope, float alpha, float lambda)
+{
+    DSB_PROFILE_T(ctx, "p2p_reduce_scatter", stride);
+    using namespace dsb;
+    if (!ctx || !pIn || !pOut) return fail(ctx, DSB200_EINVAL, "p2p_reduce_scatter: null argument");
+    if (activation == DSB200_ACT_SOFTMAX) return fail(ctx, DSB200_EUNSUPPORTED, "p2p_reduce_scatter: softmax is a row operation; pass Linear and call dsb200_activation");
+    if (!batch || !stride) return 0;
+    const uint32_t P = (uint32_t)ctx->nranks;
+    const uint32_t blocks = p2p_blocks(ctx, (uint64_t)batch * stride);
+    P2PArgs a;
+    int rc = p2p_args(ctx, slot, batch, stride, blocks, &a);
+    if (rc) return rc;
+    // 16-byte path: every rank's column range must start and end on a multiple of four for every peer (the pushes address the
+    // peers' ranges), i.e. stride divisible by 4 P
+    const bool vec = (stride % (4 * P) == 0) && (((uintptr_t)pIn) % 16 == 0) && (((uintptr_t)pOut) % 16 == 0) && (!pBias || ((uintptr_t)pBias) % 16 == 0);
+    P2PEpi e; e.bias = pBias; e.act = activation; e.slope = slope; e.alpha = alpha; e.lambda = lambda;
+    // every block waits for the peers before it sums, so all blocks must be able to run at once: at most one 256-thread block per
+    // SM without shared memory always can (a concurrent kernel of this library can delay them, but it never waits for this one)
+    if (vec) p2p_reduce_scatter_kernel<4><<<blocks, 256, 0, ctx->stream>>>(a, pIn, pOut, e);
+    else     p2p_reduce_scatter_kernel<1><<<blocks, 256, 0, ctx->stream>>>(a, pIn, pOut, e);
+    count_launch();
+    DSB_CUDA_OK(cudaGetLastError());
     return 0;
 }
 

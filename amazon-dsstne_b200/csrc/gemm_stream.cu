@@ -253,6 +253,14 @@ struct PlanK {                                     // r[8 j + s]: row t / 4 + 8 
                     const uint2 t = ldg_nc_u32x2(ptr + (2 * j + ((s >> 1) & 1)) * ld8 + 8 * (s >> 2));
                     r[8 * j + s] = t.x; r[8 * j + s + 1] = t.y;
                 }
+        } else if (rowMask == 15u && k0 + BK <= kEnd) {                          // rows 4-byte aligned only (odd pitch: a column shard)
+#pragma unroll
+            for (int j = 0; j < 2; j++)
+#pragma unroll
+                for (int s = 0; s < 8; s += 2) {
+                    const float* p = ptr + (2 * j + ((s >> 1) & 1)) * ld8 + 8 * (s >> 2);
+                    r[8 * j + s] = ldg_nc_u32(p); r[8 * j + s + 1] = ldg_nc_u32(p + 1);
+                }
         } else {
 #pragma unroll
             for (int j = 0; j < 2; j++)

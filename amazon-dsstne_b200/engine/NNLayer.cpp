@@ -102,6 +102,7 @@ void NNLayer::RefreshState(NNNetwork* pNetwork, TrainingMode trainingMode, bool 
 void NNLayer::ClearUpdates()
 {
     _unitUpdateCount = 0; _deltaUpdateCount = 0; _bActivationPending = false; _bDeltaReady = false; _bForwardDeferred = false;
+    _bUnitsGathered = false; _bBiasActDone = false;
 }
 
 void NNLayer::LoadPredictionBatch(uint32_t position, uint32_t batch)
@@ -159,8 +160,7 @@ void NNLayer::CalculateDropout(uint32_t batch)
 // the deferred forward GEMM of an output layer, run on its own (the units are wanted, or the fused kernel declined the combination)
 void NNLayer::RunDeferredForward(bool applyActivation)
 {
-    NNLayer* in = _vIncomingLayer[0];
-    getGpu().Check(dsb200_gemm_fwd_bias_act(getGpu()._ctx, _preActivationBatch, in->_stride, _localStride, in->GetUnitBuffer(),
+    getGpu().Check(dsb200_gemm_fwd_bias_act(getGpu()._ctx, _preActivationBatch, _deferredK, _localStride, _pDeferredA,
                                             _vIncomingWeight[0]->_pbWeight->_pDevData, _vIncomingWeight[0]->_pbBias->_pDevData,
                                             applyActivation ? (int)_activation : (int)Linear, GetIncomingUnitBuffer(), _RELUSlope, _ELUAlpha, _SELULambda),
                    "dsb200_gemm_fwd_bias_act (deferred)");
@@ -182,7 +182,7 @@ void NNLayer::MaterializeUnits()
 void NNLayer::ForwardPropagateFullyConnected(uint32_t position, uint32_t batch, bool bTraining)
 {
     _bUnitsArePreActivation = false;                 // the unit buffer is about to be rewritten
-    _bForwardDeferred = false;
+    if (getGpu()._numprocs == 1) _bForwardDeferred = false;   // model parallel: the layer BELOW sets it in its own forward pass (it owns the GEMM)
     dsb200_ctx* ctx = getGpu()._ctx;
     NNNetwork* net = getGpu()._pNetwork;
     const bool deferActivation = bTraining && net && FusedOutputEligible(net->GetErrorFunction());
@@ -208,6 +208,8 @@ void NNLayer::ForwardPropagateFullyConnected(uint32_t position, uint32_t batch, 
                 // nothing runs now -- CalculateErrorAsync runs GEMM + activation + loss + delta as one kernel
                 _bForwardDeferred = true;
                 _preActivationBatch = batch;
+                _pDeferredA = in->GetUnitBuffer();
+                _deferredK = in->_stride;
             } else {
                 getGpu().Check(dsb200_gemm_fwd_bias_act(ctx, batch, in->_stride, _localStride, in->GetUnitBuffer(), _vIncomingWeight[0]->_pbWeight->_pDevData,
                                                         _vIncomingWeight[0]->_pbBias->_pDevData, deferActivation ? (int)Linear : (int)_activation,
@@ -241,6 +243,8 @@ void NNLayer::ForwardPropagateFullyConnected(uint32_t position, uint32_t batch, 
 
     // ---------------------------------------------------------------- model parallel (E/NNLayer.cpp:1169-1422)
     if (_kind != Input) {
+        bool biasActDone = _bBiasActDone;                                         // the feeding layer's GEMM epilogue did both
+        _bBiasActDone = false;
         if (!_vIncomingLargerLayer.empty()) {
             // local partial products over this rank's input slice, then reduce-scatter over the units
             NNFloat sgemm_beta = (NNFloat)0.0;
@@ -262,13 +266,23 @@ void NNLayer::ForwardPropagateFullyConnected(uint32_t position, uint32_t batch, 
                 }
                 sgemm_beta = (NNFloat)1.0;
             }
-            Reduce(batch, _stride, GetIncomingUnitBuffer(), _localStride, _unitUpdateCount);
+            // kAddBias + activation (E/NNLayer.cpp:1247-1340) ride on the exchange when this is the layer's only contribution
+            const bool fuse = net->FusionEnabled() && _unitUpdateCount == 0 && _vIncomingLayer.size() == 1 && _activation != SoftMax && !biasActDone;
+            Reduce(batch, _stride, GetIncomingUnitBuffer(), _localStride, _unitUpdateCount, UnitsReduce,
+                   fuse ? _vIncomingWeight[0]->_pbBias->_pDevData : NULL, (fuse && !deferActivation) ? _activation : Linear);
+            biasActDone = biasActDone || fuse;
             _unitUpdateCount++;
         }
-        for (size_t i = 0; i < _vIncomingLayer.size(); i++)                                  // E/NNLayer.cpp:1247-1280
-            getGpu().Check(dsb200_add_bias(ctx, GetIncomingUnitBuffer(), _vIncomingWeight[i]->_pbBias->_pDevData, _localStride, batch), "dsb200_add_bias");
-        if (deferActivation) _bActivationPending = true;
-        else CalculateActivation(batch);
+        if (_bForwardDeferred) {
+            _bActivationPending = true;                                           // CalculateErrorAsync runs GEMM + bias + activation + loss + delta as one kernel
+        } else {
+            if (!biasActDone) {
+                for (size_t i = 0; i < _vIncomingLayer.size(); i++)                          // E/NNLayer.cpp:1247-1280
+                    getGpu().Check(dsb200_add_bias(ctx, GetIncomingUnitBuffer(), _vIncomingWeight[i]->_pbBias->_pDevData, _localStride, batch), "dsb200_add_bias");
+            }
+            if (deferActivation) _bActivationPending = true;
+            else if (!biasActDone) CalculateActivation(batch);
+        }
         if (bTraining && _pDropout > (NNFloat)0.0 && !_bActivationPending) CalculateDropout(batch);   // E/NNLayer.cpp:1340-1341
     }
     // circulate activations to the outgoing larger layers (E/NNLayer.cpp:1340-1421)
@@ -276,12 +290,30 @@ void NNLayer::ForwardPropagateFullyConnected(uint32_t position, uint32_t batch, 
         if (_bFastSparse)
             throw DsbEngineError("NNLayer::ForwardPropagate: sparse input layer " + _name + " feeding a wider layer is not supported model-parallel "
                                  "(the reference shards the dataset by columns but keeps full-height weights here, E/NNWeight.cpp:438 'BUG?')");
-        Gather(batch, _stride, GetUnitBuffer(), _localStride);
+        _pGatheredUnits = Gather(batch, _stride, GetUnitBuffer(), _localStride, UnitsGather);
+        _bUnitsGathered = bTraining;                                              // the backward pass of this step reuses it (E/NNLayer.cpp:2323 gathers again)
         for (size_t i = 0; i < _vOutgoingLargerLayer.size(); i++) {
             NNLayer* out = _vOutgoingLargerLayer[i];
-            const NNFloat sgemm_beta = (out->_unitUpdateCount == 0) ? (NNFloat)0.0 : (NNFloat)1.0;
-            getGpu().Check(dsb200_gemm_fwd(ctx, batch, _stride, out->_localStride, net->GetP2PSendBuffer(),
-                                           _vOutgoingLargerWeight[i]->_pbWeight->_pDevData, sgemm_beta, out->GetIncomingUnitBuffer()), "dsb200_gemm_fwd");
+            NNWeight* w = _vOutgoingLargerWeight[i];
+            const bool only = net->FusionEnabled() && out->_vIncomingLayer.size() == 1 && out->_unitUpdateCount == 0 && out->_activation != SoftMax;
+            const bool outDefer = bTraining && out->FusedOutputEligible(net->GetErrorFunction());
+            if (only && outDefer && getGpu()._bFuseOutputGemm && out->_activation == Sigmoid && out->_pDataSet && (out->_pDataSet->_attributes & NNDataSetEnums::Boolean)) {
+                // the output layer's forward GEMM is deferred into its loss / delta pass (dsb200_gemm_fwd_output_pass)
+                out->_bForwardDeferred = true;
+                out->_preActivationBatch = batch;
+                out->_pDeferredA = _pGatheredUnits;
+                out->_deferredK = _stride;
+            } else if (only) {
+                // bias + GEMM (+ activation unless the fused loss pass applies it) in one call
+                getGpu().Check(dsb200_gemm_fwd_bias_act(ctx, batch, _stride, out->_localStride, _pGatheredUnits, w->_pbWeight->_pDevData, w->_pbBias->_pDevData,
+                                                        outDefer ? (int)Linear : (int)out->_activation, out->GetIncomingUnitBuffer(),
+                                                        out->_RELUSlope, out->_ELUAlpha, out->_SELULambda), "dsb200_gemm_fwd_bias_act");
+                out->_bBiasActDone = true;
+            } else {
+                const NNFloat sgemm_beta = (out->_unitUpdateCount == 0) ? (NNFloat)0.0 : (NNFloat)1.0;
+                getGpu().Check(dsb200_gemm_fwd(ctx, batch, _stride, out->_localStride, _pGatheredUnits, w->_pbWeight->_pDevData, sgemm_beta,
+                                               out->GetIncomingUnitBuffer()), "dsb200_gemm_fwd");
+            }
             out->_unitUpdateCount++;
         }
     }
@@ -317,11 +349,10 @@ bool NNLayer::CalculateErrorAsync(uint32_t position, uint32_t batch, ErrorFuncti
         // forward GEMM + activation + loss + delta as ONE tcgen05 kernel (csrc/gemm_stream.cu); the units are not produced at all
         // (MaterializeUnits re-runs the layer if somebody asks for them).  The kernel also leaves the column sums of delta, i.e.
         // the bias gradient, so NNWeight::UpdateWeights does not read delta again.
-        NNLayer* in = _vIncomingLayer[0];
         NNWeight* w = _vIncomingWeight[0];
         dsb200_sparse v = _pDataSet->View();
         uint32_t nPartials = 0;
-        const int rc = dsb200_gemm_fwd_output_pass(getGpu()._ctx, &v, (int)ef, (int)_activation, position, batch, in->_stride, _localStride, in->GetUnitBuffer(),
+        const int rc = dsb200_gemm_fwd_output_pass(getGpu()._ctx, &v, (int)ef, (int)_activation, position, batch, _deferredK, _localStride, _pDeferredA,
                                                    w->_pbWeight->_pDevData, w->_pbBias->_pDevData, NULL, GetIncomingDeltaBuffer(), pDevAccumulator,
                                                    w->BiasPartialsBuffer(batch), &nPartials);
         if (rc == 0) {
@@ -434,80 +465,107 @@ void NNLayer::BackPropagateFullyConnected(uint32_t position, uint32_t batch)
     // ---------------------------------------------------------------- model parallel (E/NNLayer.cpp:2316-2626)
     NNFloat* pSend = net->GetP2PSendBuffer();
     if (!_vOutgoingLargerLayer.empty()) {
-        // all-gather X(L): every rank needs all of it for dW(L->L+1) of its output slice
-        Gather(batch, _stride, GetUnitBuffer(), _localStride);
+        // X(L) on every rank: every rank needs all of it for dW(L->L+1) of its output slice.  The forward pass of this step
+        // gathered it already (the reference gathers again, E/NNLayer.cpp:2323)
+        NNFloat* pX = _bUnitsGathered ? _pGatheredUnits : Gather(batch, _stride, GetUnitBuffer(), _localStride, UnitsGather);
         for (size_t i = 0; i < _vOutgoingLargerLayer.size(); i++) {
             NNLayer* out = _vOutgoingLargerLayer[i];
             NNWeight* w = _vOutgoingLargerWeight[i];
+            if (w->_bLocked) continue;
             const NNFloat sgemm_alpha = -(NNFloat)1.0 / (w->_sharingCount * (NNFloat)batch);
             const NNFloat sgemm_beta = (w->_updateCount == 0) ? (NNFloat)0.0 : (NNFloat)1.0;
-            getGpu().Check(dsb200_gemm_dw(ctx, batch, _stride, out->_localStride, sgemm_alpha, pSend, out->GetDeltaBuffer(), sgemm_beta,
+            getGpu().Check(dsb200_gemm_dw(ctx, batch, _stride, out->_localStride, sgemm_alpha, pX, out->GetDeltaBuffer(), sgemm_beta,
                                           w->_pbWeightGradient->_pDevData), "dsb200_gemm_dw");
             w->_updateCount++;
         }
-        // partial delta(L) over this rank's output slices, then reduce-scatter
-        NNFloat sgemm_beta = (NNFloat)0.0;
-        for (size_t i = 0; i < _vOutgoingLargerLayer.size(); i++) {
-            NNLayer* out = _vOutgoingLargerLayer[i];
-            getGpu().Check(dsb200_gemm_dx(ctx, batch, _stride, out->_localStride, out->GetDeltaBuffer(), _vOutgoingLargerWeight[i]->_pbWeight->_pDevData,
-                                          sgemm_beta, pSend), "dsb200_gemm_dx");
-            sgemm_beta = (NNFloat)1.0;
+        if (_kind != Input) {
+            // partial delta(L) over this rank's output slices, then reduce-scatter
+            NNFloat sgemm_beta = (NNFloat)0.0;
+            for (size_t i = 0; i < _vOutgoingLargerLayer.size(); i++) {
+                NNLayer* out = _vOutgoingLargerLayer[i];
+                getGpu().Check(dsb200_gemm_dx(ctx, batch, _stride, out->_localStride, out->GetDeltaBuffer(), _vOutgoingLargerWeight[i]->_pbWeight->_pDevData,
+                                              sgemm_beta, pSend), "dsb200_gemm_dx");
+                sgemm_beta = (NNFloat)1.0;
+            }
+            Reduce(batch, _stride, GetIncomingDeltaBuffer(), _localStride, _deltaUpdateCount, DeltaReduce);
+            _deltaUpdateCount++;
         }
-        Reduce(batch, _stride, GetIncomingDeltaBuffer(), _localStride, _deltaUpdateCount);
-        _deltaUpdateCount++;
     }
     hiddenLocal();
     if (!_vIncomingLargerLayer.empty()) {
-        // all-gather delta(L): dW and delta of the incoming larger layers need every unit of it
-        Gather(batch, _stride, GetDeltaBuffer(), _localStride);
+        // delta(L) on every rank: dW and delta of the incoming larger layers need every unit of it.  It stays where the exchange
+        // delivered it (an arena slot / a buffer of this layer) until the next step, so a deferred consumer can rely on it
+        NNFloat* pD = Gather(batch, _stride, GetDeltaBuffer(), _localStride, DeltaGather);
         for (size_t i = 0; i < _vIncomingLargerLayer.size(); i++) {
             NNLayer* in = _vIncomingLargerLayer[i];
             NNWeight* w = _vIncomingLargerWeight[i];
-            const NNFloat sgemm_alpha = -(NNFloat)1.0 / (w->_sharingCount * (NNFloat)batch);
-            const NNFloat sgemm_beta = (w->_updateCount == 0) ? (NNFloat)0.0 : (NNFloat)1.0;
-            if (in->_kind == Input && in->_bFastSparse) {
-                if (net->FusionEnabled() && net->_mode == Training && sgemm_beta == (NNFloat)0.0 && w->_sharingCount == 1 && (_stride % 4 == 0)) {
-                    // the gathered delta stays in the send buffer until UpdateWeights: this is the last Gather of the step
-                    // for the input weight (the input layer is the end of the back-propagation order)
-                    w->_bDeferredSparseGradient = true;
-                    w->_pDeferredDelta = pSend;
-                } else
-                    in->_pDataSet->CalculateSparseTransposedWeightGradient(sgemm_alpha, sgemm_beta, in->_localStride, _stride, pSend, w->_pbWeightGradient->_pDevData);
-            } else {
-                getGpu().Check(dsb200_gemm_dw(ctx, batch, in->_localStride, _stride, sgemm_alpha, in->GetUnitBuffer(), pSend, sgemm_beta,
-                                              w->_pbWeightGradient->_pDevData), "dsb200_gemm_dw");
+            if (!w->_bLocked) {
+                const NNFloat sgemm_alpha = -(NNFloat)1.0 / (w->_sharingCount * (NNFloat)batch);
+                const NNFloat sgemm_beta = (w->_updateCount == 0) ? (NNFloat)0.0 : (NNFloat)1.0;
+                if (in->_kind == Input && in->_bFastSparse) {
+                    if (net->FusionEnabled() && net->_mode == Training && sgemm_beta == (NNFloat)0.0 && w->_sharingCount == 1 && (_stride % 4 == 0)) {
+                        w->_bDeferredSparseGradient = true;                       // produced inside NNWeight::UpdateWeights, fused with the optimizer
+                        w->_pDeferredDelta = pD;
+                    } else
+                        in->_pDataSet->CalculateSparseTransposedWeightGradient(sgemm_alpha, sgemm_beta, in->_localStride, _stride, pD, w->_pbWeightGradient->_pDevData);
+                } else {
+                    getGpu().Check(dsb200_gemm_dw(ctx, batch, in->_localStride, _stride, sgemm_alpha, in->GetUnitBuffer(), pD, sgemm_beta,
+                                                  w->_pbWeightGradient->_pDevData), "dsb200_gemm_dw");
+                }
+                w->_updateCount++;
             }
-            w->_updateCount++;
             if (in->_kind != Input) {
                 const NNFloat beta2 = (in->_deltaUpdateCount == 0) ? (NNFloat)0.0 : (NNFloat)1.0;
-                getGpu().Check(dsb200_gemm_dx(ctx, batch, in->_localStride, _stride, pSend, w->_pbWeight->_pDevData, beta2, in->GetIncomingDeltaBuffer()), "dsb200_gemm_dx");
+                getGpu().Check(dsb200_gemm_dx(ctx, batch, in->_localStride, _stride, pD, w->_pbWeight->_pDevData, beta2, in->GetIncomingDeltaBuffer()), "dsb200_gemm_dx");
                 in->_deltaUpdateCount++;
             }
         }
     }
 }
 
-// NNLayer::Reduce (E/NNLayer.cpp:2702-2761): the full [batch][stride] sum sits in the send buffer;
-// this rank ends up with its unit slice.  One NCCL reduce-scatter.
-void NNLayer::Reduce(uint32_t batch, uint32_t stride, NNFloat* pBuffer, uint32_t localStride, uint32_t updateCount)
+// NNLayer::Reduce (E/NNLayer.cpp:2702-2761): the full [batch][stride] partial sums sit in the send buffer; this rank ends up with
+// the sum over the ranks of its unit slice, optionally with bias and activation applied (the peer-memory kernel does both while it
+// sums; on NCCL they are separate launches).
+void NNLayer::Reduce(uint32_t batch, uint32_t stride, NNFloat* pBuffer, uint32_t localStride, uint32_t updateCount, ExchangeSlot slot,
+                     const NNFloat* pBias, Activation activation)
 {
     NNNetwork* net = getGpu()._pNetwork;
     if (getGpu()._numprocs == 1) return;
-    if (updateCount > 0) {
-        NNFloat* tmp = net->GetScratchBuffer((size_t)batch * localStride);
-        getGpu().Check(dsb200_reduce_scatter(getGpu()._ctx, batch, stride, net->GetP2PSendBuffer(), tmp), "dsb200_reduce_scatter");
-        net->AddBuffers(pBuffer, tmp, (uint64_t)batch * localStride);
-    } else {
-        getGpu().Check(dsb200_reduce_scatter(getGpu()._ctx, batch, stride, net->GetP2PSendBuffer(), pBuffer), "dsb200_reduce_scatter");
+    dsb200_ctx* ctx = getGpu()._ctx;
+    NNFloat* dst = pBuffer;
+    if (updateCount > 0) dst = net->GetScratchBuffer((size_t)batch * localStride);
+    if (net->PeerMemoryExchange()) {
+        const bool epi = updateCount == 0;
+        getGpu().Check(dsb200_p2p_reduce_scatter(ctx, 4 * _exchangeIndex + (uint32_t)slot, batch, stride, net->GetP2PSendBuffer(), dst, epi ? pBias : NULL,
+                                                 epi ? (int)activation : (int)Linear, _RELUSlope, _ELUAlpha, _SELULambda), "dsb200_p2p_reduce_scatter");
+        if (updateCount > 0) net->AddBuffers(pBuffer, dst, (uint64_t)batch * localStride);
+        if (!epi && (pBias || activation != Linear)) throw DsbEngineError("NNLayer::Reduce: bias / activation on an accumulating exchange");
+        return;
     }
+    getGpu().Check(dsb200_reduce_scatter(ctx, batch, stride, net->GetP2PSendBuffer(), dst), "dsb200_reduce_scatter");
+    if (updateCount > 0) { net->AddBuffers(pBuffer, dst, (uint64_t)batch * localStride); return; }
+    if (pBias) getGpu().Check(dsb200_add_bias(ctx, pBuffer, pBias, localStride, batch), "dsb200_add_bias");
+    if (activation != Linear)
+        getGpu().Check(dsb200_activation(ctx, (int)activation, pBuffer, batch, localStride, _RELUSlope, _ELUAlpha, _SELULambda), "dsb200_activation");
 }
 
-// NNLayer::Gather (E/NNLayer.cpp:2764-2826): local slices -> the full [batch][stride] in the send buffer.
-void NNLayer::Gather(uint32_t batch, uint32_t stride, NNFloat* pBuffer, uint32_t localStride)
+// NNLayer::Gather (E/NNLayer.cpp:2764-2826): local slices -> the full [batch][stride] on every rank; returns where it is.
+NNFloat* NNLayer::Gather(uint32_t batch, uint32_t stride, NNFloat* pBuffer, uint32_t localStride, ExchangeSlot slot)
 {
     (void)localStride;
-    if (getGpu()._numprocs == 1) return;
-    getGpu().Check(dsb200_all_gather(getGpu()._ctx, batch, stride, pBuffer, getGpu()._pNetwork->GetP2PSendBuffer()), "dsb200_all_gather");
+    if (getGpu()._numprocs == 1) return pBuffer;
+    NNNetwork* net = getGpu()._pNetwork;
+    dsb200_ctx* ctx = getGpu()._ctx;
+    if (net->PeerMemoryExchange()) {
+        const uint32_t s = 4 * _exchangeIndex + (uint32_t)slot;
+        getGpu().Check(dsb200_p2p_all_gather(ctx, s, batch, stride, pBuffer), "dsb200_p2p_all_gather");
+        return dsb200_p2p_slot(ctx, s);
+    }
+    unique_ptr<GpuBuffer<NNFloat>>& buf = (slot == DeltaGather) ? _pbGatheredDelta : _pbGatheredUnits;
+    const uint64_t need = (uint64_t)_batch * stride;
+    if (!buf || buf->_length < need) buf.reset(new GpuBuffer<NNFloat>(need));
+    getGpu().Check(dsb200_all_gather(ctx, batch, stride, pBuffer, buf->_pDevData), "dsb200_all_gather");
+    return buf->_pDevData;
 }
 
 bool NNLayer::GetUnits(vector<NNFloat>& vUnit)

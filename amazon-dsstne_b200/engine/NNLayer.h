@@ -56,7 +56,16 @@ private:
     uint32_t                _preActivationBatch;
     bool                    _bForwardDeferred = false;    // engine option "fuse_output_gemm": the forward GEMM of this (output) layer has not run; the
                                                           // loss / delta pass runs it fused, or RunDeferredForward() runs it when the units are needed
+    const NNFloat*          _pDeferredA = NULL;           // input of the deferred forward GEMM: the units of the layer below (all of them:
+    uint32_t                _deferredK = 0;               // the gathered copy when model parallel) and their count
     void                    RunDeferredForward(bool applyActivation);
+    // model-parallel exchange state (B200: one peer-memory kernel or one NCCL call per exchange, see Reduce / Gather)
+    enum ExchangeSlot { UnitsGather = 0, UnitsReduce = 1, DeltaReduce = 2, DeltaGather = 3 };
+    uint32_t                _exchangeIndex = 0;           // position in NNNetwork::_vLayer: slot = 4 * index + ExchangeSlot
+    NNFloat*                _pGatheredUnits = NULL;       // all units of this layer on this rank, valid while _bUnitsGathered (one step)
+    bool                    _bUnitsGathered = false;
+    bool                    _bBiasActDone = false;        // the layer below already applied bias (+ activation) in its GEMM epilogue
+    unique_ptr<GpuBuffer<NNFloat>> _pbGatheredUnits, _pbGatheredDelta;   // NCCL path only: the peer-memory path gathers into its arena slots
 
     vector<NNLayer*>        _vIncomingLayer;
     vector<NNWeight*>       _vIncomingWeight;
@@ -93,8 +102,9 @@ private:
     void BackPropagateFullyConnected(uint32_t position, uint32_t batch);
     void CalculateOutputDelta(uint32_t position, uint32_t batch, ErrorFunction ef);
     void GenerateDenoisingData();
-    void Reduce(uint32_t batch, uint32_t stride, NNFloat* pBuffer, uint32_t localStride, uint32_t updateCount);
-    void Gather(uint32_t batch, uint32_t stride, NNFloat* pBuffer, uint32_t localStride);
+    void Reduce(uint32_t batch, uint32_t stride, NNFloat* pBuffer, uint32_t localStride, uint32_t updateCount, ExchangeSlot slot,
+                const NNFloat* pBias = NULL, Activation activation = Linear);
+    NNFloat* Gather(uint32_t batch, uint32_t stride, NNFloat* pBuffer, uint32_t localStride, ExchangeSlot slot);
     void ClearUpdates();
     bool FusedOutputEligible(ErrorFunction ef) const;
     void MaterializeUnits();                              // apply the activation now if the fused training pass skipped storing it

@@ -300,7 +300,9 @@ void NNNetwork::AddBuffers(NNFloat* pDst, NNFloat* pSrc, uint64_t size)
     getGpu().Check(dsb200_add_buffers(getGpu()._ctx, pDst, pSrc, size), "dsb200_add_buffers");
 }
 
-// E/NNNetwork.cpp:2666-2714: one full-width exchange buffer instead of two IPC-exported peer buffers
+// E/NNNetwork.cpp:2666-2714 allocates two IPC-exported peer buffers per rank for its copy ring.  Here: one local full-width
+// buffer for the partial sums a reduce-scatter starts from, plus -- engine option "p2p_exchange", on by default -- the
+// peer-mapped arena of csrc/comm.cu with four slots per layer (gathered units / reduced units / reduced delta / gathered delta).
 void NNNetwork::AllocatePeerBuffers()
 {
     if (getGpu()._numprocs <= 1) return;
@@ -311,6 +313,16 @@ void NNNetwork::AllocatePeerBuffers()
     }
     const uint64_t need = (uint64_t)_maxStride * _batch;
     if (!_pbP2PBuffer || _pbP2PBuffer->_length < need) _pbP2PBuffer.reset(new GpuBuffer<NNFloat>(need));
+    for (size_t i = 0; i < _vLayer.size(); i++) _vLayer[i]->_exchangeIndex = (uint32_t)i;
+    const uint64_t slotFloats = (uint64_t)_batch * (_maxStride + (uint32_t)getGpu()._numprocs);
+    if (!getGpu()._bP2PExchange) { _bPeerMemoryExchange = false; return; }
+    if (_bPeerMemoryExchange && _peerSlotFloats >= slotFloats) return;           // mapped already and large enough
+    // collective: every rank makes this call at the same point of RefreshState with the same sizes; any rank failing makes all fall back
+    const int rc = dsb200_p2p_setup(getGpu()._ctx, (uint32_t)(4 * _vLayer.size()), slotFloats);
+    _bPeerMemoryExchange = rc == 0;
+    _peerSlotFloats = _bPeerMemoryExchange ? slotFloats : 0;
+    if (rc != 0 && rc != DSB200_EUNSUPPORTED) getGpu().Check(rc, "dsb200_p2p_setup");
+    if (!_bPeerMemoryExchange && getGpu()._id == 0) printf("NNNetwork: peer-memory exchange unavailable, the exchange steps use NCCL\n");
 }
 
 void NNNetwork::RefreshState()

@@ -71,6 +71,8 @@ private:
     bool                    _verbose;
     bool                    _bRegularizationLaunched;     // LaunchError finds the regularisation kernels already in flight
     bool                    _bFusion;                     // B200 fusions on (default) / off (kernel-by-kernel, like the reference)
+    bool                    _bPeerMemoryExchange = false; // model parallel: the peer-memory arena is mapped on every rank (AllocatePeerBuffers)
+    uint64_t                _peerSlotFloats = 0;
     // divergence-brake state that survives across Train calls made one step at a time
     NNFloat                 _movingAverage;
     uint32_t                _brakeSteps, _initSteps;
@@ -102,6 +104,8 @@ public:
     void SetClearVelocity(bool bClear) { _bClearVelocity = bClear; }
     void SetFusion(bool bFusion) { _bFusion = bFusion; }
     bool FusionEnabled() const { return _bFusion; }
+    void MarkDirty() { _bDirty = true; }
+    bool PeerMemoryExchange() const { return _bPeerMemoryExchange; }     // exchange steps on the dsb200_p2p_* kernels (else NCCL)
     bool SaveNetCDF(const string& fname);
     unsigned int GetBatch() const { return _batch; }
     uint32_t GetExamples() const { return _examples; }

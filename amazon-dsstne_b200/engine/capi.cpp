@@ -72,6 +72,7 @@ int dsb200_engine_set_option(const char* name, int value)
     DSB_ENGINE_TRY
     if (name && !strcmp(name, "pinned_mirror")) { getGpu()._bPinnedMirror = value != 0; return 0; }      // engine-level option
     if (name && !strcmp(name, "fuse_output_gemm")) { getGpu()._bFuseOutputGemm = value != 0; return 0; }
+    if (name && !strcmp(name, "p2p_exchange")) { getGpu()._bP2PExchange = value != 0; if (getGpu()._pNetwork) getGpu()._pNetwork->MarkDirty(); return 0; }
     getGpu().Check(dsb200_ctx_set_option(getGpu()._ctx, name, value), "dsb200_ctx_set_option");
     DSB_ENGINE_CATCH
 }

@@ -158,8 +158,7 @@ def run_ours(args, wl, rank, world, local_rank):
     stream = torch.cuda.Stream(local_rank)
     torch.cuda.set_stream(stream)
     engine.set_stream(stream.cuda_stream)
-    if world > 1 and args.p2p:
-        engine.set_option("p2p_exchange", 1)
+    engine.set_option("p2p_exchange", 1 if args.p2p else 0)
     engine.set_option("fuse_output_gemm", 1 if args.fuse_output else 0)
 
     n_batches = 16 if wl["name"] == "c2" else 4
@@ -511,7 +510,7 @@ def main():
     ap.add_argument("--c4-steps", type=int, default=6)
     ap.add_argument("--fuse-output", type=int, default=1, help="1 (default) = output layer forward GEMM fused with loss + delta (engine option fuse_output_gemm); 0 = two calls")
     ap.add_argument("--pinned-mirror", type=int, default=0, help="e2e path: 1 = LoadSparseData uploads from the page-locked host mirror (experimental single-copy path)")
-    ap.add_argument("--p2p", type=int, default=0, help="N > 1: 1 = exchange steps as one kernel over peer memory (experimental) instead of NCCL")
+    ap.add_argument("--p2p", type=int, default=1, help="N > 1: 1 (default) = exchange steps as one kernel over peer memory each (csrc/comm.cu); 0 = NCCL")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))

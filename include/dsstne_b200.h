@@ -293,6 +293,20 @@ int dsb200_reduce_scatter(dsb200_ctx*, uint32_t batch, uint32_t stride, const fl
 /* local slice [batch][span_r] of every rank -> full [batch][stride] on every rank */
 int dsb200_all_gather(dsb200_ctx*, uint32_t batch, uint32_t stride, const float* pLocal, float* pFull);
 int dsb200_all_reduce(dsb200_ctx*, float* pBuffer, uint64_t size);
+/* The same exchange steps as ONE kernel each over peer memory (csrc/comm.cu): every rank owns an arena of `slots` regions of
+ * `slotFloats` floats, mapped by every peer (cudaIpc); a collective names the slot it delivers into, so the engine can keep the
+ * gathered operand of every layer boundary until that boundary is exchanged again.
+ *   dsb200_p2p_setup           collective; DSB200_EUNSUPPORTED when any rank could not map its peers -> stay on the NCCL calls above
+ *   dsb200_p2p_slot            local address of a slot: the full [batch][stride] result of an all-gather into it
+ *   dsb200_p2p_all_gather      local slice [batch][span_r] of every rank -> slot (full [batch][stride]) on every rank
+ *   dsb200_p2p_reduce_scatter  [batch][stride] summed over the ranks in rank order; this rank keeps its columns as
+ *                              pOut[batch][span] = activation(sum + pBias[span]) -- pBias may be NULL, activation DSB200_ACT_LINEAR
+ *                              (kAddBias + kCalculate*Activation of E/NNLayer.cpp:1257-1340 fused into the exchange)           */
+int    dsb200_p2p_setup(dsb200_ctx*, uint32_t slots, size_t slotFloats);
+float* dsb200_p2p_slot(dsb200_ctx*, uint32_t slot);
+int    dsb200_p2p_all_gather(dsb200_ctx*, uint32_t slot, uint32_t batch, uint32_t stride, const float* pLocal);
+int    dsb200_p2p_reduce_scatter(dsb200_ctx*, uint32_t slot, uint32_t batch, uint32_t stride, const float* pIn, float* pOut, const float* pBias,
+                                 int activation, float slope, float alpha, float lambda);
 int dsb200_all_reduce_u64(dsb200_ctx*, unsigned long long* pBuffer, uint64_t size);
 /* model-parallel partition rules: E/NNLayer.cpp:108-112, E/NNWeight.cpp:435-457 (host only, no GPU) */
 void dsb200_shard_range(uint32_t N, uint32_t rank, uint32_t nranks, uint32_t* pMinX, uint32_t* pMaxX);

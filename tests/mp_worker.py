@@ -34,15 +34,21 @@ def main():
     dist.broadcast(buf, 0)
     engine.startup(rank, world, local, bytes(buf.cpu().tolist()), seed=12134)
     engine.use_torch_stream(local)
-    if os.environ.get("MP_P2P"):
-        engine.set_option("p2p_exchange", 1)          # exchange steps as one kernel over peer memory instead of NCCL (csrc/comm.cu)
+    # exchange steps: one kernel over peer memory each (csrc/comm.cu, the default) or NCCL (MP_P2P=0)
+    engine.set_option("p2p_exchange", int(os.environ.get("MP_P2P", "1")))
+    gemm_mode = int(os.environ.get("MP_GEMM", "0"))   # 2 = tcgen05 3xTF32: the fused output-layer forward + streamed dW / dX on the shards
 
-    h = tiny(examples=2 * batch, width=sizes[0])
+    if os.environ.get("MP_DATA") == "ml20m":
+        from helpers import ml20m
+        h = ml20m(examples=2 * batch, width=sizes[0])
+    else:
+        h = tiny(examples=2 * batch, width=sizes[0])
     ds_in = engine.Dataset.from_host_csr("gl_input", h)
     ds_out = engine.Dataset.from_host_csr("gl_output", h)
     hidden = sizes[1:-1]
     net = engine.Network(engine.autoencoder_json(hidden, sparseness=(0.5, 2.0)), batch, [ds_in, ds_out])
     net.set_training_mode(mode)
+    net.set_gemm_mode(gemm_mode)
     Ws, bs = datagen.make_weights(sizes, scale=0.05)
     names = ["Input"] + [f"Hidden{i + 1}" for i in range(len(hidden))] + ["Output"]
     for i in range(len(sizes) - 1):

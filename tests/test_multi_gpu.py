@@ -26,45 +26,41 @@ def run_world(world, extra_env=None, port=29611):
     return json.loads(lines[-1][len("MP_RESULT "):])
 
 
+@pytest.mark.parametrize("p2p", [1, 0], ids=["peer-memory", "nccl"])
 @pytest.mark.parametrize("world", [2, 4])
-def test_model_parallel_sgd_matches_oracle(world):
-    r = run_world(world, {"MP_MODE": "0"}, port=29611 + world)
+def test_model_parallel_sgd_matches_oracle(world, p2p):
+    r = run_world(world, {"MP_MODE": "0", "MP_P2P": str(p2p)}, port=29611 + world + 10 * p2p)
     assert r["loss_err"] < 1e-5, r
     assert r["stream_loss_err"] < 1e-5, r                     # LoadSparseData while model parallel (the e2e path of bench.py at N > 1)
     for k, v in r["errs"].items():
         assert v < (5e-5 if k.startswith("b") else 1e-5), (k, v, r)
 
 
+@pytest.mark.parametrize("p2p", [1, 0], ids=["peer-memory", "nccl"])
 @pytest.mark.parametrize("world", [2, 4])
-def test_model_parallel_momentum_odd_and_uneven_units(world):
+def test_model_parallel_momentum_odd_and_uneven_units(world, p2p):
     # world 2: odd local strides (65 | 65, 33 | 33, 1025 | 1025) -> scalar kernel paths, no 128-bit alignment;
-    # world 4: 130 and 66 and 2050 do not divide by 4 -> uneven unit ranges (E/NNLayer.cpp:108-112), which take the
-    # all-reduce + slice / grouped-broadcast fallbacks of dsb200_reduce_scatter / dsb200_all_gather
-    r = run_world(world, {"MP_MODE": "1", "MP_SIZES": "[2050, 130, 66, 130, 2050]"}, port=29631 + world)
+    # world 4: 130 and 66 and 2050 do not divide by 4 -> uneven unit ranges (E/NNLayer.cpp:108-112): the peer-memory kernels
+    # address them in place, the NCCL path takes its all-reduce + slice / grouped-broadcast fallbacks
+    r = run_world(world, {"MP_MODE": "1", "MP_SIZES": "[2050, 130, 66, 130, 2050]", "MP_P2P": str(p2p), "MP_TOPK": "20"}, port=29631 + world + 10 * p2p)
     assert r["loss_err"] < 1e-5, r
+    assert r["topk_ok"] is True, r
     for k, v in r["errs"].items():
         assert v < (5e-5 if k.startswith("b") else 1e-5), (k, v, r)
 
 
-# Written at the end of round 1 after the GPU budget was spent: the scheme is pinned bit-exactly on the CPU
-# (tests/test_topk_global_scheme.py) but this GPU path has not run yet -- enable with DSB200_RUN_UNVERIFIED=1 and drop the
-# gate after the first green run.
-unverified = pytest.mark.skipif(not os.environ.get("DSB200_RUN_UNVERIFIED"), reason="not yet run on GPUs (round 1 budget); set DSB200_RUN_UNVERIFIED=1")
+@pytest.mark.parametrize("world", [2, 4, 8])
+def test_model_parallel_config3_shape_tensor_core_path(world):
+    """BASELINE config 3: the ML-20M-shape network sharded 2 / 4 / 8 ways (27,278 / 8 = 3,409.75: uneven shards), 3xTF32 mode, i.e. the
+    fused output-layer forward and the streamed dW / dX kernels on every shard, peer-memory exchange with cached gathers."""
+    r = run_world(world, {"MP_MODE": "0", "MP_SIZES": "[27278, 128, 128, 128, 27278]", "MP_BATCH": "1024", "MP_DATA": "ml20m", "MP_GEMM": "2",
+                          "MP_STEPS": "2"}, port=29651 + world)
+    assert r["loss_err"] < 3e-5, r
+    for k, v in r["errs"].items():
+        assert v < 5e-5, (k, v, r)
 
 
-@unverified
 @pytest.mark.parametrize("world", [2, 4])
 def test_model_parallel_topk_global_matches_single_process(world):
-    r = run_world(world, {"MP_MODE": "0", "MP_TOPK": "50"}, port=29651 + world)
+    r = run_world(world, {"MP_MODE": "0", "MP_TOPK": "50"}, port=29691 + world)
     assert r["topk_ok"] is True, r
-
-
-@unverified
-@pytest.mark.parametrize("world", [2, 4])
-def test_peer_memory_exchange_matches_oracle(world):
-    """option "p2p_exchange": NNLayer::Reduce / Gather as one kernel over cudaIpc-mapped peer buffers (uneven unit ranges too)."""
-    r = run_world(world, {"MP_MODE": "1", "MP_P2P": "1", "MP_SIZES": "[2050, 130, 66, 130, 2050]", "MP_TOPK": "20"}, port=29671 + world)
-    assert r["loss_err"] < 1e-5, r
-    assert r["topk_ok"] is True, r
-    for k, v in r["errs"].items():
-        assert v < (5e-5 if k.startswith("b") else 1e-5), (k, v, r)
