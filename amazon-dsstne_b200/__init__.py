@@ -255,6 +255,13 @@ class Context:
                                               C.c_float(t), C.c_uint32(b), C.c_uint32(width), _ptr(delta), _ptr(v),
                                               _ptr(gv), _ptr(bias)))
 
+    def dense_update(self, mode, galpha, X, D, alpha, lam, lam1, mu, mu1, t, v, gv, w, bv, bgv, bias):
+        """small dense layer: X^T * D weight gradient + optimizer rule + bias update in one launch (csrc/dense_small.cu)"""
+        B, k = X.shape
+        self.check(lib().dsb200_dense_update(self.h, C.c_int(mode), C.c_uint32(B), C.c_uint32(k), C.c_uint32(D.shape[1]), C.c_float(galpha),
+                                             _ptr(X), _ptr(D), C.c_float(alpha), C.c_float(lam), C.c_float(lam1), C.c_float(mu), C.c_float(mu1),
+                                             C.c_float(t), _ptr(v), _ptr(gv), _ptr(w), _ptr(bv), _ptr(bgv), _ptr(bias)))
+
     def regularization_error(self, lam, lam1, w):
         out = C.c_float()
         self.check(lib().dsb200_regularization_error(self.h, C.c_float(lam), C.c_float(lam1), _ptr(w),

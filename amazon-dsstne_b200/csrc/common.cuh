@@ -66,8 +66,12 @@ struct dsb200_ctx {
     int            p2pExchange = 0;               // option "p2p_exchange": 1 = exchange steps as one kernel over peer memory (comm.cu, experimental)
     void*          p2p         = nullptr;         // dsb::P2PState, owned by comm.cu
     int            gemmStream  = 1;               // option "gemm_stream": output-layer shapes on the TMA / tensor-memory kernels of gemm_stream.cu
-    void*          dGsWs       = nullptr;         // gemm_stream.cu: operand copies, split-K partials, target bitmap (grow only)
+    void*          dGsWs       = nullptr;         // gemm_stream.cu: split-K partials and operand copies made inside a call (grow only)
     size_t         gsWsBytes   = 0;
+    // gemm_stream.cu: operands prepared AHEAD of the call that uses them (dsb200_gemm_fwd_output_prepare / _dx_prepare on a side stream,
+    // or the forward pass preparing X for the weight gradient).  One-shot: `valid` is cleared by the call that consumes the buffer.
+    struct Prep { void* buf = nullptr; size_t bytes = 0; const void* key = nullptr; uint32_t a = 0, b = 0, c = 0; bool valid = false; };
+    Prep           prepBits, prepW, prepX;
     char           lastError[256];
 };
 

@@ -92,6 +92,7 @@ int dsb200_ctx_destroy(dsb200_ctx* ctx)
     cudaFree(ctx->dGemmWs);
     cudaFree(ctx->dHeavy);
     cudaFree(ctx->dGsWs);
+    cudaFree(ctx->prepBits.buf); cudaFree(ctx->prepW.buf); cudaFree(ctx->prepX.buf);
     delete ctx;
     return 0;
 }

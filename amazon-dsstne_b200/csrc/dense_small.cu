@@ -113,16 +113,119 @@ int dense_small_fwd(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, const f
 
 }  // namespace dsb
 
-extern "C" int dsb200_gemm_dx_hadamard(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, const float* D, const float* W, int activation,
-                                       float scale, const float* pUnit, float* Dp, float slope, float alpha, float lambda)
+namespace dsb {
+int dense_small_dx_hadamard(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, const float* D, const float* W, int activation, float scale,
+                            const float* pUnit, float* Dp, float slope, float alpha, float lambda)
 {
-    DSB_PROFILE(ctx, "gemm_dx_hadamard");
-    using namespace dsb;
-    if (!ctx || !D || !W || !pUnit || !Dp) return fail(ctx, DSB200_EINVAL, "gemm_dx_hadamard: null argument");
-    if (!B || !k || !n) return 0;
     dim3 grid((k + kDsCols - 1) / kDsCols, (B + kDsRows - 1) / kDsRows);
     dense_small_kernel<true, 1><<<grid, kDsThreads, 0, ctx->stream>>>(D, n, W, n, Dp, k, B, k, n, nullptr, pUnit, activation, scale, slope, alpha, lambda);
     count_launch();
     DSB_CUDA_OK(cudaGetLastError());
     return 0;
+}
+}  // namespace dsb
+
+// =====================================================================================================================
+// dsb200_dense_update: weight gradient + optimizer step + bias update of a SMALL dense layer in ONE launch.
+// Replaces, for the 128 x 128 hidden weights of BASELINE config 2, cublasSgemm (E/NNLayer.cpp:2223; 2 launches with its split-K
+// reduce) + k*UpdateWeights + k*UpdateBiases (E/NNWeight.cpp:729-794): four launches of ~6-14 us each, all latency bound.
+//   g[i][j]  = galpha * sum_b X[b][i] * D[b][j]          (never written)
+//   W[i][j]  = opt_weight(g, W, V, GV)                    (optimizer.cuh, the rules of E/kernels.cu:2746-3199)
+//   bias[j]  = opt_bias(sum_b D[b][j] / B, bias, ...)
+// Grid: x = row i of W (0..k-1) plus one extra index for the bias row (X == 1), y = tiles of 128 columns.  512 threads = 128
+// columns x 4 batch groups; the X column of the row is staged in shared memory once and read as a broadcast; the four group sums
+// are added in a fixed order (deterministic, exact fp32 FMA chains).
+// =====================================================================================================================
+#include "optimizer.cuh"
+
+namespace dsb {
+
+constexpr int kDuCols = 128, kDuGroups = 4, kDuThreads = kDuCols * kDuGroups, kDuMaxB = 4096;
+
+struct DuArgs {
+    const float* X; const float* D; uint32_t B, k, n;
+    float galpha;
+    float* W; float* V; float* GV;
+    float* bias; float* bV; float* bGV;
+};
+
+template <int MODE>
+__global__ void __launch_bounds__(kDuThreads)
+dense_update_kernel(const DuArgs a, const OptArgs ow, const OptArgs ob)
+{
+    __shared__ float sX[kDuMaxB];
+    __shared__ float sAcc[kDuGroups][kDuCols];
+    const uint32_t i = blockIdx.x, j = blockIdx.y * kDuCols + (threadIdx.x & (kDuCols - 1)), g = threadIdx.x / kDuCols;
+    const bool biasRow = i == a.k;
+    for (uint32_t b = threadIdx.x; b < a.B; b += kDuThreads) sX[b] = biasRow ? 1.0f : __ldg(a.X + (size_t)b * a.k + i);
+    __syncthreads();
+    const uint32_t b0 = (uint32_t)(((uint64_t)a.B * g) / kDuGroups), b1 = (uint32_t)(((uint64_t)a.B * (g + 1)) / kDuGroups);
+    float acc = 0.0f;
+    if (j < a.n) {
+        const float* p = a.D + j;
+        uint32_t b = b0;
+        for (; b + 8 <= b1; b += 8) {
+            float d[8];
+#pragma unroll
+            for (int u = 0; u < 8; u++) d[u] = __ldg(p + (size_t)(b + u) * a.n);
+#pragma unroll
+            for (int u = 0; u < 8; u++) acc = fmaf(sX[b + u], d[u], acc);
+        }
+        for (; b < b1; b++) acc = fmaf(sX[b], __ldg(p + (size_t)b * a.n), acc);
+    }
+    sAcc[g][threadIdx.x & (kDuCols - 1)] = acc;
+    __syncthreads();
+    if (g != 0 || j >= a.n) return;
+    float sum = 0.0f;
+#pragma unroll
+    for (int q = 0; q < kDuGroups; q++) sum += sAcc[q][threadIdx.x];
+    if (biasRow) {
+        float vv = opt_uses_v(MODE) ? a.bV[j] : 0.0f, ss = opt_uses_gv(MODE) ? a.bGV[j] : 0.0f;
+        a.bias[j] = opt_bias<MODE>(ob, sum / (float)a.B, a.bias[j], vv, ss);
+        if (opt_uses_v(MODE)) a.bV[j] = vv;
+        if (opt_uses_gv(MODE)) a.bGV[j] = ss;
+    } else {
+        const size_t e = (size_t)i * a.n + j;
+        float vv = opt_uses_v(MODE) ? a.V[e] : 0.0f, ss = opt_uses_gv(MODE) ? a.GV[e] : 0.0f;
+        a.W[e] = opt_weight<MODE>(ow, a.galpha * sum, a.W[e], vv, ss);
+        if (opt_uses_v(MODE)) a.V[e] = vv;
+        if (opt_uses_gv(MODE)) a.GV[e] = ss;
+    }
+}
+
+template <int MODE>
+static int launch_dense_update(dsb200_ctx* ctx, const DuArgs& a, const OptArgs& ow, const OptArgs& ob)
+{
+    dim3 grid(a.k + (a.bias ? 1u : 0u), (a.n + kDuCols - 1) / kDuCols);
+    dense_update_kernel<MODE><<<grid, kDuThreads, 0, ctx->stream>>>(a, ow, ob);
+    count_launch();
+    DSB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
+}  // namespace dsb
+
+extern "C" int dsb200_dense_update(dsb200_ctx* ctx, int mode, uint32_t B, uint32_t k, uint32_t n, float galpha, const float* X, const float* D,
+                                   float alpha, float lambda, float lambda1, float mu, float mu1, float t, float* pWeightVelocity,
+                                   float* pWeightGradientVelocity, float* pWeight, float* pBiasVelocity, float* pBiasGradientVelocity, float* pBias)
+{
+    DSB_PROFILE_T(ctx, "dense_update", (unsigned long long)k * n);
+    using namespace dsb;
+    if (!ctx || !X || !D || !pWeight) return fail(ctx, DSB200_EINVAL, "dense_update: null argument");
+    if (mode < 0 || mode > DSB200_ADAM) return fail(ctx, DSB200_EINVAL, "dense_update: bad mode");
+    if (opt_uses_v(mode) && (!pWeightVelocity || (pBias && !pBiasVelocity))) return fail(ctx, DSB200_EINVAL, "dense_update: velocity buffer missing");
+    if (opt_uses_gv(mode) && (!pWeightGradientVelocity || (pBias && !pBiasGradientVelocity))) return fail(ctx, DSB200_EINVAL, "dense_update: gradient-velocity buffer missing");
+    if (B > (uint32_t)kDuMaxB) return fail(ctx, DSB200_EUNSUPPORTED, "dense_update: batch above 4,096 (use dsb200_gemm_dw + dsb200_update_weights + dsb200_update_biases)");
+    if (!B || !k || !n) return 0;
+    DuArgs a{X, D, B, k, n, galpha, pWeight, pWeightVelocity, pWeightGradientVelocity, pBias, pBiasVelocity, pBiasGradientVelocity};
+    const OptArgs ow = make_opt(mode, alpha, lambda, lambda1, mu, mu1, t), ob = make_opt(mode, alpha, 0.0f, 0.0f, mu, mu1, t);
+    switch (mode) {
+    case DSB200_SGD:      return launch_dense_update<DSB200_SGD>(ctx, a, ow, ob);
+    case DSB200_MOMENTUM: return launch_dense_update<DSB200_MOMENTUM>(ctx, a, ow, ob);
+    case DSB200_ADAGRAD:  return launch_dense_update<DSB200_ADAGRAD>(ctx, a, ow, ob);
+    case DSB200_NESTEROV: return launch_dense_update<DSB200_NESTEROV>(ctx, a, ow, ob);
+    case DSB200_RMSPROP:  return launch_dense_update<DSB200_RMSPROP>(ctx, a, ow, ob);
+    case DSB200_ADADELTA: return launch_dense_update<DSB200_ADADELTA>(ctx, a, ow, ob);
+    default:              return launch_dense_update<DSB200_ADAM>(ctx, a, ow, ob);
+    }
 }

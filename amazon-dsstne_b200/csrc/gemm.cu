@@ -36,7 +36,11 @@ bool gemm_stream_available();
 int gemm_stream_dw(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, float alpha, const float* X, const float* D, uint32_t ldd, float beta,
                    float* G, uint32_t ldg);
 int gemm_stream_dx(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, const float* D, uint32_t ldd, const float* W, uint32_t ldw, float beta,
-                   float* Dp, uint32_t ldp);
+                   float* Dp, uint32_t ldp, const float* hadUnit, int hadAct, float hadScale, float slope, float ealpha, float lambda);
+int gemm_stream_prepare_targets(dsb200_ctx* ctx, const dsb200_sparse* s, uint32_t position, uint32_t batch, uint32_t n);
+int gemm_stream_prepare_dx(dsb200_ctx* ctx, uint32_t k, uint32_t n, const float* W, uint32_t ldw);
+int dense_small_dx_hadamard(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, const float* D, const float* W, int activation, float scale,
+                            const float* pUnit, float* Dp, float slope, float alpha, float lambda);
 int gemm_stream_out_fwd(dsb200_ctx* ctx, const dsb200_sparse* s, int ef, uint32_t position, uint32_t batch, uint32_t k, uint32_t n, const float* X,
                         const float* W, uint32_t ldw, const float* bias, float* unitOut, float* delta, uint32_t ldd, unsigned long long* acc,
                         float* pColPartials, uint32_t* pNumPartials);
@@ -113,7 +117,7 @@ int dsb200_gemm_dx(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, const fl
     if (!B || !k || !n) return 0;
     if (use_tc(ctx, B, k, n) && use_stream(ctx, B, k, n)) {
         DSB_PROFILE(ctx, "gemm_dx_stream");
-        return gemm_stream_dx(ctx, B, k, n, D, n, W, n, beta, Dp, k);
+        return gemm_stream_dx(ctx, B, k, n, D, n, W, n, beta, Dp, k, nullptr, DSB200_ACT_LINEAR, 1.0f, 0.f, 0.f, 0.f);
     }
     DSB_PROFILE(ctx, use_tc(ctx, B, k, n) ? "gemm_dx_tc" : "gemm_dx");
     if (use_tc(ctx, B, k, n)) return gemm_tc_launch(ctx, D, 0, n, W, 0, n, Dp, k, B, k, n, 1.0f, beta, nullptr, DSB200_ACT_LINEAR, 0.f, 0.f, 0.f);
@@ -123,6 +127,28 @@ int dsb200_gemm_dx(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, const fl
     if (cublasSgemm(h, CUBLAS_OP_T, CUBLAS_OP_N, (int)k, (int)B, (int)n, &one, W, (int)n, D, (int)n, &beta, Dp, (int)k) != CUBLAS_STATUS_SUCCESS)
         return fail(ctx, DSB200_ESTATE, "gemm_dx: SGEMM failure");
     return 0;
+}
+
+/* fused input delta: Dp = (D * W^T) (.) f'(pUnit) * scale -- cublasSgemm (E/NNLayer.cpp:2274) + kCalculateHadamardProduct of the layer
+ * below (E/NNLayer.cpp:2137).  Output-layer shapes: the streamed tcgen05 kernel with the product in its split-K reduction; small
+ * layers: one SIMT launch (dense_small.cu); anything else: the two calls. */
+int dsb200_gemm_dx_hadamard(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, const float* D, const float* W, int activation, float scale,
+                            const float* pUnit, float* Dp, float slope, float alpha, float lambda)
+{
+    using namespace dsb;
+    if (!ctx || !D || !W || !pUnit || !Dp) return fail(ctx, DSB200_EINVAL, "gemm_dx_hadamard: null argument");
+    if (!B || !k || !n) return 0;
+    if (use_tc(ctx, B, k, n) && use_stream(ctx, B, k, n)) {
+        DSB_PROFILE(ctx, "gemm_dx_stream");
+        return gemm_stream_dx(ctx, B, k, n, D, n, W, n, 0.0f, Dp, k, pUnit, activation, scale, slope, alpha, lambda);
+    }
+    if ((uint64_t)B * k * n <= (1ull << 27)) {
+        DSB_PROFILE(ctx, "gemm_dx_hadamard");
+        return dense_small_dx_hadamard(ctx, B, k, n, D, W, activation, scale, pUnit, Dp, slope, alpha, lambda);
+    }
+    int rc = dsb200_gemm_dx(ctx, B, k, n, D, W, 0.0f, Dp);
+    if (!rc) rc = dsb200_hadamard(ctx, activation, (uint64_t)B * k, scale, pUnit, Dp, slope, alpha, lambda);
+    return rc;
 }
 
 /* fused forward of a dense layer: C = act(A * W + bias), i.e. kClearUnit + cublasSgemm(beta = 1) + kCalculate*Activation
@@ -145,6 +171,27 @@ int dsb200_gemm_fwd_bias_act(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n
     if (!rc) rc = dsb200_gemm_fwd(ctx, B, k, n, A, W, 1.0f, C);
     if (!rc && activation != DSB200_ACT_LINEAR) rc = dsb200_activation(ctx, activation, C, B, n, slope, alpha, lambda);
     return rc;
+}
+
+// Optional hints: build, AHEAD of the calls that use them and typically on another stream (dsb200_ctx_set_stream), the operands
+// that depend only on the data batch (the transposed target bitmap of dsb200_gemm_fwd_output_pass) or only on the weights (the
+// hi / lo copies of W of dsb200_gemm_dx).  One-shot: the next matching call consumes them; without a match the call builds its own.
+int dsb200_gemm_fwd_output_prepare(dsb200_ctx* ctx, const dsb200_sparse* s, uint32_t position, uint32_t batch, uint32_t n)
+{
+    using namespace dsb;
+    if (!ctx || !s || !s->sparseStart || !s->sparseEnd || !s->sparseIndex) return fail(ctx, DSB200_EINVAL, "gemm_fwd_output_prepare: null argument");
+    if ((ctx->gemmMode != DSB200_GEMM_TF32 && ctx->gemmMode != DSB200_GEMM_TF32X3) || !ctx->gemmStream || !gemm_stream_available() || !batch || !n) return 0;
+    DSB_PROFILE(ctx, "gemm_fwd_output_prepare");
+    return gemm_stream_prepare_targets(ctx, s, position, batch, n);
+}
+
+int dsb200_gemm_dx_prepare(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, const float* W)
+{
+    using namespace dsb;
+    if (!ctx || !W) return fail(ctx, DSB200_EINVAL, "gemm_dx_prepare: null argument");
+    if (!B || !k || !n || !(use_tc(ctx, B, k, n) && use_stream(ctx, B, k, n))) return 0;
+    DSB_PROFILE(ctx, "gemm_dx_prepare");
+    return gemm_stream_prepare_dx(ctx, k, n, W, n);
 }
 
 // Forward pass of a sigmoid output layer over Boolean sparse targets with loss + delta in the GEMM epilogue (gemm_stream.cu,

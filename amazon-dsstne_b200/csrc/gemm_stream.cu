@@ -159,10 +159,10 @@ constexpr int S_LOAD_WARPS = 8, S_EPI_WARP0 = 8, S_EPI_WARPS = 4, S_TMA_WARP = 1
 constexpr int S_THREADS = 14 * 32;
 // The tensor core's fp32 accumulator truncates, so the error of a product grows with the number of MMAs chained into one accumulator
 // (measured in round 1: 2e-6 at K <= 128, 1.8e-5 at K = 1,024; an engine test on the exact config-2 network saw 4e-5 on a hidden
-// weight after two steps, all of one sign).  Chains are therefore cut every S_CHUNK k-iterations (192 MMAs): the MMA warp switches to
+// weight after two steps, all of one sign).  Chains are therefore cut every S_CHUNK k-iterations (96 MMAs): the MMA warp switches to
 // the other accumulator, and the epilogue warps add the finished chunk into an fp32 tile in SHARED MEMORY (round to nearest; 64 KB,
 // layout [column / 4][row][4] so that the 32 rows of a warp are 32 consecutive 16-byte words) while the next chunk runs.
-constexpr int S_CHUNK = 16;
+constexpr int S_CHUNK = 8;
 constexpr int S_SUM_BYTES = BM * BN * 4;
 constexpr int S_SLOTS = 4, S_DEPTH = 3;        // ring depth / register panels in flight per loader thread
 constexpr uint32_t S_ACC_COLS = 2 * BN, S_A_COLS = 2 * BK;
@@ -487,10 +487,24 @@ stream_kernel(const SArgs a, const __grid_constant__ CUtensorMap mapHi, const __
     if (warp == S_MMA_WARP) tmem_dealloc(tmem, TMEM_COLS);
 }
 
-// C = alpha * sum_z partial[z] + beta * C, optionally times f'(unit) (kCalculateHadamardProduct, E/kDelta.cu:8979-9032);
-// fixed summation order -> deterministic
+// C = alpha * sum_z partial[z] + beta * C, optionally times f'(unit) (kCalculateHadamardProduct, E/kDelta.cu:8979-9032: the delta of
+// the layer below leaves the input-delta GEMM finished); fixed summation order -> deterministic
+struct HadArgs { const float* unit; int act; float scale, slope, alpha, lambda; };
+__device__ __forceinline__ float gs_hadamard(const HadArgs& h, float x, float d)
+{
+    switch (h.act) {
+    case DSB200_ACT_SIGMOID: return x * (1.0f - x) * d;
+    case DSB200_ACT_TANH:    { const float xs = x * (1.0f / h.scale); return h.scale * (1.0f - xs * xs) * d; }
+    case DSB200_ACT_RELU:    return (x <= 0.0f) ? 0.0f : d;
+    case DSB200_ACT_LRELU:   return (x <= 0.0f) ? d * h.slope : d;
+    case DSB200_ACT_ELU:     return (x <= 0.0f) ? d * (x + h.alpha) : d;
+    case DSB200_ACT_SELU:    return (x > 0.0f) ? d * h.lambda : d * (x + h.lambda * h.alpha);
+    default:                 return d;
+    }
+}
 __global__ void __launch_bounds__(256)
-stream_reduce_kernel(const float* __restrict__ partial, uint32_t splits, uint32_t M, uint32_t N, uint32_t ldc, float alpha, float beta, float* __restrict__ C)
+stream_reduce_kernel(const float* __restrict__ partial, uint32_t splits, uint32_t M, uint32_t N, uint32_t ldc, float alpha, float beta, float* __restrict__ C,
+                     const HadArgs h)
 {
     const size_t total = (size_t)M * N;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
@@ -500,6 +514,7 @@ stream_reduce_kernel(const float* __restrict__ partial, uint32_t splits, uint32_
         float* c = C + (size_t)m * ldc + n;
         float x = alpha * s;
         if (beta != 0.0f) x += beta * *c;
+        if (h.unit) x = gs_hadamard(h, __ldg(h.unit + (size_t)m * ldc + n), x);
         *c = x;
     }
 }
@@ -797,6 +812,37 @@ out_fwd_kernel(const FArgs f, const __grid_constant__ CUtensorMap mapHi, const _
     if (warp == F_MMA_WARP) tmem_dealloc(tmem, TMEM_COLS);
 }
 
+// the three derived copies of the last hidden layer's units X[rows][cols] in one launch: xlo[r][c] = lo(X) (B operand of the forward
+// pass), xtHi[c][r] = X, xtLo[c][r] = lo(X) (B operand of the weight gradient, pitch ldt)
+__global__ void __launch_bounds__(256)
+prep_x_kernel(const float* __restrict__ X, uint32_t rows, uint32_t cols, float* __restrict__ xlo, float* __restrict__ xtHi, float* __restrict__ xtLo, uint32_t ldt)
+{
+    __shared__ float tile[32][33];
+    const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+    const uint32_t tilesC = (cols + 31) / 32, tilesR = (ldt + 31) / 32;
+    for (uint32_t t = blockIdx.x; t < tilesC * tilesR; t += gridDim.x) {
+        const uint32_t r0 = (t / tilesC) * 32, c0 = (t % tilesC) * 32;
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t r = r0 + ty + 8 * i, c = c0 + tx;
+            const float x = (r < rows && c < cols) ? __ldg(X + (size_t)r * cols + c) : 0.0f;
+            tile[ty + 8 * i][tx] = x;
+            if (r < rows && c < cols) xlo[(size_t)r * cols + c] = __uint_as_float(lo_of(__float_as_uint(x)));
+        }
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; i++) {
+            const uint32_t c = c0 + ty + 8 * i, r = r0 + tx;
+            if (c < cols && r < ldt) {
+                const float x = tile[tx][ty + 8 * i];
+                xtHi[(size_t)c * ldt + r] = x;
+                xtLo[(size_t)c * ldt + r] = __uint_as_float(lo_of(__float_as_uint(x)));
+            }
+        }
+        __syncthreads();
+    }
+}
+
 // transposed target bitmap: bit (b % 32) of bitsT[c][b / 32] = output c is a non-zero target of batch row b (cleared by the caller)
 __global__ void __launch_bounds__(256)
 target_bitmap_t_kernel(const dsb200_params P, const dsb200_sparse S, uint32_t position, uint32_t batch, uint32_t width, uint32_t wordsB,
@@ -860,6 +906,16 @@ static int gs_reserve(dsb200_ctx* ctx, size_t bytes)
     return 0;
 }
 static inline size_t al256(size_t x) { return (x + 255) & ~(size_t)255; }
+static int prep_reserve(dsb200_ctx* ctx, dsb200_ctx::Prep& p, size_t bytes)
+{
+    p.valid = false;
+    if (bytes <= p.bytes) return 0;
+    if (p.buf) { DSB_CUDA_OK(cudaDeviceSynchronize()); DSB_CUDA_OK(cudaFree(p.buf)); p.buf = nullptr; p.bytes = 0; }
+    bytes += bytes / 8;
+    DSB_CUDA_OK(cudaMalloc(&p.buf, bytes));
+    p.bytes = bytes;
+    return 0;
+}
 
 bool gemm_stream_available() { return gs::encode_fn() != nullptr; }
 
@@ -875,11 +931,17 @@ int gemm_stream_dw(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, float al
     }
     const uint32_t ldt = up4(B);
     const size_t opBytes = al256((size_t)k * ldt * sizeof(float));
-    int rc = gs_reserve(ctx, 2 * opBytes);
-    if (rc) return rc;
-    float* xtHi = reinterpret_cast<float*>(ctx->dGsWs);
-    float* xtLo = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ctx->dGsWs) + opBytes);
-    {
+    float* xtHi; float* xtLo;
+    if (ctx->prepX.valid && ctx->prepX.key == X && ctx->prepX.a == B && ctx->prepX.b == k) {
+        // the forward pass of this step left X^T (hi | lo) behind (gemm_stream_out_fwd)
+        ctx->prepX.valid = false;
+        uint8_t* pb = reinterpret_cast<uint8_t*>(ctx->prepX.buf) + al256((size_t)B * k * sizeof(float));
+        xtHi = reinterpret_cast<float*>(pb); xtLo = reinterpret_cast<float*>(pb + opBytes);
+    } else {
+        int rc = gs_reserve(ctx, 2 * opBytes);
+        if (rc) return rc;
+        xtHi = reinterpret_cast<float*>(ctx->dGsWs);
+        xtLo = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ctx->dGsWs) + opBytes);
         const uint32_t tiles = ((k + 31) / 32) * ((ldt + 31) / 32);
         transpose_split_kernel<<<std::min<uint32_t>(tiles, (uint32_t)ctx->numSMs * 8), 256, 0, ctx->stream>>>(X, k, B, k, xtHi, xtLo, ldt);
         count_launch();
@@ -901,7 +963,7 @@ int gemm_stream_dw(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, float al
 
 // Dp[B][k] = beta * Dp + D[B][n] * W[k][n]^T            (M = B, N = k, K = n split; A = D read with k contiguous)
 int gemm_stream_dx(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, const float* D, uint32_t ldd, const float* W, uint32_t ldw, float beta,
-                   float* Dp, uint32_t ldp)
+                   float* Dp, uint32_t ldp, const float* hadUnit, int hadAct, float hadScale, float slope, float ealpha, float lambda)
 {
     using namespace gs;
     static bool attrSet = false;
@@ -928,18 +990,26 @@ int gemm_stream_dx(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, const fl
     const uint32_t per = (kTiles + splits - 1) / splits;
     splits = (kTiles + per - 1) / per;
     a.splits = splits; a.kPerSplit = per * BK;
-    // operand copies: lo always; hi only when W itself cannot be a tensor map (pitch not a multiple of 16 bytes)
+    // operand copies: lo always; hi only when W itself cannot be a tensor map (pitch not a multiple of 16 bytes).  Made here, or
+    // ahead of time on another stream by dsb200_gemm_dx_prepare (W does not change between the optimizer step and this call)
     const bool direct = tma_ok(W, ldw);
     const uint32_t ldc = up4(n);
     const size_t opBytes = al256((size_t)k * ldc * sizeof(float));
     const size_t partBytes = splits > 1 ? al256((size_t)splits * B * k * sizeof(float)) : 0;
-    int rc = gs_reserve(ctx, 2 * opBytes + partBytes);
+    const bool prepared = ctx->prepW.valid && ctx->prepW.key == W && ctx->prepW.a == k && ctx->prepW.b == n && ctx->prepW.c == ldw;
+    int rc = gs_reserve(ctx, (prepared ? 0 : 2 * opBytes) + partBytes);
     if (rc) return rc;
     uint8_t* ws = reinterpret_cast<uint8_t*>(ctx->dGsWs);
-    float* wLo = reinterpret_cast<float*>(ws);
-    float* wHi = direct ? nullptr : reinterpret_cast<float*>(ws + opBytes);
-    a.partial = splits > 1 ? reinterpret_cast<float*>(ws + 2 * opBytes) : nullptr;
-    {
+    float* wLo; float* wHi;
+    if (prepared) {
+        ctx->prepW.valid = false;
+        wLo = reinterpret_cast<float*>(ctx->prepW.buf);
+        wHi = direct ? nullptr : reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ctx->prepW.buf) + opBytes);
+        a.partial = splits > 1 ? reinterpret_cast<float*>(ws) : nullptr;
+    } else {
+        wLo = reinterpret_cast<float*>(ws);
+        wHi = direct ? nullptr : reinterpret_cast<float*>(ws + opBytes);
+        a.partial = splits > 1 ? reinterpret_cast<float*>(ws + 2 * opBytes) : nullptr;
         const size_t total = (size_t)k * ldc;
         const uint32_t blocks = (uint32_t)std::min<size_t>((total + 255) / 256, (size_t)ctx->numSMs * 16);
         split_pitch_kernel<<<blocks, 256, 0, ctx->stream>>>(W, ldw, k, n, wHi, wLo, ldc);
@@ -958,10 +1028,54 @@ int gemm_stream_dx(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, const fl
     if (splits > 1) {
         const size_t total = (size_t)B * k;
         const uint32_t blocks = (uint32_t)std::min<size_t>((total + 255) / 256, (size_t)ctx->numSMs * 8);
-        stream_reduce_kernel<<<blocks, 256, 0, ctx->stream>>>(a.partial, splits, B, k, ldp, 1.0f, beta, Dp);
+        HadArgs h{hadUnit, hadAct, hadScale, slope, ealpha, lambda};
+        stream_reduce_kernel<<<blocks, 256, 0, ctx->stream>>>(a.partial, splits, B, k, ldp, 1.0f, beta, Dp, h);
         DSB_CUDA_OK(cudaGetLastError());
         count_launch();
+    } else if (hadUnit) {
+        return dsb200_hadamard(ctx, hadAct, (uint64_t)B * k, hadScale, hadUnit, Dp, slope, ealpha, lambda);
     }
+    return 0;
+}
+
+// transposed target bitmap (+ row weights) of the batch at `position` into the context's prepared-operand buffer
+static int out_fwd_prepare_bits(dsb200_ctx* ctx, const dsb200_sparse* s, uint32_t position, uint32_t batch, uint32_t n)
+{
+    using namespace gs;
+    const uint32_t wordsB = (batch + 31) / 32;
+    const size_t bitsBytes = al256((size_t)n * wordsB * sizeof(uint32_t)), rowBytes = al256((size_t)batch * sizeof(float));
+    int rc = prep_reserve(ctx, ctx->prepBits, bitsBytes + rowBytes);
+    if (rc) return rc;
+    uint32_t* bitsT = reinterpret_cast<uint32_t*>(ctx->prepBits.buf);
+    float* rowW = s->dataWeight ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ctx->prepBits.buf) + bitsBytes) : nullptr;
+    DSB_CUDA_OK(cudaMemsetAsync(bitsT, 0, (size_t)n * wordsB * sizeof(uint32_t), ctx->stream));
+    target_bitmap_t_kernel<<<std::min<uint32_t>(batch, (uint32_t)ctx->numSMs * 8), 256, 0, ctx->stream>>>(ctx->params, *s, position, batch, n, wordsB, bitsT, rowW);
+    count_launch();
+    DSB_CUDA_OK(cudaGetLastError());
+    ctx->prepBits.key = s->sparseIndex; ctx->prepBits.a = position; ctx->prepBits.b = batch; ctx->prepBits.c = n; ctx->prepBits.valid = true;
+    return 0;
+}
+int gemm_stream_prepare_targets(dsb200_ctx* ctx, const dsb200_sparse* s, uint32_t position, uint32_t batch, uint32_t n)
+{
+    return out_fwd_prepare_bits(ctx, s, position, batch, n);
+}
+// hi / lo pitch-padded copies of W[k][n] for the input-delta kernel, ahead of the call
+int gemm_stream_prepare_dx(dsb200_ctx* ctx, uint32_t k, uint32_t n, const float* W, uint32_t ldw)
+{
+    using namespace gs;
+    const bool direct = tma_ok(W, ldw);
+    const uint32_t ldc = up4(n);
+    const size_t opBytes = al256((size_t)k * ldc * sizeof(float));
+    int rc = prep_reserve(ctx, ctx->prepW, 2 * opBytes);
+    if (rc) return rc;
+    float* wLo = reinterpret_cast<float*>(ctx->prepW.buf);
+    float* wHi = direct ? nullptr : reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ctx->prepW.buf) + opBytes);
+    const size_t total = (size_t)k * ldc;
+    const uint32_t blocks = (uint32_t)std::min<size_t>((total + 255) / 256, (size_t)ctx->numSMs * 16);
+    split_pitch_kernel<<<blocks, 256, 0, ctx->stream>>>(W, ldw, k, n, wHi, wLo, ldc);
+    count_launch();
+    DSB_CUDA_OK(cudaGetLastError());
+    ctx->prepW.key = W; ctx->prepW.a = k; ctx->prepW.b = n; ctx->prepW.c = ldw; ctx->prepW.valid = true;
     return 0;
 }
 
@@ -1000,24 +1114,32 @@ int gemm_stream_out_fwd(dsb200_ctx* ctx, const dsb200_sparse* s, int ef, uint32_
     f.wordsB = (batch + 31) / 32;
     const size_t bitsBytes = al256((size_t)n * f.wordsB * sizeof(uint32_t));
     const size_t rowBytes = al256((size_t)batch * sizeof(float));
-    const size_t loBytes = al256((size_t)batch * k * sizeof(float));
-    int rc = gs_reserve(ctx, bitsBytes + rowBytes + loBytes);
-    if (rc) return rc;
-    uint8_t* ws = reinterpret_cast<uint8_t*>(ctx->dGsWs);
-    uint32_t* bitsT = reinterpret_cast<uint32_t*>(ws);
-    float* rowW = s->dataWeight ? reinterpret_cast<float*>(ws + bitsBytes) : nullptr;
-    float* xLo = reinterpret_cast<float*>(ws + bitsBytes + rowBytes);
-    DSB_CUDA_OK(cudaMemsetAsync(bitsT, 0, (size_t)n * f.wordsB * sizeof(uint32_t), ctx->stream));
-    target_bitmap_t_kernel<<<std::min<uint32_t>(batch, (uint32_t)ctx->numSMs * 8), 256, 0, ctx->stream>>>(ctx->params, *s, position, batch, n, f.wordsB, bitsT, rowW);
-    count_launch();
+    const bool bitsReady = ctx->prepBits.valid && ctx->prepBits.key == s->sparseIndex && ctx->prepBits.a == position && ctx->prepBits.b == batch && ctx->prepBits.c == n;
+    if (!bitsReady) {
+        const int rc = out_fwd_prepare_bits(ctx, s, position, batch, n);
+        if (rc) return rc;
+    }
+    ctx->prepBits.valid = false;
+    uint32_t* bitsT = reinterpret_cast<uint32_t*>(ctx->prepBits.buf);
+    float* rowW = s->dataWeight ? reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(ctx->prepBits.buf) + bitsBytes) : nullptr;
+    // derived copies of X: lo for this kernel's B operand, X^T (hi | lo) for the weight gradient that follows in the backward pass
+    const uint32_t ldt = up4(batch);
+    const size_t loBytes = al256((size_t)batch * k * sizeof(float)), xtBytes = al256((size_t)k * ldt * sizeof(float));
     f.passes = (ctx->gemmMode == DSB200_GEMM_TF32) ? 1 : 3;
-    if (f.passes == 3) {
-        const size_t total = (size_t)batch * k;
-        split_pitch_kernel<<<(uint32_t)std::min<size_t>((total + 255) / 256, (size_t)ctx->numSMs * 8), 256, 0, ctx->stream>>>(X, k, batch, k, nullptr, xLo, k);
+    int rc = prep_reserve(ctx, ctx->prepX, loBytes + 2 * xtBytes);
+    if (rc) return rc;
+    float* xLo = reinterpret_cast<float*>(ctx->prepX.buf);
+    {
+        uint8_t* pb = reinterpret_cast<uint8_t*>(ctx->prepX.buf) + loBytes;
+        const uint32_t tiles = ((k + 31) / 32) * ((ldt + 31) / 32);
+        prep_x_kernel<<<std::min<uint32_t>(tiles, (uint32_t)ctx->numSMs * 8), 256, 0, ctx->stream>>>(X, batch, k, xLo, reinterpret_cast<float*>(pb),
+                                                                                                    reinterpret_cast<float*>(pb + xtBytes), ldt);
         count_launch();
+        ctx->prepX.key = X; ctx->prepX.a = batch; ctx->prepX.b = k; ctx->prepX.valid = true;
     }
     CUtensorMap mh, ml;
     if (!make_map(&mh, X, batch, k, k) || !make_map(&ml, xLo, batch, k, k)) return fail(ctx, DSB200_ESTATE, "gemm_stream_out_fwd: cuTensorMapEncodeTiled failed");
+    (void)rowBytes;
     f.bitsT = bitsT; f.rowW = rowW; f.acc = acc; f.colPartials = pColPartials;
     if (pNumPartials) *pNumPartials = f.groups * 2;
     f.zeroTarget = ctx->params.SMCE_zeroTarget; f.oneTarget = ctx->params.SMCE_oneTarget;

@@ -434,6 +434,12 @@ void NNLayer::BackPropagateFullyConnected(uint32_t position, uint32_t batch)
                     } else
                         in->_pDataSet->CalculateSparseTransposedWeightGradient(sgemm_alpha, sgemm_beta, in->_localStride, _localStride,
                                                                                GetDeltaBuffer(), w->_pbWeightGradient->_pDevData);
+                } else if (net->FusionEnabled() && net->_mode == Training && sgemm_beta == (NNFloat)0.0 && w->_sharingCount == 1 &&
+                           SmallDense(batch, in->_localStride, _localStride)) {
+                    // small dense layer: gradient + optimizer + bias update as ONE launch from NNWeight::UpdateWeights
+                    w->_bDeferredDenseGradient = true;
+                    w->_pDeferredX = in->GetUnitBuffer();
+                    w->_pDeferredDelta = GetDeltaBuffer();
                 } else {
                     getGpu().Check(dsb200_gemm_dw(ctx, batch, in->_localStride, _localStride, sgemm_alpha, in->GetUnitBuffer(), GetDeltaBuffer(),
                                                   sgemm_beta, w->_pbWeightGradient->_pDevData), "dsb200_gemm_dw");
@@ -445,8 +451,7 @@ void NNLayer::BackPropagateFullyConnected(uint32_t position, uint32_t batch)
                 // small dense layer below with this layer as its only consumer, no sparseness penalty in between: the input
                 // delta and its Hadamard product with f'(x) in one launch (E/NNLayer.cpp:2274 + 2137)
                 const bool fuse = net->FusionEnabled() && in->_kind == Hidden && in->_vOutgoingLayer.size() == 1 && sgemm_beta == (NNFloat)0.0 &&
-                                  !(in->_bSparse && net->_bSparsenessPenalty) && in->_deltaNorm <= (NNFloat)0.0 &&
-                                  (uint64_t)batch * in->_localStride * _localStride <= (1ull << 27);
+                                  !(in->_bSparse && net->_bSparsenessPenalty) && in->_deltaNorm <= (NNFloat)0.0;
                 if (fuse) {
                     getGpu().Check(dsb200_gemm_dx_hadamard(ctx, batch, in->_localStride, _localStride, GetDeltaBuffer(), w->_pbWeight->_pDevData,
                                                            (int)in->_activation, (NNFloat)1.0 / ((NNFloat)1.0 - in->_pDropout), in->GetUnitBuffer(),
@@ -474,8 +479,13 @@ void NNLayer::BackPropagateFullyConnected(uint32_t position, uint32_t batch)
             if (w->_bLocked) continue;
             const NNFloat sgemm_alpha = -(NNFloat)1.0 / (w->_sharingCount * (NNFloat)batch);
             const NNFloat sgemm_beta = (w->_updateCount == 0) ? (NNFloat)0.0 : (NNFloat)1.0;
-            getGpu().Check(dsb200_gemm_dw(ctx, batch, _stride, out->_localStride, sgemm_alpha, pX, out->GetDeltaBuffer(), sgemm_beta,
-                                          w->_pbWeightGradient->_pDevData), "dsb200_gemm_dw");
+            if (net->FusionEnabled() && net->_mode == Training && sgemm_beta == (NNFloat)0.0 && w->_sharingCount == 1 && SmallDense(batch, _stride, out->_localStride)) {
+                w->_bDeferredDenseGradient = true;                                // one launch in NNWeight::UpdateWeights; X(L) stays in its exchange slot
+                w->_pDeferredX = pX;
+                w->_pDeferredDelta = out->GetDeltaBuffer();
+            } else
+                getGpu().Check(dsb200_gemm_dw(ctx, batch, _stride, out->_localStride, sgemm_alpha, pX, out->GetDeltaBuffer(), sgemm_beta,
+                                              w->_pbWeightGradient->_pDevData), "dsb200_gemm_dw");
             w->_updateCount++;
         }
         if (_kind != Input) {

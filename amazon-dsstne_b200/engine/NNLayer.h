@@ -107,6 +107,8 @@ private:
     NNFloat* Gather(uint32_t batch, uint32_t stride, NNFloat* pBuffer, uint32_t localStride, ExchangeSlot slot);
     void ClearUpdates();
     bool FusedOutputEligible(ErrorFunction ef) const;
+    // a dense weight small enough for the one-launch gradient + update kernel (dsb200_dense_update)
+    static bool SmallDense(uint64_t batch, uint64_t k, uint64_t n) { return batch * k * n <= (1ull << 27) && batch <= 4096; }
     void MaterializeUnits();                              // apply the activation now if the fused training pass skipped storing it
     NNFloat* GetIncomingUnitBuffer() { return _pbUnit ? _pbUnit->_pDevData : NULL; }
     NNFloat* GetUnitBuffer() { return _pbUnit ? _pbUnit->_pDevData : NULL; }

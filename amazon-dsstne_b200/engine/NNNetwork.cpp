@@ -43,7 +43,7 @@ NNNetwork::NNNetwork(NNNetworkDescriptor& d, uint32_t batch)
       _SMCE_oneTarget(d._SMCE_oneTarget), _SMCE_zeroTarget(d._SMCE_zeroTarget), _SMCE_oneScale(d._SMCE_oneScale),
       _SMCE_zeroScale(d._SMCE_zeroScale), _bShuffleIndices(d._bShuffleIndices), _shuffleIndices(0), _shuffleEpoch(0),
       _checkpoint_name(d._checkpoint_name), _checkpoint_interval(d._checkpoint_interval), _checkpoint_epochs(0), _bDirty(true),
-      _bClearVelocity(true), _scratchBufferSize(0), _maxStride(0), _errorEvent(NULL), _sideStream(NULL), _forkEvent(NULL), _joinEvent(NULL), _verbose(false), _bRegularizationLaunched(false), _bFusion(true),
+      _bClearVelocity(true), _scratchBufferSize(0), _maxStride(0), _errorEvent(NULL), _sideStream(NULL), _forkEvent(NULL), _joinEvent(NULL), _prepEvent(NULL), _verbose(false), _bRegularizationLaunched(false), _bFusion(true),
       _movingAverage(0.0f), _brakeSteps(0), _initSteps(100)
 {
     if (!getGpu()._ctx) throw DsbEngineError("NNNetwork: getGpu().Startup() has not been called (no GPU context; there is no CPU fallback)");
@@ -71,6 +71,7 @@ NNNetwork::NNNetwork(NNNetworkDescriptor& d, uint32_t batch)
     RTERROR(cudaEventCreateWithFlags(&_errorEvent, cudaEventDisableTiming), "NNNetwork: cudaEventCreate");
     RTERROR(cudaEventCreateWithFlags(&_forkEvent, cudaEventDisableTiming), "NNNetwork: cudaEventCreate");
     RTERROR(cudaEventCreateWithFlags(&_joinEvent, cudaEventDisableTiming), "NNNetwork: cudaEventCreate");
+    RTERROR(cudaEventCreateWithFlags(&_prepEvent, cudaEventDisableTiming), "NNNetwork: cudaEventCreate");
     RTERROR(cudaStreamCreateWithFlags(&_sideStream, cudaStreamNonBlocking), "NNNetwork: cudaStreamCreate");
 }
 
@@ -82,6 +83,7 @@ NNNetwork::~NNNetwork()
     if (_errorEvent) cudaEventDestroy(_errorEvent);
     if (_forkEvent) cudaEventDestroy(_forkEvent);
     if (_joinEvent) cudaEventDestroy(_joinEvent);
+    if (_prepEvent) cudaEventDestroy(_prepEvent);
     if (_sideStream) cudaStreamDestroy(_sideStream);
 }
 
@@ -388,7 +390,7 @@ void NNNetwork::ShuffleIndices()
 
 void NNNetwork::ClearUpdates()
 {
-    for (auto w : _vWeight) { w->_updateCount = 0; w->_bDeferredSparseGradient = false; w->_nBiasPartials = 0; }
+    for (auto w : _vWeight) { w->_updateCount = 0; w->_bDeferredSparseGradient = false; w->_bDeferredDenseGradient = false; w->_nBiasPartials = 0; }
     for (auto l : _vLayer) l->ClearUpdates();
 }
 
@@ -424,8 +426,45 @@ void NNNetwork::PredictTrainingBatch(uint32_t layers)
     if (_bDirty) RefreshState();
     uint32_t batch = _batch;
     if (_position + batch > _examples) batch = _examples - _position;
-    LoadBatch();
+    if (!_bBatchPrepared) LoadBatch();                    // TrainStep has it running on the side stream already
     for (auto l : _vFPOrder) l->ForwardPropagate(_position, batch, true);
+}
+
+// Everything of a training step that depends only on the data batch or on the weights as the last update left them runs on the
+// side stream BESIDE the forward pass: the transposed sparse matrix of the input batch (consumed by the sparse weight gradient at
+// the end of the step), the target bitmap of the fused output-layer forward, the hi / lo copies of the output weights for the
+// input-delta kernel, and the regularisation error.  _prepEvent marks the first three, _joinEvent the last.
+void NNNetwork::LaunchBatchPreparation(NNFloat lambda, NNFloat lambda1)
+{
+    uint32_t batch = _batch;
+    if (_position + batch > _examples) batch = _examples - _position;
+    cudaStream_t s = getGpu().GetStream();
+    dsb200_ctx* ctx = getGpu()._ctx;
+    RTERROR(cudaEventRecord(_forkEvent, s), "LaunchBatchPreparation fork");
+    RTERROR(cudaStreamWaitEvent(_sideStream, _forkEvent, 0), "LaunchBatchPreparation fork wait");
+    getGpu().Check(dsb200_ctx_set_stream(ctx, _sideStream), "dsb200_ctx_set_stream");
+    LoadBatch();
+    for (auto l : _vOutputLayer) {
+        if (!getGpu()._bFuseOutputGemm || !l->FusedOutputEligible(_errorFunction) || l->_vIncomingLayer.size() != 1) continue;
+        if (l->_activation != Sigmoid || !l->_pDataSet || !(l->_pDataSet->_attributes & NNDataSetEnums::Boolean)) continue;
+        dsb200_sparse v = l->_pDataSet->View();
+        getGpu().Check(dsb200_gemm_fwd_output_prepare(ctx, &v, _position, batch, l->_localStride), "dsb200_gemm_fwd_output_prepare");
+        NNLayer* in = l->_vIncomingLayer[0];
+        NNWeight* w = l->_vIncomingWeight[0];
+        if (in->_kind == NNLayer::Kind::Hidden && (getGpu()._numprocs == 1 || w->_bOutgoingLarger))
+            getGpu().Check(dsb200_gemm_dx_prepare(ctx, batch, in->_stride, l->_localStride, w->_pbWeight->_pDevData), "dsb200_gemm_dx_prepare");
+    }
+    RTERROR(cudaEventRecord(_prepEvent, _sideStream), "LaunchBatchPreparation prep event");
+    const bool any = lambda != (NNFloat)0.0 || lambda1 != (NNFloat)0.0;
+    unsigned long long* acc = _pbErrorAccumulator->_pDevData;
+    if (any)
+        for (auto w : _vWeight)
+            if (!w->_bShared)
+                getGpu().Check(dsb200_regularization_error_async(ctx, lambda, lambda1, w->_pbWeight->_pDevData, w->_localSize, acc + 1),
+                               "dsb200_regularization_error_async");
+    getGpu().Check(dsb200_ctx_set_stream(ctx, s), "dsb200_ctx_set_stream");
+    RTERROR(cudaEventRecord(_joinEvent, _sideStream), "LaunchBatchPreparation join");
+    _bBatchPrepared = true;
 }
 
 NNFloat NNNetwork::ReadErrorAccumulator()
@@ -448,6 +487,7 @@ void NNNetwork::LaunchError(NNFloat lambda, NNFloat lambda1)
         RTERROR(cudaMemsetAsync(acc, 0, 2 * sizeof(unsigned long long), s), "LaunchError memset");
         LaunchRegularization(lambda, lambda1, false);
     }
+    if (_bRegularizationLaunched) RTERROR(cudaStreamWaitEvent(s, _prepEvent, 0), "LaunchError prep wait");   // target bitmap, transposed matrix, W copies
     _bRegularizationLaunched = false;
     for (auto l : _vOutputLayer) l->CalculateErrorAsync(_position, batch, _errorFunction, acc);
     RTERROR(cudaStreamWaitEvent(s, _joinEvent, 0), "LaunchError join");
@@ -526,12 +566,13 @@ float NNNetwork::TrainStep(uint32_t position, NNFloat alpha, NNFloat lambda, NNF
     if (_bDirty) RefreshState();
     SetPosition(position);
     ClearUpdates();
-    if (_bFusion) {                                  // regularisation error on the side stream while the forward pass runs
+    if (_bFusion) {                                  // batch preparation + regularisation error on the side stream while the forward pass runs
         RTERROR(cudaMemsetAsync(_pbErrorAccumulator->_pDevData, 0, 2 * sizeof(unsigned long long), getGpu().GetStream()), "TrainStep memset");
-        LaunchRegularization(lambda, lambda1, true);
+        LaunchBatchPreparation(lambda, lambda1);
         _bRegularizationLaunched = true;
     }
     PredictTrainingBatch();
+    _bBatchPrepared = false;
     LaunchError(lambda, lambda1);                    // loss (+ output delta) kernels, join, and the async read-back
     BackPropagate();                                 // queued behind them; does not depend on the host seeing the loss
     RTERROR(cudaEventSynchronize(_errorEvent), "TrainStep event sync");

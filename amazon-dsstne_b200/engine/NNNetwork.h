@@ -67,7 +67,8 @@ private:
     unique_ptr<GpuBuffer<unsigned long long>> _pbErrorAccumulator;   // device fixed-point loss + pinned shadow
     cudaEvent_t             _errorEvent;
     cudaStream_t            _sideStream;                  // regularisation error runs here, beside the forward pass
-    cudaEvent_t             _forkEvent, _joinEvent;
+    cudaEvent_t             _forkEvent, _joinEvent, _prepEvent;
+    bool                    _bBatchPrepared = false;      // TrainStep launched LoadBatch on the side stream: PredictTrainingBatch must not repeat it
     bool                    _verbose;
     bool                    _bRegularizationLaunched;     // LaunchError finds the regularisation kernels already in flight
     bool                    _bFusion;                     // B200 fusions on (default) / off (kernel-by-kernel, like the reference)
@@ -149,6 +150,7 @@ private:
     void ShuffleIndices();
     tuple<NNFloat, NNFloat> CalculateError(NNFloat lambda, NNFloat lambda1);
     void LaunchError(NNFloat lambda, NNFloat lambda1);     // asynchronous part of CalculateError
+    void LaunchBatchPreparation(NNFloat lambda, NNFloat lambda1);
     void LaunchRegularization(NNFloat lambda, NNFloat lambda1, bool fork);
     void ClearUpdates();
     void BackPropagate();

@@ -163,6 +163,15 @@ void NNWeight::UpdateWeights(TrainingMode mode, uint32_t batch, NNFloat alpha, N
     dsb200_ctx* ctx = getGpu()._ctx;
     NNFloat* v = _pbWeightVelocity ? _pbWeightVelocity->_pDevData : NULL;
     NNFloat* gv = _pbWeightGradientVelocity ? _pbWeightGradientVelocity->_pDevData : NULL;
+    if (_bDeferredDenseGradient) {
+        // small dense layer: X^T * delta, the optimizer rule and the bias update in one launch (csrc/dense_small.cu); dW is never written
+        _bDeferredDenseGradient = false;
+        const NNFloat galpha = -(NNFloat)1.0 / (_sharingCount * (NNFloat)batch);                // E/NNLayer.cpp:2213
+        getGpu().Check(dsb200_dense_update(ctx, (int)mode, batch, (uint32_t)_height, (uint32_t)_width, galpha, _pDeferredX, _pDeferredDelta, alpha, lambda, lambda1,
+                                           mu, mu1, t, v, gv, _pbWeight->_pDevData, _pbBiasVelocity ? _pbBiasVelocity->_pDevData : NULL,
+                                           _pbBiasGradientVelocity ? _pbBiasGradientVelocity->_pDevData : NULL, _pbBias->_pDevData), "dsb200_dense_update");
+        return;
+    }
     if (_bDeferredSparseGradient) {
         // sparse input gradient + optimizer rule in one kernel; same arithmetic as the two calls below
         const NNFloat galpha = -(NNFloat)1.0 / (_sharingCount * (NNFloat)batch);                // E/NNLayer.cpp:2213
@@ -244,8 +253,9 @@ bool NNWeight::GetGradients(vector<NNFloat>& vGradient)
 {
     // with fusion on, the gradient of a sparse-input weight is consumed inside dsb200_sparse_wgrad_update and never written to
     // _pbWeightGradient: returning the buffer would hand out stale data
-    if (getGpu()._pNetwork && getGpu()._pNetwork->FusionEnabled() && _inputLayer._kind == NNLayer::Kind::Input && _inputLayer._bFastSparse)
-        throw DsbEngineError("NNWeight::GetGradients: the gradient of sparse-input weight " + _inputLayer._name + " -> " + _outputLayer._name +
+    if (getGpu()._pNetwork && getGpu()._pNetwork->FusionEnabled() &&
+        ((_inputLayer._kind == NNLayer::Kind::Input && _inputLayer._bFastSparse) || NNLayer::SmallDense(_inputLayer._batch, _height, _width)))
+        throw DsbEngineError("NNWeight::GetGradients: the gradient of weight " + _inputLayer._name + " -> " + _outputLayer._name +
                              " is fused into the optimizer step and never materialised; call NNNetwork::SetFusion(false) first");
     vGradient.resize(_localSize);
     _pbWeightGradient->Download(vGradient.data());

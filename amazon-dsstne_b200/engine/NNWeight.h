@@ -28,6 +28,8 @@ private:
     NNFloat     _norm;
     bool        _bDeferredSparseGradient;   // gradient will be produced inside the fused update
     NNFloat*    _pDeferredDelta;            // delta [batch][outputStride] the fused update reads
+    bool        _bDeferredDenseGradient = false;   // small dense layer: gradient + optimizer + bias update run as ONE kernel in UpdateWeights
+    const NNFloat* _pDeferredX = NULL;             // its input units [batch][_height]
     uint32_t    _nBiasPartials;             // > 0: the fused output-layer forward pass left this many rows of column sums of delta
     unique_ptr<GpuBuffer<NNFloat>> _pbBiasPartials;
     vector<NNFloat> _vWeight, _vBias;

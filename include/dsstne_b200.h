@@ -212,6 +212,12 @@ int dsb200_gemm_fwd_output_pass(dsb200_ctx*, const dsb200_sparse* s, int errorFu
                                 uint32_t k, uint32_t n, const float* A, const float* W, const float* pBias, float* pUnitOut, float* pDelta,
                                 unsigned long long* pDevAccumulator, float* pColumnSumPartials, uint32_t* pNumPartials);
 
+/* optional hints for the two calls above / below: build ahead of time -- typically on another stream, next to the forward pass --
+ * what depends only on the data batch (target bitmap of dsb200_gemm_fwd_output_pass) or only on the weights (hi / lo copies of W
+ * of dsb200_gemm_dx / dsb200_gemm_dx_hadamard).  One-shot; a call without a matching hint prepares its own operands.            */
+int dsb200_gemm_fwd_output_prepare(dsb200_ctx*, const dsb200_sparse* s, uint32_t position, uint32_t batch, uint32_t n);
+int dsb200_gemm_dx_prepare(dsb200_ctx*, uint32_t B, uint32_t k, uint32_t n, const float* W);
+
 /* ------------------------------------------------------------------ a10
  * kCalculateSparsenessPenalty / kCalculateHadamardProduct, E/kernels.h:202,205            */
 int dsb200_sparseness_penalty(dsb200_ctx*, uint32_t batch, uint32_t stride, const float* pUnit, float* pDelta,
@@ -248,6 +254,12 @@ int dsb200_update_biases(dsb200_ctx*, int mode, float alpha, float mu, float mu1
  * gbar[c] = sum_p pPartials[p][c] / batch, summed in a fixed order                                                         */
 int dsb200_update_biases_partials(dsb200_ctx*, int mode, float alpha, float mu, float mu1, float t, uint32_t batch, uint32_t width,
                                   const float* pPartials, uint32_t nPartials, float* pBiasVelocity, float* pBiasGradientVelocity, float* pBias);
+/* small dense layer: cublasSgemm weight gradient (E/NNLayer.cpp:2223, beta = 0) + k*UpdateWeights + k*UpdateBiases
+ * (E/NNWeight.cpp:729-794) in ONE launch -- g = galpha * X[B][k]^T * D[B][n] is applied to W[k][n] and never written, the bias
+ * rule runs on the column means of D (pBias NULL = weights only).  Exact fp32; B <= 4,096 (csrc/dense_small.cu).          */
+int dsb200_dense_update(dsb200_ctx*, int mode, uint32_t B, uint32_t k, uint32_t n, float galpha, const float* X, const float* D,
+                        float alpha, float lambda, float lambda1, float mu, float mu1, float t, float* pWeightVelocity,
+                        float* pWeightGradientVelocity, float* pWeight, float* pBiasVelocity, float* pBiasGradientVelocity, float* pBias);
 int dsb200_regularization_error(dsb200_ctx*, float lambda, float lambda1, const float* pWeight, uint64_t size,
                                 float* pErrorOut);            /* synchronous, by value     */
 /* asynchronous variant: adds the fixed-point (2^30) value into *pDevAccumulator (device u64) */

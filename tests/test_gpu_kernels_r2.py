@@ -195,3 +195,40 @@ def test_topk_config5_shape_row_subset(ctx, orc, dsb):
         np.testing.assert_array_equal(u32(ov[r]), ref_v[0])
     del scores
     torch.cuda.empty_cache()
+
+
+# ------------------------------------------------------------------ small dense layer: gradient + optimizer + bias in one launch
+@pytest.mark.parametrize("mode", range(7), ids=["SGD", "Momentum", "AdaGrad", "Nesterov", "RMSProp", "AdaDelta", "Adam"])
+@pytest.mark.parametrize("B,k,n", [(1024, 128, 128), (256, 100, 37), (1000, 64, 200)])
+def test_dense_update_equals_the_three_calls(ctx, dsb, mode, B, k, n):
+    """dsb200_dense_update against dsb200_gemm_dw (fp32) + dsb200_update_weights + dsb200_update_biases on the same inputs"""
+    import torch
+    g = torch.Generator(device="cuda").manual_seed(100 * mode + B)
+    X = torch.rand(B, k, device="cuda", generator=g)
+    D = torch.randn(B, n, device="cuda", generator=g) * 0.1
+    W0 = torch.randn(k, n, device="cuda", generator=g) * 0.05
+    b0 = torch.randn(n, device="cuda", generator=g) * 0.1
+    V0 = torch.rand(k, n, device="cuda", generator=g) * 0.01
+    GV0 = torch.rand(k, n, device="cuda", generator=g) * 0.01 + 1e-3
+    bV0 = torch.rand(n, device="cuda", generator=g) * 0.01
+    bGV0 = torch.rand(n, device="cuda", generator=g) * 0.01 + 1e-3
+    hp = dict(alpha=0.05, lam=1e-3, lam1=1e-4, mu=0.9, mu1=0.999, t=3.0)
+    galpha = -1.0 / B
+    # reference: the three calls
+    Wr, br, Vr, GVr, bVr, bGVr = W0.clone(), b0.clone(), V0.clone(), GV0.clone(), bV0.clone(), bGV0.clone()
+    G = torch.zeros(k, n, device="cuda")
+    ctx.set_option("gemm_mode", 0)
+    ctx.gemm_dw(X, D, G, galpha)
+    ctx.update_weights(mode, hp["alpha"], hp["lam"], hp["lam1"], hp["mu"], hp["mu1"], hp["t"], Vr, G, GVr, Wr)
+    ctx.update_biases(mode, hp["alpha"], hp["mu"], hp["mu1"], hp["t"], D, bVr, bGVr, br)
+    # one launch
+    W, b, V, GV, bV, bGV = W0.clone(), b0.clone(), V0.clone(), GV0.clone(), bV0.clone(), bGV0.clone()
+    ctx.dense_update(mode, galpha, X, D, hp["alpha"], hp["lam"], hp["lam1"], hp["mu"], hp["mu1"], hp["t"], V, GV, W, bV, bGV, b)
+    ctx.sync()
+    tol = 2e-5 if mode in (dsb.ADAGRAD, dsb.RMSPROP, dsb.ADADELTA, dsb.ADAM) else TOL     # rsqrt of a sum of squares amplifies the GEMM rounding
+    assert rel_err(host(W), host(Wr)) < tol
+    assert rel_err(host(b), host(br)) < tol
+    if mode != dsb.SGD:
+        assert rel_err(host(V), host(Vr)) < tol and rel_err(host(bV), host(bVr)) < tol
+    if mode in (dsb.ADADELTA, dsb.ADAM):
+        assert rel_err(host(GV), host(GVr)) < tol and rel_err(host(bGV), host(bGVr)) < tol
