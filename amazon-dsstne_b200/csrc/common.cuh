@@ -57,6 +57,11 @@ struct dsb200_ctx {
     size_t         gemmWsCap   = 0;               // in floats
     uint32_t*      dHeavy      = nullptr;         // sparse gradient: [0] heavy-column count, [1..] heavy-column list
     size_t         heavyCap    = 0;
+    void*          dHeavy3     = nullptr;         // unified sparse gradient: zeroed int64 accumulators, item list, slots, arrival counters
+    size_t         heavy3Bytes = 0;
+    uint32_t       heavySlots = 0, heavyN = 0, heavyM = 0;   // layout the zeroed accumulators of the unified scheme were laid out for
+    int            wgradTwoKernel = 0;            // option "wgrad_two_kernel": round 1's light + heavy kernel pair instead of the unified kernel
+    uint32_t       wgradMaxEntries = 1u << 20;    // option "wgrad_max_entries": capacity of the transposed matrix the gradient kernels are called with
     int            wgradTileKernel = 0;           // option "wgrad_tile_kernel": force the one-kernel tile scheme
     int            zStagedKernel = 0;             // option "z_staged_kernel": force the TMA-staged CTA kernel for sparse Z
     int            outputTileKernel = 0;          // option "output_tile_kernel": force the two-phase tile kernel in dsb200_output_pass

@@ -91,6 +91,7 @@ int dsb200_ctx_destroy(dsb200_ctx* ctx)
     cudaFree(ctx->dPartials);
     cudaFree(ctx->dGemmWs);
     cudaFree(ctx->dHeavy);
+    cudaFree(ctx->dHeavy3);
     cudaFree(ctx->dGsWs);
     cudaFree(ctx->prepBits.buf); cudaFree(ctx->prepW.buf); cudaFree(ctx->prepX.buf);
     delete ctx;
@@ -151,6 +152,8 @@ int dsb200_ctx_set_option(dsb200_ctx* ctx, const char* name, int value)
     if (!strcmp(name, "gemm_tc_min_work")) { ctx->gemmTcMinWork = value; return 0; }
     if (!strcmp(name, "gemm_debug")) { ctx->gemmDebug = value; return 0; }
     if (!strcmp(name, "gemm_stream")) { ctx->gemmStream = value; return 0; }
+    if (!strcmp(name, "wgrad_two_kernel")) { ctx->wgradTwoKernel = value; return 0; }
+    if (!strcmp(name, "wgrad_max_entries")) { ctx->wgradMaxEntries = (uint32_t)value; return 0; }
     return dsb::fail(ctx, DSB200_EINVAL, "unknown option");
 }
 
@@ -163,6 +166,8 @@ int dsb200_ctx_sync(dsb200_ctx* ctx)
         *ctx->dStatus = 0;
         if (st == DSB200_STATUS_Z_WORKSPACE)
             return dsb::fail(ctx, DSB200_ESTATE, "sparse_z: split-row workspace too small, call dsb200_ctx_reserve");
+        if (st & DSB200_STATUS_G_CAPACITY)
+            return dsb::fail(ctx, DSB200_ESTATE, "sparse_wgrad: the batch holds more entries than option wgrad_max_entries allows");
         if (st == DSB200_STATUS_T_OVERFLOW)
             return dsb::fail(ctx, DSB200_ESTATE, "sparse_transpose: a column overran its capacity slot");
         return dsb::fail(ctx, DSB200_ESTATE, "device status");

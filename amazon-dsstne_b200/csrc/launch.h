@@ -4,6 +4,7 @@
 
 #define DSB200_STATUS_Z_WORKSPACE 1u   // sparse-Z split-row workspace too small (dsb200_ctx_reserve)
 #define DSB200_STATUS_T_OVERFLOW  2u   // transposed column overran its capacity slot
+#define DSB200_STATUS_G_CAPACITY  4u   // sparse gradient: more heavy-column work items than option "wgrad_max_entries" allows
 
 namespace dsb {
 void count_launch(uint64_t n = 1);

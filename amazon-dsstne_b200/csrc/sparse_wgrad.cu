@@ -440,6 +440,220 @@ static int launch_wgrad2(dsb200_ctx* ctx, const GArgs& a)
     return 0;
 }
 
+// ---------------------------------------------------------------- unified scheme (n % 128 == 0), round 2
+// Round 1's pair above ran the light columns (30 us on BASELINE config 2) and then the heavy ones (21 us) although the two sets touch
+// disjoint rows, and the light kernel spilled its look-ahead registers.  Here both populations run in ONE grid:
+//   wgrad_classify_kernel   one pass over the column ranges: every column with more than 32 entries is cut into items of 32 entries
+//                           (column, first entry) and gets a slot in a zeroed int64 accumulator [slot][n]
+//   sparse_wgrad_unified    every warp first takes heavy items (list index = warp id, + warps in the grid, ...): gathers its <= 32
+//                           delta rows, adds its int64 partial sums into the column's accumulator with 64-bit atomics (exact: the
+//                           result does not depend on their order) and counts itself in; the LAST item of a column reads the totals
+//                           back, finishes the row (gradient or fused optimizer rule) and re-zeroes the slot.  Then the warp walks its
+//                           share of the light columns (<= 32 entries: one index per lane); the row it updates is requested first
+//                           (HBM, the longest latency), and the gathers run in exact-count batches -- round-2 ncu of the first version:
+//                           380 warp instructions per column at ~5 entries per column, most of them predicated-off slots of a
+//                           padded batch of 7, issue slots 40 % busy: the kernel was instruction bound.
+// A variant with one QUARTER-warp per column (four columns per warp instruction) was measured at 64 us against 36 us and dropped.
+struct UArgs {
+    uint32_t* items;            // [2 * i] = column, [2 * i + 1] = first entry
+    uint32_t* itemCount;        // [0] items, [1] heavy columns
+    uint32_t* slotOf;           // [m] accumulator slot of a heavy column
+    uint32_t* arrived;          // [slots] items of the column finished so far (zero between calls)
+    long long* acc;             // [slots][n] (zero between calls)
+    uint32_t maxItems, maxSlots;
+    uint32_t* status;           // sticky device status word of the context
+};
+
+__global__ void __launch_bounds__(256)
+wgrad_classify_kernel(uint32_t m, const uint32_t* __restrict__ tStart, const uint32_t* __restrict__ tEnd, const UArgs u)
+{
+    for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < m; c += gridDim.x * blockDim.x) {
+        const uint32_t s = __ldg(tStart + c), e = __ldg(tEnd + c);
+        if (e - s <= kHeavy2) continue;
+        const uint32_t n = (e - s + 31) / 32;
+        const uint32_t slot = atomicAdd(u.itemCount + 1, 1u);
+        const uint32_t first = atomicAdd(u.itemCount, n);
+        if (slot >= u.maxSlots || first + n > u.maxItems) { atomicOr(u.status, DSB200_STATUS_G_CAPACITY); continue; }   // reported by dsb200_ctx_sync
+        u.slotOf[c] = slot;
+        for (uint32_t i = 0; i < n; i++) { u.items[2 * (first + i)] = c; u.items[2 * (first + i) + 1] = s + 32 * i; }
+    }
+}
+
+// sum of <= 32 entries whose delta-row indices sit one per lane: full batches of 8 gathers, then the remainder with EXACT counts
+// (cnt is warp-uniform: the switch is a jump, not predication)
+template <bool ANALOG>
+__device__ __forceinline__ void gather32(const GArgs& a, const float* dcol, uint32_t cnt, uint32_t myRow, float myVal, long long (&acc)[4])
+{
+    auto ld = [&](uint32_t j, float4& x, float& tv) {
+        const uint32_t row = __shfl_sync(0xffffffffu, myRow, j);
+        if (ANALOG) tv = __shfl_sync(0xffffffffu, myVal, j);
+        x = ldg_nc_f4(reinterpret_cast<const float4*>(dcol + (size_t)row * a.n));
+    };
+    auto add = [&](float4 x, float tv) {
+        if (ANALOG) { x.x *= tv; x.y *= tv; x.z *= tv; x.w *= tv; }
+        acc[0] += fix30(x.x); acc[1] += fix30(x.y); acc[2] += fix30(x.z); acc[3] += fix30(x.w);
+    };
+    uint32_t j = 0;
+    for (; j + kGUnroll <= cnt; j += kGUnroll) {
+        float4 x[kGUnroll]; float tv[kGUnroll];
+#pragma unroll
+        for (int q = 0; q < kGUnroll; q++) { tv[q] = 1.0f; ld(j + q, x[q], tv[q]); }
+#pragma unroll
+        for (int q = 0; q < kGUnroll; q++) add(x[q], tv[q]);
+    }
+    float4 x0, x1, x2, x3; float t0 = 1.f, t1 = 1.f, t2 = 1.f, t3 = 1.f;
+    uint32_t rem = cnt - j;
+    if (rem >= 4) { ld(j, x0, t0); ld(j + 1, x1, t1); ld(j + 2, x2, t2); ld(j + 3, x3, t3); add(x0, t0); add(x1, t1); add(x2, t2); add(x3, t3); j += 4; rem -= 4; }
+    switch (rem) {
+    case 3: ld(j, x0, t0); ld(j + 1, x1, t1); ld(j + 2, x2, t2); add(x0, t0); add(x1, t1); add(x2, t2); break;
+    case 2: ld(j, x0, t0); ld(j + 1, x1, t1); add(x0, t0); add(x1, t1); break;
+    case 1: ld(j, x0, t0); add(x0, t0); break;
+    default: break;
+    }
+}
+
+struct RowRegs { float4 w, v, g; };
+template <int FUSED_MODE>
+__device__ __forceinline__ void load_row(const GArgs& a, size_t off, RowRegs& r)
+{
+    constexpr int M = FUSED_MODE < 0 ? 0 : FUSED_MODE;
+    r.w = make_float4(0, 0, 0, 0); r.v = r.w; r.g = r.w;
+    if (FUSED_MODE >= 0) {
+        r.w = *reinterpret_cast<const float4*>(a.w + off);
+        if (opt_uses_v(M))  r.v = *reinterpret_cast<const float4*>(a.v + off);
+        if (opt_uses_gv(M)) r.g = *reinterpret_cast<const float4*>(a.gv + off);
+    } else if (a.beta != 0.0f) r.w = *reinterpret_cast<const float4*>(a.dW + off);
+}
+template <int FUSED_MODE>
+__device__ __forceinline__ void finish_row_regs(const GArgs& a, size_t off, RowRegs& r, const long long (&acc)[4])
+{
+    constexpr int M = FUSED_MODE < 0 ? 0 : FUSED_MODE;
+    float g[4];
+#pragma unroll
+    for (int v = 0; v < 4; v++) g[v] = a.alpha * (__ll2float_rn(acc[v]) * 9.31322574615478515625e-10f);
+    if (FUSED_MODE < 0) {
+        float4 out = make_float4(g[0], g[1], g[2], g[3]);
+        if (a.beta != 0.0f) { out.x += a.beta * r.w.x; out.y += a.beta * r.w.y; out.z += a.beta * r.w.z; out.w += a.beta * r.w.w; }
+        *reinterpret_cast<float4*>(a.dW + off) = out;
+    } else {
+        r.w.x = opt_weight<M>(a.opt, g[0], r.w.x, r.v.x, r.g.x);
+        r.w.y = opt_weight<M>(a.opt, g[1], r.w.y, r.v.y, r.g.y);
+        r.w.z = opt_weight<M>(a.opt, g[2], r.w.z, r.v.z, r.g.z);
+        r.w.w = opt_weight<M>(a.opt, g[3], r.w.w, r.v.w, r.g.w);
+        *reinterpret_cast<float4*>(a.w + off) = r.w;
+        if (opt_uses_v(M))  *reinterpret_cast<float4*>(a.v + off) = r.v;
+        if (opt_uses_gv(M)) *reinterpret_cast<float4*>(a.gv + off) = r.g;
+    }
+}
+
+template <bool ANALOG, int FUSED_MODE>
+__global__ void __launch_bounds__(kGThreads, 2)
+sparse_wgrad_unified_kernel(const GArgs a, const UArgs u)
+{
+    const uint32_t lane = threadIdx.x & 31;
+    const uint32_t gw = (blockIdx.x * kGThreads + threadIdx.x) >> 5, nw = (gridDim.x * kGThreads) >> 5;
+    // ---- heavy columns, 32 entries per item
+    const uint32_t nItems = min(*u.itemCount, u.maxItems);
+    for (uint32_t it = gw; it < nItems; it += nw) {
+        const uint32_t c = __ldg(u.items + 2 * it), e0 = __ldg(u.items + 2 * it + 1);
+        const uint32_t s = __ldg(a.tStart + c), e = __ldg(a.tEnd + c);
+        const uint32_t cnt = min(32u, e - e0), slot = __ldg(u.slotOf + c), nItemsCol = (e - s + 31) / 32;
+        uint32_t myRow = 0; float myVal = 1.0f;
+        if (lane < cnt) { myRow = __ldg(a.tIndex + e0 + lane); if (ANALOG) myVal = __ldg(a.tData + e0 + lane); }
+        long long* accRow = u.acc + (size_t)slot * a.n;
+        for (uint32_t col = lane * 4; col < a.n; col += 128) {
+            long long acc[4] = {0, 0, 0, 0};
+            gather32<ANALOG>(a, a.delta + col, cnt, myRow, myVal, acc);
+#pragma unroll
+            for (int v = 0; v < 4; v++) atomicAdd(reinterpret_cast<unsigned long long*>(accRow + col + v), (unsigned long long)acc[v]);
+        }
+        __threadfence();
+        __syncwarp();
+        uint32_t last = 0;
+        if (lane == 0) last = (atomicAdd(u.arrived + slot, 1u) == nItemsCol - 1) ? 1u : 0u;
+        last = __shfl_sync(0xffffffffu, last, 0);
+        if (!last) continue;
+        __threadfence();
+        if (lane == 0) u.arrived[slot] = 0;                                   // zero again for the next call
+        for (uint32_t col = lane * 4; col < a.n; col += 128) {
+            long long tot[4];
+#pragma unroll
+            for (int v = 0; v < 4; v++) {
+                tot[v] = (long long)__ldcg(reinterpret_cast<const unsigned long long*>(accRow + col + v));
+                accRow[col + v] = 0;
+            }
+            finish_row<ANALOG, FUSED_MODE>(a, c, col, tot);
+        }
+    }
+    // ---- light columns: one warp each
+    for (uint32_t c = gw; c < a.m; c += nw) {
+        const size_t rowOff = (size_t)c * a.n + lane * 4;
+        RowRegs r;
+        load_row<FUSED_MODE>(a, rowOff, r);                                    // HBM: the longest latency of the column, asked for first
+        const uint32_t s = __ldg(a.tStart + c), e = __ldg(a.tEnd + c), cnt = e - s;
+        if (cnt > kHeavy2) continue;
+        uint32_t myRow = 0; float myVal = 1.0f;
+        if (lane < cnt) { myRow = __ldg(a.tIndex + s + lane); if (ANALOG) myVal = __ldg(a.tData + s + lane); }
+        for (uint32_t col = lane * 4; col < a.n; col += 128) {
+            RowRegs rn;
+            if (col + 128 < a.n) load_row<FUSED_MODE>(a, rowOff + (col - lane * 4) + 128, rn);   // next 128-column block of the row
+            long long acc[4] = {0, 0, 0, 0};
+            gather32<ANALOG>(a, a.delta + col, cnt, myRow, myVal, acc);
+            finish_row_regs<FUSED_MODE>(a, (size_t)c * a.n + col, r, acc);
+            r = rn;
+        }
+    }
+}
+
+template <bool ANALOG, int FUSED_MODE>
+static int launch_wgrad3(dsb200_ctx* ctx, const GArgs& a, uint32_t maxEntries)
+{
+    // capacities: a heavy column holds > 32 entries -> at most maxEntries / 33 of them, and at most maxEntries / 32 + that many items
+    const uint32_t maxSlots = maxEntries / 33 + 1, maxItems = maxEntries / 32 + maxSlots + 1;
+    const size_t need = 2 * sizeof(uint32_t) * 2 + (size_t)a.m * 4 + (size_t)maxSlots * 4 + (size_t)maxItems * 8 + (size_t)maxSlots * a.n * 8 + 64;
+    if (need > ctx->heavy3Bytes) {
+        DSB_CUDA_OK(cudaStreamSynchronize(ctx->stream));
+        cudaFree(ctx->dHeavy3);
+        ctx->dHeavy3 = nullptr; ctx->heavy3Bytes = 0;
+        DSB_CUDA_OK(cudaMalloc(&ctx->dHeavy3, need));
+        DSB_CUDA_OK(cudaMemsetAsync(ctx->dHeavy3, 0, need, ctx->stream));          // accumulators and arrival counters start (and stay) zero
+        ctx->heavy3Bytes = need;
+        ctx->heavySlots = maxSlots; ctx->heavyN = a.n; ctx->heavyM = a.m;
+    } else if (ctx->heavySlots != maxSlots || ctx->heavyN != a.n || ctx->heavyM != a.m) {
+        DSB_CUDA_OK(cudaMemsetAsync(ctx->dHeavy3, 0, ctx->heavy3Bytes, ctx->stream));   // the layout below changes: nothing of the old one may remain
+        ctx->heavySlots = maxSlots; ctx->heavyN = a.n; ctx->heavyM = a.m;
+    }
+    uint8_t* p = reinterpret_cast<uint8_t*>(ctx->dHeavy3);
+    UArgs u{};
+    u.status = ctx->dStatus;
+    u.acc = reinterpret_cast<long long*>(p); p += (size_t)maxSlots * a.n * 8;
+    u.items = reinterpret_cast<uint32_t*>(p); p += (size_t)maxItems * 8;
+    u.itemCount = reinterpret_cast<uint32_t*>(p); p += 16;
+    u.slotOf = reinterpret_cast<uint32_t*>(p); p += (size_t)a.m * 4;
+    u.arrived = reinterpret_cast<uint32_t*>(p);
+    u.maxItems = maxItems; u.maxSlots = maxSlots;
+    DSB_CUDA_OK(cudaMemsetAsync(u.itemCount, 0, 8, ctx->stream));
+    wgrad_classify_kernel<<<std::min<uint32_t>((a.m + 255) / 256, (uint32_t)ctx->numSMs * 4), 256, 0, ctx->stream>>>(a.m, a.tStart, a.tEnd, u);
+    count_launch();
+    static int blocksPerSM = 0;                                               // per instantiation
+    if (!blocksPerSM) {
+        int occ = 0;
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, sparse_wgrad_unified_kernel<ANALOG, FUSED_MODE>, kGThreads, 0) != cudaSuccess || occ < 1) {
+            cudaGetLastError();
+            occ = 2;
+        }
+        blocksPerSM = occ;
+    }
+    int grid = ctx->numSMs * (ctx->wgradLightBlocks > 0 ? ctx->wgradLightBlocks : blocksPerSM);
+    const uint32_t warps = kGThreads / 32;
+    if ((uint32_t)grid > (a.m + warps - 1) / warps) grid = (int)((a.m + warps - 1) / warps);
+    if (grid < 1) grid = 1;
+    sparse_wgrad_unified_kernel<ANALOG, FUSED_MODE><<<grid, kGThreads, 0, ctx->stream>>>(a, u);
+    count_launch();
+    DSB_CUDA_OK(cudaGetLastError());
+    return 0;
+}
+
 static int check_wgrad_args(dsb200_ctx* ctx, const uint32_t* tStart, const uint32_t* tEnd, const uint32_t* tIndex, const float* delta)
 {
     if (!ctx || !tStart || !tEnd || !tIndex || !delta) return fail(ctx, DSB200_EINVAL, "sparse_wgrad: null argument");
@@ -465,6 +679,7 @@ int dsb200_sparse_wgrad(dsb200_ctx* ctx, float alpha, float beta, uint32_t m, ui
     a.beta = beta; a.m = m; a.n = n;
     a.tStart = tStart; a.tEnd = tEnd; a.tIndex = tIndex; a.tData = tData; a.delta = delta; a.dW = dW;
     const bool vec = (n % 4 == 0) && ((((uintptr_t)delta | (uintptr_t)dW) % 16) == 0);
+    if (vec && (n % 128 == 0) && !ctx->wgradTileKernel && !ctx->wgradTwoKernel) return tData ? launch_wgrad3<true, -1>(ctx, a, ctx->wgradMaxEntries) : launch_wgrad3<false, -1>(ctx, a, ctx->wgradMaxEntries);
     if (vec && (n % 128 == 0) && !ctx->wgradTileKernel) return tData ? launch_wgrad2<true, -1>(ctx, a) : launch_wgrad2<false, -1>(ctx, a);
     if (vec) return tData ? launch_wgrad<true, -1>(ctx, a) : launch_wgrad<false, -1>(ctx, a);
     uint64_t blocks = ((uint64_t)m * n + 255) / 256;
@@ -499,7 +714,9 @@ int dsb200_sparse_wgrad_update(dsb200_ctx* ctx, int mode, float galpha, uint32_t
     a.opt = make_opt(mode, alpha, lambda, lambda1, mu, mu1, t);
     a.v = v; a.gv = gv; a.w = w;
     const bool two = (n % 128 == 0) && !ctx->wgradTileKernel;
-#define DSB_FUSED(M) (two ? (tData ? launch_wgrad2<true, M>(ctx, a) : launch_wgrad2<false, M>(ctx, a)) \
+    const bool uni = two && !ctx->wgradTwoKernel;
+#define DSB_FUSED(M) (uni ? (tData ? launch_wgrad3<true, M>(ctx, a, ctx->wgradMaxEntries) : launch_wgrad3<false, M>(ctx, a, ctx->wgradMaxEntries)) \
+                    : two ? (tData ? launch_wgrad2<true, M>(ctx, a) : launch_wgrad2<false, M>(ctx, a)) \
                           : (tData ? launch_wgrad<true, M>(ctx, a) : launch_wgrad<false, M>(ctx, a)))
     switch (mode) {
     case DSB200_SGD:      return DSB_FUSED(DSB200_SGD);

@@ -341,6 +341,7 @@ void NNNetwork::RefreshState()
     if (_bShuffleIndices && _mode == Training) RefreshShuffleBuffers();
     AllocatePeerBuffers();
     // split-row workspace of the sparse-Z kernel: worst case one partial row per 64 nnz plus one per example
+    uint32_t maxBatchNnz = 0;
     for (auto l : _vInputLayer) {
         if (!l->_pDataSet || l->_vOutgoingLayer.empty()) continue;
         l->_pDataSet->GenerateSparseTransposedMatrix(_batch, l);
@@ -348,10 +349,13 @@ void NNNetwork::RefreshState()
         for (auto o : l->_vOutgoingLayer) stride = max(stride, o->_stride);
         const size_t items = (size_t)l->_pDataSet->_maxBatchNnz / 64 + _batch + 1;
         getGpu().Check(dsb200_ctx_reserve(getGpu()._ctx, _batch, items * stride), "dsb200_ctx_reserve");
+        // the sparse gradient kernel sizes its heavy-column work lists from the most entries one batch can hold
+        maxBatchNnz = max(maxBatchNnz, l->_pDataSet->_maxBatchNnz);
     }
     // the gradient kernel sums in fixed point, so the order inside a transposed column does not matter: skip the
     // canonical-order pass in the training loop (kernel-level callers keep it on by default)
     getGpu().Check(dsb200_ctx_set_option(getGpu()._ctx, "transpose_sort", 0), "dsb200_ctx_set_option");
+    if (maxBatchNnz) getGpu().Check(dsb200_ctx_set_option(getGpu()._ctx, "wgrad_max_entries", (int)min<uint32_t>(maxBatchNnz + 64, 0x7fffffffu)), "dsb200_ctx_set_option");
     getGpu().SetNeuralNetwork(this);
     _bDirty = false;
 }

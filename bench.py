@@ -160,6 +160,8 @@ def run_ours(args, wl, rank, world, local_rank):
     engine.set_stream(stream.cuda_stream)
     engine.set_option("p2p_exchange", 1 if args.p2p else 0)
     engine.set_option("fuse_output_gemm", 1 if args.fuse_output else 0)
+    if args.gemm_loader >= 0:
+        engine.set_option("gemm_loader", args.gemm_loader)
 
     n_batches = 16 if wl["name"] == "c2" else 4
     data = make_data(wl, n_batches)
@@ -505,6 +507,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c2", "c4"])
     ap.add_argument("--gemm-mode", type=int, default=2, help="dense GEMMs: 0 cuBLAS fp32, 1 tcgen05 TF32, 2 tcgen05 3xTF32 (fp32-grade)")
+    ap.add_argument("--gemm-loader", type=int, default=-1, help="operand path of the general tcgen05 kernel (csrc/gemm_tc.cu), -1 = per shape")
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--side", type=int, default=1, help="1 (default) = after the headline workload also time BASELINE config 4 (1M-item layers) and config 5 (top-K) and add them as \"c4\" / \"c5\" records")
     ap.add_argument("--c4-steps", type=int, default=6)

@@ -305,7 +305,7 @@ def test_dropout_training_matches_oracle(eng, orc):
 
 
 # engine option "pinned_mirror" (single host copy per streamed batch) was written after round 1's GPU budget was spent
-STREAM_PATHS = [0] + ([1] if os.environ.get("DSB200_RUN_UNVERIFIED") else [])
+STREAM_PATHS = [0, 1]
 
 
 @pytest.mark.parametrize("pinned_mirror", STREAM_PATHS, ids=lambda v: "pinned-mirror" if v else "staging")

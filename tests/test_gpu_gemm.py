@@ -28,10 +28,9 @@ def ref64(a):
 
 LOADERS = [(0, -1), (2, -1), (2, 2), (2, 1), (2, 0), (1, 2), (1, 1), (1, 0)]
 LOADER_IDS = ["fp32", "tf32x3-auto", "tf32x3-tmemA", "tf32x3-regload", "tf32x3-cpasync", "tf32-tmemA", "tf32-regload", "tf32-cpasync"]
-if os.environ.get("DSB200_RUN_UNVERIFIED"):
-    # gemm_loader = 3 (coalesced tensor-memory A loader on tcgen05.st.16x256b) was written after round 1's GPU budget was spent
-    LOADERS += [(2, 3), (1, 3)]
-    LOADER_IDS += ["tf32x3-tmemA16x256", "tf32-tmemA16x256"]
+# gemm_loader = 3: coalesced tensor-memory A loader on tcgen05.st.16x256b (K-major A)
+LOADERS += [(2, 3), (1, 3)]
+LOADER_IDS += ["tf32x3-tmemA16x256", "tf32-tmemA16x256"]
 
 
 @pytest.mark.parametrize("mode,loader", LOADERS, ids=LOADER_IDS)

@@ -202,12 +202,15 @@ def test_sparse_transpose_unsorted_is_same_set(ctx, orc, dsb):
         np.testing.assert_array_equal(a, b)
 
 
-@pytest.fixture(params=["two_kernel", "tile"])
+@pytest.fixture(params=["unified", "two_kernel", "tile"])
 def gkernel(request, ctx):
-    """both sparse-gradient schemes: warp-per-light-column + CTA-per-heavy-column (default when n % 128 == 0) and the tile kernel"""
+    """the three sparse-gradient schemes: the unified kernel (heavy-column items + light columns in one grid; default when
+    n % 128 == 0), round 1's warp-per-light-column + CTA-per-heavy-column pair, and the tile kernel"""
     ctx.set_option("wgrad_tile_kernel", int(request.param == "tile"))
+    ctx.set_option("wgrad_two_kernel", int(request.param == "two_kernel"))
     yield request.param
     ctx.set_option("wgrad_tile_kernel", 0)
+    ctx.set_option("wgrad_two_kernel", 0)
 
 
 @pytest.mark.parametrize("case", ["tiny128", "ml20m128", "tiny1024", "analog", "beta", "stride100"])
@@ -482,7 +485,6 @@ def test_topk_kv_merge_variant(ctx, orc, dsb):
     np.testing.assert_array_equal(u32(ov), ref_v)
 
 
-@pytest.mark.skipif(not os.environ.get("DSB200_RUN_UNVERIFIED"), reason="not yet run on a GPU (round 1 budget); set DSB200_RUN_UNVERIFIED=1")
 @pytest.mark.parametrize("shards", [2, 8])
 def test_topk_sharded_merge_on_one_gpu(ctx, orc, dsb, shards):
     """The model-parallel top-K scheme (NNNetwork::CalculateTopKGlobal) with the column shards of `shards` ranks taken one
