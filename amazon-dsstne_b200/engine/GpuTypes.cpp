@@ -97,8 +97,20 @@ void GpuContext::Startup(int rank, int nranks, int device, const void* ncclUniqu
 void GpuContext::Shutdown()
 {
     if (_ctx) { dsb200_ctx_destroy(_ctx); _ctx = nullptr; }
+    if (_copyStream) { cudaStreamDestroy(_copyStream); _copyStream = nullptr; }
+    if (_dataConsumedEvent) { cudaEventDestroy(_dataConsumedEvent); _dataConsumedEvent = nullptr; }
+    _bDataConsumedValid = false;
     _bStarted = false;
     _pNetwork = nullptr;
+}
+
+cudaStream_t GpuContext::CopyStream()
+{
+    if (!_copyStream) {
+        RTERROR(cudaStreamCreateWithFlags(&_copyStream, cudaStreamNonBlocking), "GpuContext: copy stream");
+        RTERROR(cudaEventCreateWithFlags(&_dataConsumedEvent, cudaEventDisableTiming), "GpuContext: event");
+    }
+    return _copyStream;
 }
 
 void GpuContext::SetStream(cudaStream_t stream)

@@ -66,12 +66,19 @@ struct GpuContext {
     void CopyConstants();                                         // E/GpuTypes.cpp:408
     void SetStream(cudaStream_t stream);
     cudaStream_t GetStream() const { return _stream; }
+    // Streamed datasets (NNDataSet::LoadSparseData once per step) upload on their own stream so that the copies of batch k + 1 run
+    // beside the backward pass of batch k: the network records _dataConsumedEvent once the last reader of the CSR buffers of a step
+    // has been launched (NNNetwork::LaunchError); an upload waits for it on the copy stream, and the next step waits for the upload.
+    cudaStream_t CopyStream();
+    cudaEvent_t     _dataConsumedEvent = nullptr;
+    bool            _bDataConsumedValid = false;
     void GetMemoryUsage(int* gpuMemory, int* cpuMemory);
     void Check(int rc, const char* what);                         // throws on a non-zero C-ABI code
     void Synchronize();
 
 private:
     cudaStream_t    _stream;
+    cudaStream_t    _copyStream = nullptr;
 };
 
 GpuContext& getGpu();

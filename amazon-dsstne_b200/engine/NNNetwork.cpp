@@ -419,6 +419,9 @@ void NNNetwork::PredictBatch(uint32_t layers)
     if (_bDirty) RefreshState();
     uint32_t batch = _batch;
     if (_position + batch > _examples) batch = _examples - _position;
+    for (auto d : _vData) d->WaitForUpload(getGpu().GetStream());
+    getGpu()._bDataConsumedValid = false;              // this pass reads the data sets without recording where it stops
+    _bStepReadsRecorded = false;
     ClearUpdates();
     LoadBatch();
     for (auto l : _vFPOrder) l->ForwardPropagate(_position, batch, false);
@@ -494,6 +497,13 @@ void NNNetwork::LaunchError(NNFloat lambda, NNFloat lambda1)
     if (_bRegularizationLaunched) RTERROR(cudaStreamWaitEvent(s, _prepEvent, 0), "LaunchError prep wait");   // target bitmap, transposed matrix, W copies
     _bRegularizationLaunched = false;
     for (auto l : _vOutputLayer) l->CalculateErrorAsync(_position, batch, _errorFunction, acc);
+    if (_bStepReadsRecorded) {
+        // every reader of the data sets' CSR buffers in this step has been launched (sparse Z, the side-stream preparation the prep event
+        // covers, the loss / delta pass): the next batch may be uploaded beside the backward pass (NNDataSet::BeginUpload)
+        getGpu().CopyStream();
+        RTERROR(cudaEventRecord(getGpu()._dataConsumedEvent, s), "LaunchError consumed event");
+        getGpu()._bDataConsumedValid = true;
+    }
     RTERROR(cudaStreamWaitEvent(s, _joinEvent, 0), "LaunchError join");
     if (getGpu()._numprocs > 1)
         getGpu().Check(dsb200_all_reduce_u64(getGpu()._ctx, acc, 2), "dsb200_all_reduce_u64");
@@ -570,6 +580,9 @@ float NNNetwork::TrainStep(uint32_t position, NNFloat alpha, NNFloat lambda, NNF
     if (_bDirty) RefreshState();
     SetPosition(position);
     ClearUpdates();
+    for (auto d : _vData) d->WaitForUpload(getGpu().GetStream());      // a batch streamed in on the copy stream since the last step
+    getGpu()._bDataConsumedValid = false;                            // until this step's readers are on their way (LaunchError)
+    _bStepReadsRecorded = _bFusion;                                  // only the fused step waits for the side stream before the loss pass
     if (_bFusion) {                                  // batch preparation + regularisation error on the side stream while the forward pass runs
         RTERROR(cudaMemsetAsync(_pbErrorAccumulator->_pDevData, 0, 2 * sizeof(unsigned long long), getGpu().GetStream()), "TrainStep memset");
         LaunchBatchPreparation(lambda, lambda1);

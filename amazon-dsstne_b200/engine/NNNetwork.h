@@ -68,6 +68,7 @@ private:
     cudaEvent_t             _errorEvent;
     cudaStream_t            _sideStream;                  // regularisation error runs here, beside the forward pass
     cudaEvent_t             _forkEvent, _joinEvent, _prepEvent;
+    bool                    _bStepReadsRecorded = false;   // TrainStep: LaunchError records GpuContext::_dataConsumedEvent for the streaming loader
     bool                    _bBatchPrepared = false;      // TrainStep launched LoadBatch on the side stream: PredictTrainingBatch must not repeat it
     bool                    _verbose;
     bool                    _bRegularizationLaunched;     // LaunchError finds the regularisation kernels already in flight

@@ -142,8 +142,31 @@ void NNDataSet<T>::LoadSparseData(const uint64_t* srcSparseStart, const uint64_t
     UploadSparseAsync(srcSparseStart, srcSparseEnd, srcSparseData, srcSparseIndex, srcSparseEnd[_uniqueExamples - 1]);
 }
 
-// Engine option "pinned_mirror" (EXPERIMENTAL, written at the end of round 1 without GPU time left: not yet run).  The default
-// path above copies every batch twice on the host (mirror, then pinned staging); here the mirror vectors are page-locked in
+// Uploads of a streamed batch go to the copy stream when the network has recorded where the last step stopped reading the CSR
+// buffers (GpuContext::_dataConsumedEvent): they then overlap that step's backward pass instead of queueing behind it.
+template <typename T>
+cudaStream_t NNDataSet<T>::BeginUpload()
+{
+    if (!getGpu()._bDataConsumedValid) return getGpu().GetStream();
+    cudaStream_t cs = getGpu().CopyStream();
+    RTERROR(cudaStreamWaitEvent(cs, getGpu()._dataConsumedEvent, 0), "NNDataSet upload wait");
+    return cs;
+}
+
+template <typename T>
+void NNDataSet<T>::EndUpload(cudaStream_t stream, cudaEvent_t done)
+{
+    _uploadEvent = (stream != getGpu().GetStream()) ? done : nullptr;
+}
+
+template <typename T>
+void NNDataSet<T>::WaitForUpload(cudaStream_t stream)
+{
+    if (_uploadEvent) { RTERROR(cudaStreamWaitEvent(stream, _uploadEvent, 0), "NNDataSet upload join"); _uploadEvent = nullptr; }
+}
+
+// Engine option "pinned_mirror": the default  The default
+// path copies every batch twice on the host (mirror, then pinned staging); here the mirror vectors are page-locked in
 // place (cudaHostRegister, once -- their storage never moves after construction) and are themselves the source of the
 // asynchronous copies, so a batch is copied once.
 template <typename T>
@@ -164,7 +187,7 @@ bool NNDataSet<T>::UploadMirrorAsync(uint64_t dataLength)
         _mirror.ptr[i] = want[i];
     }
     if (!_mirror.done) RTERROR(cudaEventCreateWithFlags(&_mirror.done, cudaEventDisableTiming), "NNDataSet mirror event");
-    cudaStream_t stream = getGpu().GetStream();
+    cudaStream_t stream = BeginUpload();
     RTERROR(cudaMemcpyAsync(_pbSparseStart->_pDevData, _vSparseStart.data(), _uniqueExamples * sizeof(uint64_t), cudaMemcpyHostToDevice, stream), "NNDataSet upload");
     RTERROR(cudaMemcpyAsync(_pbSparseEnd->_pDevData, _vSparseEnd.data(), _uniqueExamples * sizeof(uint64_t), cudaMemcpyHostToDevice, stream), "NNDataSet upload");
     if (dataLength) RTERROR(cudaMemcpyAsync(_pbSparseIndex->_pDevData, _vSparseIndex.data(), dataLength * sizeof(uint32_t), cudaMemcpyHostToDevice, stream), "NNDataSet upload");
@@ -172,6 +195,7 @@ bool NNDataSet<T>::UploadMirrorAsync(uint64_t dataLength)
         RTERROR(cudaMemcpyAsync(_pbSparseData->_pDevData, _vSparseData.data(), dataLength * sizeof(T), cudaMemcpyHostToDevice, stream), "NNDataSet upload");
     RTERROR(cudaEventRecord(_mirror.done, stream), "NNDataSet mirror record");
     _mirror.pending = true;
+    EndUpload(stream, _mirror.done);
     return true;
 }
 
@@ -191,7 +215,7 @@ void NNDataSet<T>::UploadSparseAsync(const uint64_t* srcStart, const uint64_t* s
         RTERROR(cudaEventCreateWithFlags(&st.done, cudaEventDisableTiming), "NNDataSet staging event");
     }
     if (st.pending) { RTERROR(cudaEventSynchronize(st.done), "NNDataSet staging wait"); st.pending = false; }
-    cudaStream_t stream = getGpu().GetStream();
+    cudaStream_t stream = BeginUpload();
     memcpy(st.start, srcStart, _uniqueExamples * sizeof(uint64_t));
     memcpy(st.end, srcEnd, _uniqueExamples * sizeof(uint64_t));
     memcpy(st.index, srcIndex, dataLength * sizeof(uint32_t));
@@ -204,6 +228,7 @@ void NNDataSet<T>::UploadSparseAsync(const uint64_t* srcStart, const uint64_t* s
     }
     RTERROR(cudaEventRecord(st.done, stream), "NNDataSet staging record");
     st.pending = true;
+    EndUpload(stream, st.done);
 }
 
 template <typename T>

@@ -142,6 +142,7 @@ struct NNDataSetBase {
     uint32_t GetUniqueExamples() { return _uniqueExamples; }
 
     virtual bool SaveNetCDF(const string& fname) = 0;
+    virtual void WaitForUpload(cudaStream_t stream) = 0;      // a step that reads this data set waits for a pending copy-stream upload
     virtual void RefreshState(uint32_t batch) = 0;
     virtual bool Shard(NNDataSetEnums::Sharding sharding) = 0;
     virtual bool UnShard() = 0;
@@ -252,15 +253,19 @@ private:
         cudaEvent_t done = nullptr; bool pending = false;
     } _staging[2];
     int _stagingCur = 0;
+    cudaEvent_t _uploadEvent = nullptr;                       // recorded on the copy stream: readers of this step wait for it (WaitForUpload)
     // experimental single-copy path (engine option "pinned_mirror"): the host mirror itself is page-locked and is the copy source
     struct Mirror {
         void* ptr[4] = {nullptr, nullptr, nullptr, nullptr};      // registered storage of _vSparseStart / End / Index / Data
         cudaEvent_t done = nullptr; bool pending = false; bool unavailable = false;
     } _mirror;
     bool UploadMirrorAsync(uint64_t dataLength);              // false: page-locking failed, the caller takes the staging path
+    cudaStream_t BeginUpload();                               // the stream this upload goes to (copy stream when the last step's readers are known)
+    void EndUpload(cudaStream_t stream, cudaEvent_t done);
     unique_ptr<GpuBuffer<uint32_t>> _pbColumnCount;        // scratch of the device-side capacity table
 public:
     ~NNDataSet();
+    void WaitForUpload(cudaStream_t stream);
 private:
     float SyncError(ErrorFunction ef, Activation activation, uint32_t position, uint32_t batch, uint32_t stride, NNFloat* pUnit);
 };
