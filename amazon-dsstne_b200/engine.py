@@ -206,6 +206,12 @@ class Network:
                                                C.c_float(mu), C.c_float(mu1), C.byref(e)))
         return e.value
 
+    def validate(self, samples=0):
+        """NNNetwork::Validate: finite-difference gradient check through the training kernels; True when every probe passes"""
+        ok = C.c_int(0)
+        _check(lib().dsb200_network_validate(self.h, C.c_uint32(samples), C.byref(ok)))
+        return bool(ok.value)
+
     def predict_batch(self):
         _check(lib().dsb200_network_predict_batch(self.h))
 

@@ -663,10 +663,97 @@ float NNNetwork::Train(uint32_t epochs, NNFloat alpha, NNFloat lambda, NNFloat l
     return average_error_training + average_error_regularization;
 }
 
+// NNNetwork::Validate (E/NNNetwork.cpp:2459-2633): finite-difference check of every weight and bias gradient through the SAME kernels
+// training uses -- here on the sparse path as it is (the reference's forces nothing either: its test networks are sparse, tst/test_data/
+// validate_*.json).  delta = 1e-3 scaled by 1 / batch, threshold 20 * delta, SGD, no regularisation as in the reference, but with the
+// CENTRED difference its own comment asks for (E/NNNetwork.cpp:2472-2474) and the loss read in 2^30 fixed point instead of fp32; fusions are switched off for the duration so that the weight gradients are materialised.  A matrix with more than
+// _validateMaxSamples elements is checked on an evenly spaced sample (the reference walks every element of its 2 x 2 test networks).
 bool NNNetwork::Validate()
 {
-    throw DsbEngineError("NNNetwork::Validate: the finite-difference gradient check is re-hosted on the CPU oracle "
-                         "(tests/test_oracle_gradcheck.py) -- it forces the dense input path, which is outside the hot path");
+    bool result = true;
+    const NNFloat delta = (NNFloat)0.001, alpha = (NNFloat)1.0, lambda = (NNFloat)0.0, lambda1 = (NNFloat)0.0, mu = (NNFloat)0.0, mu1 = (NNFloat)0.0;
+    const NNFloat epsilon = delta * 20.f;
+    if (getGpu()._numprocs > 1) {
+        cout << "NNNetwork::Validate: Do not call this method from a multi-process run, just don't, mmkay?" << endl;
+        return false;
+    }
+    const bool fusion = _bFusion;
+    const TrainingMode trainingMode = _trainingMode;
+    _bFusion = false;
+    SetTrainingMode(SGD);
+    if (_mode != Validation) { _mode = Validation; _bDirty = true; }
+    if (_bDirty) RefreshState();
+    cout << "Validating network weights and biases with epsilon error threshold of " << epsilon << endl;
+    uint32_t batch = _batch;
+    SetPosition(0);
+    if (_position + batch > _examples) batch = _examples - _position;
+    auto forwardError = [&]() {
+        ClearUpdates();
+        LoadBatch();
+        for (auto l : _vFPOrder) l->ForwardPropagate(_position, batch, false);
+        CalculateError(lambda, lambda1);
+        // the loss as the kernels accumulated it (2^30 fixed point), NOT rounded to fp32: a probe moves it by ~delta * gradient = 1e-4,
+        // below the fp32 resolution of a loss summed over a whole batch (the reference's 2 x 2 test networks never get there)
+        return (double)(long long)_pbErrorAccumulator->_pSysData[0] * (1.0 / 1073741824.0) + (double)(long long)_pbErrorAccumulator->_pSysData[1] * (1.0 / 1073741824.0);
+    };
+    const double initialError = forwardError();
+    cout << "initialError " << initialError << endl;
+    BackPropagate();
+    vector<vector<NNFloat>> vWeightGradient, vBiasGradient;
+    for (auto w : _vWeight) {
+        vWeightGradient.push_back(vector<NNFloat>(w->_localSize));
+        w->_pbWeight->Download(w->_vWeight.data());
+        w->_pbBias->Download(w->_vBias.data());
+        w->_pbWeightGradient->Download(vWeightGradient.back().data());
+    }
+    // the bias gradient is not stored: take it from one SGD step with alpha = 1 and put the parameters back (E/NNNetwork.cpp:2548-2573)
+    UpdateWeights(alpha, lambda, lambda1, mu, mu1);
+    for (auto w : _vWeight) {
+        vector<NNFloat> after(w->_localBiasSize);
+        w->_pbBias->Download(after.data());
+        for (size_t b = 0; b < after.size(); b++) after[b] -= w->_vBias[b];
+        vBiasGradient.push_back(after);
+        w->_pbWeight->Upload(w->_vWeight.data());
+        w->_pbBias->Upload(w->_vBias.data());
+    }
+    for (size_t id = 0; id < _vWeight.size(); id++) {
+        NNWeight* w = _vWeight[id];
+        cout << "Validating weights between layer " << w->_inputLayer._name << " and " << w->_outputLayer._name << endl;
+        const size_t nW = w->_localSize, stepW = max<size_t>(1, nW / _validateMaxSamples);
+        for (size_t i = 0; i < nW; i += stepW) {
+            const NNFloat h = delta / (batch * w->_sharingCount);                              // the gradient carries -1 / (sharing * batch)
+            const NNFloat up = w->_vWeight[i] + h, down = w->_vWeight[i] - h;
+            RTERROR(cudaMemcpy(w->_pbWeight->_pDevData + i, &up, sizeof(NNFloat), cudaMemcpyHostToDevice), "Validate poke");
+            const double errorUp = forwardError();
+            RTERROR(cudaMemcpy(w->_pbWeight->_pDevData + i, &down, sizeof(NNFloat), cudaMemcpyHostToDevice), "Validate poke");
+            const double errorDown = forwardError();
+            RTERROR(cudaMemcpy(w->_pbWeight->_pDevData + i, &w->_vWeight[i], sizeof(NNFloat), cudaMemcpyHostToDevice), "Validate restore");
+            const NNFloat dEdW = (NNFloat)((errorUp - errorDown) / ((double)(up - down) * batch * w->_sharingCount)), g = vWeightGradient[id][i];
+            if (fabs(dEdW + g) > epsilon) {
+                cout << "Failed Weight " << i << " exceeds error threshold: " << dEdW << " vs " << g << endl;
+                result = false;
+            }
+        }
+        const size_t nB = w->_localBiasSize, stepB = max<size_t>(1, nB / _validateMaxSamples);
+        for (size_t i = 0; i < nB; i += stepB) {
+            const NNFloat h = delta / batch;
+            const NNFloat up = w->_vBias[i] + h, down = w->_vBias[i] - h;
+            RTERROR(cudaMemcpy(w->_pbBias->_pDevData + i, &up, sizeof(NNFloat), cudaMemcpyHostToDevice), "Validate poke");
+            const double errorUp = forwardError();
+            RTERROR(cudaMemcpy(w->_pbBias->_pDevData + i, &down, sizeof(NNFloat), cudaMemcpyHostToDevice), "Validate poke");
+            const double errorDown = forwardError();
+            RTERROR(cudaMemcpy(w->_pbBias->_pDevData + i, &w->_vBias[i], sizeof(NNFloat), cudaMemcpyHostToDevice), "Validate restore");
+            const NNFloat dEdb = (NNFloat)((errorUp - errorDown) / ((double)(up - down) * batch)), g = vBiasGradient[id][i];
+            if (fabs(dEdb + g) > epsilon) {
+                cout << "Failed Bias " << i << " exceeds error threshold: " << dEdb << " vs " << g << endl;
+                result = false;
+            }
+        }
+    }
+    _bFusion = fusion;
+    SetTrainingMode(trainingMode);
+    _mode = Training; _bDirty = true;
+    return result;
 }
 
 // E/NNNetwork.cpp:1792-1822.  The reference caps k at 128 here; the kernel behind this takes k <= 1024.

@@ -68,6 +68,7 @@ private:
     cudaEvent_t             _errorEvent;
     cudaStream_t            _sideStream;                  // regularisation error runs here, beside the forward pass
     cudaEvent_t             _forkEvent, _joinEvent, _prepEvent;
+    size_t                  _validateMaxSamples = 256;    // Validate(): elements checked per weight matrix / bias vector
     bool                    _bStepReadsRecorded = false;   // TrainStep: LaunchError records GpuContext::_dataConsumedEvent for the streaming loader
     bool                    _bBatchPrepared = false;      // TrainStep launched LoadBatch on the side stream: PredictTrainingBatch must not repeat it
     bool                    _verbose;
@@ -85,6 +86,7 @@ public:
     void LoadDataSets(vector<NNDataSetBase*>& vData);
     void Randomize();
     bool Validate();
+    void SetValidateSamples(size_t n) { _validateMaxSamples = n ? n : 1; }
     float Train(uint32_t epochs = 1, NNFloat alpha = (NNFloat)0.1, NNFloat lambda = (NNFloat)0.001, NNFloat lambda1 = (NNFloat)0.0,
                 NNFloat mu = (NNFloat)0.1, NNFloat mu1 = 0.0);
     // one minibatch of Train's loop body at `position` (B200 addition: lets a caller time / drive single steps)

@@ -316,6 +316,15 @@ int dsb200_network_train_step(dsb200_network* n, uint32_t position, float alpha,
     DSB_ENGINE_CATCH
 }
 
+int dsb200_network_validate(dsb200_network* n, uint32_t samplesPerMatrix, int* pOk)
+{
+    DSB_ENGINE_TRY
+    if (samplesPerMatrix) NET(n)->SetValidateSamples(samplesPerMatrix);
+    const bool ok = NET(n)->Validate();
+    if (pOk) *pOk = ok ? 1 : 0;
+    DSB_ENGINE_CATCH
+}
+
 int dsb200_describe_network_json(const char* jsonText, const char* const* dataSetNames, const uint32_t* dataSetWidths, int nSets, char* buf, size_t cap)
 {
     DSB_ENGINE_TRY

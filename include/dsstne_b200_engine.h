@@ -92,6 +92,9 @@ int dsb200_network_examples(dsb200_network* n, uint32_t* out);
 int dsb200_network_train(dsb200_network* n, uint32_t epochs, float alpha, float lambda, float lambda1, float mu, float mu1, float* pError);
 /* one minibatch of Train's loop body at `position` (loss of that minibatch through *pError) */
 int dsb200_network_train_step(dsb200_network* n, uint32_t position, float alpha, float lambda, float lambda1, float mu, float mu1, float* pError);
+/* NNNetwork::Validate (E/NNNetwork.cpp:2459-2633): finite-difference check of the weight and bias gradients on the first batch, through
+ * the training kernels; samplesPerMatrix elements per matrix (0 = default 256).  *pOk = 1 when every probe is within 20 * 1e-3. */
+int dsb200_network_validate(dsb200_network* n, uint32_t samplesPerMatrix, int* pOk);
 /* NNNetwork::PredictBatch at the current position */
 int dsb200_network_predict_batch(dsb200_network* n);
 /* NNNetwork::CalculateTopK (+ device-side exclusion filter when filter != NULL); HOST outputs [batch][k] */

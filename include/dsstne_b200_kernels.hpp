@@ -265,3 +265,9 @@ inline void kCalculateTopK(NNFloat* pOutputKey, NNFloat* pKey, uint32_t* pValue,
 { dsb200k::check(dsb200_topk(dsb200k::ctx(), pOutputKey, batch, width, k, nullptr, nullptr, nullptr, pKey, pValue), "kCalculateTopK"); }
 inline void kCalculateTopK(NNFloat* pOutputKey, uint32_t* pOutputValue, NNFloat* pKey, uint32_t* pValue, uint32_t batch, uint32_t width, uint32_t k)
 { dsb200k::check(dsb200_topk_kv(dsb200k::ctx(), pOutputKey, pOutputValue, batch, width, k, pKey, pValue), "kCalculateTopK"); }
+/* E/kernels.h:42 -- 4-arg variant with FLOAT values (a second score carried along with the key): the values travel as raw 32-bit words */
+inline void kCalculateTopK(NNFloat* pOutputKey, NNFloat* pOutputValue, NNFloat* pKey, NNFloat* pValue, uint32_t batch, uint32_t width, uint32_t k)
+{
+    dsb200k::check(dsb200_topk_kv(dsb200k::ctx(), pOutputKey, reinterpret_cast<uint32_t*>(pOutputValue), batch, width, k, pKey,
+                                  reinterpret_cast<uint32_t*>(pValue)), "kCalculateTopK");
+}

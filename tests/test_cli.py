@@ -93,3 +93,14 @@ def test_train_then_predict_recommends_inside_the_taste_group(tmp_path):
         inside += sum(1 for i in items if (int(i[1:]) >= 150) == (g == 1))
         total += len(items)
     assert inside / total > 0.9, inside / total
+
+
+@pytest.mark.gpu
+def test_reference_style_call_sites_through_the_shim_header():
+    """bin/shim_smoke: a translation unit written like the reference's callers (free functions of E/kernels.h on raw device pointers)
+    compiled against include/dsstne_b200_kernels.hpp and RUN -- a miniature training step checked against host loops."""
+    exe = os.path.join(ROOT, "amazon-dsstne_b200", "bin", "shim_smoke")
+    assert os.path.exists(exe), "run __graft_entry__.build()"
+    p = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+    assert p.returncode == 0, p.stdout + p.stderr
+    assert "shim ok" in p.stdout

@@ -414,3 +414,29 @@ def test_engine_rejects_features_outside_the_hot_path(eng):
         eng.Network(bad, 32, [ds])
     with pytest.raises(DsbError):
         eng.Network('{"Version":0.8,"Bogus":1,"Layers":[]}', 32, [ds])        # unknown key is fatal, as in the reference
+
+
+@pytest.mark.parametrize("error,smce", [("L2", None), ("ScaledMarginalCrossEntropy", (1.0, 0.0, 30.0, 1.0)), ("CrossEntropy", None)])
+@pytest.mark.parametrize("hidden", [[8], [12, 8]], ids=["one-hidden", "two-hidden"])
+def test_validate_finite_differences_on_the_gpu_engine(eng, orc, error, smce, hidden):
+    """NNNetwork::Validate (E/NNNetwork.cpp:2459-2633) run on the product: the networks of tst/test_data/validate_{L2,ScaledMarginalCrossEntropy}
+    _0{1,2}.json (sparse input -> sigmoid hidden layer(s) -> sparse sigmoid output, oneScale 30 for SMCE) at a size where the sparse kernels
+    do real work; every weight and bias gradient the training kernels produce must agree with a finite difference of the loss within 20e-3."""
+    from dsstne_b200 import datagen
+    width, batch = 40, 8
+    h = tiny(examples=batch, width=width, mean=5.0)
+    ds_in = eng.Dataset.from_host_csr("gl_input", h)
+    ds_out = eng.Dataset.from_host_csr("gl_output", h)
+    kw = {} if smce is None else {"smce": smce}
+    net = eng.Network(eng.autoencoder_json(hidden, error=error, **kw), batch, [ds_in, ds_out])
+    sizes = [width] + hidden + [width]
+    Ws, bs = datagen.make_weights(sizes, scale=0.3)
+    names = ["Input"] + [f"Hidden{i + 1}" for i in range(len(hidden))] + ["Output"]
+    for i in range(len(sizes) - 1):
+        net.set_weights(names[i], names[i + 1], Ws[i], bs[i])
+    try:
+        assert net.validate(samples=48) is True
+        # the network is usable afterwards, with its fusions back on
+        assert np.isfinite(net.train_step(0, 0.01))
+    finally:
+        net.close()
