@@ -190,7 +190,7 @@ class Context:
 
     def gemm_fwd_output_pass(self, ds, ef, act, position, A, W, bias, unit_out, delta, acc=None, col_partials=None):
         """Forward GEMM of a sigmoid output layer with loss + delta in its epilogue (Z is never written).  Returns the number of
-        rows of column-sum partials written into col_partials ([2 * ceil(B / 128)][n], optional)."""
+        rows of column-sum partials written into col_partials ([4 * ceil(B / 128)][n], optional)."""
         v = ds.view()
         B, k = A.shape
         n_part = C.c_uint32(0)

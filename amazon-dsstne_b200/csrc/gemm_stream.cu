@@ -567,13 +567,17 @@ transpose_split_kernel(const float* __restrict__ X, uint32_t ldx, uint32_t rows,
 //       (columns 0..127 hi, 128..255 lo); accumulators in columns 256..511.
 //   B = X batch tile [128 rows][K] (hi = X itself, lo = second array), TMA, ring of 32-k panels.
 //   work unit = (output slice, group of batch tiles); units are dealt round robin to the persistent CTAs.
-//   Epilogue (8 warps: quadrant = warp % 4, batch half of the tile = warp / 4): z = acc + bias[n] -> a = sigmoid(z) -> loss and
-//   delta by the target-is-zero formulas, corrected where the TRANSPOSED target bitmap (one word = 32 batch rows of output n)
-//   says so; delta[b][n] stored as 128-byte rows (32 lanes = 32 consecutive n).  Column sums of delta (the bias gradient,
-//   E/NNWeight.cpp:760-794) accumulate in the thread that owns the column and leave as one partial per (group, half).
-// Warps: 0-7 workers (A load + epilogue), 8 TMA producer, 9 MMA issuer.
+//   Epilogue (16 warps: quadrant = warp % 4, batch quarter of the tile = warp / 4; round-2 ncu with 8: 33 instructions per element,
+//   issue slots 55 % busy -- latency bound with two warps per scheduler): z = acc + bias[n] -> a = sigmoid(z) -> loss and delta, the
+//   target taken from the TRANSPOSED bitmap (one word = 32 batch rows of output n); delta[b][n] stored as 128-byte rows (32 lanes =
+//   32 consecutive n).  Column sums of delta (the bias gradient, E/NNWeight.cpp:760-794) accumulate in the thread that owns the
+//   column and leave as one partial per (group, quarter).
+//   The W^T slice of the NEXT unit is requested right before the wait for the unit's last accumulator and stored right after it, so
+//   its 32 registers never coexist with the epilogue's (the 96-register budget of 18 warps).
+// Warps: 0-15 workers (A load + epilogue), 16 TMA producer, 17 MMA issuer.
 // =====================================================================================================================
-constexpr int F_WORKERS = 8, F_TMA_WARP = 8, F_MMA_WARP = 9, F_THREADS = 10 * 32, F_SLOTS = 6;
+constexpr int F_WORKERS = 16, F_TMA_WARP = 16, F_MMA_WARP = 17, F_THREADS = 18 * 32, F_SLOTS = 6;
+constexpr int F_PARTS = F_WORKERS / 4;           // worker warps per TMEM lane quadrant = column-sum partials per (unit, column)
 constexpr int F_SMEM_BYTES = F_SLOTS * SLOT + 1024;
 constexpr uint32_t F_A_LO = 128, F_ACC0 = 256;
 
@@ -586,7 +590,7 @@ struct FArgs {
     const uint32_t* bitsT; uint32_t wordsB;
     const float* rowW;
     unsigned long long* acc;
-    float* colPartials;                            // [groups * 2][N] or NULL
+    float* colPartials;                            // [groups * F_PARTS][N] or NULL
     int passes;
     float zeroTarget, oneTarget, zeroScale, oneScale, boostZero, boostOne;
 };
@@ -659,30 +663,29 @@ out_fwd_kernel(const FArgs f, const __grid_constant__ CUtensorMap mapHi, const _
 
     if (warp < F_WORKERS) {
         // ------------------------------------------------------------ workers
-        const uint32_t q = warp & 3, h = warp >> 2;
+        const uint32_t q = warp & 3, part = warp >> 2;
         const uint32_t laneBase = (q * 32) << 16;
         float loss = 0.0f;
         uint32_t seq = 0;
-        // this thread's part of a unit's W^T slice: row n = m0 + 32 q + lane, k in [64 h, 64 h + 64)
-        uint32_t ra[64];
-        auto fetchA = [&](uint32_t unit) {
+        // this thread's part of a unit's W^T slice: row n = m0 + 32 q + lane, k in [32 part, 32 part + 32)
+        auto loadA = [&](uint32_t unit, uint32_t (&ra)[32]) {
             const uint32_t n = (unit / f.groups) * BM + q * 32 + lane;
-            const float* p = f.W + (size_t)(64 * h) * f.ldw + n;
+            const float* p = f.W + (size_t)(32 * part) * f.ldw + n;
             const bool nIn = n < f.N;
 #pragma unroll
-            for (int e = 0; e < 64; e++) ra[e] = (nIn && 64 * h + e < f.K) ? ldg_nc_u32(p + (size_t)e * f.ldw) : 0u;
+            for (int e = 0; e < 32; e++) ra[e] = (nIn && 32 * part + e < f.K) ? ldg_nc_u32(p + (size_t)e * f.ldw) : 0u;
         };
-        auto storeA = [&]() {
+        auto storeA = [&](const uint32_t (&ra)[32]) {
 #pragma unroll
-            for (int g = 0; g < 4; g++) {
+            for (int g = 0; g < 2; g++) {
                 uint32_t t[16];
 #pragma unroll
                 for (int e = 0; e < 16; e++) t[e] = hi_of(ra[16 * g + e]);
-                tmem_st16(tmem + laneBase + 64 * h + 16 * g, t);
+                tmem_st16(tmem + laneBase + 32 * part + 16 * g, t);
                 if (lo) {
 #pragma unroll
                     for (int e = 0; e < 16; e++) t[e] = lo_of(ra[16 * g + e]);
-                    tmem_st16(tmem + laneBase + F_A_LO + 64 * h + 16 * g, t);
+                    tmem_st16(tmem + laneBase + F_A_LO + 32 * part + 16 * g, t);
                 }
             }
             tmem_st_wait();
@@ -691,10 +694,9 @@ out_fwd_kernel(const FArgs f, const __grid_constant__ CUtensorMap mapHi, const _
             if (lane == 0) mbar_arrive(&aReady);
         };
         uint32_t unit = blockIdx.x;
-        if (unit < numUnits) { fetchA(unit); storeA(); }
+        if (unit < numUnits) { uint32_t ra[32]; loadA(unit, ra); storeA(ra); }
         for (; unit < numUnits; unit += gridDim.x) {
             const uint32_t next = unit + gridDim.x;
-            if (next < numUnits) fetchA(next);                                    // in flight during this unit's epilogues
             const uint32_t mT = unit / f.groups, g = unit % f.groups;
             const uint32_t n = mT * BM + q * 32 + lane;
             const bool nIn = n < f.N;
@@ -703,49 +705,51 @@ out_fwd_kernel(const FArgs f, const __grid_constant__ CUtensorMap mapHi, const _
             float colSum = 0.0f;
             for (uint32_t bt = bt0; bt < bt1; bt++, seq++) {
                 const uint32_t acc = seq & 1;
-                // this thread's two target words of the tile (32 batch rows each), requested before the accumulator is waited for
-                const uint32_t w0 = (bt * BN + h * 64) >> 5;
-                const uint32_t bits0 = (nIn && w0 < f.wordsB) ? __ldg(f.bitsT + (size_t)n * f.wordsB + w0) : 0u;
-                const uint32_t bits1 = (nIn && w0 + 1 < f.wordsB) ? __ldg(f.bitsT + (size_t)n * f.wordsB + w0 + 1) : 0u;
-                __syncwarp();
-                mbar_wait(&accFull[acc], (seq >> 1) & 1);
-                tc_fence_after();
-                if (bt + 1 == bt1 && next < numUnits) storeA();                   // every MMA of this unit has retired: A may be replaced
-#pragma unroll 1
-                for (int c = 0; c < 2; c++) {
-                    float v[32];
-                    __syncwarp();                                                 // lanes diverge below (ragged edges): re-converge for the .aligned load
-                    tmem_ld32(tmem + laneBase + F_ACC0 + acc * BN + h * 64 + c * 32, v);
-                    if (c == 1) {                                                 // this warp's half of the accumulator is in registers
-                        tc_fence_before();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&accEmpty[acc]);
-                    }
-                    const uint32_t b0 = bt * BN + h * 64 + c * 32;
-                    if (!nIn || b0 >= f.batch) continue;
-                    const uint32_t bits = c ? bits1 : bits0;                  // the host guarantees batch % 32 == 0: all 32 rows exist
-                    float* o = f.delta + (size_t)b0 * f.ldd + n;
-                    float l0 = 0.0f, l1 = 0.0f;
-#pragma unroll
-                    for (int hh = 0; hh < 2; hh++) {
-                        float x[16], d[16];
-#pragma unroll
-                        for (int j = 0; j < 16; j++) {
-                            const float wd = HASW ? __ldg(f.rowW + b0 + 16 * hh + j) : 1.0f;
-                            out_elem_flat<EF, FAST>(f, v[16 * hh + j] + bias, (bits >> (16 * hh + j)) & 1u, wd, (j & 1) ? l1 : l0, x[j], d[j]);
-                        }
-#pragma unroll
-                        for (int j = 0; j < 16; j++) { *o = d[j]; o += f.ldd; colSum += d[j]; }
-                        if (f.unit) {
-                            float* u = f.unit + (size_t)(b0 + 16 * hh) * f.ldd + n;
-#pragma unroll
-                            for (int j = 0; j < 16; j++) { *u = x[j]; u += f.ldd; }
-                        }
-                    }
-                    loss += l0 + l1;
+                const uint32_t b0 = bt * BN + part * 32;
+                // this thread's target word of the tile (32 batch rows), requested before the accumulator is waited for
+                const uint32_t bits = (nIn && b0 < f.batch) ? __ldg(f.bitsT + (size_t)n * f.wordsB + (b0 >> 5)) : 0u;
+                if (bt + 1 == bt1 && next < numUnits) {
+                    // last tile of the unit: fetch the next unit's slice while the tensor core finishes, store it as soon as every MMA that
+                    // reads the current slice has retired
+                    uint32_t ra[32];
+                    loadA(next, ra);
+                    __syncwarp();
+                    mbar_wait(&accFull[acc], (seq >> 1) & 1);
+                    tc_fence_after();
+                    storeA(ra);
+                } else {
+                    __syncwarp();
+                    mbar_wait(&accFull[acc], (seq >> 1) & 1);
+                    tc_fence_after();
                 }
+                float v[32];
+                __syncwarp();
+                tmem_ld32(tmem + laneBase + F_ACC0 + acc * BN + part * 32, v);
+                tc_fence_before();                                            // this warp's quarter of the accumulator is in registers
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&accEmpty[acc]);
+                if (!nIn || b0 >= f.batch) continue;                          // the host guarantees batch % 32 == 0: all 32 rows exist
+                float* o = f.delta + (size_t)b0 * f.ldd + n;
+                float l0 = 0.0f, l1 = 0.0f;
+#pragma unroll
+                for (int hh = 0; hh < 2; hh++) {
+                    float x[16], d[16];
+#pragma unroll
+                    for (int j = 0; j < 16; j++) {
+                        const float wd = HASW ? __ldg(f.rowW + b0 + 16 * hh + j) : 1.0f;
+                        out_elem_flat<EF, FAST>(f, v[16 * hh + j] + bias, (bits >> (16 * hh + j)) & 1u, wd, (j & 1) ? l1 : l0, x[j], d[j]);
+                    }
+#pragma unroll
+                    for (int j = 0; j < 16; j++) { *o = d[j]; o += f.ldd; colSum += d[j]; }
+                    if (f.unit) {
+                        float* u = f.unit + (size_t)(b0 + 16 * hh) * f.ldd + n;
+#pragma unroll
+                        for (int j = 0; j < 16; j++) { *u = x[j]; u += f.ldd; }
+                    }
+                }
+                loss += l0 + l1;
             }
-            if (f.colPartials && nIn) f.colPartials[(size_t)(g * 2 + h) * f.N + n] = colSum;
+            if (f.colPartials && nIn) f.colPartials[(size_t)(g * F_PARTS + part) * f.N + n] = colSum;
         }
         if (f.acc) {
             const double e = warp_sum((double)loss);
@@ -1141,7 +1145,7 @@ int gemm_stream_out_fwd(dsb200_ctx* ctx, const dsb200_sparse* s, int ef, uint32_
     if (!make_map(&mh, X, batch, k, k) || !make_map(&ml, xLo, batch, k, k)) return fail(ctx, DSB200_ESTATE, "gemm_stream_out_fwd: cuTensorMapEncodeTiled failed");
     (void)rowBytes;
     f.bitsT = bitsT; f.rowW = rowW; f.acc = acc; f.colPartials = pColPartials;
-    if (pNumPartials) *pNumPartials = f.groups * 2;
+    if (pNumPartials) *pNumPartials = f.groups * F_PARTS;
     f.zeroTarget = ctx->params.SMCE_zeroTarget; f.oneTarget = ctx->params.SMCE_oneTarget;
     f.zeroScale = ctx->params.SMCE_zeroScale; f.oneScale = ctx->params.SMCE_oneScale;
     f.boostZero = ctx->params.deltaBoost_zero; f.boostOne = ctx->params.deltaBoost_one;

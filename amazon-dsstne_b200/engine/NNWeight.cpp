@@ -197,10 +197,10 @@ void NNWeight::UpdateWeights(TrainingMode mode, uint32_t batch, NNFloat alpha, N
                                         _pbBiasGradientVelocity ? _pbBiasGradientVelocity->_pDevData : NULL, _pbBias->_pDevData), "dsb200_update_biases");
 }
 
-// [2 * ceil(batch / 128)][local bias size] floats for dsb200_gemm_fwd_output_pass
+// [4 * ceil(batch / 128)][local bias size] floats for dsb200_gemm_fwd_output_pass
 NNFloat* NNWeight::BiasPartialsBuffer(uint32_t batch)
 {
-    const uint64_t need = (uint64_t)2 * ((batch + 127) / 128) * _localBiasSize;
+    const uint64_t need = (uint64_t)4 * ((batch + 127) / 128) * _localBiasSize;
     if (!_pbBiasPartials || _pbBiasPartials->_length < need) _pbBiasPartials.reset(new GpuBuffer<NNFloat>(need));
     return _pbBiasPartials->_pDevData;
 }

@@ -206,7 +206,7 @@ int dsb200_output_pass(dsb200_ctx*, const dsb200_sparse* s, int errorFunction, i
  * the activations are written or re-read (pUnitOut, optional, receives the activations).  A [batch][k], W [k][n], bias [n].
  * Sigmoid with L2 / CrossEntropy / ScaledMarginalCrossEntropy over Boolean targets, k <= 128, a tensor-core gemm_mode: any other
  * combination returns DSB200_EUNSUPPORTED and the caller makes the two calls (dsb200_gemm_fwd_bias_act, dsb200_output_pass).
- * pColumnSumPartials (optional, device, capacity 2 * ceil(batch / 128) * n floats) receives *pNumPartials rows of [n] partial
+ * pColumnSumPartials (optional, device, capacity 4 * ceil(batch / 128) * n floats) receives *pNumPartials rows of [n] partial
  * column sums of delta -- the bias gradient of E/NNWeight.cpp:760-794 -- for dsb200_update_biases_partials.                       */
 int dsb200_gemm_fwd_output_pass(dsb200_ctx*, const dsb200_sparse* s, int errorFunction, int activation, uint32_t position, uint32_t batch,
                                 uint32_t k, uint32_t n, const float* A, const float* W, const float* pBias, float* pUnitOut, float* pDelta,

@@ -158,7 +158,7 @@ def test_forward_gemm_with_fused_output_pass(ctx, dsb, ef, want_unit, B, k, n):
         unit1 = torch.empty_like(z) if want_unit else None
         delta1 = torch.full_like(z, float("nan"))
         acc1 = torch.zeros(1, dtype=torch.int64, device="cuda")
-        parts = torch.full((2 * ((B + 127) // 128), n), float("nan"), device="cuda")
+        parts = torch.full((4 * ((B + 127) // 128), n), float("nan"), device="cuda")
         n_parts = ctx.gemm_fwd_output_pass(ds, ef, dsb.ACT_SIGMOID, 0, A, W, bias, unit1, delta1, acc1, parts)
         b0 = bias.clone(); b1 = bias.clone()
         v0 = torch.zeros(n, device="cuda"); v1 = torch.zeros(n, device="cuda")

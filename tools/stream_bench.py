@@ -38,7 +38,7 @@ def main():
     z, delta = torch.empty(B, n, device="cuda"), torch.empty(B, n, device="cuda")
     G = torch.empty(k, n, device="cuda")
     Dp = torch.empty(B, k, device="cuda")
-    parts = torch.empty(2 * ((B + 127) // 128), n, device="cuda")
+    parts = torch.empty(4 * ((B + 127) // 128), n, device="cuda")
     acc = torch.zeros(1, dtype=torch.int64, device="cuda")
     ctx.set_params(smce=(1.0, 0.0, 1.0, 1.0))
     ctx.set_option("gemm_mode", 2)

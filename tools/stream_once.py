@@ -13,7 +13,7 @@ A = torch.rand(B, k, device="cuda", generator=g); W = torch.randn(k, n, device="
 bias = torch.randn(n, device="cuda", generator=g) * 0.5 - 2.0
 ds = to_device(dsb, ml20m(examples=B, width=n))
 delta = torch.empty(B, n, device="cuda"); G = torch.zeros(k, n, device="cuda"); Dp = torch.zeros(B, k, device="cuda")
-parts = torch.empty(2 * ((B + 127) // 128), n, device="cuda")
+parts = torch.empty(4 * ((B + 127) // 128), n, device="cuda")
 acc = torch.zeros(1, dtype=torch.int64, device="cuda")
 ctx.set_params(smce=(1.0, 0.0, 1.0, 1.0))
 for _ in range(int(sys.argv[1]) if len(sys.argv) > 1 else 3):
