@@ -46,7 +46,8 @@ struct dsb200_ctx {
     int            transposeSort = 1;             // emit ascending rows inside each transposed column
     void*          comm        = nullptr;         // ncclComm_t when model parallel
     int            rank = 0, nranks = 1;
-    void*          cublas      = nullptr;         // cublasHandle_t (fp32 GEMM fallback / reference arm)
+    void*          dDenseWs    = nullptr;         // dense_small.cu: arrival counters + segment partials of the batch-split weight gradient
+    size_t         denseWsBytes = 0, denseWsTiles = 0;
     int            gemmMode    = 0;
     int            gemmDebug   = 0;               // bring-up switches of gemm_tc.cu (option "gemm_debug")
     int            noSmallDense = 0;              // option "no_small_dense": keep small dense layers on the library SGEMM

@@ -90,6 +90,7 @@ int dsb200_ctx_destroy(dsb200_ctx* ctx)
     cudaFree(ctx->dRowCounters);
     cudaFree(ctx->dPartials);
     cudaFree(ctx->dGemmWs);
+    cudaFree(ctx->dDenseWs);
     cudaFree(ctx->dHeavy);
     cudaFree(ctx->dHeavy3);
     cudaFree(ctx->dGsWs);

@@ -6,33 +6,18 @@
 //   dw : G[k][n]  = beta*G  + alpha * A[B][k]^T * D[B][n]
 //   dx : Dp[B][k] = beta*Dp + D[B][n] * W[k][n]^T
 // Modes (option "gemm_mode"):
-//   DSB200_GEMM_FP32    cuBLAS SGEMM, pedantic fp32 (what the reference runs; parity baseline)
-//   DSB200_GEMM_TF32    hand-written tcgen05 kernel (gemm_tc.cu), one tf32 MMA per k-step (~1e-3 relative)
-//   DSB200_GEMM_TF32X3  the same kernel with the 3xTF32 split (fp32-grade, bound in tests/test_gpu_gemm.py)
-// The library call is the PLAIN GEMM case the task allows cuBLAS for.
+//   DSB200_GEMM_FP32    exact fp32 FMA arithmetic on the SIMT kernel of dense_small.cu (what the reference's SGEMM computes; parity baseline)
+//   DSB200_GEMM_TF32    hand-written tcgen05 kernels (gemm_tc.cu, gemm_stream.cu), one tf32 MMA per k-step (~1e-3 relative)
+//   DSB200_GEMM_TF32X3  the same kernels with the 3xTF32 split (fp32-grade, bound in tests/test_gpu_gemm.py)
+// No library GEMM: shapes too small for the tensor-core kernels run on the SIMT kernel in every mode.
 #include "common.cuh"
 #include "launch.h"
 
-#include <cublas_v2.h>
-
 namespace dsb {
-
-static int cublas_of(dsb200_ctx* ctx, cublasHandle_t* out)
-{
-    if (!ctx->cublas) {
-        cublasHandle_t h;
-        if (cublasCreate(&h) != CUBLAS_STATUS_SUCCESS) return fail(ctx, DSB200_ESTATE, "cublasCreate failed");
-        ctx->cublas = h;
-    }
-    cublasHandle_t h = (cublasHandle_t)ctx->cublas;
-    if (cublasSetStream(h, ctx->stream) != CUBLAS_STATUS_SUCCESS) return fail(ctx, DSB200_ESTATE, "cublasSetStream failed");
-    cublasSetMathMode(h, CUBLAS_PEDANTIC_MATH);
-    *out = h;
-    return 0;
-}
 
 // gemm_stream.cu: output-layer shapes (one dimension = the hidden width) on the TMA + tensor-memory kernels
 bool gemm_stream_available();
+int gemm_stream_debug_counters(unsigned long long* out, size_t count);
 int gemm_stream_dw(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, float alpha, const float* X, const float* D, uint32_t ldd, float beta,
                    float* G, uint32_t ldg);
 int gemm_stream_dx(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, const float* D, uint32_t ldd, const float* W, uint32_t ldw, float beta,
@@ -53,6 +38,9 @@ int gemm_tc_launch(dsb200_ctx* ctx, const float* A, int aMN, uint32_t lda, const
 // latency bound and stays on the plain library SGEMM, which is also the exact-fp32 path.  Option "gemm_tc_min_tiles".
 int dense_small_fwd(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, const float* A, const float* W, const float* bias, int act, float* C,
                     float slope, float alpha, float lambda);
+// exact-fp32 SIMT GEMM (dense_small.cu): form 0 A*B, 1 A*B^T, 2 A^T*B
+int dense_gemm(dsb200_ctx* ctx, int form, uint32_t M, uint32_t N, uint32_t K, float alpha, const float* A, uint32_t lda, const float* B, uint32_t ldb,
+               float beta, float* C, uint32_t ldc);
 
 static inline bool use_tc(const dsb200_ctx* ctx, uint64_t M, uint64_t N, uint64_t K)
 {
@@ -68,10 +56,7 @@ static inline bool use_stream(const dsb200_ctx* ctx, uint64_t B, uint64_t k, uin
     return ctx->gemmStream && k <= 256 && n >= 512 && B >= 1 && gemm_stream_available();
 }
 
-void gemm_release(dsb200_ctx* ctx)
-{
-    if (ctx && ctx->cublas) { cublasDestroy((cublasHandle_t)ctx->cublas); ctx->cublas = nullptr; }
-}
+void gemm_release(dsb200_ctx*) {}
 
 }  // namespace dsb
 
@@ -84,12 +69,7 @@ int dsb200_gemm_fwd(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, const f
     if (!B || !k || !n) return 0;
     DSB_PROFILE(ctx, use_tc(ctx, B, n, k) ? "gemm_fwd_tc" : "gemm_fwd");
     if (use_tc(ctx, B, n, k)) return gemm_tc_launch(ctx, A, 0, k, W, 1, n, C, n, B, n, k, 1.0f, beta, nullptr, DSB200_ACT_LINEAR, 0.f, 0.f, 0.f);
-    cublasHandle_t h; int rc = cublas_of(ctx, &h); if (rc) return rc;
-    const float one = 1.0f;
-    // row-major C = A*W  <=>  column-major C^T = W^T * A^T (E/NNLayer.cpp:1072-1086)
-    if (cublasSgemm(h, CUBLAS_OP_N, CUBLAS_OP_N, (int)n, (int)B, (int)k, &one, W, (int)n, A, (int)k, &beta, C, (int)n) != CUBLAS_STATUS_SUCCESS)
-        return fail(ctx, DSB200_ESTATE, "gemm_fwd: SGEMM failure");
-    return 0;
+    return dense_gemm(ctx, 0, B, n, k, 1.0f, A, k, W, n, beta, C, n);                                  // E/NNLayer.cpp:1072-1086
 }
 
 int dsb200_gemm_dw(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, float alpha, const float* A, const float* D, float beta, float* G)
@@ -103,11 +83,7 @@ int dsb200_gemm_dw(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, float al
     }
     DSB_PROFILE(ctx, use_tc(ctx, k, n, B) ? "gemm_dw_tc" : "gemm_dw");
     if (use_tc(ctx, k, n, B)) return gemm_tc_launch(ctx, A, 1, k, D, 1, n, G, n, k, n, B, alpha, beta, nullptr, DSB200_ACT_LINEAR, 0.f, 0.f, 0.f);
-    cublasHandle_t h; int rc = cublas_of(ctx, &h); if (rc) return rc;
-    // G^T (n x k) = D^T (n x B) * A (B x k)   (E/NNLayer.cpp:2223-2236)
-    if (cublasSgemm(h, CUBLAS_OP_N, CUBLAS_OP_T, (int)n, (int)k, (int)B, &alpha, D, (int)n, A, (int)k, &beta, G, (int)n) != CUBLAS_STATUS_SUCCESS)
-        return fail(ctx, DSB200_ESTATE, "gemm_dw: SGEMM failure");
-    return 0;
+    return dense_gemm(ctx, 2, k, n, B, alpha, A, k, D, n, beta, G, n);                                 // E/NNLayer.cpp:2223-2236
 }
 
 int dsb200_gemm_dx(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, const float* D, const float* W, float beta, float* Dp)
@@ -121,12 +97,7 @@ int dsb200_gemm_dx(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, const fl
     }
     DSB_PROFILE(ctx, use_tc(ctx, B, k, n) ? "gemm_dx_tc" : "gemm_dx");
     if (use_tc(ctx, B, k, n)) return gemm_tc_launch(ctx, D, 0, n, W, 0, n, Dp, k, B, k, n, 1.0f, beta, nullptr, DSB200_ACT_LINEAR, 0.f, 0.f, 0.f);
-    cublasHandle_t h; int rc = cublas_of(ctx, &h); if (rc) return rc;
-    const float one = 1.0f;
-    // Dp^T (k x B) = W (k x n) * D^T (n x B)   (E/NNLayer.cpp:2274-2287)
-    if (cublasSgemm(h, CUBLAS_OP_T, CUBLAS_OP_N, (int)k, (int)B, (int)n, &one, W, (int)n, D, (int)n, &beta, Dp, (int)k) != CUBLAS_STATUS_SUCCESS)
-        return fail(ctx, DSB200_ESTATE, "gemm_dx: SGEMM failure");
-    return 0;
+    return dense_gemm(ctx, 1, B, k, n, 1.0f, D, n, W, n, beta, Dp, k);                                 // E/NNLayer.cpp:2274-2287
 }
 
 /* fused input delta: Dp = (D * W^T) (.) f'(pUnit) * scale -- cublasSgemm (E/NNLayer.cpp:2274) + kCalculateHadamardProduct of the layer
@@ -218,3 +189,10 @@ int dsb200_gemm_fwd_output_pass(dsb200_ctx* ctx, const dsb200_sparse* s, int err
 }
 
 }  // extern "C"
+
+extern "C" int dsb200_debug_counters(dsb200_ctx* ctx, unsigned long long* out, size_t count)
+{
+    if (!ctx || !out) return DSB200_EINVAL;
+    DSB_CUDA_OK(cudaDeviceSynchronize());
+    return dsb::gemm_stream_debug_counters(out, count);
+}

@@ -576,6 +576,11 @@ transpose_split_kernel(const float* __restrict__ X, uint32_t ldx, uint32_t rows,
 //   its 32 registers never coexist with the epilogue's (the 96-register budget of 18 warps).
 // Warps: 0-15 workers (A load + epilogue), 16 TMA producer, 17 MMA issuer.
 // =====================================================================================================================
+// bring-up cycle counters (gemm_debug & 65536): [CTA][16] clock64 sums, read back with dsb200_debug_counters
+__device__ unsigned long long g_dbgCounters[256 * 16];
+#define DSB_DBG_T0(on) const long long _t0 = (on) ? clock64() : 0
+#define DSB_DBG_ADD(on, var) do { if (on) var += clock64() - _t0; } while (0)
+
 constexpr int F_WORKERS = 16, F_TMA_WARP = 16, F_MMA_WARP = 17, F_THREADS = 18 * 32, F_SLOTS = 6;
 constexpr int F_PARTS = F_WORKERS / 4;           // worker warps per TMEM lane quadrant = column-sum partials per (unit, column)
 constexpr int F_SMEM_BYTES = F_SLOTS * SLOT + 1024;
@@ -592,48 +597,61 @@ struct FArgs {
     unsigned long long* acc;
     float* colPartials;                            // [groups * F_PARTS][N] or NULL
     int passes;
-    float zeroTarget, oneTarget, zeroScale, oneScale, boostZero, boostOne;
+    int debug;                                     // option "gemm_debug" (bring-up, wrong results): 1024 = no MMAs, 2048 = no element math / stores, 8192 = no stores
+    // element coefficients (see out_elem): gate thresholds on p, loss scales and signed delta scales per target value
+    float thrZ, thrNz, lZ, lNz, dZ, dNz;
 };
 
+// The element, WITHOUT control flow and in the fewest instructions (round-2 probe, tools/fwd_probe.py: with the first branch-free form --
+// 33 instructions per element -- the element math alone kept the kernel at 60 us against 40 us for the MMAs alone).
+// With s = +1 at a zero target, -1 at a non-zero one, u = s * z, E = e^u, T = 1 + E, R = 1 / T, p = E * R = sigmoid(u):
+//   x = sigmoid(z)            = p at a zero target, R at a non-zero one
+//   the log the loss needs    = log(1 - x) resp. log(x) = -log(T) either way (the reference clamps its argument at 1e-12: T <= 1e12)
+//   the delta's x resp. x - 1 = s * p
+//   the gate of SMCE          : x > zeroTarget resp. x < oneTarget  <=>  p > thr,  thr = zeroTarget resp. 1 - oneTarget
+// so, with the Raw and NonZero terms of the reference merged (the -wz*log(1-x) of the Raw kernel and the +wd*zeroScale*log(1-x) of the
+// NonZero kernel cancel exactly at a non-zero target):
+//   SMCE  loss += on * sc * wd * log T,  d = on * s * sc * wd * p        sc = zeroScale resp. oneScale
+//   CE    loss += wd * log T,            d = s * boost * wd * p
+//   L2    loss += wd / 2 * p^2,          d = s * boost * wd * p * (p * R)                    (x (1 - x) = p R)
+// One ex2, one rcp, one lg2 per element whatever the target; the target only selects signs and coefficients (f.thr*, f.l*, f.d*).
+// PLAIN = no gate and one loss scale (SMCE with zeroTarget <= 0, oneTarget >= 1, equal scales; CE): the loss is a plain sum of logs,
+// scaled once per tile.  FAST: MUFU ex2 / lg2 / rcp in log2 units (the factor ln 2 is applied to the tile's sum).
+constexpr float kLog2e = 1.4426950408889634f, kLn2 = 0.6931471805599453f;
 __device__ __forceinline__ float rcp_approx(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-// MUFU exp / log without the denormal fix-up sequences of __expf / __logf (their arguments here are never denormal: log sees
-// max(1e-12, .), and an exp that underflows gives sigmoid = 1 either way)
-__device__ __forceinline__ float exp_fast(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x * 1.4426950408889634f)); return r; }
-__device__ __forceinline__ float log_fast(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r * 0.6931471805599453f; }
+__device__ __forceinline__ float ex2_approx(float x) { float r; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+__device__ __forceinline__ float lg2_approx(float x) { float r; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 
-// The hot path: the same values WITHOUT control flow, so that the elements a thread works on interleave and hide the MUFU latency
-// and the unrolled epilogue stays inside the instruction cache (round-2 ncu of the branchy form: 20 % of the stall samples were
-// instruction fetch).  At a non-zero target the reference's Raw and NonZero terms are merged algebraically:
-//   SMCE  zero target: on = x > zeroTarget:  loss -= wz * log(1 - x),        d = wz * x
-//         one  target: on = x < oneTarget:   loss -= wd * oneScale * log(x), d = wd * oneScale * (x - 1)
-//         (the -wz*log(1-x) of the Raw kernel and the +wd*zeroScale*log(1-x) of the NonZero kernel cancel exactly)
-//   CE    loss -= wd * log(nz ? x : 1 - x),  d = wd * (nz ? boostOne * (x - 1) : boostZero * x)
-//   L2    t = nz ? x - 1 : x:  loss += wd/2 * t^2,  d = wd * boost * t * x * (1 - x)
-// so one exp, one reciprocal and one log per element whatever the target.
-template <int EF, bool FAST>
-__device__ __forceinline__ void out_elem_flat(const FArgs& f, float z, bool nz, float wd, float& loss, float& x, float& d)
+template <bool ISL2, bool FAST, bool HASW, bool PLAIN, bool WANTX>
+__device__ __forceinline__ void out_elem(const FArgs& f, float v, float cb, bool nz, float wd, float& loss, float& x, float& d)
 {
-    x = FAST ? rcp_approx(1.0f + exp_fast(-z)) : 1.0f / (1.0f + expf(-z));
-    if (EF == DSB200_ERR_L2) {
-        const float t = nz ? x - 1.0f : x;
-        loss += 0.5f * wd * t * t;
-        d = (nz ? f.boostOne : f.boostZero) * wd * t * x * (1.0f - x);
+    const float t0 = FAST ? fmaf(v, kLog2e, cb) : v + cb;                        // z (FAST: in log2 units, cb = bias * log2 e)
+    const float t = fminf(nz ? -t0 : t0, FAST ? 39.8631371f : 27.6310211f);     // T <= 1e12
+    const float E = FAST ? ex2_approx(t) : expf(t);
+    const float T = 1.0f + E;
+    const float R = FAST ? rcp_approx(T) : 1.0f / T;
+    const float p = E * R;
+    if (WANTX) x = nz ? R : p;
+    if (ISL2) {
+        const float dsc = nz ? f.dNz : f.dZ;
+        loss = fmaf(HASW ? wd * p : p, p, loss);                                 // times 1/2 per tile
+        d = (HASW ? dsc * wd : dsc) * p * (p * R);
     } else {
-        const float arg = fmaxf(kMinError, nz ? x : 1.0f - x);
-        const float lg = FAST ? log_fast(arg) : logf(arg);
-        if (EF == DSB200_ERR_SMCE) {
-            const bool on = nz ? (x < f.oneTarget) : (x > f.zeroTarget);
-            const float sc = (nz ? f.oneScale : f.zeroScale) * wd;
-            loss += on ? -sc * lg : 0.0f;
-            d = on ? sc * (nz ? x - 1.0f : x) : 0.0f;
+        const float L = FAST ? lg2_approx(T) : logf(T);
+        if (PLAIN) {
+            const float dsc = nz ? f.dNz : f.dZ;
+            loss = HASW ? fmaf(wd, L, loss) : loss + L;                          // times lZ (and ln 2) per tile
+            d = (HASW ? dsc * wd : dsc) * p;
         } else {
-            loss += -wd * lg;
-            d = wd * (nz ? f.boostOne * (x - 1.0f) : f.boostZero * x);
+            const bool on = p > (nz ? f.thrNz : f.thrZ);
+            const float lsc = nz ? f.lNz : f.lZ, dsc = nz ? f.dNz : f.dZ;
+            loss = fmaf(on ? (HASW ? lsc * wd : lsc) : 0.0f, L, loss);
+            d = on ? (HASW ? dsc * wd : dsc) * p : 0.0f;
         }
     }
 }
 
-template <int EF, bool FAST, bool HASW>
+template <bool ISL2, bool FAST, bool HASW, bool PLAIN, bool WANTX>
 __global__ void __launch_bounds__(F_THREADS, 1)
 out_fwd_kernel(const FArgs f, const __grid_constant__ CUtensorMap mapHi, const __grid_constant__ CUtensorMap mapLo)
 {
@@ -673,7 +691,7 @@ out_fwd_kernel(const FArgs f, const __grid_constant__ CUtensorMap mapHi, const _
             const float* p = f.W + (size_t)(32 * part) * f.ldw + n;
             const bool nIn = n < f.N;
 #pragma unroll
-            for (int e = 0; e < 32; e++) ra[e] = (nIn && 32 * part + e < f.K) ? ldg_nc_u32(p + (size_t)e * f.ldw) : 0u;
+            for (int e = 0; e < 32; e++) ra[e] = (nIn && 32 * part + e < f.K && !(f.debug & 32768)) ? ldg_nc_u32(p + (size_t)e * f.ldw) : 0u;
         };
         auto storeA = [&](const uint32_t (&ra)[32]) {
 #pragma unroll
@@ -694,13 +712,17 @@ out_fwd_kernel(const FArgs f, const __grid_constant__ CUtensorMap mapHi, const _
             if (lane == 0) mbar_arrive(&aReady);
         };
         uint32_t unit = blockIdx.x;
+        const bool dbgOn = (f.debug & 65536) != 0;
+        long long cTotal = 0, cWaitAcc = 0, cLd = 0, cMath = 0, cA = 0;
+        const long long tStart = dbgOn ? clock64() : 0;
         if (unit < numUnits) { uint32_t ra[32]; loadA(unit, ra); storeA(ra); }
+        if (dbgOn) cA += clock64() - tStart;
         for (; unit < numUnits; unit += gridDim.x) {
             const uint32_t next = unit + gridDim.x;
             const uint32_t mT = unit / f.groups, g = unit % f.groups;
             const uint32_t n = mT * BM + q * 32 + lane;
             const bool nIn = n < f.N;
-            const float bias = (nIn && f.bias) ? __ldg(f.bias + n) : 0.0f;
+            const float cb = ((nIn && f.bias) ? __ldg(f.bias + n) : 0.0f) * (FAST ? kLog2e : 1.0f);
             const uint32_t bt0 = g * f.tilesPerGroup, bt1 = min(f.tilesB, bt0 + f.tilesPerGroup);
             float colSum = 0.0f;
             for (uint32_t bt = bt0; bt < bt1; bt++, seq++) {
@@ -712,24 +734,28 @@ out_fwd_kernel(const FArgs f, const __grid_constant__ CUtensorMap mapHi, const _
                     // last tile of the unit: fetch the next unit's slice while the tensor core finishes, store it as soon as every MMA that
                     // reads the current slice has retired
                     uint32_t ra[32];
-                    loadA(next, ra);
+                    { DSB_DBG_T0(dbgOn); loadA(next, ra); DSB_DBG_ADD(dbgOn, cA); }
                     __syncwarp();
-                    mbar_wait(&accFull[acc], (seq >> 1) & 1);
+                    { DSB_DBG_T0(dbgOn); mbar_wait(&accFull[acc], (seq >> 1) & 1); DSB_DBG_ADD(dbgOn, cWaitAcc); }
                     tc_fence_after();
-                    storeA(ra);
+                    { DSB_DBG_T0(dbgOn); storeA(ra); DSB_DBG_ADD(dbgOn, cA); }
                 } else {
                     __syncwarp();
-                    mbar_wait(&accFull[acc], (seq >> 1) & 1);
+                    { DSB_DBG_T0(dbgOn); mbar_wait(&accFull[acc], (seq >> 1) & 1); DSB_DBG_ADD(dbgOn, cWaitAcc); }
                     tc_fence_after();
                 }
                 float v[32];
                 __syncwarp();
+                { DSB_DBG_T0(dbgOn);
                 tmem_ld32(tmem + laneBase + F_ACC0 + acc * BN + part * 32, v);
                 tc_fence_before();                                            // this warp's quarter of the accumulator is in registers
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&accEmpty[acc]);
-                if (!nIn || b0 >= f.batch) continue;                          // the host guarantees batch % 32 == 0: all 32 rows exist
+                DSB_DBG_ADD(dbgOn, cLd); }
+                if (!nIn || b0 >= f.batch || (f.debug & 2048)) continue;      // the host guarantees batch % 32 == 0: all 32 rows exist
+                DSB_DBG_T0(dbgOn);
                 float* o = f.delta + (size_t)b0 * f.ldd + n;
+                float* u = WANTX ? f.unit + (size_t)b0 * f.ldd + n : nullptr;
                 float l0 = 0.0f, l1 = 0.0f;
 #pragma unroll
                 for (int hh = 0; hh < 2; hh++) {
@@ -737,23 +763,28 @@ out_fwd_kernel(const FArgs f, const __grid_constant__ CUtensorMap mapHi, const _
 #pragma unroll
                     for (int j = 0; j < 16; j++) {
                         const float wd = HASW ? __ldg(f.rowW + b0 + 16 * hh + j) : 1.0f;
-                        out_elem_flat<EF, FAST>(f, v[16 * hh + j] + bias, (bits >> (16 * hh + j)) & 1u, wd, (j & 1) ? l1 : l0, x[j], d[j]);
+                        out_elem<ISL2, FAST, HASW, PLAIN, WANTX>(f, v[16 * hh + j], cb, (bits >> (16 * hh + j)) & 1u, wd, (j & 1) ? l1 : l0, x[j], d[j]);
                     }
 #pragma unroll
-                    for (int j = 0; j < 16; j++) { *o = d[j]; o += f.ldd; colSum += d[j]; }
-                    if (f.unit) {
-                        float* u = f.unit + (size_t)(b0 + 16 * hh) * f.ldd + n;
+                    for (int j = 0; j < 16; j++) { if (!(f.debug & 8192)) *o = d[j]; o += f.ldd; colSum += d[j]; }
+                    if (WANTX) {
 #pragma unroll
                         for (int j = 0; j < 16; j++) { *u = x[j]; u += f.ldd; }
                     }
                 }
-                loss += l0 + l1;
+                loss += (l0 + l1) * ((ISL2 ? 0.5f : (PLAIN ? f.lZ : 1.0f)) * ((FAST && !ISL2) ? kLn2 : 1.0f));
+                DSB_DBG_ADD(dbgOn, cMath);
             }
             if (f.colPartials && nIn) f.colPartials[(size_t)(g * F_PARTS + part) * f.N + n] = colSum;
         }
         if (f.acc) {
             const double e = warp_sum((double)loss);
             if (lane == 0 && e != 0.0) atomicAdd(f.acc, (unsigned long long)llrint(e * (double)kErrorScaleF));
+        }
+        if (dbgOn && (warp == 0 || warp == 15) && lane == 0 && blockIdx.x < 256) {
+            unsigned long long* o = g_dbgCounters + blockIdx.x * 16 + (warp == 0 ? 0 : 5);
+            cTotal = clock64() - tStart;
+            o[0] = cTotal; o[1] = cWaitAcc; o[2] = cLd; o[3] = cMath; o[4] = cA;
         }
     } else if (warp == F_TMA_WARP) {
         // ------------------------------------------------------------ B producer
@@ -766,9 +797,12 @@ out_fwd_kernel(const FArgs f, const __grid_constant__ CUtensorMap mapHi, const _
                     for (uint32_t kt = 0; kt < numK; kt++) {
                         mbar_wait(&bEmpty[slot], parity);
                         const uint32_t st = ringAddr + slot * SLOT;
+                        if (f.debug & 16384) { mbar_arrive(&bFull[slot]); }       // bring-up switch 16384: no TMA loads
+                        else {
                         mbar_arrive_expect_tx(&bFull[slot], lo ? SLOT : PANEL);
                         tma_load_2d(st, &mapHi, kt * BK, bt * BN, &bFull[slot]);
                         if (lo) tma_load_2d(st + PANEL, &mapLo, kt * BK, bt * BN, &bFull[slot]);
+                        }
                         if (++slot == F_SLOTS) { slot = 0; parity ^= 1; }
                     }
             }
@@ -777,24 +811,29 @@ out_fwd_kernel(const FArgs f, const __grid_constant__ CUtensorMap mapHi, const _
         // ------------------------------------------------------------ MMA issuer
         if (lane == 0) {
             uint32_t slot = 0, ph = 0, seq = 0, ui = 0;
+            const bool dbgOn = (f.debug & 65536) != 0;
+            long long cWaitA = 0, cWaitAcc = 0, cWaitB = 0, cIssue = 0;
+            const long long tStart = dbgOn ? clock64() : 0;
             for (uint32_t unit = blockIdx.x; unit < numUnits; unit += gridDim.x, ui++) {
                 const uint32_t g = unit % f.groups;
                 const uint32_t bt0 = g * f.tilesPerGroup, bt1 = min(f.tilesB, bt0 + f.tilesPerGroup);
-                mbar_wait(&aReady, ui & 1);                                       // this unit's W^T slice is in tensor memory
+                { DSB_DBG_T0(dbgOn); mbar_wait(&aReady, ui & 1); DSB_DBG_ADD(dbgOn, cWaitA); }   // this unit's W^T slice is in tensor memory
                 tc_fence_after();
                 for (uint32_t bt = bt0; bt < bt1; bt++, seq++) {
                     const uint32_t acc = seq & 1, d = tmem + F_ACC0 + acc * BN;
-                    mbar_wait(&accEmpty[acc], ((seq >> 1) & 1) ^ 1);
+                    { DSB_DBG_T0(dbgOn); mbar_wait(&accEmpty[acc], ((seq >> 1) & 1) ^ 1); DSB_DBG_ADD(dbgOn, cWaitAcc); }
                     tc_fence_after();
                     for (uint32_t kt = 0; kt < numK; kt++) {
-                        mbar_wait(&bFull[slot], ph);
+                        { DSB_DBG_T0(dbgOn); mbar_wait(&bFull[slot], ph); DSB_DBG_ADD(dbgOn, cWaitB); }
                         tc_fence_after();
+                        DSB_DBG_T0(dbgOn);
                         const uint32_t sb = ringAddr + slot * SLOT;
 #pragma unroll
                         for (int j = 0; j < BK / 8; j++) {
                             const uint64_t bHi = kmajor_desc(sb, j);
                             const uint32_t aHi = tmem + kt * BK + j * 8, first = (kt == 0 && j == 0) ? 0u : 1u;
-                            if (lo) {
+                            if (f.debug & 1024) {
+                            } else if (lo) {
                                 const uint64_t bLo = kmajor_desc(sb + PANEL, j);
                                 mma_tf32_ts(d, aHi + F_A_LO, bHi, kIdesc, first); // small terms first
                                 mma_tf32_ts(d, aHi, bLo, kIdesc, 1u);
@@ -804,10 +843,15 @@ out_fwd_kernel(const FArgs f, const __grid_constant__ CUtensorMap mapHi, const _
                             }
                         }
                         tc_commit(&bEmpty[slot]);
+                        DSB_DBG_ADD(dbgOn, cIssue);
                         if (++slot == F_SLOTS) { slot = 0; ph ^= 1; }
                     }
                     tc_commit(&accFull[acc]);
                 }
+            }
+            if (dbgOn && blockIdx.x < 256) {
+                unsigned long long* o = g_dbgCounters + blockIdx.x * 16 + 10;
+                o[0] = clock64() - tStart; o[1] = cWaitA; o[2] = cWaitAcc; o[3] = cWaitB; o[4] = cIssue;
             }
         }
     }
@@ -922,6 +966,10 @@ static int prep_reserve(dsb200_ctx* ctx, dsb200_ctx::Prep& p, size_t bytes)
 }
 
 bool gemm_stream_available() { return gs::encode_fn() != nullptr; }
+int gemm_stream_debug_counters(unsigned long long* out, size_t count)
+{
+    return cudaMemcpyFromSymbol(out, gs::g_dbgCounters, std::min<size_t>(count, 256 * 16) * sizeof(unsigned long long)) == cudaSuccess ? 0 : DSB200_ESTATE;
+}
 
 // G[k][n] = beta * G + alpha * X[B][k]^T * D[B][n]      (swapped: M = n, N = k, K = B; A = D read with m contiguous)
 int gemm_stream_dw(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, float alpha, const float* X, const float* D, uint32_t ldd, float beta,
@@ -1090,17 +1138,6 @@ int gemm_stream_out_fwd(dsb200_ctx* ctx, const dsb200_sparse* s, int ef, uint32_
 {
     using namespace gs;
     if (k > 128 || !tma_ok(X, k) || (batch & 31u)) return DSB200_EUNSUPPORTED;
-    static bool attrSet = false;
-    if (!attrSet) {
-#define DSB_ATTR(EF) \
-        DSB_CUDA_OK(cudaFuncSetAttribute(out_fwd_kernel<EF, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_BYTES)); \
-        DSB_CUDA_OK(cudaFuncSetAttribute(out_fwd_kernel<EF, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_BYTES)); \
-        DSB_CUDA_OK(cudaFuncSetAttribute(out_fwd_kernel<EF, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_BYTES)); \
-        DSB_CUDA_OK(cudaFuncSetAttribute(out_fwd_kernel<EF, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_BYTES));
-        DSB_ATTR(DSB200_ERR_SMCE) DSB_ATTR(DSB200_ERR_CROSS_ENTROPY) DSB_ATTR(DSB200_ERR_L2)
-#undef DSB_ATTR
-        attrSet = true;
-    }
     FArgs f{};
     f.W = W; f.ldw = ldw; f.bias = bias; f.N = n; f.K = k; f.batch = batch;
     f.tilesM = (n + BM - 1) / BM; f.tilesB = (batch + BN - 1) / BN;
@@ -1130,6 +1167,7 @@ int gemm_stream_out_fwd(dsb200_ctx* ctx, const dsb200_sparse* s, int ef, uint32_
     const uint32_t ldt = up4(batch);
     const size_t loBytes = al256((size_t)batch * k * sizeof(float)), xtBytes = al256((size_t)k * ldt * sizeof(float));
     f.passes = (ctx->gemmMode == DSB200_GEMM_TF32) ? 1 : 3;
+    f.debug = ctx->gemmDebug;
     int rc = prep_reserve(ctx, ctx->prepX, loBytes + 2 * xtBytes);
     if (rc) return rc;
     float* xLo = reinterpret_cast<float*>(ctx->prepX.buf);
@@ -1146,21 +1184,36 @@ int gemm_stream_out_fwd(dsb200_ctx* ctx, const dsb200_sparse* s, int ef, uint32_
     (void)rowBytes;
     f.bitsT = bitsT; f.rowW = rowW; f.acc = acc; f.colPartials = pColPartials;
     if (pNumPartials) *pNumPartials = f.groups * F_PARTS;
-    f.zeroTarget = ctx->params.SMCE_zeroTarget; f.oneTarget = ctx->params.SMCE_oneTarget;
-    f.zeroScale = ctx->params.SMCE_zeroScale; f.oneScale = ctx->params.SMCE_oneScale;
-    f.boostZero = ctx->params.deltaBoost_zero; f.boostOne = ctx->params.deltaBoost_one;
+    // element coefficients (out_elem)
+    const dsb200_params& P = ctx->params;
+    bool plain = true;
+    if (ef == DSB200_ERR_SMCE) {
+        f.thrZ = P.SMCE_zeroTarget; f.thrNz = 1.0f - P.SMCE_oneTarget;
+        f.lZ = P.SMCE_zeroScale; f.lNz = P.SMCE_oneScale; f.dZ = P.SMCE_zeroScale; f.dNz = -P.SMCE_oneScale;
+        plain = P.SMCE_zeroTarget <= 0.0f && P.SMCE_oneTarget >= 1.0f && P.SMCE_zeroScale == P.SMCE_oneScale;   // p = 0 contributes nothing either way
+    } else {
+        f.thrZ = f.thrNz = -1.0f; f.lZ = f.lNz = 1.0f; f.dZ = P.deltaBoost_zero; f.dNz = -P.deltaBoost_one;
+    }
     const uint32_t grid = std::min<uint32_t>((uint32_t)ctx->numSMs, f.tilesM * f.groups);
-#define DSB_GO(EF)                                                                                                       \
-    do {                                                                                                                 \
-        if (ctx->fastMath) { if (rowW) out_fwd_kernel<EF, true, true><<<grid, F_THREADS, F_SMEM_BYTES, ctx->stream>>>(f, mh, ml);    \
-                             else      out_fwd_kernel<EF, true, false><<<grid, F_THREADS, F_SMEM_BYTES, ctx->stream>>>(f, mh, ml); } \
-        else               { if (rowW) out_fwd_kernel<EF, false, true><<<grid, F_THREADS, F_SMEM_BYTES, ctx->stream>>>(f, mh, ml);   \
-                             else      out_fwd_kernel<EF, false, false><<<grid, F_THREADS, F_SMEM_BYTES, ctx->stream>>>(f, mh, ml); }\
-    } while (0)
-    if (ef == DSB200_ERR_SMCE) DSB_GO(DSB200_ERR_SMCE);
-    else if (ef == DSB200_ERR_CROSS_ENTROPY) DSB_GO(DSB200_ERR_CROSS_ENTROPY);
-    else DSB_GO(DSB200_ERR_L2);
-#undef DSB_GO
+    typedef void (*Kern)(const FArgs, const CUtensorMap, const CUtensorMap);
+    static const Kern table[24] = {
+#define DSB_K4(L2, FAST, HASW) out_fwd_kernel<L2, FAST, HASW, false, false>, out_fwd_kernel<L2, FAST, HASW, false, true>, \
+                               out_fwd_kernel<L2, FAST, HASW, true, false>, out_fwd_kernel<L2, FAST, HASW, true, true>
+        DSB_K4(false, false, false), DSB_K4(false, false, true), DSB_K4(false, true, false), DSB_K4(false, true, true),
+        // L2 has no gate: only its PLAIN instances exist
+        out_fwd_kernel<true, false, false, true, false>, out_fwd_kernel<true, false, false, true, true>, out_fwd_kernel<true, false, true, true, false>,
+        out_fwd_kernel<true, false, true, true, true>, out_fwd_kernel<true, true, false, true, false>, out_fwd_kernel<true, true, false, true, true>,
+        out_fwd_kernel<true, true, true, true, false>, out_fwd_kernel<true, true, true, true, true>
+#undef DSB_K4
+    };
+    static bool attrSet = false;
+    if (!attrSet) {
+        for (int i = 0; i < 24; i++) DSB_CUDA_OK(cudaFuncSetAttribute(table[i], cudaFuncAttributeMaxDynamicSharedMemorySize, F_SMEM_BYTES));
+        attrSet = true;
+    }
+    const int fast = ctx->fastMath ? 1 : 0, hasw = rowW ? 1 : 0, wantx = unitOut ? 1 : 0;
+    const Kern kern = (ef == DSB200_ERR_L2) ? table[16 + fast * 4 + hasw * 2 + wantx] : table[fast * 8 + hasw * 4 + (plain ? 2 : 0) + wantx];
+    kern<<<grid, F_THREADS, F_SMEM_BYTES, ctx->stream>>>(f, mh, ml);
     DSB_CUDA_OK(cudaGetLastError());
     count_launch();
     return 0;

@@ -118,6 +118,9 @@ uint64_t dsb200_launch_count(void);      /* kernels of this library launched so 
 /* with option "profile" = 1 every kernel entry is bracketed by CUDA events on the stream; this call
  * synchronises and writes one line per family, "name calls total_ms\n", then clears the records */
 int  dsb200_profile_report(dsb200_ctx* ctx, char* buf, size_t cap);
+/* bring-up: the clock64 counters the kernels of csrc/gemm_stream.cu leave behind under "gemm_debug" & 65536 ([CTA][16] cycle sums,
+ * layout in tools/fwd_probe.py); synchronises the device */
+int  dsb200_debug_counters(dsb200_ctx* ctx, unsigned long long* out, size_t count);
 
 /* ------------------------------------------------------------------ a14
  * kClearUnit / kAddBias, E/kernels.h:30,26 (E/kernels.cu:60-80, 564-584)          */
