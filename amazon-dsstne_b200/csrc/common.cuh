@@ -99,6 +99,14 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p)
     return (uint32_t)__cvta_generic_to_shared(p);
 }
 
+// Programmatic dependent launch (launch.h: launch_pdl): the kernels of the training step's main stream are launched with
+// programmatic stream serialization, so the NEXT kernel's CTAs are dispatched -- launch latency, parameter loads, barrier / tensor
+// memory set-up -- while this one still runs.  pdl_launch_dependents() early: lets that dispatch start once every CTA of this grid
+// has got here.  pdl_wait() before the first access to global memory that an earlier kernel may have written, and before any write:
+// returns when the preceding grids have completed and flushed.  Both are no-ops in a normally launched kernel.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 // example lookup shared by every kernel on the path (shuffle, then Indexed):
 //   E/kernels.cu:670 and :751
 __device__ __forceinline__ uint32_t example_of(const dsb200_params& P, const uint32_t* __restrict__ exIndex,

@@ -13,6 +13,7 @@
 namespace dsb {
 
 static std::atomic<uint64_t> g_launches{0};
+int g_pdl = 1;                                      // option "pdl": programmatic dependent launch of the main-stream kernels (launch.h)
 void count_launch(uint64_t n) { g_launches.fetch_add(n, std::memory_order_relaxed); }
 
 int fail(dsb200_ctx* ctx, int code, const char* what)
@@ -152,6 +153,7 @@ int dsb200_ctx_set_option(dsb200_ctx* ctx, const char* name, int value)
     if (!strcmp(name, "wgrad_light_blocks")) { ctx->wgradLightBlocks = value; return 0; }
     if (!strcmp(name, "gemm_tc_min_work")) { ctx->gemmTcMinWork = value; return 0; }
     if (!strcmp(name, "gemm_debug")) { ctx->gemmDebug = value; return 0; }
+    if (!strcmp(name, "pdl")) { dsb::g_pdl = value ? 1 : 0; return 0; }
     if (!strcmp(name, "gemm_stream")) { ctx->gemmStream = value; return 0; }
     if (!strcmp(name, "wgrad_two_kernel")) { ctx->wgradTwoKernel = value; return 0; }
     if (!strcmp(name, "wgrad_max_entries")) { ctx->wgradMaxEntries = (uint32_t)value; return 0; }

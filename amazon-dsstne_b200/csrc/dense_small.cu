@@ -105,6 +105,8 @@ dense_kernel(const Args a, const OptArgs ow, const OptArgs ob)
     float* sA = sB + SB_FLOATS;                                                // NN / NT: [32 r][PA] (k contiguous);  TN: [32 k][32 r]
     const uint32_t m0 = blockIdx.x * TM, n0 = blockIdx.y * TN, seg = blockIdx.z;
     const uint32_t sBaddr = smem_u32(sB), sAaddr = smem_u32(sA);
+    pdl_launch_dependents();
+    pdl_wait();
 
     // whole-tile facts that decide between 16-byte asynchronous copies and guarded scalar loads
     const bool colsIn = n0 + TN <= a.N;
@@ -370,7 +372,7 @@ static int launch(dsb200_ctx* ctx, Args& a, const OptArgs& ow, const OptArgs& ob
         }
     }
     dim3 grid(rowBlocks, colTiles, a.segs);
-    dense_kernel<FORM, EPI, MODE><<<grid, THREADS, 0, ctx->stream>>>(a, ow, ob);
+    DSB_CUDA_OK(launch_pdl(dense_kernel<FORM, EPI, MODE>, grid, dim3(THREADS), 0, ctx->stream, a, ow, ob));
     count_launch();
     DSB_CUDA_OK(cudaGetLastError());
     return 0;

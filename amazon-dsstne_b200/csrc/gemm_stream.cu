@@ -309,6 +309,8 @@ stream_kernel(const SArgs a, const __grid_constant__ CUtensorMap mapHi, const __
     }
     if (warp == S_TMA_WARP && lane == 0) { tma_prefetch_desc(&mapHi); tma_prefetch_desc(&mapLo); }
     if (warp == S_MMA_WARP) tmem_alloc(&tmemBase, TMEM_COLS);
+    pdl_launch_dependents();
+    pdl_wait();                                                                   // barriers, tensor memory and descriptors are set up under the previous kernel's tail
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -455,9 +457,14 @@ stream_kernel(const SArgs a, const __grid_constant__ CUtensorMap mapHi, const __
                     if (EPI == 0) {
                         float* o = a.C + (size_t)nb * a.ldc + m;
                         if (a.beta != 0.0f) {
+                            // all 16 loads first: written as o[j] = f(o[j]) the compiler must assume that the rows alias and runs 16
+                            // dependent round trips to L2 (measured: 121 us instead of 80 for the config-2 weight gradient with beta = 1)
+                            float old[16];
+#pragma unroll
+                            for (int j = 0; j < 16; j++) old[j] = (uint32_t)j < ncol ? __ldcg(o + (size_t)j * a.ldc) : 0.0f;
 #pragma unroll
                             for (int j = 0; j < 16; j++)
-                                if ((uint32_t)j < ncol) o[(size_t)j * a.ldc] = a.alpha * v[j] + a.beta * o[(size_t)j * a.ldc];
+                                if ((uint32_t)j < ncol) o[(size_t)j * a.ldc] = fmaf(a.beta, old[j], a.alpha * v[j]);
                         } else {
 #pragma unroll
                             for (int j = 0; j < 16; j++)
@@ -507,6 +514,8 @@ stream_reduce_kernel(const float* __restrict__ partial, uint32_t splits, uint32_
                      const HadArgs h)
 {
     const size_t total = (size_t)M * N;
+    pdl_launch_dependents();
+    pdl_wait();
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
         const uint32_t m = (uint32_t)(i / N), n = (uint32_t)(i % N);
         float s = 0.f;
@@ -673,6 +682,8 @@ out_fwd_kernel(const FArgs f, const __grid_constant__ CUtensorMap mapHi, const _
     }
     if (warp == F_TMA_WARP && lane == 0) { tma_prefetch_desc(&mapHi); tma_prefetch_desc(&mapLo); }
     if (warp == F_MMA_WARP) tmem_alloc(&tmemBase, TMEM_COLS);
+    pdl_launch_dependents();
+    pdl_wait();                                                                   // barriers, tensor memory and descriptors are set up under the previous kernel's tail
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -868,6 +879,8 @@ prep_x_kernel(const float* __restrict__ X, uint32_t rows, uint32_t cols, float* 
     __shared__ float tile[32][33];
     const uint32_t tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
     const uint32_t tilesC = (cols + 31) / 32, tilesR = (ldt + 31) / 32;
+    pdl_launch_dependents();
+    pdl_wait();
     for (uint32_t t = blockIdx.x; t < tilesC * tilesR; t += gridDim.x) {
         const uint32_t r0 = (t / tilesC) * 32, c0 = (t % tilesC) * 32;
 #pragma unroll
@@ -1007,7 +1020,7 @@ int gemm_stream_dw(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, float al
     a.passes = (ctx->gemmMode == DSB200_GEMM_TF32) ? 1 : 3;
     a.debug = ctx->gemmDebug;
     const uint32_t grid = std::min<uint32_t>((uint32_t)ctx->numSMs, a.tilesM * a.tilesN);
-    stream_kernel<0, 0><<<grid, S_THREADS, S_SMEM_BYTES, ctx->stream>>>(a, mh, ml);
+    DSB_CUDA_OK(launch_pdl(stream_kernel<0, 0>, dim3(grid), dim3(S_THREADS), S_SMEM_BYTES, ctx->stream, a, mh, ml));
     DSB_CUDA_OK(cudaGetLastError());
     count_launch();
     return 0;
@@ -1074,14 +1087,14 @@ int gemm_stream_dx(dsb200_ctx* ctx, uint32_t B, uint32_t k, uint32_t n, const fl
     a.passes = (ctx->gemmMode == DSB200_GEMM_TF32) ? 1 : 3;
     a.debug = ctx->gemmDebug;
     const uint32_t grid = std::min<uint32_t>(sms, tilesMN * splits);
-    stream_kernel<1, 1><<<grid, S_THREADS, S_SMEM_BYTES, ctx->stream>>>(a, mh, ml);
+    DSB_CUDA_OK(launch_pdl(stream_kernel<1, 1>, dim3(grid), dim3(S_THREADS), S_SMEM_BYTES, ctx->stream, a, mh, ml));
     DSB_CUDA_OK(cudaGetLastError());
     count_launch();
     if (splits > 1) {
         const size_t total = (size_t)B * k;
         const uint32_t blocks = (uint32_t)std::min<size_t>((total + 255) / 256, (size_t)ctx->numSMs * 8);
         HadArgs h{hadUnit, hadAct, hadScale, slope, ealpha, lambda};
-        stream_reduce_kernel<<<blocks, 256, 0, ctx->stream>>>(a.partial, splits, B, k, ldp, 1.0f, beta, Dp, h);
+        DSB_CUDA_OK(launch_pdl(stream_reduce_kernel, dim3(blocks), dim3(256), 0, ctx->stream, (const float*)a.partial, splits, B, k, ldp, 1.0f, beta, Dp, h));
         DSB_CUDA_OK(cudaGetLastError());
         count_launch();
     } else if (hadUnit) {
@@ -1174,8 +1187,8 @@ int gemm_stream_out_fwd(dsb200_ctx* ctx, const dsb200_sparse* s, int ef, uint32_
     {
         uint8_t* pb = reinterpret_cast<uint8_t*>(ctx->prepX.buf) + loBytes;
         const uint32_t tiles = ((k + 31) / 32) * ((ldt + 31) / 32);
-        prep_x_kernel<<<std::min<uint32_t>(tiles, (uint32_t)ctx->numSMs * 8), 256, 0, ctx->stream>>>(X, batch, k, xLo, reinterpret_cast<float*>(pb),
-                                                                                                    reinterpret_cast<float*>(pb + xtBytes), ldt);
+        DSB_CUDA_OK(launch_pdl(prep_x_kernel, dim3(std::min<uint32_t>(tiles, (uint32_t)ctx->numSMs * 8)), dim3(256), 0, ctx->stream, X, batch, k, xLo,
+                               reinterpret_cast<float*>(pb), reinterpret_cast<float*>(pb + xtBytes), ldt));
         count_launch();
         ctx->prepX.key = X; ctx->prepX.a = batch; ctx->prepX.b = k; ctx->prepX.valid = true;
     }
@@ -1213,7 +1226,7 @@ int gemm_stream_out_fwd(dsb200_ctx* ctx, const dsb200_sparse* s, int ef, uint32_
     }
     const int fast = ctx->fastMath ? 1 : 0, hasw = rowW ? 1 : 0, wantx = unitOut ? 1 : 0;
     const Kern kern = (ef == DSB200_ERR_L2) ? table[16 + fast * 4 + hasw * 2 + wantx] : table[fast * 8 + hasw * 4 + (plain ? 2 : 0) + wantx];
-    kern<<<grid, F_THREADS, F_SMEM_BYTES, ctx->stream>>>(f, mh, ml);
+    DSB_CUDA_OK(launch_pdl(kern, dim3(grid), dim3(F_THREADS), F_SMEM_BYTES, ctx->stream, f, mh, ml));
     DSB_CUDA_OK(cudaGetLastError());
     count_launch();
     return 0;

@@ -30,3 +30,24 @@ struct ProfileScope {
 // the same with a size tag: reported as "name@tag", so that call sites of one family with different operand sizes (the
 // output layer's 27,278 biases and a hidden layer's 128) are timed apart
 #define DSB_PROFILE_T(ctx, name, tag) dsb::ProfileScope _dsb_prof_scope((ctx), (name), (unsigned long long)(tag))
+
+// ---- programmatic dependent launch (see pdl_wait in common.cuh).  Every kernel launched through this helper executes
+// griddepcontrol.wait before it touches global memory, which keeps the chain transitive: a kernel that has passed its wait knows that
+// every earlier kernel of the stream has completed.  Option "pdl" = 0 falls back to plain launches.
+#ifdef __CUDACC__
+#include <utility>
+namespace dsb {
+extern int g_pdl;
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t stream, Args&&... args)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr; cfg.numAttrs = g_pdl ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kernel, std::forward<Args>(args)...);
+}
+}
+#endif

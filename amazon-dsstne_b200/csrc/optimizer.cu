@@ -20,6 +20,8 @@ update_weights_kernel(const OptArgs o, uint64_t size, float* __restrict__ v, con
 {
     const uint64_t tid = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x;
     const uint64_t nth = (uint64_t)gridDim.x * blockDim.x;
+    pdl_launch_dependents();
+    pdl_wait();
     if (vec) {
         const uint64_t n4 = size >> 2;
         for (uint64_t i = tid; i < n4; i += nth) {
@@ -62,6 +64,8 @@ update_biases_kernel(const OptArgs o, uint32_t batch, uint32_t width, const floa
     __shared__ float sPart[8][33];
     __shared__ uint32_t sLast;
     const uint32_t lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    pdl_launch_dependents();
+    pdl_wait();
     const uint32_t c = blockIdx.x * 32 + lane;
     const uint32_t R = gridDim.y, ry = blockIdx.y;
     const uint32_t r0 = (uint32_t)(((uint64_t)batch * ry) / R), r1 = (uint32_t)(((uint64_t)batch * (ry + 1)) / R);
@@ -140,7 +144,7 @@ static int launch_weights(dsb200_ctx* ctx, const OptArgs& o, uint64_t size, floa
     const uint64_t cap = (uint64_t)ctx->numSMs * 16;
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
-    update_weights_kernel<MODE><<<(unsigned)blocks, 256, 0, ctx->stream>>>(o, size, v, g, gv, w, vec);
+    DSB_CUDA_OK(launch_pdl(update_weights_kernel<MODE>, dim3((unsigned)blocks), dim3(256), 0, ctx->stream, o, size, v, g, gv, w, vec));
     count_launch();
     DSB_CUDA_OK(cudaGetLastError());
     return 0;
@@ -163,10 +167,8 @@ static int launch_biases(dsb200_ctx* ctx, const OptArgs& o, uint32_t batch, uint
         if (rc) return rc;
     }
     dim3 grid(tiles, R);
-    update_biases_kernel<MODE><<<grid, 256, 0, ctx->stream>>>(o, batch, width, delta, v, gv, bias,
-                                                              ctx->dPartials, ctx->dRowCounters);
+    DSB_CUDA_OK(launch_pdl(update_biases_kernel<MODE>, grid, dim3(256), 0, ctx->stream, o, batch, width, delta, v, gv, bias, ctx->dPartials, ctx->dRowCounters));
     count_launch();
-    DSB_CUDA_OK(cudaGetLastError());
     return 0;
 }
 
@@ -178,6 +180,8 @@ update_biases_partials_kernel(const OptArgs o, uint32_t batch, uint32_t width, c
                               float* __restrict__ v, float* __restrict__ gv, float* __restrict__ bias)
 {
     const uint32_t c = blockIdx.x * blockDim.x + threadIdx.x;
+    pdl_launch_dependents();
+    pdl_wait();
     if (c >= width) return;
     float tot = 0.0f;
     for (uint32_t y = 0; y < nPartials; y++) tot += __ldg(partials + (size_t)y * width + c);
@@ -192,7 +196,7 @@ template <int MODE>
 static int launch_biases_partials(dsb200_ctx* ctx, const OptArgs& o, uint32_t batch, uint32_t width, const float* partials, uint32_t nPartials,
                                   float* v, float* gv, float* bias)
 {
-    update_biases_partials_kernel<MODE><<<(width + 255) / 256, 256, 0, ctx->stream>>>(o, batch, width, partials, nPartials, v, gv, bias);
+    DSB_CUDA_OK(launch_pdl(update_biases_partials_kernel<MODE>, dim3((width + 255) / 256), dim3(256), 0, ctx->stream, o, batch, width, partials, nPartials, v, gv, bias));
     count_launch();
     DSB_CUDA_OK(cudaGetLastError());
     return 0;

@@ -467,6 +467,8 @@ struct UArgs {
 __global__ void __launch_bounds__(256)
 wgrad_classify_kernel(uint32_t m, const uint32_t* __restrict__ tStart, const uint32_t* __restrict__ tEnd, const UArgs u)
 {
+    pdl_launch_dependents();
+    pdl_wait();
     for (uint32_t c = blockIdx.x * blockDim.x + threadIdx.x; c < m; c += gridDim.x * blockDim.x) {
         const uint32_t s = __ldg(tStart + c), e = __ldg(tEnd + c);
         if (e - s <= kHeavy2) continue;
@@ -552,6 +554,8 @@ sparse_wgrad_unified_kernel(const GArgs a, const UArgs u)
 {
     const uint32_t lane = threadIdx.x & 31;
     const uint32_t gw = (blockIdx.x * kGThreads + threadIdx.x) >> 5, nw = (gridDim.x * kGThreads) >> 5;
+    pdl_launch_dependents();
+    pdl_wait();
     // ---- heavy columns, 32 entries per item
     const uint32_t nItems = min(*u.itemCount, u.maxItems);
     for (uint32_t it = gw; it < nItems; it += nw) {
@@ -633,7 +637,7 @@ static int launch_wgrad3(dsb200_ctx* ctx, const GArgs& a, uint32_t maxEntries)
     u.arrived = reinterpret_cast<uint32_t*>(p);
     u.maxItems = maxItems; u.maxSlots = maxSlots;
     DSB_CUDA_OK(cudaMemsetAsync(u.itemCount, 0, 8, ctx->stream));
-    wgrad_classify_kernel<<<std::min<uint32_t>((a.m + 255) / 256, (uint32_t)ctx->numSMs * 4), 256, 0, ctx->stream>>>(a.m, a.tStart, a.tEnd, u);
+    DSB_CUDA_OK(launch_pdl(wgrad_classify_kernel, dim3(std::min<uint32_t>((a.m + 255) / 256, (uint32_t)ctx->numSMs * 4)), dim3(256), 0, ctx->stream, a.m, a.tStart, a.tEnd, u));
     count_launch();
     static int blocksPerSM = 0;                                               // per instantiation
     if (!blocksPerSM) {
@@ -648,7 +652,7 @@ static int launch_wgrad3(dsb200_ctx* ctx, const GArgs& a, uint32_t maxEntries)
     const uint32_t warps = kGThreads / 32;
     if ((uint32_t)grid > (a.m + warps - 1) / warps) grid = (int)((a.m + warps - 1) / warps);
     if (grid < 1) grid = 1;
-    sparse_wgrad_unified_kernel<ANALOG, FUSED_MODE><<<grid, kGThreads, 0, ctx->stream>>>(a, u);
+    DSB_CUDA_OK(launch_pdl(sparse_wgrad_unified_kernel<ANALOG, FUSED_MODE>, dim3(grid), dim3(kGThreads), 0, ctx->stream, a, u));
     count_launch();
     DSB_CUDA_OK(cudaGetLastError());
     return 0;

@@ -368,6 +368,8 @@ sparse_z_warp_kernel(const ZArgs a)
     __shared__ ZWSmem sm;
     const int tid = threadIdx.x;
     const uint32_t batch = a.batch, lane = tid & 31;
+    pdl_launch_dependents();
+    pdl_wait();
 
     // ---- plan: chunk counts per row -> exclusive prefix (identical in every CTA); larger chunks if the split-row
     // workspace would overflow
@@ -523,7 +525,7 @@ static int launch_zw(dsb200_ctx* ctx, const ZArgs& a)
     const uint32_t want = (a.batch * 3u + 7u) / 8u;                        // ~3 items per row at the ML-20M row lengths
     if ((uint32_t)grid > want) grid = (int)want;
     if (grid < 1) grid = 1;
-    sparse_z_warp_kernel<ANALOG, DENOISED><<<grid, kZWThreads, 0, ctx->stream>>>(a);
+    DSB_CUDA_OK(launch_pdl(sparse_z_warp_kernel<ANALOG, DENOISED>, dim3(grid), dim3(kZWThreads), 0, ctx->stream, a));
     count_launch();
     DSB_CUDA_OK(cudaGetLastError());
     return 0;

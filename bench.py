@@ -160,6 +160,7 @@ def run_ours(args, wl, rank, world, local_rank):
     engine.set_stream(stream.cuda_stream)
     engine.set_option("p2p_exchange", 1 if args.p2p else 0)
     engine.set_option("fuse_output_gemm", 1 if args.fuse_output else 0)
+    engine.set_option("pdl", 1 if args.pdl else 0)
     if args.gemm_loader >= 0:
         engine.set_option("gemm_loader", args.gemm_loader)
 
@@ -506,13 +507,14 @@ def main():
     ap.add_argument("--warmup", type=int, default=20)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="c2", choices=["c2", "c4"])
-    ap.add_argument("--gemm-mode", type=int, default=2, help="dense GEMMs: 0 cuBLAS fp32, 1 tcgen05 TF32, 2 tcgen05 3xTF32 (fp32-grade)")
+    ap.add_argument("--gemm-mode", type=int, default=2, help="dense GEMMs: 0 exact fp32 (SIMT), 1 tcgen05 TF32, 2 tcgen05 3xTF32 (fp32-grade)")
     ap.add_argument("--gemm-loader", type=int, default=-1, help="operand path of the general tcgen05 kernel (csrc/gemm_tc.cu), -1 = per shape")
     ap.add_argument("--cpu-steps", type=int, default=3)
     ap.add_argument("--side", type=int, default=1, help="1 (default) = after the headline workload also time BASELINE config 4 (1M-item layers) and config 5 (top-K) and add them as \"c4\" / \"c5\" records")
     ap.add_argument("--c4-steps", type=int, default=6)
     ap.add_argument("--fuse-output", type=int, default=1, help="1 (default) = output layer forward GEMM fused with loss + delta (engine option fuse_output_gemm); 0 = two calls")
     ap.add_argument("--pinned-mirror", type=int, default=0, help="e2e path: 1 = LoadSparseData uploads from the page-locked host mirror (experimental single-copy path)")
+    ap.add_argument("--pdl", type=int, default=1, help="1 (default) = programmatic dependent launch of the main-stream kernels (context option pdl)")
     ap.add_argument("--p2p", type=int, default=1, help="N > 1: 1 (default) = exchange steps as one kernel over peer memory each (csrc/comm.cu); 0 = NCCL")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))

@@ -110,6 +110,8 @@ int  dsb200_ctx_reserve(dsb200_ctx* ctx, uint32_t maxBatch, size_t partialFloats
  *   "transpose_sort"     1 = sort every column of the transposed matrix (canonical order for bit-exact comparison)
  *   "fast_math"          1 (default) = MUFU exp / log / reciprocal in the output pass, as the reference (-use_fast_math); 0 = libm grade
  *   "no_tma" / "z_staged_kernel" / "wgrad_tile_kernel" / "output_tile_kernel" / "no_small_dense"   earlier kernels of a family
+ *   "pdl"                1 (default) = the kernels of the training step's main stream are launched with programmatic stream
+ *                        serialization (the next kernel's dispatch and set-up overlap the tail of the running one); 0 = plain launches
  *   "profile"            1 = bracket every entry point with CUDA events (dsb200_profile_report)                              */
 int  dsb200_ctx_set_option(dsb200_ctx* ctx, const char* name, int value);
 int  dsb200_ctx_sync(dsb200_ctx* ctx);
