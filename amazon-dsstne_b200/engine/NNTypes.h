@@ -250,7 +250,7 @@ private:
     void UploadSparseAsync(const uint64_t* srcStart, const uint64_t* srcEnd, const void* srcData, const uint32_t* srcIndex, uint64_t dataLength);
     struct Staging {
         uint64_t* start = nullptr; uint64_t* end = nullptr; uint32_t* index = nullptr; T* data = nullptr;
-        cudaEvent_t done = nullptr; bool pending = false;
+        cudaEvent_t done = nullptr; bool pending = false; size_t capacity = 0;   // capacity: entries of index / data
     } _staging[2];
     int _stagingCur = 0;
     cudaEvent_t _uploadEvent = nullptr;                       // recorded on the copy stream: readers of this step wait for it (WaitForUpload)
