@@ -138,9 +138,13 @@ int main()
         require(key[b * K] == best && val[b * K] == arg, "kCalculateTopK (3-arg)");
         for (uint32_t k = 1; k < K; k++) require(key[b * K + k] <= key[b * K + k - 1], "kCalculateTopK order");
     }
-    kCalculateTopK(dKey2, dValF, dO, dDeltaO, B, N, K);                          // keys = scores, float values = the deltas riding along
+    kCalculateTopK(dO, dDeltaO, dKey2, dValF, B, N, K);                          // E/kernels.h:42: (scores, values riding along) in, (keys, values) out
     std::vector<float> key2 = download(dKey2, B * K), valF = download(dValF, B * K);
-    for (uint32_t b = 0; b < B; b++) require(key2[b * K] == key[b * K] && valF[b * K] == D[b * N + val[b * K]], "kCalculateTopK (4-arg, float values)");
+    for (uint32_t b = 0; b < B; b++) {
+        if (!(key2[b * K] == key[b * K] && valF[b * K] == D[b * N + val[b * K]]))
+            fprintf(stderr, "row %u: key %.9g vs %.9g, value %.9g vs %.9g (column %u)\n", b, key2[b * K], key[b * K], valF[b * K], D[b * N + val[b * K]], val[b * K]);
+        require(key2[b * K] == key[b * K] && valF[b * K] == D[b * N + val[b * K]], "kCalculateTopK (4-arg, float values)");
+    }
     require(dsb200_ctx_sync(ctx) == 0, "dsb200_ctx_sync");
     dsb200_ctx_destroy(ctx);
     printf("shim ok: %d launches through the E/kernels.h names\n", (int)dsb200_launch_count());
