@@ -26,6 +26,7 @@ constexpr uint32_t kKCap     = 4096;            // candidate buffer
 constexpr uint32_t kKChunk   = 1024;            // elements per block step (4 per thread)
 constexpr uint32_t kKMaxSeg  = 131072;          // bitmap = 16 KB
 constexpr uint32_t kKMaxK    = 1024;
+constexpr uint32_t kKHistWords = 520;           // block_select: two histograms + five scratch words
 
 struct KArgs {
     const float* key; const uint32_t* value;       // value == NULL: payload = position
@@ -44,6 +45,19 @@ __device__ __forceinline__ bool before(float ka, uint32_t pa, float kb, uint32_t
 __device__ void block_sort(float* sKey, uint32_t* sPos, uint32_t* sVal, uint32_t n, bool hasVal)
 {
     const uint32_t tid = threadIdx.x;
+    if (n <= (uint32_t)kKThreads) {
+        // the usual case (k = 100): every thread counts the entries that come before its own and moves it there -- two barriers
+        // instead of the 28 of the bitonic network below (barriers, not bytes, bounded this kernel: profiles/r2_notes.md)
+        float key = 0.0f; uint32_t pos = 0, val = 0, rank = 0;
+        if (tid < n) {
+            key = sKey[tid]; pos = sPos[tid]; if (hasVal) val = sVal[tid];
+            for (uint32_t j = 0; j < n; j++) rank += before(sKey[j], sPos[j], key, pos) ? 1u : 0u;
+        }
+        __syncthreads();
+        if (tid < n) { sKey[rank] = key; sPos[rank] = pos; if (hasVal) sVal[rank] = val; }
+        __syncthreads();
+        return;
+    }
     uint32_t p2 = 2; while (p2 < n) p2 <<= 1;
     for (uint32_t i = n + tid; i < p2; i += kKThreads) { sKey[i] = -INFINITY; sPos[i] = 0xffffffffu; if (hasVal) sVal[i] = 0; }
     __syncthreads();
@@ -79,25 +93,44 @@ __device__ __forceinline__ unsigned long long composite(float key, uint32_t pos)
     return ((unsigned long long)u << 32) | (unsigned long long)(0xFFFFFFFFu - pos);
 }
 
-__device__ float block_select(float* sKey, uint32_t* sPos, uint32_t* sVal, uint32_t n, uint32_t k, bool hasVal, uint32_t* sHist /*256 + 4*/,
+__device__ float block_select(float* sKey, uint32_t* sPos, uint32_t* sVal, uint32_t n, uint32_t k, bool hasVal, uint32_t* sHist /*kKHistWords*/,
                               uint32_t* sMove /*2 * k*/)
 {
+    // sHist: two 256-bin histograms used alternately (the next pass's is zeroed while warp 0 scans the current one: two barriers
+    // per pass), then [512] digit, [513] remaining rank, [514] size of the digit's bin, [515] holes, [516] movers
     const uint32_t tid = threadIdx.x;
     unsigned long long prefix = 0, maskHigh = 0;
     uint32_t want = k;
+    for (uint32_t i = tid; i < 256; i += kKThreads) sHist[i] = 0;
+    if (tid == 0) { sHist[515] = 0; sHist[516] = 0; }
+    __syncthreads();
     for (int b = 7; b >= 0; b--) {
-        for (uint32_t i = tid; i < 256; i += kKThreads) sHist[i] = 0;
-        __syncthreads();
-        for (uint32_t i = tid; i < n; i += kKThreads) {
-            const unsigned long long c = composite(sKey[i], sPos[i]);
-            if ((c & maskHigh) == prefix) atomicAdd(&sHist[(uint32_t)(c >> (8 * b)) & 255u], 1u);
+        uint32_t* cur = sHist + (((7 - b) & 1) ? 256 : 0);
+        uint32_t* nxt = sHist + (((7 - b) & 1) ? 0 : 256);
+        // The survivors of a settled threshold share their leading bytes (keys in [0.97, 1) of uniform scores: the top two or three
+        // digits are the same for all of them), and thousands of plain atomics on ONE shared-memory word serialise: a warp whose
+        // live lanes all hold the same digit adds its count with a single atomic.
+        for (uint32_t i0 = 0; i0 < n; i0 += kKThreads) {
+            const uint32_t i = i0 + tid;
+            bool in = false; uint32_t digit = 0;
+            if (i < n) {
+                const unsigned long long c = composite(sKey[i], sPos[i]);
+                in = (c & maskHigh) == prefix;
+                digit = (uint32_t)(c >> (8 * b)) & 255u;
+            }
+            const unsigned act = __ballot_sync(0xffffffffu, in);
+            if (act == 0) continue;
+            const uint32_t d0 = __shfl_sync(0xffffffffu, digit, __ffs(act) - 1);
+            if (__all_sync(0xffffffffu, !in || digit == d0)) {
+                if ((tid & 31u) == (uint32_t)(__ffs(act) - 1)) atomicAdd(&cur[d0], (uint32_t)__popc(act));
+            } else if (in) atomicAdd(&cur[digit], 1u);
         }
         __syncthreads();
         if (tid < 32) {
             // lane l owns digits 255 - 8l .. 248 - 8l (descending); find the digit where the running count reaches `want`
             uint32_t local[8], sum = 0;
 #pragma unroll
-            for (int q = 0; q < 8; q++) { local[q] = sHist[255 - (tid * 8 + q)]; sum += local[q]; }
+            for (int q = 0; q < 8; q++) { local[q] = cur[255 - (tid * 8 + q)]; sum += local[q]; }
             uint32_t incl = sum;
 #pragma unroll
             for (int o = 1; o < 32; o <<= 1) { const uint32_t nb = __shfl_up_sync(0xffffffffu, incl, o); if (tid >= (uint32_t)o) incl += nb; }
@@ -106,33 +139,35 @@ __device__ float block_select(float* sKey, uint32_t* sPos, uint32_t* sVal, uint3
                 uint32_t run = excl;
 #pragma unroll
                 for (int q = 0; q < 8; q++) {
-                    if (run < want && want <= run + local[q]) { sHist[256] = 255 - (tid * 8 + q); sHist[257] = want - run; }
+                    if (run < want && want <= run + local[q]) { sHist[512] = 255 - (tid * 8 + q); sHist[513] = want - run; sHist[514] = local[q]; }
                     run += local[q];
                 }
             }
         }
+        for (uint32_t i = tid; i < 256; i += kKThreads) nxt[i] = 0;               // last read by warp 0 one pass ago, before a barrier
         __syncthreads();
-        prefix |= (unsigned long long)sHist[256] << (8 * b);
+        prefix |= (unsigned long long)sHist[512] << (8 * b);
         maskHigh |= 0xFFull << (8 * b);
-        want = sHist[257];
-        __syncthreads();
+        want = sHist[513];
+        // the digit's whole bin is wanted: the remaining bytes cannot change the selection (with distinct keys: after the key bytes
+        // at the latest -- the position bytes only break ties).  sHist[512..514] are rewritten after the next pass's first barrier.
+        if (want == sHist[514]) break;
     }
-    // prefix = the k-th best composite; exactly k entries are >= prefix
-    if (tid == 0) { sHist[258] = 0; sHist[259] = 0; }
-    __syncthreads();
+    // prefix = the resolved leading bytes of the k-th best composite; exactly k entries have (composite & maskHigh) >= prefix
     for (uint32_t i = tid; i < n; i += kKThreads) {
-        const bool keep = composite(sKey[i], sPos[i]) >= prefix;
-        if (i < k && !keep) sMove[atomicAdd(&sHist[258], 1u)] = i;             // hole
-        if (i >= k && keep) sMove[k + atomicAdd(&sHist[259], 1u)] = i;         // mover
+        const bool keep = (composite(sKey[i], sPos[i]) & maskHigh) >= prefix;
+        if (i < k && !keep) sMove[atomicAdd(&sHist[515], 1u)] = i;             // hole
+        if (i >= k && keep) sMove[k + atomicAdd(&sHist[516], 1u)] = i;         // mover
     }
     __syncthreads();
-    const uint32_t moves = sHist[258];                                          // == sHist[259]
+    const uint32_t moves = sHist[515];                                          // == sHist[516]
     for (uint32_t j = tid; j < moves; j += kKThreads) {
         const uint32_t dst = sMove[j], src = sMove[k + j];
         sKey[dst] = sKey[src]; sPos[dst] = sPos[src];
         if (hasVal) sVal[dst] = sVal[src];
     }
     __syncthreads();
+    // the key of the prefix (unresolved low bytes zero: a lower bound of the k-th key, which is all a threshold has to be)
     uint32_t u = (uint32_t)(prefix >> 32);
     u = (u & 0x80000000u) ? (u & 0x7FFFFFFFu) : ~u;
     return __uint_as_float(u);
@@ -146,10 +181,10 @@ topk_kernel(const KArgs a)
     float*    sKey = reinterpret_cast<float*>(smemRaw);
     uint32_t* sPos = reinterpret_cast<uint32_t*>(sKey + kKCap);
     uint32_t* sVal = sPos + kKCap;                                    // only when HAS_VALUE
-    uint32_t* sHist = HAS_VALUE ? sVal + kKCap : sVal;                // 260 words: radix-select histogram + scratch
-    uint32_t* sMove = sHist + 260;                                    // 2 * k words
+    uint32_t* sHist = HAS_VALUE ? sVal + kKCap : sVal;                // kKHistWords: radix-select histograms + scratch
+    uint32_t* sMove = sHist + kKHistWords;                            // 2 * k words
     uint32_t* sBits = sMove + 2 * a.k;                                // only when HAS_FILTER
-    __shared__ uint32_t sCount;
+    __shared__ uint32_t sCnt[3];          // appended in period p: sCnt[p % 3] (see the barrier in `consume`)
     __shared__ float sThr;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31;
@@ -159,7 +194,7 @@ topk_kernel(const KArgs a)
         const uint32_t c0 = seg * a.segLen, c1 = min(c0 + a.segLen, a.width);
         const float* row = a.key + (size_t)b * a.width;
         const uint32_t* vrow = HAS_VALUE ? a.value + (size_t)b * a.width : nullptr;
-        if (tid == 0) { sCount = 0; sThr = -kMaxValue; }
+        if (tid == 0) { sCnt[0] = 0; sCnt[1] = 0; sCnt[2] = 0; sThr = -kMaxValue; }
         if (HAS_FILTER) {
             const uint32_t words = (c1 - c0 + 31) / 32;
             for (uint32_t i = tid; i < words; i += kKThreads) sBits[i] = 0;
@@ -175,10 +210,11 @@ topk_kernel(const KArgs a)
         // element i of the row is 16-byte aligned in global memory iff (rowBase + i) % 4 == 0
         const uint32_t mis = (uint32_t)((((uintptr_t)row) >> 2) & 3);
         uint32_t budget = kKCap;                                       // free slots guaranteed before next check
+        uint32_t held = 0, period = 0;                                 // entries in the buffer at the start of the period (uniform)
         constexpr int kDepth = 4;                                      // chunks whose loads are issued together
-        for (uint32_t base0 = c0; base0 < c1; base0 += kDepth * kKChunk) {
-            // issue the loads of up to four chunks first: four independent 128-bit loads in flight per thread
-            float kx[kDepth][4];
+        constexpr uint32_t kStep = kDepth * kKChunk;
+        // the loads of a step: four independent 128-bit loads per thread; elements past the segment read as -inf (never candidates)
+        auto fetch = [&](float (&kx)[kDepth][4], uint32_t base0) {
 #pragma unroll
             for (int d = 0; d < kDepth; d++) {
                 const uint32_t p = base0 + d * kKChunk + tid * 4;
@@ -190,61 +226,104 @@ topk_kernel(const KArgs a)
                     for (int v = 0; v < 4; v++) kx[d][v] = (p + v < c1) ? __ldg(row + p + v) : -INFINITY;
                 }
             }
+        };
+        // the exclusion filter on the values of a step (U/Filters.cpp:49-67: score *= 0)
+        auto exclude = [&](float (&kx)[kDepth][4], uint32_t base0) {
+            if (!HAS_FILTER) return;
+#pragma unroll
+            for (int d = 0; d < kDepth; d++) {
+                const uint32_t p = base0 + d * kKChunk + tid * 4;
+                if (p >= c1) break;
+                // c0 and p are multiples of 4: the four exclusion bits of this float4 sit in one bitmap word
+                const uint32_t r = p - c0;
+                const uint32_t bits = (sBits[r >> 5] >> (r & 31)) & 0xFu;
+                if (bits) {
+#pragma unroll
+                    for (int v = 0; v < 4; v++)
+                        if ((bits >> v) & 1u) kx[d][v] *= 0.0f;
+                }
+            }
+        };
+        auto consume = [&](float (&kx)[kDepth][4], uint32_t base0) {
 #pragma unroll
             for (int d = 0; d < kDepth; d++) {
                 const uint32_t base = base0 + d * kKChunk;
                 if (base >= c1) break;
                 if (budget < kKChunk) {
+                    // ONE barrier per check.  The appends of a period go to sCnt[period % 3]; after the barrier nobody adds to that
+                    // counter any more, so every thread reads the same value without a second barrier; thread 0 clears the counter of
+                    // the period after next (last read one barrier ago, first written one barrier from now).
                     __syncthreads();
-                    const uint32_t n = sCount;
-                    if (n > kKCap - kKChunk) {                        // n > k here: cut back to the k best, new threshold = k-th key
-                        const float kth = block_select(sKey, sPos, sVal, n, a.k, HAS_VALUE, sHist, sMove);
-                        if (tid == 0) { sCount = a.k; sThr = kth; }
+                    held += sCnt[period % 3];
+                    period++;
+                    if (tid == 0) sCnt[(period + 1) % 3] = 0;
+                    if (held > kKCap - kKChunk) {                     // held > k here: cut back to the k best, new threshold = k-th key
+                        const float kth = block_select(sKey, sPos, sVal, held, a.k, HAS_VALUE, sHist, sMove);
+                        held = a.k;
+                        if (tid == 0) sThr = kth;
                         __syncthreads();
                     }
-                    budget = kKCap - sCount;
-                    __syncthreads();
+                    budget = kKCap - held;
                 }
                 budget -= kKChunk;
                 const float thr = sThr;
                 const uint32_t p = base + tid * 4;
-                if (HAS_FILTER && p < c1) {
-                    // c0 and p are multiples of 4: the four exclusion bits of this float4 sit in one bitmap word
-                    const uint32_t r = p - c0;
-                    const uint32_t bits = (sBits[r >> 5] >> (r & 31)) & 0xFu;
-                    if (bits) {
-#pragma unroll
-                        for (int v = 0; v < 4; v++)
-                            if ((bits >> v) & 1u) kx[d][v] *= 0.0f;                       // U/Filters.cpp:49-67: score *= 0
-                    }
-                }
-                uint32_t mask = 0;
-#pragma unroll
-                for (int v = 0; v < 4; v++)
-                    if (p + v < c1 && kx[d][v] > thr) mask |= 1u << v;
-                if (!__any_sync(0xffffffffu, mask != 0)) continue;       // common case once the threshold has settled
-                // warp-aggregated append
-                const uint32_t cnt = __popc(mask);
-                uint32_t incl = cnt;
-#pragma unroll
-                for (int o = 1; o < 32; o <<= 1) { const uint32_t nb = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= (uint32_t)o) incl += nb; }
-                const uint32_t total = __shfl_sync(0xffffffffu, incl, 31);
+                // Append by ballots.  With k = 100 the threshold sits at the 97.6th percentile after the first select, so 19 out of 20
+                // warps DO hold a candidate among their 128 elements of a chunk: the append is the common path (round-2 ncu: a prefix
+                // scan by shuffles here was most of the kernel's 1.2 G warp instructions) -- four votes, one atomic, popc offsets.
+                const unsigned b0 = __ballot_sync(0xffffffffu, kx[d][0] > thr), b1 = __ballot_sync(0xffffffffu, kx[d][1] > thr);
+                const unsigned b2 = __ballot_sync(0xffffffffu, kx[d][2] > thr), b3 = __ballot_sync(0xffffffffu, kx[d][3] > thr);
+                const uint32_t n0 = __popc(b0), n1 = n0 + __popc(b1), n2 = n1 + __popc(b2), total = n2 + __popc(b3);
+                if (total == 0) continue;
                 uint32_t wbase = 0;
-                if (lane == 31) wbase = atomicAdd(&sCount, total);
-                wbase = __shfl_sync(0xffffffffu, wbase, 31);
-                uint32_t o = wbase + incl - cnt;
-#pragma unroll
-                for (int v = 0; v < 4; v++) {
-                    if (mask & (1u << v)) {
+                if (lane == 0) wbase = held + atomicAdd(&sCnt[period % 3], total);
+                wbase = __shfl_sync(0xffffffffu, wbase, 0);
+                const unsigned lt = (1u << lane) - 1u;
+                auto put = [&](unsigned bv, uint32_t first, int v) {
+                    if ((bv >> lane) & 1u) {
+                        const uint32_t o = wbase + first + __popc(bv & lt);
                         sKey[o] = kx[d][v]; sPos[o] = p + v;
                         if (HAS_VALUE) sVal[o] = __ldg(vrow + p + v);
-                        o++;
                     }
-                }
+                };
+                put(b0, 0, 0); put(b1, n0, 1); put(b2, n1, 2); put(b3, n2, 3);
             }
+        };
+        // two register sets: the loads of step i + 1 are in flight while step i is compared, appended and -- every fourth chunk --
+        // the block meets at its barriers
+        // A first threshold without a select.  The k-th largest of ANY subset is a lower bound of the tile's k-th key: take the 256
+        // per-thread maxima of the first step (16 values each) and rank them by counting (two barriers).  For uniform scores the
+        // 100th largest of 256 such maxima is the 97.0th percentile, against 97.6 for the exact 100th of those 4,096 values.  The
+        // exact alternative -- filling the buffer with the first 4,096 values and running the radix select on them -- was HALF of
+        // the kernel at the config-5 shape (tools/topk_floor.py: 3.57 ms with that one select per tile, 1.45 ms without any).
+        // Re-ranking running maxima after 4 and 16 steps as well was measured and dropped: each ranking cost more than the smaller
+        // select at the end of the tile saved.
+        float ka[kDepth][4], kb[kDepth][4];
+        fetch(ka, c0);
+        exclude(ka, c0);
+        if (a.k <= (uint32_t)kKThreads) {
+            float mx = -INFINITY;
+#pragma unroll
+            for (int d = 0; d < kDepth; d++)
+#pragma unroll
+                for (int v = 0; v < 4; v++) mx = fmaxf(mx, ka[d][v]);
+            sKey[tid] = mx;                                                    // (the candidate buffer is still empty)
+            __syncthreads();
+            uint32_t rank = 0;
+            for (uint32_t j = 0; j < (uint32_t)kKThreads; j++) { const float o = sKey[j]; rank += (o > mx || (o == mx && j < tid)) ? 1u : 0u; }
+            // candidates must be strictly above the threshold, and an element EQUAL to the bound can still belong to the top k
+            if (rank == a.k - 1 && mx > -kMaxValue) sThr = fmaxf(nextafterf(mx, -INFINITY), -kMaxValue);
+            __syncthreads();
+        }
+        for (uint32_t base0 = c0; base0 < c1; base0 += 2 * kStep) {
+            if (base0 + kStep < c1) { fetch(kb, base0 + kStep); exclude(kb, base0 + kStep); }
+            consume(ka, base0);
+            if (base0 + kStep >= c1) break;
+            if (base0 + 2 * kStep < c1) { fetch(ka, base0 + 2 * kStep); exclude(ka, base0 + 2 * kStep); }
+            consume(kb, base0 + kStep);
         }
         __syncthreads();
-        uint32_t n = sCount;
+        uint32_t n = held + sCnt[period % 3];
         if (n > a.k) { block_select(sKey, sPos, sVal, n, a.k, HAS_VALUE, sHist, sMove); n = a.k; }
         block_sort(sKey, sPos, sVal, n, HAS_VALUE);                       // <= k (<= 1,024) entries
         float* ok = a.outKey + ((size_t)b * a.segs + seg) * a.k;
@@ -291,13 +370,18 @@ static int topk_impl(dsb200_ctx* ctx, const float* key, const uint32_t* value, u
     }
     a.outKey = candKey; a.outValue = candVal;
     const bool hasVal = value != nullptr, hasFilter = fs != nullptr;
-    size_t smem = (size_t)kKCap * 8 + (hasVal ? (size_t)kKCap * 4 : 0) + (260 + 2 * (size_t)k) * 4 + (hasFilter ? (size_t)(segLen / 32 + 1) * 4 : 0);
+    size_t smem = (size_t)kKCap * 8 + (hasVal ? (size_t)kKCap * 4 : 0) + (kKHistWords + 2 * (size_t)k) * 4 + (hasFilter ? (size_t)(segLen / 32 + 1) * 4 : 0);
     uint64_t grid = (uint64_t)batch * segs;
-    const uint64_t cap = (uint64_t)ctx->numSMs * 6;
-    if (grid > cap) grid = cap;
+    uint64_t cap = (uint64_t)ctx->numSMs * 6;
+    // the tile loop is persistent: the grid must be ONE resident wave (a block that starts after the others have finished their share
+    // runs its whole share alone; ncu of round 1's 6 blocks per SM: 1.5 waves) -- as many blocks per SM as this call's shared memory allows
 #define DSB_TOPK(V, F)                                                                                           \
     do {                                                                                                         \
         DSB_CUDA_OK(cudaFuncSetAttribute(topk_kernel<V, F>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem)); \
+        int occ = 0;                                                                                             \
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, topk_kernel<V, F>, kKThreads, smem) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 1; } \
+        cap = (uint64_t)ctx->numSMs * (uint64_t)occ;                                                             \
+        if (grid > cap) grid = cap;                                                                              \
         topk_kernel<V, F><<<(unsigned)grid, kKThreads, smem, ctx->stream>>>(a);                                  \
     } while (0)
     if (hasVal) { if (hasFilter) DSB_TOPK(true, true); else DSB_TOPK(true, false); }
@@ -309,9 +393,15 @@ static int topk_impl(dsb200_ctx* ctx, const float* key, const uint32_t* value, u
         m.key = candKey; m.value = candVal; m.batch = batch; m.width = segs * k; m.k = k; m.segs = 1;
         m.segLen = ((segs * k + kKChunk - 1) / kKChunk) * kKChunk;
         m.outKey = outKey; m.outValue = outValue;
-        smem = (size_t)kKCap * 12 + (260 + 2 * (size_t)k) * 4;
-        grid = batch; if (grid > cap) grid = cap;
+        smem = (size_t)kKCap * 12 + (kKHistWords + 2 * (size_t)k) * 4;
+        grid = batch;
         DSB_CUDA_OK(cudaFuncSetAttribute(topk_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        {
+            int occ = 0;
+            if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, topk_kernel<true, false>, kKThreads, smem) != cudaSuccess || occ < 1) { cudaGetLastError(); occ = 1; }
+            cap = (uint64_t)ctx->numSMs * (uint64_t)occ;
+        }
+        if (grid > cap) grid = cap;
         topk_kernel<true, false><<<(unsigned)grid, kKThreads, smem, ctx->stream>>>(m);
         count_launch();
         DSB_CUDA_OK(cudaGetLastError());
