@@ -74,8 +74,10 @@ def main():
     if topk:
         net.set_position(0)
         net.predict_batch()
-        units = net.get_units("Output")
-        units = np.asarray(units, dtype=np.float32).reshape(batch, -1)
+        # the unit buffer is sized for the LARGEST shard (E/NNLayer.cpp:113, as the reference allocates it): the rank's rows are the
+        # first batch x localStride floats
+        _, local_stride, _, _ = net.layer_info("Output")
+        units = np.asarray(net.get_units("Output"), dtype=np.float32)[:batch * local_stride].reshape(batch, local_stride)
         got_k, got_v = net.topk_global("Output", topk, batch, filt=ds_in)
         parts = [None] * world
         dist.all_gather_object(parts, (units, got_k, got_v))
@@ -84,6 +86,13 @@ def main():
             sl = slice(0, batch)
             want_k, want_v = orc.topk(full, topk, filt=(s_start[sl], s_end[sl], s_index))
             topk_ok = all(np.array_equal(p[1], want_k) and np.array_equal(p[2], want_v) for p in parts)
+            if not topk_ok:                                      # which rank, which row, what differs (shown by the test on failure)
+                for r, p in enumerate(parts):
+                    bad = np.nonzero((p[1] != want_k).any(axis=1) | (p[2] != want_v).any(axis=1))[0]
+                    if bad.size:
+                        b = int(bad[0])
+                        print(f"MP_TOPK_DIFF rank {r}: {bad.size} rows differ; row {b}: got keys {p[1][b][:6]} ids {p[2][b][:6]} want keys {want_k[b][:6]} ids {want_v[b][:6]}",
+                              file=sys.stderr, flush=True)
 
     # re-assemble the sharded weights on rank 0
     shards = []

@@ -241,3 +241,44 @@ def test_topk_at_the_config5_shape(ctx, orc, dsb):
     ref_k, ref_v = orc.topk(sub, K, filt=(start, end, np.concatenate(idx).astype(np.uint32)))
     np.testing.assert_array_equal(keys[rows], ref_k)
     np.testing.assert_array_equal(vals[rows], ref_v)
+
+
+@pytest.mark.parametrize("N", [37, 100, 512, 513, 1025, 4100])
+@pytest.mark.parametrize("K", [1, 20, 100])
+def test_topk_small_and_odd_widths_with_filter(ctx, orc, dsb, N, K):
+    """the widths of a model-parallel shard (2,050 / 4 = 512 | 513 columns, rows not 16-byte aligned) and widths below one chunk or
+    below K, with the exclusion filter: keys and indices bit for bit"""
+    import torch
+    rng = np.random.default_rng(N * 1000 + K)
+    B = 64
+    scores = (1.0 / (1.0 + np.exp(-rng.standard_normal((B, N)) * 2.0))).astype(np.float32)
+    h = tiny(examples=B, width=N, mean=max(1.0, N * 0.02))
+    ref_k, ref_v = orc.topk(scores, K, filt=(h.start, h.end, h.index))
+    dcsr = to_device(dsb, h)
+    ok = torch.empty((B, K), dtype=torch.float32, device="cuda")
+    ov = torch.empty((B, K), dtype=torch.int32, device="cuda")
+    ctx.topk(dev(scores), K, ok, ov, filt=(dcsr.start, dcsr.end, dcsr.index))
+    ctx.sync()
+    np.testing.assert_array_equal(host(ok), ref_k)
+    np.testing.assert_array_equal(u32(ov), ref_v)
+
+
+@pytest.mark.parametrize("P,K", [(4, 20), (8, 100), (2, 7)])
+def test_topk_kv_merge_of_rank_lists(ctx, orc, dsb, P, K):
+    """the merge step of the model-parallel top-K: P sorted lists of K (key, global id) pairs per row, some lists padded with the
+    (-MAX_VALUE, 0) of a short shard"""
+    import torch
+    rng = np.random.default_rng(P * 100 + K)
+    B = 64
+    key = np.sort(rng.random((B, P, K)).astype(np.float32), axis=2)[:, :, ::-1].copy()
+    val = rng.integers(0, 1 << 20, size=(B, P, K)).astype(np.uint32)
+    key[:, P - 1, K // 2:] = -999999999999999.0                            # a shard with fewer than K valid candidates
+    val[:, P - 1, K // 2:] = 0
+    key2, val2 = key.reshape(B, P * K), val.reshape(B, P * K)
+    ref_k, ref_v = orc.topk(key2, K, value=val2)
+    ok = torch.empty((B, K), dtype=torch.float32, device="cuda")
+    ov = torch.empty((B, K), dtype=torch.int32, device="cuda")
+    ctx.topk_kv(dev(key2), torch.from_numpy(val2.view(np.int32).copy()).cuda(), K, ok, ov)
+    ctx.sync()
+    np.testing.assert_array_equal(host(ok), ref_k)
+    np.testing.assert_array_equal(u32(ov), ref_v)
