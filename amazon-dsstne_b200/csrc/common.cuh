@@ -51,7 +51,7 @@ struct dsb200_ctx {
     int            gemmMode    = 0;
     int            gemmDebug   = 0;               // bring-up switches of gemm_tc.cu (option "gemm_debug")
     int            noSmallDense = 0;              // option "no_small_dense": keep small dense layers on the library SGEMM
-    int            gemmTcMinWork = 2048;          // option "gemm_tc_min_work": tiles x k-iterations below which cuBLAS runs
+    int            gemmTcMinWork = 1024;          // option "gemm_tc_min_work": tiles x k-iterations below which the SIMT kernel runs
     int            gemmLoader  = -1;              // option "gemm_loader": -1 / 2 = A through tensor memory, 1 = register-staged loader, 0 = cp.async + split warps
     int            gemmSplits  = 0;               // option "gemm_splits": 0 = automatic split-K factor
     float*         dGemmWs     = nullptr;         // split-K partial tiles of the tcgen05 GEMM

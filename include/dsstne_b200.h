@@ -105,7 +105,7 @@ int  dsb200_ctx_reserve(dsb200_ctx* ctx, uint32_t maxBatch, size_t partialFloats
  *                        shared memory | 2 A operand through tensor memory | 3 the same with a coalesced A loader (experimental)
  *   "gemm_stream"        1 (default) = weight gradient / input delta of layers with a narrow side (<= 256 units) run on the TMA +
  *                        tensor-memory kernels of csrc/gemm_stream.cu; 0 = the general kernel of csrc/gemm_tc.cu for every shape
- *   "gemm_tc_min_work"   tiles x k-iterations below which a GEMM stays off the tensor-core kernel (default 2048)
+ *   "gemm_tc_min_work"   tiles x k-iterations below which a GEMM stays off the tensor-core kernels (default 1024)
  *   "gemm_splits"        split-K factor, 0 = automatic;   "gemm_debug"  bring-up switches of csrc/gemm_tc.cu (wrong results)
  *   "transpose_sort"     1 = sort every column of the transposed matrix (canonical order for bit-exact comparison)
  *   "fast_math"          1 (default) = MUFU exp / log / reciprocal in the output pass, as the reference (-use_fast_math); 0 = libm grade
