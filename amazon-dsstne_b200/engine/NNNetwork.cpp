@@ -72,6 +72,7 @@ NNNetwork::NNNetwork(NNNetworkDescriptor& d, uint32_t batch)
     RTERROR(cudaEventCreateWithFlags(&_forkEvent, cudaEventDisableTiming), "NNNetwork: cudaEventCreate");
     RTERROR(cudaEventCreateWithFlags(&_joinEvent, cudaEventDisableTiming), "NNNetwork: cudaEventCreate");
     RTERROR(cudaEventCreateWithFlags(&_prepEvent, cudaEventDisableTiming), "NNNetwork: cudaEventCreate");
+    RTERROR(cudaEventCreateWithFlags(&_updateEvent, cudaEventDisableTiming), "NNNetwork: cudaEventCreate");
     RTERROR(cudaStreamCreateWithFlags(&_sideStream, cudaStreamNonBlocking), "NNNetwork: cudaStreamCreate");
 }
 
@@ -84,6 +85,7 @@ NNNetwork::~NNNetwork()
     if (_forkEvent) cudaEventDestroy(_forkEvent);
     if (_joinEvent) cudaEventDestroy(_joinEvent);
     if (_prepEvent) cudaEventDestroy(_prepEvent);
+    if (_updateEvent) cudaEventDestroy(_updateEvent);
     if (_sideStream) cudaStreamDestroy(_sideStream);
 }
 
@@ -569,6 +571,34 @@ void NNNetwork::UpdateWeights(NNFloat alpha, NNFloat lambda, NNFloat lambda1, NN
 {
     uint32_t batch = _batch;
     if (_position + batch > _examples) batch = _examples - _position;
+    // The updates of different weights are independent.  With the fusions on, the sparse-input weight's update (gradient + optimizer
+    // in one latency-bound kernel that leaves most issue slots idle) stays on the main stream and every update that touches no
+    // scratch of the context -- one-launch small dense layers, an output weight whose bias gradient came out of the fused forward --
+    // runs beside it on the side stream (round-2 launch list: 37 us of such updates in front of a 37 us sparse update).  The next
+    // step's side-stream work (operand copies of the updated weights, regularisation) is ordered behind them by the stream itself;
+    // the main stream joins before it leaves this function.
+    bool side = false;
+    cudaStream_t s = getGpu().GetStream();
+    dsb200_ctx* ctx = getGpu()._ctx;
+    vector<char> onSide(_vWeight.size(), 0);              // decided up front: the flags behind it are one-shot, cleared by the update itself
+    if (_bFusion && _sideStream) {
+        int nSide = 0, nMain = 0;
+        for (size_t i = 0; i < _vWeight.size(); i++) { onSide[i] = _vWeight[i]->UpdateTouchesNoScratch() ? 1 : 0; if (onSide[i]) nSide++; else nMain++; }
+        side = nSide > 0 && nMain > 0;
+    }
+    if (side) {
+        RTERROR(cudaEventRecord(_forkEvent, s), "UpdateWeights fork");
+        RTERROR(cudaStreamWaitEvent(_sideStream, _forkEvent, 0), "UpdateWeights fork wait");
+        getGpu().Check(dsb200_ctx_set_stream(ctx, _sideStream), "dsb200_ctx_set_stream");
+        for (int64_t i = (int64_t)_vWeight.size() - 1; i >= 0; i--)
+            if (onSide[i]) _vWeight[i]->UpdateWeights(_trainingMode, batch, alpha, lambda, lambda1, mu, mu1, (NNFloat)_batches);
+        RTERROR(cudaEventRecord(_updateEvent, _sideStream), "UpdateWeights side done");
+        getGpu().Check(dsb200_ctx_set_stream(ctx, s), "dsb200_ctx_set_stream");
+        for (int64_t i = (int64_t)_vWeight.size() - 1; i >= 0; i--)
+            if (!onSide[i]) _vWeight[i]->UpdateWeights(_trainingMode, batch, alpha, lambda, lambda1, mu, mu1, (NNFloat)_batches);
+        RTERROR(cudaStreamWaitEvent(s, _updateEvent, 0), "UpdateWeights join");
+        return;
+    }
     for (int64_t i = (int64_t)_vWeight.size() - 1; i >= 0; i--)
         _vWeight[i]->UpdateWeights(_trainingMode, batch, alpha, lambda, lambda1, mu, mu1, (NNFloat)_batches);
 }

@@ -68,6 +68,7 @@ private:
     cudaEvent_t             _errorEvent;
     cudaStream_t            _sideStream;                  // regularisation error runs here, beside the forward pass
     cudaEvent_t             _forkEvent, _joinEvent, _prepEvent;
+    cudaEvent_t             _updateEvent = NULL;          // end of the weight updates that ran on the side stream (UpdateWeights)
     size_t                  _validateMaxSamples = 256;    // Validate(): elements checked per weight matrix / bias vector
     bool                    _bStepReadsRecorded = false;   // TrainStep: LaunchError records GpuContext::_dataConsumedEvent for the streaming loader
     bool                    _bBatchPrepared = false;      // TrainStep launched LoadBatch on the side stream: PredictTrainingBatch must not repeat it

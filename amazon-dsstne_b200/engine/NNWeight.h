@@ -31,6 +31,8 @@ private:
     bool        _bDeferredDenseGradient = false;   // small dense layer: gradient + optimizer + bias update run as ONE kernel in UpdateWeights
     const NNFloat* _pDeferredX = NULL;             // its input units [batch][_height]
     uint32_t    _nBiasPartials;             // > 0: the fused output-layer forward pass left this many rows of column sums of delta
+    // true when UpdateWeights of this weight launches only kernels that use no scratch of the context (safe beside another update)
+    bool UpdateTouchesNoScratch() const { return !_bLocked && !_bDeferredSparseGradient && (_bDeferredDenseGradient || _nBiasPartials > 0); }
     unique_ptr<GpuBuffer<NNFloat>> _pbBiasPartials;
     vector<NNFloat> _vWeight, _vBias;
     unique_ptr<GpuBuffer<NNFloat>> _pbWeight, _pbBias, _pbWeightGradient;
