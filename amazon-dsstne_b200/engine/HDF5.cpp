@@ -1,0 +1,480 @@
+// HDF5.cpp -- reader of netCDF-4 containers, i.e. the HDF5 files netcdf-cxx4 writes by default (the reference's dataset and network
+// files: E/NNTypes.cpp:1081-1418, 2218-2385, E/NNNetwork.cpp:1936-1970, U/NetCDFhelper.cpp:332-416).  Host only, no libhdf5 / libnetcdf.
+//
+// What a DSSTNE file needs from the HDF5 file format (the "HDF5 File Format Specification Version 3.0" names in brackets):
+//   superblock v0 / v1 / v2 / v3                                   [II.A]
+//   object headers v1 and v2 ("OHDR"), continuation blocks         [IV.A.1]
+//   groups: symbol-table groups (B-tree v1 "TREE" + "SNOD" nodes + local heap "HEAP")  [III.A.1, III.B, III.D]
+//           and new-style groups -- link messages in the header (compact) or in a fractal heap (dense)  [IV.A.2.g, IV.A.2.c, III.G]
+//   datasets: dataspace v1 / v2, datatype (fixed point, floating point, fixed-length string), layout v3 / v4 compact and contiguous
+//   attributes v1 / v2 / v3, in the header (compact) or in a fractal heap (dense)  [IV.A.2.m, IV.A.2.v]
+// netCDF-4 on top of it: a dimension is a dataset carrying CLASS = "DIMENSION_SCALE" (a pure dimension when its NAME starts with
+// "This is a netCDF dimension but not a netCDF variable"); every other dataset of the root group is a variable; the root group's
+// attributes are the global attributes; _NCProperties, _Netcdf4Dimid, _Netcdf4Coordinates, DIMENSION_LIST, REFERENCE_LIST, CLASS, NAME
+// and _nc3_strict are bookkeeping and are dropped.
+// Dense storage is read by WALKING the heap's direct blocks (objects are packed from the start of a block in a file that was written
+// once and never edited), not through the v2 B-tree name index.  Not handled, and refused by name: chunked / filtered (compressed)
+// variables, variable-length and compound variable types, sub-groups.  DSSTNE's files have fixed-size 1-D variables: contiguous.
+#include "NetCDF.h"
+
+#include <cstdio>
+#include <cstring>
+#include <functional>
+
+namespace nc {
+namespace hdf5 {
+
+namespace {
+
+const uint64_t UNDEF = ~0ull;
+
+struct Msg { uint32_t type; uint8_t flags; std::vector<uint8_t> data; };
+
+struct Reader {
+    FILE* f;
+    std::string fname;
+    uint64_t base = 0;
+    int so = 8, sl = 8;                                // size of offsets / lengths
+
+    [[noreturn]] void fail(const std::string& what) const { throw Error("netCDF-4 / HDF5: " + fname + ": " + what); }
+
+    std::vector<uint8_t> get(uint64_t off, uint64_t n) const
+    {
+        std::vector<uint8_t> b(n);
+        if (n > (1ull << 31)) fail("implausible metadata block size");
+        if (fseeko(f, (off_t)(base + off), SEEK_SET) != 0) fail("seek failed");
+        if (n && fread(b.data(), 1, n, f) != n) fail("truncated file (metadata at offset " + std::to_string(off) + ")");
+        return b;
+    }
+    static uint64_t le(const uint8_t* p, int n)
+    {
+        uint64_t v = 0;
+        for (int i = n - 1; i >= 0; i--) v = (v << 8) | p[i];
+        return v;
+    }
+    uint64_t addr(const uint8_t* p) const
+    {
+        const uint64_t v = le(p, so);
+        return (so < 8 && v == ((1ull << (8 * so)) - 1)) ? UNDEF : v;
+    }
+
+    // ---- object header -> messages
+    void messages_v1(const std::vector<uint8_t>& blk, uint32_t& left, std::vector<Msg>& out, std::vector<std::pair<uint64_t, uint64_t>>& more) const
+    {
+        size_t p = 0;
+        while (left > 0 && p + 8 <= blk.size()) {
+            Msg m;
+            m.type = (uint32_t)le(&blk[p], 2);
+            const size_t size = (size_t)le(&blk[p + 2], 2);
+            m.flags = blk[p + 4];
+            p += 8;
+            if (p + size > blk.size()) fail("object header message runs past its block");
+            m.data.assign(blk.begin() + p, blk.begin() + p + size);
+            p += size;
+            left--;
+            if (m.type == 0x10 && m.data.size() >= (size_t)(so + sl)) more.push_back({addr(m.data.data()), le(m.data.data() + so, sl)});
+            else out.push_back(m);
+        }
+    }
+    void messages_v2(const uint8_t* p, size_t n, bool order, std::vector<Msg>& out, std::vector<std::pair<uint64_t, uint64_t>>& more) const
+    {
+        size_t q = 0;
+        const size_t hdr = order ? 6 : 4;
+        while (q + hdr <= n) {
+            Msg m;
+            m.type = p[q];
+            const size_t size = (size_t)le(p + q + 1, 2);
+            m.flags = p[q + 3];
+            q += hdr;
+            if (q + size > n) break;                                            // gap at the end of a chunk
+            m.data.assign(p + q, p + q + size);
+            q += size;
+            if (m.type == 0x10 && m.data.size() >= (size_t)(so + sl)) more.push_back({addr(m.data.data()), le(m.data.data() + so, sl)});
+            else if (m.type != 0) out.push_back(m);
+        }
+    }
+    std::vector<Msg> object(uint64_t a) const
+    {
+        std::vector<Msg> out;
+        std::vector<std::pair<uint64_t, uint64_t>> more;
+        const std::vector<uint8_t> h = get(a, 16);
+        if (h[0] == 'O' && h[1] == 'H' && h[2] == 'D' && h[3] == 'R') {
+            if (h[4] != 2) fail("object header version " + std::to_string(h[4]));
+            const uint8_t flags = h[5];
+            size_t p = 6;
+            if (flags & 0x20) p += 16;
+            if (flags & 0x10) p += 4;
+            const int szb = 1 << (flags & 3);
+            const std::vector<uint8_t> pre = get(a, p + szb);
+            const uint64_t chunk0 = le(&pre[p], szb);
+            p += szb;
+            const std::vector<uint8_t> body = get(a + p, chunk0);
+            messages_v2(body.data(), body.size(), (flags & 0x04) != 0, out, more);
+            for (size_t i = 0; i < more.size(); i++) {
+                if (more[i].second < 8) continue;
+                const std::vector<uint8_t> c = get(more[i].first, more[i].second);
+                if (memcmp(c.data(), "OCHK", 4) != 0) fail("object header continuation without the OCHK signature");
+                messages_v2(c.data() + 4, c.size() - 8, (flags & 0x04) != 0, out, more);
+            }
+            return out;
+        }
+        if (h[0] != 1) fail("unknown object header at offset " + std::to_string(a));
+        uint32_t left = (uint32_t)le(&h[2], 2);
+        const uint64_t size = le(&h[8], 4);
+        messages_v1(get(a + 16, size), left, out, more);
+        for (size_t i = 0; i < more.size() && left > 0; i++) messages_v1(get(more[i].first, more[i].second), left, out, more);
+        return out;
+    }
+
+    // ---- groups
+    void links_of_symbol_table(uint64_t btree, uint64_t heap, std::vector<std::pair<std::string, uint64_t>>& out) const
+    {
+        const std::vector<uint8_t> hh = get(heap, 8 + 2 * sl + so);
+        if (memcmp(hh.data(), "HEAP", 4) != 0) fail("local heap signature");
+        const uint64_t dsize = le(&hh[8], sl), daddr = addr(&hh[8 + 2 * sl]);
+        const std::vector<uint8_t> names = get(daddr, dsize);
+        std::function<void(uint64_t)> node = [&](uint64_t a) {
+            const std::vector<uint8_t> t = get(a, 8 + 2 * so);
+            if (memcmp(t.data(), "TREE", 4) != 0) fail("B-tree node signature");
+            if (t[4] != 0) fail("group B-tree node of the wrong type");
+            const int level = t[5];
+            const uint32_t used = (uint32_t)le(&t[6], 2);
+            const std::vector<uint8_t> body = get(a + 8 + 2 * so, (uint64_t)used * (sl + so) + sl);
+            for (uint32_t i = 0; i < used; i++) {
+                const uint64_t child = addr(&body[sl + (size_t)i * (sl + so)]);
+                if (level > 0) { node(child); continue; }
+                const std::vector<uint8_t> s = get(child, 8);
+                if (memcmp(s.data(), "SNOD", 4) != 0) fail("symbol table node signature");
+                const uint32_t n = (uint32_t)le(&s[6], 2);
+                const size_t esz = 2 * so + 24;
+                const std::vector<uint8_t> e = get(child + 8, (uint64_t)n * esz);
+                for (uint32_t k = 0; k < n; k++) {
+                    const uint64_t noff = le(&e[k * esz], so), oh = addr(&e[k * esz + so]);
+                    if (noff >= names.size()) fail("link name outside the local heap");
+                    out.push_back({std::string(reinterpret_cast<const char*>(&names[noff])), oh});
+                }
+            }
+        };
+        node(btree);
+    }
+    // one link message body; returns its length (0: not a link message)
+    size_t link_message(const uint8_t* p, size_t n, std::vector<std::pair<std::string, uint64_t>>& out) const
+    {
+        if (n < 4 || p[0] != 1) return 0;
+        const uint8_t flags = p[1];
+        size_t q = 2;
+        uint8_t type = 0;
+        if (flags & 0x08) type = p[q++];
+        if (flags & 0x04) q += 8;
+        if (flags & 0x10) q += 1;
+        const int lb = 1 << (flags & 3);
+        if (q + lb > n) return 0;
+        const uint64_t len = le(p + q, lb);
+        q += lb;
+        if (q + len > n) return 0;
+        const std::string name(reinterpret_cast<const char*>(p + q), (size_t)len);
+        q += (size_t)len;
+        if (type == 0) {
+            if (q + so > n) return 0;
+            out.push_back({name, addr(p + q)});
+            q += so;
+        } else if (type == 1) {                                                // soft link: length + path
+            if (q + 2 > n) return 0;
+            q += 2 + (size_t)le(p + q, 2);
+        } else return 0;
+        return q;
+    }
+
+    // ---- fractal heap: the payload of every direct block, in heap order
+    void heap_blocks(uint64_t a, std::vector<std::vector<uint8_t>>& out) const
+    {
+        const size_t fixed = 4 + 1 + 2 + 2 + 1 + 4 + sl + so + sl + so + 8 * sl + 2 + 2 * sl + 2 + 2 + so + 2;
+        const std::vector<uint8_t> h = get(a, fixed);
+        if (memcmp(h.data(), "FRHP", 4) != 0) fail("fractal heap signature");
+        size_t p = 5;
+        p += 2;                                                                // heap ID length
+        const uint64_t filterLen = le(&h[p], 2); p += 2;
+        const uint8_t flags = h[p++];
+        p += 4;                                                                // maximum size of managed objects
+        p += sl + so + sl + so + 8 * sl;
+        const uint32_t width = (uint32_t)le(&h[p], 2); p += 2;
+        const uint64_t startSize = le(&h[p], sl); p += sl;
+        const uint64_t maxDirect = le(&h[p], sl); p += sl;
+        const uint32_t maxHeapBits = (uint32_t)le(&h[p], 2); p += 2;
+        p += 2;                                                                // starting # of rows in the root indirect block
+        const uint64_t root = addr(&h[p]); p += so;
+        const uint32_t curRows = (uint32_t)le(&h[p], 2);
+        if (filterLen) fail("a filtered (compressed) fractal heap is not supported");
+        if (root == UNDEF) return;
+        const size_t offBytes = (maxHeapBits + 7) / 8;
+        const size_t dhdr = 5 + so + offBytes + ((flags & 2) ? 4 : 0);
+        auto direct = [&](uint64_t addrBlk, uint64_t size) {
+            const std::vector<uint8_t> b = get(addrBlk, size);
+            if (memcmp(b.data(), "FHDB", 4) != 0) fail("fractal heap direct block signature");
+            out.push_back(std::vector<uint8_t>(b.begin() + dhdr, b.end()));
+        };
+        std::function<void(uint64_t, uint32_t)> indirect = [&](uint64_t addrBlk, uint32_t rows) {
+            const size_t ihdr = 5 + so + offBytes;
+            // direct rows first, then indirect rows
+            uint32_t directRows = 0;
+            for (uint32_t r = 0; r < rows; r++) { const uint64_t bs = startSize << (r > 1 ? r - 1 : 0); if (bs <= maxDirect) directRows = r + 1; }
+            const std::vector<uint8_t> b = get(addrBlk, ihdr + (uint64_t)rows * width * so + 4);
+            if (memcmp(b.data(), "FHIB", 4) != 0) fail("fractal heap indirect block signature");
+            size_t q = ihdr;
+            for (uint32_t r = 0; r < rows; r++) {
+                const uint64_t bs = startSize << (r > 1 ? r - 1 : 0);
+                for (uint32_t c = 0; c < width; c++, q += so) {
+                    const uint64_t child = addr(&b[q]);
+                    if (child == UNDEF) continue;
+                    if (r < directRows) direct(child, bs);
+                    else {
+                        // rows of a child indirect block: it spans bs bytes of heap space
+                        uint32_t childRows = 0; uint64_t span = 0;
+                        while (span < bs) { span += (uint64_t)width * (startSize << (childRows > 1 ? childRows - 1 : 0)); childRows++; }
+                        indirect(child, childRows);
+                    }
+                }
+            }
+        };
+        if (curRows == 0) direct(root, startSize);
+        else indirect(root, curRows);
+    }
+};
+
+struct TypeInfo { bool ok = false; Type type = NC_BYTE; uint32_t size = 0; bool littleEndian = true; bool isString = false; };
+
+TypeInfo datatype_of(const uint8_t* p, size_t n)
+{
+    TypeInfo t;
+    if (n < 8) return t;
+    const int cls = p[0] & 0x0F;
+    t.size = (uint32_t)Reader::le(p + 4, 4);
+    t.littleEndian = (p[1] & 1) == 0;
+    if (cls == 0) {
+        const bool sgn = (p[1] & 0x08) != 0;
+        switch (t.size) {
+        case 1: t.type = sgn ? NC_BYTE : NC_UBYTE; break;
+        case 2: t.type = sgn ? NC_SHORT : NC_USHORT; break;
+        case 4: t.type = sgn ? NC_INT : NC_UINT; break;
+        case 8: t.type = sgn ? NC_INT64 : NC_UINT64; break;
+        default: return t;
+        }
+        t.ok = true;
+    } else if (cls == 1) {
+        if (t.size == 4) t.type = NC_FLOAT; else if (t.size == 8) t.type = NC_DOUBLE; else return t;
+        t.ok = true;
+    } else if (cls == 3) {
+        t.type = NC_CHAR; t.isString = true; t.ok = true;
+    }
+    return t;
+}
+
+// number of elements of a dataspace message (dims returned too); false when it cannot be read
+bool dataspace_of(const Reader& r, const uint8_t* p, size_t n, std::vector<uint64_t>& dims, uint64_t& nelems)
+{
+    dims.clear(); nelems = 1;
+    if (n < 4) return false;
+    const int version = p[0], rank = p[1];
+    size_t q;
+    if (version == 1) q = 8;
+    else if (version == 2) { q = 4; if (p[3] == 2) { nelems = 0; return true; } }
+    else return false;
+    if (q + (size_t)rank * r.sl > n) return false;
+    for (int i = 0; i < rank; i++) { dims.push_back(Reader::le(p + q + (size_t)i * r.sl, r.sl)); nelems *= dims.back(); }
+    return true;
+}
+
+// one attribute message body -> Att (ok = false: a type this reader does not carry, e.g. DIMENSION_LIST); returns the body's length
+size_t attribute_of(const Reader& r, const uint8_t* p, size_t n, Att& a, bool& ok)
+{
+    ok = false;
+    if (n < 8) return 0;
+    const int version = p[0];
+    if (version < 1 || version > 3) return 0;
+    const size_t nameSize = (size_t)Reader::le(p + 2, 2), dtSize = (size_t)Reader::le(p + 4, 2), dsSize = (size_t)Reader::le(p + 6, 2);
+    size_t q = version == 3 ? 9 : 8;
+    auto pad = [&](size_t x) { return version == 1 ? (x + 7) & ~(size_t)7 : x; };
+    if (q + pad(nameSize) + pad(dtSize) + pad(dsSize) > n || nameSize == 0) return 0;
+    a.name = std::string(reinterpret_cast<const char*>(p + q), nameSize - 1);
+    while (!a.name.empty() && a.name.back() == '\0') a.name.pop_back();
+    q += pad(nameSize);
+    const TypeInfo t = datatype_of(p + q, dtSize);
+    const uint32_t elemSize = dtSize >= 8 ? (uint32_t)Reader::le(p + q + 4, 4) : 0;
+    q += pad(dtSize);
+    std::vector<uint64_t> dims; uint64_t nelems = 0;
+    if (!dataspace_of(r, p + q, dsSize, dims, nelems)) return 0;
+    q += pad(dsSize);
+    const uint64_t bytes = nelems * elemSize;
+    if (q + bytes > n) return 0;
+    if (t.ok) {
+        a.type = t.type;
+        a.nelems = t.isString ? bytes : nelems;
+        a.data.assign(p + q, p + q + bytes);
+        if (t.isString) { while (!a.data.empty() && a.data.back() == 0) a.data.pop_back(); a.nelems = a.data.size(); }
+        else if (!t.littleEndian && elemSize > 1)
+            for (uint64_t i = 0; i < nelems; i++) for (uint32_t x = 0, y = elemSize - 1; x < y; x++, y--) std::swap(a.data[i * elemSize + x], a.data[i * elemSize + y]);
+        const uint16_t probe = 1;
+        if (!t.isString && *reinterpret_cast<const uint8_t*>(&probe) == 0 && elemSize > 1)                  // big-endian host
+            for (uint64_t i = 0; i < nelems; i++) for (uint32_t x = 0, y = elemSize - 1; x < y; x++, y--) std::swap(a.data[i * elemSize + x], a.data[i * elemSize + y]);
+        ok = true;
+    }
+    return q + (size_t)bytes;
+}
+
+bool hidden(const std::string& n)
+{
+    return n == "_NCProperties" || n == "_Netcdf4Dimid" || n == "_Netcdf4Coordinates" || n == "DIMENSION_LIST" || n == "REFERENCE_LIST" || n == "CLASS" ||
+           n == "NAME" || n == "_nc3_strict" || n == "_Netcdf4BugFix";
+}
+
+// all attributes of an object: header messages + dense storage
+void attributes(const Reader& r, const std::vector<Msg>& msgs, std::vector<Att>& all)
+{
+    for (const Msg& m : msgs) {
+        if (m.type == 0x0C) {
+            if (m.flags & 0x02) continue;                                       // shared message: not in DSSTNE files
+            Att a; bool ok;
+            if (attribute_of(r, m.data.data(), m.data.size(), a, ok) && ok) all.push_back(a);
+        } else if (m.type == 0x15 && m.data.size() >= 2) {
+            size_t p = 2;
+            if (m.data[1] & 1) p += 2;
+            if (p + r.so > m.data.size()) continue;
+            const uint64_t heap = r.addr(&m.data[p]);
+            if (heap == UNDEF) continue;
+            std::vector<std::vector<uint8_t>> blocks;
+            r.heap_blocks(heap, blocks);
+            for (const auto& b : blocks) {
+                size_t q = 0;
+                while (q < b.size() && b[q] != 0) {
+                    Att a; bool ok;
+                    const size_t len = attribute_of(r, b.data() + q, b.size() - q, a, ok);
+                    if (!len) break;
+                    if (ok) all.push_back(a);
+                    q += len;
+                }
+            }
+        }
+    }
+}
+
+}  // namespace
+
+void parse(FILE* f, const std::string& fname, std::vector<Dim>& dims, std::vector<Att>& atts, std::vector<Var>& vars)
+{
+    Reader r; r.f = f; r.fname = fname;
+    // ---- superblock: at 0, 512, 1024, ...
+    uint64_t sb = UNDEF;
+    for (uint64_t off = 0; off < (1ull << 24); off = off ? off * 2 : 512) {
+        uint8_t sig[8];
+        if (fseeko(f, (off_t)off, SEEK_SET) != 0 || fread(sig, 1, 8, f) != 8) break;
+        if (memcmp(sig, "\x89HDF\r\n\x1a\n", 8) == 0) { sb = off; break; }
+    }
+    if (sb == UNDEF) r.fail("no HDF5 superblock");
+    const std::vector<uint8_t> s = r.get(sb, 64);
+    const int version = s[8];
+    uint64_t rootHeader = UNDEF, rootBtree = UNDEF, rootHeap = UNDEF;
+    if (version == 0 || version == 1) {
+        r.so = s[13]; r.sl = s[14];
+        size_t p = 24 + (version == 1 ? 4 : 0);
+        const std::vector<uint8_t> t = r.get(sb, p + 4 * r.so + 2 * r.so + 8 + 16);
+        r.base = Reader::le(&t[p], r.so);
+        p += 4 * r.so;                                                          // base, free-space, end-of-file, driver-information addresses
+        p += r.so;                                                              // root group symbol table entry: link name offset
+        rootHeader = Reader::le(&t[p], r.so); p += r.so;
+        const uint32_t cache = (uint32_t)Reader::le(&t[p], 4); p += 8;
+        if (cache == 1) { rootBtree = Reader::le(&t[p], r.so); rootHeap = Reader::le(&t[p + r.so], r.so); }
+    } else if (version == 2 || version == 3) {
+        r.so = s[9]; r.sl = s[10];
+        const std::vector<uint8_t> t = r.get(sb, 12 + 4 * r.so);
+        r.base = Reader::le(&t[12], r.so);
+        rootHeader = Reader::le(&t[12 + 3 * r.so], r.so);
+    } else r.fail("superblock version " + std::to_string(version));
+    if (r.so != 8 && r.so != 4) r.fail("offsets of " + std::to_string(r.so) + " bytes");
+    if (r.base == UNDEF) r.base = 0;
+
+    // ---- root group: links and global attributes
+    const std::vector<Msg> root = r.object(rootHeader);
+    std::vector<std::pair<std::string, uint64_t>> links;
+    for (const Msg& m : root) {
+        if (m.type == 0x11 && m.data.size() >= (size_t)(2 * r.so)) { rootBtree = r.addr(m.data.data()); rootHeap = r.addr(m.data.data() + r.so); }
+        else if (m.type == 0x06) r.link_message(m.data.data(), m.data.size(), links);
+        else if (m.type == 0x02 && m.data.size() >= 2) {
+            size_t p = 2;
+            if (m.data[1] & 1) p += 8;
+            if (p + r.so > m.data.size()) continue;
+            const uint64_t heap = r.addr(&m.data[p]);
+            if (heap == UNDEF) continue;
+            std::vector<std::vector<uint8_t>> blocks;
+            r.heap_blocks(heap, blocks);
+            for (const auto& b : blocks) {
+                size_t q = 0;
+                while (q < b.size() && b[q] != 0) {
+                    const size_t len = r.link_message(b.data() + q, b.size() - q, links);
+                    if (!len) break;
+                    q += len;
+                }
+            }
+        }
+    }
+    if (links.empty() && rootBtree != UNDEF && rootHeap != UNDEF) r.links_of_symbol_table(rootBtree, rootHeap, links);
+    std::vector<Att> all;
+    attributes(r, root, all);
+    for (const Att& a : all) if (!hidden(a.name)) atts.push_back(a);
+
+    // ---- datasets: dimensions first, then variables
+    struct DS { std::string name; std::vector<uint64_t> dims; uint64_t nelems; TypeInfo t; std::vector<Att> atts; bool dimScale, pureDim; uint64_t begin; std::vector<uint8_t> inl; bool hasInline; };
+    std::vector<DS> sets;
+    for (const auto& l : links) {
+        if (l.second == UNDEF) continue;
+        const std::vector<Msg> ms = r.object(l.second);
+        const Msg* space = nullptr; const Msg* type = nullptr; const Msg* layout = nullptr;
+        bool group = false;
+        for (const Msg& m : ms) {
+            if (m.type == 0x01) space = &m; else if (m.type == 0x03) type = &m; else if (m.type == 0x08) layout = &m;
+            else if (m.type == 0x11 || m.type == 0x02) group = true;
+            if (m.type == 0x0B) r.fail("variable " + l.first + " is stored through a filter pipeline (compressed): rewrite it with `nccopy -d 0`");
+        }
+        if (group || !space || !type || !layout) continue;                      // sub-groups and committed types: not part of a DSSTNE file
+        DS d; d.name = l.first; d.hasInline = false; d.begin = 0;
+        if (!dataspace_of(r, space->data.data(), space->data.size(), d.dims, d.nelems)) r.fail("dataspace of " + l.first);
+        d.t = datatype_of(type->data.data(), type->data.size());
+        attributes(r, ms, d.atts);
+        d.dimScale = false; d.pureDim = false;
+        for (const Att& a : d.atts) {
+            if (a.name == "CLASS" && a.as_string().compare(0, 15, "DIMENSION_SCALE") == 0) d.dimScale = true;
+            if (a.name == "NAME" && a.as_string().compare(0, 52, "This is a netCDF dimension but not a netCDF variable") == 0) d.pureDim = true;
+        }
+        const std::vector<uint8_t>& L = layout->data;
+        if (L.size() < 2) r.fail("layout of " + l.first);
+        if (L[0] == 3 || L[0] == 4) {
+            if (L[1] == 0) { const size_t n = (size_t)Reader::le(&L[2], 2); if (4 + n > L.size()) r.fail("compact layout of " + l.first); d.inl.assign(L.begin() + 4, L.begin() + 4 + n); d.hasInline = true; }
+            else if (L[1] == 1) d.begin = r.addr(&L[2]);
+            else r.fail("variable " + l.first + " is chunked; DSSTNE variables are fixed-size and contiguous (rewrite it with `nccopy -k cdf5` or without chunking)");
+        } else r.fail("data layout message version " + std::to_string(L[0]) + " of " + l.first);
+        sets.push_back(d);
+    }
+    for (const DS& d : sets)
+        if (d.dimScale) { Dim x; x.name = d.name; x.size = d.dims.empty() ? 0 : d.dims[0]; dims.push_back(x); }
+    for (const DS& d : sets) {
+        if (d.dimScale && d.pureDim) continue;
+        if (!d.t.ok) r.fail("variable " + d.name + " has a type outside the netCDF atomic types");
+        Var v;
+        v.name = d.name; v.type = d.t.type;
+        v.nelems = d.t.isString ? d.nelems * d.t.size : d.nelems;
+        v.vsize = v.nelems * type_size(v.type);
+        v.begin = d.begin == UNDEF ? 0 : r.base + d.begin;
+        v.littleEndian = d.t.littleEndian;
+        v.hasInline = d.hasInline; v.inlineData = d.inl;
+        if (d.begin == UNDEF && !d.hasInline) { v.hasInline = true; v.inlineData.assign(v.vsize, 0); }    // never written: the fill value (zero)
+        for (uint64_t n : d.dims) {                                             // DIMENSION_LIST is not followed: dimensions are matched by size
+            uint32_t id = 0; bool found = false;
+            for (size_t i = 0; i < dims.size(); i++) if (dims[i].size == n && (dims[i].name == d.name || !found)) { id = (uint32_t)i; found = true; if (dims[i].name == d.name) break; }
+            if (found) v.dimids.push_back(id);
+        }
+        for (const Att& a : d.atts) if (!hidden(a.name)) v.atts.push_back(a);
+        vars.push_back(v);
+    }
+}
+
+}  // namespace hdf5
+}  // namespace nc

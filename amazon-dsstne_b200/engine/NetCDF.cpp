@@ -142,9 +142,11 @@ File::File(const std::string& fname) : _fname(fname), _version(0), _numrecs(0)
     struct Closer { FILE* f; ~Closer() { fclose(f); } } closer{f};
     uint8_t magic[8] = {0};
     if (fread(magic, 1, 4, f) != 4) throw Error("netCDF: " + fname + " is too short to be a netCDF file");
-    if (magic[0] == 0x89 && magic[1] == 'H' && magic[2] == 'D' && magic[3] == 'F')
-        throw Error("netCDF: " + fname + " is a netCDF-4 / HDF5 container; this build reads the classic formats only -- convert it once with "
-                    "`nccopy -k cdf5 " + fname + " out.nc` (CDF-5 keeps DSSTNE's uint / uint64 variables)");
+    if (magic[0] == 0x89 && magic[1] == 'H' && magic[2] == 'D' && magic[3] == 'F') {
+        _version = 4;                                                          // netCDF-4: an HDF5 container (HDF5.cpp)
+        hdf5::parse(f, fname, _dims, _atts, _vars);
+        return;
+    }
     if (magic[0] != 'C' || magic[1] != 'D' || magic[2] != 'F' || (magic[3] != 1 && magic[3] != 2 && magic[3] != 5))
         throw Error("netCDF: " + fname + " is not a netCDF classic file (bad magic)");
     _version = magic[3];
@@ -214,6 +216,11 @@ void File::read_raw(const Var& v, std::vector<uint8_t>& bytes) const
     if (!f) throw Error("netCDF: cannot reopen " + _fname);
     struct Closer { FILE* f; ~Closer() { fclose(f); } } closer{f};
     const uint64_t n = v.nelems * type_size(v.type);
+    if (v.hasInline) {
+        if (v.inlineData.size() < n) throw Error("netCDF: variable " + v.name + " is truncated in " + _fname);
+        bytes.assign(v.inlineData.begin(), v.inlineData.begin() + n);
+        return;
+    }
     bytes.resize(n);
 #if defined(_WIN32)
     if (_fseeki64(f, (long long)v.begin, SEEK_SET) != 0)
@@ -229,7 +236,12 @@ template <typename T> void File::read(const Var& v, std::vector<T>& out) const
     std::vector<uint8_t> raw;
     read_raw(v, raw);
     const size_t sz = type_size(v.type);
-    swap_elems(raw.data(), v.nelems, sz);
+    if (!v.littleEndian) swap_elems(raw.data(), v.nelems, sz);                // classic files are big-endian
+    else {
+        const uint16_t probe = 1;
+        if (*reinterpret_cast<const uint8_t*>(&probe) == 0 && sz > 1)         // little-endian data on a big-endian host
+            for (uint64_t i = 0; i < v.nelems; i++) for (size_t a = 0, b = sz - 1; a < b; a++, b--) std::swap(raw[i * sz + a], raw[i * sz + b]);
+    }
     out.resize(v.nelems);
     for (uint64_t i = 0; i < v.nelems; i++) out[i] = host_value<T>(raw.data() + i * sz, v.type);
 }
@@ -246,7 +258,7 @@ template void File::read<double>(const Var&, std::vector<double>&) const;
 std::string File::describe() const
 {
     std::ostringstream o;
-    o << "netcdf " << _fname << " (CDF-" << _version << ")\n" << "dimensions:\n";
+    o << "netcdf " << _fname << (_version == 4 ? " (netCDF-4 / HDF5" : " (CDF-") << (_version == 4 ? std::string() : std::to_string(_version)) << ")\n" << "dimensions:\n";
     for (const Dim& d : _dims) o << "\t" << d.name << " = " << d.size << "\n";
     o << "variables:\n";
     for (const Var& v : _vars) {

@@ -2,16 +2,18 @@
 // data"), enough for DSSTNE's dataset and network files ("next" row 1 of SURVEY 8f).  Host only, no libnetcdf.
 //
 // The reference reads and writes through netcdf-cxx4 (E/NNTypes.cpp:1081-1418, 2218-2385; E/NNNetwork.cpp:1936-1970;
-// U/NetCDFhelper.cpp:332-416), whose default on-disk format is netCDF-4 = HDF5.  HDF5 containers are NOT parsed here:
-// they are detected by their signature and rejected with a message naming the one-line conversion
-// (`nccopy -k cdf5 in.nc out.nc`); CDF-5 keeps the unsigned and 64-bit variable types DSSTNE uses.  Files written here
-// are CDF-5 (or CDF-2 on request, for tools that only read classic types) and open with any netCDF >= 4.4.
+// U/NetCDFhelper.cpp:332-416), whose default on-disk format is netCDF-4 = HDF5.  Such containers are recognised by their
+// signature and read by HDF5.cpp (contiguous / compact fixed-size variables and attributes of the netCDF atomic types;
+// chunked or compressed variables are refused by name with the `nccopy` line that rewrites them).  Files written here
+// are CDF-5 (or CDF-2 on request, for tools that only read classic types) and open with any netCDF >= 4.4; CDF-5 keeps
+// the unsigned and 64-bit variable types DSSTNE uses.
 //
 // Layout handled: fixed-size variables only (DSSTNE never uses the record dimension), any of the 11 atomic types,
 // global and per-variable attributes.
 #pragma once
 
 #include <cstdint>
+#include <cstdio>
 #include <map>
 #include <stdexcept>
 #include <string>
@@ -52,12 +54,15 @@ struct Var {
     uint64_t vsize;                                   // bytes in the file (padded to 4)
     uint64_t begin;                                   // file offset of the data
     uint64_t nelems;                                  // product of the dimension sizes
+    bool littleEndian = false;                        // netCDF-4 / HDF5 variables are stored in the writer's byte order (classic: big-endian)
+    bool hasInline = false;                           // HDF5 compact layout (or a never-written variable): the bytes live in the header
+    std::vector<uint8_t> inlineData;
 };
 
 class File {
 public:
     explicit File(const std::string& fname);          // parses the header; throws nc::Error
-    int version() const { return _version; }          // 1, 2 or 5
+    int version() const { return _version; }          // 1, 2 or 5 (classic family), 4 (netCDF-4 / HDF5, read only: HDF5.cpp)
     const std::vector<Dim>& dims() const { return _dims; }
     const std::vector<Att>& atts() const { return _atts; }
     const std::vector<Var>& vars() const { return _vars; }
@@ -97,5 +102,10 @@ private:
     std::vector<Att> _atts;
     std::vector<V> _vars;
 };
+
+namespace hdf5 {
+// netCDF-4 container -> the same dimension / attribute / variable tables the classic parser fills (HDF5.cpp)
+void parse(FILE* f, const std::string& fname, std::vector<Dim>& dims, std::vector<Att>& atts, std::vector<Var>& vars);
+}
 
 }  // namespace nc

@@ -404,6 +404,41 @@ def test_netcdf_datasets_and_network_checkpoint_round_trip(eng, orc, tmp_path):
     net.close(); net2.close()
 
 
+@pytest.mark.parametrize("flavour", ["old", "new"])
+def test_netcdf4_dataset_file_loads_and_trains(eng, orc, flavour):
+    """a netCDF-4 (HDF5) dataset file in the schema of U/NetCDFhelper.cpp:332-372 -- the committed fixtures of
+    tests/golden/make_hdf5_fixture.py -- through LoadNetCDF, then one training step against the oracle on the same data"""
+    import importlib.util
+    here = os.path.dirname(os.path.abspath(__file__))
+    spec = importlib.util.spec_from_file_location("make_hdf5_fixture", os.path.join(here, "golden", "make_hdf5_fixture.py"))
+    m = importlib.util.module_from_spec(spec); spec.loader.exec_module(m)
+    start, end, index, data, gatts = m.sample()
+    loaded = eng.load_netcdf(os.path.join(here, "golden", f"dataset_nc4_{flavour}.nc"))
+    assert [d.name for d in loaded] == ["gl_input"] and loaded[0].examples == 5 and loaded[0].width == 256 and loaded[0].nnz == 12
+    assert loaded[0].attributes & 3 == 1                                                # Sparse, analog (float values)
+    out = eng.Dataset("gl_output", start.astype(np.uint64), end.astype(np.uint64), index, 256)      # Boolean targets
+    sizes, batch = [256, 16, 256], 5
+    net = eng.Network(eng.autoencoder_json([16]), batch, [loaded[0], out])
+    net.set_training_mode(orc.SGD)
+    from dsstne_b200 import datagen
+    Ws, bs = datagen.make_weights(sizes, scale=0.1)
+    net.set_weights("Input", "Hidden1", Ws[0], bs[0])
+    net.set_weights("Hidden1", "Output", Ws[1], bs[1])
+    onet = orc.Network(sizes, error=orc.ERR_SMCE, mode=orc.SGD, max_batch=batch)
+    for i in range(2):
+        onet.W(i)[:] = Ws[i]; onet.b(i)[:] = bs[i]
+    onet.s.params = orc.make_params(smce=(1.0, 0.0, 1.0, 1.0))
+    oc_in = orc.Csr(start.astype(np.uint64), end.astype(np.uint64), index, data=data)
+    oc_out = orc.Csr(start.astype(np.uint64), end.astype(np.uint64), index)
+    onet.set_input(oc_in, batch)
+    got = net.train_step(0, 0.05, 0.0)
+    want, _ = onet.train_step(oc_in, oc_out, 0, batch, 0.05, 0.0)
+    assert abs(got - want) <= TOL * abs(want), (got, want)
+    W, _ = net.get_weights("Input", "Hidden1")
+    assert rel_err(W.reshape(onet.W(0).shape), onet.W(0)) < TOL
+    net.close()
+
+
 def test_engine_rejects_features_outside_the_hot_path(eng):
     from dsstne_b200 import DsbError
     h = tiny(examples=64, width=256)

@@ -5,7 +5,11 @@ Independent cross-checks with scipy.io.netcdf_file (a separate implementation of
     back by scipy with identical contents;
   * a file written by scipy (CDF-1 and CDF-2, classic int types) is parsed by OUR reader;
   * CDF-5 (uint / uint64 variables, what the engine writes) round-trips through our own reader, header fields included;
-  * netCDF-4 / HDF5 containers are rejected with the conversion hint, not mis-parsed."""
+  * netCDF-4 / HDF5 containers (what netcdf-cxx4 writes by default) are read by engine/HDF5.cpp: the two fixtures of
+    tests/golden/make_hdf5_fixture.py -- the old-style layout (superblock v0, version-1 object headers, symbol-table root group)
+    and the new-style one (superblock v2, version-2 headers, links and attributes in fractal heaps, compact / big-endian
+    variables) -- give the same dimensions, attributes and variable contents as the CDF-5 file of the same data set;
+  * chunked / compressed netCDF-4 variables, broken containers and non-netCDF files are rejected loudly, not mis-parsed."""
 import ctypes as C
 import os
 
@@ -110,13 +114,61 @@ def test_cdf5_round_trip_with_unsigned_types_weights_and_index(dsb, tmp_path):
     assert os.path.getsize(path) == begins[-1] + sizes[-1]
 
 
-def test_hdf5_and_garbage_are_rejected_loudly(dsb, tmp_path):
+def _fixture_module():
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_hdf5_fixture", os.path.join(os.path.dirname(__file__), "golden", "make_hdf5_fixture.py"))
+    m = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(m)
+    return m
+
+
+@pytest.mark.parametrize("flavour", ["old", "new"])
+def test_netcdf4_hdf5_fixture_reads_like_the_cdf5_file_of_the_same_data_set(dsb, tmp_path, flavour):
+    lib = dsb.lib()
+    m = _fixture_module()
+    golden = os.path.join(os.path.dirname(__file__), "golden", f"dataset_nc4_{flavour}.nc")
+    fresh = str(tmp_path / f"nc4_{flavour}.nc")
+    (m.write_old if flavour == "old" else m.write_new)(fresh)
+    assert open(fresh, "rb").read() == open(golden, "rb").read()              # the committed fixture is what the committed script writes
+    start, end, index, data, gatts = m.sample()
+    rc, text = describe(lib, golden)
+    assert rc == 0, text
+    assert "netCDF-4 / HDF5" in text and "examplesDim0 = 5" in text and "sparseDataDim0 = 12" in text
+    for hidden in ("_NCProperties", "DIMENSION_LIST", "_Netcdf4Dimid", "CLASS", "NAME"):
+        assert hidden not in text                                               # netCDF-4 bookkeeping is not user data
+    for k, v in gatts:
+        assert (f'{k} = "{v}"' if isinstance(v, str) else f"{k} = {v} (uint)") in text
+    assert "uint sparseStart0(examplesDim0)" in text and "float sparseData0(sparseDataDim0)" in text
+    np.testing.assert_array_equal(read_var(lib, golden, "sparseStart0"), start)
+    np.testing.assert_array_equal(read_var(lib, golden, "sparseEnd0"), end)
+    np.testing.assert_array_equal(read_var(lib, golden, "sparseIndex0"), index)
+    np.testing.assert_array_equal(read_var(lib, golden, "sparseData0"), data)
+    # the same data set written by our CDF-5 writer reads back identically
+    class H: pass
+    h = H(); h.start, h.end, h.index, h.width = start.astype(np.uint64), end.astype(np.uint64), index, 256
+    cdf5 = str(tmp_path / "same.nc")
+    assert write_sparse(lib, cdf5, 5, "gl_input", h, data=data, dtype=4) == 0
+    for v in ("sparseStart0", "sparseEnd0", "sparseIndex0", "sparseData0"):
+        np.testing.assert_array_equal(read_var(lib, golden, v), read_var(lib, cdf5, v))
+
+
+def test_unreadable_containers_are_rejected_loudly(dsb, tmp_path):
     lib = dsb.lib()
     lib.dsb200_engine_last_error.restype = C.c_char_p
     p1 = tmp_path / "nc4.nc"
-    p1.write_bytes(b"\x89HDF\r\n\x1a\n" + bytes(64))
+    p1.write_bytes(b"\x89HDF\r\n\x1a\n" + bytes(64))                          # a signature and nothing behind it
     rc, _ = describe(lib, str(p1))
-    assert rc != 0 and b"nccopy -k cdf5" in lib.dsb200_engine_last_error()
+    assert rc != 0 and b"HDF5" in lib.dsb200_engine_last_error()
+    # a chunked variable: named, with the way out
+    m = _fixture_module()
+    import struct
+    orig = m.layout_contiguous
+    m.layout_contiguous = lambda addr, size, version=3: struct.pack("<BBBQII", 3, 2, 2, addr, 4, 4) if addr != m.UNDEF else orig(addr, size, version)
+    p4 = str(tmp_path / "chunked.nc")
+    m.write_old(p4)
+    rc, _ = describe(lib, p4)
+    err = lib.dsb200_engine_last_error()
+    assert rc != 0 and b"chunked" in err and b"nccopy" in err
     p2 = tmp_path / "junk.nc"
     p2.write_bytes(b"hello world, not a netcdf file")
     rc, _ = describe(lib, str(p2))
