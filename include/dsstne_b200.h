@@ -100,7 +100,7 @@ int  dsb200_ctx_set_params(dsb200_ctx* ctx, const dsb200_params* p);
 void dsb200_params_default(dsb200_params* p);                 /* E/NNNetwork.cpp:27-58 */
 int  dsb200_ctx_reserve(dsb200_ctx* ctx, uint32_t maxBatch, size_t partialFloats);
 /* Options (all have working defaults; the alternative kernels stay selectable because the parity tests run every one of them):
- *   "gemm_mode"          DSB200_GEMM_FP32 (default: cuBLAS SGEMM, the 1e-5 parity mode) | DSB200_GEMM_TF32 | DSB200_GEMM_TF32X3
+ *   "gemm_mode"          DSB200_GEMM_FP32 (default: exact fp32 FMA arithmetic on the SIMT kernel of csrc/dense_small.cu, the 1e-5 parity mode) | DSB200_GEMM_TF32 | DSB200_GEMM_TF32X3
  *   "gemm_loader"        operand path of the tcgen05 GEMM: -1 per shape (default) | 0 cp.async + split warps | 1 registers ->
  *                        shared memory | 2 A operand through tensor memory | 3 the same with a coalesced A loader (experimental)
  *   "gemm_stream"        1 (default) = weight gradient / input delta of layers with a narrow side (<= 256 units) run on the TMA +
