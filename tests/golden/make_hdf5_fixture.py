@@ -183,36 +183,45 @@ def header_v2(img, msgs, split_after=None):
 
 # ---------------------------------------------------------------- fractal heap holding `objects` (bytes each), link or attribute messages
 def fractal_heap(img, objects, start_size, indirect):
+    """Managed objects packed block by block in heap order.  indirect = False: the root IS a direct block (everything must fit it);
+    True: a root indirect block over a doubling table of width 4 (rows 0 and 1: start_size, row r >= 2: start_size * 2^(r-1))."""
     width, max_direct, heap_bits = 4, 65536, 32
     hdr_len = 4 + 1 + 2 + 2 + 1 + 4 + 8 + 8 + 8 + 8 + 8 * 8 + 2 + 8 + 8 + 2 + 2 + 8 + 2 + 4
     hoff = img.alloc(hdr_len)
     dhdr = 5 + 8 + 4 + 4
-    blocks, cur, used = [], bytearray(), 0
-    for o in objects:                                             # pack the objects block by block
-        if dhdr + len(cur) + len(o) > start_size:
+
+    def block_size(i):
+        row = i // width
+        return start_size << (row - 1 if row > 1 else 0)
+    blocks, cur = [], bytearray()
+    for o in objects:                                             # an object never straddles two blocks
+        while dhdr + len(cur) + len(o) > block_size(len(blocks)):
+            assert cur or dhdr + len(o) <= max_direct, "object larger than any direct block"
             blocks.append(cur); cur = bytearray()
         cur += o
     blocks.append(cur)
     assert indirect or len(blocks) == 1, "objects do not fit the root direct block"
-    assert len(blocks) <= width
-    addrs = []
+    addrs, heap_off = [], 0
     for i, payload in enumerate(blocks):
-        boff = img.alloc(start_size)
-        head = b"FHDB" + struct.pack("<BQI", 0, hoff, i * start_size)
+        size = block_size(i)
+        assert size <= max_direct
+        boff = img.alloc(size)
+        head = b"FHDB" + struct.pack("<BQI", 0, hoff, heap_off)
         blk = bytearray(head + b"\0\0\0\0" + payload)
-        blk += b"\0" * (start_size - len(blk))
+        blk += b"\0" * (size - len(blk))
         blk[len(head):len(head) + 4] = struct.pack("<I", lookup3(bytes(blk[:len(head)]) + b"\0\0\0\0" + bytes(blk[len(head) + 4:])))
         img.put(boff, bytes(blk))
         addrs.append(boff)
+        heap_off += size
     if indirect:
-        ib = b"FHIB" + struct.pack("<BQI", 0, hoff, 0) + b"".join(struct.pack("<Q", addrs[i] if i < len(addrs) else UNDEF) for i in range(width))
+        rows = (len(blocks) + width - 1) // width
+        ib = b"FHIB" + struct.pack("<BQI", 0, hoff, 0) + b"".join(struct.pack("<Q", addrs[i] if i < len(addrs) else UNDEF) for i in range(width * rows))
         root = img.add(ib + struct.pack("<I", lookup3(ib)))
-        rows = 1
     else:
         root, rows = addrs[0], 0
     nobj = len(objects)
     h = (b"FRHP" + struct.pack("<BHHBI", 0, 7, 0, 0x02, 4096) + struct.pack("<QQQQ", 0, UNDEF, 0, UNDEF) +
-         struct.pack("<QQQQQQQQ", start_size * len(blocks), start_size * len(blocks), start_size * len(blocks), nobj, 0, 0, 0, 0) +
+         struct.pack("<QQQQQQQQ", heap_off, heap_off, heap_off, nobj, 0, 0, 0, 0) +
          struct.pack("<HQQHHQH", width, start_size, max_direct, heap_bits, 1, root, rows))
     img.put(hoff, h + struct.pack("<I", lookup3(h)))
     return hoff
@@ -308,6 +317,104 @@ def write_new(path):
     s = b"\x89HDF\r\n\x1a\n" + struct.pack("<BBBB", 2, 8, 8, 0) + struct.pack("<QQQQ", 0, UNDEF, eof, root)
     img.put(sb, s + struct.pack("<I", lookup3(s)))
     open(path, "wb").write(bytes(img.buf))
+
+
+# ---------------------------------------------------------------- any classic netCDF file -> the same content in a netCDF-4 layout
+_NCT = {1: np.int8, 2: "S1", 3: np.int16, 4: np.int32, 5: np.float32, 6: np.float64, 7: np.uint8, 8: np.uint16, 9: np.uint32, 10: np.int64, 11: np.uint64}
+
+
+def read_classic(path):
+    """dims [(name, size)], global attributes [(name, value)], variables [(name, dim name, numpy array)] of a CDF-1 / 2 / 5 file whose
+    variables are one-dimensional and fixed-size (every file of the DSSTNE schemas)"""
+    b = open(path, "rb").read()
+    assert b[:3] == b"CDF" and b[3] in (1, 2, 5)
+    v = b[3]
+    pos = [4]
+
+    def u(n):
+        x = int.from_bytes(b[pos[0]:pos[0] + n], "big"); pos[0] += n; return x
+    nn = (lambda: u(8)) if v == 5 else (lambda: u(4))
+
+    def name():
+        n = nn(); s_ = b[pos[0]:pos[0] + n].decode(); pos[0] += (n + 3) & ~3; return s_
+
+    def atts():
+        tag, n = u(4), nn()
+        out = []
+        for _ in range(n):
+            nm, t, ne = name(), u(4), nn()
+            if t == 2:
+                val = b[pos[0]:pos[0] + ne].decode()
+            else:
+                val = np.frombuffer(b, dtype=np.dtype(_NCT[t]).newbyteorder(">"), count=ne, offset=pos[0]).astype(_NCT[t])
+            pos[0] += (ne * np.dtype(_NCT[t]).itemsize + 3) & ~3
+            out.append((nm, val))
+        return out
+    nn()                                                          # numrecs
+    tag, n = u(4), nn()
+    dims = [(name(), nn()) for _ in range(n)]
+    gatts = atts()
+    tag, n = u(4), nn()
+    variables = []
+    for _ in range(n):
+        nm, nd = name(), nn()
+        ids = [nn() for _ in range(nd)]
+        atts()
+        t, vsize, begin = u(4), nn(), (u(4) if v == 1 else u(8))
+        assert nd == 1
+        cnt = dims[ids[0]][1]
+        arr = np.frombuffer(b, dtype=np.dtype(_NCT[t]).newbyteorder(">"), count=cnt, offset=begin).astype(_NCT[t])
+        variables.append((nm, dims[ids[0]][0], arr))
+    return dims, gatts, variables
+
+
+def convert(src, dst, flavour):
+    """flavour "old": superblock v0, version-1 headers, symbol table;  "new": superblock v2, version-2 headers, dense links and attributes"""
+    dims, gatts, variables = read_classic(src)
+    img = Image()
+    old = flavour == "old"
+    hdr, av = (header_v1, 1) if old else (header_v2, 3)
+    sb = img.alloc(96 if old else 48)
+    objs = [(n, dimension_scale(img, n, size, i, hdr, av)) for i, (n, size) in enumerate(dims)]
+    for nm, dn, arr in variables:
+        if arr.dtype.kind == "S":
+            arr = np.frombuffer(arr.tobytes(), dtype=np.uint8)     # (char variables do not occur in the DSSTNE schemas)
+        objs.append((nm, variable(img, nm, arr, hdr, av, big=(len(objs) % 3 == 0))))
+    amsg = [att_text("_NCProperties", "version=2,netcdf=4.8.1,hdf5=1.12.2", av)]
+    for k, val in gatts:
+        if isinstance(val, str):
+            amsg.append(att_text(k, val, av))
+        else:
+            amsg.append(attribute(k, datatype(val.dtype), [] if len(val) == 1 else [len(val)], val.astype(val.dtype.newbyteorder("<")).tobytes(), av))
+    if old:
+        objs.sort(key=lambda x: x[0])
+        heap_data = bytearray(b"\0" * 8)
+        name_off = {}
+        for n, _ in objs:
+            name_off[n] = len(heap_data)
+            heap_data += pad8(n.encode() + b"\0")
+        hd = img.add(bytes(heap_data))
+        heap = img.add(b"HEAP" + struct.pack("<B3xQQQ", 0, len(heap_data), UNDEF, hd))
+        assert len(objs) <= 32
+        snod = b"SNOD" + struct.pack("<BBH", 1, 0, len(objs)) + b"".join(struct.pack("<QQII16x", name_off[n], a, 0, 0) for n, a in objs)
+        snod += b"\0" * (8 + 32 * 40 - len(snod))
+        snod_off = img.add(snod)
+        tree = b"TREE" + struct.pack("<BBHQQ", 0, 0, 1, UNDEF, UNDEF) + struct.pack("<QQQ", 0, snod_off, name_off[objs[-1][0]])
+        tree += b"\0" * (24 + 33 * 8 + 32 * 8 - len(tree))
+        tree_off = img.add(tree)
+        root = header_v1(img, [(0x11, struct.pack("<QQ", tree_off, heap))] + [(0x0C, a) for a in amsg], split_after=max(2, len(amsg) // 2))
+        eof = len(img.buf)
+        img.put(sb, b"\x89HDF\r\n\x1a\n" + struct.pack("<BBBBBBBBHHI", 0, 0, 0, 0, 0, 8, 8, 0, 16, 16, 0) + struct.pack("<QQQQ", 0, UNDEF, eof, UNDEF) +
+                struct.pack("<QQII", 0, root, 1, 0) + struct.pack("<QQ", tree_off, heap))
+    else:
+        links = fractal_heap(img, [link_message(n, a, i) for i, (n, a) in enumerate(objs)], 512, indirect=True)
+        atts = fractal_heap(img, amsg, 512, indirect=True)
+        root = header_v2(img, [(0x02, struct.pack("<BBQQQ", 0, 0x01, len(objs), links, UNDEF)), (0x0A, struct.pack("<BB", 0, 0)),
+                               (0x15, struct.pack("<BBHQQ", 0, 0x01, len(amsg), atts, UNDEF))])
+        eof = len(img.buf)
+        sblk = b"\x89HDF\r\n\x1a\n" + struct.pack("<BBBB", 2, 8, 8, 0) + struct.pack("<QQQQ", 0, UNDEF, eof, root)
+        img.put(sb, sblk + struct.pack("<I", lookup3(sblk)))
+    open(dst, "wb").write(bytes(img.buf))
 
 
 if __name__ == "__main__":

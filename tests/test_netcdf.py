@@ -152,6 +152,43 @@ def test_netcdf4_hdf5_fixture_reads_like_the_cdf5_file_of_the_same_data_set(dsb,
         np.testing.assert_array_equal(read_var(lib, golden, v), read_var(lib, cdf5, v))
 
 
+@pytest.mark.parametrize("flavour", ["old", "new"])
+def test_netcdf4_container_with_a_network_sized_header(dsb, tmp_path, flavour):
+    """a header of the size of a network checkpoint (E/NNNetwork.cpp:1936-1970 writes ~30 global attributes plus ~25 per layer and
+    weight): 160 attributes of mixed types and a dozen variables, written by scipy as CDF-2 and re-laid-out as netCDF-4 by the
+    fixture script -- the dense attribute heap then spans several rows of its doubling table; both files must read the same"""
+    lib = dsb.lib()
+    m = _fixture_module()
+    rng = np.random.default_rng(7)
+    src, dst = str(tmp_path / "net.nc"), str(tmp_path / f"net_{flavour}.nc")
+    arrays = {}
+    with netcdf_file(src, "w", version=2) as f:
+        for i in range(160):
+            k = i % 4
+            setattr(f, f"att{i:03d}_{'ifsx'[k]}", [np.int32(rng.integers(-1000, 1000)), np.float32(rng.standard_normal()), f"layer{i}_name with spaces",
+                                                  np.array(rng.integers(0, 9, 5), dtype=np.int32)][k])
+        for j in range(12):
+            n = int(rng.integers(1, 400))
+            f.createDimension(f"dim{j}", n)
+            dt = ["f", "i", "d"][j % 3]
+            v = f.createVariable(f"var{j}", dt, (f"dim{j}",))
+            arrays[f"var{j}"] = (rng.standard_normal(n) * 100).astype({"f": np.float32, "i": np.int32, "d": np.float64}[dt])
+            v[:] = arrays[f"var{j}"]
+    m.convert(src, dst, flavour)
+    rc0, want = describe(lib, src)
+    rc1, got = describe(lib, dst)
+    assert rc0 == 0 and rc1 == 0, got
+
+    def body(text):                                              # attributes, dimensions, variable types and names; not offsets / container names
+        keep = []
+        for line in text.splitlines()[1:]:
+            keep.append(line.split(" begin=")[0])
+        return sorted(keep)
+    assert body(got) == body(want)
+    for name, arr in arrays.items():
+        np.testing.assert_array_equal(read_var(lib, dst, name), arr.astype(np.float64))
+
+
 def test_unreadable_containers_are_rejected_loudly(dsb, tmp_path):
     lib = dsb.lib()
     lib.dsb200_engine_last_error.restype = C.c_char_p
