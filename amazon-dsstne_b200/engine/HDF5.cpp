@@ -13,10 +13,18 @@
 // attributes are the global attributes; _NCProperties, _Netcdf4Dimid, _Netcdf4Coordinates, DIMENSION_LIST, REFERENCE_LIST, CLASS, NAME
 // and _nc3_strict are bookkeeping and are dropped.
 // Dense storage is read by WALKING the heap's direct blocks (objects are packed from the start of a block in a file that was written
-// once and never edited), not through the v2 B-tree name index.  Not handled, and refused by name: chunked / filtered (compressed)
-// variables, variable-length and compound variable types, sub-groups.  DSSTNE's files have fixed-size 1-D variables: contiguous.
+// once and never edited), not through the v2 B-tree name index.
+// Chunked variables (layout v3: a version-1 B-tree of node type 1 over the chunks [III.A.1, IV.A.2.i]) with the filters netCDF-4 can
+// switch on -- shuffle, deflate (zlib), fletcher32 (stripped, not verified) [IV.A.2.l] -- are assembled by read_chunked(); never-written
+// chunks read as the fill value [IV.A.2.f].  DSSTNE's own files have fixed-size 1-D variables and are contiguous; chunked ones come
+// out of `nccopy -d` or of tools that declare the examples dimension unlimited.
+// Not handled, and refused by name: the version-4 chunk indexes (HDF5 >= 1.10 "latest format" only, which netCDF does not write),
+// other filters (szip, zstd ...), variable-length and compound variable types, sub-groups.
 #include "NetCDF.h"
 
+#include <zlib.h>
+
+#include <algorithm>
 #include <cstdio>
 #include <cstring>
 #include <functional>
@@ -56,6 +64,27 @@ struct Reader {
     {
         const uint64_t v = le(p, so);
         return (so < 8 && v == ((1ull << (8 * so)) - 1)) ? UNDEF : v;
+    }
+
+    // ---- chunk index: version-1 B-tree, node type 1; a key is {chunk bytes, filter mask, rank + 1 element offsets}
+    void chunk_tree(uint64_t at, size_t rank, std::vector<Var::Chunk>& out, int depth = 0) const
+    {
+        if (depth > 32) fail("chunk B-tree deeper than 32 levels");
+        const std::vector<uint8_t> h = get(at, 8 + 2 * so);
+        if (memcmp(h.data(), "TREE", 4) != 0 || h[4] != 1) fail("chunk index at " + std::to_string(at) + " is not a raw-data B-tree node");
+        const int level = h[5];
+        const size_t used = (size_t)le(&h[6], 2), key = 8 + 8 * (rank + 1);
+        const std::vector<uint8_t> b = get(at + 8 + 2 * so, used * (key + so) + key);
+        for (size_t i = 0; i < used; i++) {
+            const uint8_t* k = &b[i * (key + so)];
+            const uint64_t child = addr(k + key);
+            if (child == UNDEF) continue;
+            if (level > 0) { chunk_tree(child, rank, out, depth + 1); continue; }
+            Var::Chunk c;
+            c.addr = child; c.bytes = (uint32_t)le(k, 4); c.filterMask = (uint32_t)le(k + 4, 4);
+            for (size_t d = 0; d < rank; d++) c.start.push_back(le(k + 8 + 8 * d, 8));
+            out.push_back(c);
+        }
     }
 
     // ---- object header -> messages
@@ -422,17 +451,18 @@ void parse(FILE* f, const std::string& fname, std::vector<Dim>& dims, std::vecto
     for (const Att& a : all) if (!hidden(a.name)) atts.push_back(a);
 
     // ---- datasets: dimensions first, then variables
-    struct DS { std::string name; std::vector<uint64_t> dims; uint64_t nelems; TypeInfo t; std::vector<Att> atts; bool dimScale, pureDim; uint64_t begin; std::vector<uint8_t> inl; bool hasInline; };
+    struct DS { std::string name; std::vector<uint64_t> dims; uint64_t nelems; TypeInfo t; std::vector<Att> atts; bool dimScale, pureDim; uint64_t begin; std::vector<uint8_t> inl; bool hasInline;
+                bool chunked = false; std::vector<uint64_t> chunkShape; std::vector<uint32_t> filters; std::vector<uint8_t> fill; std::vector<Var::Chunk> chunks; };
     std::vector<DS> sets;
     for (const auto& l : links) {
         if (l.second == UNDEF) continue;
         const std::vector<Msg> ms = r.object(l.second);
-        const Msg* space = nullptr; const Msg* type = nullptr; const Msg* layout = nullptr;
+        const Msg* space = nullptr; const Msg* type = nullptr; const Msg* layout = nullptr; const Msg* pipeline = nullptr; const Msg* fillv = nullptr;
         bool group = false;
         for (const Msg& m : ms) {
             if (m.type == 0x01) space = &m; else if (m.type == 0x03) type = &m; else if (m.type == 0x08) layout = &m;
             else if (m.type == 0x11 || m.type == 0x02) group = true;
-            if (m.type == 0x0B) r.fail("variable " + l.first + " is stored through a filter pipeline (compressed): rewrite it with `nccopy -d 0`");
+            else if (m.type == 0x0B) pipeline = &m; else if (m.type == 0x05) fillv = &m;
         }
         if (group || !space || !type || !layout) continue;                      // sub-groups and committed types: not part of a DSSTNE file
         DS d; d.name = l.first; d.hasInline = false; d.begin = 0;
@@ -449,8 +479,51 @@ void parse(FILE* f, const std::string& fname, std::vector<Dim>& dims, std::vecto
         if (L[0] == 3 || L[0] == 4) {
             if (L[1] == 0) { const size_t n = (size_t)Reader::le(&L[2], 2); if (4 + n > L.size()) r.fail("compact layout of " + l.first); d.inl.assign(L.begin() + 4, L.begin() + 4 + n); d.hasInline = true; }
             else if (L[1] == 1) d.begin = r.addr(&L[2]);
-            else r.fail("variable " + l.first + " is chunked; DSSTNE variables are fixed-size and contiguous (rewrite it with `nccopy -k cdf5` or without chunking)");
+            else if (L[1] == 2 && L[0] == 3) {
+                const size_t rank1 = L.size() > 2 ? L[2] : 0;                   // dimensionality = rank + 1 (the last "dimension" is the element size)
+                if (rank1 < 2 || L.size() < 3 + r.so + 4 * rank1 || rank1 - 1 != d.dims.size()) r.fail("chunked layout of " + l.first);
+                const uint64_t tree = r.addr(&L[3]);
+                for (size_t i = 0; i + 1 < rank1; i++) {
+                    d.chunkShape.push_back(Reader::le(&L[3 + r.so + 4 * i], 4));
+                    if (d.chunkShape.back() == 0) r.fail("chunked layout of " + l.first + " has an empty chunk");
+                }
+                if (Reader::le(&L[3 + r.so + 4 * (rank1 - 1)], 4) != d.t.size) r.fail("chunk element size of " + l.first + " differs from its type");
+                d.chunked = true;
+                if (tree != UNDEF) r.chunk_tree(tree, rank1 - 1, d.chunks);
+                for (Var::Chunk& c : d.chunks) c.addr += r.base;
+            }
+            else r.fail("variable " + l.first + " uses a version-4 chunk index (HDF5 'latest format'); rewrite it with `nccopy` (netCDF writes the version-3 layout)");
         } else r.fail("data layout message version " + std::to_string(L[0]) + " of " + l.first);
+        if (pipeline) {
+            if (!d.chunked) r.fail("variable " + l.first + " has a filter pipeline but is not chunked");
+            const std::vector<uint8_t>& P = pipeline->data;
+            if (P.size() < 2 || (P[0] != 1 && P[0] != 2)) r.fail("filter pipeline of " + l.first);
+            size_t p = P[0] == 1 ? 8 : 2;
+            for (int i = 0; i < P[1]; i++) {
+                if (p + 6 > P.size()) r.fail("filter pipeline of " + l.first + " is truncated");
+                const uint32_t id = (uint32_t)Reader::le(&P[p], 2); p += 2;
+                size_t nameLen = 0;
+                if (P[0] == 1 || id >= 256) { nameLen = (size_t)Reader::le(&P[p], 2); p += 2; }
+                p += 2;                                                         // flags (optional bit): a skipped filter shows in the chunk's mask
+                const size_t nvals = (size_t)Reader::le(&P[p], 2); p += 2;
+                p += P[0] == 1 ? ((nameLen + 7) & ~(size_t)7) : nameLen;
+                p += 4 * nvals;
+                if (P[0] == 1 && (nvals & 1)) p += 4;
+                if (p > P.size()) r.fail("filter pipeline of " + l.first + " is truncated");
+                if (id < 1 || id > 3) r.fail("variable " + l.first + " is stored through filter " + std::to_string(id) + "; only shuffle, deflate and fletcher32 are read (rewrite it with `nccopy -d 0`)");
+                d.filters.push_back(id);
+            }
+        }
+        if (fillv && d.chunked) {                                               // fill value message v1 / v2 / v3
+            const std::vector<uint8_t>& F = fillv->data;
+            size_t p = 0; bool defined = false;
+            if (F.size() >= 4 && (F[0] == 1 || F[0] == 2)) { defined = F[0] == 1 || F[3] != 0; p = 4; }
+            else if (F.size() >= 2 && F[0] == 3) { defined = (F[1] & 0x20) != 0; p = 2; }
+            if (defined && p + 4 <= F.size()) {
+                const size_t n = (size_t)Reader::le(&F[p], 4);
+                if (n == d.t.size && p + 4 + n <= F.size()) d.fill.assign(F.begin() + p + 4, F.begin() + p + 4 + n);
+            }
+        }
         sets.push_back(d);
     }
     for (const DS& d : sets)
@@ -466,6 +539,10 @@ void parse(FILE* f, const std::string& fname, std::vector<Dim>& dims, std::vecto
         v.littleEndian = d.t.littleEndian;
         v.hasInline = d.hasInline; v.inlineData = d.inl;
         if (d.begin == UNDEF && !d.hasInline) { v.hasInline = true; v.inlineData.assign(v.vsize, 0); }    // never written: the fill value (zero)
+        if (d.chunked) {
+            v.chunked = true; v.begin = 0; v.chunkElemBytes = d.t.size;
+            v.shape = d.dims; v.chunkShape = d.chunkShape; v.filters = d.filters; v.fill = d.fill; v.chunks = d.chunks;
+        }
         for (uint64_t n : d.dims) {                                             // DIMENSION_LIST is not followed: dimensions are matched by size
             uint32_t id = 0; bool found = false;
             for (size_t i = 0; i < dims.size(); i++) if (dims[i].size == n && (dims[i].name == d.name || !found)) { id = (uint32_t)i; found = true; if (dims[i].name == d.name) break; }
@@ -473,6 +550,71 @@ void parse(FILE* f, const std::string& fname, std::vector<Dim>& dims, std::vecto
         }
         for (const Att& a : d.atts) if (!hidden(a.name)) v.atts.push_back(a);
         vars.push_back(v);
+    }
+}
+
+// Chunks -> the variable's bytes in row-major order.  The pipeline is undone last filter first; a set bit i in a chunk's mask means
+// filter i was skipped for that chunk when it was written.
+void read_chunked(FILE* f, const std::string& fname, const Var& v, std::vector<uint8_t>& out)
+{
+    auto fail = [&](const std::string& what) -> void { throw Error("netCDF-4 / HDF5: " + fname + ": variable " + v.name + ": " + what); };
+    const size_t rank = v.shape.size();
+    const uint64_t eb = v.chunkElemBytes;
+    if (rank == 0 || v.chunkShape.size() != rank || eb == 0) fail("chunked layout without a shape");
+    uint64_t total = eb, chunkBytes = eb;
+    for (size_t d = 0; d < rank; d++) { total *= v.shape[d]; chunkBytes *= v.chunkShape[d]; }
+    if (chunkBytes > (1ull << 32)) fail("chunks of more than 4 GiB");
+    out.resize(total);
+    if (v.fill.size() == eb) for (uint64_t i = 0; i < total; i += eb) memcpy(&out[i], v.fill.data(), eb);
+    else std::fill(out.begin(), out.end(), (uint8_t)0);
+
+    std::vector<uint64_t> stride(rank, eb);                                    // bytes per step of dimension d in the variable / in a chunk
+    std::vector<uint64_t> cstride(rank, eb);
+    for (size_t d = rank - 1; d-- > 0;) { stride[d] = stride[d + 1] * v.shape[d + 1]; cstride[d] = cstride[d + 1] * v.chunkShape[d + 1]; }
+
+    std::vector<uint8_t> raw, tmp;
+    for (const Var::Chunk& c : v.chunks) {
+        if (c.start.size() != rank) fail("chunk key of the wrong rank");
+        raw.resize(c.bytes);
+        if (fseeko(f, (off_t)c.addr, SEEK_SET) != 0 || (c.bytes && fread(raw.data(), 1, c.bytes, f) != c.bytes)) fail("truncated chunk at offset " + std::to_string(c.addr));
+        for (size_t i = v.filters.size(); i-- > 0;) {
+            if ((c.filterMask >> i) & 1) continue;
+            if (v.filters[i] == 3) {                                             // fletcher32: four trailing bytes
+                if (raw.size() < 4) fail("checksummed chunk shorter than its checksum");
+                raw.resize(raw.size() - 4);
+            } else if (v.filters[i] == 1) {                                      // deflate
+                tmp.resize(chunkBytes + 64);
+                uLongf n = (uLongf)tmp.size();
+                const int rc = uncompress(tmp.data(), &n, raw.data(), (uLong)raw.size());
+                if (rc != Z_OK) fail("chunk at offset " + std::to_string(c.addr) + " does not inflate (zlib " + std::to_string(rc) + ")");
+                raw.assign(tmp.begin(), tmp.begin() + n);
+            } else if (v.filters[i] == 2) {                                      // shuffle: byte b of every element stored together
+                const size_t n = raw.size() / eb;
+                if (eb > 1 && n > 1) {
+                    tmp.resize(raw.size());
+                    for (size_t b = 0; b < eb; b++) for (size_t e = 0; e < n; e++) tmp[e * eb + b] = raw[b * n + e];
+                    for (size_t r = n * eb; r < raw.size(); r++) tmp[r] = raw[r];
+                    raw.swap(tmp);
+                }
+            }
+        }
+        if (raw.size() != chunkBytes) fail("chunk at offset " + std::to_string(c.addr) + " holds " + std::to_string(raw.size()) + " bytes, its shape says " + std::to_string(chunkBytes));
+        bool outside = false;
+        for (size_t d = 0; d < rank; d++) if (c.start[d] >= v.shape[d]) outside = true;
+        if (outside) continue;
+        const uint64_t run = std::min<uint64_t>(v.chunkShape[rank - 1], v.shape[rank - 1] - c.start[rank - 1]) * eb;
+        std::vector<uint64_t> at(rank, 0);                                      // odometer over the chunk's rows (all dimensions but the last)
+        for (;;) {
+            uint64_t dst = 0, src = 0; bool inside = true;
+            for (size_t d = 0; d + 1 < rank; d++) {
+                if (c.start[d] + at[d] >= v.shape[d]) inside = false;
+                dst += (c.start[d] + at[d]) * stride[d]; src += at[d] * cstride[d];
+            }
+            if (inside) memcpy(&out[dst + c.start[rank - 1] * eb], &raw[src], run);
+            size_t d = rank - 1;
+            while (d-- > 0) { if (++at[d] < v.chunkShape[d]) break; at[d] = 0; }
+            if (d == (size_t)-1) break;
+        }
     }
 }
 

@@ -221,6 +221,11 @@ void File::read_raw(const Var& v, std::vector<uint8_t>& bytes) const
         bytes.assign(v.inlineData.begin(), v.inlineData.begin() + n);
         return;
     }
+    if (v.chunked) {
+        hdf5::read_chunked(f, _fname, v, bytes);
+        if (bytes.size() != n) throw Error("netCDF: variable " + v.name + " has " + std::to_string(bytes.size()) + " bytes of chunks for " + std::to_string(n) + " in " + _fname);
+        return;
+    }
     bytes.resize(n);
 #if defined(_WIN32)
     if (_fseeki64(f, (long long)v.begin, SEEK_SET) != 0)

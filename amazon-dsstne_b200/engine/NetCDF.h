@@ -57,6 +57,14 @@ struct Var {
     bool littleEndian = false;                        // netCDF-4 / HDF5 variables are stored in the writer's byte order (classic: big-endian)
     bool hasInline = false;                           // HDF5 compact layout (or a never-written variable): the bytes live in the header
     std::vector<uint8_t> inlineData;
+    // HDF5 chunked layout (what netCDF-4 uses for compressed variables and variables over an unlimited dimension): HDF5.cpp reads it
+    struct Chunk { uint64_t addr; uint32_t bytes; uint32_t filterMask; std::vector<uint64_t> start; };
+    bool chunked = false;
+    uint32_t chunkElemBytes = 0;
+    std::vector<uint64_t> shape, chunkShape;          // in elements
+    std::vector<uint32_t> filters;                    // the pipeline in write order: 1 deflate, 2 shuffle, 3 fletcher32
+    std::vector<uint8_t> fill;                        // one element: what never-written chunks read as (empty: zero)
+    std::vector<Chunk> chunks;
 };
 
 class File {
@@ -106,6 +114,8 @@ private:
 namespace hdf5 {
 // netCDF-4 container -> the same dimension / attribute / variable tables the classic parser fills (HDF5.cpp)
 void parse(FILE* f, const std::string& fname, std::vector<Dim>& dims, std::vector<Att>& atts, std::vector<Var>& vars);
+// bytes of a chunked variable in row-major order, filters undone, in the file's byte order
+void read_chunked(FILE* f, const std::string& fname, const Var& v, std::vector<uint8_t>& bytes);
 }
 
 }  // namespace nc

@@ -250,14 +250,114 @@ def dimension_scale(img, name, size, dimid, hdr, av):
     return hdr(img, msgs)
 
 
-def variable(img, name, arr, hdr, av, how="contiguous", big=False):
+def fletcher32(b):
+    """HDF5's checksum of a chunk (H5_checksum_fletcher32): 16-bit big-endian words, both sums folded modulo 65535"""
+    s1 = s2 = 0
+    for i in range(0, len(b) - 1, 2):
+        s1 = (s1 + ((b[i] << 8) | b[i + 1])) % 65535
+        s2 = (s2 + s1) % 65535
+    if len(b) % 2:
+        s1 = (s1 + (b[-1] << 8)) % 65535
+        s2 = (s2 + s1) % 65535
+    return (s2 << 16) | s1
+
+
+def filter_pipeline(filters, elem, version):
+    """message 0x0B: filters = names out of shuffle / deflate / fletcher32 in pipeline order"""
+    ids = {"deflate": (1, [6]), "shuffle": (2, [elem]), "fletcher32": (3, [])}
+    out = struct.pack("<BB6x", 1, len(filters)) if version == 1 else struct.pack("<BB", 2, len(filters))
+    for f in filters:
+        fid, vals = ids[f]
+        if version == 1:
+            nm = pad8(f.encode() + b"\0")
+            out += struct.pack("<HHHH", fid, len(nm), 1 if f != "fletcher32" else 0, len(vals)) + nm + b"".join(struct.pack("<I", x) for x in vals)
+            if len(vals) % 2:
+                out += b"\0" * 4
+        else:
+            out += struct.pack("<HHH", fid, 1 if f != "fletcher32" else 0, len(vals)) + b"".join(struct.pack("<I", x) for x in vals)
+    return out
+
+
+def chunk_btree(img, entries, end, fanout=64):
+    """version-1 B-tree of node type 1 over 1-D chunks; entries = [(start element, stored bytes, filter mask, address)], in order"""
+    def key(size, mask, start):
+        start = start if isinstance(start, tuple) else (start,)
+        return struct.pack("<II", size, mask) + b"".join(struct.pack("<Q", x) for x in start) + struct.pack("<Q", 0)
+
+    def node(level, items, upper):                                 # items = [(first start, size, mask, child address)]
+        body = b"TREE" + struct.pack("<BBHQQ", 1, level, len(items), UNDEF, UNDEF)
+        for start, size, mask, child in items:
+            body += key(size, mask, start) + struct.pack("<Q", child)
+        body += key(0, 0, upper)
+        body += b"\0" * max(0, 24 + (2 * 32 + 1) * len(key(0, 0, upper)) + 2 * 32 * 8 - len(body))    # nodes are allocated for 2 K = 64 children
+        return img.add(body)
+    level, items = 0, entries
+    while True:
+        groups = [items[i:i + fanout] for i in range(0, len(items), fanout)] or [[]]
+        nodes = []
+        for gi, g in enumerate(groups):
+            upper = groups[gi + 1][0][0] if gi + 1 < len(groups) else end
+            nodes.append((g[0][0] if g else 0, g[0][1] if g else 0, g[0][2] if g else 0, node(level, g, upper)))
+        if len(nodes) == 1:
+            return nodes[0][3]
+        level, items = level + 1, nodes
+
+
+def variable(img, name, arr, hdr, av, how="contiguous", big=False, chunk=0, filters=(), skip_filter_on=None, holes=()):
+    """how = contiguous | compact | v4 (layout message version 4) | chunked (chunk elements per chunk, `filters` applied in order;
+    chunk number skip_filter_on is stored with its deflate step skipped and flagged in its mask; chunk numbers in `holes` are never written)"""
     raw = arr.astype(arr.dtype.newbyteorder(">" if big else "<")).tobytes()
+    extra = []
     if how == "compact":
         lay = layout_compact(raw)
+    elif how == "chunked":
+        import zlib
+        elem = arr.dtype.itemsize
+        entries = []
+        if arr.ndim == 2:                                           # chunk = (rows, columns); chunks in row-major order of their origin
+            origins = [(r0, c0) for r0 in range(0, arr.shape[0], chunk[0]) for c0 in range(0, arr.shape[1], chunk[1])]
+            stored = arr.astype(arr.dtype.newbyteorder(">" if big else "<"))
+        else:
+            origins = list(range(0, len(arr), chunk))
+        for ci, first in enumerate(origins):
+            if ci in holes:
+                continue
+            if arr.ndim == 2:
+                tile = np.zeros(chunk, dtype=stored.dtype)
+                part = stored[first[0]:first[0] + chunk[0], first[1]:first[1] + chunk[1]]
+                tile[:part.shape[0], :part.shape[1]] = part
+                piece = tile.tobytes()
+            else:
+                piece = raw[first * elem:(first + chunk) * elem]
+                piece += b"\0" * (chunk * elem - len(piece))        # edge chunks are stored whole
+            mask = 0
+            for fi, f in enumerate(filters):
+                if f == "shuffle":
+                    piece = np.frombuffer(piece, dtype=np.uint8).reshape(-1, elem).T.tobytes()
+                elif f == "deflate":
+                    if ci == skip_filter_on:
+                        mask |= 1 << fi
+                    else:
+                        piece = zlib.compress(piece, 6)
+                elif f == "fletcher32":
+                    piece = piece + struct.pack("<I", fletcher32(piece))
+            entries.append((first, len(piece), mask, img.add(piece)))
+        if arr.ndim == 2:
+            tree = chunk_btree(img, entries, (-(-arr.shape[0] // chunk[0]) * chunk[0], 0)) if entries else UNDEF
+            lay = struct.pack("<BBBQIII", 3, 2, 3, tree, chunk[0], chunk[1], elem)
+        else:
+            tree = chunk_btree(img, entries, -(-len(arr) // chunk) * chunk) if entries else UNDEF
+            lay = struct.pack("<BBBQII", 3, 2, 2, tree, chunk, elem)
+        if filters:
+            extra.append((0x0B, filter_pipeline(filters, elem, 1 if av == 1 else 2)))
     else:
         doff = img.add(raw)
         lay = layout_contiguous(doff, len(raw), 4 if how == "v4" else 3)
-    msgs = [(0x01, dataspace([len(arr)], 1 if av == 1 else 2)), (0x03, datatype(arr.dtype, big=big)), (0x05, struct.pack("<BBBB", 2, 2, 0, 0)), (0x08, lay),
+    fill = struct.pack("<BBBB", 2, 2, 0, 0)
+    if holes:                                                       # a defined fill value: the element 7 (what the reader must return for the holes)
+        fv = np.array([7], dtype=arr.dtype.newbyteorder(">" if big else "<")).tobytes()
+        fill = struct.pack("<BBBBI", 2, 2, 0, 1, len(fv)) + fv if av == 1 else struct.pack("<BBI", 3, 0x20 | 0x09, len(fv)) + fv
+    msgs = [(0x01, dataspace(list(arr.shape), 1 if av == 1 else 2)), (0x03, datatype(arr.dtype, big=big)), (0x05, fill), (0x08, lay)] + extra + [
             (0x0C, attribute("DIMENSION_LIST", vlen_reference_type(), [1], struct.pack("<IQI", 1, UNDEF, 0), av))]
     return hdr(img, msgs, split_after=3 if how == "v4" else None)
 
@@ -368,8 +468,9 @@ def read_classic(path):
     return dims, gatts, variables
 
 
-def convert(src, dst, flavour):
-    """flavour "old": superblock v0, version-1 headers, symbol table;  "new": superblock v2, version-2 headers, dense links and attributes"""
+def convert(src, dst, flavour, storage=None):
+    """flavour "old": superblock v0, version-1 headers, symbol table;  "new": superblock v2, version-2 headers, dense links and attributes.
+    storage: None (contiguous) or a function (variable number, name, array) -> keyword arguments of variable() (how / chunk / filters ...)"""
     dims, gatts, variables = read_classic(src)
     img = Image()
     old = flavour == "old"
@@ -379,7 +480,10 @@ def convert(src, dst, flavour):
     for nm, dn, arr in variables:
         if arr.dtype.kind == "S":
             arr = np.frombuffer(arr.tobytes(), dtype=np.uint8)     # (char variables do not occur in the DSSTNE schemas)
-        objs.append((nm, variable(img, nm, arr, hdr, av, big=(len(objs) % 3 == 0))))
+        kw = dict(storage(len(objs), nm, arr)) if storage else {}
+        if "shape" in kw:                                          # store a 1-D variable as a 2-D one of the same row-major content
+            arr = arr.reshape(kw.pop("shape"))
+        objs.append((nm, variable(img, nm, arr, hdr, av, big=(len(objs) % 3 == 0), **kw)))
     amsg = [att_text("_NCProperties", "version=2,netcdf=4.8.1,hdf5=1.12.2", av)]
     for k, val in gatts:
         if isinstance(val, str):

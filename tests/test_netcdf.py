@@ -189,6 +189,84 @@ def test_netcdf4_container_with_a_network_sized_header(dsb, tmp_path, flavour):
         np.testing.assert_array_equal(read_var(lib, dst, name), arr.astype(np.float64))
 
 
+_STORAGE = {
+    "chunked": lambda i, nm, a: dict(how="chunked", chunk=37),
+    "deflate": lambda i, nm, a: dict(how="chunked", chunk=64, filters=("deflate",)),
+    "shuffle+deflate": lambda i, nm, a: dict(how="chunked", chunk=50, filters=("shuffle", "deflate")),
+    "shuffle+deflate+fletcher32": lambda i, nm, a: dict(how="chunked", chunk=128, filters=("shuffle", "deflate", "fletcher32"), skip_filter_on=1),
+    "fletcher32+deflate": lambda i, nm, a: dict(how="chunked", chunk=41, filters=("fletcher32", "deflate")),
+    "two-level index": lambda i, nm, a: dict(how="chunked", chunk=3, filters=("shuffle", "deflate") if i % 2 else ()),
+    "mixed": lambda i, nm, a: [dict(), dict(how="compact"), dict(how="chunked", chunk=1000, filters=("deflate",)), dict(how="chunked", chunk=1)][i % 4],
+}
+
+
+@pytest.mark.parametrize("flavour", ["old", "new"])
+@pytest.mark.parametrize("storage", sorted(_STORAGE))
+def test_netcdf4_chunked_and_compressed_variables(dsb, tmp_path, flavour, storage):
+    """what `nccopy -d N -s` or a writer with an unlimited examples dimension produces: variables cut into chunks behind a version-1
+    B-tree (one and two levels: 2 K = 64 children per node), stored through shuffle / deflate / fletcher32 in either order, one chunk
+    with its deflate step skipped (mask bit), chunks that do not divide the length; all seven element types of the DSSTNE schemas"""
+    lib = dsb.lib()
+    m = _fixture_module()
+    rng = np.random.default_rng(11)
+    src, dst = str(tmp_path / "d.nc"), str(tmp_path / f"d_{flavour}.nc")
+    arrays = {}
+    with netcdf_file(src, "w", version=2) as f:
+        f.datasets = np.int32(1)
+        for j, dt in enumerate(["f", "i", "d", "b", "h", "i", "f", "d"]):
+            n = [611, 257, 1, 300, 129, 64, 5000, 200][j]
+            f.createDimension(f"dim{j}", n)
+            v = f.createVariable(f"var{j}", dt, (f"dim{j}",))
+            np_dt = {"f": np.float32, "i": np.int32, "d": np.float64, "b": np.int8, "h": np.int16}[dt]
+            arrays[f"var{j}"] = (rng.integers(-5, 5, n) * 3).astype(np_dt) if j % 2 else (rng.standard_normal(n) * 50).astype(np_dt)
+            v[:] = arrays[f"var{j}"]
+    m.convert(src, dst, flavour, storage=_STORAGE[storage])
+    rc, text = describe(lib, dst)
+    assert rc == 0, text
+    for name, arr in arrays.items():
+        np.testing.assert_array_equal(read_var(lib, dst, name), arr.astype(np.float64), err_msg=f"{name} ({storage}, {flavour})")
+
+
+@pytest.mark.parametrize("flavour", ["old", "new"])
+def test_netcdf4_two_dimensional_chunks(dsb, tmp_path, flavour):
+    """not a DSSTNE layout, but what a generic tool may hand over: a 2-D variable in (rows, columns) tiles that overhang both edges;
+    read_var returns it row-major"""
+    lib = dsb.lib()
+    m = _fixture_module()
+    src, dst = str(tmp_path / "t.nc"), str(tmp_path / f"t_{flavour}.nc")
+    a = (np.random.default_rng(5).standard_normal(23 * 17) * 9).astype(np.float32)
+    with netcdf_file(src, "w", version=2) as f:
+        f.createDimension("n", a.size)
+        f.createVariable("v", "f", ("n",))[:] = a
+        f.createVariable("w", "f", ("n",))[:] = -a
+    m.convert(src, dst, flavour, storage=lambda i, nm, arr: dict(how="chunked", shape=(23, 17), chunk=(5, 4) if nm == "v" else (23, 17),
+                                                               filters=("shuffle", "deflate") if nm == "v" else (), holes=(3,) if nm == "v" else ()))
+    want = a.astype(np.float64).reshape(23, 17).copy()
+    want[0:5, 12:16] = 7                                                      # chunk number 3 of the first row of tiles
+    np.testing.assert_array_equal(read_var(lib, dst, "v").reshape(23, 17), want)
+    np.testing.assert_array_equal(read_var(lib, dst, "w"), -a.astype(np.float64))
+
+
+@pytest.mark.parametrize("flavour", ["old", "new"])
+def test_netcdf4_never_written_chunks_read_as_the_fill_value(dsb, tmp_path, flavour):
+    lib = dsb.lib()
+    m = _fixture_module()
+    src, dst = str(tmp_path / "h.nc"), str(tmp_path / f"h_{flavour}.nc")
+    a = np.arange(100, dtype=np.int32)
+    with netcdf_file(src, "w", version=2) as f:
+        f.createDimension("n", 100)
+        v = f.createVariable("v", "i", ("n",))
+        v[:] = a
+        w = f.createVariable("w", "f", ("n",))
+        w[:] = a.astype(np.float32)
+    m.convert(src, dst, flavour, storage=lambda i, nm, arr: dict(how="chunked", chunk=16, holes=(1, 6) if nm == "v" else tuple(range(7)), filters=("deflate",)))
+    want = a.astype(np.float64).copy()
+    want[16:32] = 7
+    want[96:] = 7
+    np.testing.assert_array_equal(read_var(lib, dst, "v"), want)
+    np.testing.assert_array_equal(read_var(lib, dst, "w"), np.full(100, 7.0))     # no chunk written at all: no index either
+
+
 def test_unreadable_containers_are_rejected_loudly(dsb, tmp_path):
     lib = dsb.lib()
     lib.dsb200_engine_last_error.restype = C.c_char_p
@@ -196,16 +274,45 @@ def test_unreadable_containers_are_rejected_loudly(dsb, tmp_path):
     p1.write_bytes(b"\x89HDF\r\n\x1a\n" + bytes(64))                          # a signature and nothing behind it
     rc, _ = describe(lib, str(p1))
     assert rc != 0 and b"HDF5" in lib.dsb200_engine_last_error()
-    # a chunked variable: named, with the way out
+    # chunk indexes of HDF5's "latest format" (layout message version 4, class chunked) and foreign filters: named, with the way out
     m = _fixture_module()
     import struct
     orig = m.layout_contiguous
-    m.layout_contiguous = lambda addr, size, version=3: struct.pack("<BBBQII", 3, 2, 2, addr, 4, 4) if addr != m.UNDEF else orig(addr, size, version)
-    p4 = str(tmp_path / "chunked.nc")
-    m.write_old(p4)
+    try:
+        m.layout_contiguous = lambda addr, size, version=3: struct.pack("<BBBBBQ", 4, 2, 0, 1, 4, addr) if addr != m.UNDEF else orig(addr, size, version)
+        p4 = str(tmp_path / "v4index.nc")
+        m.write_old(p4)
+    finally:
+        m.layout_contiguous = orig
     rc, _ = describe(lib, p4)
     err = lib.dsb200_engine_last_error()
-    assert rc != 0 and b"chunked" in err and b"nccopy" in err
+    assert rc != 0 and b"version-4 chunk index" in err and b"nccopy" in err
+    origp = m.filter_pipeline
+    try:
+        m.filter_pipeline = lambda filters, elem, version: origp(filters, elem, version).replace(struct.pack("<H", 1), struct.pack("<H", 4), 1) if version == 2 else origp(filters, elem, version)
+        src, p5 = str(tmp_path / "z.nc"), str(tmp_path / "szip.nc")
+        with netcdf_file(src, "w", version=2) as f:
+            f.createDimension("n", 10)
+            f.createVariable("v", "i", ("n",))[:] = np.arange(10, dtype=np.int32)
+        m.convert(src, p5, "new", storage=lambda i, nm, a: dict(how="chunked", chunk=4, filters=("deflate",)))
+    finally:
+        m.filter_pipeline = origp
+    rc, _ = describe(lib, p5)
+    err = lib.dsb200_engine_last_error()
+    assert rc != 0 and b"filter 4;" in err and b"nccopy" in err, err
+    # a chunk that does not inflate: the error names the variable and the offset
+    p6 = str(tmp_path / "corrupt.nc")
+    m.convert(src, p6, "old", storage=lambda i, nm, a: dict(how="chunked", chunk=4, filters=("deflate",)))
+    blob = bytearray(open(p6, "rb").read())
+    at = blob.index(b"\x78\x9c")                                            # first zlib stream
+    blob[at + 2:at + 6] = b"\xff\xff\xff\xff"
+    open(p6, "wb").write(bytes(blob))
+    assert describe(lib, p6)[0] == 0                                         # the header is fine ...
+    out = np.zeros(10)
+    n = C.c_uint64()
+    rc = lib.dsb200_netcdf_read_var(p6.encode(), b"v", out.ctypes.data_as(C.c_void_p), C.c_uint64(10), C.byref(n))
+    err = lib.dsb200_engine_last_error()
+    assert rc != 0 and b"variable v" in err and b"does not inflate" in err, err       # ... the data is not
     p2 = tmp_path / "junk.nc"
     p2.write_bytes(b"hello world, not a netcdf file")
     rc, _ = describe(lib, str(p2))
