@@ -151,6 +151,10 @@ class Context:
                                                  C.c_int(int(denoised)), C.c_uint32(N), _ptr(tstart), _ptr(tend),
                                                  _ptr(tindex), _ptr(tdata)))
 
+    def transposed_capacity(self, ds, rows, N, count, tstart, total=None):
+        v = ds.view()
+        self.check(lib().dsb200_transposed_capacity(self.h, C.byref(v), C.c_uint32(rows), C.c_uint32(N), _ptr(count), _ptr(tstart), _ptr(total)))
+
     def sparse_wgrad(self, alpha, beta, tstart, tend, tindex, tdata, delta, dW):
         m, n = dW.shape
         self.check(lib().dsb200_sparse_wgrad(self.h, C.c_float(alpha), C.c_float(beta), C.c_uint32(m), C.c_uint32(n),

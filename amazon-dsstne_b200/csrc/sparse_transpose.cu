@@ -223,37 +223,68 @@ column_count_kernel(const uint64_t* __restrict__ start, const uint64_t* __restri
     }
 }
 
-// single CTA: exclusive scan of align32(count) -> tStart; total capacity -> *pTotal (may be NULL)
+// single CTA: exclusive scan of align32(count) -> tStart; total capacity -> *pTotal (may be NULL).  Tiles of 1024 x 8 columns:
+// every thread takes eight consecutive counts (two 16-byte loads when the table is aligned), so a warp reads 1 KB in one go and
+// the eight loads of a thread do not wait for each other; the running total is carried from tile to tile.
+constexpr int kScanItems = 8;
+
 __global__ void __launch_bounds__(1024)
 capacity_scan_kernel(const uint32_t* __restrict__ count, uint32_t N, uint32_t* __restrict__ tStart, uint32_t* __restrict__ pTotal)
 {
     __shared__ uint32_t sWarp[32];
+    __shared__ uint32_t sTile;
     const uint32_t tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const uint32_t per = (N + 1023) / 1024;
-    const uint32_t lo = min(tid * per, N), hi = min(lo + per, N);
-    uint32_t local = 0;
-    for (uint32_t i = lo; i < hi; i++) local += (count[i] + 31u) & ~31u;
-    uint32_t incl = local;
+    const bool vec = ((reinterpret_cast<uintptr_t>(count) | reinterpret_cast<uintptr_t>(tStart)) & 15) == 0;
+    uint32_t carry = 0;
+    for (uint64_t base = 0; base < N; base += 1024ull * kScanItems) {
+        const uint64_t first = base + (uint64_t)tid * kScanItems;
+        uint32_t v[kScanItems];
+        const bool whole = first + kScanItems <= N;
+        if (whole && vec) {
+            const uint4 a = __ldg(reinterpret_cast<const uint4*>(count + first)), b = __ldg(reinterpret_cast<const uint4*>(count + first) + 1);
+            v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+        } else {
 #pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-        const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
-        if (lane >= (uint32_t)o) incl += n;
-    }
-    if (lane == 31) sWarp[warp] = incl;
-    __syncthreads();
-    if (warp == 0) {
-        uint32_t w = sWarp[lane], wi = w;
+            for (int k = 0; k < kScanItems; k++) v[k] = (first + k < N) ? __ldg(count + first + k) : 0u;
+        }
+        uint32_t local = 0;
+#pragma unroll
+        for (int k = 0; k < kScanItems; k++) { v[k] = (v[k] + 31u) & ~31u; local += v[k]; }
+        uint32_t incl = local;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
-            const uint32_t n = __shfl_up_sync(0xffffffffu, wi, o);
-            if (lane >= (uint32_t)o) wi += n;
+            const uint32_t n = __shfl_up_sync(0xffffffffu, incl, o);
+            if (lane >= (uint32_t)o) incl += n;
         }
-        sWarp[lane] = wi - w;                                             // exclusive warp offsets
-        if (lane == 31 && pTotal) *pTotal = wi;
+        if (lane == 31) sWarp[warp] = incl;
+        __syncthreads();
+        if (warp == 0) {
+            const uint32_t w = sWarp[lane];
+            uint32_t wi = w;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const uint32_t n = __shfl_up_sync(0xffffffffu, wi, o);
+                if (lane >= (uint32_t)o) wi += n;
+            }
+            sWarp[lane] = wi - w;                                         // exclusive warp offsets
+            if (lane == 31) sTile = wi;
+        }
+        __syncthreads();
+        uint32_t run = carry + sWarp[warp] + incl - local;
+        carry += sTile;
+        if (whole && vec) {
+            uint4 a, b;
+            a.x = run; run += v[0]; a.y = run; run += v[1]; a.z = run; run += v[2]; a.w = run; run += v[3];
+            b.x = run; run += v[4]; b.y = run; run += v[5]; b.z = run; run += v[6]; b.w = run;
+            reinterpret_cast<uint4*>(tStart + first)[0] = a;
+            reinterpret_cast<uint4*>(tStart + first)[1] = b;
+        } else {
+#pragma unroll
+            for (int k = 0; k < kScanItems; k++) { if (first + k < N) tStart[first + k] = run; run += v[k]; }
+        }
+        __syncthreads();                                                  // sWarp / sTile are rewritten by the next tile
     }
-    __syncthreads();
-    uint32_t run = sWarp[warp] + incl - local;
-    for (uint32_t i = lo; i < hi; i++) { tStart[i] = run; run += (count[i] + 31u) & ~31u; }
+    if (tid == 0 && pTotal) *pTotal = carry;
 }
 
 }  // namespace dsb

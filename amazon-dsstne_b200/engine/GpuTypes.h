@@ -52,8 +52,9 @@ struct GpuContext {
                                               // sparse targets is deferred into the loss / delta pass and runs as dsb200_gemm_fwd_output_pass (Z never written)
     bool            _bP2PExchange = true;     // engine option "p2p_exchange" (default on): model-parallel exchange steps as one kernel over peer
                                               // memory (dsb200_p2p_*); falls back to NCCL when the peers cannot be mapped
-    bool            _bPinnedMirror = false;   // engine option "pinned_mirror" (experimental): NNDataSet::LoadSparseData uploads straight from
-                                              // the page-locked host mirror instead of copying every batch a second time into staging
+    bool            _bPinnedMirror = true;    // engine option "pinned_mirror" (default on): NNDataSet::LoadSparseData uploads straight from the
+                                              // page-locked host mirror instead of copying every batch a second time into staging (0, or a
+                                              // failed cudaHostRegister: the two-copy staging path)
     long long       _totalGPUMemory, _totalCPUMemory;
 
     GpuContext();

@@ -431,9 +431,11 @@ void NNLayer::BackPropagateFullyConnected(uint32_t position, uint32_t batch)
                         // produced inside NNWeight::UpdateWeights, fused with the optimizer: dW is never written
                         w->_bDeferredSparseGradient = true;
                         w->_pDeferredDelta = GetDeltaBuffer();
-                    } else
+                    } else {
+                        net->WaitForTransposed();
                         in->_pDataSet->CalculateSparseTransposedWeightGradient(sgemm_alpha, sgemm_beta, in->_localStride, _localStride,
                                                                                GetDeltaBuffer(), w->_pbWeightGradient->_pDevData);
+                    }
                 } else if (net->FusionEnabled() && net->_mode == Training && sgemm_beta == (NNFloat)0.0 && w->_sharingCount == 1 &&
                            SmallDense(batch, in->_localStride, _localStride)) {
                     // small dense layer: gradient + optimizer + bias update as ONE launch from NNWeight::UpdateWeights
@@ -516,8 +518,10 @@ void NNLayer::BackPropagateFullyConnected(uint32_t position, uint32_t batch)
                     if (net->FusionEnabled() && net->_mode == Training && sgemm_beta == (NNFloat)0.0 && w->_sharingCount == 1 && (_stride % 4 == 0)) {
                         w->_bDeferredSparseGradient = true;                       // produced inside NNWeight::UpdateWeights, fused with the optimizer
                         w->_pDeferredDelta = pD;
-                    } else
+                    } else {
+                        net->WaitForTransposed();
                         in->_pDataSet->CalculateSparseTransposedWeightGradient(sgemm_alpha, sgemm_beta, in->_localStride, _stride, pD, w->_pbWeightGradient->_pDevData);
+                    }
                 } else {
                     getGpu().Check(dsb200_gemm_dw(ctx, batch, in->_localStride, _stride, sgemm_alpha, in->GetUnitBuffer(), pD, sgemm_beta,
                                                   w->_pbWeightGradient->_pDevData), "dsb200_gemm_dw");

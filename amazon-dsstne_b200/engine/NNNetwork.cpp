@@ -72,6 +72,8 @@ NNNetwork::NNNetwork(NNNetworkDescriptor& d, uint32_t batch)
     RTERROR(cudaEventCreateWithFlags(&_forkEvent, cudaEventDisableTiming), "NNNetwork: cudaEventCreate");
     RTERROR(cudaEventCreateWithFlags(&_joinEvent, cudaEventDisableTiming), "NNNetwork: cudaEventCreate");
     RTERROR(cudaEventCreateWithFlags(&_prepEvent, cudaEventDisableTiming), "NNNetwork: cudaEventCreate");
+    RTERROR(cudaEventCreateWithFlags(&_regEvent, cudaEventDisableTiming), "NNNetwork: cudaEventCreate");
+    RTERROR(cudaEventCreateWithFlags(&_lossPassEvent, cudaEventDisableTiming), "NNNetwork: cudaEventCreate");
     RTERROR(cudaEventCreateWithFlags(&_updateEvent, cudaEventDisableTiming), "NNNetwork: cudaEventCreate");
     RTERROR(cudaStreamCreateWithFlags(&_sideStream, cudaStreamNonBlocking), "NNNetwork: cudaStreamCreate");
 }
@@ -85,6 +87,8 @@ NNNetwork::~NNNetwork()
     if (_forkEvent) cudaEventDestroy(_forkEvent);
     if (_joinEvent) cudaEventDestroy(_joinEvent);
     if (_prepEvent) cudaEventDestroy(_prepEvent);
+    if (_regEvent) cudaEventDestroy(_regEvent);
+    if (_lossPassEvent) cudaEventDestroy(_lossPassEvent);
     if (_updateEvent) cudaEventDestroy(_updateEvent);
     if (_sideStream) cudaStreamDestroy(_sideStream);
 }
@@ -440,9 +444,14 @@ void NNNetwork::PredictTrainingBatch(uint32_t layers)
 }
 
 // Everything of a training step that depends only on the data batch or on the weights as the last update left them runs on the
-// side stream BESIDE the forward pass: the transposed sparse matrix of the input batch (consumed by the sparse weight gradient at
-// the end of the step), the target bitmap of the fused output-layer forward, the hi / lo copies of the output weights for the
-// input-delta kernel, and the regularisation error.  _prepEvent marks the first three, _joinEvent the last.
+// side stream BESIDE the forward pass, in the order the main stream needs it:
+//   _prepEvent  the target bitmap of the fused output-layer forward and the hi / lo copies of the output weights for the input-delta
+//               kernel -- the loss pass waits for it ~40 us into the step;
+//   _regEvent   the regularisation error -- the loss read-back waits for it;
+//   _joinEvent  the transposed sparse matrix of the input batch (for a streamed batch including its capacity table, built on the
+//               device) -- only the sparse weight gradient at the end of the step reads it: WaitForTransposed().
+// (Round-2 step trace, tools/e2e_probe.py: with one event for all of it the loss left the device 140 us into the step, 40 us
+// after the forward kernels were through, 162 us for a streamed batch.)
 void NNNetwork::LaunchBatchPreparation(NNFloat lambda, NNFloat lambda1)
 {
     uint32_t batch = _batch;
@@ -452,7 +461,6 @@ void NNNetwork::LaunchBatchPreparation(NNFloat lambda, NNFloat lambda1)
     RTERROR(cudaEventRecord(_forkEvent, s), "LaunchBatchPreparation fork");
     RTERROR(cudaStreamWaitEvent(_sideStream, _forkEvent, 0), "LaunchBatchPreparation fork wait");
     getGpu().Check(dsb200_ctx_set_stream(ctx, _sideStream), "dsb200_ctx_set_stream");
-    LoadBatch();
     for (auto l : _vOutputLayer) {
         if (!getGpu()._bFuseOutputGemm || !l->FusedOutputEligible(_errorFunction) || l->_vIncomingLayer.size() != 1) continue;
         if (l->_activation != Sigmoid || !l->_pDataSet || !(l->_pDataSet->_attributes & NNDataSetEnums::Boolean)) continue;
@@ -471,9 +479,19 @@ void NNNetwork::LaunchBatchPreparation(NNFloat lambda, NNFloat lambda1)
             if (!w->_bShared)
                 getGpu().Check(dsb200_regularization_error_async(ctx, lambda, lambda1, w->_pbWeight->_pDevData, w->_localSize, acc + 1),
                                "dsb200_regularization_error_async");
+    RTERROR(cudaEventRecord(_regEvent, _sideStream), "LaunchBatchPreparation regularisation event");
+    LoadBatch();
     getGpu().Check(dsb200_ctx_set_stream(ctx, s), "dsb200_ctx_set_stream");
     RTERROR(cudaEventRecord(_joinEvent, _sideStream), "LaunchBatchPreparation join");
     _bBatchPrepared = true;
+    _bTransposePending = true;
+}
+
+void NNNetwork::WaitForTransposed()
+{
+    if (!_bTransposePending) return;
+    RTERROR(cudaStreamWaitEvent(getGpu().GetStream(), _joinEvent, 0), "WaitForTransposed");
+    _bTransposePending = false;
 }
 
 NNFloat NNNetwork::ReadErrorAccumulator()
@@ -496,17 +514,24 @@ void NNNetwork::LaunchError(NNFloat lambda, NNFloat lambda1)
         RTERROR(cudaMemsetAsync(acc, 0, 2 * sizeof(unsigned long long), s), "LaunchError memset");
         LaunchRegularization(lambda, lambda1, false);
     }
-    if (_bRegularizationLaunched) RTERROR(cudaStreamWaitEvent(s, _prepEvent, 0), "LaunchError prep wait");   // target bitmap, transposed matrix, W copies
+    if (_bRegularizationLaunched) RTERROR(cudaStreamWaitEvent(s, _prepEvent, 0), "LaunchError prep wait");   // target bitmap, W copies
     _bRegularizationLaunched = false;
     for (auto l : _vOutputLayer) l->CalculateErrorAsync(_position, batch, _errorFunction, acc);
     if (_bStepReadsRecorded) {
-        // every reader of the data sets' CSR buffers in this step has been launched (sparse Z, the side-stream preparation the prep event
-        // covers, the loss / delta pass): the next batch may be uploaded beside the backward pass (NNDataSet::BeginUpload)
+        // every reader of the data sets' CSR buffers in this step has been launched -- sparse Z and the loss / delta pass on this stream,
+        // the target bitmap and the transposed matrix on the side stream: the event is recorded where both streams are past them, and
+        // the next batch may be uploaded beside the backward pass (NNDataSet::BeginUpload)
         getGpu().CopyStream();
-        RTERROR(cudaEventRecord(getGpu()._dataConsumedEvent, s), "LaunchError consumed event");
+        if (_bTransposePending) {
+            RTERROR(cudaEventRecord(_lossPassEvent, s), "LaunchError loss pass event");
+            RTERROR(cudaStreamWaitEvent(_sideStream, _lossPassEvent, 0), "LaunchError loss pass wait");
+            RTERROR(cudaEventRecord(getGpu()._dataConsumedEvent, _sideStream), "LaunchError consumed event");
+        } else {
+            RTERROR(cudaEventRecord(getGpu()._dataConsumedEvent, s), "LaunchError consumed event");
+        }
         getGpu()._bDataConsumedValid = true;
     }
-    RTERROR(cudaStreamWaitEvent(s, _joinEvent, 0), "LaunchError join");
+    RTERROR(cudaStreamWaitEvent(s, _regEvent, 0), "LaunchError regularisation join");
     if (getGpu()._numprocs > 1)
         getGpu().Check(dsb200_all_reduce_u64(getGpu()._ctx, acc, 2), "dsb200_all_reduce_u64");
     RTERROR(cudaMemcpyAsync(_pbErrorAccumulator->_pSysData, acc, 2 * sizeof(unsigned long long), cudaMemcpyDeviceToHost, s), "LaunchError copy");
@@ -534,9 +559,9 @@ void NNNetwork::LaunchRegularization(NNFloat lambda, NNFloat lambda1, bool fork)
                                "dsb200_regularization_error_async");
     if (fork && any) {
         getGpu().Check(dsb200_ctx_set_stream(getGpu()._ctx, s), "dsb200_ctx_set_stream");
-        RTERROR(cudaEventRecord(_joinEvent, _sideStream), "LaunchRegularization join");
+        RTERROR(cudaEventRecord(_regEvent, _sideStream), "LaunchRegularization join");
     } else {
-        RTERROR(cudaEventRecord(_joinEvent, s), "LaunchRegularization join");
+        RTERROR(cudaEventRecord(_regEvent, s), "LaunchRegularization join");
     }
 }
 
@@ -603,6 +628,37 @@ void NNNetwork::UpdateWeights(NNFloat alpha, NNFloat lambda, NNFloat lambda1, NN
         _vWeight[i]->UpdateWeights(_trainingMode, batch, alpha, lambda, lambda1, mu, mu1, (NNFloat)_batches);
 }
 
+void NNNetwork::SetStepTrace(bool on)
+{
+    if (on && !_trace.start[0])
+        for (int i = 0; i < StepTrace::kRing; i++) {
+            RTERROR(cudaEventCreate(&_trace.start[i]), "step trace event");
+            RTERROR(cudaEventCreate(&_trace.loss[i]), "step trace event");
+            RTERROR(cudaEventCreate(&_trace.end[i]), "step trace event");
+        }
+    _trace.on = on; _trace.steps = 0;
+    for (double& h : _trace.host) h = 0;
+}
+
+int NNNetwork::StepTraceReport(double* out, int cap)
+{
+    if (!out || cap < 9 || !_trace.steps) return 0;
+    RTERROR(cudaDeviceSynchronize(), "step trace sync");
+    for (int i = 0; i < 6; i++) out[i] = _trace.host[i] / (double)_trace.steps * 1e6;
+    const uint64_t n = min<uint64_t>(_trace.steps, StepTrace::kRing);
+    double fwd = 0, bwd = 0, gap = 0; uint64_t gaps = 0;
+    for (uint64_t k = 0; k < n; k++) {
+        const uint64_t step = _trace.steps - n + k;
+        const int i = (int)(step % StepTrace::kRing);
+        float ms = 0;
+        RTERROR(cudaEventElapsedTime(&ms, _trace.start[i], _trace.loss[i]), "step trace elapsed"); fwd += ms;
+        RTERROR(cudaEventElapsedTime(&ms, _trace.loss[i], _trace.end[i]), "step trace elapsed"); bwd += ms;
+        if (k + 1 < n) { RTERROR(cudaEventElapsedTime(&ms, _trace.end[i], _trace.start[(i + 1) % StepTrace::kRing]), "step trace elapsed"); gap += ms; gaps++; }
+    }
+    out[6] = fwd / (double)n * 1e3; out[7] = bwd / (double)n * 1e3; out[8] = gaps ? gap / (double)gaps * 1e3 : 0;
+    return 9;
+}
+
 // Body of the minibatch loop of NNNetwork::Train (E/NNNetwork.cpp:1601-1650) for the batch at `position`.
 float NNNetwork::TrainStep(uint32_t position, NNFloat alpha, NNFloat lambda, NNFloat lambda1, NNFloat mu, NNFloat mu1, NNFloat* pRegularization)
 {
@@ -610,6 +666,12 @@ float NNNetwork::TrainStep(uint32_t position, NNFloat alpha, NNFloat lambda, NNF
     if (_bDirty) RefreshState();
     SetPosition(position);
     ClearUpdates();
+    using clk = std::chrono::steady_clock;
+    const bool trace = _trace.on;
+    const int ti = (int)(_trace.steps % StepTrace::kRing);
+    clk::time_point t0, t1;
+    auto lap = [&](int slot) { if (trace) { t1 = clk::now(); _trace.host[slot] += std::chrono::duration<double>(t1 - t0).count(); t0 = t1; } };
+    if (trace) { RTERROR(cudaEventRecord(_trace.start[ti], getGpu().GetStream()), "step trace"); t0 = clk::now(); }
     for (auto d : _vData) d->WaitForUpload(getGpu().GetStream());      // a batch streamed in on the copy stream since the last step
     getGpu()._bDataConsumedValid = false;                            // until this step's readers are on their way (LaunchError)
     _bStepReadsRecorded = _bFusion;                                  // only the fused step waits for the side stream before the loss pass
@@ -618,11 +680,17 @@ float NNNetwork::TrainStep(uint32_t position, NNFloat alpha, NNFloat lambda, NNF
         LaunchBatchPreparation(lambda, lambda1);
         _bRegularizationLaunched = true;
     }
+    lap(0);
     PredictTrainingBatch();
     _bBatchPrepared = false;
+    lap(1);
     LaunchError(lambda, lambda1);                    // loss (+ output delta) kernels, join, and the async read-back
+    if (trace) RTERROR(cudaEventRecord(_trace.loss[ti], getGpu().GetStream()), "step trace");
+    lap(2);
     BackPropagate();                                 // queued behind them; does not depend on the host seeing the loss
+    lap(3);
     RTERROR(cudaEventSynchronize(_errorEvent), "TrainStep event sync");
+    lap(4);
     const NNFloat error_training = (NNFloat)((double)(long long)_pbErrorAccumulator->_pSysData[0] * (1.0 / 1073741824.0));
     const NNFloat error_regularization = (NNFloat)((double)(long long)_pbErrorAccumulator->_pSysData[1] * (1.0 / 1073741824.0));
     if (pRegularization) *pRegularization = error_regularization;
@@ -637,10 +705,12 @@ float NNNetwork::TrainStep(uint32_t position, NNFloat alpha, NNFloat lambda, NNF
         }
     } else _initSteps--;
     if (_brakeSteps > 0) { step_alpha *= (NNFloat)0.1; _brakeSteps--; }
+    WaitForTransposed();                             // the sparse weight gradient inside the update is its first (and only) reader
     if (_brakeSteps < 24) {
         _batches++;                                  // before the update: Adam reads it (E/NNNetwork.cpp:1646-1649)
         UpdateWeights(step_alpha, lambda, lambda1, mu, mu1);
     }
+    if (trace) { RTERROR(cudaEventRecord(_trace.end[ti], getGpu().GetStream()), "step trace"); lap(5); _trace.steps++; }
     return error_training;
 }
 

@@ -66,8 +66,17 @@ private:
     unique_ptr<GpuBuffer<NNFloat>> _pbP2PBuffer;          // full-width exchange buffer ("P2P send buffer")
     unique_ptr<GpuBuffer<unsigned long long>> _pbErrorAccumulator;   // device fixed-point loss + pinned shadow
     cudaEvent_t             _errorEvent;
+    // engine option "step_trace" (diagnostics): where a TrainStep spends host and device time (dsb200_engine_step_trace)
+    struct StepTrace {
+        static const int kRing = 64;
+        bool on = false;
+        cudaEvent_t start[kRing] = {}, loss[kRing] = {}, end[kRing] = {};
+        uint64_t steps = 0;
+        double host[6] = {0, 0, 0, 0, 0, 0};           // seconds: preparation launches, forward launches, loss launches, backward launches, wait for the loss, update launches
+    } _trace;
     cudaStream_t            _sideStream;                  // regularisation error runs here, beside the forward pass
-    cudaEvent_t             _forkEvent, _joinEvent, _prepEvent;
+    cudaEvent_t             _forkEvent, _joinEvent, _prepEvent, _regEvent = NULL, _lossPassEvent = NULL;
+    bool                    _bTransposePending = false;   // the side stream is still building this step's transposed matrix (_joinEvent): WaitForTransposed()
     cudaEvent_t             _updateEvent = NULL;          // end of the weight updates that ran on the side stream (UpdateWeights)
     size_t                  _validateMaxSamples = 256;    // Validate(): elements checked per weight matrix / bias vector
     bool                    _bStepReadsRecorded = false;   // TrainStep: LaunchError records GpuContext::_dataConsumedEvent for the streaming loader
@@ -91,6 +100,9 @@ public:
     float Train(uint32_t epochs = 1, NNFloat alpha = (NNFloat)0.1, NNFloat lambda = (NNFloat)0.001, NNFloat lambda1 = (NNFloat)0.0,
                 NNFloat mu = (NNFloat)0.1, NNFloat mu1 = 0.0);
     // one minibatch of Train's loop body at `position` (B200 addition: lets a caller time / drive single steps)
+    void WaitForTransposed();                             // main stream waits for the side stream's transposed matrix, once per step, at its first consumer
+    void SetStepTrace(bool on);
+    int StepTraceReport(double* out, int cap);            // 6 host means (us) + 3 device means (us): start->loss, loss->end, end->next start
     float TrainStep(uint32_t position, NNFloat alpha, NNFloat lambda, NNFloat lambda1, NNFloat mu, NNFloat mu1, NNFloat* pRegularization = NULL);
     void PredictBatch(uint32_t layers = 0);
     void CalculateTopK(const string& layer, uint32_t k, GpuBuffer<NNFloat>* pbKey, GpuBuffer<uint32_t>* pbValue);

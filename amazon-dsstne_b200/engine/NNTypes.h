@@ -254,7 +254,7 @@ private:
     } _staging[2];
     int _stagingCur = 0;
     cudaEvent_t _uploadEvent = nullptr;                       // recorded on the copy stream: readers of this step wait for it (WaitForUpload)
-    // experimental single-copy path (engine option "pinned_mirror"): the host mirror itself is page-locked and is the copy source
+    // single-copy path (engine option "pinned_mirror", default on): the host mirror itself is page-locked and is the copy source
     struct Mirror {
         void* ptr[4] = {nullptr, nullptr, nullptr, nullptr};      // registered storage of _vSparseStart / End / Index / Data
         cudaEvent_t done = nullptr; bool pending = false; bool unavailable = false;

@@ -72,6 +72,7 @@ int dsb200_engine_set_option(const char* name, int value)
     DSB_ENGINE_TRY
     if (name && !strcmp(name, "pinned_mirror")) { getGpu()._bPinnedMirror = value != 0; return 0; }      // engine-level option
     if (name && !strcmp(name, "fuse_output_gemm")) { getGpu()._bFuseOutputGemm = value != 0; return 0; }
+    if (name && !strcmp(name, "step_trace")) { if (!getGpu()._pNetwork) throw DsbEngineError("step_trace: no network"); getGpu()._pNetwork->SetStepTrace(value != 0); return 0; }
     if (name && !strcmp(name, "p2p_exchange")) { getGpu()._bP2PExchange = value != 0; if (getGpu()._pNetwork) getGpu()._pNetwork->MarkDirty(); return 0; }
     getGpu().Check(dsb200_ctx_set_option(getGpu()._ctx, name, value), "dsb200_ctx_set_option");
     DSB_ENGINE_CATCH
@@ -82,6 +83,11 @@ int dsb200_engine_profile_report(char* buf, size_t cap)
     DSB_ENGINE_TRY
     getGpu().Check(dsb200_profile_report(getGpu()._ctx, buf, cap), "dsb200_profile_report");
     DSB_ENGINE_CATCH
+}
+
+int dsb200_engine_step_trace(double* out, int cap)
+{
+    try { return getGpu()._pNetwork ? getGpu()._pNetwork->StepTraceReport(out, cap) : 0; } catch (...) { return -1; }
 }
 
 int dsb200_engine_rank(void) { return getGpu()._id; }

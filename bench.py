@@ -425,8 +425,7 @@ def run_e2e(args, wl, data, engine, dsstne_b200, stream, world=1):
     net.set_training_mode(dsstne_b200.SGD)
     net.set_gemm_mode(args.gemm_mode)
     h2d = d2h = 0
-    if args.pinned_mirror:
-        engine.set_option("pinned_mirror", 1)
+    engine.set_option("pinned_mirror", 1 if args.pinned_mirror else 0)
 
     def step(i):
         nonlocal h2d, d2h
@@ -515,7 +514,7 @@ def main():
     ap.add_argument("--side", type=int, default=1, help="1 (default) = after the headline workload also time BASELINE config 4 (1M-item layers) and config 5 (top-K) and add them as \"c4\" / \"c5\" records")
     ap.add_argument("--c4-steps", type=int, default=6)
     ap.add_argument("--fuse-output", type=int, default=1, help="1 (default) = output layer forward GEMM fused with loss + delta (engine option fuse_output_gemm); 0 = two calls")
-    ap.add_argument("--pinned-mirror", type=int, default=0, help="e2e path: 1 = LoadSparseData uploads from the page-locked host mirror (experimental single-copy path)")
+    ap.add_argument("--pinned-mirror", type=int, default=1, help="e2e path: 1 (default, the engine's default) = LoadSparseData uploads from the page-locked host mirror, one host copy per batch; 0 = two-copy staging path")
     ap.add_argument("--pdl", type=int, default=1, help="1 (default) = programmatic dependent launch of the main-stream kernels (context option pdl)")
     ap.add_argument("--p2p", type=int, default=1, help="N > 1: 1 (default) = exchange steps as one kernel over peer memory each (csrc/comm.cu); 0 = NCCL")
     args = ap.parse_args()

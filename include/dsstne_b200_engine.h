@@ -35,6 +35,11 @@ int dsb200_engine_set_stream(void* cudaStream);
 int dsb200_engine_sync(void);
 int dsb200_engine_set_option(const char* name, int value);      /* forwards to dsb200_ctx_set_option */
 int dsb200_engine_profile_report(char* buf, size_t cap);        /* forwards to dsb200_profile_report */
+/* diagnostics, engine option "step_trace" = 1 (set after the network exists): means over the traced NNNetwork::TrainStep calls, in
+ * microseconds -- out[0..5] host time of: side-stream preparation launches, forward launches, loss-pass launches, backward launches,
+ * the wait for the loss, update launches; out[6..8] device time between: start of the step and the loss, the loss and the end of
+ * the updates, the end of a step and the start of the next (the device waiting for the host).  Returns the number of values.      */
+int dsb200_engine_step_trace(double* out, int cap);
 int dsb200_engine_rank(void);
 int dsb200_engine_nranks(void);
 

@@ -304,7 +304,7 @@ def test_dropout_training_matches_oracle(eng, orc):
     net.close()
 
 
-# engine option "pinned_mirror" (single host copy per streamed batch) was written after round 1's GPU budget was spent
+# engine option "pinned_mirror" (single host copy per streamed batch, the default) and the two-copy staging path behind it
 STREAM_PATHS = [0, 1]
 
 
@@ -347,7 +347,7 @@ def test_streamed_batches_through_load_sparse_match_oracle(eng, orc, pinned_mirr
             want, _ = onet.train_step(oc, oc, b * batch, batch, 0.025, 1e-4, 0.0, 0.5, 0.0)
             assert abs(got - want) <= TOL * abs(want), f"step {step}"
     finally:
-        eng.set_option("pinned_mirror", 0)
+        eng.set_option("pinned_mirror", 1)
     for i in range(2):
         W, bb = net.get_weights(names[i], names[i + 1])
         assert rel_err(W.reshape(onet.W(i).shape), onet.W(i)) < TOL

@@ -282,3 +282,33 @@ def test_topk_kv_merge_of_rank_lists(ctx, orc, dsb, P, K):
     ctx.sync()
     np.testing.assert_array_equal(host(ok), ref_k)
     np.testing.assert_array_equal(u32(ov), ref_v)
+
+
+# ------------------------------------------------------------------ capacity table of a streamed batch, built on the device
+@pytest.mark.parametrize("width", [1, 100, 8192, 8193, 27278, 100003])
+@pytest.mark.parametrize("misaligned", [False, True])
+def test_transposed_capacity_table_on_the_device(ctx, orc, dsb, width, misaligned):
+    """dsb200_transposed_capacity (the streaming caller's replacement of the host pass of E/NNTypes.cpp:1631-1735): tStart = exclusive
+    prefix of the per-column counts rounded up to 32, total = the capacity; widths on both sides of the 8,192-column tile of the scan,
+    tables at 16-byte and at 4-byte alignment; equal to the oracle's table when the dataset is one batch"""
+    import torch
+    from dsstne_b200 import datagen
+    rows = 300
+    h = datagen.make_csr(rows, width, min(20.5, width * 0.6), dist="binomial", col="zipf" if width > 1000 else "uniform")
+    counts = np.bincount(h.index[int(h.start[0]):int(h.end[rows - 1])], minlength=width).astype(np.uint64)
+    aligned = (counts + 31) // 32 * 32
+    want = np.concatenate([[0], np.cumsum(aligned)[:-1]]).astype(np.uint32)
+    off = 1 if misaligned else 0
+    d_count = torch.full((width + 8,), 0x7fffffff, dtype=torch.int32, device="cuda")
+    d_start = torch.full((width + 8,), -1, dtype=torch.int32, device="cuda")
+    d_total = torch.zeros(1, dtype=torch.int32, device="cuda")
+    ctx.transposed_capacity(to_device(dsb, h), rows, width, d_count[off:], d_start[off:], d_total)
+    ctx.sync()
+    got = d_start.cpu().numpy().view(np.uint32)
+    np.testing.assert_array_equal(got[off:off + width], want)
+    assert (got[:off] == 0xffffffff).all() and (got[off + width:] == 0xffffffff).all()        # nothing written outside the table
+    np.testing.assert_array_equal(d_count.cpu().numpy().view(np.uint32)[off:off + width], counts.astype(np.uint32))
+    assert int(d_total.item()) == int(aligned.sum())
+    tstart, cap = orc.transposed_capacity(to_oracle(orc, h), width, rows)
+    np.testing.assert_array_equal(tstart, want)
+    assert cap == int(aligned.sum())
