@@ -42,14 +42,16 @@ struct Reader {
     FILE* f;
     std::string fname;
     uint64_t base = 0;
+    uint64_t fileSize = 0;                             // nothing is allocated for a block that cannot be inside the file
     int so = 8, sl = 8;                                // size of offsets / lengths
 
     [[noreturn]] void fail(const std::string& what) const { throw Error("netCDF-4 / HDF5: " + fname + ": " + what); }
 
     std::vector<uint8_t> get(uint64_t off, uint64_t n) const
     {
+        if (n > (1ull << 31) || off > fileSize || base + off > fileSize || n > fileSize - (base + off))
+            fail("truncated file (metadata block of " + std::to_string(n) + " bytes at offset " + std::to_string(off) + ")");
         std::vector<uint8_t> b(n);
-        if (n > (1ull << 31)) fail("implausible metadata block size");
         if (fseeko(f, (off_t)(base + off), SEEK_SET) != 0) fail("seek failed");
         if (n && fread(b.data(), 1, n, f) != n) fail("truncated file (metadata at offset " + std::to_string(off) + ")");
         return b;
@@ -391,6 +393,7 @@ void attributes(const Reader& r, const std::vector<Msg>& msgs, std::vector<Att>&
 void parse(FILE* f, const std::string& fname, std::vector<Dim>& dims, std::vector<Att>& atts, std::vector<Var>& vars)
 {
     Reader r; r.f = f; r.fname = fname;
+    if (fseeko(f, 0, SEEK_END) == 0) r.fileSize = (uint64_t)ftello(f);
     // ---- superblock: at 0, 512, 1024, ...
     uint64_t sb = UNDEF;
     for (uint64_t off = 0; off < (1ull << 24); off = off ? off * 2 : 512) {
@@ -564,6 +567,13 @@ void read_chunked(FILE* f, const std::string& fname, const Var& v, std::vector<u
     uint64_t total = eb, chunkBytes = eb;
     for (size_t d = 0; d < rank; d++) { total *= v.shape[d]; chunkBytes *= v.chunkShape[d]; }
     if (chunkBytes > (1ull << 32)) fail("chunks of more than 4 GiB");
+    uint64_t fileSize = 0;
+    if (fseeko(f, 0, SEEK_END) == 0) fileSize = (uint64_t)ftello(f);
+    for (const Var::Chunk& c : v.chunks)
+        if (c.addr > fileSize || c.bytes > fileSize - c.addr) fail("truncated chunk at offset " + std::to_string(c.addr));
+    if (v.chunks.empty() && total > (1ull << 36)) fail("an unwritten variable of " + std::to_string(total) + " bytes");
+    if (total / std::max<uint64_t>(chunkBytes, 1) > 64 * (uint64_t)v.chunks.size() + 1024 && total > (1ull << 30))
+        fail("implausible shape: " + std::to_string(total) + " bytes over " + std::to_string(v.chunks.size()) + " chunks");
     out.resize(total);
     if (v.fill.size() == eb) for (uint64_t i = 0; i < total; i += eb) memcpy(&out[i], v.fill.data(), eb);
     else std::fill(out.begin(), out.end(), (uint8_t)0);

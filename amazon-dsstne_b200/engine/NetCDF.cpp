@@ -226,6 +226,10 @@ void File::read_raw(const Var& v, std::vector<uint8_t>& bytes) const
         if (bytes.size() != n) throw Error("netCDF: variable " + v.name + " has " + std::to_string(bytes.size()) + " bytes of chunks for " + std::to_string(n) + " in " + _fname);
         return;
     }
+    if (fseeko(f, 0, SEEK_END) == 0) {
+        const uint64_t size = (uint64_t)ftello(f);
+        if (v.begin > size || n > size - v.begin) throw Error("netCDF: variable " + v.name + " is truncated in " + _fname);
+    }
     bytes.resize(n);
 #if defined(_WIN32)
     if (_fseeki64(f, (long long)v.begin, SEEK_SET) != 0)

@@ -321,3 +321,57 @@ def test_unreadable_containers_are_rejected_loudly(dsb, tmp_path):
     p3.write_bytes(b"CDF\x05\x00\x00")
     rc, _ = describe(lib, str(p3))
     assert rc != 0 and b"truncated" in lib.dsb200_engine_last_error()
+
+
+_FUZZ = r"""
+import ctypes as C, os, sys
+import numpy as np
+sys.path.insert(0, sys.argv[1])
+import dsstne_b200
+lib = dsstne_b200.lib()
+blob = open(sys.argv[2], "rb").read()
+tmp = sys.argv[3]
+rng = np.random.default_rng(3)
+buf = C.create_string_buffer(1 << 16)
+out = np.zeros(4096, dtype=np.float64)
+cases = [blob[:n] for n in range(0, len(blob), 5)]
+for i in range(400):
+    b = bytearray(blob)
+    for _ in range(1 + i % 3):
+        b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 256))
+    cases.append(bytes(b))
+bad = 0
+for b in cases:
+    open(tmp, "wb").write(b)
+    bad += lib.dsb200_netcdf_describe(tmp.encode(), buf, C.c_size_t(len(buf))) != 0
+    for name in (b"sparseStart0", b"sparseIndex0", b"sparseData0", b"v"):
+        n = C.c_uint64()
+        lib.dsb200_netcdf_read_var(tmp.encode(), name, out.ctypes.data_as(C.c_void_p), C.c_uint64(out.size), C.byref(n))
+print("survived", len(cases), "rejected", bad)
+"""
+
+
+@pytest.mark.parametrize("which", ["old", "new", "chunked"])
+def test_damaged_netcdf4_containers_never_crash_the_reader(dsb, tmp_path, which):
+    """every prefix (step 5) of a container and 400 copies with one to three bytes overwritten: the reader either reads the file or
+    returns an error -- no crash, no hang, no unbounded allocation (run in a child process so that a crash fails only this test)"""
+    import subprocess
+    import sys
+    here = os.path.dirname(os.path.abspath(__file__))
+    if which == "chunked":
+        m = _fixture_module()
+        src, path = str(tmp_path / "c.nc"), str(tmp_path / "c4.nc")
+        with netcdf_file(src, "w", version=2) as f:
+            f.createDimension("n", 700)
+            f.createVariable("v", "f", ("n",))[:] = np.arange(700, dtype=np.float32)
+            f.createVariable("sparseIndex0", "i", ("n",))[:] = np.arange(700, dtype=np.int32)
+        m.convert(src, path, "old", storage=lambda i, nm, a: dict(how="chunked", chunk=3 if nm == "v" else 64, filters=("shuffle", "deflate", "fletcher32")))
+    else:
+        path = os.path.join(here, "golden", f"dataset_nc4_{which}.nc")
+    script = tmp_path / "fuzz.py"
+    script.write_text(_FUZZ)
+    r = subprocess.run([sys.executable, str(script), os.path.dirname(here), path, str(tmp_path / "damaged.nc")],
+                       capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "survived" in r.stdout, (r.returncode, r.stdout[-300:], r.stderr[-600:])
+    rejected = int(r.stdout.split()[-1])
+    assert rejected > 100                                                     # the truncated ones at the very least
