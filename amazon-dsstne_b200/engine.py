@@ -194,6 +194,14 @@ class Network:
     def set_position(self, pos):
         _check(lib().dsb200_network_set_position(self.h, C.c_uint32(pos)))
 
+    def get_shuffle_indices(self):
+        n = C.c_uint32()
+        _check(lib().dsb200_network_get_shuffle_indices(self.h, None, C.c_uint32(0), C.byref(n)))
+        out = np.zeros(n.value, dtype=np.uint32)
+        if n.value:
+            _check(lib().dsb200_network_get_shuffle_indices(self.h, _p(out), C.c_uint32(out.size), C.byref(n)))
+        return out
+
     def train(self, epochs, alpha, lam=0.0, lam1=0.0, mu=0.0, mu1=0.0):
         e = C.c_float()
         _check(lib().dsb200_network_train(self.h, C.c_uint32(epochs), C.c_float(alpha), C.c_float(lam), C.c_float(lam1),

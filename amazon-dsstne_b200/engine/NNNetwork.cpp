@@ -384,12 +384,14 @@ static inline uint64_t mix64(uint64_t z)
     return z ^ (z >> 31);
 }
 
-// E/NNNetwork.cpp:826-907 shuffles with cuRAND keys + CUB sort on rank 0 and broadcasts the result; the
-// permutation is "parity unpinned" (SURVEY 8c).  Here: Fisher-Yates on the host from the counter-based
-// generator, identical on every rank; examples beyond the last full batch stay in place as in the reference.
+// E/NNNetwork.cpp:874-907 restarts from the identity every epoch, sorts all `_examples` indices by cuRAND keys on rank 0 and
+// broadcasts the result; the permutation itself is "parity unpinned" (it is whatever cuRAND's stream gives).  Here:
+// the same restart from the identity, then Fisher-Yates over all indices on the host from the counter-based generator keyed by
+// (seed, epoch) -- identical on every rank without a broadcast, and a function of the epoch number alone.
 void NNNetwork::ShuffleIndices()
 {
     RefreshShuffleBuffers();
+    for (uint32_t i = 0; i < _examples; i++) _vShuffleIndex[i] = i;
     const uint64_t key = mix64((uint64_t)getGpu()._seed ^ mix64(0x5f3759dfull + _shuffleEpoch++));
     for (uint32_t i = _examples; i > 1; i--) {
         const uint32_t j = (uint32_t)(mix64(key + (uint64_t)i * 0x9e3779b97f4a7c15ull) % i);
@@ -421,7 +423,7 @@ void NNNetwork::LoadBatch()
 void NNNetwork::PredictBatch(uint32_t layers)
 {
     if (layers > _vLayer.size()) return;
-    if (_mode != Prediction) { _mode = Prediction; _bDirty = true; }
+    if (_mode != Prediction || getGpu()._pNetwork != this) { _mode = Prediction; _bDirty = true; }      // (another network may have been published since)
     if (_bDirty) RefreshState();
     uint32_t batch = _batch;
     if (_position + batch > _examples) batch = _examples - _position;
@@ -662,7 +664,7 @@ int NNNetwork::StepTraceReport(double* out, int cap)
 // Body of the minibatch loop of NNNetwork::Train (E/NNNetwork.cpp:1601-1650) for the batch at `position`.
 float NNNetwork::TrainStep(uint32_t position, NNFloat alpha, NNFloat lambda, NNFloat lambda1, NNFloat mu, NNFloat mu1, NNFloat* pRegularization)
 {
-    if (_mode != Training) { _mode = Training; _bDirty = true; }
+    if (_mode != Training || getGpu()._pNetwork != this) { _mode = Training; _bDirty = true; }      // (another network may have been published since)
     if (_bDirty) RefreshState();
     SetPosition(position);
     ClearUpdates();
@@ -716,7 +718,7 @@ float NNNetwork::TrainStep(uint32_t position, NNFloat alpha, NNFloat lambda, NNF
 
 float NNNetwork::Train(uint32_t epochs, NNFloat alpha, NNFloat lambda, NNFloat lambda1, NNFloat mu, NNFloat mu1)
 {
-    if (_mode != Training) { _mode = Training; _bDirty = true; }
+    if (_mode != Training || getGpu()._pNetwork != this) { _mode = Training; _bDirty = true; }      // (another network may have been published since)
     if (_bDirty) RefreshState();
     if (_trainingMode != SGD && _bClearVelocity) {
         for (auto w : _vWeight) w->ClearVelocity();
@@ -781,7 +783,7 @@ bool NNNetwork::Validate()
     const TrainingMode trainingMode = _trainingMode;
     _bFusion = false;
     SetTrainingMode(SGD);
-    if (_mode != Validation) { _mode = Validation; _bDirty = true; }
+    if (_mode != Validation || getGpu()._pNetwork != this) { _mode = Validation; _bDirty = true; }      // (another network may have been published since)
     if (_bDirty) RefreshState();
     cout << "Validating network weights and biases with epsilon error threshold of " << epsilon << endl;
     uint32_t batch = _batch;

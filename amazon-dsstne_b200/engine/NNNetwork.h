@@ -100,6 +100,7 @@ public:
     float Train(uint32_t epochs = 1, NNFloat alpha = (NNFloat)0.1, NNFloat lambda = (NNFloat)0.001, NNFloat lambda1 = (NNFloat)0.0,
                 NNFloat mu = (NNFloat)0.1, NNFloat mu1 = 0.0);
     // one minibatch of Train's loop body at `position` (B200 addition: lets a caller time / drive single steps)
+    const std::vector<uint32_t>& ShuffleIndexVector() const { return _vShuffleIndex; }
     void WaitForTransposed();                             // main stream waits for the side stream's transposed matrix, once per step, at its first consumer
     void SetStepTrace(bool on);
     int StepTraceReport(double* out, int cap);            // 6 host means (us) + 3 device means (us): start->loss, loss->end, end->next start

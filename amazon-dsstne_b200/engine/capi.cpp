@@ -295,6 +295,14 @@ int dsb200_network_set_training_mode(dsb200_network* n, int mode) { DSB_ENGINE_T
 int dsb200_network_set_batch(dsb200_network* n, uint32_t batch) { DSB_ENGINE_TRY NET(n)->SetBatch(batch); DSB_ENGINE_CATCH }
 int dsb200_network_set_position(dsb200_network* n, uint32_t position) { DSB_ENGINE_TRY NET(n)->SetPosition(position); DSB_ENGINE_CATCH }
 int dsb200_network_set_shuffle_indices(dsb200_network* n, int flag) { DSB_ENGINE_TRY NET(n)->SetShuffleIndices(flag != 0); DSB_ENGINE_CATCH }
+int dsb200_network_get_shuffle_indices(dsb200_network* n, uint32_t* out, uint32_t cap, uint32_t* pCount)
+{
+    DSB_ENGINE_TRY
+    const std::vector<uint32_t>& v = NET(n)->ShuffleIndexVector();
+    if (pCount) *pCount = (uint32_t)v.size();
+    if (out) for (size_t i = 0; i < v.size() && i < cap; i++) out[i] = v[i];
+    DSB_ENGINE_CATCH
+}
 int dsb200_network_set_decay(dsb200_network* n, float decay) { DSB_ENGINE_TRY NET(n)->SetDecay(decay); DSB_ENGINE_CATCH }
 int dsb200_network_set_fusion(dsb200_network* n, int flag) { DSB_ENGINE_TRY NET(n)->SetFusion(flag != 0); DSB_ENGINE_CATCH }
 int dsb200_network_set_gemm_mode(dsb200_network* n, int gemmMode)

@@ -88,6 +88,9 @@ int dsb200_network_set_training_mode(dsb200_network* n, int trainingMode);
 int dsb200_network_set_batch(dsb200_network* n, uint32_t batch);
 int dsb200_network_set_position(dsb200_network* n, uint32_t position);
 int dsb200_network_set_shuffle_indices(dsb200_network* n, int flag);
+/* the permutation the last NNNetwork::ShuffleIndices() (E/NNNetwork.cpp:826-907) left: position p of an epoch reads example out[p];
+ * *pCount = its length (0 before the first shuffled epoch); copies min(cap, *pCount) entries                                  */
+int dsb200_network_get_shuffle_indices(dsb200_network* n, uint32_t* out, uint32_t cap, uint32_t* pCount);
 int dsb200_network_set_decay(dsb200_network* n, float decay);
 int dsb200_network_set_fusion(dsb200_network* n, int flag);          /* B200 fusions on (default) / off */
 int dsb200_network_set_gemm_mode(dsb200_network* n, int gemmMode);   /* DSB200_GEMM_* */

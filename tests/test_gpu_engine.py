@@ -355,6 +355,61 @@ def test_streamed_batches_through_load_sparse_match_oracle(eng, orc, pinned_mirr
     net.close()
 
 
+def test_epoch_shuffle_is_a_permutation_and_trains_like_the_permuted_dataset(eng, dsb):
+    """NNNetwork::ShuffleIndices (E/NNNetwork.cpp:874-907; the permutation itself is unpinned -- cuRAND in the reference, the counter
+    based generator here): every epoch draws a fresh permutation of all examples from the identity, a function of (seed, epoch);
+    an epoch with shuffling on gives the losses and weights of an epoch without shuffling over the data set laid out in that order"""
+    from dsstne_b200 import datagen
+    batch, examples, sizes = 64, 4 * 64, [2048, 64, 2048]
+    h = tiny(examples=examples, width=2048)
+    Ws, bs = datagen.make_weights(sizes, scale=0.05)
+    names = ["Input", "Hidden1", "Output"]
+
+    def network(data, shuffle, W, b):
+        ds = [eng.Dataset.from_host_csr("gl_input", data), eng.Dataset.from_host_csr("gl_output", data)]
+        net = eng.Network(eng.autoencoder_json([64], shuffle=shuffle), batch, ds)
+        net.set_training_mode(dsb.SGD)
+        for i in range(2):
+            net.set_weights(names[i], names[i + 1], W[i], b[i])
+        return net
+
+    def weights(net):
+        out = [net.get_weights(names[i], names[i + 1]) for i in range(2)]
+        return [w for w, _ in out], [b for _, b in out]
+
+    def permuted(perm):
+        lens = (h.end - h.start).astype(np.uint64)[perm]
+        end = np.cumsum(lens).astype(np.uint64)
+        index = np.concatenate([h.index[int(h.start[i]):int(h.end[i])] for i in perm]).astype(np.uint32)
+        return datagen.HostCsr(end - lens, end, index, h.width)
+
+    a = network(h, True, Ws, bs)                                     # (one network at a time: the engine publishes ONE to the kernels)
+    epochs = []
+    for epoch in range(2):
+        err = a.train(1, 0.025, 1e-4, 0.0, 0.0, 0.0)
+        perm = a.get_shuffle_indices()
+        assert perm.size == examples and np.array_equal(np.sort(perm), np.arange(examples, dtype=np.uint32))
+        assert not np.array_equal(perm, np.arange(examples, dtype=np.uint32))
+        epochs.append((err, perm, weights(a)))
+    a.close()
+    assert not np.array_equal(epochs[0][1], epochs[1][1])
+    state = (Ws, bs)
+    for epoch, (err_a, perm, after) in enumerate(epochs):
+        b = network(permuted(perm), False, *state)                  # same start of the epoch, rows physically in the shuffled order
+        err_b = b.train(1, 0.025, 1e-4, 0.0, 0.0, 0.0)
+        Wb, bb = weights(b)
+        b.close()
+        assert abs(err_a - err_b) <= 1e-5 * abs(err_b), f"epoch {epoch}: {err_a} vs {err_b}"
+        for i in range(2):
+            assert rel_err(after[0][i], Wb[i]) < 1e-5 and rel_err(after[1][i], bb[i]) < 1e-5, f"epoch {epoch}, weight {i}"
+        state = after
+    c = network(h, True, Ws, bs)                                     # a new network draws the same sequence of permutations
+    c.train(1, 0.025, 1e-4, 0.0, 0.0, 0.0)
+    first = c.get_shuffle_indices()
+    c.close()
+    assert np.array_equal(first, epochs[0][1])
+
+
 def test_predict_and_topk_with_filter(eng, orc):
     sizes, batch = [2048, 128, 2048], 256
     h = tiny(examples=256, width=2048)
